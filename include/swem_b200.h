@@ -1,0 +1,131 @@
+/*
+ * swem_b200.h -- C ABI of the B200-native SWEM memory hot path (libswem_b200.so).
+ *
+ * The reference (lmm077/SWEM) is pure Python/PyTorch and has no FFI; the boundary it offers for
+ * this path is the Python class methods/SWEM/modules.py::SWEMCore.  Each entry point below
+ * replaces the body of one of its methods and is what a ctypes/pybind stub inside that class
+ * binds:
+ *
+ *   swem_em_forward       <- SWEMCore.swem            methods/SWEM/modules.py:129-168
+ *                            (= swe_step :112-120, swm_step :122-127, sww_step :93-110, nu :164-165)
+ *   swem_readout_forward  <- SWEMCore.get_affinity    methods/SWEM/modules.py:232-276
+ *                            + perm_inv_feat :198-208 + the l2norms of matching :282-283
+ *                            + the concat placement of matching :291
+ *   swem_em_masks         <- mask prep of SWEM.memorize  methods/SWEM/swem.py:80-84
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to contiguous fp32 (row-major, last index fastest) unless
+ *     stated; the caller (PyTorch) owns all memory, the library never allocates device memory;
+ *   - `stream` is a cudaStream_t passed as void*; calls are asynchronous on it and never
+ *     synchronise the device;
+ *   - return value 0 = ok, non-zero = SwemStatus; swem_last_error() gives a thread-local message;
+ *   - unsupported shapes fail loudly (SWEM_ERR_UNSUPPORTED); there is no CPU fallback.
+ *
+ * Index names: b batch, n object, s side (0 = background, 1 = foreground), c key channel (Ck),
+ * d value channel (Cv), p pixel (HW = H/16 * W/16), l basis (L per side per bank).
+ */
+#ifndef SWEM_B200_H_
+#define SWEM_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SWEM_B200_ABI_VERSION 1
+
+typedef enum SwemStatus {
+  SWEM_OK = 0,
+  SWEM_ERR_INVALID_ARG = 1,   /* null pointer, non-positive dim, tau <= 0 ...            */
+  SWEM_ERR_UNSUPPORTED = 2,   /* shape outside what the kernels implement                */
+  SWEM_ERR_WORKSPACE = 3,     /* workspace missing or smaller than swem_*_workspace_bytes */
+  SWEM_ERR_CUDA = 4,          /* a CUDA runtime call or launch failed                    */
+  SWEM_ERR_DEVICE = 5         /* not running on an sm_100 device                         */
+} SwemStatus;
+
+/* Which kernel family runs.  AUTO picks the fused tcgen05 kernels when the shape is one they
+ * cover and the generic tiled kernels otherwise; the other two values force one family (the
+ * tests use them to check both against the oracle). */
+typedef enum SwemPath {
+  SWEM_PATH_AUTO = 0,
+  SWEM_PATH_GENERIC = 1,
+  SWEM_PATH_FUSED = 2
+} SwemPath;
+
+typedef struct SwemDims {
+  int32_t B;        /* batch                                   */
+  int32_t N;        /* objects                                 */
+  int32_t Ck;       /* key channels                            */
+  int32_t Cv;       /* value channels                          */
+  int32_t HW;       /* pixels at stride 16                     */
+  int32_t L;        /* bases per side per bank (n_bases)       */
+  int32_t n_iters;  /* EM iterations (memorize only)           */
+  int32_t n_banks;  /* 1 or 2 banks read (readout only)        */
+  int32_t topl;     /* ranks of the permutation-invariant feature (readout only) */
+  float   tau;      /* softmax temperature                     */
+} SwemDims;
+
+/* ---- sequential weighted EM update: reference SWEMCore.swem, modules.py:129-168 ------------- */
+typedef struct SwemEmArgs {
+  SwemDims dims;
+  const float* x;            /* [B, Ck, HW]        raw key features (NOT normalised, :116)       */
+  const float* v;            /* [B, N, Cv, HW]     value features                                 */
+  const float* masks;        /* [B, N, 2, HW]      [bg, fg] pixel weights                         */
+  const float* kappa_prior;  /* [B, N, 2, Ck, L]   prior key bases (random_init rows for new objects, :136-146) */
+  const float* nu_prior;     /* [B, N, 2, Cv, L]                                                  */
+  const float* zita_prior;   /* [B, N, 2, L]                                                      */
+  float* kappa;              /* out [B, N, 2, Ck, L]                                              */
+  float* nu;                 /* out [B, N, 2, Cv, L]                                              */
+  float* zita;               /* out [B, N, 2, L]                                                  */
+  float* z_last;             /* optional out [B, N, 2, HW, L]: responsibilities of the last E-step (NULL = skip) */
+  void*  workspace;          /* >= swem_em_workspace_bytes(&dims, path) bytes, 256-byte aligned  */
+  size_t workspace_bytes;
+  int32_t path;              /* SwemPath                                                          */
+} SwemEmArgs;
+
+size_t swem_em_workspace_bytes(const SwemDims* dims, int32_t path);
+int    swem_em_forward(const SwemEmArgs* args, void* stream);
+
+/* ---- readout: reference SWEMCore.matching -> get_affinity -> perm_inv_feat, modules.py:198-293 */
+typedef struct SwemReadArgs {
+  SwemDims dims;
+  const float* qk;           /* [B, Ck, HW]  raw query key (the l2norm of :282 is fused)          */
+  const float* kappa[2];     /* per bank [B, N, 2, Ck, L], order [first, update] (:295-306); raw, the l2norm of :283 is fused */
+  const float* nu[2];        /* per bank [B, N, 2, Cv, L]                                         */
+  float* out;                /* [B*N, out_channels, HW] caller-allocated concat buffer (:291)     */
+  int32_t out_channels;      /* channel count of `out` (reference: 2*Cv + 2*topl)                 */
+  int32_t mem_channel;       /* first channel of mem_out (Cv channels; reference: 0)              */
+  int32_t s_channel;         /* first channel of S (2*topl channels; reference: 2*Cv)             */
+  void*  workspace;          /* >= swem_readout_workspace_bytes(&dims, path)                      */
+  size_t workspace_bytes;
+  int32_t path;              /* SwemPath                                                          */
+} SwemReadArgs;
+
+size_t swem_readout_workspace_bytes(const SwemDims* dims, int32_t path);
+int    swem_readout_forward(const SwemReadArgs* args, void* stream);
+
+/* ---- mask prep of SWEM.memorize, swem.py:80-84 ------------------------------------------------
+ * hard: [B, N+1, Hm, Wm] int64 one-hot (channel 0 = background, skipped), nearest-resized;
+ * soft: [B, N+1, Hs, Ws] fp32 probabilities, bilinear-resized (align_corners = false);
+ * out : [B, N, 2, H16, W16] with out[:,:,0] = (1-hard)(1-soft), out[:,:,1] = hard*soft.        */
+int swem_em_masks(const int64_t* hard, int32_t Hm, int32_t Wm,
+                  const float* soft, int32_t Hs, int32_t Ws,
+                  int32_t B, int32_t N, int32_t H16, int32_t W16,
+                  float* out, void* stream);
+
+/* ---- misc ------------------------------------------------------------------------------------ */
+int         swem_abi_version(void);          /* == SWEM_B200_ABI_VERSION                          */
+const char* swem_last_error(void);           /* thread-local, never NULL                          */
+int         swem_device_check(int device);   /* SWEM_OK iff `device` is compute capability 10.x   */
+/* 1 if the fused tcgen05 kernels cover these dims (what SWEM_PATH_AUTO would pick), else 0.     */
+int         swem_em_fused_supported(const SwemDims* dims);
+int         swem_readout_fused_supported(const SwemDims* dims);
+/* number of kernel launches the last call on this thread issued (for bench.py's gpu_launches)   */
+int         swem_last_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* SWEM_B200_H_ */

@@ -1,0 +1,86 @@
+"""ctypes binding of ``libswem_b200.so`` (C ABI declared in ``include/swem_b200.h``).
+
+The library is built in-tree by ``__graft_entry__.build()`` / ``make -C swem_b200/csrc``.  There is
+no fallback: if it is missing, or a call fails, a ``RuntimeError`` is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libswem_b200.so')
+
+PATH_AUTO, PATH_GENERIC, PATH_FUSED = 0, 1, 2
+
+EXPORTS = (
+    'swem_abi_version', 'swem_last_error', 'swem_device_check', 'swem_last_launch_count',
+    'swem_em_workspace_bytes', 'swem_em_forward', 'swem_em_fused_supported',
+    'swem_readout_workspace_bytes', 'swem_readout_forward', 'swem_readout_fused_supported',
+    'swem_em_masks',
+)
+
+
+class SwemDims(C.Structure):
+    _fields_ = [('B', C.c_int32), ('N', C.c_int32), ('Ck', C.c_int32), ('Cv', C.c_int32),
+                ('HW', C.c_int32), ('L', C.c_int32), ('n_iters', C.c_int32), ('n_banks', C.c_int32),
+                ('topl', C.c_int32), ('tau', C.c_float)]
+
+
+class SwemEmArgs(C.Structure):
+    _fields_ = [('dims', SwemDims),
+                ('x', C.c_void_p), ('v', C.c_void_p), ('masks', C.c_void_p),
+                ('kappa_prior', C.c_void_p), ('nu_prior', C.c_void_p), ('zita_prior', C.c_void_p),
+                ('kappa', C.c_void_p), ('nu', C.c_void_p), ('zita', C.c_void_p),
+                ('z_last', C.c_void_p),
+                ('workspace', C.c_void_p), ('workspace_bytes', C.c_size_t),
+                ('path', C.c_int32)]
+
+
+class SwemReadArgs(C.Structure):
+    _fields_ = [('dims', SwemDims),
+                ('qk', C.c_void_p),
+                ('kappa', C.c_void_p * 2), ('nu', C.c_void_p * 2),
+                ('out', C.c_void_p),
+                ('out_channels', C.c_int32), ('mem_channel', C.c_int32), ('s_channel', C.c_int32),
+                ('workspace', C.c_void_p), ('workspace_bytes', C.c_size_t),
+                ('path', C.c_int32)]
+
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load the shared library once; raise loudly when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise RuntimeError(
+            f'{LIB_PATH} not found: the SWEM hot path is CUDA-only (no CPU fallback). '
+            'Build it with `python -c "import __graft_entry__ as g; g.build()"` or `make -C swem_b200/csrc`.')
+    lib = C.CDLL(LIB_PATH)
+    lib.swem_abi_version.restype = C.c_int
+    lib.swem_last_error.restype = C.c_char_p
+    lib.swem_device_check.argtypes = [C.c_int]
+    lib.swem_last_launch_count.restype = C.c_int
+    lib.swem_em_workspace_bytes.argtypes = [C.POINTER(SwemDims), C.c_int32]
+    lib.swem_em_workspace_bytes.restype = C.c_size_t
+    lib.swem_em_forward.argtypes = [C.POINTER(SwemEmArgs), C.c_void_p]
+    lib.swem_em_fused_supported.argtypes = [C.POINTER(SwemDims)]
+    lib.swem_readout_workspace_bytes.argtypes = [C.POINTER(SwemDims), C.c_int32]
+    lib.swem_readout_workspace_bytes.restype = C.c_size_t
+    lib.swem_readout_forward.argtypes = [C.POINTER(SwemReadArgs), C.c_void_p]
+    lib.swem_readout_fused_supported.argtypes = [C.POINTER(SwemDims)]
+    lib.swem_em_masks.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32,
+                                  C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
+    if lib.swem_abi_version() != 1:
+        raise RuntimeError(f'libswem_b200.so ABI version {lib.swem_abi_version()} != 1')
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().swem_last_error().decode('utf-8', 'replace')
+        raise RuntimeError(f'{what} failed (status {rc}): {msg}')

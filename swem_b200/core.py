@@ -1,0 +1,220 @@
+"""``SWEMCore`` -- the drop-in replacement of the reference's ``methods/SWEM/modules.py::SWEMCore``.
+
+Same constructor, attributes and methods (``empty`` / ``memorize`` / ``matching`` / ``get_mem`` /
+``swem`` / ``random_init``, ``memories['first'|'update'].bases`` dicts with keys
+``kappa (B,N,2,Ck,L)``, ``nu (B,N,2,Cv,L)``, ``zita (B,N,2,1,L)``, ``fusion_layer.layer_f/layer_a``
+state-dict keys), but the E / M / W steps, the nu update and the readout attention run in the
+CUDA kernels of ``libswem_b200.so`` through its C ABI (``include/swem_b200.h``).
+
+What stays torch, as in the reference: the RNG draw for new bases (``random_init`` uses the
+global generator of the key's device, modules.py:170-178, so seeding behaves identically), the
+bank bookkeeping (modules.py:29-60,183-193) and the GLU fusion conv (modules.py:13-26).
+
+There is no CPU path: tensors must live on an sm_100 device and the library must be built.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Dict, Optional, Tuple
+
+import torch
+from torch import nn
+
+from . import _lib
+from .networks import FeatureFusionLayer
+
+Bases = Dict[str, torch.Tensor]
+
+
+class MemoryBank:
+    """One bank of bases; 'fixed' only appends objects it has not seen, 'updated' is replaced."""
+
+    def __init__(self, mode: str = 'updated'):
+        assert mode in ('fixed', 'updated')
+        self.mode = mode
+        self.bases: Optional[Bases] = None
+        self.n_objs = 0
+
+    def initial_memory(self):
+        self.bases, self.n_objs = None, 0
+
+    def add_new(self, bases: Bases):
+        if self.bases is None:
+            self.bases, self.n_objs = bases, bases['kappa'].shape[1]
+            return
+        n = bases['kappa'].shape[1]
+        if n > self.n_objs:
+            self.bases = {k: torch.cat([self.bases[k], bases[k][:, self.n_objs:]], dim=1) for k in bases}
+        self.n_objs = n
+
+    def update(self, bases: Bases):
+        if self.mode == 'fixed':
+            self.add_new(bases)
+        else:
+            self.bases = bases
+
+
+class _Workspace:
+    """Per-device scratch buffer handed to the kernels (grown on demand, never shrunk)."""
+
+    def __init__(self):
+        self._buf: Dict[torch.device, torch.Tensor] = {}
+
+    def get(self, device: torch.device, nbytes: int) -> torch.Tensor:
+        buf = self._buf.get(device)
+        if buf is None or buf.numel() < nbytes:
+            buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+            self._buf[device] = buf
+        return buf
+
+
+_WORKSPACE = _Workspace()
+
+
+def _f32c(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise RuntimeError(f'swem_b200: `{name}` is on {t.device}; the SWEM hot path runs on a B200 only '
+                           '(no CPU fallback -- use oracle/ for CPU checking)')
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def _no_grad_inputs(*tensors):
+    if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors):
+        raise NotImplementedError('swem_b200: backward through the fused EM/readout kernels is not '
+                                  'implemented yet; call under torch.no_grad()')
+
+
+class SWEMCore(nn.Module):
+    # SWEM_PATH_* of the C ABI; tests flip this to exercise both kernel families
+    kernel_path = _lib.PATH_AUTO
+
+    def __init__(self, n_bases=256, valdim=512, n_iters=4, tau=0.05, topl=64):
+        super().__init__()
+        assert tau > 0
+        self.n_bases, self.n_iters, self.tau, self.valdim = n_bases, n_iters, tau, valdim
+        self.memories = {'first': MemoryBank('fixed'), 'update': MemoryBank('updated')}
+        self.p_drop = 0.0
+        self.topl = int(min(n_bases, topl))
+        self.fusion_layer = FeatureFusionLayer(valdim * 2 + self.topl * 2, valdim)
+        self.launches = 0          # kernels launched by this object's last memorize/matching call
+
+    # -- bank state ------------------------------------------------------------------------
+    def empty(self):
+        for bank in self.memories.values():
+            bank.initial_memory()
+
+    def get_mem(self) -> Tuple[torch.Tensor, torch.Tensor]:
+        banks = [m.bases for m in self.memories.values() if m.bases is not None]
+        return (torch.cat([b['kappa'] for b in banks], dim=-1), torch.cat([b['nu'] for b in banks], dim=-1))
+
+    def random_init(self, size, norm_dim=-2, dtype=None, device=None):
+        """Fresh bases for objects without a prior; draws from torch's global RNG like the reference."""
+        B, N, _, _, L = size
+        kappa = torch.zeros(size=size).type(dtype).to(device)
+        kappa.normal_(0, math.sqrt(2.0 / size[-1]))
+        kappa = kappa / (torch.linalg.norm(kappa, dim=norm_dim, keepdim=True) + 1e-6)
+        nu = torch.zeros(B, N, 2, self.valdim, L).type(dtype).to(device)
+        zita = torch.zeros(B, N, 2, 1, L).type(dtype).to(device) + 1e-6
+        return kappa, nu, zita
+
+    # -- memorize --------------------------------------------------------------------------
+    def swem(self, x, v, masks, bases_: Optional[Bases] = None, return_z: bool = False) -> Bases:
+        """x (B,Ck,H,W) raw key, v (B,N,Cv,H,W), masks (B,N,2,H,W) -> bases dict (one fused EM update)."""
+        _no_grad_inputs(x, v, masks)
+        B, Ck, H, W = x.shape
+        N = masks.shape[1]
+        L = self.n_bases
+        if bases_ is None:
+            kappa_, nu_, zita_ = self.random_init((B, N, 2, Ck, L), dtype=x.type(), device=x.device)
+        else:
+            kappa_, nu_, zita_ = bases_['kappa'], bases_['nu'], bases_['zita']
+        n_new = N - kappa_.shape[1]
+        if n_new > 0:
+            k2, n2, z2 = self.random_init((B, n_new, 2, Ck, L), dtype=x.type(), device=x.device)
+            kappa_, nu_, zita_ = torch.cat([kappa_, k2], 1), torch.cat([nu_, n2], 1), torch.cat([zita_, z2], 1)
+
+        x, v, masks = _f32c(x, 'x'), _f32c(v, 'v'), _f32c(masks, 'masks')
+        kappa_, nu_, zita_ = _f32c(kappa_, 'kappa'), _f32c(nu_, 'nu'), _f32c(zita_, 'zita')
+        Cv = v.shape[2]
+        if v.shape[:2] != (B, N) or v.shape[-2:] != (H, W) or kappa_.shape != (B, N, 2, Ck, L) \
+                or nu_.shape != (B, N, 2, Cv, L) or masks.shape != (B, N, 2, H, W):
+            raise RuntimeError(f'swem: inconsistent shapes x{tuple(x.shape)} v{tuple(v.shape)} '
+                               f'masks{tuple(masks.shape)} kappa{tuple(kappa_.shape)} nu{tuple(nu_.shape)}')
+        dev = x.device
+        kappa = torch.empty_like(kappa_)
+        nu = torch.empty_like(nu_)
+        zita = torch.empty_like(zita_)
+        z_last = torch.empty(B, N, 2, H * W, L, device=dev, dtype=torch.float32) if return_z else None
+
+        lib = _lib.load()
+        dims = _lib.SwemDims(B, N, Ck, Cv, H * W, L, self.n_iters, 0, 0, self.tau)
+        need = lib.swem_em_workspace_bytes(C.byref(dims), self.kernel_path)
+        ws = _WORKSPACE.get(dev, need)
+        args = _lib.SwemEmArgs(dims, x.data_ptr(), v.data_ptr(), masks.data_ptr(),
+                               kappa_.data_ptr(), nu_.data_ptr(), zita_.data_ptr(),
+                               kappa.data_ptr(), nu.data_ptr(), zita.data_ptr(),
+                               z_last.data_ptr() if return_z else None,
+                               ws.data_ptr(), ws.numel(), self.kernel_path)
+        with torch.cuda.device(dev):
+            rc = lib.swem_em_forward(C.byref(args), torch.cuda.current_stream(dev).cuda_stream)
+        _lib.check(rc, 'swem_em_forward')
+        self.launches = lib.swem_last_launch_count()
+        bases = {'kappa': kappa, 'nu': nu, 'zita': zita}
+        if return_z:
+            bases['z'] = z_last
+        return bases
+
+    def memorize(self, qk, qv, masks):
+        prior = self.memories['update'].bases
+        if prior is None:
+            prior = self.memories['first'].bases
+        bases = self.swem(qk, qv, masks, prior)
+        if self.memories['first'].bases is None:
+            self.memories['first'].update(bases)
+        else:
+            self.memories['first'].update(bases)
+            self.memories['update'].update(bases)
+
+    # -- readout ---------------------------------------------------------------------------
+    def matching_features(self, qk, qv) -> Tuple[torch.Tensor, int]:
+        """-> the concat buffer [mem_out | qv | S] (B*N, 2*Cv + 2*topl, H, W) and N."""
+        if self.training and self.p_drop > 0:
+            raise NotImplementedError('swem_b200: memory dropout (p_drop > 0) is not implemented')
+        banks = [m.bases for m in self.memories.values() if m.bases is not None]
+        if not banks:
+            raise RuntimeError('matching() before any memorize(): memory is empty')
+        _no_grad_inputs(qk, qv, *[b['nu'] for b in banks])
+        qk, qv = _f32c(qk, 'qk'), _f32c(qv, 'qv')
+        B, Ck, H, W = qk.shape
+        _, N, _, Cv, L = banks[0]['nu'].shape
+        dev = qk.device
+        chans = 2 * Cv + 2 * self.topl
+        feats = torch.empty(B * N, chans, H, W, device=dev, dtype=torch.float32)
+        feats.view(B, N, chans, H, W)[:, :, Cv:2 * Cv] = qv.unsqueeze(1)
+
+        lib = _lib.load()
+        dims = _lib.SwemDims(B, N, Ck, Cv, H * W, L, 0, len(banks), self.topl, self.tau)
+        need = lib.swem_readout_workspace_bytes(C.byref(dims), self.kernel_path)
+        ws = _WORKSPACE.get(dev, need)
+        kap = [_f32c(b['kappa'], 'kappa') for b in banks]
+        nus = [_f32c(b['nu'], 'nu') for b in banks]
+        args = _lib.SwemReadArgs(dims, qk.data_ptr(),
+                                 (C.c_void_p * 2)(*[k.data_ptr() for k in kap] + [None] * (2 - len(kap))),
+                                 (C.c_void_p * 2)(*[n.data_ptr() for n in nus] + [None] * (2 - len(nus))),
+                                 feats.data_ptr(), chans, 0, 2 * Cv,
+                                 ws.data_ptr(), ws.numel(), self.kernel_path)
+        with torch.cuda.device(dev):
+            rc = lib.swem_readout_forward(C.byref(args), torch.cuda.current_stream(dev).cuda_stream)
+        _lib.check(rc, 'swem_readout_forward')
+        self.launches = lib.swem_last_launch_count()
+        return feats, N
+
+    def matching(self, qk, qv):
+        feats, n = self.matching_features(qk, qv)
+        return self.fusion_layer(feats), n
+
+    def forward(self, qk, qv):
+        pass

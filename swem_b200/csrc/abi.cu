@@ -1,0 +1,169 @@
+// extern "C" surface of libswem_b200.so: argument validation, family dispatch, mask prep.
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace swem {
+
+static thread_local char g_err[512] = "";
+static thread_local int g_launches = 0;
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void count_launch(int n) { g_launches += n; }
+void reset_launch_count() { g_launches = 0; }
+
+static int check_dims(const SwemDims& d, bool em) {
+  SWEM_CHECK_ARG(d.B > 0 && d.N > 0 && d.Ck > 0 && d.Cv > 0 && d.HW > 0 && d.L > 0,
+                 "non-positive dimension (B=%d N=%d Ck=%d Cv=%d HW=%d L=%d)", d.B, d.N, d.Ck, d.Cv, d.HW, d.L);
+  SWEM_CHECK_ARG(d.tau > 0.f, "tau must be > 0 (got %g)", (double)d.tau);   // reference modules.py:70
+  if (em) {
+    SWEM_CHECK_ARG(d.n_iters >= 1, "n_iters must be >= 1 (got %d)", d.n_iters);
+  } else {
+    SWEM_CHECK_ARG(d.n_banks == 1 || d.n_banks == 2, "n_banks must be 1 or 2 (got %d)", d.n_banks);
+    SWEM_CHECK_ARG(d.topl >= 1 && d.topl <= d.L * d.n_banks, "topl=%d outside [1, Lt=%d]", d.topl, d.L * d.n_banks);
+  }
+  return SWEM_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// mask prep (reference swem.py:80-84): nearest-resized hard mask x bilinear-resized soft mask.
+// Index arithmetic follows ATen's upsample kernels (float scale = in/out; nearest: floor(dst*scale);
+// bilinear, align_corners=false: src = scale*(dst+0.5)-0.5 clamped at 0).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int nearest_src(int dst, int in, int out, float scale) {
+  if (in == out) return dst;
+  if (out == 2 * in) return dst >> 1;
+  return min((int)floorf(dst * scale), in - 1);
+}
+
+__global__ void em_masks_kernel(const long long* __restrict__ hard, int Hm, int Wm,
+                                const float* __restrict__ soft, int Hs, int Ws, int B, int N, int H, int W,
+                                float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * N * H * W) return;
+  const int w = i % W, h = (i / W) % H, n = (i / (W * H)) % N, b = i / (W * H * N);
+  const float sh_n = (float)Hm / (float)H, sw_n = (float)Wm / (float)W;
+  const int hy = nearest_src(h, Hm, H, sh_n), hx = nearest_src(w, Wm, W, sw_n);
+  const float hv = (float)hard[(((long long)b * (N + 1) + n + 1) * Hm + hy) * Wm + hx];
+
+  const float sh = (float)Hs / (float)H, sw = (float)Ws / (float)W;
+  float sy = sh * (h + 0.5f) - 0.5f, sx = sw * (w + 0.5f) - 0.5f;
+  sy = sy < 0.f ? 0.f : sy;
+  sx = sx < 0.f ? 0.f : sx;
+  const int y0 = min((int)sy, Hs - 1), x0 = min((int)sx, Ws - 1);
+  const int y1 = y0 + (y0 < Hs - 1 ? 1 : 0), x1 = x0 + (x0 < Ws - 1 ? 1 : 0);
+  const float ly = fminf(fmaxf(sy - y0, 0.f), 1.f), lx = fminf(fmaxf(sx - x0, 0.f), 1.f);
+  const float* sp = soft + ((long long)b * (N + 1) + n + 1) * Hs * Ws;
+  const float sv = (1.f - ly) * ((1.f - lx) * sp[y0 * Ws + x0] + lx * sp[y0 * Ws + x1]) +
+                   ly * ((1.f - lx) * sp[y1 * Ws + x0] + lx * sp[y1 * Ws + x1]);
+  float* op = out + (((long long)b * N + n) * 2) * H * W + h * W + w;
+  op[0] = (1.f - hv) * (1.f - sv);
+  op[(long long)H * W] = hv * sv;
+}
+
+}  // namespace swem
+
+using namespace swem;
+
+extern "C" {
+
+int swem_abi_version(void) { return SWEM_B200_ABI_VERSION; }
+const char* swem_last_error(void) { return g_err; }
+int swem_last_launch_count(void) { return g_launches; }
+
+int swem_device_check(int device) {
+  cudaDeviceProp prop;
+  SWEM_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    set_error("device %d is sm_%d%d; libswem_b200 is built for sm_100a only", device, prop.major, prop.minor);
+    return SWEM_ERR_DEVICE;
+  }
+  return SWEM_OK;
+}
+
+int swem_em_fused_supported(const SwemDims* d) { return d && fused_em_supported(*d) ? 1 : 0; }
+int swem_readout_fused_supported(const SwemDims* d) { return d && fused_readout_supported(*d) ? 1 : 0; }
+
+static bool use_fused_em(const SwemDims& d, int path) {
+  return path == SWEM_PATH_FUSED || (path == SWEM_PATH_AUTO && fused_em_supported(d));
+}
+static bool use_fused_readout(const SwemDims& d, int path) {
+  return path == SWEM_PATH_FUSED || (path == SWEM_PATH_AUTO && fused_readout_supported(d));
+}
+
+size_t swem_em_workspace_bytes(const SwemDims* d, int32_t path) {
+  if (!d || check_dims(*d, true)) return 0;
+  if (path == SWEM_PATH_FUSED && !fused_em_supported(*d)) return 0;
+  return use_fused_em(*d, path) ? fused_em_workspace(*d) : generic_em_workspace(*d);
+}
+
+int swem_em_forward(const SwemEmArgs* a, void* stream) {
+  reset_launch_count();
+  SWEM_CHECK_ARG(a != nullptr, "args is NULL");
+  if (int rc = check_dims(a->dims, true)) return rc;
+  SWEM_CHECK_ARG(a->x && a->v && a->masks && a->kappa_prior && a->nu_prior && a->zita_prior,
+                 "a required input pointer is NULL");
+  SWEM_CHECK_ARG(a->kappa && a->nu && a->zita, "a required output pointer is NULL");
+  SWEM_CHECK_ARG(a->path >= SWEM_PATH_AUTO && a->path <= SWEM_PATH_FUSED, "bad path %d", a->path);
+  if (a->path == SWEM_PATH_FUSED && !fused_em_supported(a->dims)) {
+    set_error("fused EM kernels do not cover Ck=%d Cv=%d L=%d HW=%d", a->dims.Ck, a->dims.Cv, a->dims.L, a->dims.HW);
+    return SWEM_ERR_UNSUPPORTED;
+  }
+  const size_t need = swem_em_workspace_bytes(&a->dims, a->path);
+  if (!a->workspace || a->workspace_bytes < need || (reinterpret_cast<uintptr_t>(a->workspace) & 255)) {
+    set_error("EM workspace: need %zu bytes 256-aligned, got %zu at %p", need, a->workspace_bytes, a->workspace);
+    return SWEM_ERR_WORKSPACE;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return use_fused_em(a->dims, a->path) ? fused_em_forward(*a, st) : generic_em_forward(*a, st);
+}
+
+size_t swem_readout_workspace_bytes(const SwemDims* d, int32_t path) {
+  if (!d || check_dims(*d, false)) return 0;
+  if (path == SWEM_PATH_FUSED && !fused_readout_supported(*d)) return 0;
+  return use_fused_readout(*d, path) ? fused_readout_workspace(*d) : generic_readout_workspace(*d);
+}
+
+int swem_readout_forward(const SwemReadArgs* a, void* stream) {
+  reset_launch_count();
+  SWEM_CHECK_ARG(a != nullptr, "args is NULL");
+  if (int rc = check_dims(a->dims, false)) return rc;
+  const SwemDims& d = a->dims;
+  SWEM_CHECK_ARG(a->qk && a->out, "qk/out pointer is NULL");
+  for (int k = 0; k < d.n_banks; ++k) SWEM_CHECK_ARG(a->kappa[k] && a->nu[k], "bank %d pointer is NULL", k);
+  SWEM_CHECK_ARG(a->mem_channel >= 0 && a->mem_channel + d.Cv <= a->out_channels &&
+                 a->s_channel >= 0 && a->s_channel + 2 * d.topl <= a->out_channels,
+                 "channel placement outside out_channels=%d", a->out_channels);
+  SWEM_CHECK_ARG(a->path >= SWEM_PATH_AUTO && a->path <= SWEM_PATH_FUSED, "bad path %d", a->path);
+  if (a->path == SWEM_PATH_FUSED && !fused_readout_supported(d)) {
+    set_error("fused readout kernels do not cover Ck=%d Cv=%d L=%d banks=%d", d.Ck, d.Cv, d.L, d.n_banks);
+    return SWEM_ERR_UNSUPPORTED;
+  }
+  const size_t need = swem_readout_workspace_bytes(&d, a->path);
+  if (!a->workspace || a->workspace_bytes < need || (reinterpret_cast<uintptr_t>(a->workspace) & 255)) {
+    set_error("readout workspace: need %zu bytes 256-aligned, got %zu at %p", need, a->workspace_bytes, a->workspace);
+    return SWEM_ERR_WORKSPACE;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return use_fused_readout(d, a->path) ? fused_readout_forward(*a, st) : generic_readout_forward(*a, st);
+}
+
+int swem_em_masks(const int64_t* hard, int32_t Hm, int32_t Wm, const float* soft, int32_t Hs, int32_t Ws,
+                  int32_t B, int32_t N, int32_t H16, int32_t W16, float* out, void* stream) {
+  reset_launch_count();
+  SWEM_CHECK_ARG(hard && soft && out, "NULL pointer");
+  SWEM_CHECK_ARG(Hm > 0 && Wm > 0 && Hs > 0 && Ws > 0 && B > 0 && N > 0 && H16 > 0 && W16 > 0, "non-positive size");
+  const int n = B * N * H16 * W16;
+  em_masks_kernel<<<(n + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const long long*>(hard), Hm, Wm, soft, Hs, Ws, B, N, H16, W16, out);
+  SWEM_LAUNCH_CHECK();
+  return SWEM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,491 @@
+// Generic-shape kernel family of libswem_b200.so: any Ck / Cv / L / HW, fp32 throughout.
+//
+// This family covers every shape the reference accepts (the fused tcgen05 family in fused_*.cu
+// covers the BASELINE shapes and is what SWEM_PATH_AUTO picks for them).  It is organised as a
+// strided batched tile GEMM plus row kernels, with the reference's operation order:
+//
+//   memorize (reference modules.py:129-168), per EM iteration i:
+//     khat   = kappa / (||kappa||_c + eps)                      kappa_unit_kernel      (:115)
+//     a      = x^T khat                                         sgemm                  (:116)
+//     w      = masks * (1 - side share of exp((a/||x|| - max)/tau))   em_assign_kernel (:93-110, i>0)
+//     z      = softmax_l((a - max_l a)/tau) * w                 em_assign_kernel       (:117-119)
+//     zita   = zita_ + sum_p z                                  colsum + zita kernels  (:125)
+//     kappa  = (zita_ kappa_ + x z) / zita                      sgemm + bases_finalize (:126)
+//   nu = (zita_ nu_ + v z_last) / zita                          sgemm + bases_finalize (:164-165)
+//
+// Note the W-step logits l2norm(x)^T khat (:98-100) equal a / (||x||+eps) with the SAME khat the
+// next E-step uses, so one GEMM per iteration serves both steps.
+//
+//   readout (modules.py:232-293): scores = q^T khat / (||q||+eps) -> P = softmax over (side, j)
+//   -> mem_out = V P (sgemm, accumulated over banks and sides) ; S from sorted top-l of P.
+#include <float.h>
+
+#include "common.cuh"
+
+namespace swem {
+
+// ------------------------------------------------------------------------------------------
+// strided, 3-level batched SGEMM: C[z][m][n] (+)= sum_k A[z][m][k] * B[z][k][n]
+// ------------------------------------------------------------------------------------------
+struct GemmShape {
+  int M, N, K;
+  long long sAm, sAk, sBk, sBn, sCm, sCn;   // element strides
+  int n0, n1, n2;                           // batch grid; blockIdx.z -> (i0, i1, i2)
+  long long bA[3], bB[3], bC[3];            // batch strides (0 = broadcast)
+  int accumulate;                           // 1: C += ...
+};
+
+template <int BM, int BN, int BK, int TM, int TN>
+__global__ void __launch_bounds__((BM / TM) * (BN / TN))
+sgemm_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ C, GemmShape g) {
+  constexpr int NT = (BM / TM) * (BN / TN);
+  __shared__ float As[BK][BM + 4];
+  __shared__ float Bs[BK][BN + 4];
+  const int z = blockIdx.z;
+  const int i2 = z % g.n2, i1 = (z / g.n2) % g.n1, i0 = z / (g.n2 * g.n1);
+  A += i0 * g.bA[0] + i1 * g.bA[1] + i2 * g.bA[2];
+  B += i0 * g.bB[0] + i1 * g.bB[1] + i2 * g.bB[2];
+  C += i0 * g.bC[0] + i1 * g.bC[1] + i2 * g.bC[2];
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int tid = threadIdx.x;
+  const int tx = tid % (BN / TN), ty = tid / (BN / TN);
+  const bool a_mfast = (g.sAm == 1), b_nfast = (g.sBn == 1);
+  float acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+  for (int k0 = 0; k0 < g.K; k0 += BK) {
+    for (int e = tid; e < BM * BK; e += NT) {
+      int m, k;
+      if (a_mfast) { m = e % BM; k = e / BM; } else { k = e % BK; m = e / BK; }
+      float val = 0.f;
+      if (m0 + m < g.M && k0 + k < g.K) val = A[(long long)(m0 + m) * g.sAm + (long long)(k0 + k) * g.sAk];
+      As[k][m] = val;
+    }
+    for (int e = tid; e < BN * BK; e += NT) {
+      int n, k;
+      if (b_nfast) { n = e % BN; k = e / BN; } else { k = e % BK; n = e / BK; }
+      float val = 0.f;
+      if (n0 + n < g.N && k0 + k < g.K) val = B[(long long)(k0 + k) * g.sBk + (long long)(n0 + n) * g.sBn];
+      Bs[k][n] = val;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      float a[TM], b[TN];
+#pragma unroll
+      for (int i = 0; i < TM; ++i) a[i] = As[k][ty * TM + i];
+#pragma unroll
+      for (int j = 0; j < TN; ++j) b[j] = Bs[k][tx * TN + j];
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    const int m = m0 + ty * TM + i;
+    if (m >= g.M) continue;
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      const int n = n0 + tx * TN + j;
+      if (n >= g.N) continue;
+      float* p = C + (long long)m * g.sCm + (long long)n * g.sCn;
+      *p = g.accumulate ? (*p + acc[i][j]) : acc[i][j];
+    }
+  }
+}
+
+static int launch_gemm(const float* A, const float* B, float* C, const GemmShape& g, cudaStream_t st) {
+  const int nb = g.n0 * g.n1 * g.n2;
+  const long long big_tiles = (long long)((g.M + 63) / 64) * ((g.N + 63) / 64) * nb;
+  if (big_tiles >= 120) {
+    dim3 grid((g.N + 63) / 64, (g.M + 63) / 64, nb);
+    sgemm_kernel<64, 64, 16, 4, 4><<<grid, 256, 0, st>>>(A, B, C, g);
+  } else {
+    dim3 grid((g.N + 31) / 32, (g.M + 31) / 32, nb);
+    sgemm_kernel<32, 32, 16, 2, 2><<<grid, 256, 0, st>>>(A, B, C, g);
+  }
+  SWEM_LAUNCH_CHECK();
+  return SWEM_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// row / column kernels
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// inv[b][p] = 1 / (||x[b,:,p]||_2 + eps)
+__global__ void pixel_inv_norm_kernel(const float* __restrict__ x, float* __restrict__ inv, int B, int C, int HW) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * HW) return;
+  const int b = i / HW, p = i % HW;
+  const float* xp = x + (long long)b * C * HW + p;
+  float ss = 0.f;
+  for (int c = 0; c < C; ++c) { const float t = xp[(long long)c * HW]; ss = fmaf(t, t, ss); }
+  inv[i] = 1.f / (sqrtf(ss) + kEpsNorm);
+}
+
+// khat[g][c][l] = kappa[g][c][l] / (||kappa[g,:,l]||_2 + eps),  g over (b,n,s)
+__global__ void kappa_unit_kernel(const float* __restrict__ kappa, float* __restrict__ khat, int G, int C, int L) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= G * L) return;
+  const int g = i / L, l = i % L;
+  const float* kp = kappa + (long long)g * C * L + l;
+  float ss = 0.f;
+  for (int c = 0; c < C; ++c) { const float t = kp[(long long)c * L]; ss = fmaf(t, t, ss); }
+  const float nrm = sqrtf(ss) + kEpsNorm;
+  float* op = khat + (long long)g * C * L + l;
+  for (int c = 0; c < C; ++c) op[(long long)c * L] = kp[(long long)c * L] / nrm;
+}
+
+// One warp per (unit u, pixel p).  a: [U][2][HW][L] logits x^T khat, overwritten with z.
+__global__ void em_assign_kernel(float* __restrict__ a, const float* __restrict__ inv_nx,
+                                 const float* __restrict__ masks, int U, int N, int HW, int L,
+                                 float inv_tau, int do_w) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= U * HW) return;
+  const int u = warp / HW, p = warp % HW, b = u / N;
+  float* row0 = a + ((long long)(u * 2 + 0) * HW + p) * L;
+  float* row1 = a + ((long long)(u * 2 + 1) * HW + p) * L;
+  float w0 = masks[(long long)(u * 2 + 0) * HW + p];
+  float w1 = masks[(long long)(u * 2 + 1) * HW + p];
+  if (do_w) {
+    // W-step (reference :93-110) on t = a / (||x_p|| + eps)
+    const float inv = inv_nx[b * HW + p];
+    float mx = -FLT_MAX;
+    for (int l = lane; l < L; l += 32) mx = fmaxf(mx, fmaxf(row0[l], row1[l]) * inv);
+    // (a*inv) is monotone in a for inv > 0, but take the max of the products like the reference
+    mx = warp_max(mx);
+    float e0 = 0.f, e1 = 0.f;
+    for (int l = lane; l < L; l += 32) {
+      e0 += expf((row0[l] * inv - mx) * inv_tau);
+      e1 += expf((row1[l] * inv - mx) * inv_tau);
+    }
+    e0 = warp_sum(e0);
+    e1 = warp_sum(e1);
+    const float tot = e0 + e1;
+    w0 *= (1.f - e0 / tot);
+    w1 *= (1.f - e1 / tot);
+  }
+  // E-step (reference :112-120), each side separately
+#pragma unroll
+  for (int s = 0; s < 2; ++s) {
+    float* row = s ? row1 : row0;
+    const float w = s ? w1 : w0;
+    float mx = -FLT_MAX;
+    for (int l = lane; l < L; l += 32) mx = fmaxf(mx, row[l]);
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int l = lane; l < L; l += 32) sum += expf((row[l] - mx) * inv_tau);
+    sum = warp_sum(sum);
+    for (int l = lane; l < L; l += 32) row[l] = expf((row[l] - mx) * inv_tau) / sum * w;
+  }
+}
+
+// part[g][chunk][l] = sum over the chunk's pixels of z[g][p][l]
+__global__ void colsum_partial_kernel(const float* __restrict__ z, float* __restrict__ part, int HW, int L,
+                                      int chunk_px, int n_chunks) {
+  const int g = blockIdx.y, ch = blockIdx.x;
+  const int p0 = ch * chunk_px, p1 = min(HW, p0 + chunk_px);
+  for (int l = threadIdx.x; l < L; l += blockDim.x) {
+    const float* zp = z + ((long long)g * HW + p0) * L + l;
+    float s = 0.f;
+    for (int p = p0; p < p1; ++p, zp += L) s += *zp;
+    part[((long long)g * n_chunks + ch) * L + l] = s;
+  }
+}
+
+// zita[g][l] = zita_prior[g][l] + sum_chunks part[g][chunk][l]   (fixed order -> deterministic)
+__global__ void zita_kernel(const float* __restrict__ zita_prior, const float* __restrict__ part,
+                            float* __restrict__ zita, int G, int L, int n_chunks) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= G * L) return;
+  const int g = i / L, l = i % L;
+  float s = 0.f;
+  for (int c = 0; c < n_chunks; ++c) s += part[((long long)g * n_chunks + c) * L + l];
+  zita[i] = zita_prior[i] + s;
+}
+
+// out[g][r][l] = (zita_prior[g][l] * prior[g][r][l] + acc[g][r][l]) / zita[g][l]; acc may alias out
+__global__ void bases_finalize_kernel(const float* __restrict__ prior, const float* acc,
+                                      const float* __restrict__ zita_prior, const float* __restrict__ zita,
+                                      float* out, int G, int R, int L) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)G * R * L) return;
+  const int l = (int)(i % L);
+  const int g = (int)(i / ((long long)R * L));
+  out[i] = (zita_prior[g * L + l] * prior[i] + acc[i]) / zita[g * L + l];
+}
+
+// One warp per (u, p): scores row [2Lt] -> P = softmax over both sides of (score/||q||)/tau, in place.
+__global__ void readout_rows_kernel(float* __restrict__ sc, const float* __restrict__ inv_nq, int U, int N,
+                                    int HW, int W2, float inv_tau) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= U * HW) return;
+  const int u = warp / HW, p = warp % HW, b = u / N;
+  float* row = sc + ((long long)u * HW + p) * W2;
+  const float inv = inv_nq[b * HW + p];
+  float mx = -FLT_MAX;
+  for (int j = lane; j < W2; j += 32) mx = fmaxf(mx, row[j] * inv);
+  mx = warp_max(mx);
+  float sum = 0.f;
+  for (int j = lane; j < W2; j += 32) sum += expf((row[j] * inv - mx) * inv_tau);
+  sum = warp_sum(sum);
+  for (int j = lane; j < W2; j += 32) row[j] = expf((row[j] * inv - mx) * inv_tau) / sum;
+}
+
+// ------------------------------------------------------------------------------------------
+// permutation-invariant feature (reference :198-208).  One warp per (u, p); lanes hold Lt/32
+// values per side; 'topl' rounds of {local max, warp arg-max, retire the winner}; the running
+// sums advance in rank order exactly like the reference's sequential loop.  f is scale
+// invariant, so the normalised P serves as well as the un-normalised exp-affinity.
+// ------------------------------------------------------------------------------------------
+template <int NPL>
+__global__ void __launch_bounds__(256) perm_inv_kernel(const float* __restrict__ P, int U, int HW, int Lt,
+                                                       int topl, float* __restrict__ out, int out_channels,
+                                                       int s_channel) {
+  extern __shared__ float tile[];          // [2*topl][33]
+  const int u = blockIdx.y;
+  const int p_base = blockIdx.x * 32;
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int q = wid; q < 32; q += 8) {
+    const int p = p_base + q;
+    if (p >= HW) break;
+    const float* row = P + ((long long)u * HW + p) * (2 * Lt);
+    float v0[NPL], v1[NPL];
+#pragma unroll
+    for (int i = 0; i < NPL; ++i) {
+      const int j = i * 32 + lane;
+      v0[i] = j < Lt ? row[j] : -1.f;
+      v1[i] = j < Lt ? row[Lt + j] : -1.f;
+    }
+    float run0 = 0.f, run1 = 0.f;
+    for (int r = 0; r < topl; ++r) {
+      float m0 = v0[0], m1 = v1[0];
+#pragma unroll
+      for (int i = 1; i < NPL; ++i) { m0 = fmaxf(m0, v0[i]); m1 = fmaxf(m1, v1[i]); }
+      const float g0 = warp_max(m0), g1 = warp_max(m1);
+      const unsigned b0 = __ballot_sync(0xffffffffu, m0 == g0);
+      const unsigned b1 = __ballot_sync(0xffffffffu, m1 == g1);
+      if (lane == __ffs(b0) - 1) {
+        bool done = false;
+#pragma unroll
+        for (int i = 0; i < NPL; ++i)
+          if (!done && v0[i] == g0) { v0[i] = -1.f; done = true; }
+      }
+      if (lane == __ffs(b1) - 1) {
+        bool done = false;
+#pragma unroll
+        for (int i = 0; i < NPL; ++i)
+          if (!done && v1[i] == g1) { v1[i] = -1.f; done = true; }
+      }
+      run0 += g0;
+      run1 += g1;
+      if (lane == (r & 31)) {
+        const float f = run0 / (run0 + run1);
+        tile[r * 33 + q] = f;
+        tile[(topl + r) * 33 + q] = 1.f - f;
+      }
+    }
+  }
+  __syncthreads();
+  const int npx = min(32, HW - p_base);
+  for (int e = threadIdx.x; e < 2 * topl * 32; e += blockDim.x) {
+    const int ch = e >> 5, q = e & 31;
+    if (q < npx) out[((long long)u * out_channels + s_channel + ch) * HW + p_base + q] = tile[ch * 33 + q];
+  }
+}
+
+int launch_perm_inv(const float* P, int U, int HW, int Lt, int topl, float* out, int out_channels,
+                    int s_channel, cudaStream_t st) {
+  dim3 grid((HW + 31) / 32, U);
+  const size_t smem = (size_t)2 * topl * 33 * sizeof(float);
+  const int npl = (Lt + 31) / 32;
+#define SWEM_PI(NPL_) perm_inv_kernel<NPL_><<<grid, 256, smem, st>>>(P, U, HW, Lt, topl, out, out_channels, s_channel)
+  if (npl <= 1) SWEM_PI(1);
+  else if (npl <= 2) SWEM_PI(2);
+  else if (npl <= 4) SWEM_PI(4);
+  else if (npl <= 8) SWEM_PI(8);
+  else if (npl <= 16) SWEM_PI(16);
+  else if (npl <= 32) SWEM_PI(32);
+  else {
+    set_error("perm_inv: Lt=%d > 1024 unsupported", Lt);
+    return SWEM_ERR_UNSUPPORTED;
+  }
+#undef SWEM_PI
+  SWEM_LAUNCH_CHECK();
+  return SWEM_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// memorize
+// ------------------------------------------------------------------------------------------
+static constexpr int kChunkPx = 128;
+
+size_t generic_em_workspace(const SwemDims& d) {
+  const size_t U = (size_t)d.B * d.N, G = U * 2;
+  const size_t n_chunks = (d.HW + kChunkPx - 1) / kChunkPx;
+  size_t bytes = 0;
+  bytes += align_up(G * d.HW * d.L * 4, 256);         // a / z
+  bytes += align_up(G * d.Ck * d.L * 4, 256);         // khat
+  bytes += align_up(G * d.Ck * d.L * 4, 256);         // kappa (iterate)
+  bytes += align_up((size_t)d.B * d.HW * 4, 256);     // inv ||x||
+  bytes += align_up(G * n_chunks * d.L * 4, 256);     // column-sum partials
+  return bytes + 256;
+}
+
+int generic_em_forward(const SwemEmArgs& a, cudaStream_t st) {
+  const SwemDims& d = a.dims;
+  const int U = d.B * d.N, G = U * 2;
+  const int n_chunks = (d.HW + kChunkPx - 1) / kChunkPx;
+  Arena ws(a.workspace);
+  float* z = a.z_last ? a.z_last : ws.take<float>((size_t)G * d.HW * d.L);
+  if (a.z_last) (void)ws.take<float>((size_t)G * d.HW * d.L);
+  float* khat = ws.take<float>((size_t)G * d.Ck * d.L);
+  float* kcur = ws.take<float>((size_t)G * d.Ck * d.L);
+  float* inv_nx = ws.take<float>((size_t)d.B * d.HW);
+  float* part = ws.take<float>((size_t)G * n_chunks * d.L);
+  const float inv_tau = 1.f / d.tau;
+
+  pixel_inv_norm_kernel<<<(d.B * d.HW + 255) / 256, 256, 0, st>>>(a.x, inv_nx, d.B, d.Ck, d.HW);
+  SWEM_LAUNCH_CHECK();
+
+  for (int it = 0; it < d.n_iters; ++it) {
+    const float* ksrc = (it == 0) ? a.kappa_prior : kcur;
+    kappa_unit_kernel<<<(G * d.L + 127) / 128, 128, 0, st>>>(ksrc, khat, G, d.Ck, d.L);
+    SWEM_LAUNCH_CHECK();
+    {  // a[b,n,s][p][l] = sum_c x[b][c][p] khat[b,n,s][c][l]
+      GemmShape g{};
+      g.M = d.HW; g.N = d.L; g.K = d.Ck;
+      g.sAm = 1; g.sAk = d.HW; g.sBk = d.L; g.sBn = 1; g.sCm = d.L; g.sCn = 1;
+      g.n0 = d.B; g.n1 = d.N; g.n2 = 2;
+      g.bA[0] = (long long)d.Ck * d.HW; g.bA[1] = 0; g.bA[2] = 0;
+      g.bB[0] = (long long)d.N * 2 * d.Ck * d.L; g.bB[1] = 2LL * d.Ck * d.L; g.bB[2] = (long long)d.Ck * d.L;
+      g.bC[0] = (long long)d.N * 2 * d.HW * d.L; g.bC[1] = 2LL * d.HW * d.L; g.bC[2] = (long long)d.HW * d.L;
+      if (int rc = launch_gemm(a.x, khat, z, g, st)) return rc;
+    }
+    {
+      const long long threads = (long long)U * d.HW * 32;
+      em_assign_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(z, inv_nx, a.masks, U, d.N, d.HW, d.L,
+                                                                          inv_tau, it > 0);
+      SWEM_LAUNCH_CHECK();
+    }
+    colsum_partial_kernel<<<dim3(n_chunks, G), min(d.L, 256), 0, st>>>(z, part, d.HW, d.L, kChunkPx, n_chunks);
+    SWEM_LAUNCH_CHECK();
+    zita_kernel<<<(G * d.L + 127) / 128, 128, 0, st>>>(a.zita_prior, part, a.zita, G, d.L, n_chunks);
+    SWEM_LAUNCH_CHECK();
+    float* kdst = (it == d.n_iters - 1) ? a.kappa : kcur;
+    {  // acc[b,n,s][c][l] = sum_p x[b][c][p] z[b,n,s][p][l]
+      GemmShape g{};
+      g.M = d.Ck; g.N = d.L; g.K = d.HW;
+      g.sAm = d.HW; g.sAk = 1; g.sBk = d.L; g.sBn = 1; g.sCm = d.L; g.sCn = 1;
+      g.n0 = d.B; g.n1 = d.N; g.n2 = 2;
+      g.bA[0] = (long long)d.Ck * d.HW; g.bA[1] = 0; g.bA[2] = 0;
+      g.bB[0] = (long long)d.N * 2 * d.HW * d.L; g.bB[1] = 2LL * d.HW * d.L; g.bB[2] = (long long)d.HW * d.L;
+      g.bC[0] = (long long)d.N * 2 * d.Ck * d.L; g.bC[1] = 2LL * d.Ck * d.L; g.bC[2] = (long long)d.Ck * d.L;
+      if (int rc = launch_gemm(a.x, z, kdst, g, st)) return rc;
+    }
+    {
+      const long long n = (long long)G * d.Ck * d.L;
+      bases_finalize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a.kappa_prior, kdst, a.zita_prior, a.zita,
+                                                                         kdst, G, d.Ck, d.L);
+      SWEM_LAUNCH_CHECK();
+    }
+  }
+  {  // nu acc[b,n,s][dch][l] = sum_p v[b,n][dch][p] z[b,n,s][p][l]
+    GemmShape g{};
+    g.M = d.Cv; g.N = d.L; g.K = d.HW;
+    g.sAm = d.HW; g.sAk = 1; g.sBk = d.L; g.sBn = 1; g.sCm = d.L; g.sCn = 1;
+    g.n0 = d.B; g.n1 = d.N; g.n2 = 2;
+    g.bA[0] = (long long)d.N * d.Cv * d.HW; g.bA[1] = (long long)d.Cv * d.HW; g.bA[2] = 0;
+    g.bB[0] = (long long)d.N * 2 * d.HW * d.L; g.bB[1] = 2LL * d.HW * d.L; g.bB[2] = (long long)d.HW * d.L;
+    g.bC[0] = (long long)d.N * 2 * d.Cv * d.L; g.bC[1] = 2LL * d.Cv * d.L; g.bC[2] = (long long)d.Cv * d.L;
+    if (int rc = launch_gemm(a.v, z, a.nu, g, st)) return rc;
+    const long long n = (long long)G * d.Cv * d.L;
+    bases_finalize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a.nu_prior, a.nu, a.zita_prior, a.zita, a.nu,
+                                                                       G, d.Cv, d.L);
+    SWEM_LAUNCH_CHECK();
+  }
+  return SWEM_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// readout
+// ------------------------------------------------------------------------------------------
+size_t generic_readout_workspace(const SwemDims& d) {
+  const size_t U = (size_t)d.B * d.N, G = U * 2;
+  const size_t Lt = (size_t)d.L * d.n_banks;
+  size_t bytes = 0;
+  bytes += align_up(U * d.HW * 2 * Lt * 4, 256);              // scores / P
+  bytes += align_up(G * d.Ck * d.L * 4, 256) * d.n_banks;     // khat per bank
+  bytes += align_up((size_t)d.B * d.HW * 4, 256);             // inv ||q||
+  return bytes + 256;
+}
+
+int generic_readout_forward(const SwemReadArgs& a, cudaStream_t st) {
+  const SwemDims& d = a.dims;
+  const int U = d.B * d.N, G = U * 2;
+  const int Lt = d.L * d.n_banks, W2 = 2 * Lt;
+  Arena ws(a.workspace);
+  float* P = ws.take<float>((size_t)U * d.HW * W2);
+  float* khat[2] = {nullptr, nullptr};
+  for (int k = 0; k < d.n_banks; ++k) khat[k] = ws.take<float>((size_t)G * d.Ck * d.L);
+  float* inv_nq = ws.take<float>((size_t)d.B * d.HW);
+
+  pixel_inv_norm_kernel<<<(d.B * d.HW + 255) / 256, 256, 0, st>>>(a.qk, inv_nq, d.B, d.Ck, d.HW);
+  SWEM_LAUNCH_CHECK();
+  for (int k = 0; k < d.n_banks; ++k) {
+    kappa_unit_kernel<<<(G * d.L + 127) / 128, 128, 0, st>>>(a.kappa[k], khat[k], G, d.Ck, d.L);
+    SWEM_LAUNCH_CHECK();
+    // P[u][p][s*Lt + k*L + l] = sum_c q[b][c][p] khat_k[u,s][c][l]
+    GemmShape g{};
+    g.M = d.HW; g.N = d.L; g.K = d.Ck;
+    g.sAm = 1; g.sAk = d.HW; g.sBk = d.L; g.sBn = 1; g.sCm = W2; g.sCn = 1;
+    g.n0 = d.B; g.n1 = d.N; g.n2 = 2;
+    g.bA[0] = (long long)d.Ck * d.HW; g.bA[1] = 0; g.bA[2] = 0;
+    g.bB[0] = (long long)d.N * 2 * d.Ck * d.L; g.bB[1] = 2LL * d.Ck * d.L; g.bB[2] = (long long)d.Ck * d.L;
+    g.bC[0] = (long long)d.N * d.HW * W2; g.bC[1] = (long long)d.HW * W2; g.bC[2] = Lt;
+    if (int rc = launch_gemm(a.qk, khat[k], P + (size_t)k * d.L, g, st)) return rc;
+  }
+  {
+    const long long threads = (long long)U * d.HW * 32;
+    readout_rows_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(P, inv_nq, U, d.N, d.HW, W2, 1.f / d.tau);
+    SWEM_LAUNCH_CHECK();
+  }
+  // mem_out[u][dch][p] = sum_{s,k,l} nu_k[u,s][dch][l] P[u][p][s*Lt + k*L + l]
+  bool first = true;
+  for (int s = 0; s < 2; ++s)
+    for (int k = 0; k < d.n_banks; ++k) {
+      GemmShape g{};
+      g.M = d.Cv; g.N = d.HW; g.K = d.L;
+      g.sAm = d.L; g.sAk = 1; g.sBk = 1; g.sBn = W2; g.sCm = d.HW; g.sCn = 1;
+      g.n0 = d.B; g.n1 = d.N; g.n2 = 1;
+      g.bA[0] = (long long)d.N * 2 * d.Cv * d.L; g.bA[1] = 2LL * d.Cv * d.L; g.bA[2] = 0;
+      g.bB[0] = (long long)d.N * d.HW * W2; g.bB[1] = (long long)d.HW * W2; g.bB[2] = 0;
+      g.bC[0] = (long long)d.N * a.out_channels * d.HW; g.bC[1] = (long long)a.out_channels * d.HW; g.bC[2] = 0;
+      g.accumulate = first ? 0 : 1;
+      first = false;
+      if (int rc = launch_gemm(a.nu[k] + (size_t)s * d.Cv * d.L, P + (size_t)s * Lt + (size_t)k * d.L,
+                               a.out + (size_t)a.mem_channel * d.HW, g, st))
+        return rc;
+    }
+  return launch_perm_inv(P, U, d.HW, Lt, d.topl, a.out, a.out_channels, a.s_channel, st);
+}
+
+}  // namespace swem

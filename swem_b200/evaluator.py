@@ -1,0 +1,77 @@
+"""Per-sequence inference loops on tensors -- the host-side mirror of the reference's
+``SWEMEvaluator.evaluate_davis_seq`` / ``evaluate_ytvos_seq`` (methods/SWEM/swem_evaluator.py:59-148).
+
+Dataset loading, PNG dumping and J&F scoring of the reference's ``BasicEvaluator`` are out of
+scope; these loops take frames and first-frame masks as tensors
+and return the per-frame argmax masks, calling the model only through ``model(mode, ...)``.
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+import torch.nn.functional as F
+
+
+def hard_masks_from_scores(pred_mask: torch.Tensor):
+    """(B,N+1,H,W) scores -> argmax (B,1,H,W) and its int64 one-hot (B,N+1,H,W)."""
+    pred = torch.argmax(pred_mask, dim=1, keepdim=True)
+    idx = torch.arange(pred_mask.shape[1], dtype=pred.dtype, device=pred.device).view(1, -1, 1, 1)
+    return pred, (pred == idx).type_as(pred)
+
+
+@torch.no_grad()
+def evaluate_davis_seq(model, frames: torch.Tensor, init_masks: List[Optional[torch.Tensor]], out_size,
+                       on_frame=None):
+    """frames (B,T,3,h,w); init_masks[0] (B,N+1,H,W) float one-hot.  Returns (preds, pred_scores):
+    lists of T-1 tensors (B,H,W) int64 and (B,N+1,H,W) float.  ``on_frame(i, pred)`` is an optional
+    hook called after frame i's mask is available (used by bench.py for the D2H read)."""
+    b, t, c, h, w = frames.shape
+    mk16, _, s16, _, _ = model('encode_key', frames[:, 0])
+    init_mask = F.interpolate(init_masks[0], size=(h, w), mode='nearest')
+    mv16 = model('encode_value', frames[:, 0], init_mask.float(), s16)
+    model('init', mk16, mv16, init_masks[0])
+    preds, scores = [], []
+    for i in range(1, t):
+        qk16, qv16, s16, s8, s4 = model('encode_key', frames[:, i])
+        context, n = model('match', qk16, qv16)
+        _, pred_mask = model('segment', n, context, s8, s4, None, out_size)
+        scores.append(pred_mask.clone())
+        pred, hard = hard_masks_from_scores(pred_mask)
+        if i < t - 1:
+            soft = F.interpolate(pred_mask, size=(h, w), mode='bilinear', align_corners=False)
+            mv16 = model('encode_value', frames[:, i], soft, s16)
+            model('memorize', qk16, mv16, hard, soft)
+        preds.append(pred[:, 0])
+        if on_frame is not None:
+            on_frame(i, pred[:, 0])
+    return preds, scores
+
+
+@torch.no_grad()
+def evaluate_ytvos_seq(model, frames: torch.Tensor, init_masks: List[Optional[torch.Tensor]], out_size):
+    """Like :func:`evaluate_davis_seq`, but ``init_masks[i]`` (None or (B,N'+1,H,W)) introduces the
+    objects that first appear in frame i; their scores are spliced in before the argmax and the
+    memory grows by N' objects at the next memorize."""
+    b, t, c, h, w = frames.shape
+    mk16, _, s16, _, _ = model('encode_key', frames[:, 0])
+    init_mask = F.interpolate(init_masks[0], size=(h, w), mode='nearest')
+    mv16 = model('encode_value', frames[:, 0], init_mask.float(), s16)
+    model('init', mk16, mv16, init_masks[0])
+    preds = []
+    for i in range(1, t):
+        qk16, qv16, s16, s8, s4 = model('encode_key', frames[:, i])
+        context, n = model('match', qk16, qv16)
+        _, pred_mask = model('segment', n, context, s8, s4, None, out_size)
+        if init_masks[i] is not None:
+            fresh = init_masks[i][:, 1:]
+            taken = fresh.sum(dim=1, keepdim=True).expand_as(pred_mask)
+            pred_mask[taken > 0] = 0
+            pred_mask = torch.cat([pred_mask, fresh], dim=1)
+        pred, hard = hard_masks_from_scores(pred_mask)
+        if i < t - 1:
+            soft = F.interpolate(pred_mask, size=(h, w), mode='bilinear', align_corners=False)
+            mv16 = model('encode_value', frames[:, i], soft, s16)
+            model('memorize', qk16, mv16, hard, soft)
+        preds.append(pred[:, 0])
+    return preds
