@@ -1,0 +1,332 @@
+#!/usr/bin/env python
+"""Headline benchmark: 480p frames/sec of the SWEM per-frame loop on synthetic DAVIS-2017-shaped
+sequences (BASELINE.json configs[1]: 854x480 -> 864x480, 5 objects, ResNet-50 key encoder, Ck=64,
+L=128 bases, 4 EM iterations) plus the roofline of the EM + readout kernels.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+A step = one frame of the reference's hot loop (swem_evaluator.py:73-93): encode_key -> match
+(readout kernels) -> segment -> encode_value -> memorize (EM kernels).  One process per GPU
+(torchrun for N > 1), every rank runs its own sequence (weak scaling, no collective on the hot
+path), timing = CUDA events bracketed by barrier + synchronize, max over ranks.
+
+Prints ONE JSON line (rank 0).  `value`: frames already resident in HBM.  `e2e`: each step's
+frame is copied from pinned host memory and its mask is read back to the host inside the timed
+region.  `roofline`: algorithmic FLOPs of memorize + readout / their CUDA-event time.
+`cpu_baseline` / `--impl reference`: the reference algorithm's CPU port (oracle/) on host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+CFG = dict(keydim=64, valdim=512, n_bases=128, n_iters=4, tau=0.05, topl=64, single_obj=False, backbone='resnet50')
+H, W = 480, 864
+METRIC = '480p frames/sec'
+UNIT = 'frames/s'
+
+
+def workload_config(n_obj, extra=None):
+    c = {'workload': f'davis17_synthetic_{H}x{W}_{n_obj}obj', 'frame': [H, W], 'objects': n_obj,
+         'key_dim': CFG['keydim'], 'value_dim': CFG['valdim'], 'bases': CFG['n_bases'], 'em_iters': CFG['n_iters'],
+         'tau': CFG['tau'], 'topl': CFG['topl'], 'backbone': CFG['backbone'], 'weights': 'random-init seed 0',
+         'sharding': 'one sequence per rank'}
+    c.update(extra or {})
+    return c
+
+
+def hot_path_flops(n_obj, hw, lt):
+    """Algorithmic FLOPs per frame of memorize + readout (SURVEY section 8a / BASELINE.md section 3)."""
+    ck, cv, L, it = CFG['keydim'], CFG['valdim'], CFG['n_bases'], CFG['n_iters']
+    f_mem = 4 * n_obj * hw * L * (ck * (3 * it - 1) + cv)
+    f_read = 4 * n_obj * hw * lt * (ck + cv)
+    return f_mem, f_read
+
+
+def hot_path_bytes(n_obj, hw, lt):
+    ck, cv, L, tl = CFG['keydim'], CFG['valdim'], CFG['n_bases'], CFG['topl']
+    b_mem = 4 * (ck * hw + n_obj * cv * hw + 2 * n_obj * hw + 4 * n_obj * L * (ck + cv + 1))
+    b_read = 4 * (ck * hw + 2 * n_obj * lt * (ck + cv) + n_obj * cv * hw + 2 * n_obj * tl * hw)
+    return b_mem, b_read
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return dict(tflops=d['bf16_tflops_sustained'], tflops_burst=d['bf16_tflops'], hbm=d['hbm_gbs'], source='measured')
+    return dict(tflops=1400.0, tflops_burst=1590.0, hbm=6650.0, source='fallback')
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled every 200 ms during the timed region."""
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.proc, self.path = index, None, None
+
+    def __enter__(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix='.csv')
+            os.close(fd)
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.Q}',
+                                          '--format=csv,noheader,nounits', '-lms', '200'],
+                                         stdout=open(self.path, 'w'), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+        return self
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            time.sleep(0.25)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        out = {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
+        if self.proc is None or not self.path:
+            return out
+        sm, mx, reasons = [], [], set()
+        for line in open(self.path):
+            f = [x.strip() for x in line.split(',')]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        try:
+            os.unlink(self.path)
+        except OSError:
+            pass
+        return out
+
+
+def build_model(device):
+    from swem_b200 import SWEM, make_config
+    torch.manual_seed(0)
+    return SWEM(make_config(**CFG)).eval().to(device)
+
+
+def make_sequence(n_frames, n_obj, seed):
+    from swem_b200.synthetic import davis_sequence
+    return davis_sequence(n_frames, n_obj, seed=seed, size=(H, W))
+
+
+# --------------------------------------------------------------------------------------------
+# CPU port of the reference path (oracle/) -- cpu_baseline leg and --impl reference
+# --------------------------------------------------------------------------------------------
+def cpu_reference_fps(n_obj, steps, warmup, seed=1):
+    """frames/s of the reference algorithm on host cores: oracle core + the same torch networks on CPU."""
+    from oracle import swem_oracle as O
+    from swem_b200 import SWEM, make_config
+    torch.set_num_threads(os.cpu_count() or 1)
+    torch.manual_seed(0)
+    nets = SWEM(make_config(**CFG)).eval()
+    model = O.OracleSWEM(nets, CFG['n_bases'], CFG['n_iters'], CFG['tau'], CFG['topl'], CFG['valdim'])
+    frames, init = make_sequence(1 + warmup + steps + 1, n_obj, seed)
+    from torch.nn import functional as F
+    with torch.no_grad():
+        torch.manual_seed(1234)
+        mk16, _, s16, _, _ = model.encode_key(frames[:, 0])
+        mv16 = model.encode_value(frames[:, 0], F.interpolate(init, size=(H, W), mode='nearest'), s16)
+        model.init(mk16, mv16, init)
+        t0 = None
+        for i in range(1, 1 + warmup + steps):
+            if i == 1 + warmup:
+                t0 = time.perf_counter()
+            qk16, qv16, s16, s8, s4 = model.encode_key(frames[:, i])
+            ctx, n = model.match(qk16, qv16)
+            _, pm = model.segment(n, ctx, s8, s4, (H, W))
+            _, hard = O.one_hot_from_argmax(pm)
+            soft = F.interpolate(pm, size=(H, W), mode='bilinear', align_corners=False)
+            mv16 = model.encode_value(frames[:, i], soft, s16)
+            model.memorize(qk16, mv16, hard, soft)
+        dt = time.perf_counter() - t0
+    return steps / dt, dt, torch.get_num_threads()
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    fps, dt, cores = cpu_reference_fps(args.objects, args.steps, args.warmup)
+    sample = f'{args.steps} frames after {args.warmup} warm-up frames of the same workload, fp32, torch CPU'
+    line = {'impl': 'reference', 'metric': METRIC, 'value': fps, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': 1e3 * dt / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': workload_config(args.objects, {'device': 'host CPU'}),
+            'cpu_baseline': {'value': fps, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
+            'e2e': {'value': fps, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'gpu_launches': 0}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------
+# B200 arm
+# --------------------------------------------------------------------------------------------
+def run_b200(args, rank, world, local_rank):
+    import torch.distributed as dist
+    from swem_b200 import _lib
+    from swem_b200.evaluator import SequenceRunner
+
+    assert torch.cuda.is_available(), 'bench.py needs a CUDA device (no CPU fallback)'
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    _lib.check(_lib.load().swem_device_check(local_rank), 'swem_device_check')
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    K, Wm, n_obj = args.steps, args.warmup, args.objects
+    model = build_model(dev)
+    core = model.swem_core
+    frames, init = make_sequence(1 + Wm + K, n_obj, seed=1 + rank)
+    frames_pinned = frames[0].pin_memory()                       # (T,3,H,W) host
+    init_dev = init.to(dev)
+    hw = (H // 16) * (W // 16)
+
+    # instrumentation kept outside the product: CUDA events around the two C-ABI calls, launch counts
+    ev, launches = {'em': [], 'read': []}, [0]
+    raw_swem, raw_read = core.swem, core.matching_features
+
+    def timed(fn, bucket):
+        def wrapper(*a, **k):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = fn(*a, **k)
+            e1.record()
+            ev[bucket].append((e0, e1))
+            launches[0] += core.launches
+            return r
+        return wrapper
+
+    def run_phase(host_io):
+        """start on frame 0, Wm warm-up steps, then K timed steps; returns (ms, masks checksum)."""
+        runner = SequenceRunner(model, (H, W))
+        stage = torch.empty(1, 3, H, W, device=dev)
+        mask_host = torch.empty(K, H, W, dtype=torch.uint8).pin_memory()
+        resident = None if host_io else frames_pinned.to(dev)
+        torch.manual_seed(1234 + rank)
+        runner.start(frames_pinned[0:1].to(dev), init_dev)
+        for i in range(1, 1 + Wm):
+            runner.step(frames_pinned[i:i + 1].to(dev))
+        for b in ev.values():
+            b.clear()
+        launches[0] = 0
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        with ClockSampler(local_rank) as clk:
+            t0.record()
+            for k in range(K):
+                i = 1 + Wm + k
+                if host_io:
+                    stage.copy_(frames_pinned[i:i + 1], non_blocking=True)
+                    pred = runner.step(stage)
+                    mask_host[k].copy_(pred[0].to(torch.uint8), non_blocking=True)
+                else:
+                    pred = runner.step(resident[i:i + 1])
+            t1.record()
+            barrier()
+        ms = t0.elapsed_time(t1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms, clk.summary(), (int(mask_host.sum()) if host_io else int(pred.sum()))
+
+    core.swem, core.matching_features = timed(raw_swem, 'em'), timed(raw_read, 'read')
+    ms_res, clocks, _ = run_phase(host_io=False)
+    em_ms = statistics.mean(a.elapsed_time(b) for a, b in ev['em'])
+    read_ms = statistics.mean(a.elapsed_time(b) for a, b in ev['read'])
+    n_launch = launches[0]
+    core.swem, core.matching_features = raw_swem, raw_read
+    ms_e2e, clocks_e2e, _ = run_phase(host_io=True)
+
+    fps = world * K / (ms_res / 1e3)
+    fps_e2e = world * K / (ms_e2e / 1e3)
+    peaks = measured_peaks()
+    f_mem, f_read = hot_path_flops(n_obj, hw, 2 * CFG['n_bases'])
+    b_mem, b_read = hot_path_bytes(n_obj, hw, 2 * CFG['n_bases'])
+    hot_s = (em_ms + read_ms) / 1e3
+    achieved = (f_mem + f_read) / hot_s / 1e12
+    lib = _lib.load()
+    import ctypes as C
+    dims = _lib.SwemDims(1, n_obj, CFG['keydim'], CFG['valdim'], hw, CFG['n_bases'], CFG['n_iters'], 2, CFG['topl'], CFG['tau'])
+    family = {'em': 'fused-tcgen05' if lib.swem_em_fused_supported(C.byref(dims)) else 'generic-fp32',
+              'readout': 'fused-tcgen05' if lib.swem_readout_fused_supported(C.byref(dims)) else 'generic-fp32'}
+    line = {
+        'metric': METRIC, 'value': fps, 'unit': UNIT, 'n_gpus': world, 'steps': K, 'warmup': Wm,
+        'ms_per_step': ms_res / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f32 I/O; EM/readout contractions ' + ('f16 hi+lo split, f32 accumulate' if 'fused' in family['em'] else 'f32'),
+        'data': 'synthetic',
+        'config': workload_config(n_obj, {'kernel_family': family, 'l2': 'every step reads a new 5 MB frame and '
+                                          '>230 MB of fp32 weights + activations (> 126 MB L2); no explicit flush',
+                                          'torch_convs': 'cudnn, allow_tf32 default'}),
+        'e2e': {'value': fps_e2e, 'unit': UNIT, 'h2d_bytes_per_step': 3 * H * W * 4, 'd2h_bytes_per_step': H * W,
+                'ms_per_step': ms_e2e / K},
+        'gpu_launches': n_launch,
+        'clocks': {k: clocks[k] for k in ('sm_mhz', 'sm_max_mhz', 'reasons')},
+        'roofline': {'bound': 'tensor', 'achieved': achieved, 'peak': peaks['tflops'], 'unit': 'TFLOP/s',
+                     'frac': achieved / peaks['tflops'], 'traffic': None,
+                     'kernel': 'memorize (EM) + readout, per frame', 'peak_source': peaks['source'] + ' bf16 sustained',
+                     'em_us': em_ms * 1e3, 'readout_us': read_ms * 1e3, 'flops_per_frame': f_mem + f_read,
+                     'hbm_gbs': (b_mem + b_read) / hot_s / 1e9, 'hbm_frac': (b_mem + b_read) / hot_s / 1e9 / peaks['hbm'],
+                     'hot_path_share_of_step': (em_ms + read_ms) / (ms_res / K)},
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        steps = args.cpu_steps
+        fps_cpu, dt, cores = cpu_reference_fps(n_obj, steps, 1)
+        line['cpu_baseline'] = {'value': fps_cpu, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+                                'sample': f'{steps} frames (after 1 warm-up frame) of the same workload, fp32 torch CPU, {dt:.1f} s'}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--objects', type=int, default=5)
+    ap.add_argument('--cpu-steps', type=int, default=3, help='frames of the bounded cpu_baseline sample')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    local_rank = int(os.environ.get('LOCAL_RANK', 0))
+    if args.impl == 'reference':
+        run_reference(args, rank, world)
+    else:
+        run_b200(args, rank, world, local_rank)
+
+
+if __name__ == '__main__':
+    main()

@@ -75,3 +75,34 @@ def evaluate_ytvos_seq(model, frames: torch.Tensor, init_masks: List[Optional[to
             model('memorize', qk16, mv16, hard, soft)
         preds.append(pred[:, 0])
     return preds
+
+
+class SequenceRunner:
+    """Frame-at-a-time form of :func:`evaluate_davis_seq` (same calls in the same order), for callers
+    that stream frames -- bench.py uploads one frame per step and reads one mask back per step."""
+
+    def __init__(self, model, out_size):
+        self.model, self.out_size = model, out_size
+
+    @torch.no_grad()
+    def start(self, frame0: torch.Tensor, init_mask: torch.Tensor) -> None:
+        """frame0 (B,3,h,w); init_mask (B,N+1,H,W) float one-hot: encode + 'init' (frame 0 of the loop)."""
+        h, w = frame0.shape[-2:]
+        mk16, _, s16, _, _ = self.model('encode_key', frame0)
+        m0 = F.interpolate(init_mask, size=(h, w), mode='nearest')
+        mv16 = self.model('encode_value', frame0, m0.float(), s16)
+        self.model('init', mk16, mv16, init_mask)
+
+    @torch.no_grad()
+    def step(self, frame: torch.Tensor, memorize: bool = True) -> torch.Tensor:
+        """One frame: encode_key -> match -> segment -> (encode_value -> memorize).  Returns (B,H,W) int64."""
+        h, w = frame.shape[-2:]
+        qk16, qv16, s16, s8, s4 = self.model('encode_key', frame)
+        context, n = self.model('match', qk16, qv16)
+        _, pred_mask = self.model('segment', n, context, s8, s4, None, self.out_size)
+        pred, hard = hard_masks_from_scores(pred_mask)
+        if memorize:
+            soft = F.interpolate(pred_mask, size=(h, w), mode='bilinear', align_corners=False)
+            mv16 = self.model('encode_value', frame, soft, s16)
+            self.model('memorize', qk16, mv16, hard, soft)
+        return pred[:, 0]
