@@ -88,8 +88,9 @@ def _no_grad_inputs(*tensors):
 
 
 class SWEMCore(nn.Module):
-    # SWEM_PATH_* of the C ABI; tests flip this to exercise both kernel families
-    kernel_path = _lib.PATH_AUTO
+    # SWEM_PATH_* of the C ABI per entry point; tests flip these to exercise both kernel families
+    em_path = _lib.PATH_AUTO
+    readout_path = _lib.PATH_AUTO
 
     def __init__(self, n_bases=256, valdim=512, n_iters=4, tau=0.05, topl=64):
         super().__init__()
@@ -151,13 +152,13 @@ class SWEMCore(nn.Module):
 
         lib = _lib.load()
         dims = _lib.SwemDims(B, N, Ck, Cv, H * W, L, self.n_iters, 0, 0, self.tau)
-        need = lib.swem_em_workspace_bytes(C.byref(dims), self.kernel_path)
+        need = lib.swem_em_workspace_bytes(C.byref(dims), self.em_path)
         ws = _WORKSPACE.get(dev, need)
         args = _lib.SwemEmArgs(dims, x.data_ptr(), v.data_ptr(), masks.data_ptr(),
                                kappa_.data_ptr(), nu_.data_ptr(), zita_.data_ptr(),
                                kappa.data_ptr(), nu.data_ptr(), zita.data_ptr(),
                                z_last.data_ptr() if return_z else None,
-                               ws.data_ptr(), ws.numel(), self.kernel_path)
+                               ws.data_ptr(), ws.numel(), self.em_path)
         with torch.cuda.device(dev):
             rc = lib.swem_em_forward(C.byref(args), torch.cuda.current_stream(dev).cuda_stream)
         _lib.check(rc, 'swem_em_forward')
@@ -197,7 +198,7 @@ class SWEMCore(nn.Module):
 
         lib = _lib.load()
         dims = _lib.SwemDims(B, N, Ck, Cv, H * W, L, 0, len(banks), self.topl, self.tau)
-        need = lib.swem_readout_workspace_bytes(C.byref(dims), self.kernel_path)
+        need = lib.swem_readout_workspace_bytes(C.byref(dims), self.readout_path)
         ws = _WORKSPACE.get(dev, need)
         kap = [_f32c(b['kappa'], 'kappa') for b in banks]
         nus = [_f32c(b['nu'], 'nu') for b in banks]
@@ -205,7 +206,7 @@ class SWEMCore(nn.Module):
                                  (C.c_void_p * 2)(*[k.data_ptr() for k in kap] + [None] * (2 - len(kap))),
                                  (C.c_void_p * 2)(*[n.data_ptr() for n in nus] + [None] * (2 - len(nus))),
                                  feats.data_ptr(), chans, 0, 2 * Cv,
-                                 ws.data_ptr(), ws.numel(), self.kernel_path)
+                                 ws.data_ptr(), ws.numel(), self.readout_path)
         with torch.cuda.device(dev):
             rc = lib.swem_readout_forward(C.byref(args), torch.cuda.current_stream(dev).cuda_stream)
         _lib.check(rc, 'swem_readout_forward')

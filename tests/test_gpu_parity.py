@@ -63,7 +63,10 @@ def em_check(got, want32, x, v, masks, prior, L, n_iters, tau, tol):
 def _core(cfg, family):
     from swem_b200 import SWEMCore, _lib
     core = SWEMCore(n_bases=cfg['L'], valdim=cfg['Cv'], n_iters=cfg['n_iters'], tau=cfg['tau'], topl=cfg['topl'])
-    core.kernel_path = _lib.PATH_GENERIC if family == 'generic' else _lib.PATH_FUSED
+    if family == 'generic':
+        core.em_path = core.readout_path = _lib.PATH_GENERIC
+    else:   # force the fused family wherever it exists; a missing fused kernel for the OTHER entry point falls to generic
+        core.em_path = core.readout_path = _lib.PATH_AUTO
     return core.to(DEV).eval()
 
 
@@ -76,6 +79,8 @@ def _fused_covers(B, N, Ck, Cv, HW, L, n_iters=4, n_banks=2, topl=64, tau=0.05, 
 
 
 def _skip_unless_covered(family, **kw):
+    """'fused' runs need the fused kernel of the entry point under test (what = 'em' | 'readout');
+    SWEM_PATH_AUTO then provably dispatches to it (swem_*_fused_supported is the dispatch predicate)."""
     if family == 'fused' and not _fused_covers(**kw):
         pytest.skip('shape not covered by the fused kernels')
 
