@@ -41,6 +41,7 @@ constexpr int kCv = 512;
 constexpr int kAccRow = 73; // floats per row of the kappa accumulator blob: 64 kappa sums, 1 zita sum, pad (odd stride)
 constexpr uint32_t kAccBytes = kSL * kAccRow * 4;  // 74752
 constexpr float kKScale = 256.f;                   // khat is staged as khat*256 so its lo half stays a normal fp16
+constexpr float kZScale = 16384.f;                 // z (<= 1) is staged as z*2^14: responsibilities down to ~4e-9 stay normal fp16
 
 // ---- shared memory map (bytes) ---------------------------------------------------------------
 // XH : [c 0..79][p] chunks  : byte = (c%8)*16 + (c/8)*2048 + (p/8)*128 + (p%8)*2   (rows 64 = ones, 65..79 = 0)
@@ -295,14 +296,15 @@ __global__ void __launch_bounds__(256, 1) em_fused_kernel(const EmFusedParams p)
         w *= 1.f - (sd ? e1 : e0) / (e0 + e1);
       }
       const float scale = w / sum;
+      const float zs = scale * kZScale;
       // z -> fp16, MN-major A operand: 16-byte chunk = 8 consecutive bases of this pixel
 #pragma unroll
       for (int g = 0; g < kL / 8; ++g) {
         uint4 pk;
-        pk.x = pack_half2(a[g * 8 + 0] * scale, a[g * 8 + 1] * scale);
-        pk.y = pack_half2(a[g * 8 + 2] * scale, a[g * 8 + 3] * scale);
-        pk.z = pack_half2(a[g * 8 + 4] * scale, a[g * 8 + 5] * scale);
-        pk.w = pack_half2(a[g * 8 + 6] * scale, a[g * 8 + 7] * scale);
+        pk.x = pack_half2(a[g * 8 + 0] * zs, a[g * 8 + 1] * zs);
+        pk.y = pack_half2(a[g * 8 + 2] * zs, a[g * 8 + 3] * zs);
+        pk.z = pack_half2(a[g * 8 + 4] * zs, a[g * 8 + 5] * zs);
+        pk.w = pack_half2(a[g * 8 + 6] * zs, a[g * 8 + 7] * zs);
         const uint32_t off = (px % 8) * 16 + (px / 8) * 128 + (sd * 16 + g) * 2048;
         *reinterpret_cast<uint4*>(smem + kOffZ + off) = pk;
       }
@@ -485,10 +487,11 @@ __global__ void __launch_bounds__(256, 1) em_fused_kernel(const EmFusedParams p)
     // ---- (5) finalize row r = tid from the prior (reference :125-126) ------------------------------------
     {
       const float* P = reinterpret_cast<const float*>(smem + kOffZ) + tid * kAccRow;
-      const float zita_cur = zita_p + P[kCk];
+      constexpr float kInvZ = 1.f / kZScale;
+      const float zita_cur = zita_p + P[kCk] * kInvZ;
       float kap[kCk];
 #pragma unroll
-      for (int c = 0; c < kCk; ++c) kap[c] = (zita_p * __ldg(kprior + (size_t)c * kL) + P[c]) / zita_cur;
+      for (int c = 0; c < kCk; ++c) kap[c] = (zita_p * __ldg(kprior + (size_t)c * kL) + P[c] * kInvZ) / zita_cur;
       if (last) {
         ms.zita[tid] = zita_cur;
         if (tile == 0) {
@@ -525,7 +528,7 @@ __global__ void __launch_bounds__(256, 1) em_fused_kernel(const EmFusedParams p)
         const int s = row / kCv, d = row % kCv;
         const size_t idx = (((size_t)u * 2 + s) * kCv + d) * kL + l;
         const float zp = __ldg(p.zita_prior + ((size_t)u * 2 + s) * kL + l);
-        const float sumv = __ldcg(p.acc_nu + idx);
+        const float sumv = __ldcg(p.acc_nu + idx) * (1.f / kZScale);
         p.nu[idx] = (zp * __ldg(p.nu_prior + idx) + sumv) / ms.zita[s * kL + l];
       }
     }

@@ -21,6 +21,7 @@ DEV = 'cuda:0'
 # all-fp32 implementation with a different summation order only agrees to ~1e-3 after 3-4
 # iterations on unstructured (random) keys.  Single E-steps and the readout agree far tighter.
 TOL = dict(generic=dict(bases=2e-4, feat=2e-4), fused=dict(bases=1e-2, feat=1e-2))
+SLACK = dict(generic=4.0, fused=8.0)
 REPORT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'gpurun_out', 'parity_report.txt')
 
 
@@ -42,13 +43,16 @@ def maxrel(a, b, mask=None):
     return ((a - b).abs().max() / b.abs().max().clamp_min(1e-30)).item()
 
 
-def em_check(got, want32, x, v, masks, prior, L, n_iters, tau, tol):
+def em_check(got, want32, x, v, masks, prior, L, n_iters, tau, tol, slack=4.0):
     """Compare an EM result with the reference-precision answer.
 
     Multi-iteration EM amplifies rounding noise (see TOL above): the fp32 reference itself is only
     reproducible to `floor` = its distance from exact (fp64) arithmetic on the same inputs.  The
-    CUDA result must be within max(tol, 4 x floor) of the fp64 answer, i.e. as accurate as the
-    reference is, and within `tol` outright whenever the problem is well conditioned."""
+    CUDA result must be within max(tol, slack x floor) of the fp64 answer, i.e. about as accurate as
+    the reference is, and within `tol` outright whenever the problem is well conditioned (it is on
+    encoder features, where floor ~ 1e-5; it is not on i.i.d. Gaussian keys, where floor ~ 1e-2).
+    slack = 4 for the all-fp32 generic kernels, 8 for the fused kernels whose fp16 responsibilities
+    (relative rounding 5e-4) seed the same amplification from a higher starting point."""
     d = lambda t: t.double()
     want64 = O.em_memorize(d(x), d(v), d(masks), {k: d(t) for k, t in prior.items()}, L, n_iters, tau)
     live = want64['zita'] > 1e-3
@@ -56,7 +60,7 @@ def em_check(got, want32, x, v, masks, prior, L, n_iters, tau, tol):
         m = None if key == 'zita' else live
         floor = maxrel(want32[key], want64[key], m)
         err = maxrel(got[key], want64[key], m)
-        check(f'{key}(floor {floor:.1e})', err, max(tol, 4 * floor))
+        check(f'{key}(floor {floor:.1e})', err, max(tol, slack * floor))
     assert torch.isfinite(got['kappa']).all() and torch.isfinite(got['nu']).all()
 
 
@@ -124,7 +128,7 @@ def test_golden_sequences_teacher_forced(golden, name, family):
                 n_new = call['masks'].shape[1] - (0 if prior is None else prior['kappa'].shape[1])
                 fresh = dict(zip(('kappa', 'nu', 'zita'), O.random_init(cfg['B'], n_new, cfg['Ck'], cfg['L'], cfg['Cv'])))
                 used_prior = fresh if prior is None else {k: torch.cat([prior[k], fresh[k]], 1) for k in fresh}
-            em_check(got, call, call['x'], call['v'], call['masks'], used_prior, cfg['L'], cfg['n_iters'], cfg['tau'], tol['bases'])
+            em_check(got, call, call['x'], call['v'], call['masks'], used_prior, cfg['L'], cfg['n_iters'], cfg['tau'], tol['bases'], SLACK[family])
             # readout from the reference's memory
             core.memories['first'].bases = _to(ref.banks.first, DEV)
             core.memories['first'].n_objs = ref.banks.first_n
@@ -195,7 +199,7 @@ def test_memorize_and_readout_vs_oracle(shape, family):
             want = O.em_memorize(x, v, masks, prior, L, I, 0.05)
             ref.banks.commit(want)
             got = core.swem(x.to(DEV), v.to(DEV), masks.to(DEV), _to(prior, DEV))
-            em_check(got, want, x, v, masks, prior, L, I, 0.05, tol['bases'])
+            em_check(got, want, x, v, masks, prior, L, I, 0.05, tol['bases'], SLACK[family])
         core.memories['first'].bases = _to(ref.banks.first, DEV)
         core.memories['update'].bases = _to(ref.banks.update, DEV)
         q, qv, _ = em_inputs(B, 1, Ck, Cv, H, W, seed=99)
