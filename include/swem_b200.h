@@ -122,6 +122,10 @@ int         swem_device_check(int device);   /* SWEM_OK iff `device` is compute 
 /* 1 if the fused tcgen05 kernels cover these dims (what SWEM_PATH_AUTO would pick), else 0.     */
 int         swem_em_fused_supported(const SwemDims* dims);
 int         swem_readout_fused_supported(const SwemDims* dims);
+/* Diagnostics: install (dev != NULL) or remove (NULL) a device buffer of >= 256 int64.  While
+ * installed, CTA 0 of the fused EM kernel writes buf[0] = number of phase stamps and buf[1..] =
+ * %globaltimer nanoseconds at its phase boundaries (tools/profile_phases.py prints them).       */
+int         swem_set_profile_buffer(void* dev, size_t bytes);
 /* number of kernel launches the last call on this thread issued (for bench.py's gpu_launches)   */
 int         swem_last_launch_count(void);
 

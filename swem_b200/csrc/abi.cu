@@ -87,6 +87,15 @@ int swem_device_check(int device) {
   return SWEM_OK;
 }
 
+int swem_set_profile_buffer(void* dev, size_t bytes) {
+  if (dev != nullptr && bytes < 256 * sizeof(long long)) {
+    set_error("profile buffer needs >= 2048 bytes");
+    return SWEM_ERR_INVALID_ARG;
+  }
+  set_profile_buffer(dev);
+  return SWEM_OK;
+}
+
 int swem_em_fused_supported(const SwemDims* d) { return d && fused_em_supported(*d) ? 1 : 0; }
 int swem_readout_fused_supported(const SwemDims* d) { return d && fused_readout_supported(*d) ? 1 : 0; }
 

@@ -1,0 +1,36 @@
+// Device helpers shared by the fused tcgen05 kernels (fused_em.cu, fused_readout.cu).
+#pragma once
+
+#include <cuda_fp16.h>
+#include <stdint.h>
+
+namespace swem {
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// Wait until all T tiles of this unit have arrived at `counter`.  Bounded: a protocol bug aborts
+// the kernel with an error instead of hanging the GPU.
+__device__ __forceinline__ bool wait_counter(const unsigned* counter, unsigned target) {
+  for (unsigned i = 0; i < (1u << 24); ++i) {
+    if (ld_acquire_u32(counter) >= target) return true;
+    __nanosleep(32);
+  }
+  return false;
+}
+
+__device__ __forceinline__ long long global_ns() {
+  long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void split_half(float v, __half& hi, __half& lo) {
+  hi = __float2half_rn(v);
+  lo = __float2half_rn(v - __half2float(hi));
+}
+
+
+}  // namespace swem

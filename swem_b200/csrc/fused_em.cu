@@ -27,6 +27,7 @@
 
 #include "common.cuh"
 #include "tc05.cuh"
+#include "fused_common.cuh"
 
 namespace swem {
 
@@ -97,30 +98,16 @@ struct EmFusedParams {
   float* acc_nu;       // [U][2][512][128], zeroed before launch
   unsigned* counters;  // [U][n_iters + 1], zeroed before launch
   int* status;         // device error word (0 = ok)
+  long long* prof;     // optional: phase time stamps (ns) of CTA 0, see swem_set_profile_buffer
   int N, HW, T, n_iters, u0;
   float c1s;           // log2(e) / (tau * kKScale): scales staged logits into exp2 arguments
 };
 
-__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
-  unsigned v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-
-// Wait until all T tiles of this unit have arrived at `counter`.  Bounded: a protocol bug aborts
-// the kernel with an error instead of hanging the GPU.
-__device__ __forceinline__ bool wait_counter(const unsigned* counter, unsigned target) {
-  for (unsigned i = 0; i < (1u << 24); ++i) {
-    if (ld_acquire_u32(counter) >= target) return true;
-    __nanosleep(32);
-  }
-  return false;
-}
-
-__device__ __forceinline__ void split_half(float v, __half& hi, __half& lo) {
-  hi = __float2half_rn(v);
-  lo = __float2half_rn(v - __half2float(hi));
-}
+// phase stamp: CTA 0 / thread 0 only, when a profile buffer is installed
+#define EM_STAMP()                                                   \
+  do {                                                               \
+    if (p.prof != nullptr && blockIdx.x == 0 && tid == 0 && n_stamp < 250) p.prof[1 + n_stamp++] = global_ns(); \
+  } while (0)
 
 __global__ void __launch_bounds__(256, 1) em_fused_kernel(const EmFusedParams p) {
   using namespace em;
@@ -134,6 +121,8 @@ __global__ void __launch_bounds__(256, 1) em_fused_kernel(const EmFusedParams p)
   const int HW = p.HW;
   const int I = p.n_iters;
   const uint32_t sbase = smem_u32(smem);
+  int n_stamp = 0;
+  EM_STAMP();
 
   // ---- one-time setup -------------------------------------------------------------------------
   if (warp == 0) tmem_alloc(&ms.tmem_base, 512);
@@ -224,6 +213,7 @@ __global__ void __launch_bounds__(256, 1) em_fused_kernel(const EmFusedParams p)
     stage_khat(kap);
   }
   bool failed = false;               // block-uniform
+  EM_STAMP();                        // setup done
 
   const uint32_t idesc_e = make_idesc(128, 256, kFmtF16, kFmtF16, kMajorMN, kMajorK);
   const uint32_t idesc_m80 = make_idesc(128, 80, kFmtF16, kFmtF16, kMajorMN, kMajorK);
@@ -255,6 +245,7 @@ __global__ void __launch_bounds__(256, 1) em_fused_kernel(const EmFusedParams p)
     ok = ok && mbar_wait(&ms.bar_mma, ph_mma);
     ph_mma ^= 1;
     tc_fence_after_sync();
+    EM_STAMP();                      // logits GEMM done
 
     // ---- (2) epilogue: thread <-> (pixel px, side sd) ----------------------------------------------
     {
@@ -320,6 +311,7 @@ __global__ void __launch_bounds__(256, 1) em_fused_kernel(const EmFusedParams p)
     __syncthreads();
     tc_fence_after_sync();
 
+    EM_STAMP();                      // epilogue done
     // ---- (3) M-step GEMM: [kappa sums | zita sum] per side ------------------------------------------
     if (tid == 0) {
 #pragma unroll
@@ -340,6 +332,7 @@ __global__ void __launch_bounds__(256, 1) em_fused_kernel(const EmFusedParams p)
     ph_mma ^= 1;
     tc_fence_after_sync();
 
+    EM_STAMP();                      // M GEMM done
     // partial of this tile, row r = tid: 64 kappa sums + zita sum (kept in registers for now)
     float part[kCk + 1];
     {
@@ -374,20 +367,28 @@ __global__ void __launch_bounds__(256, 1) em_fused_kernel(const EmFusedParams p)
             ok = ok && mbar_wait(&ms.bar_stage[st], ph_stage[st]);
             ph_stage[st] ^= 1;
           }
-          // V chunk [256 d][32 px] fp32 -> fp16 K-major B operand.  thread <-> value channel row
+          // V chunk [256 d][32 px] fp32 -> fp16 K-major B operand.  A warp reads 4 rows x 128 B per
+          // instruction (lane -> row lane/8, pixels 4*(lane%8)..+3), 8 instructions cover its 32 rows.
           {
-            const int d = half * 256 + tid;
-            const float* vrow = p.v + ((size_t)u * kCv + d) * HW;
             uint8_t* stage = smem + kOffVS + st * kVStage;
+            const int px4 = (lane & 7) * 4;
+            const int pxg = p0 + ch * 32 + px4;
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              __align__(16) __half h[8];
-#pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                const int px = p0 + ch * 32 + g * 8 + e;
-                h[e] = __float2half_rn(px < HW ? __ldg(vrow + px) : 0.f);
+            for (int j = 0; j < 8; ++j) {
+              const int dl = warp * 32 + j * 4 + (lane >> 3);          // row within this half
+              const float* src = p.v + ((size_t)u * kCv + half * 256 + dl) * HW + pxg;
+              float f0 = 0.f, f1 = 0.f, f2 = 0.f, f3 = 0.f;
+              if (pxg + 3 < HW) {
+                f0 = __ldg(src); f1 = __ldg(src + 1); f2 = __ldg(src + 2); f3 = __ldg(src + 3);
+              } else {
+                if (pxg < HW) f0 = __ldg(src);
+                if (pxg + 1 < HW) f1 = __ldg(src + 1);
+                if (pxg + 2 < HW) f2 = __ldg(src + 2);
               }
-              *reinterpret_cast<uint4*>(stage + (tid % 8) * 16 + (tid / 8) * 128 + g * 4096) = *reinterpret_cast<uint4*>(h);
+              uint2 pk;
+              pk.x = pack_half2(f0, f1);
+              pk.y = pack_half2(f2, f3);
+              *reinterpret_cast<uint2*>(stage + (dl % 8) * 16 + (dl / 8) * 128 + (px4 / 8) * 4096 + (px4 % 8) * 2) = pk;
             }
           }
           fence_proxy_async_smem();
@@ -413,6 +414,7 @@ __global__ void __launch_bounds__(256, 1) em_fused_kernel(const EmFusedParams p)
         ok = ok && mbar_wait(&ms.bar_mma, ph_mma);
         ph_mma ^= 1;
         tc_fence_after_sync();
+        EM_STAMP();                  // nu pass GEMMs done
         // drain: TMEM [side][128 l][256 d] -> smem [side][64 d][128 l] -> bulk reduce-add into acc_nu
         {
           const int sd = warp >> 2, l = (warp & 3) * 32 + lane;
@@ -445,6 +447,7 @@ __global__ void __launch_bounds__(256, 1) em_fused_kernel(const EmFusedParams p)
         tc_fence_before_sync();
         __syncthreads();
         tc_fence_after_sync();
+        EM_STAMP();                  // nu pass drained
       }
       // drain the stage barriers' outstanding phases is unnecessary: the kernel ends after this phase
     }
@@ -462,15 +465,21 @@ __global__ void __launch_bounds__(256, 1) em_fused_kernel(const EmFusedParams p)
     __syncthreads();
     float* acc = p.acc_k + ((size_t)(u * I + it)) * (kSL * kAccRow);
     unsigned* counter = p.counters + (size_t)u * (I + 1) + it;
+    // prior row of this thread's basis: issue the 64 loads now so they fly during the cross-tile wait
+    float kpr[kCk];
+#pragma unroll
+    for (int c = 0; c < kCk; ++c) kpr[c] = __ldg(kprior + (size_t)c * kL);
     if (tid == 0) {
       asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(acc),
                    "r"(sbase + kOffZ), "r"(kAccBytes)
                    : "memory");
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+      EM_STAMP();                    // partial reduce-added
       __threadfence();
       atomicAdd(counter, 1u);
       const bool arrived = wait_counter(counter, (unsigned)p.T);
+      EM_STAMP();                    // all tiles arrived
       if (!arrived) ms.abort_flag = 1;
       __threadfence();
       asm volatile("fence.proxy.async;" ::: "memory");
@@ -484,6 +493,7 @@ __global__ void __launch_bounds__(256, 1) em_fused_kernel(const EmFusedParams p)
       failed = true;
       break;
     }
+    EM_STAMP();                      // total loaded
     // ---- (5) finalize row r = tid from the prior (reference :125-126) ------------------------------------
     {
       const float* P = reinterpret_cast<const float*>(smem + kOffZ) + tid * kAccRow;
@@ -491,7 +501,7 @@ __global__ void __launch_bounds__(256, 1) em_fused_kernel(const EmFusedParams p)
       const float zita_cur = zita_p + P[kCk] * kInvZ;
       float kap[kCk];
 #pragma unroll
-      for (int c = 0; c < kCk; ++c) kap[c] = (zita_p * __ldg(kprior + (size_t)c * kL) + P[c] * kInvZ) / zita_cur;
+      for (int c = 0; c < kCk; ++c) kap[c] = (zita_p * kpr[c] + P[c] * kInvZ) / zita_cur;
       if (last) {
         ms.zita[tid] = zita_cur;
         if (tile == 0) {
@@ -505,6 +515,7 @@ __global__ void __launch_bounds__(256, 1) em_fused_kernel(const EmFusedParams p)
       }
     }
     __syncthreads();
+    EM_STAMP();                      // finalize done
   }
 
   // ---- nu: all tiles have reduce-added their partials; normalise a slice (reference :164-165) -------------
@@ -535,6 +546,8 @@ __global__ void __launch_bounds__(256, 1) em_fused_kernel(const EmFusedParams p)
   }
   tc_fence_before_sync();
   __syncthreads();
+  EM_STAMP();                        // nu normalised
+  if (p.prof != nullptr && blockIdx.x == 0 && tid == 0) p.prof[0] = n_stamp;
   if (warp == 0) tmem_dealloc(tmem, 512);
   if (failed || ms.abort_flag) __trap();   // surface a protocol time-out as a CUDA error, never as silent garbage
 }
@@ -542,6 +555,9 @@ __global__ void __launch_bounds__(256, 1) em_fused_kernel(const EmFusedParams p)
 // ------------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------------
+static long long* g_prof = nullptr;
+void set_profile_buffer(void* dev) { g_prof = static_cast<long long*>(dev); }
+
 static int sm_count() {
   static int n = 0;
   if (n == 0) {
@@ -591,6 +607,7 @@ int fused_em_forward(const SwemEmArgs& a, cudaStream_t st) {
   p.acc_k = acc_k; p.acc_nu = acc_nu; p.counters = counters; p.status = status;
   p.N = d.N; p.HW = d.HW; p.T = T; p.n_iters = d.n_iters;
   p.c1s = kLog2e / (d.tau * em::kKScale);
+  p.prof = g_prof;
   // all CTAs of a launch spin on each other: keep every launch co-resident (<= 1 CTA per SM)
   const int units_per_launch = sm_count() / T > 0 ? sm_count() / T : 1;
   for (int u0 = 0; u0 < U; u0 += units_per_launch) {

@@ -1,0 +1,411 @@
+// Fused readout (attention from query pixels to the memory bases) for sm_100a: tcgen05 + TMEM + TMA.
+//
+// Covers Ck = 64, L = 128, Cv = 512, 1 or 2 banks, any HW / B*N.  Reference semantics:
+// methods/SWEM/modules.py:278-293 (matching), :232-276 (get_affinity), :198-208 (perm_inv_feat).
+//
+// Two launches + the shared top-l kernel:
+//   1. readout_prep_kernel: memory banks -> tensor-core operand blobs in global memory:
+//        khat = l2norm(kappa)*256 as fp16 hi/lo K-major B operands per (unit, side)   (:283)
+//        nu as fp16 hi/lo K-major B operands per (unit, value-channel half, 16-column k-step)
+//      (blobs are byte-for-byte the shared-memory images, so the main kernel stages them with
+//       plain cp.async.bulk copies)
+//   2. readout_fused_kernel: one CTA per (unit, 128-pixel tile, value-channel half):
+//        scores a[p, j] = q_p . khat_j         24 x tcgen05.mma M128 N256 K16 (hi/lo split, 3 terms)
+//        t = a / (||q_p|| + eps) (:282), joint max over both sides (:248-249), E = exp((t - max)/tau)
+//        E -> fp16 written back INTO TMEM over the scores (packed, 2 per column) = A operand of
+//        mem_out[p, d] = sum_j E[p, j] nu[d, j]  64..128 x tcgen05.mma (A from TMEM, B = nu hi/lo via an
+//        8-stage TMA ring), then divided by the row sum of the rounded E (:265, :272-273)
+//        The un-normalised E (fp32) also goes to a scratch buffer for
+//   3. perm_inv_kernel (generic.cu): sorted top-l running sums -> S channels (:198-208)
+// mem_out lands in channels [mem_channel, +Cv) and S in [s_channel, +2*topl) of the caller's
+// concat buffer (:291), so no torch.cat of those pieces is needed.
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+#include "fused_common.cuh"
+#include "tc05.cuh"
+
+namespace swem {
+
+using namespace tc05;
+
+namespace ro {
+constexpr int kTP = 128;
+constexpr int kCk = 64;
+constexpr int kL = 128;
+constexpr int kCv = 512;
+constexpr int kDH = 256;                 // value channels per CTA
+constexpr float kKScale = 256.f;         // khat staged as khat*256 (lo half stays normal fp16)
+constexpr float kEScale = 1024.f;        // E (<= 1) staged as E*2^10
+constexpr int kStages = 8;
+constexpr uint32_t kStageBytes = 16384;  // one k-step of nu: [256 d][16 j] fp16 hi (8 KB) + lo (8 KB)
+
+// shared memory map
+constexpr uint32_t kOffQH = 0;                         // [c 64][p 128] chunks, 16 KB (MN-major A: SBO 128, LBO 2048)
+constexpr uint32_t kOffQL = kOffQH + 8 * 2048;
+constexpr uint32_t kOffKB = kOffQL + 8 * 2048;         // 2 sides x (hi 32 KB + lo 32 KB) khat blobs; later the nu ring
+constexpr uint32_t kKBSide = 65536;
+constexpr uint32_t kOffRing = kOffKB;                  // 8 x 16 KB, aliases the khat blobs once the scores are done
+constexpr uint32_t kOffMisc = kOffKB + 2 * kKBSide;
+struct Misc {
+  float inv_nq[kTP];
+  float ex_max[2][kTP];
+  float ex_sum[2][kTP];
+  uint64_t bar_k[2];
+  uint64_t bar_mma;
+  uint64_t bar_full[kStages];
+  uint64_t bar_empty[kStages];
+  uint32_t tmem_base;
+  int pad;
+};
+constexpr uint32_t kSmemBytes = kOffMisc + sizeof(Misc) + 128;
+static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
+}  // namespace ro
+
+struct ReadoutFusedParams {
+  const float* qk;        // [B][64][HW]
+  const uint8_t* kblob;   // [U][2 sides][hi | lo] each n_banks*16 KB
+  const uint8_t* vblob;   // [U][2 halves][KS2 k-steps][16 KB]
+  float* out;             // [U][out_channels][HW]
+  float* escratch;        // [U][HW][2*Lt] fp32 un-normalised E (for the top-l feature)
+  int N, HW, T, n_banks, out_channels, mem_channel;
+  float c1s;              // log2(e) / (tau * kKScale)
+};
+
+// ---- prep: banks -> operand blobs ------------------------------------------------------------------
+// khat blob of (u, s): K-major rows j = bank*128 + l, byte = (j%8)*16 + (j/8)*128 + (c/8)*LBO + (c%8)*2,
+// LBO = n_banks*2048; hi plane then lo plane.
+__global__ void readout_prep_kappa_kernel(const float* __restrict__ k0, const float* __restrict__ k1, int U, int n_banks,
+                                          uint8_t* __restrict__ kblob) {
+  using namespace ro;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;       // (u, s, bank, l)
+  if (i >= U * 2 * n_banks * kL) return;
+  const int l = i % kL, bank = (i / kL) % n_banks, s = (i / (kL * n_banks)) % 2, u = i / (kL * n_banks * 2);
+  const float* kp = (bank ? k1 : k0) + (((size_t)u * 2 + s) * kCk) * kL + l;
+  float v[kCk];
+  float ss = 0.f;
+#pragma unroll
+  for (int c = 0; c < kCk; ++c) {
+    v[c] = __ldg(kp + (size_t)c * kL);
+    ss = fmaf(v[c], v[c], ss);
+  }
+  const float sc = kKScale / (sqrtf(ss) + kEpsNorm);
+  const uint32_t plane = n_banks * 16384;                     // bytes of one (hi or lo) plane
+  const uint32_t lbo = n_banks * 2048;
+  uint8_t* base = kblob + ((size_t)u * 2 + s) * 2 * plane;
+  const int j = bank * kL + l;
+#pragma unroll
+  for (int g = 0; g < 8; ++g) {
+    __align__(16) __half hi[8];
+    __align__(16) __half lo[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) split_half(v[g * 8 + e] * sc, hi[e], lo[e]);
+    const uint32_t off = (j % 8) * 16 + (j / 8) * 128 + g * lbo;
+    *reinterpret_cast<uint4*>(base + off) = *reinterpret_cast<uint4*>(hi);
+    *reinterpret_cast<uint4*>(base + plane + off) = *reinterpret_cast<uint4*>(lo);
+  }
+}
+
+// nu blob of (u, half h, k-step kk): rows d (256), 16 columns j = 16*kk..; byte = (d%8)*16 + (d/8)*128 +
+// (jj/8)*4096 + (jj%8)*2; hi plane (8 KB) then lo plane.  Column order j = s*Lt + bank*128 + l (:272, :295-306).
+__global__ void readout_prep_nu_kernel(const float* __restrict__ n0, const float* __restrict__ n1, int U, int n_banks,
+                                       uint8_t* __restrict__ vblob) {
+  using namespace ro;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // (u, s, bank, d, l-group of 8)
+  const long long total = (long long)U * 2 * n_banks * kCv * (kL / 8);
+  if (i >= total) return;
+  const int lg = (int)(i % (kL / 8));
+  const int d = (int)((i / (kL / 8)) % kCv);
+  const int bank = (int)((i / ((kL / 8) * kCv)) % n_banks);
+  const int s = (int)((i / ((long long)(kL / 8) * kCv * n_banks)) % 2);
+  const int u = (int)(i / ((long long)(kL / 8) * kCv * n_banks * 2));
+  const float4* src = reinterpret_cast<const float4*>((bank ? n1 : n0) + (((size_t)u * 2 + s) * kCv + d) * kL + lg * 8);
+  const float4 a = __ldg(src), b = __ldg(src + 1);
+  const float vals[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+  __align__(16) __half hi[8];
+  __align__(16) __half lo[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) split_half(vals[e], hi[e], lo[e]);
+  const int Lt = n_banks * kL;
+  const int j = s * Lt + bank * kL + lg * 8;
+  const int kk = j / 16, jg = (j / 8) % 2;
+  const int h = d / kDH, dl = d % kDH;
+  const int ks2 = 2 * Lt / 16;
+  uint8_t* base = vblob + (((size_t)u * 2 + h) * ks2 + kk) * kStageBytes;
+  const uint32_t off = (dl % 8) * 16 + (dl / 8) * 128 + jg * 4096;
+  *reinterpret_cast<uint4*>(base + off) = *reinterpret_cast<uint4*>(hi);
+  *reinterpret_cast<uint4*>(base + 8192 + off) = *reinterpret_cast<uint4*>(lo);
+}
+
+// ---- main kernel --------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256, 1) readout_fused_kernel(const ReadoutFusedParams p) {
+  using namespace ro;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  Misc& ms = *reinterpret_cast<Misc*>(smem + kOffMisc);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int h = blockIdx.x & 1;
+  const int tile = (blockIdx.x >> 1) % p.T;
+  const int u = (blockIdx.x >> 1) / p.T;
+  const int b = u / p.N;
+  const int p0 = tile * kTP;
+  const int HW = p.HW;
+  const int nb = p.n_banks;
+  const int Lt = nb * kL;                 // columns per side
+  const int ks_side = Lt / 16;            // PV k-steps per side
+  const int ks2 = 2 * ks_side;
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t kplane = nb * 16384;     // bytes of one khat plane (hi or lo) of one side
+
+  if (warp == 0) tmem_alloc(&ms.tmem_base, 512);
+  if (tid == 0) {
+    mbar_init(&ms.bar_k[0], 1);
+    mbar_init(&ms.bar_k[1], 1);
+    mbar_init(&ms.bar_mma, 1);
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&ms.bar_full[i], 1);
+      mbar_init(&ms.bar_empty[i], 1);
+    }
+    fence_mbar_init();
+    // khat blobs of both sides (hi + lo planes are contiguous): two bulk copies
+    for (int s = 0; s < 2; ++s) {
+      mbar_expect_tx(&ms.bar_k[s], 2 * kplane);
+      bulk_g2s(smem + kOffKB + s * kKBSide, p.kblob + ((size_t)u * 2 + s) * 2 * kplane, 2 * kplane, &ms.bar_k[s]);
+    }
+  }
+  // query tile: norms (thread <-> pixel) and fp16 hi/lo MN-major A operand
+  if (tid < kTP) {
+    const int px = p0 + tid;
+    float ss = 0.f;
+    if (px < HW) {
+      const float* qp = p.qk + (size_t)b * kCk * HW + px;
+#pragma unroll 8
+      for (int c = 0; c < kCk; ++c) {
+        const float t = __ldg(qp + (size_t)c * HW);
+        ss = fmaf(t, t, ss);
+      }
+    }
+    ms.inv_nq[tid] = 1.f / (sqrtf(ss) + kEpsNorm);
+  }
+  {
+    const int c = tid >> 2;
+    const float* qrow = p.qk + ((size_t)b * kCk + c) * HW;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int pg = (tid & 3) * 4 + j;
+      __align__(16) __half hi[8];
+      __align__(16) __half lo[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int px = p0 + pg * 8 + e;
+        split_half(px < HW ? __ldg(qrow + px) : 0.f, hi[e], lo[e]);
+      }
+      const uint32_t off = (c % 8) * 16 + (c / 8) * 2048 + pg * 128;
+      *reinterpret_cast<uint4*>(smem + kOffQH + off) = *reinterpret_cast<uint4*>(hi);
+      *reinterpret_cast<uint4*>(smem + kOffQL + off) = *reinterpret_cast<uint4*>(lo);
+    }
+  }
+  fence_proxy_async_smem();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = ms.tmem_base;
+  bool ok = true;
+
+  // ---- scores: side s -> TMEM columns [256 s, 256 s + Lt) ---------------------------------------------
+  if (tid == 0) {
+    const uint32_t idesc = make_idesc(128, Lt, kFmtF16, kFmtF16, kMajorMN, kMajorK);
+    const uint32_t lbo_k = nb * 2048;
+    for (int s = 0; s < 2; ++s) {
+      ok = mbar_wait(&ms.bar_k[s], 0) && ok;
+      const uint32_t kb = sbase + kOffKB + s * kKBSide;
+#pragma unroll
+      for (int term = 0; term < 3; ++term) {
+        const uint32_t qa = sbase + (term == 2 ? kOffQL : kOffQH);
+        const uint32_t kbt = kb + (term == 1 ? kplane : 0);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          const uint64_t ad = make_sdesc(qa + kk * 2 * 2048, /*lbo*/ 2048, /*sbo*/ 128);
+          const uint64_t bd = make_sdesc(kbt + kk * 2 * lbo_k, /*lbo*/ lbo_k, /*sbo*/ 128);
+          mma_f16_ss(tmem + s * 256, ad, bd, idesc, (term | kk) ? 1u : 0u);
+        }
+      }
+    }
+    mma_commit(&ms.bar_mma);
+  }
+  ok = mbar_wait(&ms.bar_mma, 0) && ok;
+  tc_fence_after_sync();
+
+  // the khat blobs are dead: start streaming nu k-steps into the ring (aliases them)
+  const uint8_t* vsrc = p.vblob + ((size_t)u * 2 + h) * ks2 * kStageBytes;
+  if (tid == 0) {
+    fence_proxy_async_smem();
+    for (int kk = 0; kk < kStages && kk < ks2; ++kk) {
+      mbar_expect_tx(&ms.bar_full[kk], kStageBytes);
+      bulk_g2s(smem + kOffRing + kk * kStageBytes, vsrc + (size_t)kk * kStageBytes, kStageBytes, &ms.bar_full[kk]);
+    }
+  }
+
+  // ---- softmax epilogue: thread <-> (pixel px, side sd) ------------------------------------------------
+  const int px = (warp & 3) * 32 + lane, sd = warp >> 2;
+  const uint32_t lane_base = (warp & 3) * 32;
+  float inv_total;
+  {
+    const int nchunk = Lt / 32;
+    float mx = -3.0e38f;
+    for (int q = 0; q < nchunk; ++q) {
+      uint32_t r[32];
+      tmem_ld32(tmem_addr(tmem, lane_base, sd * 256 + q * 32), r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(r[j]));
+    }
+    ms.ex_max[sd][px] = mx;
+    __syncthreads();
+    const float gm = fmaxf(ms.ex_max[0][px], ms.ex_max[1][px]);     // inv_nq > 0: max of a*inv = inv * max a
+    const float cw = ms.inv_nq[px] * p.c1s;
+    float sum = 0.f;
+    const bool write_e = (h == 0) && (p0 + px < HW);
+    float* erow = p.escratch + ((size_t)u * HW + p0 + px) * (2 * Lt) + sd * Lt;
+    for (int q = 0; q < nchunk; ++q) {
+      uint32_t r[32];
+      tmem_ld32(tmem_addr(tmem, lane_base, sd * 256 + q * 32), r);
+      tmem_ld_wait();
+      uint32_t pk[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float e0 = exp2f((__uint_as_float(r[2 * j]) - gm) * cw);
+        const float e1 = exp2f((__uint_as_float(r[2 * j + 1]) - gm) * cw);
+        const __half2 hh = __floats2half2_rn(e0 * kEScale, e1 * kEScale);
+        const float2 back = __half22float2(hh);
+        sum += back.x + back.y;                                      // row sum of the ROUNDED operand
+        pk[j] = *reinterpret_cast<const uint32_t*>(&hh);
+        r[2 * j] = __float_as_uint(e0);
+        r[2 * j + 1] = __float_as_uint(e1);
+      }
+      if (write_e) {
+        float4* dst = reinterpret_cast<float4*>(erow + q * 32);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          dst[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                               __uint_as_float(r[4 * j + 3]));
+      }
+      // packed E overwrites columns this thread has already consumed: [256 sd + 16 q, +16)
+      tmem_st16(tmem_addr(tmem, lane_base, sd * 256 + q * 16), pk);
+    }
+    tmem_st_wait();
+    ms.ex_sum[sd][px] = sum;
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    inv_total = 1.f / (ms.ex_sum[0][px] + ms.ex_sum[1][px]);
+  }
+
+  // ---- mem_out = E nu^T: A from TMEM (packed E), B from the ring; accumulators at columns 128.. and 384.. ----
+  if (tid == 0) {
+    const uint32_t idesc = make_idesc(128, 128, kFmtF16, kFmtF16, kMajorK, kMajorK);
+    uint32_t ph_full[kStages], ph_empty[kStages];
+    for (int i = 0; i < kStages; ++i) ph_full[i] = ph_empty[i] = 0;
+    for (int kk = 0; kk < ks2; ++kk) {
+      const int st = kk % kStages;
+      ok = mbar_wait(&ms.bar_full[st], ph_full[st]) && ok;
+      ph_full[st] ^= 1;
+      tc_fence_after_sync();
+      const uint32_t a_tmem = tmem + (kk / ks_side) * 256 + (kk % ks_side) * 8;
+      const uint32_t vb = sbase + kOffRing + st * kStageBytes;
+#pragma unroll
+      for (int term = 0; term < 2; ++term)
+#pragma unroll
+        for (int nh = 0; nh < 2; ++nh) {
+          const uint64_t bd = make_sdesc(vb + term * 8192 + nh * 2048, /*lbo*/ 4096, /*sbo*/ 128);
+          mma_f16_ts(tmem + 128 + nh * 256, a_tmem, bd, idesc, (kk | term) ? 1u : 0u);
+        }
+      mma_commit(&ms.bar_empty[st]);
+      // refill the stage consumed one step ago with the k-step that will use it next
+      if (kk >= 1) {
+        const int prev = kk - 1, nxt = prev + kStages;
+        if (nxt < ks2) {
+          const int ps = prev % kStages;
+          ok = mbar_wait(&ms.bar_empty[ps], ph_empty[ps]) && ok;
+          ph_empty[ps] ^= 1;
+          mbar_expect_tx(&ms.bar_full[ps], kStageBytes);
+          bulk_g2s(smem + kOffRing + ps * kStageBytes, vsrc + (size_t)nxt * kStageBytes, kStageBytes, &ms.bar_full[ps]);
+        }
+      }
+    }
+    mma_commit(&ms.bar_mma);
+  }
+  ok = mbar_wait(&ms.bar_mma, 1) && ok;
+  tc_fence_after_sync();
+
+  // ---- normalise and store: warps 0-3 -> channels [0,128) of this half, warps 4-7 -> [128,256) ---------------
+  {
+    const int nh = warp >> 2;
+    const float scale = inv_total;             // the 2^10 of E cancels against the row sum of the same operand
+    float* obase = p.out + ((size_t)u * p.out_channels + p.mem_channel + h * kDH + nh * 128) * HW + p0 + px;
+    const bool in_range = p0 + px < HW;
+    for (int q = 0; q < 4; ++q) {
+      uint32_t r[32];
+      tmem_ld32(tmem_addr(tmem, lane_base, 128 + nh * 256 + q * 32), r);
+      tmem_ld_wait();
+      if (in_range) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) obase[(size_t)(q * 32 + j) * HW] = __uint_as_float(r[j]) * scale;
+      }
+    }
+  }
+  tc_fence_before_sync();
+  const int bad = __syncthreads_or(!ok);
+  if (warp == 0) tmem_dealloc(tmem, 512);
+  if (bad) __trap();
+}
+
+// ------------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------------
+bool fused_readout_supported(const SwemDims& d) {
+  return d.Ck == ro::kCk && d.L == ro::kL && d.Cv == ro::kCv && (d.n_banks == 1 || d.n_banks == 2) && d.topl >= 1 &&
+         d.topl <= 64 && d.HW >= 1;
+}
+
+size_t fused_readout_workspace(const SwemDims& d) {
+  const size_t U = (size_t)d.B * d.N;
+  const size_t Lt = (size_t)d.L * d.n_banks;
+  size_t bytes = 0;
+  bytes += align_up(U * 2 * 2 * d.n_banks * 16384, 256);                 // khat blobs
+  bytes += align_up(U * 2 * (2 * Lt / 16) * ro::kStageBytes, 256);       // nu blobs
+  bytes += align_up(U * d.HW * 2 * Lt * 4, 256);                         // E scratch
+  return bytes + 256;
+}
+
+int fused_readout_forward(const SwemReadArgs& a, cudaStream_t st) {
+  const SwemDims& d = a.dims;
+  const int U = d.B * d.N, nb = d.n_banks, Lt = d.L * nb;
+  const int T = (d.HW + ro::kTP - 1) / ro::kTP;
+  Arena ws(a.workspace);
+  uint8_t* kblob = ws.take<uint8_t>((size_t)U * 2 * 2 * nb * 16384);
+  uint8_t* vblob = ws.take<uint8_t>((size_t)U * 2 * (2 * Lt / 16) * ro::kStageBytes);
+  float* escr = ws.take<float>((size_t)U * d.HW * 2 * Lt);
+
+  {
+    const int n = U * 2 * nb * ro::kL;
+    readout_prep_kappa_kernel<<<(n + 127) / 128, 128, 0, st>>>(a.kappa[0], a.kappa[nb - 1], U, nb, kblob);
+    SWEM_LAUNCH_CHECK();
+    const long long m = (long long)U * 2 * nb * ro::kCv * (ro::kL / 8);
+    readout_prep_nu_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(a.nu[0], a.nu[nb - 1], U, nb, vblob);
+    SWEM_LAUNCH_CHECK();
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    SWEM_CUDA(cudaFuncSetAttribute(readout_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ro::kSmemBytes));
+    attr_set = true;
+  }
+  ReadoutFusedParams p{};
+  p.qk = a.qk; p.kblob = kblob; p.vblob = vblob; p.out = a.out; p.escratch = escr;
+  p.N = d.N; p.HW = d.HW; p.T = T; p.n_banks = nb; p.out_channels = a.out_channels; p.mem_channel = a.mem_channel;
+  p.c1s = kLog2e / (d.tau * ro::kKScale);
+  readout_fused_kernel<<<U * T * 2, 256, ro::kSmemBytes, st>>>(p);
+  SWEM_LAUNCH_CHECK();
+  return launch_perm_inv(escr, U, d.HW, Lt, d.topl, a.out, a.out_channels, a.s_channel, st);
+}
+
+}  // namespace swem

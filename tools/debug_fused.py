@@ -57,3 +57,35 @@ if __name__ == '__main__':
     run(1, 1, 8, 16, 2)
     run(1, 2, 30, 54, 1)
     run(1, 2, 30, 54, 4)
+
+
+def free_running():
+    from swem_b200 import SWEM, make_config
+    from swem_b200.evaluator import evaluate_davis_seq
+    from swem_b200.synthetic import davis_sequence
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.manual_seed(0)
+    cfg = make_config(keydim=64, n_bases=128, n_iters=4, topl=64)
+    nets_cpu = SWEM(cfg).eval()
+    T, N, h, w = 6, 3, 240, 432
+    frames, init = davis_sequence(T, N, seed=1, size=(h, w))
+    prior = dict(zip(('kappa', 'nu', 'zita'), O.random_init(1, N, 64, 128, 512, generator=torch.Generator().manual_seed(4))))
+    oracle = O.OracleSWEM(nets_cpu, 128, 4, 0.05, 64)
+    real_init = O.random_init
+    O.random_init = lambda *a, **k: (prior['kappa'], prior['nu'], prior['zita'])
+    want = torch.stack(O.run_davis_sequence(oracle, frames, init, (h, w)))
+    O.random_init = real_init
+    for fam, path in (('generic', _lib.PATH_GENERIC), ('fused', _lib.PATH_AUTO)):
+        model = SWEM(cfg).eval()
+        model.load_state_dict(nets_cpu.state_dict())
+        model = model.cuda()
+        model.swem_core.em_path = path
+        model.swem_core.random_init = lambda size, norm_dim=-2, dtype=None, device=None: tuple(t.to(device) for t in (prior['kappa'], prior['nu'], prior['zita']))
+        got, _ = evaluate_davis_seq(model, frames.cuda(), [init.cuda()] + [None] * (T - 1), (h, w))
+        got = torch.stack(got).cpu()
+        print(fam, 'free-running agreement per frame', [round(v, 5) for v in (got == want).flatten(1).float().mean(dim=1).tolist()])
+
+
+if __name__ == '__main__':
+    free_running()

@@ -1,0 +1,54 @@
+"""Phase-level timing of the fused EM kernel (CTA 0 time stamps) + CUDA-event timing of both entry points."""
+import ctypes as C, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from swem_b200 import SWEMCore, _lib
+from swem_b200.synthetic import em_inputs
+
+def main(N=5, H=30, W=54, I=4, reps=50):
+    dev = torch.device('cuda:0')
+    lib = _lib.load()
+    Ck, Cv, L = 64, 512, 128
+    x, v, masks = (t.to(dev) for t in em_inputs(1, N, Ck, Cv, H, W, seed=0))
+    core = SWEMCore(n_bases=L, valdim=Cv, n_iters=I, tau=0.05, topl=64).to(dev).eval()
+    with torch.no_grad():
+        core.memorize(x, v, masks)
+        core.memorize(x, v, masks)
+        prior = core.memories['update'].bases
+        for _ in range(3):
+            core.swem(x, v, masks, prior)
+        buf = torch.zeros(256, dtype=torch.int64, device=dev)
+        _lib.check(lib.swem_set_profile_buffer(buf.data_ptr(), buf.numel() * 8), 'set_profile')
+        core.swem(x, v, masks, prior)
+        torch.cuda.synchronize()
+        lib.swem_set_profile_buffer(None, 0)
+        st = buf.cpu().tolist()
+        n = st[0]
+        t = st[1:1 + n]
+        print(f'N={N} HW={H*W} I={I}: {n} stamps, total {(t[-1]-t[0])/1e3:.1f} us')
+        names = ['setup']
+        for it in range(I):
+            names += [f'it{it} logits GEMM', f'it{it} epilogue', f'it{it} M GEMM']
+            if it == I - 1:
+                names += ['nu pass0 GEMM', 'nu pass0 drain', 'nu pass1 GEMM', 'nu pass1 drain']
+            names += [f'it{it} reduce-add', f'it{it} wait tiles', f'it{it} load total', f'it{it} finalize']
+        names += ['nu normalise']
+        for k in range(1, n):
+            print(f'  {names[k-1] if k-1 < len(names) else "?":24s} {(t[k]-t[k-1])/1e3:8.2f} us')
+        for name, fn in (('memorize(EM)', lambda: core.swem(x, v, masks, prior)),
+                         ('readout', lambda: core.matching_features(x, v[:, 0]))):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            for _ in range(5):
+                fn()
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(reps):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            print(f'{name}: {e0.elapsed_time(e1) / reps * 1e3:.1f} us per call (events, {reps} reps, launches/call {core.launches})')
+
+if __name__ == '__main__':
+    main()
+    main(N=1)
+    main(N=5, I=1)
