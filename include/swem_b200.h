@@ -124,7 +124,8 @@ int         swem_em_fused_supported(const SwemDims* dims);
 int         swem_readout_fused_supported(const SwemDims* dims);
 /* Diagnostics: install (dev != NULL) or remove (NULL) a device buffer of >= 256 int64.  While
  * installed, CTA 0 of the fused EM kernel writes buf[0] = number of phase stamps and buf[1..] =
- * %globaltimer nanoseconds at its phase boundaries (tools/profile_phases.py prints them).       */
+ * %globaltimer nanoseconds at its phase boundaries; the fused readout kernel does the same at
+ * buf[128] / buf[129..] (tools/profile_phases.py prints them).                                   */
 int         swem_set_profile_buffer(void* dev, size_t bytes);
 /* number of kernel launches the last call on this thread issued (for bench.py's gpu_launches)   */
 int         swem_last_launch_count(void);

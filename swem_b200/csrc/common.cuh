@@ -69,6 +69,7 @@ size_t generic_readout_workspace(const SwemDims& d);
 int generic_readout_forward(const SwemReadArgs& a, cudaStream_t st);
 
 void set_profile_buffer(void* dev);
+long long* get_profile_buffer();
 bool fused_em_supported(const SwemDims& d);
 size_t fused_em_workspace(const SwemDims& d);
 int fused_em_forward(const SwemEmArgs& a, cudaStream_t st);

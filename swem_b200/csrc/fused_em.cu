@@ -557,6 +557,7 @@ __global__ void __launch_bounds__(256, 1) em_fused_kernel(const EmFusedParams p)
 // ------------------------------------------------------------------------------------------------------
 static long long* g_prof = nullptr;
 void set_profile_buffer(void* dev) { g_prof = static_cast<long long*>(dev); }
+long long* get_profile_buffer() { return g_prof; }
 
 static int sm_count() {
   static int n = 0;

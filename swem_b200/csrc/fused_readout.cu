@@ -68,9 +68,15 @@ struct ReadoutFusedParams {
   const uint8_t* vblob;   // [U][2 halves][KS2 k-steps][16 KB]
   float* out;             // [U][out_channels][HW]
   float* escratch;        // [U][HW][2*Lt] fp32 un-normalised E (for the top-l feature)
+  long long* prof;        // optional phase stamps of CTA 0 (slots 128..), see swem_set_profile_buffer
   int N, HW, T, n_banks, out_channels, mem_channel;
   float c1s;              // log2(e) / (tau * kKScale)
 };
+
+#define RO_STAMP()                                                                                   \
+  do {                                                                                               \
+    if (p.prof != nullptr && blockIdx.x == 0 && tid == 0 && n_stamp < 100) p.prof[129 + n_stamp++] = global_ns(); \
+  } while (0)
 
 // ---- prep: banks -> operand blobs ------------------------------------------------------------------
 // khat blob of (u, s): K-major rows j = bank*128 + l, byte = (j%8)*16 + (j/8)*128 + (c/8)*LBO + (c%8)*2,
@@ -155,6 +161,8 @@ __global__ void __launch_bounds__(256, 1) readout_fused_kernel(const ReadoutFuse
   const int ks2 = 2 * ks_side;
   const uint32_t sbase = smem_u32(smem);
   const uint32_t kplane = nb * 16384;     // bytes of one khat plane (hi or lo) of one side
+  int n_stamp = 0;
+  RO_STAMP();
 
   if (warp == 0) tmem_alloc(&ms.tmem_base, 512);
   if (tid == 0) {
@@ -210,6 +218,7 @@ __global__ void __launch_bounds__(256, 1) readout_fused_kernel(const ReadoutFuse
   tc_fence_after_sync();
   const uint32_t tmem = ms.tmem_base;
   bool ok = true;
+  RO_STAMP();   // setup (query tile staged)
 
   // ---- scores: side s -> TMEM columns [256 s, 256 s + Lt) ---------------------------------------------
   if (tid == 0) {
@@ -234,6 +243,7 @@ __global__ void __launch_bounds__(256, 1) readout_fused_kernel(const ReadoutFuse
   }
   ok = mbar_wait(&ms.bar_mma, 0) && ok;
   tc_fence_after_sync();
+  RO_STAMP();   // scores done
 
   // the khat blobs are dead: start streaming nu k-steps into the ring (aliases them)
   const uint8_t* vsrc = p.vblob + ((size_t)u * 2 + h) * ks2 * kStageBytes;
@@ -261,6 +271,7 @@ __global__ void __launch_bounds__(256, 1) readout_fused_kernel(const ReadoutFuse
     }
     ms.ex_max[sd][px] = mx;
     __syncthreads();
+    RO_STAMP(); // max pass
     const float gm = fmaxf(ms.ex_max[0][px], ms.ex_max[1][px]);     // inv_nq > 0: max of a*inv = inv * max a
     const float cw = ms.inv_nq[px] * p.c1s;
     float sum = 0.f;
@@ -299,6 +310,7 @@ __global__ void __launch_bounds__(256, 1) readout_fused_kernel(const ReadoutFuse
     tc_fence_after_sync();
     inv_total = 1.f / (ms.ex_sum[0][px] + ms.ex_sum[1][px]);
   }
+  RO_STAMP();   // exp pass + E packed
 
   // ---- mem_out = E nu^T: A from TMEM (packed E), B from the ring; accumulators at columns 128.. and 384.. ----
   if (tid == 0) {
@@ -334,8 +346,10 @@ __global__ void __launch_bounds__(256, 1) readout_fused_kernel(const ReadoutFuse
     }
     mma_commit(&ms.bar_mma);
   }
+  RO_STAMP();   // PV issued
   ok = mbar_wait(&ms.bar_mma, 1) && ok;
   tc_fence_after_sync();
+  RO_STAMP();   // PV done
 
   // ---- normalise and store: warps 0-3 -> channels [0,128) of this half, warps 4-7 -> [128,256) ---------------
   {
@@ -355,6 +369,8 @@ __global__ void __launch_bounds__(256, 1) readout_fused_kernel(const ReadoutFuse
   }
   tc_fence_before_sync();
   const int bad = __syncthreads_or(!ok);
+  RO_STAMP();   // stored
+  if (p.prof != nullptr && blockIdx.x == 0 && tid == 0) p.prof[128] = n_stamp;
   if (warp == 0) tmem_dealloc(tmem, 512);
   if (bad) __trap();
 }
@@ -403,6 +419,7 @@ int fused_readout_forward(const SwemReadArgs& a, cudaStream_t st) {
   p.qk = a.qk; p.kblob = kblob; p.vblob = vblob; p.out = a.out; p.escratch = escr;
   p.N = d.N; p.HW = d.HW; p.T = T; p.n_banks = nb; p.out_channels = a.out_channels; p.mem_channel = a.mem_channel;
   p.c1s = kLog2e / (d.tau * ro::kKScale);
+  p.prof = get_profile_buffer();
   readout_fused_kernel<<<U * T * 2, 256, ro::kSmemBytes, st>>>(p);
   SWEM_LAUNCH_CHECK();
   return launch_perm_inv(escr, U, d.HW, Lt, d.topl, a.out, a.out_channels, a.s_channel, st);

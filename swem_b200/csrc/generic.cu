@@ -251,58 +251,119 @@ __global__ void readout_rows_kernel(float* __restrict__ sc, const float* __restr
 }
 
 // ------------------------------------------------------------------------------------------
-// permutation-invariant feature (reference :198-208).  One warp per (u, p); lanes hold Lt/32
-// values per side; 'topl' rounds of {local max, warp arg-max, retire the winner}; the running
-// sums advance in rank order exactly like the reference's sequential loop.  f is scale
-// invariant, so the normalised P serves as well as the un-normalised exp-affinity.
+// permutation-invariant feature (reference :198-208).  One warp per (u, p), both sides at once.
+// The Lt values of a side are sorted in registers by a bitonic network on packed words
+//   word = (fp32 bits of E, top 32-B bits) << B | column index      (E >= 0: bit order = value order)
+// so one unsigned min/max moves key and index together; the top-l columns are then re-read in
+// exact fp32 for the running sums.  Keys keep >= 14 mantissa bits, so two values can only swap
+// ranks when they agree to ~1e-4 relative, which perturbs a running sum by less than that times
+// the smaller of the two.  f is scale invariant, so any positive multiple of exp-affinity works.
 // ------------------------------------------------------------------------------------------
+template <int NPL>
+__device__ __forceinline__ void bitonic_desc2(uint32_t (&a)[NPL], uint32_t (&b)[NPL], int lane) {
+  constexpr int N = 32 * NPL;
+#pragma unroll
+  for (int sz = 2; sz <= N; sz <<= 1) {
+#pragma unroll
+    for (int d = sz >> 1; d > 0; d >>= 1) {
+      if (d < NPL) {            // partner lives in this lane
+#pragma unroll
+        for (int k = 0; k < NPL; ++k) {
+          if ((k & d) == 0) {
+            const bool desc = (sz < NPL) ? ((k & sz) == 0) : (((lane * NPL) & sz) == 0);
+            const uint32_t alo = min(a[k], a[k | d]), ahi = max(a[k], a[k | d]);
+            a[k] = desc ? ahi : alo;
+            a[k | d] = desc ? alo : ahi;
+            const uint32_t blo = min(b[k], b[k | d]), bhi = max(b[k], b[k | d]);
+            b[k] = desc ? bhi : blo;
+            b[k | d] = desc ? blo : bhi;
+          }
+        }
+      } else {                  // partner lives in lane ^ (d / NPL), same register
+        const int ld = d / NPL;
+        const bool desc = (((lane * NPL) & sz) == 0);
+        const bool take_max = (desc == ((lane & ld) == 0));
+#pragma unroll
+        for (int k = 0; k < NPL; ++k) {
+          const uint32_t ya = __shfl_xor_sync(0xffffffffu, a[k], ld);
+          const uint32_t yb = __shfl_xor_sync(0xffffffffu, b[k], ld);
+          a[k] = take_max ? max(a[k], ya) : min(a[k], ya);
+          b[k] = take_max ? max(b[k], yb) : min(b[k], yb);
+        }
+      }
+    }
+  }
+}
+
 template <int NPL>
 __global__ void __launch_bounds__(256) perm_inv_kernel(const float* __restrict__ P, int U, int HW, int Lt,
                                                        int topl, float* __restrict__ out, int out_channels,
                                                        int s_channel) {
-  extern __shared__ float tile[];          // [2*topl][33]
+  constexpr int N = 32 * NPL;
+  constexpr int IDXB = (NPL == 1 ? 5 : NPL == 2 ? 6 : NPL == 4 ? 7 : NPL == 8 ? 8 : NPL == 16 ? 9 : 10);
+  extern __shared__ float tile[];                               // [2*topl][33] then uint32 top[8 warps][2][64]
+  uint32_t* top = reinterpret_cast<uint32_t*>(tile + 2 * topl * 33);
   const int u = blockIdx.y;
   const int p_base = blockIdx.x * 32;
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint32_t* mytop = top + wid * 128;
   for (int q = wid; q < 32; q += 8) {
     const int p = p_base + q;
     if (p >= HW) break;
     const float* row = P + ((long long)u * HW + p) * (2 * Lt);
-    float v0[NPL], v1[NPL];
+    uint32_t a[NPL], b[NPL];
 #pragma unroll
-    for (int i = 0; i < NPL; ++i) {
-      const int j = i * 32 + lane;
-      v0[i] = j < Lt ? row[j] : -1.f;
-      v1[i] = j < Lt ? row[Lt + j] : -1.f;
+    for (int k = 0; k < NPL; ++k) {
+      const int i = lane * NPL + k;
+      const uint32_t va = i < Lt ? __float_as_uint(row[i]) : 0u;
+      const uint32_t vb = i < Lt ? __float_as_uint(row[Lt + i]) : 0u;
+      a[k] = ((va >> (IDXB - 1)) << IDXB) | (uint32_t)i;
+      b[k] = ((vb >> (IDXB - 1)) << IDXB) | (uint32_t)i;
     }
-    float run0 = 0.f, run1 = 0.f;
-    for (int r = 0; r < topl; ++r) {
-      float m0 = v0[0], m1 = v1[0];
+    bitonic_desc2<NPL>(a, b, lane);
+    // rank r sits in lane r / NPL, register r % NPL; publish the top-l words
 #pragma unroll
-      for (int i = 1; i < NPL; ++i) { m0 = fmaxf(m0, v0[i]); m1 = fmaxf(m1, v1[i]); }
-      const float g0 = warp_max(m0), g1 = warp_max(m1);
-      const unsigned b0 = __ballot_sync(0xffffffffu, m0 == g0);
-      const unsigned b1 = __ballot_sync(0xffffffffu, m1 == g1);
-      if (lane == __ffs(b0) - 1) {
-        bool done = false;
-#pragma unroll
-        for (int i = 0; i < NPL; ++i)
-          if (!done && v0[i] == g0) { v0[i] = -1.f; done = true; }
+    for (int k = 0; k < NPL; ++k) {
+      const int r = lane * NPL + k;
+      if (r < 64) {
+        mytop[r] = a[k];
+        mytop[64 + r] = b[k];
       }
-      if (lane == __ffs(b1) - 1) {
-        bool done = false;
+    }
+    __syncwarp();
+    // lane handles ranks lane and lane + 32: exact values, inclusive running sums over rank
+    float c0[2], c1[2];
 #pragma unroll
-        for (int i = 0; i < NPL; ++i)
-          if (!done && v1[i] == g1) { v1[i] = -1.f; done = true; }
+    for (int hlf = 0; hlf < 2; ++hlf) {
+      const int r = lane + 32 * hlf;
+      float x0 = 0.f, x1 = 0.f;
+      if (r < topl) {
+        const int i0 = mytop[r] & (N - 1), i1 = mytop[64 + r] & (N - 1);
+        x0 = i0 < Lt ? row[i0] : 0.f;          // padding words can only surface if real values are exact zeros
+        x1 = i1 < Lt ? row[Lt + i1] : 0.f;
       }
-      run0 += g0;
-      run1 += g1;
-      if (lane == (r & 31)) {
-        const float f = run0 / (run0 + run1);
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const float y0 = __shfl_up_sync(0xffffffffu, x0, o);
+        const float y1 = __shfl_up_sync(0xffffffffu, x1, o);
+        if (lane >= o) { x0 += y0; x1 += y1; }
+      }
+      c0[hlf] = x0;
+      c1[hlf] = x1;
+    }
+    const float t0 = __shfl_sync(0xffffffffu, c0[0], 31), t1 = __shfl_sync(0xffffffffu, c1[0], 31);
+    c0[1] += t0;
+    c1[1] += t1;
+#pragma unroll
+    for (int hlf = 0; hlf < 2; ++hlf) {
+      const int r = lane + 32 * hlf;
+      if (r < topl) {
+        const float f = c0[hlf] / (c0[hlf] + c1[hlf]);
         tile[r * 33 + q] = f;
         tile[(topl + r) * 33 + q] = 1.f - f;
       }
     }
+    __syncwarp();
   }
   __syncthreads();
   const int npx = min(32, HW - p_base);
@@ -314,8 +375,12 @@ __global__ void __launch_bounds__(256) perm_inv_kernel(const float* __restrict__
 
 int launch_perm_inv(const float* P, int U, int HW, int Lt, int topl, float* out, int out_channels,
                     int s_channel, cudaStream_t st) {
+  if (topl > 64) {
+    set_error("perm_inv: topl=%d > 64 unsupported", topl);
+    return SWEM_ERR_UNSUPPORTED;
+  }
   dim3 grid((HW + 31) / 32, U);
-  const size_t smem = (size_t)2 * topl * 33 * sizeof(float);
+  const size_t smem = (size_t)2 * topl * 33 * sizeof(float) + 8 * 128 * sizeof(uint32_t);
   const int npl = (Lt + 31) / 32;
 #define SWEM_PI(NPL_) perm_inv_kernel<NPL_><<<grid, 256, smem, st>>>(P, U, HW, Lt, topl, out, out_channels, s_channel)
   if (npl <= 1) SWEM_PI(1);

@@ -35,6 +35,17 @@ def main(N=5, H=30, W=54, I=4, reps=50):
         names += ['nu normalise']
         for k in range(1, n):
             print(f'  {names[k-1] if k-1 < len(names) else "?":24s} {(t[k]-t[k-1])/1e3:8.2f} us')
+        _lib.check(lib.swem_set_profile_buffer(buf.data_ptr(), buf.numel() * 8), 'set_profile')
+        core.matching_features(x, v[:, 0])
+        torch.cuda.synchronize()
+        lib.swem_set_profile_buffer(None, 0)
+        st = buf.cpu().tolist()
+        n = st[128]
+        t = st[129:129 + n]
+        rn = ['setup', 'scores GEMM', 'max pass', 'exp pass', 'PV issue', 'PV drain wait', 'store']
+        print(f'readout_fused CTA0: total {(t[-1]-t[0])/1e3:.1f} us')
+        for k in range(1, n):
+            print(f'  {rn[k-1] if k-1 < len(rn) else "?":24s} {(t[k]-t[k-1])/1e3:8.2f} us')
         for name, fn in (('memorize(EM)', lambda: core.swem(x, v, masks, prior)),
                          ('readout', lambda: core.matching_features(x, v[:, 0]))):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
