@@ -27,6 +27,12 @@ __device__ __forceinline__ long long global_ns() {
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
   return t;
 }
+// 2^x on the SFU (MUFU.EX2): relative error ~2^-22, flushes results below the normal range to 0
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ void split_half(float v, __half& hi, __half& lo) {
   hi = __float2half_rn(v);
   lo = __float2half_rn(v - __half2float(hi));

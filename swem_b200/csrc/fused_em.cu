@@ -52,7 +52,8 @@ constexpr float kZScale = 16384.f;                 // z (<= 1) is staged as z*2^
 // Z  : [sl 0..255][p] MN-major A: byte = (sl%8)*2 + (p%8)*16 + (sl/8)*2048 + (p/8)*128   -> SBO=2048, LBO=128
 // P  : fp32 [256][73] staging of the M-step partial / total (aliases Z)
 // VS : 3 stages x [d 0..255][p 0..31] K-major: byte = (d%8)*16 + (d/8)*128 + (p/8)*4096 + (p%8)*2 -> SBO=128, LBO=4096
-// NS : fp32 [2 sides][64 d][128 l] staging of nu partials (aliases KH/KL)
+// ZL : lo half of z, same layout as Z (aliases KH/KL: khat is dead between the logits GEMM and the finalize)
+// NS : fp32 [2 sides][32 d][128 l] staging of nu partials (aliases XH/XL, dead after the last M-step GEMM)
 constexpr uint32_t kOffXH = 0;
 constexpr uint32_t kOffXL = kOffXH + 10 * 2048;
 constexpr uint32_t kOffKH = kOffXL + 8 * 2048;
@@ -61,7 +62,8 @@ constexpr uint32_t kOffZ = kOffKL + 8 * 4096;
 constexpr uint32_t kOffVS = kOffZ + kAccBytes;            // 74752 is a multiple of 128
 constexpr uint32_t kVStage = 4 * 4096;                    // 16 KB
 constexpr uint32_t kOffMisc = kOffVS + 3 * kVStage;
-constexpr uint32_t kOffNS = kOffKH;                       // 64 KB
+constexpr uint32_t kOffZL = kOffKH;                       // 64 KB
+constexpr uint32_t kOffNS = kOffXH;                       // 32 KB of the 36 KB X region
 struct Misc {
   float inv_nx[kTP];
   float mask[2][kTP];
@@ -228,7 +230,10 @@ __global__ void __launch_bounds__(256, 1) em_fused_kernel(const EmFusedParams p)
     tc_fence_after_sync();
 
     // ---- (1) logits GEMM -----------------------------------------------------------------------
-    if (tid == 0) {
+    // (single-thread sections are written as warp 0 / lane 0 + __syncwarp so that the other lanes of
+    //  warp 0 park at the warp barrier instead of spinning on an mbarrier in a divergent branch)
+    if (warp == 0) {
+      if (lane == 0) {
 #pragma unroll
       for (int term = 0; term < 3; ++term) {
         const uint32_t xa = sbase + (term == 2 ? kOffXL : kOffXH);
@@ -241,6 +246,8 @@ __global__ void __launch_bounds__(256, 1) em_fused_kernel(const EmFusedParams p)
         }
       }
       mma_commit(&ms.bar_mma);
+      }
+      __syncwarp();
     }
     ok = ok && mbar_wait(&ms.bar_mma, ph_mma);
     ph_mma ^= 1;
@@ -271,13 +278,13 @@ __global__ void __launch_bounds__(256, 1) em_fused_kernel(const EmFusedParams p)
         const float cw = ms.inv_nx[px] * p.c1s;
         float e = 0.f;
 #pragma unroll
-        for (int i = 0; i < kL; ++i) e += exp2f((a[i] - gm) * cw);
+        for (int i = 0; i < kL; ++i) e += fast_exp2((a[i] - gm) * cw);
         ms.ex_sum[sd][px] = e;
       }
       float sum = 0.f;
 #pragma unroll
       for (int i = 0; i < kL; ++i) {
-        a[i] = exp2f((a[i] - mx) * p.c1s);
+        a[i] = fast_exp2((a[i] - mx) * p.c1s);
         sum += a[i];
       }
       __syncthreads();
@@ -288,16 +295,16 @@ __global__ void __launch_bounds__(256, 1) em_fused_kernel(const EmFusedParams p)
       }
       const float scale = w / sum;
       const float zs = scale * kZScale;
-      // z -> fp16, MN-major A operand: 16-byte chunk = 8 consecutive bases of this pixel
+      // z -> fp16 hi + lo, MN-major A operands: 16-byte chunk = 8 consecutive bases of this pixel
 #pragma unroll
       for (int g = 0; g < kL / 8; ++g) {
-        uint4 pk;
-        pk.x = pack_half2(a[g * 8 + 0] * zs, a[g * 8 + 1] * zs);
-        pk.y = pack_half2(a[g * 8 + 2] * zs, a[g * 8 + 3] * zs);
-        pk.z = pack_half2(a[g * 8 + 4] * zs, a[g * 8 + 5] * zs);
-        pk.w = pack_half2(a[g * 8 + 6] * zs, a[g * 8 + 7] * zs);
+        __align__(16) __half hi[8];
+        __align__(16) __half lo[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) split_half(a[g * 8 + e] * zs, hi[e], lo[e]);
         const uint32_t off = (px % 8) * 16 + (px / 8) * 128 + (sd * 16 + g) * 2048;
-        *reinterpret_cast<uint4*>(smem + kOffZ + off) = pk;
+        *reinterpret_cast<uint4*>(smem + kOffZ + off) = *reinterpret_cast<uint4*>(hi);
+        *reinterpret_cast<uint4*>(smem + kOffZL + off) = *reinterpret_cast<uint4*>(lo);
       }
       if (p.z_last != nullptr && it == I - 1 && p0 + px < HW) {
         float4* dst = reinterpret_cast<float4*>(p.z_last + (((size_t)u * 2 + sd) * HW + p0 + px) * kL);
@@ -313,20 +320,25 @@ __global__ void __launch_bounds__(256, 1) em_fused_kernel(const EmFusedParams p)
 
     EM_STAMP();                      // epilogue done
     // ---- (3) M-step GEMM: [kappa sums | zita sum] per side ------------------------------------------
-    if (tid == 0) {
+    if (warp == 0) {
+      if (lane == 0) {
 #pragma unroll
       for (int sd = 0; sd < 2; ++sd) {
         const uint32_t za = sbase + kOffZ + sd * 16 * 2048;
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) {
           const uint64_t ad = make_sdesc(za + kk * 2 * 128, /*lbo*/ 128, /*sbo*/ 2048);
+          const uint64_t al = make_sdesc(za + (kOffZL - kOffZ) + kk * 2 * 128, /*lbo*/ 128, /*sbo*/ 2048);
           const uint64_t bh = make_sdesc(sbase + kOffXH + kk * 2 * 128, /*lbo*/ 128, /*sbo*/ 2048);
           const uint64_t bl = make_sdesc(sbase + kOffXL + kk * 2 * 128, /*lbo*/ 128, /*sbo*/ 2048);
-          mma_f16_ss(tmem + kColM + sd * 80, ad, bh, idesc_m80, kk ? 1u : 0u);
-          mma_f16_ss(tmem + kColM + sd * 80, ad, bl, idesc_m64, 1u);
+          mma_f16_ss(tmem + kColM + sd * 80, ad, bh, idesc_m80, kk ? 1u : 0u);   // z_hi x_hi (+ zita column)
+          mma_f16_ss(tmem + kColM + sd * 80, ad, bl, idesc_m64, 1u);             // z_hi x_lo
+          mma_f16_ss(tmem + kColM + sd * 80, al, bh, idesc_m80, 1u);             // z_lo x_hi
         }
       }
       mma_commit(&ms.bar_mma);
+      }
+      __syncwarp();
     }
     ok = ok && mbar_wait(&ms.bar_mma, ph_mma);
     ph_mma ^= 1;
@@ -395,7 +407,8 @@ __global__ void __launch_bounds__(256, 1) em_fused_kernel(const EmFusedParams p)
           tc_fence_before_sync();
           __syncthreads();
           tc_fence_after_sync();
-          if (tid == 0) {
+          if (warp == 0) {
+            if (lane == 0) {
             const uint32_t vb = sbase + kOffVS + st * kVStage;
 #pragma unroll
             for (int sd = 0; sd < 2; ++sd) {
@@ -403,12 +416,16 @@ __global__ void __launch_bounds__(256, 1) em_fused_kernel(const EmFusedParams p)
 #pragma unroll
               for (int kk = 0; kk < 2; ++kk) {
                 const uint64_t ad = make_sdesc(za + (ch * 2 + kk) * 2 * 128, /*lbo*/ 128, /*sbo*/ 2048);
+                const uint64_t al = make_sdesc(za + (kOffZL - kOffZ) + (ch * 2 + kk) * 2 * 128, /*lbo*/ 128, /*sbo*/ 2048);
                 const uint64_t bd = make_sdesc(vb + kk * 2 * 4096, /*lbo*/ 4096, /*sbo*/ 128);
                 mma_f16_ss(tmem + kColNu + sd * 256, ad, bd, idesc_nu, (ch | kk) ? 1u : 0u);
+                mma_f16_ss(tmem + kColNu + sd * 256, al, bd, idesc_nu, 1u);
               }
             }
             mma_commit(&ms.bar_stage[st]);
             if (ch == 3) mma_commit(&ms.bar_mma);
+            }
+            __syncwarp();
           }
         }
         ok = ok && mbar_wait(&ms.bar_mma, ph_mma);
@@ -419,23 +436,22 @@ __global__ void __launch_bounds__(256, 1) em_fused_kernel(const EmFusedParams p)
         {
           const int sd = warp >> 2, l = (warp & 3) * 32 + lane;
           float* ns = reinterpret_cast<float*>(smem + kOffNS);
-          for (int q = 0; q < 4; ++q) {
-#pragma unroll
-            for (int hq = 0; hq < 2; ++hq) {
+          for (int q = 0; q < 8; ++q) {
+            {
               uint32_t r[32];
-              tmem_ld32(tmem_addr(tmem, (warp & 3) * 32, kColNu + sd * 256 + q * 64 + hq * 32), r);
+              tmem_ld32(tmem_addr(tmem, (warp & 3) * 32, kColNu + sd * 256 + q * 32), r);
               tmem_ld_wait();
 #pragma unroll
-              for (int j = 0; j < 32; ++j) ns[(sd * 64 + hq * 32 + j) * 128 + l] = __uint_as_float(r[j]);
+              for (int j = 0; j < 32; ++j) ns[(sd * 32 + j) * 128 + l] = __uint_as_float(r[j]);
             }
             fence_proxy_async_smem();
             __syncthreads();
             if (tid == 0) {
 #pragma unroll
               for (int s2 = 0; s2 < 2; ++s2) {
-                float* dst = p.acc_nu + (((size_t)u * 2 + s2) * kCv + half * 256 + q * 64) * kL;
+                float* dst = p.acc_nu + (((size_t)u * 2 + s2) * kCv + half * 256 + q * 32) * kL;
                 asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(dst),
-                             "r"(smem_u32(ns + s2 * 64 * 128)), "r"(64 * 128 * 4)
+                             "r"(smem_u32(ns + s2 * 32 * 128)), "r"(32 * 128 * 4)
                              : "memory");
               }
               asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -469,7 +485,8 @@ __global__ void __launch_bounds__(256, 1) em_fused_kernel(const EmFusedParams p)
     float kpr[kCk];
 #pragma unroll
     for (int c = 0; c < kCk; ++c) kpr[c] = __ldg(kprior + (size_t)c * kL);
-    if (tid == 0) {
+    if (warp == 0) {
+      if (lane == 0) {
       asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(acc),
                    "r"(sbase + kOffZ), "r"(kAccBytes)
                    : "memory");
@@ -485,6 +502,8 @@ __global__ void __launch_bounds__(256, 1) em_fused_kernel(const EmFusedParams p)
       asm volatile("fence.proxy.async;" ::: "memory");
       mbar_expect_tx(&ms.bar_tma, kAccBytes);
       bulk_g2s(smem + kOffZ, acc, kAccBytes, &ms.bar_tma);
+      }
+      __syncwarp();
     }
     ok = ok && mbar_wait(&ms.bar_tma, ph_tma);
     ph_tma ^= 1;

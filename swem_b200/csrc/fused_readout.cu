@@ -144,6 +144,7 @@ __global__ void readout_prep_nu_kernel(const float* __restrict__ n0, const float
 }
 
 // ---- main kernel --------------------------------------------------------------------------------------
+template <int NB>   // number of banks read (1 or 2): fixes every loop count, so the MMA issue loops unroll
 __global__ void __launch_bounds__(256, 1) readout_fused_kernel(const ReadoutFusedParams p) {
   using namespace ro;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -155,12 +156,12 @@ __global__ void __launch_bounds__(256, 1) readout_fused_kernel(const ReadoutFuse
   const int b = u / p.N;
   const int p0 = tile * kTP;
   const int HW = p.HW;
-  const int nb = p.n_banks;
-  const int Lt = nb * kL;                 // columns per side
-  const int ks_side = Lt / 16;            // PV k-steps per side
-  const int ks2 = 2 * ks_side;
+  constexpr int nb = NB;
+  constexpr int Lt = nb * kL;             // columns per side
+  constexpr int ks_side = Lt / 16;        // PV k-steps per side
+  constexpr int ks2 = 2 * ks_side;
   const uint32_t sbase = smem_u32(smem);
-  const uint32_t kplane = nb * 16384;     // bytes of one khat plane (hi or lo) of one side
+  constexpr uint32_t kplane = nb * 16384; // bytes of one khat plane (hi or lo) of one side
   int n_stamp = 0;
   RO_STAMP();
 
@@ -221,9 +222,12 @@ __global__ void __launch_bounds__(256, 1) readout_fused_kernel(const ReadoutFuse
   RO_STAMP();   // setup (query tile staged)
 
   // ---- scores: side s -> TMEM columns [256 s, 256 s + Lt) ---------------------------------------------
-  if (tid == 0) {
+  // (single-thread sections: warp 0 / lane 0 + __syncwarp, so the rest of warp 0 parks at the warp
+  //  barrier instead of spinning on an mbarrier in a divergent branch and starving lane 0)
+  if (warp == 0) {
+    if (lane == 0) {
     const uint32_t idesc = make_idesc(128, Lt, kFmtF16, kFmtF16, kMajorMN, kMajorK);
-    const uint32_t lbo_k = nb * 2048;
+    constexpr uint32_t lbo_k = nb * 2048;
     for (int s = 0; s < 2; ++s) {
       ok = mbar_wait(&ms.bar_k[s], 0) && ok;
       const uint32_t kb = sbase + kOffKB + s * kKBSide;
@@ -240,6 +244,8 @@ __global__ void __launch_bounds__(256, 1) readout_fused_kernel(const ReadoutFuse
       }
     }
     mma_commit(&ms.bar_mma);
+    }
+    __syncwarp();
   }
   ok = mbar_wait(&ms.bar_mma, 0) && ok;
   tc_fence_after_sync();
@@ -260,7 +266,7 @@ __global__ void __launch_bounds__(256, 1) readout_fused_kernel(const ReadoutFuse
   const uint32_t lane_base = (warp & 3) * 32;
   float inv_total;
   {
-    const int nchunk = Lt / 32;
+    constexpr int nchunk = Lt / 32;
     float mx = -3.0e38f;
     for (int q = 0; q < nchunk; ++q) {
       uint32_t r[32];
@@ -275,8 +281,6 @@ __global__ void __launch_bounds__(256, 1) readout_fused_kernel(const ReadoutFuse
     const float gm = fmaxf(ms.ex_max[0][px], ms.ex_max[1][px]);     // inv_nq > 0: max of a*inv = inv * max a
     const float cw = ms.inv_nq[px] * p.c1s;
     float sum = 0.f;
-    const bool write_e = (h == 0) && (p0 + px < HW);
-    float* erow = p.escratch + ((size_t)u * HW + p0 + px) * (2 * Lt) + sd * Lt;
     for (int q = 0; q < nchunk; ++q) {
       uint32_t r[32];
       tmem_ld32(tmem_addr(tmem, lane_base, sd * 256 + q * 32), r);
@@ -284,8 +288,8 @@ __global__ void __launch_bounds__(256, 1) readout_fused_kernel(const ReadoutFuse
       uint32_t pk[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
-        const float e0 = exp2f((__uint_as_float(r[2 * j]) - gm) * cw);
-        const float e1 = exp2f((__uint_as_float(r[2 * j + 1]) - gm) * cw);
+        const float e0 = fast_exp2((__uint_as_float(r[2 * j]) - gm) * cw);
+        const float e1 = fast_exp2((__uint_as_float(r[2 * j + 1]) - gm) * cw);
         const __half2 hh = __floats2half2_rn(e0 * kEScale, e1 * kEScale);
         const float2 back = __half22float2(hh);
         sum += back.x + back.y;                                      // row sum of the ROUNDED operand
@@ -293,12 +297,25 @@ __global__ void __launch_bounds__(256, 1) readout_fused_kernel(const ReadoutFuse
         r[2 * j] = __float_as_uint(e0);
         r[2 * j + 1] = __float_as_uint(e1);
       }
-      if (write_e) {
-        float4* dst = reinterpret_cast<float4*>(erow + q * 32);
+      if (h == 0) {
+        // E chunk [32 px of this warp][32 cols] -> scratch rows.  Transposed through shared memory (the dead
+        // query tile; XOR-swizzled float4 slots) so that one store instruction covers 4 rows x 128 B.
+        float4* tbuf = reinterpret_cast<float4*>(smem + kOffQH) + warp * 256;      // [32 rows][8 float4]
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-          dst[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
-                               __uint_as_float(r[4 * j + 3]));
+          tbuf[lane * 8 + (j ^ (lane & 7))] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                                          __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+        __syncwarp();
+        const int c4 = lane & 7;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int row = i * 4 + (lane >> 3);
+          const int pxr = p0 + (warp & 3) * 32 + row;
+          const float4 val = tbuf[row * 8 + (c4 ^ (row & 7))];
+          if (pxr < HW)
+            *reinterpret_cast<float4*>(p.escratch + ((size_t)u * HW + pxr) * (2 * Lt) + sd * Lt + q * 32 + c4 * 4) = val;
+        }
+        __syncwarp();
       }
       // packed E overwrites columns this thread has already consumed: [256 sd + 16 q, +16)
       tmem_st16(tmem_addr(tmem, lane_base, sd * 256 + q * 16), pk);
@@ -313,15 +330,18 @@ __global__ void __launch_bounds__(256, 1) readout_fused_kernel(const ReadoutFuse
   RO_STAMP();   // exp pass + E packed
 
   // ---- mem_out = E nu^T: A from TMEM (packed E), B from the ring; accumulators at columns 128.. and 384.. ----
-  if (tid == 0) {
+  if (warp == 0) {
+    if (lane == 0) {
     const uint32_t idesc = make_idesc(128, 128, kFmtF16, kFmtF16, kMajorK, kMajorK);
-    uint32_t ph_full[kStages], ph_empty[kStages];
-    for (int i = 0; i < kStages; ++i) ph_full[i] = ph_empty[i] = 0;
+    constexpr int kLag = 3;     // refill the stage consumed kLag steps ago: its MMAs have retired, no issue stall
+    long long c_full = 0, c_issue = 0, c_empty = 0;   // diagnostics (cycles), only stored when profiling
+#pragma unroll
     for (int kk = 0; kk < ks2; ++kk) {
       const int st = kk % kStages;
-      ok = mbar_wait(&ms.bar_full[st], ph_full[st]) && ok;
-      ph_full[st] ^= 1;
+      const long long c0 = clock64();
+      ok = mbar_wait(&ms.bar_full[st], (kk / kStages) & 1) && ok;
       tc_fence_after_sync();
+      const long long c1 = clock64();
       const uint32_t a_tmem = tmem + (kk / ks_side) * 256 + (kk % ks_side) * 8;
       const uint32_t vb = sbase + kOffRing + st * kStageBytes;
 #pragma unroll
@@ -332,19 +352,26 @@ __global__ void __launch_bounds__(256, 1) readout_fused_kernel(const ReadoutFuse
           mma_f16_ts(tmem + 128 + nh * 256, a_tmem, bd, idesc, (kk | term) ? 1u : 0u);
         }
       mma_commit(&ms.bar_empty[st]);
-      // refill the stage consumed one step ago with the k-step that will use it next
-      if (kk >= 1) {
-        const int prev = kk - 1, nxt = prev + kStages;
-        if (nxt < ks2) {
-          const int ps = prev % kStages;
-          ok = mbar_wait(&ms.bar_empty[ps], ph_empty[ps]) && ok;
-          ph_empty[ps] ^= 1;
-          mbar_expect_tx(&ms.bar_full[ps], kStageBytes);
-          bulk_g2s(smem + kOffRing + ps * kStageBytes, vsrc + (size_t)nxt * kStageBytes, kStageBytes, &ms.bar_full[ps]);
-        }
+      const long long c2 = clock64();
+      c_full += c1 - c0;
+      c_issue += c2 - c1;
+      if (kk >= kLag && kk - kLag + kStages < ks2) {
+        const int prev = kk - kLag, nxt = prev + kStages;
+        const int ps = prev % kStages;
+        ok = mbar_wait(&ms.bar_empty[ps], (prev / kStages) & 1) && ok;
+        mbar_expect_tx(&ms.bar_full[ps], kStageBytes);
+        bulk_g2s(smem + kOffRing + ps * kStageBytes, vsrc + (size_t)nxt * kStageBytes, kStageBytes, &ms.bar_full[ps]);
+        c_empty += clock64() - c2;
       }
     }
+    if (p.prof != nullptr && blockIdx.x == 0) {
+      p.prof[230] = c_full;
+      p.prof[231] = c_issue;
+      p.prof[232] = c_empty;
+    }
     mma_commit(&ms.bar_mma);
+    }
+    __syncwarp();
   }
   RO_STAMP();   // PV issued
   ok = mbar_wait(&ms.bar_mma, 1) && ok;
@@ -412,7 +439,8 @@ int fused_readout_forward(const SwemReadArgs& a, cudaStream_t st) {
   }
   static bool attr_set = false;
   if (!attr_set) {
-    SWEM_CUDA(cudaFuncSetAttribute(readout_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ro::kSmemBytes));
+    SWEM_CUDA(cudaFuncSetAttribute(readout_fused_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ro::kSmemBytes));
+    SWEM_CUDA(cudaFuncSetAttribute(readout_fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ro::kSmemBytes));
     attr_set = true;
   }
   ReadoutFusedParams p{};
@@ -420,7 +448,8 @@ int fused_readout_forward(const SwemReadArgs& a, cudaStream_t st) {
   p.N = d.N; p.HW = d.HW; p.T = T; p.n_banks = nb; p.out_channels = a.out_channels; p.mem_channel = a.mem_channel;
   p.c1s = kLog2e / (d.tau * ro::kKScale);
   p.prof = get_profile_buffer();
-  readout_fused_kernel<<<U * T * 2, 256, ro::kSmemBytes, st>>>(p);
+  if (nb == 1) readout_fused_kernel<1><<<U * T * 2, 256, ro::kSmemBytes, st>>>(p);
+  else readout_fused_kernel<2><<<U * T * 2, 256, ro::kSmemBytes, st>>>(p);
   SWEM_LAUNCH_CHECK();
   return launch_perm_inv(escr, U, d.HW, Lt, d.topl, a.out, a.out_channels, a.s_channel, st);
 }

@@ -49,7 +49,7 @@ def run(B, N, H, W, I, seed=0, zp=0.0):
     print('  sample nu fused', f['nu'][0, 0, 0, :2, :4].flatten().tolist(), 'want', want['nu'][0, 0, 0, :2, :4].flatten().tolist())
     return outs
 
-if __name__ == '__main__':
+if __name__ == '__main__' and len(sys.argv) == 1:
     run(1, 1, 8, 16, 1)
     run(1, 1, 8, 16, 1, zp=3.0)
     run(1, 1, 6, 10, 1)
@@ -87,5 +87,39 @@ def free_running():
         print(fam, 'free-running agreement per frame', [round(v, 5) for v in (got == want).flatten(1).float().mean(dim=1).tolist()])
 
 
-if __name__ == '__main__':
+if __name__ == '__main__' and len(sys.argv) == 1:
     free_running()
+
+
+def free_running_480p(T=7, N=5):
+    """BASELINE configs[1]-shaped: 480x864, 5 objects; GPU (AUTO = fused) vs CPU oracle, same weights."""
+    from swem_b200 import SWEM, make_config
+    from swem_b200.evaluator import evaluate_davis_seq
+    from swem_b200.synthetic import davis_sequence
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.manual_seed(0)
+    cfg = make_config(keydim=64, n_bases=128, n_iters=4, topl=64)
+    nets_cpu = SWEM(cfg).eval()
+    h, w = 480, 864
+    frames, init = davis_sequence(T, N, seed=1, size=(h, w))
+    prior = dict(zip(('kappa', 'nu', 'zita'), O.random_init(1, N, 64, 128, 512, generator=torch.Generator().manual_seed(4))))
+    oracle = O.OracleSWEM(nets_cpu, 128, 4, 0.05, 64)
+    real_init = O.random_init
+    O.random_init = lambda *a, **k: (prior['kappa'], prior['nu'], prior['zita'])
+    want = torch.stack(O.run_davis_sequence(oracle, frames, init, (h, w)))
+    O.random_init = real_init
+    G, A = _lib.PATH_GENERIC, _lib.PATH_AUTO
+    for fam, em_path, ro_path in (('generic/generic', G, G), ('fusedEM/genericRO', A, G), ('genericEM/fusedRO', G, A), ('fused/fused', A, A)):
+        model = SWEM(cfg).eval()
+        model.load_state_dict(nets_cpu.state_dict())
+        model = model.cuda()
+        model.swem_core.em_path, model.swem_core.readout_path = em_path, ro_path
+        model.swem_core.random_init = lambda size, norm_dim=-2, dtype=None, device=None: tuple(t.to(device) for t in (prior['kappa'], prior['nu'], prior['zita']))
+        got, _ = evaluate_davis_seq(model, frames.cuda(), [init.cuda()] + [None] * (T - 1), (h, w))
+        got = torch.stack(got).cpu()
+        print(fam, '480p free-running agreement per frame', [round(v, 5) for v in (got == want).flatten(1).float().mean(dim=1).tolist()])
+
+
+if __name__ == '__main__' and len(sys.argv) > 1 and sys.argv[1] == '480p':
+    free_running_480p()

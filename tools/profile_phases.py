@@ -46,6 +46,7 @@ def main(N=5, H=30, W=54, I=4, reps=50):
         print(f'readout_fused CTA0: total {(t[-1]-t[0])/1e3:.1f} us')
         for k in range(1, n):
             print(f'  {rn[k-1] if k-1 < len(rn) else "?":24s} {(t[k]-t[k-1])/1e3:8.2f} us')
+        print(f'  PV loop cycles: wait-full {st[230]}  issue {st[231]}  wait-empty+tma {st[232]}')
         for name, fn in (('memorize(EM)', lambda: core.swem(x, v, masks, prior)),
                          ('readout', lambda: core.matching_features(x, v[:, 0]))):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
