@@ -87,6 +87,12 @@ def _no_grad_inputs(*tensors):
                                   'implemented yet; call under torch.no_grad()')
 
 
+def _invoke(name, call):
+    """Every C-ABI launch goes through here; profilers (bench.py) replace it to bracket the call with
+    CUDA events on the launching stream."""
+    return call()
+
+
 class SWEMCore(nn.Module):
     # SWEM_PATH_* of the C ABI per entry point; tests flip these to exercise both kernel families
     em_path = _lib.PATH_AUTO
@@ -160,7 +166,8 @@ class SWEMCore(nn.Module):
                                z_last.data_ptr() if return_z else None,
                                ws.data_ptr(), ws.numel(), self.em_path)
         with torch.cuda.device(dev):
-            rc = lib.swem_em_forward(C.byref(args), torch.cuda.current_stream(dev).cuda_stream)
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            rc = _invoke('em', lambda: lib.swem_em_forward(C.byref(args), stream))
         _lib.check(rc, 'swem_em_forward')
         self.launches = lib.swem_last_launch_count()
         bases = {'kappa': kappa, 'nu': nu, 'zita': zita}
@@ -208,7 +215,8 @@ class SWEMCore(nn.Module):
                                  feats.data_ptr(), chans, 0, 2 * Cv,
                                  ws.data_ptr(), ws.numel(), self.readout_path)
         with torch.cuda.device(dev):
-            rc = lib.swem_readout_forward(C.byref(args), torch.cuda.current_stream(dev).cuda_stream)
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            rc = _invoke('readout', lambda: lib.swem_readout_forward(C.byref(args), stream))
         _lib.check(rc, 'swem_readout_forward')
         self.launches = lib.swem_last_launch_count()
         return feats, N

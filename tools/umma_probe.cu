@@ -97,6 +97,71 @@ __global__ void __launch_bounds__(128) probe(const uint8_t* a_img, const uint8_t
   if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
+// ---- throughput: 64 statically unrolled MMAs into one accumulator, SS vs TS (A from TMEM) -----
+template <int N, bool TS, bool ALT>
+__global__ void __launch_bounds__(128) tput(long long* cycles, int* status) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < (16384 + N * 128 * 2) / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;  // 1.0h
+  if (warp == 0) tmem_alloc(&tmem_base_s, 512);
+  if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+  fence_proxy_async_smem();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = tmem_base_s;
+  if (TS) {
+    uint32_t r[8];
+    for (int j = 0; j < 8; ++j) r[j] = 0x3c003c00u;
+    for (int c = 0; c < 64; c += 8) tmem_st8(tmem_addr(tmem, warp * 32, 256 + c), r);
+    tmem_st_wait();
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+  }
+  long long t0 = 0, t1 = 0;
+  if (warp == 0) {
+    if ((tid & 31) == 0) {
+      const uint32_t idesc = make_idesc(128, N, kFmtF16, kFmtF16, kMajorK, kMajorK);
+      const uint32_t sa = smem_u32(smem), sb = smem_u32(smem) + 16384;
+      t0 = clock64();
+#pragma unroll
+      for (int k = 0; k < 64; ++k) {
+        const uint64_t bd = make_sdesc(sb + (k & 7) * 256, 128, 1024);
+        const uint32_t d = ALT ? tmem + (k & 1) * 128 : tmem;       // ALT: alternate between two accumulators
+        if (TS) mma_f16_ts(d, tmem_addr(tmem, 0, 256 + (k & 7) * 8), bd, idesc, k > 1);
+        else mma_f16_ss(d, make_sdesc(sa + (k & 7) * 256, 128, 1024), bd, idesc, k > 1);
+      }
+      mma_commit(&bar);
+      t1 = clock64();
+    }
+    __syncwarp();
+  }
+  const bool ok = mbar_wait(&bar, 0, 1u << 22);
+  const long long t2 = clock64();
+  if (tid == 0) { cycles[0] = t1 - t0; cycles[1] = t2 - t0; *status = ok ? 0 : 1; }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+template <int N, bool TS, bool ALT>
+static int run_tput(const char* name) {
+  long long* dc; int* ds;
+  cudaMalloc(&dc, 16); cudaMalloc(&ds, 4);
+  const size_t smem = 16384 + N * 128 * 2 + 1024;
+  cudaFuncSetAttribute(tput<N, TS, ALT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  tput<N, TS, ALT><<<1, 128, smem>>>(dc, ds);
+  cudaError_t e = cudaDeviceSynchronize();
+  long long c[2]; int st;
+  cudaMemcpy(c, dc, 16, cudaMemcpyDeviceToHost); cudaMemcpy(&st, ds, 4, cudaMemcpyDeviceToHost);
+  printf("[tput] %s: %s issue %lld cyc, issue+complete %lld cyc for 64 MMAs (%.1f cyc/MMA)%s\n", name,
+         e == cudaSuccess ? "ok" : cudaGetErrorString(e), c[0], c[1], c[1] / 64.0, st ? " TIMEOUT" : "");
+  return 0;
+}
+
 // ---- host ------------------------------------------------------------------------------------
 static int esz(int kind) { return kind == 0 ? 2 : 4; }
 
@@ -118,6 +183,13 @@ static void put(std::vector<uint8_t>& img, uint32_t o, int kind, float v) {
 
 int main(int argc, char** argv) {
   const int t = argc > 1 ? atoi(argv[1]) : 0;
+  if (t == 20) return run_tput<128, false, false>("SS M128 N128 K16");
+  if (t == 21) return run_tput<128, true, false>("TS M128 N128 K16");
+  if (t == 22) return run_tput<256, false, false>("SS M128 N256 K16");
+  if (t == 23) return run_tput<256, true, false>("TS M128 N256 K16");
+  if (t == 24) return run_tput<64, false, false>("SS M128 N64 K16");
+  if (t == 25) return run_tput<128, true, true>("TS M128 N128 K16, two accumulators alternating");
+  if (t == 26) return run_tput<128, false, true>("SS M128 N128 K16, two accumulators alternating");
   Cfg c{};
   c.repeat = 1;
   const char* name = "";
