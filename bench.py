@@ -130,7 +130,7 @@ def build_model(device):
     from swem_b200 import SWEM, make_config
     torch.manual_seed(0)
     model = SWEM(make_config(**CFG)).eval().to(device)
-    if os.environ.get('SWEM_CHANNELS_LAST', '0') == '1':      # torch-side experiment; numerics unchanged
+    if os.environ.get('SWEM_CHANNELS_LAST', '1') == '1':      # torch-side layout choice (cuDNN picks NHWC kernels anyway)
         model = model.to(memory_format=torch.channels_last)
     return model
 
@@ -292,7 +292,7 @@ def run_b200(args, rank, world, local_rank):
         'data': 'synthetic',
         'config': workload_config(n_obj, {'kernel_family': family, 'l2': 'every step reads a new 5 MB frame and '
                                           '>230 MB of fp32 weights + activations (> 126 MB L2); no explicit flush',
-                                          'torch_convs': 'cudnn, allow_tf32 default'}),
+                                          'torch_convs': 'cudnn, allow_tf32 default, channels_last=' + os.environ.get('SWEM_CHANNELS_LAST', '1')}),
         'e2e': {'value': fps_e2e, 'unit': UNIT, 'h2d_bytes_per_step': 3 * H * W * 4, 'd2h_bytes_per_step': H * W,
                 'ms_per_step': ms_e2e / K},
         'gpu_launches': n_launch,

@@ -4,6 +4,8 @@
 #include <cuda_fp16.h>
 #include <stdint.h>
 
+#include "tc05.cuh"
+
 namespace swem {
 
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
@@ -21,6 +23,17 @@ __device__ __forceinline__ bool wait_counter(const unsigned* counter, unsigned t
   }
   return false;
 }
+
+// Block-wide wait on an mbarrier phase: ONE thread polls, everybody else parks on the hardware barrier.
+// (256 threads polling try_wait starve the single issuing thread of the very mbarrier / TMA / MMA slots
+//  it needs -- measured 5x slower MMA issue loops.)  A time-out latches `abort_flag` (uniform after the barrier).
+#define SWEM_CTA_WAIT(bar, parity, abort_flag)                 \
+  do {                                                         \
+    if (threadIdx.x == 0) {                                    \
+      if (!tc05::mbar_wait((bar), (parity))) (abort_flag) = 1; \
+    }                                                          \
+    __syncthreads();                                           \
+  } while (0)
 
 __device__ __forceinline__ long long global_ns() {
   long long t;

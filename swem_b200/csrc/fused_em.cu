@@ -185,7 +185,6 @@ __global__ void __launch_bounds__(256, 1) em_fused_kernel(const EmFusedParams p)
   tc_fence_after_sync();
   const uint32_t tmem = ms.tmem_base;
   uint32_t ph_mma = 0, ph_tma = 0;   // mbarrier phase parities
-  bool ok = true;
 
   // thread <-> basis row r = tid (side = r / 128, l = r % 128) in the finalize steps
   const int row_s = tid >> 7, row_l = tid & 127;
@@ -249,7 +248,7 @@ __global__ void __launch_bounds__(256, 1) em_fused_kernel(const EmFusedParams p)
       }
       __syncwarp();
     }
-    ok = ok && mbar_wait(&ms.bar_mma, ph_mma);
+    SWEM_CTA_WAIT(&ms.bar_mma, ph_mma, ms.abort_flag);
     ph_mma ^= 1;
     tc_fence_after_sync();
     EM_STAMP();                      // logits GEMM done
@@ -340,7 +339,7 @@ __global__ void __launch_bounds__(256, 1) em_fused_kernel(const EmFusedParams p)
       }
       __syncwarp();
     }
-    ok = ok && mbar_wait(&ms.bar_mma, ph_mma);
+    SWEM_CTA_WAIT(&ms.bar_mma, ph_mma, ms.abort_flag);
     ph_mma ^= 1;
     tc_fence_after_sync();
 
@@ -370,39 +369,52 @@ __global__ void __launch_bounds__(256, 1) em_fused_kernel(const EmFusedParams p)
       // ---- nu partial = Z^T V^T, two passes over value-channel halves (Z must still be intact) --------
       __syncthreads();
       tc_fence_after_sync();
-      uint32_t ph_stage[3] = {0, 0, 0};
-      int chunk_seq = 0;
-      for (int half = 0; half < 2; ++half) {
-        for (int ch = 0; ch < 4; ++ch, ++chunk_seq) {
-          const int st = chunk_seq % 3;
-          if (chunk_seq >= 3) {          // stage reuse: wait for the MMAs that read it
-            ok = ok && mbar_wait(&ms.bar_stage[st], ph_stage[st]);
-            ph_stage[st] ^= 1;
-          }
-          // V chunk [256 d][32 px] fp32 -> fp16 K-major B operand.  A warp reads 4 rows x 128 B per
-          // instruction (lane -> row lane/8, pixels 4*(lane%8)..+3), 8 instructions cover its 32 rows.
-          {
-            uint8_t* stage = smem + kOffVS + st * kVStage;
-            const int px4 = (lane & 7) * 4;
-            const int pxg = p0 + ch * 32 + px4;
+      // V chunk (seq = half*4 + ch): [256 d][32 px] fp32.  A warp reads 4 rows x 128 B per instruction
+      // (lane -> row lane/8, pixels 4*(lane%8)..+3); 8 instructions cover its 32 rows.  Loads of chunk
+      // seq+1 are issued into registers before chunk seq is converted and staged (software prefetch).
+      const int px4 = (lane & 7) * 4;
+      const bool vec_ok = (HW & 3) == 0;
+      auto load_chunk = [&](int seq, float4 (&buf)[8]) {
+        const int half = seq >> 2, ch = seq & 3;
+        const int pxg = p0 + ch * 32 + px4;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const int dl = warp * 32 + j * 4 + (lane >> 3);          // row within this half
-              const float* src = p.v + ((size_t)u * kCv + half * 256 + dl) * HW + pxg;
-              float f0 = 0.f, f1 = 0.f, f2 = 0.f, f3 = 0.f;
-              if (pxg + 3 < HW) {
-                f0 = __ldg(src); f1 = __ldg(src + 1); f2 = __ldg(src + 2); f3 = __ldg(src + 3);
-              } else {
-                if (pxg < HW) f0 = __ldg(src);
-                if (pxg + 1 < HW) f1 = __ldg(src + 1);
-                if (pxg + 2 < HW) f2 = __ldg(src + 2);
-              }
-              uint2 pk;
-              pk.x = pack_half2(f0, f1);
-              pk.y = pack_half2(f2, f3);
-              *reinterpret_cast<uint2*>(stage + (dl % 8) * 16 + (dl / 8) * 128 + (px4 / 8) * 4096 + (px4 % 8) * 2) = pk;
-            }
+        for (int j = 0; j < 8; ++j) {
+          const int dl = warp * 32 + j * 4 + (lane >> 3);
+          const float* src = p.v + ((size_t)u * kCv + half * 256 + dl) * HW + pxg;
+          float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (vec_ok && pxg + 3 < HW) {
+            f = __ldg(reinterpret_cast<const float4*>(src));
+          } else {
+            if (pxg < HW) f.x = __ldg(src);
+            if (pxg + 1 < HW) f.y = __ldg(src + 1);
+            if (pxg + 2 < HW) f.z = __ldg(src + 2);
+            if (pxg + 3 < HW) f.w = __ldg(src + 3);
           }
+          buf[j] = f;
+        }
+      };
+      auto store_chunk = [&](int st, const float4 (&buf)[8]) {
+        uint8_t* stage = smem + kOffVS + st * kVStage;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int dl = warp * 32 + j * 4 + (lane >> 3);
+          uint2 pk;
+          pk.x = pack_half2(buf[j].x, buf[j].y);
+          pk.y = pack_half2(buf[j].z, buf[j].w);
+          *reinterpret_cast<uint2*>(stage + (dl % 8) * 16 + (dl / 8) * 128 + (px4 / 8) * 4096 + (px4 % 8) * 2) = pk;
+        }
+      };
+      float4 vbuf[2][8];
+      load_chunk(0, vbuf[0]);
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          const int seq = half * 4 + ch;
+          const int st = seq % 3;
+          if (seq + 1 < 8) load_chunk(seq + 1, vbuf[(seq + 1) & 1]);
+          if (seq >= 3) SWEM_CTA_WAIT(&ms.bar_stage[st], ((seq / 3) - 1) & 1, ms.abort_flag);   // stage reuse: its MMAs retired
+          store_chunk(st, vbuf[seq & 1]);
           fence_proxy_async_smem();
           tc_fence_before_sync();
           __syncthreads();
@@ -428,15 +440,21 @@ __global__ void __launch_bounds__(256, 1) em_fused_kernel(const EmFusedParams p)
             __syncwarp();
           }
         }
-        ok = ok && mbar_wait(&ms.bar_mma, ph_mma);
+        SWEM_CTA_WAIT(&ms.bar_mma, ph_mma, ms.abort_flag);
         ph_mma ^= 1;
         tc_fence_after_sync();
         EM_STAMP();                  // nu pass GEMMs done
-        // drain: TMEM [side][128 l][256 d] -> smem [side][64 d][128 l] -> bulk reduce-add into acc_nu
+        // drain: TMEM [side][128 l][256 d] -> smem [side][32 d][128 l] -> bulk reduce-add into acc_nu.  Two staging
+        // buffers (the dead X region and the first V stage, both idle now): round q only waits for the reads of q-2.
         {
           const int sd = warp >> 2, l = (warp & 3) * 32 + lane;
-          float* ns = reinterpret_cast<float*>(smem + kOffNS);
+#pragma unroll 1
           for (int q = 0; q < 8; ++q) {
+            float* ns = reinterpret_cast<float*>(smem + ((q & 1) ? kOffVS : kOffNS));
+            if (q >= 2) {
+              if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+              __syncthreads();
+            }
             {
               uint32_t r[32];
               tmem_ld32(tmem_addr(tmem, (warp & 3) * 32, kColNu + sd * 256 + q * 32), r);
@@ -455,10 +473,9 @@ __global__ void __launch_bounds__(256, 1) em_fused_kernel(const EmFusedParams p)
                              : "memory");
               }
               asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-              asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
             }
-            __syncthreads();
           }
+          if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging may be reused now
         }
         tc_fence_before_sync();
         __syncthreads();
@@ -505,9 +522,9 @@ __global__ void __launch_bounds__(256, 1) em_fused_kernel(const EmFusedParams p)
       }
       __syncwarp();
     }
-    ok = ok && mbar_wait(&ms.bar_tma, ph_tma);
+    SWEM_CTA_WAIT(&ms.bar_tma, ph_tma, ms.abort_flag);
     ph_tma ^= 1;
-    if (__syncthreads_or((!ok) || ms.abort_flag)) {
+    if (ms.abort_flag) {
       if (tid == 0) atomicExch(p.status, 1 + it);
       failed = true;
       break;
@@ -518,9 +535,10 @@ __global__ void __launch_bounds__(256, 1) em_fused_kernel(const EmFusedParams p)
       const float* P = reinterpret_cast<const float*>(smem + kOffZ) + tid * kAccRow;
       constexpr float kInvZ = 1.f / kZScale;
       const float zita_cur = zita_p + P[kCk] * kInvZ;
+      const float rz = 1.f / zita_cur;
       float kap[kCk];
 #pragma unroll
-      for (int c = 0; c < kCk; ++c) kap[c] = (zita_p * kpr[c] + P[c] * kInvZ) / zita_cur;
+      for (int c = 0; c < kCk; ++c) kap[c] = (zita_p * kpr[c] + P[c] * kInvZ) * rz;
       if (last) {
         ms.zita[tid] = zita_cur;
         if (tile == 0) {
@@ -537,38 +555,35 @@ __global__ void __launch_bounds__(256, 1) em_fused_kernel(const EmFusedParams p)
     EM_STAMP();                      // finalize done
   }
 
-  // ---- nu: all tiles have reduce-added their partials; normalise a slice (reference :164-165) -------------
-  if (!failed) {
-    unsigned* counter = p.counters + (size_t)u * (I + 1) + I;
-    if (tid == 0) {
-      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-      __threadfence();
-      atomicAdd(counter, 1u);
-      if (!wait_counter(counter, (unsigned)p.T)) {
-        ms.abort_flag = 1;
-        atomicExch(p.status, 100);
-      }
-      __threadfence();
-    }
-    __syncthreads();
-    if (!ms.abort_flag) {
-      // rows (s, d) of nu, 128 l each; this CTA takes rows tile, tile + T, ...; two rows per pass
-      const int l = tid & 127;
-      for (int row = tile * 2 + (tid >> 7); row < 2 * kCv; row += 2 * p.T) {
-        const int s = row / kCv, d = row % kCv;
-        const size_t idx = (((size_t)u * 2 + s) * kCv + d) * kL + l;
-        const float zp = __ldg(p.zita_prior + ((size_t)u * 2 + s) * kL + l);
-        const float sumv = __ldcg(p.acc_nu + idx) * (1.f / kZScale);
-        p.nu[idx] = (zp * __ldg(p.nu_prior + idx) + sumv) / ms.zita[s * kL + l];
-      }
-    }
-  }
+  // nu = (zita_ nu_ + acc_nu / 2^14) / zita (reference :164-165) is applied by nu_finalize_kernel, launched right
+  // after this kernel: stream order replaces a third cross-CTA wait here.
   tc_fence_before_sync();
   __syncthreads();
-  EM_STAMP();                        // nu normalised
+  EM_STAMP();                        // done
   if (p.prof != nullptr && blockIdx.x == 0 && tid == 0) p.prof[0] = n_stamp;
   if (warp == 0) tmem_dealloc(tmem, 512);
   if (failed || ms.abort_flag) __trap();   // surface a protocol time-out as a CUDA error, never as silent garbage
+}
+
+// nu[g][d][l] = (zita_prior[g][l] * nu_prior[g][d][l] + acc_nu[g][d][l] / 2^14) / zita[g][l],  g = (b, n, s)
+__global__ void nu_finalize_kernel(const float* __restrict__ acc_nu, const float* __restrict__ nu_prior,
+                                   const float* __restrict__ zita_prior, const float* __restrict__ zita,
+                                   float* __restrict__ nu, int G) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;          // float4 index
+  if (i >= G * em::kCv * em::kL / 4) return;
+  const int l4 = i % (em::kL / 4);
+  const int g = i / (em::kCv * em::kL / 4);
+  const float4 a = __ldcg(reinterpret_cast<const float4*>(acc_nu) + i);
+  const float4 pr = __ldg(reinterpret_cast<const float4*>(nu_prior) + i);
+  const float4 zp = __ldg(reinterpret_cast<const float4*>(zita_prior) + g * (em::kL / 4) + l4);
+  const float4 z = __ldg(reinterpret_cast<const float4*>(zita) + g * (em::kL / 4) + l4);
+  constexpr float k = 1.f / em::kZScale;
+  float4 o;
+  o.x = (zp.x * pr.x + a.x * k) / z.x;
+  o.y = (zp.y * pr.y + a.y * k) / z.y;
+  o.z = (zp.z * pr.z + a.z * k) / z.z;
+  o.w = (zp.w * pr.w + a.w * k) / z.w;
+  reinterpret_cast<float4*>(nu)[i] = o;
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -634,6 +649,11 @@ int fused_em_forward(const SwemEmArgs& a, cudaStream_t st) {
     const int nu = (U - u0 < units_per_launch) ? (U - u0) : units_per_launch;
     p.u0 = u0;
     em_fused_kernel<<<nu * T, 256, em::kSmemBytes, st>>>(p);
+    SWEM_LAUNCH_CHECK();
+  }
+  {
+    const int n4 = U * 2 * em::kCv * em::kL / 4;
+    nu_finalize_kernel<<<(n4 + 255) / 256, 256, 0, st>>>(acc_nu, a.nu_prior, a.zita_prior, a.zita, a.nu, U * 2);
     SWEM_LAUNCH_CHECK();
   }
   return SWEM_OK;

@@ -20,6 +20,7 @@
 // mem_out lands in channels [mem_channel, +Cv) and S in [s_channel, +2*topl) of the caller's
 // concat buffer (:291), so no torch.cat of those pieces is needed.
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "fused_common.cuh"
@@ -56,7 +57,7 @@ struct Misc {
   uint64_t bar_full[kStages];
   uint64_t bar_empty[kStages];
   uint32_t tmem_base;
-  int pad;
+  int abort_flag;
 };
 constexpr uint32_t kSmemBytes = kOffMisc + sizeof(Misc) + 128;
 static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
@@ -174,6 +175,7 @@ __global__ void __launch_bounds__(256, 1) readout_fused_kernel(const ReadoutFuse
       mbar_init(&ms.bar_full[i], 1);
       mbar_init(&ms.bar_empty[i], 1);
     }
+    ms.abort_flag = 0;
     fence_mbar_init();
     // khat blobs of both sides (hi + lo planes are contiguous): two bulk copies
     for (int s = 0; s < 2; ++s) {
@@ -247,7 +249,7 @@ __global__ void __launch_bounds__(256, 1) readout_fused_kernel(const ReadoutFuse
     }
     __syncwarp();
   }
-  ok = mbar_wait(&ms.bar_mma, 0) && ok;
+  SWEM_CTA_WAIT(&ms.bar_mma, 0, ms.abort_flag);
   tc_fence_after_sync();
   RO_STAMP();   // scores done
 
@@ -255,6 +257,7 @@ __global__ void __launch_bounds__(256, 1) readout_fused_kernel(const ReadoutFuse
   const uint8_t* vsrc = p.vblob + ((size_t)u * 2 + h) * ks2 * kStageBytes;
   if (tid == 0) {
     fence_proxy_async_smem();
+#pragma unroll
     for (int kk = 0; kk < kStages && kk < ks2; ++kk) {
       mbar_expect_tx(&ms.bar_full[kk], kStageBytes);
       bulk_g2s(smem + kOffRing + kk * kStageBytes, vsrc + (size_t)kk * kStageBytes, kStageBytes, &ms.bar_full[kk]);
@@ -333,48 +336,37 @@ __global__ void __launch_bounds__(256, 1) readout_fused_kernel(const ReadoutFuse
   if (warp == 0) {
     if (lane == 0) {
     const uint32_t idesc = make_idesc(128, 128, kFmtF16, kFmtF16, kMajorK, kMajorK);
+    // One thread issues everything, so this loop is latency-bound on its own instruction stream: keep it
+    // lean (descriptors advanced by constant adds, every index a compile-time constant after unrolling).
     constexpr int kLag = 3;     // refill the stage consumed kLag steps ago: its MMAs have retired, no issue stall
-    long long c_full = 0, c_issue = 0, c_empty = 0;   // diagnostics (cycles), only stored when profiling
+    const uint64_t bdesc0 = make_sdesc(sbase + kOffRing, /*lbo*/ 4096, /*sbo*/ 128);
 #pragma unroll
     for (int kk = 0; kk < ks2; ++kk) {
       const int st = kk % kStages;
-      const long long c0 = clock64();
       ok = mbar_wait(&ms.bar_full[st], (kk / kStages) & 1) && ok;
       tc_fence_after_sync();
-      const long long c1 = clock64();
       const uint32_t a_tmem = tmem + (kk / ks_side) * 256 + (kk % ks_side) * 8;
-      const uint32_t vb = sbase + kOffRing + st * kStageBytes;
 #pragma unroll
       for (int term = 0; term < 2; ++term)
 #pragma unroll
-        for (int nh = 0; nh < 2; ++nh) {
-          const uint64_t bd = make_sdesc(vb + term * 8192 + nh * 2048, /*lbo*/ 4096, /*sbo*/ 128);
-          mma_f16_ts(tmem + 128 + nh * 256, a_tmem, bd, idesc, (kk | term) ? 1u : 0u);
-        }
+        for (int nh = 0; nh < 2; ++nh)
+          mma_f16_ts(tmem + 128 + nh * 256, a_tmem, bdesc0 + ((st * kStageBytes + term * 8192 + nh * 2048) >> 4), idesc,
+                     (kk | term) ? 1u : 0u);
       mma_commit(&ms.bar_empty[st]);
-      const long long c2 = clock64();
-      c_full += c1 - c0;
-      c_issue += c2 - c1;
       if (kk >= kLag && kk - kLag + kStages < ks2) {
         const int prev = kk - kLag, nxt = prev + kStages;
         const int ps = prev % kStages;
         ok = mbar_wait(&ms.bar_empty[ps], (prev / kStages) & 1) && ok;
         mbar_expect_tx(&ms.bar_full[ps], kStageBytes);
         bulk_g2s(smem + kOffRing + ps * kStageBytes, vsrc + (size_t)nxt * kStageBytes, kStageBytes, &ms.bar_full[ps]);
-        c_empty += clock64() - c2;
       }
-    }
-    if (p.prof != nullptr && blockIdx.x == 0) {
-      p.prof[230] = c_full;
-      p.prof[231] = c_issue;
-      p.prof[232] = c_empty;
     }
     mma_commit(&ms.bar_mma);
     }
     __syncwarp();
   }
   RO_STAMP();   // PV issued
-  ok = mbar_wait(&ms.bar_mma, 1) && ok;
+  SWEM_CTA_WAIT(&ms.bar_mma, 1, ms.abort_flag);
   tc_fence_after_sync();
   RO_STAMP();   // PV done
 
@@ -395,7 +387,7 @@ __global__ void __launch_bounds__(256, 1) readout_fused_kernel(const ReadoutFuse
     }
   }
   tc_fence_before_sync();
-  const int bad = __syncthreads_or(!ok);
+  const int bad = __syncthreads_or((!ok) || ms.abort_flag);
   RO_STAMP();   // stored
   if (p.prof != nullptr && blockIdx.x == 0 && tid == 0) p.prof[128] = n_stamp;
   if (warp == 0) tmem_dealloc(tmem, 512);

@@ -38,6 +38,8 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity
 // Bounded wait: returns false if the phase did not complete within ~max_spins polls, so a wrong
 // descriptor shows up as an error code instead of a hung GPU.
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, uint32_t max_spins = (1u << 24)) {
+  if (mbar_try_wait(bar, parity)) return true;      // common case inline; the retry loop stays rolled
+#pragma unroll 1
   for (uint32_t i = 0; i < max_spins; ++i)
     if (mbar_try_wait(bar, parity)) return true;
   return false;

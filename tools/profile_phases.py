@@ -32,7 +32,7 @@ def main(N=5, H=30, W=54, I=4, reps=50):
             if it == I - 1:
                 names += ['nu pass0 GEMM', 'nu pass0 drain', 'nu pass1 GEMM', 'nu pass1 drain']
             names += [f'it{it} reduce-add', f'it{it} wait tiles', f'it{it} load total', f'it{it} finalize']
-        names += ['nu normalise']
+        names += ['exit']
         for k in range(1, n):
             print(f'  {names[k-1] if k-1 < len(names) else "?":24s} {(t[k]-t[k-1])/1e3:8.2f} us')
         _lib.check(lib.swem_set_profile_buffer(buf.data_ptr(), buf.numel() * 8), 'set_profile')
@@ -46,7 +46,6 @@ def main(N=5, H=30, W=54, I=4, reps=50):
         print(f'readout_fused CTA0: total {(t[-1]-t[0])/1e3:.1f} us')
         for k in range(1, n):
             print(f'  {rn[k-1] if k-1 < len(rn) else "?":24s} {(t[k]-t[k-1])/1e3:8.2f} us')
-        print(f'  PV loop cycles: wait-full {st[230]}  issue {st[231]}  wait-empty+tma {st[232]}')
         for name, fn in (('memorize(EM)', lambda: core.swem(x, v, masks, prior)),
                          ('readout', lambda: core.matching_features(x, v[:, 0]))):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
