@@ -12,6 +12,8 @@
  *                            + perm_inv_feat :198-208 + the l2norms of matching :282-283
  *                            + the concat placement of matching :291
  *   swem_em_masks         <- mask prep of SWEM.memorize  methods/SWEM/swem.py:80-84
+ *   swem_decode_tail      <- final up-sampling of Decoder.forward (methods/basic_modules/networks.py:214-215)
+ *                            + SWEM.decode / aggregate      methods/SWEM/swem.py:92-116
  *
  * Conventions
  *   - every pointer is a DEVICE pointer to contiguous fp32 (row-major, last index fastest) unless
@@ -114,6 +116,14 @@ int swem_em_masks(const int64_t* hard, int32_t Hm, int32_t Wm,
                   const float* soft, int32_t Hs, int32_t Ws,
                   int32_t B, int32_t N, int32_t H16, int32_t W16,
                   float* out, void* stream);
+
+/* ---- decoder tail: Decoder.forward's final F.interpolate (networks.py:214-215) + SWEM.decode / aggregate
+ * (swem.py:92-116), one pass.  logits_lr: [B*N, Hl, Wl] output of the decoder's `pred` conv (1/4 resolution);
+ * bilinear (align_corners = false) to (H, W), sigmoid, optional valid_obj [B, N+1] mask (:100-101),
+ * background = prod(1 - p), clamp to [1e-7, 1-1e-7], logit, softmax over the N+1 classes.
+ * logits_out, prob_out: [B, N+1, H, W].  N <= 16.                                                    */
+int swem_decode_tail(const float* logits_lr, int32_t B, int32_t N, int32_t Hl, int32_t Wl, int32_t H, int32_t W,
+                     const float* valid_obj, float* logits_out, float* prob_out, void* stream);
 
 /* ---- misc ------------------------------------------------------------------------------------ */
 int         swem_abi_version(void);          /* == SWEM_B200_ABI_VERSION                          */

@@ -17,7 +17,7 @@ EXPORTS = (
     'swem_abi_version', 'swem_last_error', 'swem_device_check', 'swem_last_launch_count',
     'swem_em_workspace_bytes', 'swem_em_forward', 'swem_em_fused_supported',
     'swem_readout_workspace_bytes', 'swem_readout_forward', 'swem_readout_fused_supported',
-    'swem_em_masks', 'swem_set_profile_buffer',
+    'swem_em_masks', 'swem_decode_tail', 'swem_set_profile_buffer',
 )
 
 
@@ -74,6 +74,7 @@ def load() -> C.CDLL:
     lib.swem_readout_fused_supported.argtypes = [C.POINTER(SwemDims)]
     lib.swem_em_masks.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32,
                                   C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
+    lib.swem_decode_tail.argtypes = [C.c_void_p] + [C.c_int32] * 6 + [C.c_void_p] * 4
     lib.swem_set_profile_buffer.argtypes = [C.c_void_p, C.c_size_t]
     if lib.swem_abi_version() != 1:
         raise RuntimeError(f'libswem_b200.so ABI version {lib.swem_abi_version()} != 1')

@@ -67,6 +67,53 @@ __global__ void em_masks_kernel(const long long* __restrict__ hard, int Hm, int 
   op[(long long)H * W] = hv * sv;
 }
 
+// ------------------------------------------------------------------------------------------
+// decoder tail (reference networks.py:214-215 + swem.py:92-116): bilinear up-sampling of the N per-object
+// logit planes to the output size, sigmoid, soft aggregation with the background product, clamp, logit,
+// softmax over the N+1 classes -- one pass over the output instead of ~12 element-wise launches.
+// ------------------------------------------------------------------------------------------
+constexpr int kMaxTailObjs = 16;
+
+__global__ void decode_tail_kernel(const float* __restrict__ lr, int B, int N, int Hl, int Wl, int H, int W,
+                                   const float* __restrict__ valid, float* __restrict__ logits_out,
+                                   float* __restrict__ prob_out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * H * W) return;
+  const int x = i % W, y = (i / W) % H, b = i / (W * H);
+  const float sh = (float)Hl / (float)H, sw = (float)Wl / (float)W;
+  float sy = sh * (y + 0.5f) - 0.5f, sx = sw * (x + 0.5f) - 0.5f;
+  sy = sy < 0.f ? 0.f : sy;
+  sx = sx < 0.f ? 0.f : sx;
+  const int y0 = min((int)sy, Hl - 1), x0 = min((int)sx, Wl - 1);
+  const int y1 = y0 + (y0 < Hl - 1 ? 1 : 0), x1 = x0 + (x0 < Wl - 1 ? 1 : 0);
+  const float ly = sy - y0, lx = sx - x0, my = 1.f - ly, mx = 1.f - lx;
+  float prob[kMaxTailObjs + 1];
+  float bg = 1.f;
+  for (int n = 0; n < N; ++n) {
+    const float* pl = lr + (size_t)(b * N + n) * Hl * Wl;
+    const float v = my * (mx * pl[y0 * Wl + x0] + lx * pl[y0 * Wl + x1]) + ly * (mx * pl[y1 * Wl + x0] + lx * pl[y1 * Wl + x1]);
+    float pr = 1.f / (1.f + expf(-v));
+    if (valid != nullptr) pr *= valid[b * (N + 1) + n + 1];
+    prob[n + 1] = pr;
+    bg *= 1.f - pr;
+  }
+  prob[0] = bg;
+  float mxl = -3.0e38f;
+  for (int k = 0; k <= N; ++k) {
+    const float c = fminf(fmaxf(prob[k], 1e-7f), 1.f - 1e-7f);
+    const float lg = logf(c / (1.f - c));
+    prob[k] = lg;
+    mxl = fmaxf(mxl, lg);
+    logits_out[((size_t)(b * (N + 1) + k) * H + y) * W + x] = lg;
+  }
+  float sum = 0.f;
+  for (int k = 0; k <= N; ++k) {
+    prob[k] = expf(prob[k] - mxl);
+    sum += prob[k];
+  }
+  for (int k = 0; k <= N; ++k) prob_out[((size_t)(b * (N + 1) + k) * H + y) * W + x] = prob[k] / sum;
+}
+
 }  // namespace swem
 
 using namespace swem;
@@ -171,6 +218,22 @@ int swem_em_masks(const int64_t* hard, int32_t Hm, int32_t Wm, const float* soft
   const int n = B * N * H16 * W16;
   em_masks_kernel<<<(n + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const long long*>(hard), Hm, Wm, soft, Hs, Ws, B, N, H16, W16, out);
+  SWEM_LAUNCH_CHECK();
+  return SWEM_OK;
+}
+
+int swem_decode_tail(const float* logits_lr, int32_t B, int32_t N, int32_t Hl, int32_t Wl, int32_t H, int32_t W,
+                     const float* valid_obj, float* logits_out, float* prob_out, void* stream) {
+  reset_launch_count();
+  SWEM_CHECK_ARG(logits_lr && logits_out && prob_out, "NULL pointer");
+  SWEM_CHECK_ARG(B > 0 && N > 0 && Hl > 0 && Wl > 0 && H > 0 && W > 0, "non-positive size");
+  if (N > kMaxTailObjs) {
+    set_error("decode tail supports at most %d objects (got %d)", kMaxTailObjs, N);
+    return SWEM_ERR_UNSUPPORTED;
+  }
+  const int n = B * H * W;
+  decode_tail_kernel<<<(n + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(logits_lr, B, N, Hl, Wl, H, W, valid_obj,
+                                                                                     logits_out, prob_out);
   SWEM_LAUNCH_CHECK();
   return SWEM_OK;
 }

@@ -135,6 +135,30 @@ __global__ void __launch_bounds__(256, 1) em_fused_kernel(const EmFusedParams p)
     ms.abort_flag = 0;
     fence_mbar_init();
   }
+  // thread <-> basis row r = tid (side = r / 128, l = r % 128) in the finalize steps
+  const int row_s = tid >> 7, row_l = tid & 127;
+  const float zita_p = __ldg(p.zita_prior + ((size_t)u * 2 + row_s) * kL + row_l);
+  const float* kprior = p.kappa_prior + (((size_t)u * 2 + row_s) * kCk) * kL + row_l;   // + c*kL
+  // khat = l2norm(kappa) * 256 -> fp16 hi/lo rows of the K-major B operand (reference :115)
+  auto stage_khat = [&](const float (&kap)[kCk]) {
+    float ss = 0.f;
+#pragma unroll
+    for (int c = 0; c < kCk; ++c) ss = fmaf(kap[c], kap[c], ss);
+    const float sc = kKScale / (sqrtf(ss) + kEpsNorm);
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      __align__(16) __half hi[8];
+      __align__(16) __half lo[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) split_half(kap[g * 8 + e] * sc, hi[e], lo[e]);
+      const uint32_t off = (tid % 8) * 16 + (tid / 8) * 128 + g * 4096;
+      *reinterpret_cast<uint4*>(smem + kOffKH + off) = *reinterpret_cast<uint4*>(hi);
+      *reinterpret_cast<uint4*>(smem + kOffKL + off) = *reinterpret_cast<uint4*>(lo);
+    }
+  };
+  float kap0[kCk];                   // kappa^0 = prior: loads issued first, consumed after the X tile is staged
+#pragma unroll
+  for (int c = 0; c < kCk; ++c) kap0[c] = __ldg(kprior + (size_t)c * kL);
   // pixel norms + masks (thread <-> pixel)
   if (tid < kTP) {
     const int px = p0 + tid;
@@ -180,39 +204,13 @@ __global__ void __launch_bounds__(256, 1) em_fused_kernel(const EmFusedParams p)
       *reinterpret_cast<uint4*>(smem + kOffXH + (r % 8) * 16 + (r / 8) * 2048 + pg * 128) = *reinterpret_cast<uint4*>(vals);
     }
   }
+  stage_khat(kap0);
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem = ms.tmem_base;
   uint32_t ph_mma = 0, ph_tma = 0;   // mbarrier phase parities
 
-  // thread <-> basis row r = tid (side = r / 128, l = r % 128) in the finalize steps
-  const int row_s = tid >> 7, row_l = tid & 127;
-  const float zita_p = __ldg(p.zita_prior + ((size_t)u * 2 + row_s) * kL + row_l);
-  const float* kprior = p.kappa_prior + (((size_t)u * 2 + row_s) * kCk) * kL + row_l;   // + c*kL
-  // khat = l2norm(kappa) * 256 -> fp16 hi/lo rows of the K-major B operand (reference :115)
-  auto stage_khat = [&](const float (&kap)[kCk]) {
-    float ss = 0.f;
-#pragma unroll
-    for (int c = 0; c < kCk; ++c) ss = fmaf(kap[c], kap[c], ss);
-    const float sc = kKScale / (sqrtf(ss) + kEpsNorm);
-#pragma unroll
-    for (int g = 0; g < 8; ++g) {
-      __align__(16) __half hi[8];
-      __align__(16) __half lo[8];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) split_half(kap[g * 8 + e] * sc, hi[e], lo[e]);
-      const uint32_t off = (tid % 8) * 16 + (tid / 8) * 128 + g * 4096;
-      *reinterpret_cast<uint4*>(smem + kOffKH + off) = *reinterpret_cast<uint4*>(hi);
-      *reinterpret_cast<uint4*>(smem + kOffKL + off) = *reinterpret_cast<uint4*>(lo);
-    }
-  };
-  {
-    float kap[kCk];                  // kappa^0 = prior
-#pragma unroll
-    for (int c = 0; c < kCk; ++c) kap[c] = __ldg(kprior + (size_t)c * kL);
-    stage_khat(kap);
-  }
   bool failed = false;               // block-uniform
   EM_STAMP();                        // setup done
 
@@ -428,10 +426,9 @@ __global__ void __launch_bounds__(256, 1) em_fused_kernel(const EmFusedParams p)
 #pragma unroll
               for (int kk = 0; kk < 2; ++kk) {
                 const uint64_t ad = make_sdesc(za + (ch * 2 + kk) * 2 * 128, /*lbo*/ 128, /*sbo*/ 2048);
-                const uint64_t al = make_sdesc(za + (kOffZL - kOffZ) + (ch * 2 + kk) * 2 * 128, /*lbo*/ 128, /*sbo*/ 2048);
                 const uint64_t bd = make_sdesc(vb + kk * 2 * 4096, /*lbo*/ 4096, /*sbo*/ 128);
+                // z_hi only: v is a single fp16 here, so the z_lo term would not improve nu
                 mma_f16_ss(tmem + kColNu + sd * 256, ad, bd, idesc_nu, (ch | kk) ? 1u : 0u);
-                mma_f16_ss(tmem + kColNu + sd * 256, al, bd, idesc_nu, 1u);
               }
             }
             mma_commit(&ms.bar_stage[st]);

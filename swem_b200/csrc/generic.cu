@@ -301,13 +301,14 @@ __global__ void __launch_bounds__(256) perm_inv_kernel(const float* __restrict__
                                                        int s_channel) {
   constexpr int N = 32 * NPL;
   constexpr int IDXB = (NPL == 1 ? 5 : NPL == 2 ? 6 : NPL == 4 ? 7 : NPL == 8 ? 8 : NPL == 16 ? 9 : 10);
-  extern __shared__ float tile[];                               // [2*topl][33] then uint32 top[8 warps][2][64]
-  uint32_t* top = reinterpret_cast<uint32_t*>(tile + 2 * topl * 33);
+  constexpr int PXB = 8;                                        // pixels per block: one per warp (many small blocks balance the SMs)
+  extern __shared__ float tile[];                               // [2*topl][PXB+1] then uint32 top[8 warps][2][64]
+  uint32_t* top = reinterpret_cast<uint32_t*>(tile + 2 * topl * (PXB + 1));
   const int u = blockIdx.y;
-  const int p_base = blockIdx.x * 32;
+  const int p_base = blockIdx.x * PXB;
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint32_t* mytop = top + wid * 128;
-  for (int q = wid; q < 32; q += 8) {
+  for (int q = wid; q < PXB; q += 8) {
     const int p = p_base + q;
     if (p >= HW) break;
     const float* row = P + ((long long)u * HW + p) * (2 * Lt);
@@ -359,17 +360,17 @@ __global__ void __launch_bounds__(256) perm_inv_kernel(const float* __restrict__
       const int r = lane + 32 * hlf;
       if (r < topl) {
         const float f = c0[hlf] / (c0[hlf] + c1[hlf]);
-        tile[r * 33 + q] = f;
-        tile[(topl + r) * 33 + q] = 1.f - f;
+        tile[r * (PXB + 1) + q] = f;
+        tile[(topl + r) * (PXB + 1) + q] = 1.f - f;
       }
     }
     __syncwarp();
   }
   __syncthreads();
-  const int npx = min(32, HW - p_base);
-  for (int e = threadIdx.x; e < 2 * topl * 32; e += blockDim.x) {
-    const int ch = e >> 5, q = e & 31;
-    if (q < npx) out[((long long)u * out_channels + s_channel + ch) * HW + p_base + q] = tile[ch * 33 + q];
+  const int npx = min(PXB, HW - p_base);
+  for (int e = threadIdx.x; e < 2 * topl * PXB; e += blockDim.x) {
+    const int ch = e / PXB, q = e % PXB;
+    if (q < npx) out[((long long)u * out_channels + s_channel + ch) * HW + p_base + q] = tile[ch * (PXB + 1) + q];
   }
 }
 
@@ -379,8 +380,8 @@ int launch_perm_inv(const float* P, int U, int HW, int Lt, int topl, float* out,
     set_error("perm_inv: topl=%d > 64 unsupported", topl);
     return SWEM_ERR_UNSUPPORTED;
   }
-  dim3 grid((HW + 31) / 32, U);
-  const size_t smem = (size_t)2 * topl * 33 * sizeof(float) + 8 * 128 * sizeof(uint32_t);
+  dim3 grid((HW + 7) / 8, U);
+  const size_t smem = (size_t)2 * topl * 9 * sizeof(float) + 8 * 128 * sizeof(uint32_t);
   const int npl = (Lt + 31) / 32;
 #define SWEM_PI(NPL_) perm_inv_kernel<NPL_><<<grid, 256, smem, st>>>(P, U, HW, Lt, topl, out, out_channels, s_channel)
   if (npl <= 1) SWEM_PI(1);

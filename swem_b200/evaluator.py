@@ -13,6 +13,15 @@ import torch
 import torch.nn.functional as F
 
 
+def _to_frame_size(pred_mask: torch.Tensor, h: int, w: int) -> torch.Tensor:
+    """The reference always calls F.interpolate(pred_mask, (h, w), bilinear, align_corners=False)
+    (swem_evaluator.py:91); for equal sizes that map is the identity (source index = destination index,
+    weight 1), so the launch is skipped -- bit-identical result."""
+    if pred_mask.shape[-2:] == (h, w):
+        return pred_mask
+    return F.interpolate(pred_mask, size=(h, w), mode='bilinear', align_corners=False)
+
+
 def hard_masks_from_scores(pred_mask: torch.Tensor):
     """(B,N+1,H,W) scores -> argmax (B,1,H,W) and its int64 one-hot (B,N+1,H,W)."""
     pred = torch.argmax(pred_mask, dim=1, keepdim=True)
@@ -39,7 +48,7 @@ def evaluate_davis_seq(model, frames: torch.Tensor, init_masks: List[Optional[to
         scores.append(pred_mask.clone())
         pred, hard = hard_masks_from_scores(pred_mask)
         if i < t - 1:
-            soft = F.interpolate(pred_mask, size=(h, w), mode='bilinear', align_corners=False)
+            soft = _to_frame_size(pred_mask, h, w)
             mv16 = model('encode_value', frames[:, i], soft, s16)
             model('memorize', qk16, mv16, hard, soft)
         preds.append(pred[:, 0])
@@ -70,7 +79,7 @@ def evaluate_ytvos_seq(model, frames: torch.Tensor, init_masks: List[Optional[to
             pred_mask = torch.cat([pred_mask, fresh], dim=1)
         pred, hard = hard_masks_from_scores(pred_mask)
         if i < t - 1:
-            soft = F.interpolate(pred_mask, size=(h, w), mode='bilinear', align_corners=False)
+            soft = _to_frame_size(pred_mask, h, w)
             mv16 = model('encode_value', frames[:, i], soft, s16)
             model('memorize', qk16, mv16, hard, soft)
         preds.append(pred[:, 0])
@@ -102,7 +111,7 @@ class SequenceRunner:
         _, pred_mask = self.model('segment', n, context, s8, s4, None, self.out_size)
         pred, hard = hard_masks_from_scores(pred_mask)
         if memorize:
-            soft = F.interpolate(pred_mask, size=(h, w), mode='bilinear', align_corners=False)
+            soft = _to_frame_size(pred_mask, h, w)
             mv16 = self.model('encode_value', frame, soft, s16)
             self.model('memorize', qk16, mv16, hard, soft)
         return pred[:, 0]

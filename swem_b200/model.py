@@ -17,6 +17,8 @@ from .networks import Decoder, KeyEncoder, KeyProjection, ValueEncoder, ValueEnc
 class SWEM(nn.Module):
     #: build the (B,N,2,H16,W16) EM masks with the library's kernel (True) or with torch ops (False)
     fused_mask_prep = True
+    #: run up-sampling + sigmoid + aggregation + softmax of `decode` as one kernel (inference on CUDA only)
+    fused_decode_tail = True
 
     def __init__(self, config_model):
         super().__init__()
@@ -81,6 +83,20 @@ class SWEM(nn.Module):
     def decode(self, n, context, s8, s4, valid_obj, out_size):
         s8 = s8.unsqueeze(1).expand(-1, n, -1, -1, -1).flatten(end_dim=1)
         s4 = s4.unsqueeze(1).expand(-1, n, -1, -1, -1).flatten(end_dim=1)
+        if self.fused_decode_tail and context.is_cuda and not torch.is_grad_enabled() and n <= 16:
+            lr = self.decoder.lowres_logits(context, s8, s4).float().contiguous()      # (B*n, 1, Hl, Wl)
+            b = lr.shape[0] // n
+            h, w = int(out_size[0]), int(out_size[1])
+            logits = torch.empty(b, n + 1, h, w, device=lr.device, dtype=torch.float32)
+            prob = torch.empty_like(logits)
+            valid = None if valid_obj is None else valid_obj.float().contiguous()
+            with torch.cuda.device(lr.device):
+                rc = _lib.load().swem_decode_tail(lr.data_ptr(), b, n, lr.shape[-2], lr.shape[-1], h, w,
+                                                  None if valid is None else valid.data_ptr(),
+                                                  logits.data_ptr(), prob.data_ptr(),
+                                                  torch.cuda.current_stream(lr.device).cuda_stream)
+            _lib.check(rc, 'swem_decode_tail')
+            return logits, prob
         preds = torch.sigmoid(self.decoder(context, s8, s4, out_size))
         preds = preds.view(-1, n, *preds.shape[-2:])
         if valid_obj is not None:

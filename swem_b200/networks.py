@@ -297,10 +297,13 @@ class Decoder(nn.Module):
         self.up_8_4 = UpsampleBlock(inplanes[2], 256, mdim)
         self.pred = nn.Conv2d(mdim, 1, 3, padding=1)
 
-    def forward(self, f16, f8, f4, osize):
+    def lowres_logits(self, f16, f8, f4):
+        """The logit plane at 1/4 resolution, i.e. ``forward`` without its final up-sampling."""
         x = self.up_8_4(f4, self.up_16_8(f8, self.compress(f16)))
-        x = self.pred(F.relu(x))
-        return F.interpolate(x, size=osize, mode='bilinear', align_corners=False)
+        return self.pred(F.relu(x))
+
+    def forward(self, f16, f8, f4, osize):
+        return F.interpolate(self.lowres_logits(f16, f8, f4), size=osize, mode='bilinear', align_corners=False)
 
 
 class FeatureFusionLayer(nn.Module):

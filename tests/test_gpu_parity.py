@@ -384,3 +384,65 @@ def test_free_running_masks_vs_oracle(case):
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
     per_frame = (got == want).flatten(1).float().mean(dim=1)
     check('min_agree', 1.0 - per_frame.min().item(), 1.0 - bound)
+
+
+def test_ytvos_sequence_with_late_object_vs_oracle():
+    """BASELINE configs[2] shape family: a YouTube-VOS-style sequence (480x848 -> HW = 1590, not a multiple
+    of 4 or 128) where an object first appears mid-sequence: the memory grows by one object, random_init
+    covers only the new object (modules.py:140-146) and the 'first' bank appends it (modules.py:44-53)."""
+    from swem_b200 import SWEM, make_config
+    from swem_b200.evaluator import evaluate_ytvos_seq
+    from swem_b200.synthetic import ytvos_materialise
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        torch.manual_seed(0)
+        cfg = make_config(keydim=64, n_bases=128, n_iters=4, topl=64)
+        nets_cpu = SWEM(cfg).eval()
+        model = SWEM(cfg).eval()
+        model.load_state_dict(nets_cpu.state_dict())
+        model = model.to(DEV)
+        spec = dict(h=480, w=848, t=6, n_obj=3, n_late=1, late_frame=2, seed=11)
+        frames, init_masks = ytvos_materialise(spec)
+        oracle = O.OracleSWEM(nets_cpu, 128, 4, 0.05, 64)
+        # both sides draw new bases from the same seeded CPU generator, in the same order
+        gen_o, gen_g = torch.Generator().manual_seed(77), torch.Generator().manual_seed(77)
+        oracle.core.generator = gen_o
+
+        def gpu_init(size, norm_dim=-2, dtype=None, device=None):
+            B, N, _, Ck, L = size
+            return tuple(t.to(device) for t in O.random_init(B, N, Ck, L, 512, generator=gen_g))
+        model.swem_core.random_init = gpu_init
+        want = torch.stack(O.run_ytvos_sequence(oracle, frames, init_masks, (480, 848)))
+        got = torch.stack(evaluate_ytvos_seq(model, frames.to(DEV), [m if m is None else m.to(DEV) for m in init_masks],
+                                             (480, 848))).cpu()
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    assert model.swem_core.memories['first'].n_objs == 3 and model.swem_core.get_mem()[0].shape[1] == 3
+    assert int(want.max()) == 3                                   # the late object is being tracked
+    per_frame = (got == want).flatten(1).float().mean(dim=1)
+    check('min_agree', 1.0 - per_frame.min().item(), 1.0 - 0.999)
+
+
+def test_decode_tail_kernel_matches_torch():
+    """swem_decode_tail vs the torch ops it replaces (networks.py:214-215 + swem.py:92-116)."""
+    from swem_b200 import SWEM, make_config
+    torch.manual_seed(3)
+    model = SWEM(make_config(backbone='resnet18', n_bases=16)).eval().to(DEV)
+    n, b = 5, 1
+    ctx = torch.randn(b * n, 512, 30, 54, device=DEV)
+    s8 = torch.randn(b, 128, 60, 108, device=DEV)
+    s4 = torch.randn(b, 64, 120, 216, device=DEV)
+    valid = torch.tensor([[1., 1., 0., 1., 1., 1.]], device=DEV)
+    with torch.no_grad():
+        for v in (None, valid):
+            for out_size in ((480, 864), (480, 854)):
+                model.fused_decode_tail = True
+                lg, pr = model('segment', n, ctx, s8, s4, v, out_size)
+                model.fused_decode_tail = False
+                lg0, pr0 = model('segment', n, ctx, s8, s4, v, out_size)
+                assert lg.shape == lg0.shape == (b, n + 1, *out_size)
+                assert (lg - lg0).abs().max().item() < 2e-3 * max(1.0, lg0.abs().max().item())
+                assert (pr - pr0).abs().max().item() < 1e-5
+                assert (pr.argmax(1) == pr0.argmax(1)).float().mean().item() > 0.9999
