@@ -97,6 +97,9 @@ class SWEMCore(nn.Module):
     # SWEM_PATH_* of the C ABI per entry point; tests flip these to exercise both kernel families
     em_path = _lib.PATH_AUTO
     readout_path = _lib.PATH_AUTO
+    #: True: the 'update' bank keeps its tensors and is overwritten in place (needed when the frame step is
+    #: replayed from a CUDA graph, where every address is baked in).  False: replaced wholesale like the reference.
+    static_banks = False
 
     def __init__(self, n_bases=256, valdim=512, n_iters=4, tau=0.05, topl=64):
         super().__init__()
@@ -184,7 +187,12 @@ class SWEMCore(nn.Module):
             self.memories['first'].update(bases)
         else:
             self.memories['first'].update(bases)
-            self.memories['update'].update(bases)
+            upd = self.memories['update']
+            if self.static_banks and upd.bases is not None and upd.bases['kappa'].shape == bases['kappa'].shape:
+                for key in ('kappa', 'nu', 'zita'):
+                    upd.bases[key].copy_(bases[key])
+            else:
+                upd.update(bases)
 
     # -- readout ---------------------------------------------------------------------------
     def matching_features(self, qk, qv) -> Tuple[torch.Tensor, int]:

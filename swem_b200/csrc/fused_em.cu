@@ -51,7 +51,8 @@ constexpr float kZScale = 16384.f;                 // z (<= 1) is staged as z*2^
 // KH/KL : [sl 0..255][c] K-major: byte = (sl%8)*16 + (sl/8)*128 + (c/8)*4096 + (c%8)*2  -> SBO=128, LBO=4096
 // Z  : [sl 0..255][p] MN-major A: byte = (sl%8)*2 + (p%8)*16 + (sl/8)*2048 + (p/8)*128   -> SBO=2048, LBO=128
 // P  : fp32 [256][73] staging of the M-step partial / total (aliases Z)
-// VS : 3 stages x [d 0..255][p 0..31] K-major: byte = (d%8)*16 + (d/8)*128 + (p/8)*4096 + (p%8)*2 -> SBO=128, LBO=4096
+// VS : V stage [d 0..255][p 0..31] K-major, hi plane (16 KB) then lo plane: byte = (d%8)*16 + (d/8)*128 + (p/8)*4096 + (p%8)*2
+//      -> SBO=128, LBO=4096.  Two stages of 32 KB: stage 0 at kOffVS, stage 1 in the X region (idle during the nu GEMMs)
 // ZL : lo half of z, same layout as Z (aliases KH/KL: khat is dead between the logits GEMM and the finalize)
 // NS : fp32 [2 sides][32 d][128 l] staging of nu partials (aliases XH/XL, dead after the last M-step GEMM)
 constexpr uint32_t kOffXH = 0;
@@ -60,8 +61,8 @@ constexpr uint32_t kOffKH = kOffXL + 8 * 2048;
 constexpr uint32_t kOffKL = kOffKH + 8 * 4096;
 constexpr uint32_t kOffZ = kOffKL + 8 * 4096;
 constexpr uint32_t kOffVS = kOffZ + kAccBytes;            // 74752 is a multiple of 128
-constexpr uint32_t kVStage = 4 * 4096;                    // 16 KB
-constexpr uint32_t kOffMisc = kOffVS + 3 * kVStage;
+constexpr uint32_t kVPlane = 4 * 4096;                    // 16 KB: one fp16 plane of a V stage
+constexpr uint32_t kOffMisc = kOffVS + 3 * kVPlane;       // (48 KB reserved: stage 0 uses 32 KB, the drain staging 32 KB)
 constexpr uint32_t kOffZL = kOffKH;                       // 64 KB
 constexpr uint32_t kOffNS = kOffXH;                       // 32 KB of the 36 KB X region
 struct Misc {
@@ -72,7 +73,7 @@ struct Misc {
   float zita[kSL];
   uint64_t bar_mma;
   uint64_t bar_tma;
-  uint64_t bar_stage[3];
+  uint64_t bar_stage[2];
   uint32_t tmem_base;
   int abort_flag;
 };
@@ -131,7 +132,7 @@ __global__ void __launch_bounds__(256, 1) em_fused_kernel(const EmFusedParams p)
   if (tid == 0) {
     mbar_init(&ms.bar_mma, 1);
     mbar_init(&ms.bar_tma, 1);
-    for (int i = 0; i < 3; ++i) mbar_init(&ms.bar_stage[i], 1);
+    for (int i = 0; i < 2; ++i) mbar_init(&ms.bar_stage[i], 1);
     ms.abort_flag = 0;
     fence_mbar_init();
   }
@@ -391,15 +392,27 @@ __global__ void __launch_bounds__(256, 1) em_fused_kernel(const EmFusedParams p)
           buf[j] = f;
         }
       };
+      auto stage_ptr = [&](int st) -> uint8_t* { return smem + (st ? kOffXH : kOffVS); };
       auto store_chunk = [&](int st, const float4 (&buf)[8]) {
-        uint8_t* stage = smem + kOffVS + st * kVStage;
+        uint8_t* stage = stage_ptr(st);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const int dl = warp * 32 + j * 4 + (lane >> 3);
-          uint2 pk;
-          pk.x = pack_half2(buf[j].x, buf[j].y);
-          pk.y = pack_half2(buf[j].z, buf[j].w);
-          *reinterpret_cast<uint2*>(stage + (dl % 8) * 16 + (dl / 8) * 128 + (px4 / 8) * 4096 + (px4 % 8) * 2) = pk;
+          __half h0, h1, h2, h3, l0, l1, l2, l3;
+          split_half(buf[j].x, h0, l0);
+          split_half(buf[j].y, h1, l1);
+          split_half(buf[j].z, h2, l2);
+          split_half(buf[j].w, h3, l3);
+          const __half2 ha = __halves2half2(h0, h1), hb = __halves2half2(h2, h3);
+          const __half2 la = __halves2half2(l0, l1), lb = __halves2half2(l2, l3);
+          uint2 ph, pl;
+          ph.x = *reinterpret_cast<const uint32_t*>(&ha);
+          ph.y = *reinterpret_cast<const uint32_t*>(&hb);
+          pl.x = *reinterpret_cast<const uint32_t*>(&la);
+          pl.y = *reinterpret_cast<const uint32_t*>(&lb);
+          const uint32_t off = (dl % 8) * 16 + (dl / 8) * 128 + (px4 / 8) * 4096 + (px4 % 8) * 2;
+          *reinterpret_cast<uint2*>(stage + off) = ph;
+          *reinterpret_cast<uint2*>(stage + kVPlane + off) = pl;
         }
       };
       float4 vbuf[2][8];
@@ -409,9 +422,9 @@ __global__ void __launch_bounds__(256, 1) em_fused_kernel(const EmFusedParams p)
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) {
           const int seq = half * 4 + ch;
-          const int st = seq % 3;
+          const int st = seq & 1;
           if (seq + 1 < 8) load_chunk(seq + 1, vbuf[(seq + 1) & 1]);
-          if (seq >= 3) SWEM_CTA_WAIT(&ms.bar_stage[st], ((seq / 3) - 1) & 1, ms.abort_flag);   // stage reuse: its MMAs retired
+          if (seq >= 2) SWEM_CTA_WAIT(&ms.bar_stage[st], ((seq / 2) - 1) & 1, ms.abort_flag);   // stage reuse: its MMAs retired
           store_chunk(st, vbuf[seq & 1]);
           fence_proxy_async_smem();
           tc_fence_before_sync();
@@ -419,16 +432,19 @@ __global__ void __launch_bounds__(256, 1) em_fused_kernel(const EmFusedParams p)
           tc_fence_after_sync();
           if (warp == 0) {
             if (lane == 0) {
-            const uint32_t vb = sbase + kOffVS + st * kVStage;
+            const uint32_t vb = sbase + (st ? kOffXH : kOffVS);
 #pragma unroll
             for (int sd = 0; sd < 2; ++sd) {
               const uint32_t za = sbase + kOffZ + sd * 16 * 2048;
 #pragma unroll
               for (int kk = 0; kk < 2; ++kk) {
                 const uint64_t ad = make_sdesc(za + (ch * 2 + kk) * 2 * 128, /*lbo*/ 128, /*sbo*/ 2048);
-                const uint64_t bd = make_sdesc(vb + kk * 2 * 4096, /*lbo*/ 4096, /*sbo*/ 128);
-                // z_hi only: v is a single fp16 here, so the z_lo term would not improve nu
-                mma_f16_ss(tmem + kColNu + sd * 256, ad, bd, idesc_nu, (ch | kk) ? 1u : 0u);
+                const uint64_t al = make_sdesc(za + (kOffZL - kOffZ) + (ch * 2 + kk) * 2 * 128, /*lbo*/ 128, /*sbo*/ 2048);
+                const uint64_t bh = make_sdesc(vb + kk * 2 * 4096, /*lbo*/ 4096, /*sbo*/ 128);
+                const uint64_t bl = make_sdesc(vb + kVPlane + kk * 2 * 4096, /*lbo*/ 4096, /*sbo*/ 128);
+                mma_f16_ss(tmem + kColNu + sd * 256, ad, bh, idesc_nu, (ch | kk) ? 1u : 0u);   // z_hi v_hi
+                mma_f16_ss(tmem + kColNu + sd * 256, ad, bl, idesc_nu, 1u);                     // z_hi v_lo
+                mma_f16_ss(tmem + kColNu + sd * 256, al, bh, idesc_nu, 1u);                     // z_lo v_hi
               }
             }
             mma_commit(&ms.bar_stage[st]);

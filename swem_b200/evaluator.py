@@ -115,3 +115,48 @@ class SequenceRunner:
             mv16 = self.model('encode_value', frame, soft, s16)
             self.model('memorize', qk16, mv16, hard, soft)
         return pred[:, 0]
+
+
+class GraphedSequenceRunner(SequenceRunner):
+    """:class:`SequenceRunner` whose steady-state step is captured once into a CUDA graph and replayed.
+
+    A frame of the loop is ~450 kernel launches (torch encoders/decoder + our kernels); replaying them as
+    one graph removes the CPU launch cost.  The first ``eager_steps`` frames run eagerly (the memory reaches
+    its steady shape -- both banks present -- after the second memorize), then one step is captured with a
+    static input frame; the 'update' bank is switched to in-place updates (``SWEMCore.static_banks``) so the
+    addresses baked into the graph stay valid.  ``step`` returns a static tensor that the next step
+    overwrites.  Sequences whose object count changes must use the eager runner.
+    """
+
+    def __init__(self, model, out_size, eager_steps: int = 2):
+        super().__init__(model, out_size)
+        self.eager_steps = max(2, eager_steps)
+        self._seen = 0
+        self._graph = None
+        self._frame = None
+        self._pred = None
+
+    @torch.no_grad()
+    def start(self, frame0, init_mask):
+        self._seen, self._graph = 0, None
+        self.model.swem_core.static_banks = False
+        super().start(frame0, init_mask)
+
+    @torch.no_grad()
+    def step(self, frame, memorize: bool = True):
+        if self._graph is None:
+            if self._seen < self.eager_steps:
+                self._seen += 1
+                return super().step(frame, memorize)
+            core = self.model.swem_core
+            core.static_banks = True
+            self._frame = frame.clone()
+            torch.cuda.synchronize(frame.device)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                self._pred = super().step(self._frame, memorize)
+            self._graph = graph
+            # capture does not execute: run the captured step once for this frame
+        self._frame.copy_(frame, non_blocking=True)
+        self._graph.replay()
+        return self._pred

@@ -446,3 +446,24 @@ def test_decode_tail_kernel_matches_torch():
                 assert (lg - lg0).abs().max().item() < 2e-3 * max(1.0, lg0.abs().max().item())
                 assert (pr - pr0).abs().max().item() < 1e-5
                 assert (pr.argmax(1) == pr0.argmax(1)).float().mean().item() > 0.9999
+
+
+def test_cuda_graph_runner_matches_eager_runner():
+    """Replaying the frame step from a CUDA graph (static banks updated in place) tracks the eager loop."""
+    from swem_b200 import SWEM, make_config
+    from swem_b200.evaluator import GraphedSequenceRunner, SequenceRunner
+    from swem_b200.synthetic import davis_sequence
+    torch.manual_seed(0)
+    model = SWEM(make_config(keydim=64, n_bases=128, n_iters=4, topl=64)).eval().to(DEV)
+    T, N, h, w = 7, 3, 240, 432
+    frames, init = davis_sequence(T, N, seed=2, size=(h, w))
+    frames, init = frames.to(DEV), init.to(DEV)
+    outs = []
+    for cls in (SequenceRunner, GraphedSequenceRunner):
+        torch.manual_seed(5)
+        runner = cls(model, (h, w))
+        runner.start(frames[:, 0], init)
+        outs.append(torch.stack([runner.step(frames[:, i]).clone() for i in range(1, T)]).cpu())
+        model.swem_core.static_banks = False
+    agree = (outs[0] == outs[1]).flatten(1).float().mean(dim=1)
+    check('graph_vs_eager', 1.0 - agree.min().item(), 1e-3)     # not bit-exact: the reduce-add order varies run to run
