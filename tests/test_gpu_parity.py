@@ -453,17 +453,24 @@ def test_cuda_graph_runner_matches_eager_runner():
     from swem_b200 import SWEM, make_config
     from swem_b200.evaluator import GraphedSequenceRunner, SequenceRunner
     from swem_b200.synthetic import davis_sequence
-    torch.manual_seed(0)
-    model = SWEM(make_config(keydim=64, n_bases=128, n_iters=4, topl=64)).eval().to(DEV)
-    T, N, h, w = 7, 3, 240, 432
-    frames, init = davis_sequence(T, N, seed=2, size=(h, w))
-    frames, init = frames.to(DEV), init.to(DEV)
-    outs = []
-    for cls in (SequenceRunner, GraphedSequenceRunner):
-        torch.manual_seed(5)
-        runner = cls(model, (h, w))
-        runner.start(frames[:, 0], init)
-        outs.append(torch.stack([runner.step(frames[:, i]).clone() for i in range(1, T)]).cpu())
-        model.swem_core.static_banks = False
-    agree = (outs[0] == outs[1]).flatten(1).float().mean(dim=1)
-    check('graph_vs_eager', 1.0 - agree.min().item(), 1e-3)     # not bit-exact: the reduce-add order varies run to run
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False      # cuDNN may pick other algorithms under capture; keep them all fp32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        torch.manual_seed(0)
+        model = SWEM(make_config(keydim=64, n_bases=128, n_iters=4, topl=64)).eval().to(DEV)
+        T, N, h, w = 7, 3, 240, 432
+        frames, init = davis_sequence(T, N, seed=2, size=(h, w))
+        frames, init = frames.to(DEV), init.to(DEV)
+        outs = []
+        for cls in (SequenceRunner, SequenceRunner, GraphedSequenceRunner):
+            torch.manual_seed(5)
+            runner = cls(model, (h, w))
+            runner.start(frames[:, 0], init)
+            outs.append(torch.stack([runner.step(frames[:, i]).clone() for i in range(1, T)]).cpu())
+            model.swem_core.static_banks = False
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    noise = 1.0 - (outs[0] == outs[1]).flatten(1).float().mean(dim=1).min().item()    # eager vs eager (reduce-add order)
+    agree = (outs[0] == outs[2]).flatten(1).float().mean(dim=1)
+    check(f'graph_vs_eager(eager noise {noise:.1e})', 1.0 - agree.min().item(), max(2e-3, 4 * noise))
