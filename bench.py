@@ -234,9 +234,16 @@ def run_b200(args, rank, world, local_rank):
         launches[0] += lib.swem_last_launch_count()
         return rc
 
+    use_engine = os.environ.get('SWEM_ENGINE', '1') == '1'
+    stages = model
+    if use_engine:                                               # inference form of the torch stages (same weights, same function)
+        from swem_b200.engine import FrameEngine
+        stages = FrameEngine(model, channels_last=os.environ.get('SWEM_CHANNELS_LAST', '1') == '1',
+                             fused_conv=os.environ.get('SWEM_FUSED_CONV', '1') == '1')
+
     def run_phase(host_io, graphed):
         """start on frame 0, Wm warm-up steps, then K timed steps; returns (ms, clocks, masks checksum)."""
-        runner = (GraphedSequenceRunner if graphed else SequenceRunner)(model, (H, W))
+        runner = (GraphedSequenceRunner if graphed else SequenceRunner)(stages, (H, W))
         core.static_banks = False
         stage = torch.empty(1, 3, H, W, device=dev)
         mask_host = torch.empty(K, H, W, dtype=torch.uint8).pin_memory()
@@ -301,7 +308,10 @@ def run_b200(args, rank, world, local_rank):
         'config': workload_config(n_obj, {'kernel_family': family, 'frame_step': 'CUDA graph replay' if use_graph else 'eager',
                                           'eager_ms_per_step': ms_eager / K, 'l2': 'every step reads a new 5 MB frame and '
                                           '>230 MB of fp32 weights + activations (> 126 MB L2); no explicit flush',
-                                          'torch_convs': 'cudnn, allow_tf32 default, channels_last=' + os.environ.get('SWEM_CHANNELS_LAST', '1')}),
+                                          'torch_convs': 'cudnn, allow_tf32 default, channels_last=' + os.environ.get('SWEM_CHANNELS_LAST', '1'),
+                                          'torch_stages': ('FrameEngine (BN folded, fused conv+bias+relu=' + os.environ.get('SWEM_FUSED_CONV', '1')
+                                                           + ', object-independent conv halves computed once per frame)') if use_engine
+                                                          else 'plain nn.Modules'}),
         'e2e': {'value': fps_e2e, 'unit': UNIT, 'h2d_bytes_per_step': 3 * H * W * 4, 'd2h_bytes_per_step': H * W,
                 'ms_per_step': ms_e2e / K},
         'gpu_launches': n_launch,

@@ -197,19 +197,41 @@ class SWEMCore(nn.Module):
     # -- readout ---------------------------------------------------------------------------
     def matching_features(self, qk, qv) -> Tuple[torch.Tensor, int]:
         """-> the concat buffer [mem_out | qv | S] (B*N, 2*Cv + 2*topl, H, W) and N."""
+        N, Cv = self._readout_objects()
+        _no_grad_inputs(qv)
+        qv = _f32c(qv, 'qv')
+        B, _, H, W = qk.shape
+        chans = 2 * Cv + 2 * self.topl
+        feats = torch.empty(B * N, chans, H, W, device=qk.device, dtype=torch.float32)
+        feats.view(B, N, chans, H, W)[:, :, Cv:2 * Cv] = qv.unsqueeze(1)
+        return self.readout_into(qk, feats, 0, 2 * Cv), N
+
+    def _readout_objects(self) -> Tuple[int, int]:
+        banks = [m.bases for m in self.memories.values() if m.bases is not None]
+        if not banks:
+            raise RuntimeError('matching() before any memorize(): memory is empty')
+        return banks[0]['nu'].shape[1], banks[0]['nu'].shape[3]
+
+    def readout_into(self, qk, feats, mem_channel: int, s_channel: int) -> torch.Tensor:
+        """Readout kernels only: write ``mem_out`` into channels [mem_channel, +Cv) and ``S`` into channels
+        [s_channel, +2*topl) of the caller's contiguous fp32 buffer ``feats`` (B*N, C, H, W).  The reference
+        layout is ``matching_features``; inference engines that split the fusion conv use a narrower buffer."""
         if self.training and self.p_drop > 0:
             raise NotImplementedError('swem_b200: memory dropout (p_drop > 0) is not implemented')
         banks = [m.bases for m in self.memories.values() if m.bases is not None]
         if not banks:
             raise RuntimeError('matching() before any memorize(): memory is empty')
-        _no_grad_inputs(qk, qv, *[b['nu'] for b in banks])
-        qk, qv = _f32c(qk, 'qk'), _f32c(qv, 'qv')
+        _no_grad_inputs(qk, *[b['nu'] for b in banks])
+        qk = _f32c(qk, 'qk')
         B, Ck, H, W = qk.shape
         _, N, _, Cv, L = banks[0]['nu'].shape
         dev = qk.device
-        chans = 2 * Cv + 2 * self.topl
-        feats = torch.empty(B * N, chans, H, W, device=dev, dtype=torch.float32)
-        feats.view(B, N, chans, H, W)[:, :, Cv:2 * Cv] = qv.unsqueeze(1)
+        chans = feats.shape[1]
+        if (not feats.is_cuda or feats.dtype != torch.float32 or not feats.is_contiguous()
+                or feats.shape != (B * N, chans, H, W) or mem_channel < 0 or mem_channel + Cv > chans
+                or s_channel < 0 or s_channel + 2 * self.topl > chans):
+            raise RuntimeError(f'readout_into: bad output buffer {tuple(feats.shape)} {feats.dtype} for B*N={B * N}, '
+                               f'mem_channel={mem_channel}, s_channel={s_channel}')
 
         lib = _lib.load()
         dims = _lib.SwemDims(B, N, Ck, Cv, H * W, L, 0, len(banks), self.topl, self.tau)
@@ -220,14 +242,14 @@ class SWEMCore(nn.Module):
         args = _lib.SwemReadArgs(dims, qk.data_ptr(),
                                  (C.c_void_p * 2)(*[k.data_ptr() for k in kap] + [None] * (2 - len(kap))),
                                  (C.c_void_p * 2)(*[n.data_ptr() for n in nus] + [None] * (2 - len(nus))),
-                                 feats.data_ptr(), chans, 0, 2 * Cv,
+                                 feats.data_ptr(), chans, mem_channel, s_channel,
                                  ws.data_ptr(), ws.numel(), self.readout_path)
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev).cuda_stream
             rc = _invoke('readout', lambda: lib.swem_readout_forward(C.byref(args), stream))
         _lib.check(rc, 'swem_readout_forward')
         self.launches = lib.swem_last_launch_count()
-        return feats, N
+        return feats
 
     def matching(self, qk, qv):
         feats, n = self.matching_features(qk, qv)

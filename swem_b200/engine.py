@@ -1,0 +1,251 @@
+"""``FrameEngine`` -- inference form of the torch stages that surround the SWEM memory.
+
+The reference runs its encoders / fusion conv / decoder exactly as they are written for training
+(``methods/SWEM/swem.py:45-116``, ``methods/basic_modules/networks.py``): BatchNorm as its own pass,
+ReLU / residual adds as separate kernels, and -- because every object is treated as one more batch
+sample -- the *object-independent* parts of several convolutions recomputed once per object.  After the
+EM + readout path is fused these pieces are ~98 % of a frame.  This
+engine evaluates the SAME function from the SAME ``SWEM`` module's parameters, reorganised for
+inference (``eval()`` + ``no_grad`` only):
+
+* BatchNorm folded into the preceding conv (running statistics, ``networks.py`` ResNet trunks);
+* conv + bias + ReLU and conv + bias + residual + ReLU issued as single cuDNN fused ops;
+* ``key_proj`` and ``key_comp`` (``swem.py:45-49``) share one conv over ``f16``;
+* linearity splits for inputs that do not depend on the object:
+    - value-encoder fuser ``block1`` (``networks.py:94-106``): ``conv(cat[x_obj, f16])`` =
+      ``conv_a(x_obj) + conv_b(f16)``, the 1024-channel ``f16`` half computed once per frame; its
+      ``conv1`` and ``downsample`` read the same input and are stacked into one conv;
+    - GLU fusion (``modules.py:13-26``): ``layer_f`` / ``layer_a`` stacked, the ``qv`` third of the
+      concat ``[mem_out | qv | S]`` (``modules.py:291``) convolved once per frame; the readout kernels
+      write ``mem_out`` / ``S`` into a 640-channel buffer, the ``qv`` copy disappears;
+    - decoder ``skip_conv`` of ``s8`` / ``s4`` (``networks.py:186-203``) computed once per frame instead
+      of once per object, and the N-fold ``expand`` copies of ``s8`` / ``s4`` (``swem.py:93-94``) dropped.
+
+Only summation order changes (fp32 / TF32 rounding); tests compare the engine with the plain modules
+and with the CPU reference port.  It is called like the model (``engine('encode_key', frame)`` ...), so the
+sequence runners in ``evaluator.py`` take either.  There is no CPU fallback
+of the memory kernels here: ``init`` / ``memorize`` / the readout go to ``SWEMCore``.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Tuple
+
+import torch
+import torch.nn.functional as F
+
+from . import _lib
+from .networks import _Basic, _Bottle
+
+ConvP = Tuple[torch.Tensor, Optional[torch.Tensor], int, int]      # weight, bias, stride, padding
+
+
+def _fold_bn(conv, bn) -> Tuple[torch.Tensor, torch.Tensor]:
+    """conv -> BatchNorm(eval) as one affine conv: w' = w * g/sqrt(var+eps), b' = beta + (b - mean) * g/sqrt(var+eps)."""
+    scale = bn.weight / torch.sqrt(bn.running_var + bn.eps)
+    w = conv.weight * scale.view(-1, 1, 1, 1)
+    b0 = conv.bias if conv.bias is not None else torch.zeros_like(bn.running_mean)
+    return w, bn.bias + (b0 - bn.running_mean) * scale
+
+
+class FrameEngine:
+    def __init__(self, model, channels_last: bool = True, fused_conv: bool = True):
+        self.model = model
+        self.channels_last = channels_last
+        self.fused_conv = fused_conv
+        self._built = False
+
+    # ------------------------------------------------------------------------------------------
+    # parameter preparation
+    # ------------------------------------------------------------------------------------------
+    def _w(self, w: torch.Tensor) -> torch.Tensor:
+        w = w.detach().float()
+        return w.contiguous(memory_format=torch.channels_last) if self.channels_last else w.contiguous()
+
+    def _cp(self, w, b, stride=1, padding=1) -> ConvP:
+        return (self._w(w), None if b is None else b.detach().float().contiguous(), stride, padding)
+
+    def _folded(self, conv, bn) -> ConvP:
+        w, b = _fold_bn(conv, bn)
+        return self._cp(w, b, conv.stride[0], conv.padding[0])
+
+    def _plain(self, conv) -> ConvP:
+        return self._cp(conv.weight, conv.bias, conv.stride[0], conv.padding[0])
+
+    def _stage(self, stage) -> List[dict]:
+        blocks = []
+        for blk in stage:
+            d = {'kind': 'bottle' if isinstance(blk, _Bottle) else 'basic',
+                 'c1': self._folded(blk.conv1, blk.bn1), 'c2': self._folded(blk.conv2, blk.bn2),
+                 'down': None if blk.downsample is None else self._folded(blk.downsample[0], blk.downsample[1])}
+            if isinstance(blk, _Bottle):
+                d['c3'] = self._folded(blk.conv3, blk.bn3)
+            else:
+                assert isinstance(blk, _Basic)
+            blocks.append(d)
+        return blocks
+
+    @torch.no_grad()
+    def refresh(self) -> None:
+        """(Re)derive the inference parameters from the model's current weights (call after loading a checkpoint)."""
+        m = self.model
+        if m.training:
+            raise RuntimeError('FrameEngine is inference-only: call model.eval() first')
+        ke, ve, dec = m.key_encoder, m.value_encoder, m.decoder
+        self.k_stem = self._folded(ke.conv1, ke.bn1)
+        self.k_stages = [self._stage(s) for s in (ke.res2, ke.layer2, ke.layer3)]
+        kp, kc = m.key_proj.key_proj, m.key_comp
+        self.keydim = kp.out_channels
+        self.k_heads = self._cp(torch.cat([kp.weight, kc.weight], 0), torch.cat([kp.bias, kc.bias], 0), 1, 1)
+
+        self.v_stem = self._folded(ve.conv1, ve.bn1)
+        self.v_stages = [self._stage(s) for s in (ve.layer1, ve.layer2, ve.layer3)]
+        b1, b2 = ve.fuser.block1, ve.fuser.block2
+        cx = ve.layer3[-1].conv2.out_channels                      # channels of the per-object half of cat[x, f16]
+        self.f_has_down = b1.downsample is not None                 # reference R50: 1280 -> 512, yes; R18 trunk: 512 -> 512, no
+        convs = [b1.conv1] + ([b1.downsample] if self.f_has_down else [])
+        w = torch.cat([c.weight for c in convs], 0)                 # [2*512, 1280, 3, 3]: rows = [conv1 | downsample]
+        b = torch.cat([c.bias for c in convs], 0)
+        self.f_obj = self._cp(w[:, :cx], None, 1, 1)                # per object, bias carried by the shared half
+        self.f_shared = self._cp(w[:, cx:], b, 1, 1)                # once per frame
+        self.f_mid = b1.conv1.out_channels
+        self.f_b1c2 = self._plain(b1.conv2)
+        self.f_b2c1, self.f_b2c2 = self._plain(b2.conv1), self._plain(b2.conv2)
+
+        core = m.swem_core
+        fl = core.fusion_layer
+        cv, tl = core.valdim, core.topl
+        w = torch.cat([fl.layer_f.weight, fl.layer_a.weight], 0)   # [2*512, 2*Cv + 2*topl, 3, 3]
+        b = torch.cat([fl.layer_f.bias, fl.layer_a.bias], 0)
+        self.g_obj = self._cp(torch.cat([w[:, :cv], w[:, 2 * cv:]], 1), None, 1, 1)     # [mem_out | S] channels
+        self.g_shared = self._cp(w[:, cv:2 * cv], b, 1, 1)                               # qv channels
+        self.g_out = fl.layer_f.out_channels
+
+        if dec.compress.downsample is not None:
+            raise RuntimeError('FrameEngine expects Decoder.compress to keep its width (reference: 512 -> 512)')
+        self.d_c1, self.d_c2 = self._plain(dec.compress.conv1), self._plain(dec.compress.conv2)
+        self.d_up = []
+        for up in (dec.up_16_8, dec.up_8_4):
+            rb = up.out_conv
+            d = {'skip': self._plain(up.skip_conv), 'c1': self._plain(rb.conv1), 'c2': self._plain(rb.conv2),
+                 'down': None if rb.downsample is None else self._plain(rb.downsample)}
+            self.d_up.append(d)
+        self.d_pred = self._plain(dec.pred)
+        self._built = True
+
+    def _ready(self):
+        if not self._built:
+            self.refresh()
+        if torch.is_grad_enabled():
+            raise RuntimeError('FrameEngine is inference-only: call it under torch.no_grad()')
+
+    # ------------------------------------------------------------------------------------------
+    # conv helpers
+    # ------------------------------------------------------------------------------------------
+    def _conv(self, x, p: ConvP, relu: bool = False, add: Optional[torch.Tensor] = None):
+        w, b, s, pad = p
+        if self.fused_conv and relu and x.is_cuda and b is not None:
+            if add is None:
+                return torch.cudnn_convolution_relu(x, w, b, (s, s), (pad, pad), (1, 1), 1)
+            return torch.cudnn_convolution_add_relu(x, w, add, 1.0, b, (s, s), (pad, pad), (1, 1), 1)
+        y = F.conv2d(x, w, b, stride=s, padding=pad)
+        if add is not None:
+            y.add_(add)
+        return F.relu_(y) if relu else y
+
+    def _run_stage(self, x, blocks):
+        for d in blocks:
+            y = self._conv(x, d['c1'], relu=True)
+            if d['kind'] == 'bottle':
+                y = self._conv(y, d['c2'], relu=True)
+                last = d['c3']
+            else:
+                last = d['c2']
+            skip = x if d['down'] is None else self._conv(x, d['down'])
+            x = self._conv(y, last, relu=True, add=skip)
+        return x
+
+    def _trunk(self, x, stem, stages, taps=False):
+        x = F.max_pool2d(self._conv(x, stem, relu=True), 3, stride=2, padding=1)
+        feats = []
+        for st in stages:
+            x = self._run_stage(x, st)
+            feats.append(x)
+        return feats if taps else x
+
+    # ------------------------------------------------------------------------------------------
+    # the model's modes (swem.py:118-132)
+    # ------------------------------------------------------------------------------------------
+    def encode_key(self, frames):
+        """frames (B,3,H,W) -> (qk16, qv16, f16, f8, f4), as SWEM.encode_key (swem.py:45-49)."""
+        self._ready()
+        ke = self.model.key_encoder
+        f4, f8, f16 = self._trunk((frames - ke.mean) / ke.std, self.k_stem, self.k_stages, taps=True)
+        heads = self._conv(f16, self.k_heads)
+        return heads[:, :self.keydim], heads[:, self.keydim:], f16, f8, f4
+
+    def encode_value(self, frame, masks, s16):
+        """frame (B,3,H,W), masks (B,N+1,H,W), s16 = f16 of the same frame -> (B,N,Cv,H16,W16) (swem.py:51-62)."""
+        self._ready()
+        m, ve = self.model, self.model.value_encoder
+        n = masks.shape[1] - 1
+        bsz = frame.shape[0]
+        image = ((frame - ve.mean) / ve.std).unsqueeze(1).expand(-1, n, -1, -1, -1)
+        planes = [image, masks[:, 1:].unsqueeze(2)]
+        if not m.single_object:
+            others = 1 - masks - masks[:, 0:1]
+            planes.append(others[:, 1:].unsqueeze(2))
+        x = torch.cat(planes, dim=2).flatten(end_dim=1)            # (B*N, 3 + extra, H, W)
+        if self.channels_last:
+            x = x.contiguous(memory_format=torch.channels_last)
+        x = self._trunk(x, self.v_stem, self.v_stages)             # (B*N, 256, H16, W16), post-ReLU
+        # fuser.block1 on cat[x, f16]: both halves are post-ReLU, so block1's leading ReLU is the identity
+        shared = self._conv(s16, self.f_shared)                    # (B, 1024, H16, W16): [conv1 | downsample] of the f16 half
+        y = self._conv(x, self.f_obj)
+        y = y.view(bsz, n, *y.shape[1:]).add_(shared.unsqueeze(1)).flatten(end_dim=1)
+        r = self._conv(F.relu(y[:, :self.f_mid]), self.f_b1c2)
+        if self.f_has_down:
+            x = r.add_(y[:, self.f_mid:])
+        else:
+            x = r.add_(torch.cat([x.view(bsz, n, *x.shape[1:]), s16.unsqueeze(1).expand(-1, n, -1, -1, -1)], 2).flatten(end_dim=1))
+        x = x + ve.fuser.attention(x)
+        r = self._conv(self._conv(F.relu(x), self.f_b2c1, relu=True), self.f_b2c2)
+        x = r.add_(x)
+        return x.view(bsz, n, *x.shape[1:])
+
+    def match(self, qk16, qv16):
+        """Readout + GLU fusion: (context (B*N, Cv, H, W), N), as SWEMCore.matching (modules.py:278-293)."""
+        self._ready()
+        core = self.model.swem_core
+        n, cv = core._readout_objects()
+        bsz, _, h, w = qk16.shape
+        feats = torch.empty(bsz * n, cv + 2 * core.topl, h, w, device=qk16.device, dtype=torch.float32)
+        core.readout_into(qk16, feats, 0, cv)                      # [mem_out | S]
+        shared = self._conv(qv16, self.g_shared)                   # (B, 1024, H, W): [layer_f | layer_a] of the qv third
+        y = self._conv(feats, self.g_obj)
+        y = y.view(bsz, n, *y.shape[1:]).add_(shared.unsqueeze(1)).flatten(end_dim=1)
+        return y[:, :self.g_out] * torch.sigmoid(y[:, self.g_out:]), n
+
+    def decode(self, n, context, s8, s4, valid_obj, out_size):
+        """-> (logits, prob) (B, N+1, H, W), as SWEM.decode (swem.py:92-108)."""
+        self._ready()
+        bsz = context.shape[0] // n
+        x = self._conv(self._conv(F.relu(context), self.d_c1, relu=True), self.d_c2).add_(context)
+        for d, skip_f in zip(self.d_up, (s8, s4)):
+            skip = self._conv(skip_f, d['skip'])                   # once per frame, not per object
+            up = F.interpolate(x, size=skip.shape[-2:], mode='bilinear', align_corners=False)
+            x = up.view(bsz, n, *up.shape[1:]).add_(skip.unsqueeze(1)).flatten(end_dim=1)
+            r = self._conv(self._conv(F.relu(x), d['c1'], relu=True), d['c2'])
+            x = r.add_(x if d['down'] is None else self._conv(x, d['down']))
+        lr = self._conv(F.relu_(x), self.d_pred)                   # (B*n, 1, Hl, Wl)
+        return self.model.decode_from_lowres(lr, n, valid_obj, out_size)
+
+    _MODES = {'encode_key': 'encode_key', 'encode_value': 'encode_value', 'match': 'match', 'segment': 'decode'}
+
+    def __call__(self, mode, *args, **kwargs):
+        if mode in self._MODES:
+            return getattr(self, self._MODES[mode])(*args, **kwargs)
+        return self.model(mode, *args, **kwargs)                   # 'init' / 'memorize': the memory itself
+
+    @property
+    def swem_core(self):
+        return self.model.swem_core

@@ -148,7 +148,7 @@ class GraphedSequenceRunner(SequenceRunner):
             if self._seen < self.eager_steps:
                 self._seen += 1
                 return super().step(frame, memorize)
-            core = self.model.swem_core
+            core = self.model.swem_core                          # (FrameEngine forwards .swem_core to its model)
             core.static_banks = True
             self._frame = frame.clone()
             torch.cuda.synchronize(frame.device)

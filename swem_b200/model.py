@@ -84,20 +84,31 @@ class SWEM(nn.Module):
         s8 = s8.unsqueeze(1).expand(-1, n, -1, -1, -1).flatten(end_dim=1)
         s4 = s4.unsqueeze(1).expand(-1, n, -1, -1, -1).flatten(end_dim=1)
         if self.fused_decode_tail and context.is_cuda and not torch.is_grad_enabled() and n <= 16:
-            lr = self.decoder.lowres_logits(context, s8, s4).float().contiguous()      # (B*n, 1, Hl, Wl)
-            b = lr.shape[0] // n
-            h, w = int(out_size[0]), int(out_size[1])
-            logits = torch.empty(b, n + 1, h, w, device=lr.device, dtype=torch.float32)
-            prob = torch.empty_like(logits)
-            valid = None if valid_obj is None else valid_obj.float().contiguous()
-            with torch.cuda.device(lr.device):
-                rc = _lib.load().swem_decode_tail(lr.data_ptr(), b, n, lr.shape[-2], lr.shape[-1], h, w,
-                                                  None if valid is None else valid.data_ptr(),
-                                                  logits.data_ptr(), prob.data_ptr(),
-                                                  torch.cuda.current_stream(lr.device).cuda_stream)
-            _lib.check(rc, 'swem_decode_tail')
-            return logits, prob
+            return self.decode_from_lowres(self.decoder.lowres_logits(context, s8, s4), n, valid_obj, out_size)
         preds = torch.sigmoid(self.decoder(context, s8, s4, out_size))
+        return self._aggregate_objects(preds, n, valid_obj)
+
+    def decode_from_lowres(self, lr, n, valid_obj, out_size):
+        """(B*n, 1, Hl, Wl) decoder logits at 1/4 resolution -> (logits, prob) (B, n+1, H, W): the final
+        up-sampling of ``Decoder.forward`` + sigmoid + aggregation + softmax (swem.py:92-116)."""
+        if not (self.fused_decode_tail and lr.is_cuda and not torch.is_grad_enabled() and n <= 16):
+            preds = torch.sigmoid(F.interpolate(lr, size=out_size, mode='bilinear', align_corners=False))
+            return self._aggregate_objects(preds, n, valid_obj)
+        lr = lr.float().contiguous()
+        b = lr.shape[0] // n
+        h, w = int(out_size[0]), int(out_size[1])
+        logits = torch.empty(b, n + 1, h, w, device=lr.device, dtype=torch.float32)
+        prob = torch.empty_like(logits)
+        valid = None if valid_obj is None else valid_obj.float().contiguous()
+        with torch.cuda.device(lr.device):
+            rc = _lib.load().swem_decode_tail(lr.data_ptr(), b, n, lr.shape[-2], lr.shape[-1], h, w,
+                                              None if valid is None else valid.data_ptr(),
+                                              logits.data_ptr(), prob.data_ptr(),
+                                              torch.cuda.current_stream(lr.device).cuda_stream)
+        _lib.check(rc, 'swem_decode_tail')
+        return logits, prob
+
+    def _aggregate_objects(self, preds, n, valid_obj):
         preds = preds.view(-1, n, *preds.shape[-2:])
         if valid_obj is not None:
             preds = preds * valid_obj[:, 1:].unsqueeze(2).unsqueeze(2)

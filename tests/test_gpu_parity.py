@@ -474,3 +474,116 @@ def test_cuda_graph_runner_matches_eager_runner():
     noise = 1.0 - (outs[0] == outs[1]).flatten(1).float().mean(dim=1).min().item()    # eager vs eager (reduce-add order)
     agree = (outs[0] == outs[2]).flatten(1).float().mean(dim=1)
     check(f'graph_vs_eager(eager noise {noise:.1e})', 1.0 - agree.min().item(), max(2e-3, 4 * noise))
+
+
+@pytest.mark.parametrize('fused_conv', [False, True])
+def test_frame_engine_matches_modules(fused_conv):
+    """FrameEngine (BN folded, fused cuDNN conv+bias+relu, object-independent conv halves shared, readout into the
+    640-channel buffer) vs the plain torch modules on the same weights, every stage, fp32 convs."""
+    from swem_b200 import SWEM, make_config
+    from swem_b200.engine import FrameEngine
+    from swem_b200.synthetic import davis_sequence
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        torch.manual_seed(0)
+        model = SWEM(make_config(keydim=64, n_bases=128, n_iters=4, topl=64)).eval().to(DEV)
+        g = torch.Generator().manual_seed(3)
+        for m in model.modules():                      # non-trivial running statistics, so the folding is exercised
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.running_mean.copy_(torch.randn(m.num_features, generator=g) * 0.1)
+                m.running_var.copy_(torch.rand(m.num_features, generator=g) * 0.5 + 0.75)
+        eng = FrameEngine(model, channels_last=True, fused_conv=fused_conv)
+        N, h, w = 3, 240, 432
+        frames, init = davis_sequence(3, N, seed=2, size=(h, w))
+        frames, init = frames.to(DEV), init.to(DEV)
+        with torch.no_grad():
+            want = model('encode_key', frames[:, 0])
+            got = eng('encode_key', frames[:, 0])
+            for a, b, name in zip(got, want, ('qk16', 'qv16', 'f16', 'f8', 'f4')):
+                check(name, maxrel(a, b), 1e-4)
+            qk16, qv16, s16, s8, s4 = want
+            m0 = torch.nn.functional.interpolate(init, size=(h, w), mode='nearest')
+            mv = model('encode_value', frames[:, 0], m0, s16)
+            check('mv16', maxrel(eng('encode_value', frames[:, 0], m0, s16), mv), 1e-4)
+            torch.manual_seed(1)
+            model('init', qk16, mv, init)
+            model('memorize', qk16, mv, init.long(), init)         # both banks present
+            ctx_want, n = model('match', qk16, qv16)
+            ctx_got, n2 = eng('match', qk16, qv16)
+            assert n == n2 == N
+            check('context', maxrel(ctx_got, ctx_want), 1e-3)      # two launches of the readout: reduce-add order noise
+            lg_want, pr_want = model('segment', n, ctx_want, s8, s4, None, (h, w))
+            lg_got, pr_got = eng('segment', n, ctx_want, s8, s4, None, (h, w))
+            check('logits', maxrel(lg_got, lg_want), 1e-4)
+            check('prob', maxrel(pr_got, pr_want), 1e-4)
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def test_frame_engine_free_running_masks_vs_oracle():
+    """North-star mask agreement (>= 99.9 % per frame, 480p, 5 objects) with the whole per-frame loop in its
+    production form: FrameEngine stages + fused kernels, against the CPU oracle on the plain modules."""
+    from swem_b200 import SWEM, make_config
+    from swem_b200.engine import FrameEngine
+    from swem_b200.evaluator import evaluate_davis_seq
+    from swem_b200.synthetic import davis_sequence
+    T, N, h, w = 6, 5, 480, 864
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        torch.manual_seed(0)
+        cfg = make_config(keydim=64, n_bases=128, n_iters=4, topl=64)
+        nets_cpu = SWEM(cfg).eval()
+        model = SWEM(cfg).eval()
+        model.load_state_dict(nets_cpu.state_dict())
+        model = model.to(DEV)
+        frames, init = davis_sequence(T, N, seed=1, size=(h, w))
+        prior = dict(zip(('kappa', 'nu', 'zita'), O.random_init(1, N, 64, 128, 512, generator=torch.Generator().manual_seed(4))))
+        oracle = O.OracleSWEM(nets_cpu, 128, 4, 0.05, 64)
+        model.swem_core.random_init = lambda size, norm_dim=-2, dtype=None, device=None: tuple(t.to(device) for t in (prior['kappa'], prior['nu'], prior['zita']))
+        real_init = O.random_init
+        O.random_init = lambda *a, **k: (prior['kappa'], prior['nu'], prior['zita'])
+        try:
+            want = torch.stack(O.run_davis_sequence(oracle, frames, init, (h, w)))
+        finally:
+            O.random_init = real_init
+        got, _ = evaluate_davis_seq(FrameEngine(model), frames.to(DEV), [init.to(DEV)] + [None] * (T - 1), (h, w))
+        got = torch.stack(got).cpu()
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    per_frame = (got == want).flatten(1).float().mean(dim=1)
+    check('min_agree', 1.0 - per_frame.min().item(), 1.0 - 0.999)
+
+
+def test_generic_family_is_bit_reproducible():
+    """The generic kernels use no atomics: the same inputs must give bit-identical bases and features, call after
+    call (a stress loop that would expose a race or a read of uninitialised scratch)."""
+    cfg = dict(L=8, Cv=24, n_iters=3, tau=0.05, topl=4)
+    core = _core(cfg, 'generic')
+    g = torch.Generator().manual_seed(11)
+    B, N, Ck, H, W = 2, 2, 16, 5, 7
+    x = torch.randn(B, Ck, H, W, generator=g).to(DEV)
+    v = torch.randn(B, N, cfg['Cv'], H, W, generator=g).to(DEV)
+    masks = torch.rand(B, N, 2, H, W, generator=g).to(DEV)
+    prior = _to(dict(zip(('kappa', 'nu', 'zita'), O.random_init(B, N, Ck, cfg['L'], cfg['Cv'], generator=g))), DEV)
+    ref = None
+    with torch.no_grad():
+        for rep in range(40):
+            if rep % 2:                                   # dirty the caching allocator's blocks between calls
+                junk = torch.full((1 << 18,), float('nan'), device=DEV); del junk
+            bases = core.swem(x, v, masks, prior)
+            core.memories['first'].bases, core.memories['first'].n_objs = bases, N
+            core.memories['update'].bases = None if rep % 4 < 2 else bases
+            feats, _ = core.matching_features(x, v[:, 0])
+            out = [bases[k].cpu() for k in ('kappa', 'nu', 'zita')] + [feats.cpu()]
+            key = rep % 4 < 2
+            if ref is None:
+                ref = {}
+            if key not in ref:
+                ref[key] = out
+            else:
+                for a, b in zip(out, ref[key]):
+                    assert torch.equal(a, b), f'rep {rep}: generic kernels are not reproducible'
