@@ -24,6 +24,7 @@
 // After the last E-step: nu partial = Z^T V^T (two passes over Cv halves, V streamed through a
 // 3-stage fp16 ring), reduce-added the same way, then each CTA normalises a slice of nu.
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "tc05.cuh"
@@ -616,13 +617,34 @@ static int sm_count() {
   return n;
 }
 
+// SWEM_EM_KERNEL=v1 keeps the first-generation kernel of this file (one CTA per tile, both sides); the default is the
+// pair kernel of fused_em2.cu.
+static bool use_v1() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SWEM_EM_KERNEL");
+    v = (e != nullptr && e[0] == 'v' && e[1] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+
+int launch_nu_finalize(const float* acc_nu, const float* nu_prior, const float* zita_prior, const float* zita, float* nu,
+                       int G, cudaStream_t st) {
+  const int n4 = G * em::kCv * em::kL / 4;
+  nu_finalize_kernel<<<(n4 + 255) / 256, 256, 0, st>>>(acc_nu, nu_prior, zita_prior, zita, nu, G);
+  SWEM_LAUNCH_CHECK();
+  return SWEM_OK;
+}
+
 bool fused_em_supported(const SwemDims& d) {
+  if (!use_v1()) return fused_em2_supported(d);
   if (d.Ck != em::kCk || d.L != em::kL || d.Cv != em::kCv || d.n_iters < 1 || d.n_iters > 16) return false;
   const int T = (d.HW + em::kTP - 1) / em::kTP;
   return T >= 1 && T <= 128;
 }
 
 size_t fused_em_workspace(const SwemDims& d) {
+  if (!use_v1()) return fused_em2_workspace(d);
   const size_t U = (size_t)d.B * d.N;
   size_t bytes = 0;
   bytes += align_up(U * d.n_iters * em::kAccBytes, 256);
@@ -632,6 +654,7 @@ size_t fused_em_workspace(const SwemDims& d) {
 }
 
 int fused_em_forward(const SwemEmArgs& a, cudaStream_t st) {
+  if (!use_v1()) return fused_em2_forward(a, st);
   const SwemDims& d = a.dims;
   const int U = d.B * d.N;
   const int T = (d.HW + em::kTP - 1) / em::kTP;
@@ -664,12 +687,7 @@ int fused_em_forward(const SwemEmArgs& a, cudaStream_t st) {
     em_fused_kernel<<<nu * T, 256, em::kSmemBytes, st>>>(p);
     SWEM_LAUNCH_CHECK();
   }
-  {
-    const int n4 = U * 2 * em::kCv * em::kL / 4;
-    nu_finalize_kernel<<<(n4 + 255) / 256, 256, 0, st>>>(acc_nu, a.nu_prior, a.zita_prior, a.zita, a.nu, U * 2);
-    SWEM_LAUNCH_CHECK();
-  }
-  return SWEM_OK;
+  return launch_nu_finalize(acc_nu, a.nu_prior, a.zita_prior, a.zita, a.nu, U * 2, st);
 }
 
 }  // namespace swem

@@ -1,0 +1,675 @@
+// Fused sequential-weighted-EM kernel, second generation ("pair" kernel): one CTA per
+// (unit u = (b,n), pixel tile of 128 px, side s), the two sides of a tile forming a 2-CTA cluster.
+//
+// Same arithmetic and reference semantics as fused_em.cu (methods/SWEM/modules.py:129-168: E :112-120,
+// M :122-127, W :93-110, nu :164-165; operands fp16 hi + lo, fp32 accumulation in TMEM, fp32 softmax),
+// reorganised so that a 5-object 480p frame fills 130 of the 148 SMs instead of 65:
+//
+//   * every per-CTA phase handles one side only: 128 logits columns, 128 basis rows, half the exps, half
+//     of the M-step / nu partials that have to be reduce-added through L2;
+//   * the only coupling between the sides -- the W-step's share of exp-affinity per side (:101-108) -- is
+//     one (max, sum) pair per pixel exchanged through distributed shared memory and a cluster barrier;
+//   * nu = Z^T V^T needs a single pass (its [128 bases][512 channels] accumulator is exactly the 512 TMEM
+//     columns); V is converted once per call to fp16 hi/lo operand images by `v_blob_kernel`, so this
+//     kernel streams it with plain bulk-async copies (3-stage ring, issued by one thread, prefetched from
+//     the first cycle of the kernel) instead of staging it through registers.
+//
+// Cross-tile sums (M-step partials, nu partials) use the same protocol as fused_em.cu: bulk reduce-add
+// into an L2-resident accumulator, per-(unit, side, iteration) arrival counter, bounded spin.
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+#include "tc05.cuh"
+#include "fused_common.cuh"
+
+namespace swem {
+
+using namespace tc05;
+
+namespace em2 {
+constexpr int kTP = 128;    // pixels per CTA
+constexpr int kCk = 64;
+constexpr int kL = 128;     // bases per side = rows owned by one CTA
+constexpr int kCv = 512;
+constexpr int kAccRow = 73; // floats per accumulator row: 64 kappa sums, 1 zita sum, pad (odd stride)
+constexpr uint32_t kAccBytes = kL * kAccRow * 4;   // 37376
+constexpr float kKScale = 256.f;
+constexpr float kZScale = 16384.f;
+constexpr uint32_t kStageBytes = 32768;            // one V operand image: [256 d][32 px] fp16, hi plane then lo plane
+constexpr uint32_t kVPlane = 16384;
+constexpr int kStages = 3;
+constexpr int kChunks = 8;                         // per tile: 2 channel halves x 4 pixel quarters
+
+// ---- shared memory map (bytes) ---------------------------------------------------------------
+// XH : [c 0..79][p] : byte = (c%8)*16 + (c/8)*2048 + (p/8)*128 + (p%8)*2      (row 64 = ones, 65..79 = 0)
+// XL : [c 0..63][p]   E-step A (MN-major, r=p, k=c): SBO=128, LBO=2048; M-step B (K-major, r=c, k=p): SBO=2048, LBO=128
+// KH/KL : [l 0..127][c] K-major: byte = (l%8)*16 + (l/8)*128 + (c/8)*2048 + (c%8)*2   -> SBO=128, LBO=2048
+// Z  : [l 0..127][p] MN-major A: byte = (l%8)*2 + (p%8)*16 + (l/8)*2048 + (p/8)*128   -> SBO=2048, LBO=128
+// ZL : lo half of z (aliases KH/KL: khat is dead between the logits GEMM and the finalize)
+// P  : fp32 [128][73] staging of the M-step partial / total (aliases Z)
+// VS : ring of V operand images, each [d 0..255][p 0..31] K-major: byte = (d%8)*16 + (d/8)*128 + (p/8)*4096 + (p%8)*2
+//      -> SBO=128, LBO=4096; hi plane then lo plane.  The nu drain staging (2 x 32 KB fp32) aliases the ring.
+constexpr uint32_t kOffXH = 0;
+constexpr uint32_t kOffXL = kOffXH + 10 * 2048;
+constexpr uint32_t kOffKH = kOffXL + 8 * 2048;
+constexpr uint32_t kOffKL = kOffKH + 8 * 2048;
+constexpr uint32_t kOffZ = kOffKL + 8 * 2048;
+constexpr uint32_t kOffZL = kOffKH;
+constexpr uint32_t kOffVS = kOffZ + kAccBytes;
+constexpr uint32_t kOffMisc = kOffVS + kStages * kStageBytes;
+static_assert(kAccBytes % 128 == 0 && kAccBytes >= 16 * 2048, "P must cover Z");
+struct Misc {
+  float inv_nx[kTP];
+  float mask[kTP];
+  float hmax[2][kTP];
+  float hsum[2][kTP];
+  float hew[2][kTP];
+  float2 mbox[2][2][kTP];   // [iteration parity][side][pixel] = (side max of the logits, side sum of W-step exps)
+  uint64_t bar_mma;
+  uint64_t bar_tma;
+  uint64_t bar_full[kStages];
+  uint64_t bar_empty[kStages];
+  uint32_t tmem_base;
+  int abort_flag;
+};
+constexpr uint32_t kSmemBytes = kOffMisc + sizeof(Misc) + 128;
+static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
+
+// TMEM columns
+constexpr uint32_t kColE = 0;      // [128 px][128]  E / W logits of this side
+constexpr uint32_t kColM = 128;    // [128 l][80]    M-step sums
+constexpr uint32_t kColNu = 0;     // [128 l][512 d] nu sums (after the last M-step partial has been read out)
+}  // namespace em2
+
+struct EmPairParams {
+  const float* x;
+  const float* masks;
+  const float* kappa_prior;
+  const float* zita_prior;
+  float* kappa;
+  float* zita;
+  float* z_last;
+  const uint8_t* vblob;  // [U][T][8][32 KB] operand images written by v_blob_kernel
+  float* acc_k;          // [U][n_iters][2][128][73], zeroed before launch
+  float* acc_nu;         // [U][2][512][128], zeroed before launch
+  unsigned* counters;    // [U][n_iters][2], zeroed before launch
+  int* status;
+  long long* prof;
+  int N, HW, T, n_iters, u0;
+  float c1s;             // log2(e) / (tau * kKScale)
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ uint32_t map_to_peer(uint32_t smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_cluster_f2(uint32_t addr, float a, float b) {
+  asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(a), "f"(b) : "memory");
+}
+
+#define EM2_STAMP()                                                  \
+  do {                                                               \
+    if (p.prof != nullptr && blockIdx.x == 0 && tid == 0 && n_stamp < 120) p.prof[1 + n_stamp++] = global_ns(); \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------------
+// V -> fp16 hi/lo operand images.  Block = (unit, tile, chunk = channel half h * 4 + pixel quarter q):
+// [256 d][32 px] fp32 in, 32 KB image out (pixels past HW are zero).
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) v_blob_kernel(const float* __restrict__ v, uint8_t* __restrict__ blob, int HW, int T) {
+  using namespace em2;
+  const int chunk = blockIdx.x % kChunks;
+  const int tile = (blockIdx.x / kChunks) % T;
+  const int u = blockIdx.x / (kChunks * T);
+  const int h = chunk >> 2, q = chunk & 3;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane & 3;                               // group of 8 pixels
+  const int px0 = tile * kTP + q * 32 + g * 8;
+  const bool vec_ok = ((HW & 3) == 0) && (px0 + 7 < HW);
+  uint8_t* out = blob + (size_t)blockIdx.x * kStageBytes;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int d = warp * 32 + j * 8 + (lane >> 2);      // 0..255
+    const float* src = v + ((size_t)u * kCv + h * 256 + d) * HW + px0;
+    float f[8];
+    if (vec_ok) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(src));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(src) + 1);
+      f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) f[e] = (px0 + e < HW) ? __ldg(src + e) : 0.f;
+    }
+    __align__(16) __half hi[8];
+    __align__(16) __half lo[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) split_half(f[e], hi[e], lo[e]);
+    const uint32_t off = (d % 8) * 16 + (d / 8) * 128 + g * 4096;
+    *reinterpret_cast<uint4*>(out + off) = *reinterpret_cast<uint4*>(hi);
+    *reinterpret_cast<uint4*>(out + kVPlane + off) = *reinterpret_cast<uint4*>(lo);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) em_pair_kernel(const EmPairParams p) {
+  using namespace em2;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  Misc& ms = *reinterpret_cast<Misc*>(smem + kOffMisc);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int sd = (int)cluster_ctarank();                // side handled by this CTA (0 = background, 1 = foreground)
+  const int pair = blockIdx.x >> 1;
+  const int tile = pair % p.T;
+  const int u = p.u0 + pair / p.T;
+  const int b = u / p.N;
+  const int p0 = tile * kTP;
+  const int HW = p.HW;
+  const int I = p.n_iters;
+  const uint32_t sbase = smem_u32(smem);
+  int n_stamp = 0;
+  EM2_STAMP();
+
+  // ---- one-time setup -------------------------------------------------------------------------
+  if (warp == 0) tmem_alloc(&ms.tmem_base, 512);
+  if (tid == 0) {
+    mbar_init(&ms.bar_mma, 1);
+    mbar_init(&ms.bar_tma, 1);
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&ms.bar_full[i], 1);
+      mbar_init(&ms.bar_empty[i], 1);
+    }
+    ms.abort_flag = 0;
+    fence_mbar_init();
+    // V operand images of this tile: the first kStages chunks start flying now, they are consumed after the last E-step
+    const uint8_t* src = p.vblob + ((size_t)u * p.T + tile) * kChunks * kStageBytes;
+    for (int k = 0; k < kStages; ++k) {
+      mbar_expect_tx(&ms.bar_full[k], kStageBytes);
+      bulk_g2s(smem + kOffVS + k * kStageBytes, src + (size_t)k * kStageBytes, kStageBytes, &ms.bar_full[k]);
+    }
+  }
+  // rows: thread tid < 128 <-> basis l = tid of side sd (finalize steps)
+  const bool row_thread = tid < kL;
+  const int gs = u * 2 + sd;                            // (b, n, s) index
+  const float zita_p = row_thread ? __ldg(p.zita_prior + (size_t)gs * kL + tid) : 0.f;
+  const float* kprior = p.kappa_prior + ((size_t)gs * kCk) * kL + (tid & (kL - 1));   // + c*kL
+  auto stage_khat = [&](const float (&kap)[kCk]) {      // khat = l2norm(kappa) * 256 -> fp16 hi/lo K-major rows (reference :115)
+    float ss = 0.f;
+#pragma unroll
+    for (int c = 0; c < kCk; ++c) ss = fmaf(kap[c], kap[c], ss);
+    const float sc = kKScale / (sqrtf(ss) + kEpsNorm);
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      __align__(16) __half hi[8];
+      __align__(16) __half lo[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) split_half(kap[g * 8 + e] * sc, hi[e], lo[e]);
+      const uint32_t off = (tid % 8) * 16 + (tid / 8) * 128 + g * 2048;
+      *reinterpret_cast<uint4*>(smem + kOffKH + off) = *reinterpret_cast<uint4*>(hi);
+      *reinterpret_cast<uint4*>(smem + kOffKL + off) = *reinterpret_cast<uint4*>(lo);
+    }
+  };
+  float kap0[kCk];
+  if (row_thread) {
+#pragma unroll
+    for (int c = 0; c < kCk; ++c) kap0[c] = __ldg(kprior + (size_t)c * kL);
+  }
+  // pixel norms + this side's mask (threads 128..255 <-> pixel, so they overlap with the prior loads of the row threads)
+  if (!row_thread) {
+    const int q = tid - kL, px = p0 + q;
+    float ss = 0.f;
+    if (px < HW) {
+      const float* xp = p.x + (size_t)b * kCk * HW + px;
+#pragma unroll 8
+      for (int c = 0; c < kCk; ++c) {
+        const float t = __ldg(xp + (size_t)c * HW);
+        ss = fmaf(t, t, ss);
+      }
+    }
+    ms.inv_nx[q] = 1.f / (sqrtf(ss) + kEpsNorm);
+    ms.mask[q] = px < HW ? __ldg(p.masks + (size_t)gs * HW + px) : 0.f;
+  }
+  // X tile -> fp16 hi/lo chunks.  thread -> (channel c = tid/4, 4 pixel groups of 8)
+  {
+    const int c = tid >> 2;
+    const float* xrow = p.x + ((size_t)b * kCk + c) * HW;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int pg = (tid & 3) * 4 + j;
+      __align__(16) __half hi[8];
+      __align__(16) __half lo[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int px = p0 + pg * 8 + e;
+        const float val = px < HW ? __ldg(xrow + px) : 0.f;
+        split_half(val, hi[e], lo[e]);
+      }
+      const uint32_t off = (c % 8) * 16 + (c / 8) * 2048 + pg * 128;
+      *reinterpret_cast<uint4*>(smem + kOffXH + off) = *reinterpret_cast<uint4*>(hi);
+      *reinterpret_cast<uint4*>(smem + kOffXL + off) = *reinterpret_cast<uint4*>(lo);
+    }
+    for (int i = tid; i < 16 * 16; i += 256) {          // augmented rows 64..79 of XH: row 64 = 1 (-> zita), rest 0
+      const int r = 64 + (i >> 4), pg = i & 15;
+      const __half one = __float2half_rn(r == 64 ? 1.f : 0.f);
+      __align__(16) __half vals[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) vals[e] = one;
+      *reinterpret_cast<uint4*>(smem + kOffXH + (r % 8) * 16 + (r / 8) * 2048 + pg * 128) = *reinterpret_cast<uint4*>(vals);
+    }
+  }
+  if (row_thread) stage_khat(kap0);
+  tc_fence_before_sync();
+  cluster_arrive();                   // both CTAs of the pair are running before any remote shared-memory store
+  cluster_wait();
+  tc_fence_after_sync();
+  const uint32_t tmem = ms.tmem_base;
+  uint32_t ph_mma = 0, ph_tma = 0;
+  bool failed = false;
+  EM2_STAMP();                        // setup done
+
+  const uint32_t idesc_e = make_idesc(128, 128, kFmtF16, kFmtF16, kMajorMN, kMajorK);
+  const uint32_t idesc_m80 = make_idesc(128, 80, kFmtF16, kFmtF16, kMajorMN, kMajorK);
+  const uint32_t idesc_m64 = make_idesc(128, 64, kFmtF16, kFmtF16, kMajorMN, kMajorK);
+  const uint32_t idesc_nu = make_idesc(128, 256, kFmtF16, kFmtF16, kMajorMN, kMajorK);
+  const uint32_t peer_mbox = map_to_peer(smem_u32(&ms.mbox[0][0][0]), (uint32_t)(sd ^ 1));
+
+  for (int it = 0; it < I; ++it) {
+    fence_proxy_async_smem();
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+
+    // ---- (1) logits of this side: a[p, l] = x_p . khat_l ---------------------------------------------
+    if (warp == 0) {
+      if (lane == 0) {
+#pragma unroll
+        for (int term = 0; term < 3; ++term) {
+          const uint32_t xa = sbase + (term == 2 ? kOffXL : kOffXH);
+          const uint32_t kb = sbase + (term == 1 ? kOffKL : kOffKH);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            const uint64_t ad = make_sdesc(xa + kk * 2 * 2048, /*lbo*/ 2048, /*sbo*/ 128);
+            const uint64_t bd = make_sdesc(kb + kk * 2 * 2048, /*lbo*/ 2048, /*sbo*/ 128);
+            mma_f16_ss(tmem + kColE, ad, bd, idesc_e, (term | kk) ? 1u : 0u);
+          }
+        }
+        mma_commit(&ms.bar_mma);
+      }
+      __syncwarp();
+    }
+    SWEM_CTA_WAIT(&ms.bar_mma, ph_mma, ms.abort_flag);
+    ph_mma ^= 1;
+    tc_fence_after_sync();
+    EM2_STAMP();                      // logits GEMM done
+
+    // ---- (2) epilogue: thread <-> (pixel px, half hb of this side's bases) ------------------------------
+    {
+      const int px = (warp & 3) * 32 + lane, hb = warp >> 2;
+      const bool do_w = it > 0;
+      float a[64];
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        uint32_t r[32];
+        tmem_ld32(tmem_addr(tmem, (warp & 3) * 32, kColE + hb * 64 + q * 32), r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) a[q * 32 + j] = __uint_as_float(r[j]);
+      }
+      float mx = a[0];
+#pragma unroll
+      for (int i = 1; i < 64; ++i) mx = fmaxf(mx, a[i]);
+      ms.hmax[hb][px] = mx;
+      __syncthreads();
+      mx = fmaxf(ms.hmax[0][px], ms.hmax[1][px]);       // max over this side's 128 bases
+      // W-step (reference :93-110) works on t = a * inv_nx with the max over BOTH sides; each side sums its exps
+      // against its own max and the pair rescales after the exchange: exp(t - M) = exp(t - m_s) * exp(m_s - M).
+      const float cw = ms.inv_nx[px] * p.c1s;
+      float e = 0.f, sum = 0.f;
+      if (do_w) {
+#pragma unroll
+        for (int i = 0; i < 64; ++i) e += fast_exp2((a[i] - mx) * cw);
+      }
+#pragma unroll
+      for (int i = 0; i < 64; ++i) {
+        a[i] = fast_exp2((a[i] - mx) * p.c1s);
+        sum += a[i];
+      }
+      ms.hsum[hb][px] = sum;
+      ms.hew[hb][px] = e;
+      __syncthreads();
+      sum = ms.hsum[0][px] + ms.hsum[1][px];
+      float w = ms.mask[px];
+      if (do_w) {
+        const int par = it & 1;
+        if (hb == 0) {
+          const float es = ms.hew[0][px] + ms.hew[1][px];
+          ms.mbox[par][sd][px] = make_float2(mx, es);
+          st_cluster_f2(peer_mbox + (uint32_t)(((par * 2 + sd) * kTP + px) * sizeof(float2)), mx, es);
+        }
+        cluster_arrive();
+        cluster_wait();
+        const float2 m0 = ms.mbox[par][0][px], m1 = ms.mbox[par][1][px];
+        const float gm = fmaxf(m0.x, m1.x);
+        const float e0 = m0.y * fast_exp2((m0.x - gm) * cw), e1 = m1.y * fast_exp2((m1.x - gm) * cw);
+        w *= 1.f - (sd ? e1 : e0) / (e0 + e1);
+      }
+      const float scale = w / sum;
+      const float zs = scale * kZScale;
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        __align__(16) __half hi[8];
+        __align__(16) __half lo[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) split_half(a[g * 8 + k] * zs, hi[k], lo[k]);
+        const uint32_t off = (px % 8) * 16 + (px / 8) * 128 + (hb * 8 + g) * 2048;
+        *reinterpret_cast<uint4*>(smem + kOffZ + off) = *reinterpret_cast<uint4*>(hi);
+        *reinterpret_cast<uint4*>(smem + kOffZL + off) = *reinterpret_cast<uint4*>(lo);
+      }
+      if (p.z_last != nullptr && it == I - 1 && p0 + px < HW) {
+        float4* dst = reinterpret_cast<float4*>(p.z_last + ((size_t)gs * HW + p0 + px) * kL + hb * 64);
+#pragma unroll
+        for (int g = 0; g < 16; ++g)
+          dst[g] = make_float4(a[g * 4] * scale, a[g * 4 + 1] * scale, a[g * 4 + 2] * scale, a[g * 4 + 3] * scale);
+      }
+    }
+    fence_proxy_async_smem();
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    EM2_STAMP();                      // epilogue done
+
+    // ---- (3) M-step GEMM: [sum_p z x | sum_p z] for this side's 128 bases --------------------------------
+    if (warp == 0) {
+      if (lane == 0) {
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          const uint64_t ad = make_sdesc(sbase + kOffZ + kk * 2 * 128, /*lbo*/ 128, /*sbo*/ 2048);
+          const uint64_t al = make_sdesc(sbase + kOffZL + kk * 2 * 128, /*lbo*/ 128, /*sbo*/ 2048);
+          const uint64_t bh = make_sdesc(sbase + kOffXH + kk * 2 * 128, /*lbo*/ 128, /*sbo*/ 2048);
+          const uint64_t bl = make_sdesc(sbase + kOffXL + kk * 2 * 128, /*lbo*/ 128, /*sbo*/ 2048);
+          mma_f16_ss(tmem + kColM, ad, bh, idesc_m80, kk ? 1u : 0u);   // z_hi x_hi (+ zita column)
+          mma_f16_ss(tmem + kColM, ad, bl, idesc_m64, 1u);             // z_hi x_lo
+          mma_f16_ss(tmem + kColM, al, bh, idesc_m80, 1u);             // z_lo x_hi
+        }
+        mma_commit(&ms.bar_mma);
+      }
+      __syncwarp();
+    }
+    SWEM_CTA_WAIT(&ms.bar_mma, ph_mma, ms.abort_flag);
+    ph_mma ^= 1;
+    tc_fence_after_sync();
+    EM2_STAMP();                      // M GEMM done
+
+    float part[kCk + 1];              // partial of this tile for row l = tid (row threads only)
+    if (row_thread) {
+      uint32_t r[32];
+      const uint32_t base = tmem_addr(tmem, (warp & 3) * 32, kColM);
+      tmem_ld32(base, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) part[j] = __uint_as_float(r[j]);
+      tmem_ld32(base + 32, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) part[32 + j] = __uint_as_float(r[j]);
+      uint32_t r16[16];
+      tmem_ld16(base + 64, r16);
+      tmem_ld_wait();
+      part[64] = __uint_as_float(r16[0]);
+    }
+    tc_fence_before_sync();
+
+    const bool last = (it == I - 1);
+    if (last) {
+      // ---- nu partial = Z^T V^T for this side: one pass, V images streamed through the ring ---------------
+      __syncthreads();
+      tc_fence_after_sync();
+      if (warp == 0) {
+        if (lane == 0) {
+          const uint8_t* src = p.vblob + ((size_t)u * p.T + tile) * kChunks * kStageBytes;
+#pragma unroll 1
+          for (int seq = 0; seq < kChunks; ++seq) {
+            const int st = seq % kStages;
+            if (!mbar_wait(&ms.bar_full[st], (seq / kStages) & 1)) ms.abort_flag = 1;
+            tc_fence_after_sync();
+            const int h = seq >> 2, q = seq & 3;
+            const uint32_t vb = sbase + kOffVS + st * kStageBytes;
+#pragma unroll
+            for (int kk = 0; kk < 2; ++kk) {
+              const uint64_t ad = make_sdesc(sbase + kOffZ + (q * 2 + kk) * 2 * 128, /*lbo*/ 128, /*sbo*/ 2048);
+              const uint64_t al = make_sdesc(sbase + kOffZL + (q * 2 + kk) * 2 * 128, /*lbo*/ 128, /*sbo*/ 2048);
+              const uint64_t bh = make_sdesc(vb + kk * 2 * 4096, /*lbo*/ 4096, /*sbo*/ 128);
+              const uint64_t bl = make_sdesc(vb + kVPlane + kk * 2 * 4096, /*lbo*/ 4096, /*sbo*/ 128);
+              mma_f16_ss(tmem + kColNu + h * 256, ad, bh, idesc_nu, (q | kk) ? 1u : 0u);   // z_hi v_hi
+              mma_f16_ss(tmem + kColNu + h * 256, ad, bl, idesc_nu, 1u);                    // z_hi v_lo
+              mma_f16_ss(tmem + kColNu + h * 256, al, bh, idesc_nu, 1u);                    // z_lo v_hi
+            }
+            mma_commit(&ms.bar_empty[st]);
+            if (seq >= 1 && seq + 2 < kChunks) {        // refill the stage chunk seq-1 used: its MMAs have had a chunk's time to retire
+              const int pst = (seq - 1) % kStages;
+              if (!mbar_wait(&ms.bar_empty[pst], ((seq - 1) / kStages) & 1)) ms.abort_flag = 1;
+              mbar_expect_tx(&ms.bar_full[pst], kStageBytes);
+              bulk_g2s(smem + kOffVS + pst * kStageBytes, src + (size_t)(seq + 2) * kStageBytes, kStageBytes, &ms.bar_full[pst]);
+            }
+          }
+          mma_commit(&ms.bar_mma);
+        }
+        __syncwarp();
+      }
+      SWEM_CTA_WAIT(&ms.bar_mma, ph_mma, ms.abort_flag);
+      ph_mma ^= 1;
+      tc_fence_after_sync();
+      EM2_STAMP();                    // nu GEMMs done
+      // drain: TMEM [128 l][512 d] -> smem [64 d][128 l] fp32 -> bulk reduce-add into acc_nu, 8 rounds, two staging
+      // buffers in the (now idle) V ring: round q only waits for the reads of round q-2.
+      {
+        const int l = (warp & 3) * 32 + lane, cg = warp >> 2;
+#pragma unroll 1
+        for (int q = 0; q < 8; ++q) {
+          float* ns = reinterpret_cast<float*>(smem + kOffVS + (q & 1) * kStageBytes);
+          if (q >= 2) {
+            if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            __syncthreads();
+          }
+          {
+            uint32_t r[32];
+            tmem_ld32(tmem_addr(tmem, (warp & 3) * 32, kColNu + q * 64 + cg * 32), r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) ns[(cg * 32 + j) * 128 + l] = __uint_as_float(r[j]);
+          }
+          fence_proxy_async_smem();
+          __syncthreads();
+          if (tid == 0) {
+            float* dst = p.acc_nu + ((size_t)gs * kCv + q * 64) * kL;
+            asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(dst),
+                         "r"(smem_u32(ns)), "r"(64 * 128 * 4)
+                         : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+        }
+        if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      }
+      tc_fence_before_sync();
+      __syncthreads();
+      tc_fence_after_sync();
+      EM2_STAMP();                    // nu drained
+    }
+
+    // ---- (4) cross-tile reduction of the M-step partial ---------------------------------------------------
+    __syncthreads();                  // Z is dead now: P may alias it
+    if (row_thread) {
+      float* P = reinterpret_cast<float*>(smem + kOffZ);
+#pragma unroll
+      for (int c = 0; c <= kCk; ++c) P[tid * kAccRow + c] = part[c];
+#pragma unroll
+      for (int c = kCk + 1; c < kAccRow; ++c) P[tid * kAccRow + c] = 0.f;
+    }
+    fence_proxy_async_smem();
+    __syncthreads();
+    float* acc = p.acc_k + ((size_t)(u * I + it) * 2 + sd) * (kL * kAccRow);
+    unsigned* counter = p.counters + ((size_t)u * I + it) * 2 + sd;
+    float kpr[kCk];                   // prior row: loads fly during the cross-tile wait
+    if (row_thread) {
+#pragma unroll
+      for (int c = 0; c < kCk; ++c) kpr[c] = __ldg(kprior + (size_t)c * kL);
+    }
+    if (warp == 0) {
+      if (lane == 0) {
+        asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(acc),
+                     "r"(sbase + kOffZ), "r"(kAccBytes)
+                     : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        EM2_STAMP();                  // partial reduce-added
+        __threadfence();
+        atomicAdd(counter, 1u);
+        const bool arrived = wait_counter(counter, (unsigned)p.T);
+        EM2_STAMP();                  // all tiles arrived
+        if (!arrived) ms.abort_flag = 1;
+        __threadfence();
+        asm volatile("fence.proxy.async;" ::: "memory");
+        mbar_expect_tx(&ms.bar_tma, kAccBytes);
+        bulk_g2s(smem + kOffZ, acc, kAccBytes, &ms.bar_tma);
+      }
+      __syncwarp();
+    }
+    SWEM_CTA_WAIT(&ms.bar_tma, ph_tma, ms.abort_flag);
+    ph_tma ^= 1;
+    if (ms.abort_flag) {
+      if (tid == 0) atomicExch(p.status, 1 + it);
+      failed = true;
+      break;
+    }
+    EM2_STAMP();                      // total loaded
+    // ---- (5) finalize row l = tid from the prior (reference :125-126) ---------------------------------------
+    if (row_thread) {
+      const float* P = reinterpret_cast<const float*>(smem + kOffZ) + tid * kAccRow;
+      constexpr float kInvZ = 1.f / kZScale;
+      const float zita_cur = zita_p + P[kCk] * kInvZ;
+      const float rz = 1.f / zita_cur;
+      float kap[kCk];
+#pragma unroll
+      for (int c = 0; c < kCk; ++c) kap[c] = (zita_p * kpr[c] + P[c] * kInvZ) * rz;
+      if (last) {
+        if (tile == 0) {
+          p.zita[(size_t)gs * kL + tid] = zita_cur;
+          float* kout = p.kappa + ((size_t)gs * kCk) * kL + tid;
+#pragma unroll
+          for (int c = 0; c < kCk; ++c) kout[(size_t)c * kL] = kap[c];
+        }
+      } else {
+        stage_khat(kap);
+      }
+    }
+    __syncthreads();
+    EM2_STAMP();                      // finalize done
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  EM2_STAMP();
+  if (p.prof != nullptr && blockIdx.x == 0 && tid == 0) p.prof[0] = n_stamp;
+  if (warp == 0) tmem_dealloc(tmem, 512);
+  if (failed || ms.abort_flag) __trap();
+}
+
+// ------------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------------
+static int max_pairs_resident() {
+  static int n = -1;
+  if (n < 0) {
+    cudaFuncSetAttribute(em_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)em2::kSmemBytes);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2, 1, 1);
+    cfg.blockDim = dim3(256, 1, 1);
+    cfg.dynamicSmemBytes = em2::kSmemBytes;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int clusters = 0;
+    if (cudaOccupancyMaxActiveClusters(&clusters, em_pair_kernel, &cfg) != cudaSuccess || clusters <= 0) {
+      cudaGetLastError();
+      int dev = 0, sms = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      clusters = sms / 2 - 2;                          // conservative guess
+    }
+    n = clusters;
+  }
+  return n;
+}
+
+bool fused_em2_supported(const SwemDims& d) {
+  if (d.Ck != em2::kCk || d.L != em2::kL || d.Cv != em2::kCv || d.n_iters < 1 || d.n_iters > 16) return false;
+  const int T = (d.HW + em2::kTP - 1) / em2::kTP;
+  return T >= 1 && T <= 64;
+}
+
+size_t fused_em2_workspace(const SwemDims& d) {
+  const size_t U = (size_t)d.B * d.N;
+  const size_t T = (d.HW + em2::kTP - 1) / em2::kTP;
+  size_t bytes = 0;
+  bytes += align_up(U * d.n_iters * 2 * em2::kAccBytes, 256);
+  bytes += align_up(U * 2 * em2::kCv * em2::kL * 4, 256);
+  bytes += align_up(U * d.n_iters * 2 * 4 + 4, 256);
+  bytes += align_up(U * T * em2::kChunks * em2::kStageBytes, 256);
+  return bytes + 256;
+}
+
+int fused_em2_forward(const SwemEmArgs& a, cudaStream_t st) {
+  const SwemDims& d = a.dims;
+  const int U = d.B * d.N;
+  const int T = (d.HW + em2::kTP - 1) / em2::kTP;
+  Arena ws(a.workspace);
+  float* acc_k = ws.take<float>((size_t)U * d.n_iters * 2 * em2::kL * em2::kAccRow);
+  float* acc_nu = ws.take<float>((size_t)U * 2 * em2::kCv * em2::kL);
+  unsigned* counters = ws.take<unsigned>((size_t)U * d.n_iters * 2 + 1);
+  int* status = reinterpret_cast<int*>(counters + (size_t)U * d.n_iters * 2);
+  SWEM_CUDA(cudaMemsetAsync(a.workspace, 0, ws.off, st));
+  count_launch();
+  uint8_t* vblob = ws.take<uint8_t>((size_t)U * T * em2::kChunks * em2::kStageBytes);
+
+  v_blob_kernel<<<U * T * em2::kChunks, 256, 0, st>>>(a.v, vblob, d.HW, T);
+  SWEM_LAUNCH_CHECK();
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    SWEM_CUDA(cudaFuncSetAttribute(em_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)em2::kSmemBytes));
+    attr_set = true;
+  }
+  EmPairParams p{};
+  p.x = a.x; p.masks = a.masks;
+  p.kappa_prior = a.kappa_prior; p.zita_prior = a.zita_prior;
+  p.kappa = a.kappa; p.zita = a.zita; p.z_last = a.z_last;
+  p.vblob = vblob;
+  p.acc_k = acc_k; p.acc_nu = acc_nu; p.counters = counters; p.status = status;
+  p.N = d.N; p.HW = d.HW; p.T = T; p.n_iters = d.n_iters;
+  p.c1s = kLog2e / (d.tau * em2::kKScale);
+  p.prof = get_profile_buffer();
+  // all CTAs of a launch spin on each other: every launch must be co-resident (1 CTA per SM, 2-CTA clusters);
+  // units that do not fit are spread evenly over the fewest launches
+  const int upl_max = max_pairs_resident() / T > 0 ? max_pairs_resident() / T : 1;
+  const int n_launch = (U + upl_max - 1) / upl_max;
+  const int upl = (U + n_launch - 1) / n_launch;
+  for (int u0 = 0; u0 < U; u0 += upl) {
+    const int nu = (U - u0 < upl) ? (U - u0) : upl;
+    p.u0 = u0;
+    em_pair_kernel<<<nu * T * 2, 256, em2::kSmemBytes, st>>>(p);
+    SWEM_LAUNCH_CHECK();
+  }
+  return launch_nu_finalize(acc_nu, a.nu_prior, a.zita_prior, a.zita, a.nu, U * 2, st);
+}
+
+}  // namespace swem
