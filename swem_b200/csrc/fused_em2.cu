@@ -10,12 +10,16 @@
 //   * the only coupling between the sides -- the W-step's share of exp-affinity per side (:101-108) -- is
 //     one (max, sum) pair per pixel exchanged through distributed shared memory and a cluster barrier;
 //   * nu = Z^T V^T needs a single pass (its [128 bases][512 channels] accumulator is exactly the 512 TMEM
-//     columns); V is converted once per call to fp16 hi/lo operand images by `v_blob_kernel`, so this
-//     kernel streams it with plain bulk-async copies (3-stage ring, issued by one thread, prefetched from
-//     the first cycle of the kernel) instead of staging it through registers.
+//     columns); during set-up each CTA converts half of its tile's V to fp16 hi/lo operand images in global
+//     memory (L2-resident), and after the last E-step both CTAs stream all of them back with plain bulk-async
+//     copies (3-stage ring issued by one thread, first stages prefetched ~40 us ahead) -- no register staging
+//     on the critical path, and the conversion is shared by the pair;
+//   * nu is normalised in this kernel: the last M-step barrier also covers the nu reduce-adds, after it every
+//     CTA finalises a slice of value channels (no separate kernel, no third cross-tile wait).
 //
-// Cross-tile sums (M-step partials, nu partials) use the same protocol as fused_em.cu: bulk reduce-add
-// into an L2-resident accumulator, per-(unit, side, iteration) arrival counter, bounded spin.
+// Cross-tile sums go through L2-resident accumulators with a per-(unit, side, iteration) arrival counter (bounded
+// spin, co-resident grid): M-step partials as fp32 reductions straight from registers (red.global.add), the 256 KB
+// nu partial of a CTA as bulk reduce-adds from shared memory.
 #include <cuda_fp16.h>
 
 #include "common.cuh"
@@ -31,8 +35,7 @@ constexpr int kTP = 128;    // pixels per CTA
 constexpr int kCk = 64;
 constexpr int kL = 128;     // bases per side = rows owned by one CTA
 constexpr int kCv = 512;
-constexpr int kAccRow = 73; // floats per accumulator row: 64 kappa sums, 1 zita sum, pad (odd stride)
-constexpr uint32_t kAccBytes = kL * kAccRow * 4;   // 37376
+constexpr uint32_t kAccBytes = (kCk + 1) * kL * 4; // M-step accumulator of one (unit, iteration, side): [64 kappa sums + zita sum][128 l]
 constexpr float kKScale = 256.f;
 constexpr float kZScale = 16384.f;
 constexpr uint32_t kStageBytes = 32768;            // one V operand image: [256 d][32 px] fp16, hi plane then lo plane
@@ -46,7 +49,6 @@ constexpr int kChunks = 8;                         // per tile: 2 channel halves
 // KH/KL : [l 0..127][c] K-major: byte = (l%8)*16 + (l/8)*128 + (c/8)*2048 + (c%8)*2   -> SBO=128, LBO=2048
 // Z  : [l 0..127][p] MN-major A: byte = (l%8)*2 + (p%8)*16 + (l/8)*2048 + (p/8)*128   -> SBO=2048, LBO=128
 // ZL : lo half of z (aliases KH/KL: khat is dead between the logits GEMM and the finalize)
-// P  : fp32 [128][73] staging of the M-step partial / total (aliases Z)
 // VS : ring of V operand images, each [d 0..255][p 0..31] K-major: byte = (d%8)*16 + (d/8)*128 + (p/8)*4096 + (p%8)*2
 //      -> SBO=128, LBO=4096; hi plane then lo plane.  The nu drain staging (2 x 32 KB fp32) aliases the ring.
 constexpr uint32_t kOffXH = 0;
@@ -55,9 +57,8 @@ constexpr uint32_t kOffKH = kOffXL + 8 * 2048;
 constexpr uint32_t kOffKL = kOffKH + 8 * 2048;
 constexpr uint32_t kOffZ = kOffKL + 8 * 2048;
 constexpr uint32_t kOffZL = kOffKH;
-constexpr uint32_t kOffVS = kOffZ + kAccBytes;
+constexpr uint32_t kOffVS = kOffZ + 16 * 2048;
 constexpr uint32_t kOffMisc = kOffVS + kStages * kStageBytes;
-static_assert(kAccBytes % 128 == 0 && kAccBytes >= 16 * 2048, "P must cover Z");
 struct Misc {
   float inv_nx[kTP];
   float mask[kTP];
@@ -66,7 +67,6 @@ struct Misc {
   float hew[2][kTP];
   float2 mbox[2][2][kTP];   // [iteration parity][side][pixel] = (side max of the logits, side sum of W-step exps)
   uint64_t bar_mma;
-  uint64_t bar_tma;
   uint64_t bar_full[kStages];
   uint64_t bar_empty[kStages];
   uint32_t tmem_base;
@@ -83,14 +83,17 @@ constexpr uint32_t kColNu = 0;     // [128 l][512 d] nu sums (after the last M-s
 
 struct EmPairParams {
   const float* x;
+  const float* v;
   const float* masks;
   const float* kappa_prior;
+  const float* nu_prior;
   const float* zita_prior;
   float* kappa;
+  float* nu;
   float* zita;
   float* z_last;
-  const uint8_t* vblob;  // [U][T][8][32 KB] operand images written by v_blob_kernel
-  float* acc_k;          // [U][n_iters][2][128][73], zeroed before launch
+  uint8_t* vblob;        // [U][T][8][32 KB] scratch: operand images of V (written in set-up, read after the last E-step)
+  float* acc_k;          // [U][n_iters][2][65][128], zeroed before launch
   float* acc_nu;         // [U][2][512][128], zeroed before launch
   unsigned* counters;    // [U][n_iters][2], zeroed before launch
   int* status;
@@ -121,41 +124,50 @@ __device__ __forceinline__ void st_cluster_f2(uint32_t addr, float a, float b) {
   } while (0)
 
 // ------------------------------------------------------------------------------------------------------
-// V -> fp16 hi/lo operand images.  Block = (unit, tile, chunk = channel half h * 4 + pixel quarter q):
-// [256 d][32 px] fp32 in, 32 KB image out (pixels past HW are zero).
+// V -> fp16 hi/lo operand images, done by the whole CTA for the 4 chunks (pixel quarters) of channel half h:
+// each chunk is [256 d][32 px] fp32 in, a 32 KB image out (pixels past HW are zero).
 // ------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) v_blob_kernel(const float* __restrict__ v, uint8_t* __restrict__ blob, int HW, int T) {
+__device__ __forceinline__ void convert_v_half(const float* __restrict__ vsrc /* [256][HW] rows of this half */,
+                                               uint8_t* __restrict__ images /* 4 x 32 KB */, int p0, int HW, int warp, int lane) {
   using namespace em2;
-  const int chunk = blockIdx.x % kChunks;
-  const int tile = (blockIdx.x / kChunks) % T;
-  const int u = blockIdx.x / (kChunks * T);
-  const int h = chunk >> 2, q = chunk & 3;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane & 3;                               // group of 8 pixels
-  const int px0 = tile * kTP + q * 32 + g * 8;
-  const bool vec_ok = ((HW & 3) == 0) && (px0 + 7 < HW);
-  uint8_t* out = blob + (size_t)blockIdx.x * kStageBytes;
+  const bool aligned = (HW & 3) == 0;
+  auto load = [&](int q, float (&f)[4][8]) {
+    const int px0 = p0 + q * 32 + g * 8;
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int d = warp * 32 + j * 8 + (lane >> 2);      // 0..255
-    const float* src = v + ((size_t)u * kCv + h * 256 + d) * HW + px0;
-    float f[8];
-    if (vec_ok) {
-      const float4 a = __ldg(reinterpret_cast<const float4*>(src));
-      const float4 b = __ldg(reinterpret_cast<const float4*>(src) + 1);
-      f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
-    } else {
+    for (int j = 0; j < 4; ++j) {
+      const int d = warp * 32 + j * 8 + (lane >> 2);    // 0..255
+      const float* src = vsrc + (size_t)d * HW + px0;
+      if (aligned && px0 + 7 < HW) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(src));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(src) + 1);
+        f[j][0] = a.x; f[j][1] = a.y; f[j][2] = a.z; f[j][3] = a.w; f[j][4] = b.x; f[j][5] = b.y; f[j][6] = b.z; f[j][7] = b.w;
+      } else {
 #pragma unroll
-      for (int e = 0; e < 8; ++e) f[e] = (px0 + e < HW) ? __ldg(src + e) : 0.f;
+        for (int e = 0; e < 8; ++e) f[j][e] = (px0 + e < HW) ? __ldg(src + e) : 0.f;
+      }
     }
-    __align__(16) __half hi[8];
-    __align__(16) __half lo[8];
+  };
+  auto store = [&](int q, const float (&f)[4][8]) {
+    uint8_t* out = images + (size_t)q * kStageBytes;
 #pragma unroll
-    for (int e = 0; e < 8; ++e) split_half(f[e], hi[e], lo[e]);
-    const uint32_t off = (d % 8) * 16 + (d / 8) * 128 + g * 4096;
-    *reinterpret_cast<uint4*>(out + off) = *reinterpret_cast<uint4*>(hi);
-    *reinterpret_cast<uint4*>(out + kVPlane + off) = *reinterpret_cast<uint4*>(lo);
-  }
+    for (int j = 0; j < 4; ++j) {
+      const int d = warp * 32 + j * 8 + (lane >> 2);
+      __align__(16) __half hi[8];
+      __align__(16) __half lo[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) split_half(f[j][e], hi[e], lo[e]);
+      const uint32_t off = (d % 8) * 16 + (d / 8) * 128 + g * 4096;
+      *reinterpret_cast<uint4*>(out + off) = *reinterpret_cast<uint4*>(hi);
+      *reinterpret_cast<uint4*>(out + kVPlane + off) = *reinterpret_cast<uint4*>(lo);
+    }
+  };
+  // all 32 loads of a thread (128 KB per CTA) are in flight before the first conversion: one memory round trip
+  float buf[4][4][8];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) load(q, buf[q]);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) store(q, buf[q]);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -180,20 +192,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) em_pair_kern
   if (warp == 0) tmem_alloc(&ms.tmem_base, 512);
   if (tid == 0) {
     mbar_init(&ms.bar_mma, 1);
-    mbar_init(&ms.bar_tma, 1);
     for (int i = 0; i < kStages; ++i) {
       mbar_init(&ms.bar_full[i], 1);
       mbar_init(&ms.bar_empty[i], 1);
     }
     ms.abort_flag = 0;
     fence_mbar_init();
-    // V operand images of this tile: the first kStages chunks start flying now, they are consumed after the last E-step
-    const uint8_t* src = p.vblob + ((size_t)u * p.T + tile) * kChunks * kStageBytes;
-    for (int k = 0; k < kStages; ++k) {
-      mbar_expect_tx(&ms.bar_full[k], kStageBytes);
-      bulk_g2s(smem + kOffVS + k * kStageBytes, src + (size_t)k * kStageBytes, kStageBytes, &ms.bar_full[k]);
-    }
   }
+  // V operand images: this CTA converts channel half `sd` of the tile (the peer converts the other half); both read
+  // all 8 images back through the bulk-copy ring after the last E-step.
+  uint8_t* const vimg = p.vblob + ((size_t)u * p.T + tile) * kChunks * kStageBytes;
+  convert_v_half(p.v + ((size_t)u * kCv + sd * 256) * HW, vimg + (size_t)sd * 4 * kStageBytes, p0, HW, warp, lane);
+  __threadfence();
+  asm volatile("fence.proxy.async;" ::: "memory");     // generic-proxy global stores -> visible to the bulk-copy (async proxy) reads
   // rows: thread tid < 128 <-> basis l = tid of side sd (finalize steps)
   const bool row_thread = tid < kL;
   const int gs = u * 2 + sd;                            // (b, n, s) index
@@ -265,11 +276,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) em_pair_kern
   }
   if (row_thread) stage_khat(kap0);
   tc_fence_before_sync();
-  cluster_arrive();                   // both CTAs of the pair are running before any remote shared-memory store
-  cluster_wait();
+  cluster_arrive();                   // both CTAs of the pair are running before any remote shared-memory store,
+  cluster_wait();                     // and both halves of the tile's V images are written
   tc_fence_after_sync();
+  if (tid == 0) {                     // the first kStages images start flying now; they are consumed after the last E-step
+    asm volatile("fence.proxy.async;" ::: "memory");
+    for (int k = 0; k < kStages; ++k) {
+      mbar_expect_tx(&ms.bar_full[k], kStageBytes);
+      bulk_g2s(smem + kOffVS + k * kStageBytes, vimg + (size_t)k * kStageBytes, kStageBytes, &ms.bar_full[k]);
+    }
+  }
   const uint32_t tmem = ms.tmem_base;
-  uint32_t ph_mma = 0, ph_tma = 0;
+  uint32_t ph_mma = 0;
   bool failed = false;
   EM2_STAMP();                        // setup done
 
@@ -432,7 +450,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) em_pair_kern
       tc_fence_after_sync();
       if (warp == 0) {
         if (lane == 0) {
-          const uint8_t* src = p.vblob + ((size_t)u * p.T + tile) * kChunks * kStageBytes;
+          const uint8_t* src = vimg;
 #pragma unroll 1
           for (int seq = 0; seq < kChunks; ++seq) {
             const int st = seq % kStages;
@@ -494,7 +512,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) em_pair_kern
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
         }
-        if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        // full completion (not just .read): the arrival on this iteration's counter below also publishes the nu sums
+        if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
       }
       tc_fence_before_sync();
       __syncthreads();
@@ -502,62 +521,47 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) em_pair_kern
       EM2_STAMP();                    // nu drained
     }
 
-    // ---- (4) cross-tile reduction of the M-step partial ---------------------------------------------------
-    __syncthreads();                  // Z is dead now: P may alias it
-    if (row_thread) {
-      float* P = reinterpret_cast<float*>(smem + kOffZ);
-#pragma unroll
-      for (int c = 0; c <= kCk; ++c) P[tid * kAccRow + c] = part[c];
-#pragma unroll
-      for (int c = kCk + 1; c < kAccRow; ++c) P[tid * kAccRow + c] = 0.f;
-    }
-    fence_proxy_async_smem();
-    __syncthreads();
-    float* acc = p.acc_k + ((size_t)(u * I + it) * 2 + sd) * (kL * kAccRow);
+    // ---- (4) cross-tile reduction of the M-step partial: fire-and-forget fp32 reductions straight from registers into
+    // the L2-resident accumulator [c][l] (coalesced over l), fence, arrive; after the last tile arrived every CTA
+    // reads the total back the same way.
+    float* acc = p.acc_k + ((size_t)(u * I + it) * 2 + sd) * ((kCk + 1) * kL);
     unsigned* counter = p.counters + ((size_t)u * I + it) * 2 + sd;
     float kpr[kCk];                   // prior row: loads fly during the cross-tile wait
     if (row_thread) {
 #pragma unroll
+      for (int c = 0; c <= kCk; ++c) atomicAdd(acc + c * kL + tid, part[c]);
+#pragma unroll
       for (int c = 0; c < kCk; ++c) kpr[c] = __ldg(kprior + (size_t)c * kL);
+      __threadfence();
     }
-    if (warp == 0) {
-      if (lane == 0) {
-        asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(acc),
-                     "r"(sbase + kOffZ), "r"(kAccBytes)
-                     : "memory");
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-        EM2_STAMP();                  // partial reduce-added
-        __threadfence();
-        atomicAdd(counter, 1u);
-        const bool arrived = wait_counter(counter, (unsigned)p.T);
-        EM2_STAMP();                  // all tiles arrived
-        if (!arrived) ms.abort_flag = 1;
-        __threadfence();
-        asm volatile("fence.proxy.async;" ::: "memory");
-        mbar_expect_tx(&ms.bar_tma, kAccBytes);
-        bulk_g2s(smem + kOffZ, acc, kAccBytes, &ms.bar_tma);
-      }
-      __syncwarp();
+    __syncthreads();
+    if (tid == 0) {
+      EM2_STAMP();                    // partial reduce-added
+      atomicAdd(counter, 1u);
+      const bool arrived = wait_counter(counter, (unsigned)p.T);
+      EM2_STAMP();                    // all tiles arrived
+      if (!arrived) ms.abort_flag = 1;
+      __threadfence();
     }
-    SWEM_CTA_WAIT(&ms.bar_tma, ph_tma, ms.abort_flag);
-    ph_tma ^= 1;
+    __syncthreads();
     if (ms.abort_flag) {
       if (tid == 0) atomicExch(p.status, 1 + it);
       failed = true;
       break;
     }
-    EM2_STAMP();                      // total loaded
     // ---- (5) finalize row l = tid from the prior (reference :125-126) ---------------------------------------
     if (row_thread) {
-      const float* P = reinterpret_cast<const float*>(smem + kOffZ) + tid * kAccRow;
       constexpr float kInvZ = 1.f / kZScale;
-      const float zita_cur = zita_p + P[kCk] * kInvZ;
-      const float rz = 1.f / zita_cur;
       float kap[kCk];
 #pragma unroll
-      for (int c = 0; c < kCk; ++c) kap[c] = (zita_p * kpr[c] + P[c] * kInvZ) * rz;
+      for (int c = 0; c < kCk; ++c) kap[c] = __ldcg(acc + c * kL + tid);
+      const float zita_cur = zita_p + __ldcg(acc + kCk * kL + tid) * kInvZ;
+      const float rz = 1.f / zita_cur;
+#pragma unroll
+      for (int c = 0; c < kCk; ++c) kap[c] = (zita_p * kpr[c] + kap[c] * kInvZ) * rz;
       if (last) {
+        ms.hsum[0][tid] = rz;         // (dead E-step scratch) 1 / zita and the prior zita of row l, for the nu slice below
+        ms.hsum[1][tid] = zita_p;
         if (tile == 0) {
           p.zita[(size_t)gs * kL + tid] = zita_cur;
           float* kout = p.kappa + ((size_t)gs * kCk) * kL + tid;
@@ -570,6 +574,28 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) em_pair_kern
     }
     __syncthreads();
     EM2_STAMP();                      // finalize done
+    if (last) {
+      // ---- nu = (zita_ nu_ + sum / 2^14) / zita (reference :164-165) for this tile's slice of value channels: the counter
+      // wait above ordered every tile's nu reduce-adds (completed before its arrival) before these loads.
+      const int dper = (kCv + p.T - 1) / p.T;
+      const int d0 = tile * dper, d1 = min(kCv, d0 + dper);
+      constexpr float kInvZ = 1.f / kZScale;
+      const float4* acc4 = reinterpret_cast<const float4*>(p.acc_nu + (size_t)gs * kCv * kL);
+      const float4* pri4 = reinterpret_cast<const float4*>(p.nu_prior + (size_t)gs * kCv * kL);
+      float4* out4 = reinterpret_cast<float4*>(p.nu + (size_t)gs * kCv * kL);
+      for (int i = d0 * (kL / 4) + tid; i < d1 * (kL / 4); i += 256) {
+        const int l = (i % (kL / 4)) * 4;
+        const float4 a = __ldcg(acc4 + i);
+        const float4 pr = __ldg(pri4 + i);
+        float4 o;
+        o.x = (ms.hsum[1][l + 0] * pr.x + a.x * kInvZ) * ms.hsum[0][l + 0];
+        o.y = (ms.hsum[1][l + 1] * pr.y + a.y * kInvZ) * ms.hsum[0][l + 1];
+        o.z = (ms.hsum[1][l + 2] * pr.z + a.z * kInvZ) * ms.hsum[0][l + 2];
+        o.w = (ms.hsum[1][l + 3] * pr.w + a.w * kInvZ) * ms.hsum[0][l + 3];
+        out4[i] = o;
+      }
+      EM2_STAMP();                    // nu slice written
+    }
   }
 
   tc_fence_before_sync();
@@ -633,7 +659,7 @@ int fused_em2_forward(const SwemEmArgs& a, cudaStream_t st) {
   const int U = d.B * d.N;
   const int T = (d.HW + em2::kTP - 1) / em2::kTP;
   Arena ws(a.workspace);
-  float* acc_k = ws.take<float>((size_t)U * d.n_iters * 2 * em2::kL * em2::kAccRow);
+  float* acc_k = ws.take<float>((size_t)U * d.n_iters * 2 * (em2::kAccBytes / 4));
   float* acc_nu = ws.take<float>((size_t)U * 2 * em2::kCv * em2::kL);
   unsigned* counters = ws.take<unsigned>((size_t)U * d.n_iters * 2 + 1);
   int* status = reinterpret_cast<int*>(counters + (size_t)U * d.n_iters * 2);
@@ -641,18 +667,15 @@ int fused_em2_forward(const SwemEmArgs& a, cudaStream_t st) {
   count_launch();
   uint8_t* vblob = ws.take<uint8_t>((size_t)U * T * em2::kChunks * em2::kStageBytes);
 
-  v_blob_kernel<<<U * T * em2::kChunks, 256, 0, st>>>(a.v, vblob, d.HW, T);
-  SWEM_LAUNCH_CHECK();
-
   static bool attr_set = false;
   if (!attr_set) {
     SWEM_CUDA(cudaFuncSetAttribute(em_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)em2::kSmemBytes));
     attr_set = true;
   }
   EmPairParams p{};
-  p.x = a.x; p.masks = a.masks;
-  p.kappa_prior = a.kappa_prior; p.zita_prior = a.zita_prior;
-  p.kappa = a.kappa; p.zita = a.zita; p.z_last = a.z_last;
+  p.x = a.x; p.v = a.v; p.masks = a.masks;
+  p.kappa_prior = a.kappa_prior; p.nu_prior = a.nu_prior; p.zita_prior = a.zita_prior;
+  p.kappa = a.kappa; p.nu = a.nu; p.zita = a.zita; p.z_last = a.z_last;
   p.vblob = vblob;
   p.acc_k = acc_k; p.acc_nu = acc_nu; p.counters = counters; p.status = status;
   p.N = d.N; p.HW = d.HW; p.T = T; p.n_iters = d.n_iters;
@@ -669,7 +692,7 @@ int fused_em2_forward(const SwemEmArgs& a, cudaStream_t st) {
     em_pair_kernel<<<nu * T * 2, 256, em2::kSmemBytes, st>>>(p);
     SWEM_LAUNCH_CHECK();
   }
-  return launch_nu_finalize(acc_nu, a.nu_prior, a.zita_prior, a.zita, a.nu, U * 2, st);
+  return SWEM_OK;
 }
 
 }  // namespace swem

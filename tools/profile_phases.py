@@ -32,7 +32,10 @@ def main(N=5, H=30, W=54, I=4, reps=50):
             if it == I - 1:
                 names += (['nu pass0 GEMM', 'nu pass0 drain', 'nu pass1 GEMM', 'nu pass1 drain'] if os.environ.get('SWEM_EM_KERNEL') == 'v1'
                           else ['nu GEMM', 'nu drain'])
-            names += [f'it{it} reduce-add', f'it{it} wait tiles', f'it{it} load total', f'it{it} finalize']
+            names += ([f'it{it} reduce-add', f'it{it} wait tiles', f'it{it} load total', f'it{it} finalize'] if os.environ.get('SWEM_EM_KERNEL') == 'v1'
+                      else [f'it{it} reduce-add', f'it{it} wait tiles', f'it{it} finalize'])
+        if os.environ.get('SWEM_EM_KERNEL') != 'v1':
+            names += ['nu slice']
         names += ['exit']
         for k in range(1, n):
             print(f'  {names[k-1] if k-1 < len(names) else "?":24s} {(t[k]-t[k-1])/1e3:8.2f} us')
