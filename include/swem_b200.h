@@ -90,6 +90,27 @@ typedef struct SwemEmArgs {
 size_t swem_em_workspace_bytes(const SwemDims* dims, int32_t path);
 int    swem_em_forward(const SwemEmArgs* args, void* stream);
 
+/* ---- backward of the EM update (training; BASELINE configs[4]).  In the reference only the last line of swem,
+ * nu = (zita_ * nu_ + v z) / zita (modules.py:164-165), is differentiable -- E / M / W steps run under
+ * @torch.no_grad() (:93,:112,:122) -- so with z = z_last saved by swem_em_forward:
+ *     grad_v[b,n,d,p]        = sum_{s,l} grad_nu[b,n,s,d,l] / zita[b,n,s,l] * z[b,n,s,p,l]
+ *     grad_nu_prior[b,n,s,d,l] = grad_nu[b,n,s,d,l] * zita_prior[b,n,s,l] / zita[b,n,s,l]
+ * Uses dims B, N, Cv, HW, L (Ck / n_iters / tau are ignored).                                         */
+typedef struct SwemEmBwdArgs {
+  SwemDims dims;
+  const float* z_last;        /* [B, N, 2, HW, L]  saved by the forward                              */
+  const float* zita_prior;    /* [B, N, 2, L]                                                        */
+  const float* zita;          /* [B, N, 2, L]      output of the forward                             */
+  const float* grad_nu;       /* [B, N, 2, Cv, L]  incoming gradient                                 */
+  float* grad_v;              /* out [B, N, Cv, HW]           (NULL = skip)                          */
+  float* grad_nu_prior;       /* out [B, N, 2, Cv, L]         (NULL = skip)                          */
+  void*  workspace;           /* >= swem_em_backward_workspace_bytes(&dims)                          */
+  size_t workspace_bytes;
+} SwemEmBwdArgs;
+
+size_t swem_em_backward_workspace_bytes(const SwemDims* dims);
+int    swem_em_backward(const SwemEmBwdArgs* args, void* stream);
+
 /* ---- readout: reference SWEMCore.matching -> get_affinity -> perm_inv_feat, modules.py:198-293 */
 typedef struct SwemReadArgs {
   SwemDims dims;

@@ -18,6 +18,7 @@ EXPORTS = (
     'swem_em_workspace_bytes', 'swem_em_forward', 'swem_em_fused_supported',
     'swem_readout_workspace_bytes', 'swem_readout_forward', 'swem_readout_fused_supported',
     'swem_em_masks', 'swem_decode_tail', 'swem_set_profile_buffer',
+    'swem_em_backward_workspace_bytes', 'swem_em_backward',
 )
 
 
@@ -35,6 +36,13 @@ class SwemEmArgs(C.Structure):
                 ('z_last', C.c_void_p),
                 ('workspace', C.c_void_p), ('workspace_bytes', C.c_size_t),
                 ('path', C.c_int32)]
+
+
+class SwemEmBwdArgs(C.Structure):
+    _fields_ = [('dims', SwemDims),
+                ('z_last', C.c_void_p), ('zita_prior', C.c_void_p), ('zita', C.c_void_p), ('grad_nu', C.c_void_p),
+                ('grad_v', C.c_void_p), ('grad_nu_prior', C.c_void_p),
+                ('workspace', C.c_void_p), ('workspace_bytes', C.c_size_t)]
 
 
 class SwemReadArgs(C.Structure):
@@ -68,6 +76,9 @@ def load() -> C.CDLL:
     lib.swem_em_workspace_bytes.restype = C.c_size_t
     lib.swem_em_forward.argtypes = [C.POINTER(SwemEmArgs), C.c_void_p]
     lib.swem_em_fused_supported.argtypes = [C.POINTER(SwemDims)]
+    lib.swem_em_backward_workspace_bytes.argtypes = [C.POINTER(SwemDims)]
+    lib.swem_em_backward_workspace_bytes.restype = C.c_size_t
+    lib.swem_em_backward.argtypes = [C.POINTER(SwemEmBwdArgs), C.c_void_p]
     lib.swem_readout_workspace_bytes.argtypes = [C.POINTER(SwemDims), C.c_int32]
     lib.swem_readout_workspace_bytes.restype = C.c_size_t
     lib.swem_readout_forward.argtypes = [C.POINTER(SwemReadArgs), C.c_void_p]

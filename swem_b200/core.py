@@ -6,6 +6,8 @@ Same constructor, attributes and methods (``empty`` / ``memorize`` / ``matching`
 state-dict keys), but the E / M / W steps, the nu update and the readout attention run in the
 CUDA kernels of ``libswem_b200.so`` through its C ABI (``include/swem_b200.h``).
 
+Training: ``swem_b200/autograd.py`` (nu is differentiable in v and the prior nu; the readout in qk and nu).
+
 What stays torch, as in the reference: the RNG draw for new bases (``random_init`` uses the
 global generator of the key's device, modules.py:170-178, so seeding behaves identically), the
 bank bookkeeping (modules.py:29-60,183-193) and the GLU fusion conv (modules.py:13-26).
@@ -81,10 +83,8 @@ def _f32c(t: torch.Tensor, name: str) -> torch.Tensor:
     return t.contiguous()
 
 
-def _no_grad_inputs(*tensors):
-    if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors):
-        raise NotImplementedError('swem_b200: backward through the fused EM/readout kernels is not '
-                                  'implemented yet; call under torch.no_grad()')
+def _wants_grad(*tensors) -> bool:
+    return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors)
 
 
 def _invoke(name, call):
@@ -132,8 +132,10 @@ class SWEMCore(nn.Module):
 
     # -- memorize --------------------------------------------------------------------------
     def swem(self, x, v, masks, bases_: Optional[Bases] = None, return_z: bool = False) -> Bases:
-        """x (B,Ck,H,W) raw key, v (B,N,Cv,H,W), masks (B,N,2,H,W) -> bases dict (one fused EM update)."""
-        _no_grad_inputs(x, v, masks)
+        """x (B,Ck,H,W) raw key, v (B,N,Cv,H,W), masks (B,N,2,H,W) -> bases dict (one fused EM update).
+
+        Gradients (training): nu is differentiable in ``v`` and in the prior ``nu`` (reference :164-165); kappa and
+        zita are constants, like under the reference's ``@torch.no_grad()`` steps."""
         B, Ck, H, W = x.shape
         N = masks.shape[1]
         L = self.n_bases
@@ -146,9 +148,23 @@ class SWEMCore(nn.Module):
             k2, n2, z2 = self.random_init((B, n_new, 2, Ck, L), dtype=x.type(), device=x.device)
             kappa_, nu_, zita_ = torch.cat([kappa_, k2], 1), torch.cat([nu_, n2], 1), torch.cat([zita_, z2], 1)
 
-        x, v, masks = _f32c(x, 'x'), _f32c(v, 'v'), _f32c(masks, 'masks')
-        kappa_, nu_, zita_ = _f32c(kappa_, 'kappa'), _f32c(nu_, 'nu'), _f32c(zita_, 'zita')
-        Cv = v.shape[2]
+        x, masks = _f32c(x.detach(), 'x'), _f32c(masks.detach(), 'masks')
+        kappa_, zita_ = _f32c(kappa_.detach(), 'kappa'), _f32c(zita_.detach(), 'zita')
+        v, nu_ = _f32c(v, 'v'), _f32c(nu_, 'nu')
+        if _wants_grad(v, nu_):
+            from .autograd import EMFunction
+            kappa, nu, zita = EMFunction.apply(self, x, v, masks, kappa_, nu_, zita_)
+            return {'kappa': kappa, 'nu': nu, 'zita': zita}
+        kappa, nu, zita, z = self._em_launch(x, v.detach(), masks, kappa_, nu_.detach(), zita_, return_z)
+        bases = {'kappa': kappa, 'nu': nu, 'zita': zita}
+        if return_z:
+            bases['z'] = z
+        return bases
+
+    def _em_launch(self, x, v, masks, kappa_, nu_, zita_, return_z: bool):
+        """One ``swem_em_forward`` call on contiguous fp32 CUDA tensors -> (kappa, nu, zita, z_last | None)."""
+        B, Ck, H, W = x.shape
+        N, L, Cv = masks.shape[1], self.n_bases, v.shape[2]
         if v.shape[:2] != (B, N) or v.shape[-2:] != (H, W) or kappa_.shape != (B, N, 2, Ck, L) \
                 or nu_.shape != (B, N, 2, Cv, L) or masks.shape != (B, N, 2, H, W):
             raise RuntimeError(f'swem: inconsistent shapes x{tuple(x.shape)} v{tuple(v.shape)} '
@@ -173,10 +189,7 @@ class SWEMCore(nn.Module):
             rc = _invoke('em', lambda: lib.swem_em_forward(C.byref(args), stream))
         _lib.check(rc, 'swem_em_forward')
         self.launches = lib.swem_last_launch_count()
-        bases = {'kappa': kappa, 'nu': nu, 'zita': zita}
-        if return_z:
-            bases['z'] = z_last
-        return bases
+        return kappa, nu, zita, z_last
 
     def memorize(self, qk, qv, masks):
         prior = self.memories['update'].bases
@@ -198,47 +211,58 @@ class SWEMCore(nn.Module):
     def matching_features(self, qk, qv) -> Tuple[torch.Tensor, int]:
         """-> the concat buffer [mem_out | qv | S] (B*N, 2*Cv + 2*topl, H, W) and N."""
         N, Cv = self._readout_objects()
-        _no_grad_inputs(qv)
-        qv = _f32c(qv, 'qv')
+        banks = self._banks()
         B, _, H, W = qk.shape
+        if _wants_grad(qk, qv, *[b['nu'] for b in banks]):       # training: kernels forward, autograd-visible concat
+            from .autograd import ReadoutFunction
+            qk = _f32c(qk, 'qk')
+            ms = ReadoutFunction.apply(self, qk, len(banks), *[_f32c(b['kappa'].detach(), 'kappa') for b in banks],
+                                       *[_f32c(b['nu'], 'nu') for b in banks])
+            qv = qv.unsqueeze(1).expand(-1, N, -1, -1, -1).flatten(end_dim=1)
+            return torch.cat([ms[:, :Cv], qv, ms[:, Cv:]], dim=1), N
+        qv = _f32c(qv, 'qv')
         chans = 2 * Cv + 2 * self.topl
         feats = torch.empty(B * N, chans, H, W, device=qk.device, dtype=torch.float32)
         feats.view(B, N, chans, H, W)[:, :, Cv:2 * Cv] = qv.unsqueeze(1)
         return self.readout_into(qk, feats, 0, 2 * Cv), N
 
+    def _banks(self):
+        return [m.bases for m in self.memories.values() if m.bases is not None]
+
     def _readout_objects(self) -> Tuple[int, int]:
-        banks = [m.bases for m in self.memories.values() if m.bases is not None]
+        banks = self._banks()
         if not banks:
             raise RuntimeError('matching() before any memorize(): memory is empty')
         return banks[0]['nu'].shape[1], banks[0]['nu'].shape[3]
 
     def readout_into(self, qk, feats, mem_channel: int, s_channel: int) -> torch.Tensor:
-        """Readout kernels only: write ``mem_out`` into channels [mem_channel, +Cv) and ``S`` into channels
-        [s_channel, +2*topl) of the caller's contiguous fp32 buffer ``feats`` (B*N, C, H, W).  The reference
+        """Readout kernels only (no autograd): write ``mem_out`` into channels [mem_channel, +Cv) and ``S`` into
+        channels [s_channel, +2*topl) of the caller's contiguous fp32 buffer ``feats`` (B*N, C, H, W).  The reference
         layout is ``matching_features``; inference engines that split the fusion conv use a narrower buffer."""
-        if self.training and self.p_drop > 0:
-            raise NotImplementedError('swem_b200: memory dropout (p_drop > 0) is not implemented')
-        banks = [m.bases for m in self.memories.values() if m.bases is not None]
+        banks = self._banks()
         if not banks:
             raise RuntimeError('matching() before any memorize(): memory is empty')
-        _no_grad_inputs(qk, *[b['nu'] for b in banks])
-        qk = _f32c(qk, 'qk')
+        return self._readout_launch(_f32c(qk.detach(), 'qk'), [_f32c(b['kappa'].detach(), 'kappa') for b in banks],
+                                    [_f32c(b['nu'].detach(), 'nu') for b in banks], feats, mem_channel, s_channel)
+
+    def _readout_launch(self, qk, kap, nus, feats, mem_channel: int, s_channel: int) -> torch.Tensor:
+        """One ``swem_readout_forward`` call on contiguous fp32 CUDA tensors (kap / nus: one entry per bank)."""
+        if self.training and self.p_drop > 0:
+            raise NotImplementedError('swem_b200: memory dropout (p_drop > 0) is not implemented')
         B, Ck, H, W = qk.shape
-        _, N, _, Cv, L = banks[0]['nu'].shape
+        _, N, _, Cv, L = nus[0].shape
         dev = qk.device
         chans = feats.shape[1]
         if (not feats.is_cuda or feats.dtype != torch.float32 or not feats.is_contiguous()
                 or feats.shape != (B * N, chans, H, W) or mem_channel < 0 or mem_channel + Cv > chans
                 or s_channel < 0 or s_channel + 2 * self.topl > chans):
-            raise RuntimeError(f'readout_into: bad output buffer {tuple(feats.shape)} {feats.dtype} for B*N={B * N}, '
+            raise RuntimeError(f'readout: bad output buffer {tuple(feats.shape)} {feats.dtype} for B*N={B * N}, '
                                f'mem_channel={mem_channel}, s_channel={s_channel}')
 
         lib = _lib.load()
-        dims = _lib.SwemDims(B, N, Ck, Cv, H * W, L, 0, len(banks), self.topl, self.tau)
+        dims = _lib.SwemDims(B, N, Ck, Cv, H * W, L, 0, len(nus), self.topl, self.tau)
         need = lib.swem_readout_workspace_bytes(C.byref(dims), self.readout_path)
         ws = _WORKSPACE.get(dev, need)
-        kap = [_f32c(b['kappa'], 'kappa') for b in banks]
-        nus = [_f32c(b['nu'], 'nu') for b in banks]
         args = _lib.SwemReadArgs(dims, qk.data_ptr(),
                                  (C.c_void_p * 2)(*[k.data_ptr() for k in kap] + [None] * (2 - len(kap))),
                                  (C.c_void_p * 2)(*[n.data_ptr() for n in nus] + [None] * (2 - len(nus))),

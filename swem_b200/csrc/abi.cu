@@ -180,6 +180,27 @@ int swem_em_forward(const SwemEmArgs* a, void* stream) {
   return use_fused_em(a->dims, a->path) ? fused_em_forward(*a, st) : generic_em_forward(*a, st);
 }
 
+size_t swem_em_backward_workspace_bytes(const SwemDims* d) {
+  if (!d || d->B <= 0 || d->N <= 0 || d->Cv <= 0 || d->HW <= 0 || d->L <= 0) return 0;
+  return generic_em_backward_workspace(*d);
+}
+
+int swem_em_backward(const SwemEmBwdArgs* a, void* stream) {
+  reset_launch_count();
+  SWEM_CHECK_ARG(a != nullptr, "args is NULL");
+  const SwemDims& d = a->dims;
+  SWEM_CHECK_ARG(d.B > 0 && d.N > 0 && d.Cv > 0 && d.HW > 0 && d.L > 0,
+                 "non-positive dimension (B=%d N=%d Cv=%d HW=%d L=%d)", d.B, d.N, d.Cv, d.HW, d.L);
+  SWEM_CHECK_ARG(a->z_last && a->zita_prior && a->zita && a->grad_nu, "a required input pointer is NULL");
+  SWEM_CHECK_ARG(a->grad_v || a->grad_nu_prior, "both output pointers are NULL");
+  const size_t need = swem_em_backward_workspace_bytes(&d);
+  if (!a->workspace || a->workspace_bytes < need || (reinterpret_cast<uintptr_t>(a->workspace) & 255)) {
+    set_error("EM backward workspace: need %zu bytes 256-aligned, got %zu at %p", need, a->workspace_bytes, a->workspace);
+    return SWEM_ERR_WORKSPACE;
+  }
+  return generic_em_backward(*a, static_cast<cudaStream_t>(stream));
+}
+
 size_t swem_readout_workspace_bytes(const SwemDims* d, int32_t path) {
   if (!d || check_dims(*d, false)) return 0;
   if (path == SWEM_PATH_FUSED && !fused_readout_supported(*d)) return 0;

@@ -492,6 +492,52 @@ int generic_em_forward(const SwemEmArgs& a, cudaStream_t st) {
 }
 
 // ------------------------------------------------------------------------------------------
+// memorize, backward (reference: autograd through modules.py:164-165, the only differentiable line of swem)
+// ------------------------------------------------------------------------------------------
+// w[g][d][l] = grad_nu[g][d][l] / zita[g][l] ;  grad_nu_prior[g][d][l] = w * zita_prior[g][l]
+__global__ void nu_grad_scale_kernel(const float* __restrict__ gnu, const float* __restrict__ zita_prior,
+                                     const float* __restrict__ zita, float* __restrict__ w, float* __restrict__ gprior,
+                                     int G, int R, int L) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)G * R * L) return;
+  const int l = (int)(i % L);
+  const int g = (int)(i / ((long long)R * L));
+  const float t = gnu[i] / zita[g * L + l];
+  w[i] = t;
+  if (gprior != nullptr) gprior[i] = t * zita_prior[g * L + l];
+}
+
+size_t generic_em_backward_workspace(const SwemDims& d) {
+  return align_up((size_t)d.B * d.N * 2 * d.Cv * d.L * 4, 256) + 256;
+}
+
+int generic_em_backward(const SwemEmBwdArgs& a, cudaStream_t st) {
+  const SwemDims& d = a.dims;
+  const int G = d.B * d.N * 2;
+  Arena ws(a.workspace);
+  float* w = ws.take<float>((size_t)G * d.Cv * d.L);
+  {
+    const long long n = (long long)G * d.Cv * d.L;
+    nu_grad_scale_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a.grad_nu, a.zita_prior, a.zita, w, a.grad_nu_prior,
+                                                                      G, d.Cv, d.L);
+    SWEM_LAUNCH_CHECK();
+  }
+  if (a.grad_v == nullptr) return SWEM_OK;
+  for (int s = 0; s < 2; ++s) {   // grad_v[b,n][dch][p] (+)= sum_l w[b,n,s][dch][l] z[b,n,s][p][l]
+    GemmShape g{};
+    g.M = d.Cv; g.N = d.HW; g.K = d.L;
+    g.sAm = d.L; g.sAk = 1; g.sBk = 1; g.sBn = d.L; g.sCm = d.HW; g.sCn = 1;
+    g.n0 = d.B; g.n1 = d.N; g.n2 = 1;
+    g.bA[0] = (long long)d.N * 2 * d.Cv * d.L; g.bA[1] = 2LL * d.Cv * d.L; g.bA[2] = 0;
+    g.bB[0] = (long long)d.N * 2 * d.HW * d.L; g.bB[1] = 2LL * d.HW * d.L; g.bB[2] = 0;
+    g.bC[0] = (long long)d.N * d.Cv * d.HW; g.bC[1] = (long long)d.Cv * d.HW; g.bC[2] = 0;
+    g.accumulate = s;
+    if (int rc = launch_gemm(w + (size_t)s * d.Cv * d.L, a.z_last + (size_t)s * d.HW * d.L, a.grad_v, g, st)) return rc;
+  }
+  return SWEM_OK;
+}
+
+// ------------------------------------------------------------------------------------------
 // readout
 // ------------------------------------------------------------------------------------------
 size_t generic_readout_workspace(const SwemDims& d) {

@@ -1,0 +1,145 @@
+"""Gradients through the memory (training path, BASELINE configs[4]) against the CPU oracle's autograd in fp64.
+
+Reference contract: memorize -> gradient to v and to the prior nu only; matching -> gradient
+to the raw query key, the nu of both banks, and (through torch) qv.  Tolerance: max-rel 1e-3 on every gradient."""
+import pytest
+import torch
+
+from oracle import swem_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+from test_gpu_parity import _core, _skip_unless_covered, _to, check, maxrel      # noqa: E402
+
+SHAPES = {   # B, N, Ck, Cv, L, H, W, topl
+    'small': (2, 2, 16, 24, 8, 5, 7, 4),
+    'train': (2, 2, 64, 512, 128, 24, 24, 64),       # HW = 576: the reference's 384x384 training crops
+}
+
+
+def _problem(shape, seed=0):
+    B, N, Ck, Cv, L, H, W, topl = SHAPES[shape]
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, Ck, H, W, generator=g) * 2.3
+    v = torch.randn(B, N, Cv, H, W, generator=g) * 1.8
+    fg = (torch.rand(B, N, H, W, generator=g) < 0.3).float()
+    fg[:, -1, : H // 2] = 0
+    masks = torch.stack([1 - fg, fg], dim=2)
+    prior = dict(zip(('kappa', 'nu', 'zita'), O.random_init(B, N, Ck, L, Cv, generator=g)))
+    prior['nu'] = torch.randn(B, N, 2, Cv, L, generator=g)
+    prior['zita'] = prior['zita'] + torch.rand(B, N, 2, 1, L, generator=g) * 3
+    return x, v, masks, prior
+
+
+@pytest.mark.parametrize('family', ['generic', 'fused'])
+@pytest.mark.parametrize('shape', ['small', 'train'])
+def test_em_backward(shape, family):
+    B, N, Ck, Cv, L, H, W, topl = SHAPES[shape]
+    _skip_unless_covered(family, B=B, N=N, Ck=Ck, Cv=Cv, HW=H * W, L=L, n_iters=1, topl=topl)
+    x, v, masks, prior = _problem(shape)
+    G = torch.randn(B, N, 2, Cv, L, generator=torch.Generator().manual_seed(5))
+    # oracle, fp64 autograd, one EM iteration (well conditioned: the responsibilities agree to ~1e-6)
+    d = lambda t: t.double()
+    v64 = d(v).requires_grad_()
+    p64 = {k: d(t) for k, t in prior.items()}
+    p64['nu'].requires_grad_()
+    want = O.em_memorize(d(x), v64, d(masks), p64, L, 1, 0.05)
+    (want['nu'] * d(G)).sum().backward()
+
+    core = _core(dict(L=L, Cv=Cv, n_iters=1, tau=0.05, topl=topl), family).train()
+    vg = v.to(DEV).requires_grad_()
+    pg = _to(prior, DEV)
+    pg['nu'].requires_grad_()
+    got = core.swem(x.to(DEV), vg, masks.to(DEV), pg)
+    assert got['nu'].requires_grad and not got['kappa'].requires_grad and not got['zita'].requires_grad
+    (got['nu'] * G.to(DEV)).sum().backward()
+    tol = 2e-4 if family == 'generic' else 1e-3
+    check('nu', maxrel(got['nu'], want['nu']), tol)
+    check('grad_v', maxrel(vg.grad, v64.grad), tol)
+    check('grad_nu_prior', maxrel(pg['nu'].grad, p64['nu'].grad), tol)
+    # multi-iteration: the backward must be the exact linear map of ITS OWN saved responsibilities
+    core.n_iters = 3
+    vg.grad = None
+    bases = core.swem(x.to(DEV), vg.detach(), masks.to(DEV), _to(prior, DEV), return_z=True)
+    got = core.swem(x.to(DEV), vg, masks.to(DEV), _to(prior, DEV))
+    (got['nu'] * G.to(DEV)).sum().backward()
+    w = (G.to(DEV) / bases['zita']).double()
+    ref = torch.einsum('bnsdl,bnspl->bndp', w, bases['z'].double()).view_as(vg)
+    check('grad_v_linear', maxrel(vg.grad, ref), 2e-3 if family == 'fused' else 1e-5)   # fused: z differs run to run (reduce order)
+
+
+@pytest.mark.parametrize('family', ['generic', 'fused'])
+@pytest.mark.parametrize('shape', ['small', 'train'])
+def test_readout_backward(shape, family):
+    B, N, Ck, Cv, L, H, W, topl = SHAPES[shape]
+    _skip_unless_covered(family, B=B, N=N, Ck=Ck, Cv=Cv, HW=H * W, L=L, n_iters=1, topl=topl, what='readout')
+    g = torch.Generator().manual_seed(9)
+    qk = torch.randn(B, Ck, H, W, generator=g) * 2.3
+    qv = torch.randn(B, Cv, H, W, generator=g)
+    banks = []
+    for k in range(2):
+        kap, _, _ = O.random_init(B, N, Ck, L, Cv, generator=g)
+        banks.append({'kappa': kap, 'nu': torch.randn(B, N, 2, Cv, L, generator=g), 'zita': torch.ones(B, N, 2, 1, L)})
+    chans = 2 * Cv + 2 * topl
+    G = torch.randn(B * N, chans, H, W, generator=g)
+
+    d = lambda t: t.double()
+    q64, qv64 = d(qk).requires_grad_(), d(qv).requires_grad_()
+    nu64 = [d(b['nu']).requires_grad_() for b in banks]
+    mk = torch.cat([d(b['kappa']) for b in banks], dim=-1)
+    S, mem = O.readout(O.l2norm(q64, 1), O.l2norm(mk, -2), torch.cat(nu64, dim=-1), 0.05, topl)
+    want = torch.cat([mem.flatten(end_dim=1), qv64.unsqueeze(1).expand(-1, N, -1, -1, -1).flatten(end_dim=1), S], dim=1)
+    (want * d(G)).sum().backward()
+
+    core = _core(dict(L=L, Cv=Cv, n_iters=1, tau=0.05, topl=topl), family).train()
+    qg, qvg = qk.to(DEV).requires_grad_(), qv.to(DEV).requires_grad_()
+    bg = [_to(b, DEV) for b in banks]
+    for b in bg:
+        b['nu'].requires_grad_()
+    core.memories['first'].bases, core.memories['first'].n_objs = bg[0], N
+    core.memories['update'].bases = bg[1]
+    feats, n = core.matching_features(qg, qvg)
+    assert n == N and feats.shape == want.shape
+    (feats * G.to(DEV)).sum().backward()
+    tol = 2e-4 if family == 'generic' else 1e-2
+    check('feats', maxrel(feats, want), tol)
+    check('grad_qk', maxrel(qg.grad, q64.grad), 1e-3)
+    check('grad_qv', maxrel(qvg.grad, qv64.grad), 1e-5)
+    for k in range(2):
+        check(f'grad_nu{k}', maxrel(bg[k]['nu'].grad, nu64[k].grad), 1e-3)
+
+
+def test_training_step_runs_end_to_end():
+    """3-frame clip, 2 objects (the reference's one_step, swem_trainer.py:59-108, restated): loss.backward()
+    reaches encoders, fusion conv and decoder through the CUDA memory; BN stays in eval like the reference (:37-39)."""
+    from swem_b200 import SWEM, make_config
+    from swem_b200.synthetic import davis_sequence
+    torch.manual_seed(0)
+    model = SWEM(make_config(keydim=64, n_bases=128, n_iters=4, topl=64)).to(DEV).train()
+    for m in model.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.eval()
+    T, N, h, w = 3, 2, 96, 96
+    frames, init = davis_sequence(T, N, seed=3, size=(h, w))
+    frames, init = frames.to(DEV), init.to(DEV)
+    label = init.argmax(dim=1)
+    mk16, _, s16, _, _ = model('encode_key', frames[:, 0])
+    mv16 = model('encode_value', frames[:, 0], init, s16)
+    model('init', mk16, mv16, init.long())
+    loss = 0
+    for i in range(1, T):
+        qk16, qv16, s16, s8, s4 = model('encode_key', frames[:, i])
+        ctx, n = model('match', qk16, qv16)
+        logits, prob = model('segment', n, ctx, s8, s4, None, (h, w))
+        loss = loss + torch.nn.functional.cross_entropy(logits, label)
+        if i < T - 1:
+            hard = torch.nn.functional.one_hot(prob.argmax(1), N + 1).permute(0, 3, 1, 2)
+            mv16 = model('encode_value', frames[:, i], prob, s16)
+            model('memorize', qk16, mv16, hard, prob)
+    loss.backward()
+    assert torch.isfinite(loss)
+    for name in ('key_encoder.conv1.weight', 'value_encoder.conv1.weight', 'key_proj.key_proj.weight',
+                 'swem_core.fusion_layer.layer_f.weight', 'decoder.pred.weight'):
+        gr = dict(model.named_parameters())[name].grad
+        assert gr is not None and torch.isfinite(gr).all() and gr.abs().max() > 0, name
