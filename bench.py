@@ -33,9 +33,9 @@ import torch  # noqa: E402
 
 CFG = dict(keydim=64, valdim=512, n_bases=128, n_iters=4, tau=0.05, topl=64, single_obj=False, backbone='resnet50')
 H, W = 480, 864
-# dram__bytes_read.sum + dram__bytes_write.sum of one em_fused_kernel launch at this workload, from the committed
-# `ncu --set full` capture profiles/r1_em_fused_kernel_ncu_full.txt (algorithmic bytes: 23.0 MB)
-NCU_TRAFFIC = {'fused-tcgen05': 24285440}
+# dram__bytes_read.sum + dram__bytes_write.sum of one em_pair_kernel launch at this workload, from the committed
+# `ncu --set full` capture profiles/r1_em_pair_kernel_ncu_full.txt (24.079 MB + 14 KB; algorithmic bytes: 23.0 MB)
+NCU_TRAFFIC = {'fused-tcgen05': 24093184}
 METRIC = '480p frames/sec'
 UNIT = 'frames/s'
 
@@ -295,7 +295,7 @@ def run_b200(args, rank, world, local_rank):
     f_mem, f_read = hot_path_flops(n_obj, hw, 2 * CFG['n_bases'])
     b_mem, b_read = hot_path_bytes(n_obj, hw, 2 * CFG['n_bases'])
     hot_s = (em_ms + read_ms) / 1e3
-    achieved = f_mem / (em_ms / 1e3) / 1e12                     # dominant kernel: em_fused_kernel (one launch per frame)
+    achieved = f_mem / (em_ms / 1e3) / 1e12                     # dominant kernel: em_pair_kernel (one launch per frame)
     import ctypes as C
     dims = _lib.SwemDims(1, n_obj, CFG['keydim'], CFG['valdim'], hw, CFG['n_bases'], CFG['n_iters'], 2, CFG['topl'], CFG['tau'])
     family = {'em': 'fused-tcgen05' if lib.swem_em_fused_supported(C.byref(dims)) else 'generic-fp32',
@@ -318,7 +318,7 @@ def run_b200(args, rank, world, local_rank):
         'clocks': {k: clocks[k] for k in ('sm_mhz', 'sm_max_mhz', 'reasons')},
         'roofline': {'bound': 'tensor', 'achieved': achieved, 'peak': peaks['tflops'], 'unit': 'TFLOP/s',
                      'frac': achieved / peaks['tflops'], 'traffic': NCU_TRAFFIC.get(family['em']),
-                     'kernel': 'em_fused_kernel via swem_em_forward (1 memset + 1 kernel per frame)' if 'fused' in family['em']
+                     'kernel': 'em_pair_kernel via swem_em_forward (1 memset + 1 kernel per frame)' if 'fused' in family['em']
                                else 'generic EM kernels via swem_em_forward',
                      'peak_source': peaks['source'] + ' bf16 sustained (kernel timed with CUDA events inside an eager pass of the same K frames)',
                      'algorithmic_flops_per_launch': f_mem, 'algorithmic_bytes_per_launch': b_mem,

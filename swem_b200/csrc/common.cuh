@@ -75,11 +75,6 @@ long long* get_profile_buffer();
 bool fused_em_supported(const SwemDims& d);
 size_t fused_em_workspace(const SwemDims& d);
 int fused_em_forward(const SwemEmArgs& a, cudaStream_t st);
-bool fused_em2_supported(const SwemDims& d);
-size_t fused_em2_workspace(const SwemDims& d);
-int fused_em2_forward(const SwemEmArgs& a, cudaStream_t st);
-int launch_nu_finalize(const float* acc_nu, const float* nu_prior, const float* zita_prior, const float* zita, float* nu,
-                       int G, cudaStream_t st);
 bool fused_readout_supported(const SwemDims& d);
 size_t fused_readout_workspace(const SwemDims& d);
 int fused_readout_forward(const SwemReadArgs& a, cudaStream_t st);

@@ -1,30 +1,32 @@
-// Fused sequential-weighted-EM kernel for sm_100a (tcgen05 + TMEM), one launch per memorize call.
+// Fused sequential-weighted-EM kernel for sm_100a (tcgen05 + TMEM + bulk-async copies), one launch per memorize call:
+// one CTA per (unit u = (b,n), pixel tile of 128 px, side s), the two sides of a tile forming a 2-CTA cluster.
 //
-// Covers the BASELINE shape family: Ck = 64, L = 128 bases per side, Cv = 512, any HW, any B*N.
-// Reference semantics: methods/SWEM/modules.py:129-168 (swem), :112-120 (E), :122-127 (M),
-// :93-110 (W), :164-165 (nu).  Arithmetic: operands fp16, with x and the unit bases split into
-// hi + lo halves on the Ck contraction (3 MMAs: hi*hi + hi*lo + lo*hi ~ fp32-accurate logits),
-// fp32 accumulation in TMEM, fp32 softmax / normalisation.
+// Covers the BASELINE shape family: Ck = 64, L = 128 bases per side, Cv = 512, any HW up to 128 x (#SMs / 2) pixels,
+// any B*N.  Reference semantics: methods/SWEM/modules.py:129-168 (swem), :112-120 (E), :122-127 (M), :93-110 (W),
+// :164-165 (nu).  Arithmetic: operands fp16 with x, the unit bases, the responsibilities and v split into hi + lo
+// halves (3 MMAs per product: hi*hi + hi*lo + lo*hi ~ fp32-accurate), fp32 accumulation in TMEM, fp32 softmax /
+// normalisation.  The W-step logits l2norm(x).khat equal the E-step logits x.khat / (||x_p|| + eps) -- same khat --
+// so one GEMM per iteration serves both steps.
 //
-// Decomposition: one CTA per (unit u = (b,n), pixel tile of 128 px), both sides [bg | fg] = 256
-// basis columns.  All CTAs of a launch are co-resident (grid <= #SMs, 1 CTA/SM); the M-step sum
-// over pixel tiles is a bulk-async reduce-add of each CTA's partial into an L2-resident
-// accumulator followed by a per-unit arrival counter; every CTA then reads the total back and
-// re-derives the unit bases for its next E-step locally (no second exchange).
+// Decomposition (a 5-object 480p frame fills 130 of the 148 SMs; the first-generation kernel, one CTA per tile with
+// both sides, filled 65 and took 101 us against 70 us -- profiles/r1_phases_em_v1.txt vs r1_phases_em_pair.txt):
 //
-// Per EM iteration in a CTA (256 threads, thread <-> (pixel, side) in the epilogues and
-// thread <-> basis row in the finalize):
-//   1. a[p, sl] = x_p . khat_sl        12 x tcgen05.mma M128 N256 K16 (A = X^T MN-major, B = khat K-major)
-//      The W-step logits l2norm(x).khat equal a / (||x_p|| + eps): the same accumulators serve both.
-//   2. epilogue: W-step weights (iteration > 0) and per-side softmax * weight -> z (fp16) into
-//      shared memory as the MN-major A operand of the M-step
-//   3. [sum_p z x | sum_p z] = Z^T [X^T | 1]   32 x tcgen05.mma M128 N80/64 K16 per CTA
-//   4. partial -> smem -> cp.reduce.async.bulk (add.f32) -> L2 accumulator; arrive; wait; bulk load total
-//   5. kappa = (zita_ kappa_ + sum)/zita ; khat = l2norm(kappa) -> fp16 hi/lo K-major B operand
-// After the last E-step: nu partial = Z^T V^T (two passes over Cv halves, V streamed through a
-// 3-stage fp16 ring), reduce-added the same way, then each CTA normalises a slice of nu.
+//   * every per-CTA phase handles one side only: 128 logits columns, 128 basis rows, half the exps, half
+//     of the M-step / nu partials that have to be reduce-added through L2;
+//   * the only coupling between the sides -- the W-step's share of exp-affinity per side (:101-108) -- is
+//     one (max, sum) pair per pixel exchanged through distributed shared memory and a cluster barrier;
+//   * nu = Z^T V^T needs a single pass (its [128 bases][512 channels] accumulator is exactly the 512 TMEM
+//     columns); during set-up each CTA converts half of its tile's V to fp16 hi/lo operand images in global
+//     memory (L2-resident), and after the last E-step both CTAs stream all of them back with plain bulk-async
+//     copies (3-stage ring issued by one thread, first stages prefetched ~40 us ahead) -- no register staging
+//     on the critical path, and the conversion is shared by the pair;
+//   * nu is normalised in this kernel: the last M-step barrier also covers the nu reduce-adds, after it every
+//     CTA finalises a slice of value channels (no separate kernel, no third cross-tile wait).
+//
+// Cross-tile sums go through L2-resident accumulators with a per-(unit, side, iteration) arrival counter (bounded
+// spin, co-resident grid): M-step partials as fp32 reductions straight from registers (red.global.add), the 256 KB
+// nu partial of a CTA as bulk reduce-adds from shared memory.
 #include <cuda_fp16.h>
-#include <stdlib.h>
 
 #include "common.cuh"
 #include "tc05.cuh"
@@ -37,44 +39,42 @@ using namespace tc05;
 namespace em {
 constexpr int kTP = 128;    // pixels per CTA
 constexpr int kCk = 64;
-constexpr int kL = 128;     // bases per side
-constexpr int kSL = 256;    // both sides
+constexpr int kL = 128;     // bases per side = rows owned by one CTA
 constexpr int kCv = 512;
-constexpr int kAccRow = 73; // floats per row of the kappa accumulator blob: 64 kappa sums, 1 zita sum, pad (odd stride)
-constexpr uint32_t kAccBytes = kSL * kAccRow * 4;  // 74752
-constexpr float kKScale = 256.f;                   // khat is staged as khat*256 so its lo half stays a normal fp16
-constexpr float kZScale = 16384.f;                 // z (<= 1) is staged as z*2^14: responsibilities down to ~4e-9 stay normal fp16
+constexpr uint32_t kAccBytes = (kCk + 1) * kL * 4; // M-step accumulator of one (unit, iteration, side): [64 kappa sums + zita sum][128 l]
+constexpr float kKScale = 256.f;
+constexpr float kZScale = 16384.f;
+constexpr uint32_t kStageBytes = 32768;            // one V operand image: [256 d][32 px] fp16, hi plane then lo plane
+constexpr uint32_t kVPlane = 16384;
+constexpr int kStages = 3;
+constexpr int kChunks = 8;                         // per tile: 2 channel halves x 4 pixel quarters
 
 // ---- shared memory map (bytes) ---------------------------------------------------------------
-// XH : [c 0..79][p] chunks  : byte = (c%8)*16 + (c/8)*2048 + (p/8)*128 + (p%8)*2   (rows 64 = ones, 65..79 = 0)
-// XL : [c 0..63][p]
-//      as E-step A (MN-major, r=p, k=c): SBO=128,  LBO=2048 ; as M-step B (K-major, r=c, k=p): SBO=2048, LBO=128
-// KH/KL : [sl 0..255][c] K-major: byte = (sl%8)*16 + (sl/8)*128 + (c/8)*4096 + (c%8)*2  -> SBO=128, LBO=4096
-// Z  : [sl 0..255][p] MN-major A: byte = (sl%8)*2 + (p%8)*16 + (sl/8)*2048 + (p/8)*128   -> SBO=2048, LBO=128
-// P  : fp32 [256][73] staging of the M-step partial / total (aliases Z)
-// VS : V stage [d 0..255][p 0..31] K-major, hi plane (16 KB) then lo plane: byte = (d%8)*16 + (d/8)*128 + (p/8)*4096 + (p%8)*2
-//      -> SBO=128, LBO=4096.  Two stages of 32 KB: stage 0 at kOffVS, stage 1 in the X region (idle during the nu GEMMs)
-// ZL : lo half of z, same layout as Z (aliases KH/KL: khat is dead between the logits GEMM and the finalize)
-// NS : fp32 [2 sides][32 d][128 l] staging of nu partials (aliases XH/XL, dead after the last M-step GEMM)
+// XH : [c 0..79][p] : byte = (c%8)*16 + (c/8)*2048 + (p/8)*128 + (p%8)*2      (row 64 = ones, 65..79 = 0)
+// XL : [c 0..63][p]   E-step A (MN-major, r=p, k=c): SBO=128, LBO=2048; M-step B (K-major, r=c, k=p): SBO=2048, LBO=128
+// KH/KL : [l 0..127][c] K-major: byte = (l%8)*16 + (l/8)*128 + (c/8)*2048 + (c%8)*2   -> SBO=128, LBO=2048
+// Z  : [l 0..127][p] MN-major A: byte = (l%8)*2 + (p%8)*16 + (l/8)*2048 + (p/8)*128   -> SBO=2048, LBO=128
+// ZL : lo half of z (aliases KH/KL: khat is dead between the logits GEMM and the finalize)
+// VS : ring of V operand images, each [d 0..255][p 0..31] K-major: byte = (d%8)*16 + (d/8)*128 + (p/8)*4096 + (p%8)*2
+//      -> SBO=128, LBO=4096; hi plane then lo plane.  The nu drain staging (2 x 32 KB fp32) aliases the ring.
 constexpr uint32_t kOffXH = 0;
 constexpr uint32_t kOffXL = kOffXH + 10 * 2048;
 constexpr uint32_t kOffKH = kOffXL + 8 * 2048;
-constexpr uint32_t kOffKL = kOffKH + 8 * 4096;
-constexpr uint32_t kOffZ = kOffKL + 8 * 4096;
-constexpr uint32_t kOffVS = kOffZ + kAccBytes;            // 74752 is a multiple of 128
-constexpr uint32_t kVPlane = 4 * 4096;                    // 16 KB: one fp16 plane of a V stage
-constexpr uint32_t kOffMisc = kOffVS + 3 * kVPlane;       // (48 KB reserved: stage 0 uses 32 KB, the drain staging 32 KB)
-constexpr uint32_t kOffZL = kOffKH;                       // 64 KB
-constexpr uint32_t kOffNS = kOffXH;                       // 32 KB of the 36 KB X region
+constexpr uint32_t kOffKL = kOffKH + 8 * 2048;
+constexpr uint32_t kOffZ = kOffKL + 8 * 2048;
+constexpr uint32_t kOffZL = kOffKH;
+constexpr uint32_t kOffVS = kOffZ + 16 * 2048;
+constexpr uint32_t kOffMisc = kOffVS + kStages * kStageBytes;
 struct Misc {
   float inv_nx[kTP];
-  float mask[2][kTP];
-  float ex_max[2][kTP];
-  float ex_sum[2][kTP];
-  float zita[kSL];
+  float mask[kTP];
+  float hmax[2][kTP];
+  float hsum[2][kTP];
+  float hew[2][kTP];
+  float2 mbox[2][2][kTP];   // [iteration parity][side][pixel] = (side max of the logits, side sum of W-step exps)
   uint64_t bar_mma;
-  uint64_t bar_tma;
-  uint64_t bar_stage[2];
+  uint64_t bar_full[kStages];
+  uint64_t bar_empty[kStages];
   uint32_t tmem_base;
   int abort_flag;
 };
@@ -82,12 +82,12 @@ constexpr uint32_t kSmemBytes = kOffMisc + sizeof(Misc) + 128;
 static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 
 // TMEM columns
-constexpr uint32_t kColE = 0;      // [128 px][256]   E / W logits
-constexpr uint32_t kColM = 256;    // side s at 256 + 80*s : [128 sl][80]
-constexpr uint32_t kColNu = 0;     // nu pass: side s at 256*s : [128 sl][256 d]
+constexpr uint32_t kColE = 0;      // [128 px][128]  E / W logits of this side
+constexpr uint32_t kColM = 128;    // [128 l][80]    M-step sums
+constexpr uint32_t kColNu = 0;     // [128 l][512 d] nu sums (after the last M-step partial has been read out)
 }  // namespace em
 
-struct EmFusedParams {
+struct EmPairParams {
   const float* x;
   const float* v;
   const float* masks;
@@ -98,28 +98,94 @@ struct EmFusedParams {
   float* nu;
   float* zita;
   float* z_last;
-  float* acc_k;        // [U][n_iters][256][73], zeroed before launch
-  float* acc_nu;       // [U][2][512][128], zeroed before launch
-  unsigned* counters;  // [U][n_iters + 1], zeroed before launch
-  int* status;         // device error word (0 = ok)
-  long long* prof;     // optional: phase time stamps (ns) of CTA 0, see swem_set_profile_buffer
+  uint8_t* vblob;        // [U][T][8][32 KB] scratch: operand images of V (written in set-up, read after the last E-step)
+  float* acc_k;          // [U][n_iters][2][65][128], zeroed before launch
+  float* acc_nu;         // [U][2][512][128], zeroed before launch
+  unsigned* counters;    // [U][n_iters][2], zeroed before launch
+  int* status;
+  long long* prof;
   int N, HW, T, n_iters, u0;
-  float c1s;           // log2(e) / (tau * kKScale): scales staged logits into exp2 arguments
+  float c1s;             // log2(e) / (tau * kKScale)
 };
 
-// phase stamp: CTA 0 / thread 0 only, when a profile buffer is installed
-#define EM_STAMP()                                                   \
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ uint32_t map_to_peer(uint32_t smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_cluster_f2(uint32_t addr, float a, float b) {
+  asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(a), "f"(b) : "memory");
+}
+
+#define EM_STAMP()                                                  \
   do {                                                               \
-    if (p.prof != nullptr && blockIdx.x == 0 && tid == 0 && n_stamp < 250) p.prof[1 + n_stamp++] = global_ns(); \
+    if (p.prof != nullptr && blockIdx.x == 0 && tid == 0 && n_stamp < 120) p.prof[1 + n_stamp++] = global_ns(); \
   } while (0)
 
-__global__ void __launch_bounds__(256, 1) em_fused_kernel(const EmFusedParams p) {
+// ------------------------------------------------------------------------------------------------------
+// V -> fp16 hi/lo operand images, done by the whole CTA for the 4 chunks (pixel quarters) of channel half h:
+// each chunk is [256 d][32 px] fp32 in, a 32 KB image out (pixels past HW are zero).
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void convert_v_half(const float* __restrict__ vsrc /* [256][HW] rows of this half */,
+                                               uint8_t* __restrict__ images /* 4 x 32 KB */, int p0, int HW, int warp, int lane) {
+  using namespace em;
+  const int g = lane & 3;                               // group of 8 pixels
+  const bool aligned = (HW & 3) == 0;
+  auto load = [&](int q, float (&f)[4][8]) {
+    const int px0 = p0 + q * 32 + g * 8;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int d = warp * 32 + j * 8 + (lane >> 2);    // 0..255
+      const float* src = vsrc + (size_t)d * HW + px0;
+      if (aligned && px0 + 7 < HW) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(src));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(src) + 1);
+        f[j][0] = a.x; f[j][1] = a.y; f[j][2] = a.z; f[j][3] = a.w; f[j][4] = b.x; f[j][5] = b.y; f[j][6] = b.z; f[j][7] = b.w;
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[j][e] = (px0 + e < HW) ? __ldg(src + e) : 0.f;
+      }
+    }
+  };
+  auto store = [&](int q, const float (&f)[4][8]) {
+    uint8_t* out = images + (size_t)q * kStageBytes;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int d = warp * 32 + j * 8 + (lane >> 2);
+      __align__(16) __half hi[8];
+      __align__(16) __half lo[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) split_half(f[j][e], hi[e], lo[e]);
+      const uint32_t off = (d % 8) * 16 + (d / 8) * 128 + g * 4096;
+      *reinterpret_cast<uint4*>(out + off) = *reinterpret_cast<uint4*>(hi);
+      *reinterpret_cast<uint4*>(out + kVPlane + off) = *reinterpret_cast<uint4*>(lo);
+    }
+  };
+  // all 32 loads of a thread (128 KB per CTA) are in flight before the first conversion: one memory round trip
+  float buf[4][4][8];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) load(q, buf[q]);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) store(q, buf[q]);
+}
+
+// ------------------------------------------------------------------------------------------------------
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) em_pair_kernel(const EmPairParams p) {
   using namespace em;
   extern __shared__ __align__(1024) uint8_t smem[];
   Misc& ms = *reinterpret_cast<Misc*>(smem + kOffMisc);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int tile = blockIdx.x % p.T;
-  const int u = p.u0 + blockIdx.x / p.T;
+  const int sd = (int)cluster_ctarank();                // side handled by this CTA (0 = background, 1 = foreground)
+  const int pair = blockIdx.x >> 1;
+  const int tile = pair % p.T;
+  const int u = p.u0 + pair / p.T;
   const int b = u / p.N;
   const int p0 = tile * kTP;
   const int HW = p.HW;
@@ -132,17 +198,25 @@ __global__ void __launch_bounds__(256, 1) em_fused_kernel(const EmFusedParams p)
   if (warp == 0) tmem_alloc(&ms.tmem_base, 512);
   if (tid == 0) {
     mbar_init(&ms.bar_mma, 1);
-    mbar_init(&ms.bar_tma, 1);
-    for (int i = 0; i < 2; ++i) mbar_init(&ms.bar_stage[i], 1);
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&ms.bar_full[i], 1);
+      mbar_init(&ms.bar_empty[i], 1);
+    }
     ms.abort_flag = 0;
     fence_mbar_init();
   }
-  // thread <-> basis row r = tid (side = r / 128, l = r % 128) in the finalize steps
-  const int row_s = tid >> 7, row_l = tid & 127;
-  const float zita_p = __ldg(p.zita_prior + ((size_t)u * 2 + row_s) * kL + row_l);
-  const float* kprior = p.kappa_prior + (((size_t)u * 2 + row_s) * kCk) * kL + row_l;   // + c*kL
-  // khat = l2norm(kappa) * 256 -> fp16 hi/lo rows of the K-major B operand (reference :115)
-  auto stage_khat = [&](const float (&kap)[kCk]) {
+  // V operand images: this CTA converts channel half `sd` of the tile (the peer converts the other half); both read
+  // all 8 images back through the bulk-copy ring after the last E-step.
+  uint8_t* const vimg = p.vblob + ((size_t)u * p.T + tile) * kChunks * kStageBytes;
+  convert_v_half(p.v + ((size_t)u * kCv + sd * 256) * HW, vimg + (size_t)sd * 4 * kStageBytes, p0, HW, warp, lane);
+  __threadfence();
+  asm volatile("fence.proxy.async;" ::: "memory");     // generic-proxy global stores -> visible to the bulk-copy (async proxy) reads
+  // rows: thread tid < 128 <-> basis l = tid of side sd (finalize steps)
+  const bool row_thread = tid < kL;
+  const int gs = u * 2 + sd;                            // (b, n, s) index
+  const float zita_p = row_thread ? __ldg(p.zita_prior + (size_t)gs * kL + tid) : 0.f;
+  const float* kprior = p.kappa_prior + ((size_t)gs * kCk) * kL + (tid & (kL - 1));   // + c*kL
+  auto stage_khat = [&](const float (&kap)[kCk]) {      // khat = l2norm(kappa) * 256 -> fp16 hi/lo K-major rows (reference :115)
     float ss = 0.f;
 #pragma unroll
     for (int c = 0; c < kCk; ++c) ss = fmaf(kap[c], kap[c], ss);
@@ -153,17 +227,19 @@ __global__ void __launch_bounds__(256, 1) em_fused_kernel(const EmFusedParams p)
       __align__(16) __half lo[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) split_half(kap[g * 8 + e] * sc, hi[e], lo[e]);
-      const uint32_t off = (tid % 8) * 16 + (tid / 8) * 128 + g * 4096;
+      const uint32_t off = (tid % 8) * 16 + (tid / 8) * 128 + g * 2048;
       *reinterpret_cast<uint4*>(smem + kOffKH + off) = *reinterpret_cast<uint4*>(hi);
       *reinterpret_cast<uint4*>(smem + kOffKL + off) = *reinterpret_cast<uint4*>(lo);
     }
   };
-  float kap0[kCk];                   // kappa^0 = prior: loads issued first, consumed after the X tile is staged
+  float kap0[kCk];
+  if (row_thread) {
 #pragma unroll
-  for (int c = 0; c < kCk; ++c) kap0[c] = __ldg(kprior + (size_t)c * kL);
-  // pixel norms + masks (thread <-> pixel)
-  if (tid < kTP) {
-    const int px = p0 + tid;
+    for (int c = 0; c < kCk; ++c) kap0[c] = __ldg(kprior + (size_t)c * kL);
+  }
+  // pixel norms + this side's mask (threads 128..255 <-> pixel, so they overlap with the prior loads of the row threads)
+  if (!row_thread) {
+    const int q = tid - kL, px = p0 + q;
     float ss = 0.f;
     if (px < HW) {
       const float* xp = p.x + (size_t)b * kCk * HW + px;
@@ -173,17 +249,16 @@ __global__ void __launch_bounds__(256, 1) em_fused_kernel(const EmFusedParams p)
         ss = fmaf(t, t, ss);
       }
     }
-    ms.inv_nx[tid] = 1.f / (sqrtf(ss) + kEpsNorm);
-    ms.mask[0][tid] = px < HW ? __ldg(p.masks + ((size_t)u * 2 + 0) * HW + px) : 0.f;
-    ms.mask[1][tid] = px < HW ? __ldg(p.masks + ((size_t)u * 2 + 1) * HW + px) : 0.f;
+    ms.inv_nx[q] = 1.f / (sqrtf(ss) + kEpsNorm);
+    ms.mask[q] = px < HW ? __ldg(p.masks + (size_t)gs * HW + px) : 0.f;
   }
-  // X tile -> fp16 hi/lo chunks.  thread -> (channel c = tid/4 [+64 for the aug rows], 4 pixel-groups)
+  // X tile -> fp16 hi/lo chunks.  thread -> (channel c = tid/4, 4 pixel groups of 8)
   {
-    const int c = tid >> 2;                  // 0..63
+    const int c = tid >> 2;
     const float* xrow = p.x + ((size_t)b * kCk + c) * HW;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const int pg = (tid & 3) * 4 + j;      // pixel group of 8
+      const int pg = (tid & 3) * 4 + j;
       __align__(16) __half hi[8];
       __align__(16) __half lo[8];
 #pragma unroll
@@ -196,8 +271,7 @@ __global__ void __launch_bounds__(256, 1) em_fused_kernel(const EmFusedParams p)
       *reinterpret_cast<uint4*>(smem + kOffXH + off) = *reinterpret_cast<uint4*>(hi);
       *reinterpret_cast<uint4*>(smem + kOffXL + off) = *reinterpret_cast<uint4*>(lo);
     }
-    // augmented rows 64..79 of XH: row 64 = 1 (column-sum of z -> zita), rows 65..79 = 0
-    for (int i = tid; i < 16 * 16; i += 256) {
+    for (int i = tid; i < 16 * 16; i += 256) {          // augmented rows 64..79 of XH: row 64 = 1 (-> zita), rest 0
       const int r = 64 + (i >> 4), pg = i & 15;
       const __half one = __float2half_rn(r == 64 ? 1.f : 0.f);
       __align__(16) __half vals[8];
@@ -206,45 +280,50 @@ __global__ void __launch_bounds__(256, 1) em_fused_kernel(const EmFusedParams p)
       *reinterpret_cast<uint4*>(smem + kOffXH + (r % 8) * 16 + (r / 8) * 2048 + pg * 128) = *reinterpret_cast<uint4*>(vals);
     }
   }
-  stage_khat(kap0);
+  if (row_thread) stage_khat(kap0);
   tc_fence_before_sync();
-  __syncthreads();
+  cluster_arrive();                   // both CTAs of the pair are running before any remote shared-memory store,
+  cluster_wait();                     // and both halves of the tile's V images are written
   tc_fence_after_sync();
+  if (tid == 0) {                     // the first kStages images start flying now; they are consumed after the last E-step
+    asm volatile("fence.proxy.async;" ::: "memory");
+    for (int k = 0; k < kStages; ++k) {
+      mbar_expect_tx(&ms.bar_full[k], kStageBytes);
+      bulk_g2s(smem + kOffVS + k * kStageBytes, vimg + (size_t)k * kStageBytes, kStageBytes, &ms.bar_full[k]);
+    }
+  }
   const uint32_t tmem = ms.tmem_base;
-  uint32_t ph_mma = 0, ph_tma = 0;   // mbarrier phase parities
-
-  bool failed = false;               // block-uniform
+  uint32_t ph_mma = 0;
+  bool failed = false;
   EM_STAMP();                        // setup done
 
-  const uint32_t idesc_e = make_idesc(128, 256, kFmtF16, kFmtF16, kMajorMN, kMajorK);
+  const uint32_t idesc_e = make_idesc(128, 128, kFmtF16, kFmtF16, kMajorMN, kMajorK);
   const uint32_t idesc_m80 = make_idesc(128, 80, kFmtF16, kFmtF16, kMajorMN, kMajorK);
   const uint32_t idesc_m64 = make_idesc(128, 64, kFmtF16, kFmtF16, kMajorMN, kMajorK);
   const uint32_t idesc_nu = make_idesc(128, 256, kFmtF16, kFmtF16, kMajorMN, kMajorK);
+  const uint32_t peer_mbox = map_to_peer(smem_u32(&ms.mbox[0][0][0]), (uint32_t)(sd ^ 1));
 
   for (int it = 0; it < I; ++it) {
-    // KH / KL hold khat of the current kappa (staged before the loop / at the end of the previous iteration)
     fence_proxy_async_smem();
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
 
-    // ---- (1) logits GEMM -----------------------------------------------------------------------
-    // (single-thread sections are written as warp 0 / lane 0 + __syncwarp so that the other lanes of
-    //  warp 0 park at the warp barrier instead of spinning on an mbarrier in a divergent branch)
+    // ---- (1) logits of this side: a[p, l] = x_p . khat_l ---------------------------------------------
     if (warp == 0) {
       if (lane == 0) {
 #pragma unroll
-      for (int term = 0; term < 3; ++term) {
-        const uint32_t xa = sbase + (term == 2 ? kOffXL : kOffXH);
-        const uint32_t kb = sbase + (term == 1 ? kOffKL : kOffKH);
+        for (int term = 0; term < 3; ++term) {
+          const uint32_t xa = sbase + (term == 2 ? kOffXL : kOffXH);
+          const uint32_t kb = sbase + (term == 1 ? kOffKL : kOffKH);
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
-          const uint64_t ad = make_sdesc(xa + kk * 2 * 2048, /*lbo*/ 2048, /*sbo*/ 128);
-          const uint64_t bd = make_sdesc(kb + kk * 2 * 4096, /*lbo*/ 4096, /*sbo*/ 128);
-          mma_f16_ss(tmem + kColE, ad, bd, idesc_e, (term | kk) ? 1u : 0u);
+          for (int kk = 0; kk < 4; ++kk) {
+            const uint64_t ad = make_sdesc(xa + kk * 2 * 2048, /*lbo*/ 2048, /*sbo*/ 128);
+            const uint64_t bd = make_sdesc(kb + kk * 2 * 2048, /*lbo*/ 2048, /*sbo*/ 128);
+            mma_f16_ss(tmem + kColE, ad, bd, idesc_e, (term | kk) ? 1u : 0u);
+          }
         }
-      }
-      mma_commit(&ms.bar_mma);
+        mma_commit(&ms.bar_mma);
       }
       __syncwarp();
     }
@@ -253,62 +332,73 @@ __global__ void __launch_bounds__(256, 1) em_fused_kernel(const EmFusedParams p)
     tc_fence_after_sync();
     EM_STAMP();                      // logits GEMM done
 
-    // ---- (2) epilogue: thread <-> (pixel px, side sd) ----------------------------------------------
+    // ---- (2) epilogue: thread <-> (pixel px, half hb of this side's bases) ------------------------------
     {
-      const int px = (warp & 3) * 32 + lane, sd = warp >> 2;
-      float a[kL];
+      const int px = (warp & 3) * 32 + lane, hb = warp >> 2;
+      const bool do_w = it > 0;
+      float a[64];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
+      for (int q = 0; q < 2; ++q) {
         uint32_t r[32];
-        tmem_ld32(tmem_addr(tmem, (warp & 3) * 32, kColE + sd * kL + q * 32), r);
+        tmem_ld32(tmem_addr(tmem, (warp & 3) * 32, kColE + hb * 64 + q * 32), r);
         tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 32; ++j) a[q * 32 + j] = __uint_as_float(r[j]);
       }
       float mx = a[0];
 #pragma unroll
-      for (int i = 1; i < kL; ++i) mx = fmaxf(mx, a[i]);
-      const bool do_w = it > 0;
-      if (do_w) ms.ex_max[sd][px] = mx;
+      for (int i = 1; i < 64; ++i) mx = fmaxf(mx, a[i]);
+      ms.hmax[hb][px] = mx;
       __syncthreads();
+      mx = fmaxf(ms.hmax[0][px], ms.hmax[1][px]);       // max over this side's 128 bases
+      // W-step (reference :93-110) works on t = a * inv_nx with the max over BOTH sides; each side sums its exps
+      // against its own max and the pair rescales after the exchange: exp(t - M) = exp(t - m_s) * exp(m_s - M).
+      const float cw = ms.inv_nx[px] * p.c1s;
+      float e = 0.f, sum = 0.f;
       if (do_w) {
-        // W-step (reference :93-110): t = a * inv_nx ; joint max over both sides
-        const float gm = fmaxf(ms.ex_max[0][px], ms.ex_max[1][px]);
-        const float cw = ms.inv_nx[px] * p.c1s;
-        float e = 0.f;
 #pragma unroll
-        for (int i = 0; i < kL; ++i) e += fast_exp2((a[i] - gm) * cw);
-        ms.ex_sum[sd][px] = e;
+        for (int i = 0; i < 64; ++i) e += fast_exp2((a[i] - mx) * cw);
       }
-      float sum = 0.f;
 #pragma unroll
-      for (int i = 0; i < kL; ++i) {
+      for (int i = 0; i < 64; ++i) {
         a[i] = fast_exp2((a[i] - mx) * p.c1s);
         sum += a[i];
       }
+      ms.hsum[hb][px] = sum;
+      ms.hew[hb][px] = e;
       __syncthreads();
-      float w = ms.mask[sd][px];
+      sum = ms.hsum[0][px] + ms.hsum[1][px];
+      float w = ms.mask[px];
       if (do_w) {
-        const float e0 = ms.ex_sum[0][px], e1 = ms.ex_sum[1][px];
+        const int par = it & 1;
+        if (hb == 0) {
+          const float es = ms.hew[0][px] + ms.hew[1][px];
+          ms.mbox[par][sd][px] = make_float2(mx, es);
+          st_cluster_f2(peer_mbox + (uint32_t)(((par * 2 + sd) * kTP + px) * sizeof(float2)), mx, es);
+        }
+        cluster_arrive();
+        cluster_wait();
+        const float2 m0 = ms.mbox[par][0][px], m1 = ms.mbox[par][1][px];
+        const float gm = fmaxf(m0.x, m1.x);
+        const float e0 = m0.y * fast_exp2((m0.x - gm) * cw), e1 = m1.y * fast_exp2((m1.x - gm) * cw);
         w *= 1.f - (sd ? e1 : e0) / (e0 + e1);
       }
       const float scale = w / sum;
       const float zs = scale * kZScale;
-      // z -> fp16 hi + lo, MN-major A operands: 16-byte chunk = 8 consecutive bases of this pixel
 #pragma unroll
-      for (int g = 0; g < kL / 8; ++g) {
+      for (int g = 0; g < 8; ++g) {
         __align__(16) __half hi[8];
         __align__(16) __half lo[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) split_half(a[g * 8 + e] * zs, hi[e], lo[e]);
-        const uint32_t off = (px % 8) * 16 + (px / 8) * 128 + (sd * 16 + g) * 2048;
+        for (int k = 0; k < 8; ++k) split_half(a[g * 8 + k] * zs, hi[k], lo[k]);
+        const uint32_t off = (px % 8) * 16 + (px / 8) * 128 + (hb * 8 + g) * 2048;
         *reinterpret_cast<uint4*>(smem + kOffZ + off) = *reinterpret_cast<uint4*>(hi);
         *reinterpret_cast<uint4*>(smem + kOffZL + off) = *reinterpret_cast<uint4*>(lo);
       }
       if (p.z_last != nullptr && it == I - 1 && p0 + px < HW) {
-        float4* dst = reinterpret_cast<float4*>(p.z_last + (((size_t)u * 2 + sd) * HW + p0 + px) * kL);
+        float4* dst = reinterpret_cast<float4*>(p.z_last + ((size_t)gs * HW + p0 + px) * kL + hb * 64);
 #pragma unroll
-        for (int g = 0; g < kL / 4; ++g)
+        for (int g = 0; g < 16; ++g)
           dst[g] = make_float4(a[g * 4] * scale, a[g * 4 + 1] * scale, a[g * 4 + 2] * scale, a[g * 4 + 3] * scale);
       }
     }
@@ -316,39 +406,34 @@ __global__ void __launch_bounds__(256, 1) em_fused_kernel(const EmFusedParams p)
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
-
     EM_STAMP();                      // epilogue done
-    // ---- (3) M-step GEMM: [kappa sums | zita sum] per side ------------------------------------------
+
+    // ---- (3) M-step GEMM: [sum_p z x | sum_p z] for this side's 128 bases --------------------------------
     if (warp == 0) {
       if (lane == 0) {
 #pragma unroll
-      for (int sd = 0; sd < 2; ++sd) {
-        const uint32_t za = sbase + kOffZ + sd * 16 * 2048;
-#pragma unroll
         for (int kk = 0; kk < 8; ++kk) {
-          const uint64_t ad = make_sdesc(za + kk * 2 * 128, /*lbo*/ 128, /*sbo*/ 2048);
-          const uint64_t al = make_sdesc(za + (kOffZL - kOffZ) + kk * 2 * 128, /*lbo*/ 128, /*sbo*/ 2048);
+          const uint64_t ad = make_sdesc(sbase + kOffZ + kk * 2 * 128, /*lbo*/ 128, /*sbo*/ 2048);
+          const uint64_t al = make_sdesc(sbase + kOffZL + kk * 2 * 128, /*lbo*/ 128, /*sbo*/ 2048);
           const uint64_t bh = make_sdesc(sbase + kOffXH + kk * 2 * 128, /*lbo*/ 128, /*sbo*/ 2048);
           const uint64_t bl = make_sdesc(sbase + kOffXL + kk * 2 * 128, /*lbo*/ 128, /*sbo*/ 2048);
-          mma_f16_ss(tmem + kColM + sd * 80, ad, bh, idesc_m80, kk ? 1u : 0u);   // z_hi x_hi (+ zita column)
-          mma_f16_ss(tmem + kColM + sd * 80, ad, bl, idesc_m64, 1u);             // z_hi x_lo
-          mma_f16_ss(tmem + kColM + sd * 80, al, bh, idesc_m80, 1u);             // z_lo x_hi
+          mma_f16_ss(tmem + kColM, ad, bh, idesc_m80, kk ? 1u : 0u);   // z_hi x_hi (+ zita column)
+          mma_f16_ss(tmem + kColM, ad, bl, idesc_m64, 1u);             // z_hi x_lo
+          mma_f16_ss(tmem + kColM, al, bh, idesc_m80, 1u);             // z_lo x_hi
         }
-      }
-      mma_commit(&ms.bar_mma);
+        mma_commit(&ms.bar_mma);
       }
       __syncwarp();
     }
     SWEM_CTA_WAIT(&ms.bar_mma, ph_mma, ms.abort_flag);
     ph_mma ^= 1;
     tc_fence_after_sync();
-
     EM_STAMP();                      // M GEMM done
-    // partial of this tile, row r = tid: 64 kappa sums + zita sum (kept in registers for now)
-    float part[kCk + 1];
-    {
+
+    float part[kCk + 1];              // partial of this tile for row l = tid (row threads only)
+    if (row_thread) {
       uint32_t r[32];
-      const uint32_t base = tmem_addr(tmem, (warp & 3) * 32, kColM + row_s * 80);
+      const uint32_t base = tmem_addr(tmem, (warp & 3) * 32, kColM);
       tmem_ld32(base, r);
       tmem_ld_wait();
 #pragma unroll
@@ -366,198 +451,126 @@ __global__ void __launch_bounds__(256, 1) em_fused_kernel(const EmFusedParams p)
 
     const bool last = (it == I - 1);
     if (last) {
-      // ---- nu partial = Z^T V^T, two passes over value-channel halves (Z must still be intact) --------
+      // ---- nu partial = Z^T V^T for this side: one pass, V images streamed through the ring ---------------
       __syncthreads();
       tc_fence_after_sync();
-      // V chunk (seq = half*4 + ch): [256 d][32 px] fp32.  A warp reads 4 rows x 128 B per instruction
-      // (lane -> row lane/8, pixels 4*(lane%8)..+3); 8 instructions cover its 32 rows.  Loads of chunk
-      // seq+1 are issued into registers before chunk seq is converted and staged (software prefetch).
-      const int px4 = (lane & 7) * 4;
-      const bool vec_ok = (HW & 3) == 0;
-      auto load_chunk = [&](int seq, float4 (&buf)[8]) {
-        const int half = seq >> 2, ch = seq & 3;
-        const int pxg = p0 + ch * 32 + px4;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int dl = warp * 32 + j * 4 + (lane >> 3);
-          const float* src = p.v + ((size_t)u * kCv + half * 256 + dl) * HW + pxg;
-          float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (vec_ok && pxg + 3 < HW) {
-            f = __ldg(reinterpret_cast<const float4*>(src));
-          } else {
-            if (pxg < HW) f.x = __ldg(src);
-            if (pxg + 1 < HW) f.y = __ldg(src + 1);
-            if (pxg + 2 < HW) f.z = __ldg(src + 2);
-            if (pxg + 3 < HW) f.w = __ldg(src + 3);
-          }
-          buf[j] = f;
-        }
-      };
-      auto stage_ptr = [&](int st) -> uint8_t* { return smem + (st ? kOffXH : kOffVS); };
-      auto store_chunk = [&](int st, const float4 (&buf)[8]) {
-        uint8_t* stage = stage_ptr(st);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int dl = warp * 32 + j * 4 + (lane >> 3);
-          __half h0, h1, h2, h3, l0, l1, l2, l3;
-          split_half(buf[j].x, h0, l0);
-          split_half(buf[j].y, h1, l1);
-          split_half(buf[j].z, h2, l2);
-          split_half(buf[j].w, h3, l3);
-          const __half2 ha = __halves2half2(h0, h1), hb = __halves2half2(h2, h3);
-          const __half2 la = __halves2half2(l0, l1), lb = __halves2half2(l2, l3);
-          uint2 ph, pl;
-          ph.x = *reinterpret_cast<const uint32_t*>(&ha);
-          ph.y = *reinterpret_cast<const uint32_t*>(&hb);
-          pl.x = *reinterpret_cast<const uint32_t*>(&la);
-          pl.y = *reinterpret_cast<const uint32_t*>(&lb);
-          const uint32_t off = (dl % 8) * 16 + (dl / 8) * 128 + (px4 / 8) * 4096 + (px4 % 8) * 2;
-          *reinterpret_cast<uint2*>(stage + off) = ph;
-          *reinterpret_cast<uint2*>(stage + kVPlane + off) = pl;
-        }
-      };
-      float4 vbuf[2][8];
-      load_chunk(0, vbuf[0]);
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-#pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
-          const int seq = half * 4 + ch;
-          const int st = seq & 1;
-          if (seq + 1 < 8) load_chunk(seq + 1, vbuf[(seq + 1) & 1]);
-          if (seq >= 2) SWEM_CTA_WAIT(&ms.bar_stage[st], ((seq / 2) - 1) & 1, ms.abort_flag);   // stage reuse: its MMAs retired
-          store_chunk(st, vbuf[seq & 1]);
-          fence_proxy_async_smem();
-          tc_fence_before_sync();
-          __syncthreads();
-          tc_fence_after_sync();
-          if (warp == 0) {
-            if (lane == 0) {
-            const uint32_t vb = sbase + (st ? kOffXH : kOffVS);
-#pragma unroll
-            for (int sd = 0; sd < 2; ++sd) {
-              const uint32_t za = sbase + kOffZ + sd * 16 * 2048;
-#pragma unroll
-              for (int kk = 0; kk < 2; ++kk) {
-                const uint64_t ad = make_sdesc(za + (ch * 2 + kk) * 2 * 128, /*lbo*/ 128, /*sbo*/ 2048);
-                const uint64_t al = make_sdesc(za + (kOffZL - kOffZ) + (ch * 2 + kk) * 2 * 128, /*lbo*/ 128, /*sbo*/ 2048);
-                const uint64_t bh = make_sdesc(vb + kk * 2 * 4096, /*lbo*/ 4096, /*sbo*/ 128);
-                const uint64_t bl = make_sdesc(vb + kVPlane + kk * 2 * 4096, /*lbo*/ 4096, /*sbo*/ 128);
-                mma_f16_ss(tmem + kColNu + sd * 256, ad, bh, idesc_nu, (ch | kk) ? 1u : 0u);   // z_hi v_hi
-                mma_f16_ss(tmem + kColNu + sd * 256, ad, bl, idesc_nu, 1u);                     // z_hi v_lo
-                mma_f16_ss(tmem + kColNu + sd * 256, al, bh, idesc_nu, 1u);                     // z_lo v_hi
-              }
-            }
-            mma_commit(&ms.bar_stage[st]);
-            if (ch == 3) mma_commit(&ms.bar_mma);
-            }
-            __syncwarp();
-          }
-        }
-        SWEM_CTA_WAIT(&ms.bar_mma, ph_mma, ms.abort_flag);
-        ph_mma ^= 1;
-        tc_fence_after_sync();
-        EM_STAMP();                  // nu pass GEMMs done
-        // drain: TMEM [side][128 l][256 d] -> smem [side][32 d][128 l] -> bulk reduce-add into acc_nu.  Two staging
-        // buffers (the dead X region and the first V stage, both idle now): round q only waits for the reads of q-2.
-        {
-          const int sd = warp >> 2, l = (warp & 3) * 32 + lane;
+      if (warp == 0) {
+        if (lane == 0) {
+          const uint8_t* src = vimg;
 #pragma unroll 1
-          for (int q = 0; q < 8; ++q) {
-            float* ns = reinterpret_cast<float*>(smem + ((q & 1) ? kOffVS : kOffNS));
-            if (q >= 2) {
-              if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-              __syncthreads();
-            }
-            {
-              uint32_t r[32];
-              tmem_ld32(tmem_addr(tmem, (warp & 3) * 32, kColNu + sd * 256 + q * 32), r);
-              tmem_ld_wait();
+          for (int seq = 0; seq < kChunks; ++seq) {
+            const int st = seq % kStages;
+            if (!mbar_wait(&ms.bar_full[st], (seq / kStages) & 1)) ms.abort_flag = 1;
+            tc_fence_after_sync();
+            const int h = seq >> 2, q = seq & 3;
+            const uint32_t vb = sbase + kOffVS + st * kStageBytes;
 #pragma unroll
-              for (int j = 0; j < 32; ++j) ns[(sd * 32 + j) * 128 + l] = __uint_as_float(r[j]);
+            for (int kk = 0; kk < 2; ++kk) {
+              const uint64_t ad = make_sdesc(sbase + kOffZ + (q * 2 + kk) * 2 * 128, /*lbo*/ 128, /*sbo*/ 2048);
+              const uint64_t al = make_sdesc(sbase + kOffZL + (q * 2 + kk) * 2 * 128, /*lbo*/ 128, /*sbo*/ 2048);
+              const uint64_t bh = make_sdesc(vb + kk * 2 * 4096, /*lbo*/ 4096, /*sbo*/ 128);
+              const uint64_t bl = make_sdesc(vb + kVPlane + kk * 2 * 4096, /*lbo*/ 4096, /*sbo*/ 128);
+              mma_f16_ss(tmem + kColNu + h * 256, ad, bh, idesc_nu, (q | kk) ? 1u : 0u);   // z_hi v_hi
+              mma_f16_ss(tmem + kColNu + h * 256, ad, bl, idesc_nu, 1u);                    // z_hi v_lo
+              mma_f16_ss(tmem + kColNu + h * 256, al, bh, idesc_nu, 1u);                    // z_lo v_hi
             }
-            fence_proxy_async_smem();
-            __syncthreads();
-            if (tid == 0) {
-#pragma unroll
-              for (int s2 = 0; s2 < 2; ++s2) {
-                float* dst = p.acc_nu + (((size_t)u * 2 + s2) * kCv + half * 256 + q * 32) * kL;
-                asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(dst),
-                             "r"(smem_u32(ns + s2 * 32 * 128)), "r"(32 * 128 * 4)
-                             : "memory");
-              }
-              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            mma_commit(&ms.bar_empty[st]);
+            if (seq >= 1 && seq + 2 < kChunks) {        // refill the stage chunk seq-1 used: its MMAs have had a chunk's time to retire
+              const int pst = (seq - 1) % kStages;
+              if (!mbar_wait(&ms.bar_empty[pst], ((seq - 1) / kStages) & 1)) ms.abort_flag = 1;
+              mbar_expect_tx(&ms.bar_full[pst], kStageBytes);
+              bulk_g2s(smem + kOffVS + pst * kStageBytes, src + (size_t)(seq + 2) * kStageBytes, kStageBytes, &ms.bar_full[pst]);
             }
           }
-          if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging may be reused now
+          mma_commit(&ms.bar_mma);
         }
-        tc_fence_before_sync();
-        __syncthreads();
-        tc_fence_after_sync();
-        EM_STAMP();                  // nu pass drained
+        __syncwarp();
       }
-      // drain the stage barriers' outstanding phases is unnecessary: the kernel ends after this phase
+      SWEM_CTA_WAIT(&ms.bar_mma, ph_mma, ms.abort_flag);
+      ph_mma ^= 1;
+      tc_fence_after_sync();
+      EM_STAMP();                    // nu GEMMs done
+      // drain: TMEM [128 l][512 d] -> smem [64 d][128 l] fp32 -> bulk reduce-add into acc_nu, 8 rounds, two staging
+      // buffers in the (now idle) V ring: round q only waits for the reads of round q-2.
+      {
+        const int l = (warp & 3) * 32 + lane, cg = warp >> 2;
+#pragma unroll 1
+        for (int q = 0; q < 8; ++q) {
+          float* ns = reinterpret_cast<float*>(smem + kOffVS + (q & 1) * kStageBytes);
+          if (q >= 2) {
+            if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            __syncthreads();
+          }
+          {
+            uint32_t r[32];
+            tmem_ld32(tmem_addr(tmem, (warp & 3) * 32, kColNu + q * 64 + cg * 32), r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) ns[(cg * 32 + j) * 128 + l] = __uint_as_float(r[j]);
+          }
+          fence_proxy_async_smem();
+          __syncthreads();
+          if (tid == 0) {
+            float* dst = p.acc_nu + ((size_t)gs * kCv + q * 64) * kL;
+            asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(dst),
+                         "r"(smem_u32(ns)), "r"(64 * 128 * 4)
+                         : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+        }
+        // full completion (not just .read): the arrival on this iteration's counter below also publishes the nu sums
+        if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+      }
+      tc_fence_before_sync();
+      __syncthreads();
+      tc_fence_after_sync();
+      EM_STAMP();                    // nu drained
     }
 
-    // ---- (4) cross-tile reduction of the M-step partial -----------------------------------------------
-    __syncthreads();                       // Z is dead now (all MMAs reading it have completed): P may alias it
-    {
-      float* P = reinterpret_cast<float*>(smem + kOffZ);
+    // ---- (4) cross-tile reduction of the M-step partial: fire-and-forget fp32 reductions straight from registers into
+    // the L2-resident accumulator [c][l] (coalesced over l), fence, arrive; after the last tile arrived every CTA
+    // reads the total back the same way.
+    float* acc = p.acc_k + ((size_t)(u * I + it) * 2 + sd) * ((kCk + 1) * kL);
+    unsigned* counter = p.counters + ((size_t)u * I + it) * 2 + sd;
+    float kpr[kCk];                   // prior row: loads fly during the cross-tile wait
+    if (row_thread) {
 #pragma unroll
-      for (int c = 0; c <= kCk; ++c) P[tid * kAccRow + c] = part[c];
+      for (int c = 0; c <= kCk; ++c) atomicAdd(acc + c * kL + tid, part[c]);
 #pragma unroll
-      for (int c = kCk + 1; c < kAccRow; ++c) P[tid * kAccRow + c] = 0.f;
-    }
-    fence_proxy_async_smem();
-    __syncthreads();
-    float* acc = p.acc_k + ((size_t)(u * I + it)) * (kSL * kAccRow);
-    unsigned* counter = p.counters + (size_t)u * (I + 1) + it;
-    // prior row of this thread's basis: issue the 64 loads now so they fly during the cross-tile wait
-    float kpr[kCk];
-#pragma unroll
-    for (int c = 0; c < kCk; ++c) kpr[c] = __ldg(kprior + (size_t)c * kL);
-    if (warp == 0) {
-      if (lane == 0) {
-      asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(acc),
-                   "r"(sbase + kOffZ), "r"(kAccBytes)
-                   : "memory");
-      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-      EM_STAMP();                    // partial reduce-added
+      for (int c = 0; c < kCk; ++c) kpr[c] = __ldg(kprior + (size_t)c * kL);
       __threadfence();
+    }
+    __syncthreads();
+    if (tid == 0) {
+      EM_STAMP();                    // partial reduce-added
       atomicAdd(counter, 1u);
       const bool arrived = wait_counter(counter, (unsigned)p.T);
       EM_STAMP();                    // all tiles arrived
       if (!arrived) ms.abort_flag = 1;
       __threadfence();
-      asm volatile("fence.proxy.async;" ::: "memory");
-      mbar_expect_tx(&ms.bar_tma, kAccBytes);
-      bulk_g2s(smem + kOffZ, acc, kAccBytes, &ms.bar_tma);
-      }
-      __syncwarp();
     }
-    SWEM_CTA_WAIT(&ms.bar_tma, ph_tma, ms.abort_flag);
-    ph_tma ^= 1;
+    __syncthreads();
     if (ms.abort_flag) {
       if (tid == 0) atomicExch(p.status, 1 + it);
       failed = true;
       break;
     }
-    EM_STAMP();                      // total loaded
-    // ---- (5) finalize row r = tid from the prior (reference :125-126) ------------------------------------
-    {
-      const float* P = reinterpret_cast<const float*>(smem + kOffZ) + tid * kAccRow;
+    // ---- (5) finalize row l = tid from the prior (reference :125-126) ---------------------------------------
+    if (row_thread) {
       constexpr float kInvZ = 1.f / kZScale;
-      const float zita_cur = zita_p + P[kCk] * kInvZ;
-      const float rz = 1.f / zita_cur;
       float kap[kCk];
 #pragma unroll
-      for (int c = 0; c < kCk; ++c) kap[c] = (zita_p * kpr[c] + P[c] * kInvZ) * rz;
+      for (int c = 0; c < kCk; ++c) kap[c] = __ldcg(acc + c * kL + tid);
+      const float zita_cur = zita_p + __ldcg(acc + kCk * kL + tid) * kInvZ;
+      const float rz = 1.f / zita_cur;
+#pragma unroll
+      for (int c = 0; c < kCk; ++c) kap[c] = (zita_p * kpr[c] + kap[c] * kInvZ) * rz;
       if (last) {
-        ms.zita[tid] = zita_cur;
+        ms.hsum[0][tid] = rz;         // (dead E-step scratch) 1 / zita and the prior zita of row l, for the nu slice below
+        ms.hsum[1][tid] = zita_p;
         if (tile == 0) {
-          p.zita[((size_t)u * 2 + row_s) * kL + row_l] = zita_cur;
-          float* kout = p.kappa + (((size_t)u * 2 + row_s) * kCk) * kL + row_l;
+          p.zita[(size_t)gs * kL + tid] = zita_cur;
+          float* kout = p.kappa + ((size_t)gs * kCk) * kL + tid;
 #pragma unroll
           for (int c = 0; c < kCk; ++c) kout[(size_t)c * kL] = kap[c];
         }
@@ -567,37 +580,36 @@ __global__ void __launch_bounds__(256, 1) em_fused_kernel(const EmFusedParams p)
     }
     __syncthreads();
     EM_STAMP();                      // finalize done
+    if (last) {
+      // ---- nu = (zita_ nu_ + sum / 2^14) / zita (reference :164-165) for this tile's slice of value channels: the counter
+      // wait above ordered every tile's nu reduce-adds (completed before its arrival) before these loads.
+      const int dper = (kCv + p.T - 1) / p.T;
+      const int d0 = tile * dper, d1 = min(kCv, d0 + dper);
+      constexpr float kInvZ = 1.f / kZScale;
+      const float4* acc4 = reinterpret_cast<const float4*>(p.acc_nu + (size_t)gs * kCv * kL);
+      const float4* pri4 = reinterpret_cast<const float4*>(p.nu_prior + (size_t)gs * kCv * kL);
+      float4* out4 = reinterpret_cast<float4*>(p.nu + (size_t)gs * kCv * kL);
+      for (int i = d0 * (kL / 4) + tid; i < d1 * (kL / 4); i += 256) {
+        const int l = (i % (kL / 4)) * 4;
+        const float4 a = __ldcg(acc4 + i);
+        const float4 pr = __ldg(pri4 + i);
+        float4 o;
+        o.x = (ms.hsum[1][l + 0] * pr.x + a.x * kInvZ) * ms.hsum[0][l + 0];
+        o.y = (ms.hsum[1][l + 1] * pr.y + a.y * kInvZ) * ms.hsum[0][l + 1];
+        o.z = (ms.hsum[1][l + 2] * pr.z + a.z * kInvZ) * ms.hsum[0][l + 2];
+        o.w = (ms.hsum[1][l + 3] * pr.w + a.w * kInvZ) * ms.hsum[0][l + 3];
+        out4[i] = o;
+      }
+      EM_STAMP();                    // nu slice written
+    }
   }
 
-  // nu = (zita_ nu_ + acc_nu / 2^14) / zita (reference :164-165) is applied by nu_finalize_kernel, launched right
-  // after this kernel: stream order replaces a third cross-CTA wait here.
   tc_fence_before_sync();
   __syncthreads();
-  EM_STAMP();                        // done
+  EM_STAMP();
   if (p.prof != nullptr && blockIdx.x == 0 && tid == 0) p.prof[0] = n_stamp;
   if (warp == 0) tmem_dealloc(tmem, 512);
-  if (failed || ms.abort_flag) __trap();   // surface a protocol time-out as a CUDA error, never as silent garbage
-}
-
-// nu[g][d][l] = (zita_prior[g][l] * nu_prior[g][d][l] + acc_nu[g][d][l] / 2^14) / zita[g][l],  g = (b, n, s)
-__global__ void nu_finalize_kernel(const float* __restrict__ acc_nu, const float* __restrict__ nu_prior,
-                                   const float* __restrict__ zita_prior, const float* __restrict__ zita,
-                                   float* __restrict__ nu, int G) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;          // float4 index
-  if (i >= G * em::kCv * em::kL / 4) return;
-  const int l4 = i % (em::kL / 4);
-  const int g = i / (em::kCv * em::kL / 4);
-  const float4 a = __ldcg(reinterpret_cast<const float4*>(acc_nu) + i);
-  const float4 pr = __ldg(reinterpret_cast<const float4*>(nu_prior) + i);
-  const float4 zp = __ldg(reinterpret_cast<const float4*>(zita_prior) + g * (em::kL / 4) + l4);
-  const float4 z = __ldg(reinterpret_cast<const float4*>(zita) + g * (em::kL / 4) + l4);
-  constexpr float k = 1.f / em::kZScale;
-  float4 o;
-  o.x = (zp.x * pr.x + a.x * k) / z.x;
-  o.y = (zp.y * pr.y + a.y * k) / z.y;
-  o.z = (zp.z * pr.z + a.z * k) / z.z;
-  o.w = (zp.w * pr.w + a.w * k) / z.w;
-  reinterpret_cast<float4*>(nu)[i] = o;
+  if (failed || ms.abort_flag) __trap();
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -607,87 +619,90 @@ static long long* g_prof = nullptr;
 void set_profile_buffer(void* dev) { g_prof = static_cast<long long*>(dev); }
 long long* get_profile_buffer() { return g_prof; }
 
-static int sm_count() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+static int max_pairs_resident() {
+  static int n = -1;
+  if (n < 0) {
+    cudaFuncSetAttribute(em_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)em::kSmemBytes);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2, 1, 1);
+    cfg.blockDim = dim3(256, 1, 1);
+    cfg.dynamicSmemBytes = em::kSmemBytes;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int clusters = 0;
+    if (cudaOccupancyMaxActiveClusters(&clusters, em_pair_kernel, &cfg) != cudaSuccess || clusters <= 0) {
+      cudaGetLastError();
+      int dev = 0, sms = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      clusters = sms / 2 - 2;                          // conservative guess
+    }
+    n = clusters;
   }
   return n;
 }
 
-// SWEM_EM_KERNEL=v1 keeps the first-generation kernel of this file (one CTA per tile, both sides); the default is the
-// pair kernel of fused_em2.cu.
-static bool use_v1() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("SWEM_EM_KERNEL");
-    v = (e != nullptr && e[0] == 'v' && e[1] == '1') ? 1 : 0;
-  }
-  return v == 1;
-}
-
-int launch_nu_finalize(const float* acc_nu, const float* nu_prior, const float* zita_prior, const float* zita, float* nu,
-                       int G, cudaStream_t st) {
-  const int n4 = G * em::kCv * em::kL / 4;
-  nu_finalize_kernel<<<(n4 + 255) / 256, 256, 0, st>>>(acc_nu, nu_prior, zita_prior, zita, nu, G);
-  SWEM_LAUNCH_CHECK();
-  return SWEM_OK;
-}
-
 bool fused_em_supported(const SwemDims& d) {
-  if (!use_v1()) return fused_em2_supported(d);
   if (d.Ck != em::kCk || d.L != em::kL || d.Cv != em::kCv || d.n_iters < 1 || d.n_iters > 16) return false;
   const int T = (d.HW + em::kTP - 1) / em::kTP;
-  return T >= 1 && T <= 128;
+  return T >= 1 && T <= 64;            // all pairs of one unit must be co-resident (74 pairs on a B200)
 }
 
 size_t fused_em_workspace(const SwemDims& d) {
-  if (!use_v1()) return fused_em2_workspace(d);
   const size_t U = (size_t)d.B * d.N;
+  const size_t T = (d.HW + em::kTP - 1) / em::kTP;
   size_t bytes = 0;
-  bytes += align_up(U * d.n_iters * em::kAccBytes, 256);
+  bytes += align_up(U * d.n_iters * 2 * em::kAccBytes, 256);
   bytes += align_up(U * 2 * em::kCv * em::kL * 4, 256);
-  bytes += align_up(U * (d.n_iters + 1) * 4 + 4, 256);
+  bytes += align_up(U * d.n_iters * 2 * 4 + 4, 256);
+  bytes += align_up(U * T * em::kChunks * em::kStageBytes, 256);
   return bytes + 256;
 }
 
 int fused_em_forward(const SwemEmArgs& a, cudaStream_t st) {
-  if (!use_v1()) return fused_em2_forward(a, st);
   const SwemDims& d = a.dims;
   const int U = d.B * d.N;
   const int T = (d.HW + em::kTP - 1) / em::kTP;
   Arena ws(a.workspace);
-  float* acc_k = ws.take<float>((size_t)U * d.n_iters * em::kSL * em::kAccRow);
+  float* acc_k = ws.take<float>((size_t)U * d.n_iters * 2 * (em::kAccBytes / 4));
   float* acc_nu = ws.take<float>((size_t)U * 2 * em::kCv * em::kL);
-  unsigned* counters = ws.take<unsigned>((size_t)U * (d.n_iters + 1) + 1);
-  int* status = reinterpret_cast<int*>(counters + (size_t)U * (d.n_iters + 1));
+  unsigned* counters = ws.take<unsigned>((size_t)U * d.n_iters * 2 + 1);
+  int* status = reinterpret_cast<int*>(counters + (size_t)U * d.n_iters * 2);
   SWEM_CUDA(cudaMemsetAsync(a.workspace, 0, ws.off, st));
   count_launch();
+  uint8_t* vblob = ws.take<uint8_t>((size_t)U * T * em::kChunks * em::kStageBytes);
 
   static bool attr_set = false;
   if (!attr_set) {
-    SWEM_CUDA(cudaFuncSetAttribute(em_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)em::kSmemBytes));
+    SWEM_CUDA(cudaFuncSetAttribute(em_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)em::kSmemBytes));
     attr_set = true;
   }
-  EmFusedParams p{};
+  EmPairParams p{};
   p.x = a.x; p.v = a.v; p.masks = a.masks;
   p.kappa_prior = a.kappa_prior; p.nu_prior = a.nu_prior; p.zita_prior = a.zita_prior;
   p.kappa = a.kappa; p.nu = a.nu; p.zita = a.zita; p.z_last = a.z_last;
+  p.vblob = vblob;
   p.acc_k = acc_k; p.acc_nu = acc_nu; p.counters = counters; p.status = status;
   p.N = d.N; p.HW = d.HW; p.T = T; p.n_iters = d.n_iters;
   p.c1s = kLog2e / (d.tau * em::kKScale);
-  p.prof = g_prof;
-  // all CTAs of a launch spin on each other: keep every launch co-resident (<= 1 CTA per SM)
-  const int units_per_launch = sm_count() / T > 0 ? sm_count() / T : 1;
-  for (int u0 = 0; u0 < U; u0 += units_per_launch) {
-    const int nu = (U - u0 < units_per_launch) ? (U - u0) : units_per_launch;
+  p.prof = get_profile_buffer();
+  // all CTAs of a launch spin on each other: every launch must be co-resident (1 CTA per SM, 2-CTA clusters);
+  // units that do not fit are spread evenly over the fewest launches
+  const int upl_max = max_pairs_resident() / T > 0 ? max_pairs_resident() / T : 1;
+  const int n_launch = (U + upl_max - 1) / upl_max;
+  const int upl = (U + n_launch - 1) / n_launch;
+  for (int u0 = 0; u0 < U; u0 += upl) {
+    const int nu = (U - u0 < upl) ? (U - u0) : upl;
     p.u0 = u0;
-    em_fused_kernel<<<nu * T, 256, em::kSmemBytes, st>>>(p);
+    em_pair_kernel<<<nu * T * 2, 256, em::kSmemBytes, st>>>(p);
     SWEM_LAUNCH_CHECK();
   }
-  return launch_nu_finalize(acc_nu, a.nu_prior, a.zita_prior, a.zita, a.nu, U * 2, st);
+  return SWEM_OK;
 }
 
 }  // namespace swem

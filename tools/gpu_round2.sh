@@ -5,9 +5,7 @@ rm -f gpurun_out/parity_report.txt
 timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "fused or reproducible or free_running or engine or ytvos" 2>&1 | tail -15 > gpurun_out/r1_tests_v2.log
 tail -5 gpurun_out/r1_tests_v2.log
 timeout 300 python tools/profile_phases.py > gpurun_out/r1_phases_v2.log 2>&1
-SWEM_EM_KERNEL=v1 timeout 300 python tools/profile_phases.py > gpurun_out/r1_phases_v1.log 2>&1
 grep -v "^  " gpurun_out/r1_phases_v2.log; head -40 gpurun_out/r1_phases_v2.log
-grep "memorize" gpurun_out/r1_phases_v1.log
 timeout 600 python bench.py --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/r1_bench_v2.log 2>&1
 python - <<'PY'
 import json

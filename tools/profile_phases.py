@@ -30,13 +30,9 @@ def main(N=5, H=30, W=54, I=4, reps=50):
         for it in range(I):
             names += [f'it{it} logits GEMM', f'it{it} epilogue', f'it{it} M GEMM']
             if it == I - 1:
-                names += (['nu pass0 GEMM', 'nu pass0 drain', 'nu pass1 GEMM', 'nu pass1 drain'] if os.environ.get('SWEM_EM_KERNEL') == 'v1'
-                          else ['nu GEMM', 'nu drain'])
-            names += ([f'it{it} reduce-add', f'it{it} wait tiles', f'it{it} load total', f'it{it} finalize'] if os.environ.get('SWEM_EM_KERNEL') == 'v1'
-                      else [f'it{it} reduce-add', f'it{it} wait tiles', f'it{it} finalize'])
-        if os.environ.get('SWEM_EM_KERNEL') != 'v1':
-            names += ['nu slice']
-        names += ['exit']
+                names += ['nu GEMM', 'nu drain']
+            names += [f'it{it} reduce-add', f'it{it} wait tiles', f'it{it} finalize']
+        names += ['nu slice', 'exit']
         for k in range(1, n):
             print(f'  {names[k-1] if k-1 < len(names) else "?":24s} {(t[k]-t[k-1])/1e3:8.2f} us')
         _lib.check(lib.swem_set_profile_buffer(buf.data_ptr(), buf.numel() * 8), 'set_profile')
