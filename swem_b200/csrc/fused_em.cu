@@ -17,8 +17,9 @@
 //     one (max, sum) pair per pixel exchanged through distributed shared memory and a cluster barrier;
 //   * nu = Z^T V^T needs a single pass (its [128 bases][512 channels] accumulator is exactly the 512 TMEM
 //     columns); during set-up each CTA converts half of its tile's V to fp16 hi/lo operand images in global
-//     memory (L2-resident), and after the last E-step both CTAs stream all of them back with plain bulk-async
-//     copies (3-stage ring issued by one thread, first stages prefetched ~40 us ahead) -- no register staging
+//     memory (L2-resident; one chunk in set-up, the others by warps 4-7 in the shadow of the cross-tile
+//     reductions), and after the last E-step both CTAs stream all of them back with plain bulk-async copies
+//     (3-stage ring: one thread issues the MMAs, another refills stages as they retire) -- no register staging
 //     on the critical path, and the conversion is shared by the pair;
 //   * nu is normalised in this kernel: the last M-step barrier also covers the nu reduce-adds, after it every
 //     CTA finalises a slice of value channels (no separate kernel, no third cross-tile wait).
@@ -46,8 +47,8 @@ constexpr float kKScale = 256.f;
 constexpr float kZScale = 16384.f;
 constexpr uint32_t kStageBytes = 32768;            // one V operand image: [256 d][32 px] fp16, hi plane then lo plane
 constexpr uint32_t kVPlane = 16384;
-constexpr int kStages = 3;
-constexpr int kChunks = 8;                         // per tile: 2 channel halves x 4 pixel quarters
+constexpr int kChunks = 8;                         // images per tile: 2 channel halves x 4 pixel quarters
+constexpr int kStages = 3;                         // bulk-copy ring, one image per stage
 
 // ---- shared memory map (bytes) ---------------------------------------------------------------
 // XH : [c 0..79][p] : byte = (c%8)*16 + (c/8)*2048 + (p/8)*128 + (p%8)*2      (row 64 = ones, 65..79 = 0)
@@ -130,50 +131,42 @@ __device__ __forceinline__ void st_cluster_f2(uint32_t addr, float a, float b) {
   } while (0)
 
 // ------------------------------------------------------------------------------------------------------
-// V -> fp16 hi/lo operand images, done by the whole CTA for the 4 chunks (pixel quarters) of channel half h:
-// each chunk is [256 d][32 px] fp32 in, a 32 KB image out (pixels past HW are zero).
+// V -> fp16 hi/lo operand image of ONE chunk ([256 d][32 px] fp32 in, 32 KB out; pixels past HW are zero), done by
+// NW warps (`w` = warp index inside the group).  All loads of a thread are in flight before the first conversion.
 // ------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void convert_v_half(const float* __restrict__ vsrc /* [256][HW] rows of this half */,
-                                               uint8_t* __restrict__ images /* 4 x 32 KB */, int p0, int HW, int warp, int lane) {
+template <int NW>
+__device__ __forceinline__ void convert_v_chunk(const float* __restrict__ vsrc /* [256][HW] rows of this channel half */,
+                                                uint8_t* __restrict__ image, int px_base, int HW, int w, int lane) {
   using namespace em;
+  constexpr int J = 256 / (NW * 8);                     // rows of 8 channels per warp
   const int g = lane & 3;                               // group of 8 pixels
-  const bool aligned = (HW & 3) == 0;
-  auto load = [&](int q, float (&f)[4][8]) {
-    const int px0 = p0 + q * 32 + g * 8;
+  const int px0 = px_base + g * 8;
+  const bool vec = ((HW & 3) == 0) && (px0 + 7 < HW);
+  float f[J][8];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int d = warp * 32 + j * 8 + (lane >> 2);    // 0..255
-      const float* src = vsrc + (size_t)d * HW + px0;
-      if (aligned && px0 + 7 < HW) {
-        const float4 a = __ldg(reinterpret_cast<const float4*>(src));
-        const float4 b = __ldg(reinterpret_cast<const float4*>(src) + 1);
-        f[j][0] = a.x; f[j][1] = a.y; f[j][2] = a.z; f[j][3] = a.w; f[j][4] = b.x; f[j][5] = b.y; f[j][6] = b.z; f[j][7] = b.w;
-      } else {
+  for (int j = 0; j < J; ++j) {
+    const int d = w * (J * 8) + j * 8 + (lane >> 2);    // 0..255
+    const float* src = vsrc + (size_t)d * HW + px0;
+    if (vec) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(src));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(src) + 1);
+      f[j][0] = a.x; f[j][1] = a.y; f[j][2] = a.z; f[j][3] = a.w; f[j][4] = b.x; f[j][5] = b.y; f[j][6] = b.z; f[j][7] = b.w;
+    } else {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) f[j][e] = (px0 + e < HW) ? __ldg(src + e) : 0.f;
-      }
+      for (int e = 0; e < 8; ++e) f[j][e] = (px0 + e < HW) ? __ldg(src + e) : 0.f;
     }
-  };
-  auto store = [&](int q, const float (&f)[4][8]) {
-    uint8_t* out = images + (size_t)q * kStageBytes;
+  }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int d = warp * 32 + j * 8 + (lane >> 2);
-      __align__(16) __half hi[8];
-      __align__(16) __half lo[8];
+  for (int j = 0; j < J; ++j) {
+    const int d = w * (J * 8) + j * 8 + (lane >> 2);
+    __align__(16) __half hi[8];
+    __align__(16) __half lo[8];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) split_half(f[j][e], hi[e], lo[e]);
-      const uint32_t off = (d % 8) * 16 + (d / 8) * 128 + g * 4096;
-      *reinterpret_cast<uint4*>(out + off) = *reinterpret_cast<uint4*>(hi);
-      *reinterpret_cast<uint4*>(out + kVPlane + off) = *reinterpret_cast<uint4*>(lo);
-    }
-  };
-  // all 32 loads of a thread (128 KB per CTA) are in flight before the first conversion: one memory round trip
-  float buf[4][4][8];
-#pragma unroll
-  for (int q = 0; q < 4; ++q) load(q, buf[q]);
-#pragma unroll
-  for (int q = 0; q < 4; ++q) store(q, buf[q]);
+    for (int e = 0; e < 8; ++e) split_half(f[j][e], hi[e], lo[e]);
+    const uint32_t off = (d % 8) * 16 + (d / 8) * 128 + g * 4096;
+    *reinterpret_cast<uint4*>(image + off) = *reinterpret_cast<uint4*>(hi);
+    *reinterpret_cast<uint4*>(image + kVPlane + off) = *reinterpret_cast<uint4*>(lo);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -205,10 +198,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) em_pair_kern
     ms.abort_flag = 0;
     fence_mbar_init();
   }
-  // V operand images: this CTA converts channel half `sd` of the tile (the peer converts the other half); both read
-  // all 8 images back through the bulk-copy ring after the last E-step.
+  // V operand images: this CTA converts channel half `sd` of the tile = 4 chunks (the peer converts the other half); both
+  // read all 8 images back through the bulk-copy ring after the last E-step.  Only as many chunks as cannot be hidden
+  // later are converted here by the whole CTA; the rest is done one per iteration by warps 4-7 while the row threads
+  // (warps 0-3) run the cross-tile reduction and the finalize -- the conversion is HBM-bound and would otherwise be
+  // 6 us of exposed set-up.  The W-step cluster barrier of the last iteration publishes all of them to the pair.
   uint8_t* const vimg = p.vblob + ((size_t)u * p.T + tile) * kChunks * kStageBytes;
-  convert_v_half(p.v + ((size_t)u * kCv + sd * 256) * HW, vimg + (size_t)sd * 4 * kStageBytes, p0, HW, warp, lane);
+  const float* const vhalf = p.v + ((size_t)u * kCv + sd * 256) * HW;
+  uint8_t* const my_images = vimg + (size_t)sd * 4 * kStageBytes;
+  int chunks_done = (I >= 4) ? 1 : 5 - I;               // I = 1 -> 4 (no later barrier), 2 -> 3, 3 -> 2, >= 4 -> 1
+  for (int q = 0; q < chunks_done; ++q) convert_v_chunk<8>(vhalf, my_images + (size_t)q * kStageBytes, p0 + q * 32, HW, warp, lane);
   __threadfence();
   asm volatile("fence.proxy.async;" ::: "memory");     // generic-proxy global stores -> visible to the bulk-copy (async proxy) reads
   // rows: thread tid < 128 <-> basis l = tid of side sd (finalize steps)
@@ -285,13 +284,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) em_pair_kern
   cluster_arrive();                   // both CTAs of the pair are running before any remote shared-memory store,
   cluster_wait();                     // and both halves of the tile's V images are written
   tc_fence_after_sync();
-  if (tid == 0) {                     // the first kStages images start flying now; they are consumed after the last E-step
+  auto load_image = [&](int k) {       // ring stage k % kStages <- image k of the tile
+    const int st = k % kStages;
+    mbar_expect_tx(&ms.bar_full[st], kStageBytes);
+    bulk_g2s(smem + kOffVS + st * kStageBytes, vimg + (size_t)k * kStageBytes, kStageBytes, &ms.bar_full[st]);
+  };
+  auto prefetch_images = [&]() {       // the first kStages images start flying; they are consumed after the last E-step
     asm volatile("fence.proxy.async;" ::: "memory");
-    for (int k = 0; k < kStages; ++k) {
-      mbar_expect_tx(&ms.bar_full[k], kStageBytes);
-      bulk_g2s(smem + kOffVS + k * kStageBytes, vimg + (size_t)k * kStageBytes, kStageBytes, &ms.bar_full[k]);
-    }
-  }
+    for (int k = 0; k < kStages; ++k) load_image(k);
+  };
+  if (I == 1 && tid == 0) prefetch_images();
   const uint32_t tmem = ms.tmem_base;
   uint32_t ph_mma = 0;
   bool failed = false;
@@ -354,30 +356,33 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) em_pair_kern
       // W-step (reference :93-110) works on t = a * inv_nx with the max over BOTH sides; each side sums its exps
       // against its own max and the pair rescales after the exchange: exp(t - M) = exp(t - m_s) * exp(m_s - M).
       const float cw = ms.inv_nx[px] * p.c1s;
-      float e = 0.f, sum = 0.f;
-      if (do_w) {
+      const int par = it & 1;
+      if (do_w) {                                       // W-step sums first: the exchange flies while the E-step exps run
+        float e = 0.f;
 #pragma unroll
         for (int i = 0; i < 64; ++i) e += fast_exp2((a[i] - mx) * cw);
-      }
-#pragma unroll
-      for (int i = 0; i < 64; ++i) {
-        a[i] = fast_exp2((a[i] - mx) * p.c1s);
-        sum += a[i];
-      }
-      ms.hsum[hb][px] = sum;
-      ms.hew[hb][px] = e;
-      __syncthreads();
-      sum = ms.hsum[0][px] + ms.hsum[1][px];
-      float w = ms.mask[px];
-      if (do_w) {
-        const int par = it & 1;
+        ms.hew[hb][px] = e;
+        __syncthreads();
         if (hb == 0) {
           const float es = ms.hew[0][px] + ms.hew[1][px];
           ms.mbox[par][sd][px] = make_float2(mx, es);
           st_cluster_f2(peer_mbox + (uint32_t)(((par * 2 + sd) * kTP + px) * sizeof(float2)), mx, es);
         }
         cluster_arrive();
+      }
+      float sum = 0.f;
+#pragma unroll
+      for (int i = 0; i < 64; ++i) {
+        a[i] = fast_exp2((a[i] - mx) * p.c1s);
+        sum += a[i];
+      }
+      ms.hsum[hb][px] = sum;
+      __syncthreads();
+      sum = ms.hsum[0][px] + ms.hsum[1][px];
+      float w = ms.mask[px];
+      if (do_w) {
         cluster_wait();
+        if (it == I - 1 && tid == 0) prefetch_images();  // every chunk of the pair was converted before this barrier
         const float2 m0 = ms.mbox[par][0][px], m1 = ms.mbox[par][1][px];
         const float gm = fmaxf(m0.x, m1.x);
         const float e0 = m0.y * fast_exp2((m0.x - gm) * cw), e1 = m1.y * fast_exp2((m1.x - gm) * cw);
@@ -456,7 +461,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) em_pair_kern
       tc_fence_after_sync();
       if (warp == 0) {
         if (lane == 0) {
-          const uint8_t* src = vimg;
 #pragma unroll 1
           for (int seq = 0; seq < kChunks; ++seq) {
             const int st = seq % kStages;
@@ -474,15 +478,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) em_pair_kern
               mma_f16_ss(tmem + kColNu + h * 256, ad, bl, idesc_nu, 1u);                    // z_hi v_lo
               mma_f16_ss(tmem + kColNu + h * 256, al, bh, idesc_nu, 1u);                    // z_lo v_hi
             }
-            mma_commit(&ms.bar_empty[st]);
-            if (seq >= 1 && seq + 2 < kChunks) {        // refill the stage chunk seq-1 used: its MMAs have had a chunk's time to retire
-              const int pst = (seq - 1) % kStages;
-              if (!mbar_wait(&ms.bar_empty[pst], ((seq - 1) / kStages) & 1)) ms.abort_flag = 1;
-              mbar_expect_tx(&ms.bar_full[pst], kStageBytes);
-              bulk_g2s(smem + kOffVS + pst * kStageBytes, src + (size_t)(seq + 2) * kStageBytes, kStageBytes, &ms.bar_full[pst]);
-            }
+            mma_commit(&ms.bar_empty[st]);              // -> the producer thread (warp 1) refills this stage
           }
           mma_commit(&ms.bar_mma);
+        }
+        __syncwarp();
+      } else if (warp == 1) {
+        if (lane == 0) {              // producer: refill a stage as soon as the MMAs that read it have retired
+#pragma unroll 1
+          for (int k = kStages; k < kChunks; ++k) {
+            const int st = k % kStages;
+            if (!mbar_wait(&ms.bar_empty[st], ((k - kStages) / kStages) & 1)) ms.abort_flag = 1;
+            load_image(k);
+          }
         }
         __syncwarp();
       }
@@ -533,52 +541,60 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) em_pair_kern
     float* acc = p.acc_k + ((size_t)(u * I + it) * 2 + sd) * ((kCk + 1) * kL);
     unsigned* counter = p.counters + ((size_t)u * I + it) * 2 + sd;
     float kpr[kCk];                   // prior row: loads fly during the cross-tile wait
-    if (row_thread) {
+    if (row_thread) {                 // warps 0-3; they synchronise among themselves on named barrier 1
 #pragma unroll
       for (int c = 0; c <= kCk; ++c) atomicAdd(acc + c * kL + tid, part[c]);
+      __threadfence();                // (the prior-row loads come after it: a fence waits for every earlier access)
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (tid == 0) {
+        EM_STAMP();                   // partial reduce-added
+        atomicAdd(counter, 1u);
+      }
 #pragma unroll
       for (int c = 0; c < kCk; ++c) kpr[c] = __ldg(kprior + (size_t)c * kL);
+      if (tid == 0) {
+        const bool arrived = wait_counter(counter, (unsigned)p.T);
+        EM_STAMP();                   // all tiles arrived
+        if (!arrived) ms.abort_flag = 1;
+        __threadfence();
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      // ---- (5) finalize row l = tid from the prior (reference :125-126) -------------------------------------
+      if (!ms.abort_flag) {
+        constexpr float kInvZ = 1.f / kZScale;
+        float kap[kCk];
+#pragma unroll
+        for (int c = 0; c < kCk; ++c) kap[c] = __ldcg(acc + c * kL + tid);
+        const float zita_cur = zita_p + __ldcg(acc + kCk * kL + tid) * kInvZ;
+        const float rz = 1.f / zita_cur;
+#pragma unroll
+        for (int c = 0; c < kCk; ++c) kap[c] = (zita_p * kpr[c] + kap[c] * kInvZ) * rz;
+        if (last) {
+          ms.hsum[0][tid] = rz;       // (dead E-step scratch) 1 / zita and the prior zita of row l, for the nu slice below
+          ms.hsum[1][tid] = zita_p;
+          if (tile == 0) {
+            p.zita[(size_t)gs * kL + tid] = zita_cur;
+            float* kout = p.kappa + ((size_t)gs * kCk) * kL + tid;
+#pragma unroll
+            for (int c = 0; c < kCk; ++c) kout[(size_t)c * kL] = kap[c];
+          }
+        } else {
+          stage_khat(kap);
+        }
+      }
+    } else if (chunks_done < 4 && !last) {
+      // warps 4-7: one more V chunk, hidden behind the row threads' reduction, cross-tile wait and finalize
+      convert_v_chunk<4>(vhalf, my_images + (size_t)chunks_done * kStageBytes, p0 + chunks_done * 32, HW, warp - 4, lane);
       __threadfence();
+      asm volatile("fence.proxy.async;" ::: "memory");
     }
-    __syncthreads();
-    if (tid == 0) {
-      EM_STAMP();                    // partial reduce-added
-      atomicAdd(counter, 1u);
-      const bool arrived = wait_counter(counter, (unsigned)p.T);
-      EM_STAMP();                    // all tiles arrived
-      if (!arrived) ms.abort_flag = 1;
-      __threadfence();
-    }
+    if (chunks_done < 4 && !last) ++chunks_done;
     __syncthreads();
     if (ms.abort_flag) {
       if (tid == 0) atomicExch(p.status, 1 + it);
       failed = true;
       break;
     }
-    // ---- (5) finalize row l = tid from the prior (reference :125-126) ---------------------------------------
-    if (row_thread) {
-      constexpr float kInvZ = 1.f / kZScale;
-      float kap[kCk];
-#pragma unroll
-      for (int c = 0; c < kCk; ++c) kap[c] = __ldcg(acc + c * kL + tid);
-      const float zita_cur = zita_p + __ldcg(acc + kCk * kL + tid) * kInvZ;
-      const float rz = 1.f / zita_cur;
-#pragma unroll
-      for (int c = 0; c < kCk; ++c) kap[c] = (zita_p * kpr[c] + kap[c] * kInvZ) * rz;
-      if (last) {
-        ms.hsum[0][tid] = rz;         // (dead E-step scratch) 1 / zita and the prior zita of row l, for the nu slice below
-        ms.hsum[1][tid] = zita_p;
-        if (tile == 0) {
-          p.zita[(size_t)gs * kL + tid] = zita_cur;
-          float* kout = p.kappa + ((size_t)gs * kCk) * kL + tid;
-#pragma unroll
-          for (int c = 0; c < kCk; ++c) kout[(size_t)c * kL] = kap[c];
-        }
-      } else {
-        stage_khat(kap);
-      }
-    }
-    __syncthreads();
     EM_STAMP();                      // finalize done
     if (last) {
       // ---- nu = (zita_ nu_ + sum / 2^14) / zita (reference :164-165) for this tile's slice of value channels: the counter
