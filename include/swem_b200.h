@@ -12,6 +12,8 @@
  *                            + perm_inv_feat :198-208 + the l2norms of matching :282-283
  *                            + the concat placement of matching :291
  *   swem_em_masks         <- mask prep of SWEM.memorize  methods/SWEM/swem.py:80-84
+ *   swem_upsample_add     <- UpsampleBlock.forward      methods/basic_modules/networks.py:192-196
+ *   swem_bias_add_act     <- residual tail of ResBlock.forward  networks.py:25-32
  *   swem_decode_tail      <- final up-sampling of Decoder.forward (methods/basic_modules/networks.py:214-215)
  *                            + SWEM.decode / aggregate      methods/SWEM/swem.py:92-116
  *
@@ -145,6 +147,19 @@ int swem_em_masks(const int64_t* hard, int32_t Hm, int32_t Wm,
  * logits_out, prob_out: [B, N+1, H, W].  N <= 16.                                                    */
 int swem_decode_tail(const float* logits_lr, int32_t B, int32_t N, int32_t Hl, int32_t Wl, int32_t H, int32_t W,
                      const float* valid_obj, float* logits_out, float* prob_out, void* stream);
+
+/* ---- decoder glue, channels-last (NHWC) fp32: UpsampleBlock.forward (networks.py:192-196) and the residual tail of
+ * ResBlock.forward (:25-32) as single passes.
+ *   swem_upsample_add : x[bn] = skip[bn / n] + bilinear(lo_a[bn] (+ lo_b[bn])) (+ bias[c]);  x_relu = relu(x) (optional)
+ *                       lo_a, lo_b: [BN, h, w, C]; skip: [BN / n, H, W, C]; x, x_relu: [BN, H, W, C]; bilinear with
+ *                       align_corners = false (ATen index arithmetic); `bias` carries the per-channel biases of the
+ *                       convolutions that produced lo_a / lo_b / skip (interpolation reproduces constants).
+ *   swem_bias_add_act : out = act(a (+ b) (+ bias[c])) over `pixels` x C, act = relu or identity.
+ * C must be a multiple of 4; optional pointers may be NULL.                                                       */
+int swem_upsample_add(const float* lo_a, const float* lo_b, const float* bias, const float* skip, int32_t BN, int32_t n,
+                      int32_t h, int32_t w, int32_t H, int32_t W, int32_t C, float* x, float* x_relu, void* stream);
+int swem_bias_add_act(const float* a, const float* b, const float* bias, int64_t pixels, int32_t C, int32_t relu,
+                      float* out, void* stream);
 
 /* ---- misc ------------------------------------------------------------------------------------ */
 int         swem_abi_version(void);          /* == SWEM_B200_ABI_VERSION                          */

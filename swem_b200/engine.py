@@ -19,7 +19,10 @@ inference (``eval()`` + ``no_grad`` only):
       concat ``[mem_out | qv | S]`` (``modules.py:291``) convolved once per frame; the readout kernels
       write ``mem_out`` / ``S`` into a 640-channel buffer, the ``qv`` copy disappears;
     - decoder ``skip_conv`` of ``s8`` / ``s4`` (``networks.py:186-203``) computed once per frame instead
-      of once per object, and the N-fold ``expand`` copies of ``s8`` / ``s4`` (``swem.py:93-94``) dropped.
+      of once per object, and the N-fold ``expand`` copies of ``s8`` / ``s4`` (``swem.py:93-94``) dropped;
+* decoder glue as single passes (``swem_upsample_add`` / ``swem_bias_add_act`` of the C ABI, NHWC): bias add +
+  bilinear up-sampling + skip add + ReLU, and bias + residual add + ReLU -- the reference spends five to six
+  full passes over (objects x 256 x H/4 x W/4) tensors on them.
 
 Only summation order changes (fp32 / TF32 rounding); tests compare the engine with the plain modules
 and with the CPU reference port.  It is called like the model (``engine('encode_key', frame)`` ...), so the
@@ -48,10 +51,11 @@ def _fold_bn(conv, bn) -> Tuple[torch.Tensor, torch.Tensor]:
 
 
 class FrameEngine:
-    def __init__(self, model, channels_last: bool = True, fused_conv: bool = True):
+    def __init__(self, model, channels_last: bool = True, fused_conv: bool = True, stage_kernels: bool = True):
         self.model = model
         self.channels_last = channels_last
         self.fused_conv = fused_conv
+        self.stage_kernels = stage_kernels and channels_last     # the decoder glue kernels of libswem_b200 are NHWC
         self._built = False
 
     # ------------------------------------------------------------------------------------------
@@ -130,6 +134,16 @@ class FrameEngine:
                  'down': None if rb.downsample is None else self._plain(rb.downsample)}
             self.d_up.append(d)
         self.d_pred = self._plain(dec.pred)
+        # per-channel constants handed to the fused glue kernels instead of separate bias passes: the biases of the convs
+        # that feed each up-sampling (conv2 [+ downsample] of the previous ResBlock, skip_conv of this level), and of the last ResBlock
+        def bias_of(p: ConvP):
+            return p[1]
+        prev = bias_of(self.d_c2)
+        self.d_bias = []
+        for d in self.d_up:
+            self.d_bias.append((prev + bias_of(d['skip'])).contiguous())
+            prev = bias_of(d['c2']) + (bias_of(d['down']) if d['down'] is not None else 0)
+        self.d_bias.append(prev.contiguous())
         self._built = True
 
     def _ready(self):
@@ -225,18 +239,60 @@ class FrameEngine:
         y = y.view(bsz, n, *y.shape[1:]).add_(shared.unsqueeze(1)).flatten(end_dim=1)
         return y[:, :self.g_out] * torch.sigmoid(y[:, self.g_out:]), n
 
+    @staticmethod
+    def _nobias(p: ConvP) -> ConvP:
+        return (p[0], None, p[2], p[3])
+
+    def _glue_ok(self, *ts) -> bool:
+        return self.stage_kernels and all(t is None or (t.is_cuda and t.dtype == torch.float32) for t in ts)
+
+    def _cl(self, t):
+        return t if t.is_contiguous(memory_format=torch.channels_last) else t.contiguous(memory_format=torch.channels_last)
+
+    def _upsample_add(self, lo_a, lo_b, bias, skip, n):
+        """x = skip[b] + bilinear(lo_a + lo_b) + bias  and relu(x)  (UpsampleBlock.forward, networks.py:192-196)."""
+        if self._glue_ok(lo_a, lo_b, skip) and lo_a.shape[1] % 4 == 0:
+            lo_a, skip = self._cl(lo_a), self._cl(skip)
+            lo_b = None if lo_b is None else self._cl(lo_b)
+            bn, c, h, w = lo_a.shape
+            H, W = skip.shape[-2:]
+            x = torch.empty((bn, c, H, W), device=lo_a.device, dtype=torch.float32, memory_format=torch.channels_last)
+            xr = torch.empty_like(x)
+            with torch.cuda.device(lo_a.device):
+                rc = _lib.load().swem_upsample_add(lo_a.data_ptr(), None if lo_b is None else lo_b.data_ptr(), bias.data_ptr(),
+                                                   skip.data_ptr(), bn, n, h, w, H, W, c, x.data_ptr(), xr.data_ptr(),
+                                                   torch.cuda.current_stream(lo_a.device).cuda_stream)
+            _lib.check(rc, 'swem_upsample_add')
+            return x, xr
+        lo = lo_a if lo_b is None else lo_a + lo_b
+        up = F.interpolate(lo, size=skip.shape[-2:], mode='bilinear', align_corners=False)
+        x = up.view(-1, n, *up.shape[1:]).add_(skip.unsqueeze(1)).flatten(end_dim=1).add_(bias.view(1, -1, 1, 1))
+        return x, F.relu(x)
+
+    def _bias_add_relu(self, a, b, bias):
+        """relu(a + b + bias): the residual tail of ResBlock.forward (networks.py:25-32) + the ReLU that follows it."""
+        if self._glue_ok(a, b) and a.shape[1] % 4 == 0:
+            a, b = self._cl(a), self._cl(b)
+            out = torch.empty_like(a)
+            with torch.cuda.device(a.device):
+                rc = _lib.load().swem_bias_add_act(a.data_ptr(), b.data_ptr(), bias.data_ptr(), a.shape[0] * a.shape[2] * a.shape[3],
+                                                   a.shape[1], 1, out.data_ptr(), torch.cuda.current_stream(a.device).cuda_stream)
+            _lib.check(rc, 'swem_bias_add_act')
+            return out
+        return F.relu_(a + b + bias.view(1, -1, 1, 1))
+
     def decode(self, n, context, s8, s4, valid_obj, out_size):
-        """-> (logits, prob) (B, N+1, H, W), as SWEM.decode (swem.py:92-108)."""
+        """-> (logits, prob) (B, N+1, H, W), as SWEM.decode (swem.py:92-108).  Convolutions whose output only feeds an
+        up-sampling or a residual add run without their bias pass; the constants go to the glue kernels (`d_bias`)."""
         self._ready()
-        bsz = context.shape[0] // n
-        x = self._conv(self._conv(F.relu(context), self.d_c1, relu=True), self.d_c2).add_(context)
-        for d, skip_f in zip(self.d_up, (s8, s4)):
-            skip = self._conv(skip_f, d['skip'])                   # once per frame, not per object
-            up = F.interpolate(x, size=skip.shape[-2:], mode='bilinear', align_corners=False)
-            x = up.view(bsz, n, *up.shape[1:]).add_(skip.unsqueeze(1)).flatten(end_dim=1)
-            r = self._conv(self._conv(F.relu(x), d['c1'], relu=True), d['c2'])
-            x = r.add_(x if d['down'] is None else self._conv(x, d['down']))
-        lr = self._conv(F.relu_(x), self.d_pred)                   # (B*n, 1, Hl, Wl)
+        lo_a = self._conv(self._conv(F.relu(context), self.d_c1, relu=True), self._nobias(self.d_c2))
+        lo_b = context
+        for d, skip_f, bias in zip(self.d_up, (s8, s4), self.d_bias):
+            skip = self._conv(skip_f, self._nobias(d['skip']))        # once per frame, not per object
+            x, xr = self._upsample_add(lo_a, lo_b, bias, skip, n)
+            lo_a = self._conv(self._conv(xr, d['c1'], relu=True), self._nobias(d['c2']))
+            lo_b = x if d['down'] is None else self._conv(x, self._nobias(d['down']))
+        lr = self._conv(self._bias_add_relu(lo_a, lo_b, self.d_bias[-1]), self.d_pred)      # (B*n, 1, Hl, Wl)
         return self.model.decode_from_lowres(lr, n, valid_obj, out_size)
 
     _MODES = {'encode_key': 'encode_key', 'encode_value': 'encode_value', 'match': 'match', 'segment': 'decode'}

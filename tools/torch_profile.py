@@ -1,0 +1,50 @@
+"""torch.profiler view of one eager frame step (FrameEngine): which aten ops / kernels take the time, with shapes."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from torch.profiler import ProfilerActivity, profile
+from swem_b200 import SWEM, make_config
+from swem_b200.engine import FrameEngine
+from swem_b200.evaluator import SequenceRunner
+from swem_b200.synthetic import davis_sequence
+
+dev = torch.device('cuda:0')
+torch.manual_seed(0)
+model = SWEM(make_config(keydim=64, n_bases=128, n_iters=4, topl=64)).eval().to(dev).to(memory_format=torch.channels_last)
+eng = FrameEngine(model)
+frames, init = davis_sequence(8, 5, seed=1)
+frames, init = frames.to(dev), init.to(dev)
+runner = SequenceRunner(eng, (480, 864))
+with torch.no_grad():
+    runner.start(frames[:, 0], init)
+    for i in range(1, 5):
+        runner.step(frames[:, i])
+    torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], record_shapes=True) as prof:
+        for i in range(5, 8):
+            runner.step(frames[:, i])
+        torch.cuda.synchronize()
+rows = [e for e in prof.key_averages(group_by_input_shape=True) if e.key.startswith('aten::') and e.self_device_time_total > 0]
+rows.sort(key=lambda e: -e.self_device_time_total)
+print('self CUDA us per frame | calls per frame | op | input shapes')
+for e in rows[:70]:
+    print(f'{e.self_device_time_total / 3:10.1f} {e.count / 3:6.1f}  {e.key:34s} {str(e.input_shapes)[:150]}')
+print('total self CUDA us per frame', sum(e.self_device_time_total for e in rows) / 3)
+
+# stem conv: 5 input planes vs zero-padded to 8
+import torch.nn.functional as F
+def t(fn, n=20):
+    for _ in range(3): fn()
+    torch.cuda.synchronize(); a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(n): fn()
+    b.record(); torch.cuda.synchronize(); return a.elapsed_time(b) / n * 1e3
+for cin in (5, 8):
+    x = torch.randn(5, cin, 480, 864, device=dev).contiguous(memory_format=torch.channels_last)
+    w = torch.randn(64, cin, 7, 7, device=dev).contiguous(memory_format=torch.channels_last)
+    bias = torch.zeros(64, device=dev)
+    print('stem conv cin', cin, 'fused relu', t(lambda: torch.cudnn_convolution_relu(x, w, bias, (2, 2), (3, 3), (1, 1), 1)), 'us; plain', t(lambda: F.conv2d(x, w, bias, 2, 3)), 'us')
+    xn = x.contiguous()
+    wn = w.contiguous()
+    print('   NCHW plain', t(lambda: F.conv2d(xn, wn, bias, 2, 3)), 'us')
+
