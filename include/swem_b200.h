@@ -160,6 +160,9 @@ int swem_upsample_add(const float* lo_a, const float* lo_b, const float* bias, c
                       int32_t h, int32_t w, int32_t H, int32_t W, int32_t C, float* x, float* x_relu, void* stream);
 int swem_bias_add_act(const float* a, const float* b, const float* bias, int64_t pixels, int32_t C, int32_t relu,
                       float* out, void* stream);
+/* 3x3 / stride 2 / padding 1 max pooling of the ResNet stems (networks.py:150, mod_resnet.py), NHWC:
+ * in [N, H, W, C] -> out [N, (H-1)/2+1, (W-1)/2+1, C].                                                           */
+int swem_maxpool3x3s2(const float* in, int32_t N, int32_t H, int32_t W, int32_t C, float* out, void* stream);
 
 /* ---- misc ------------------------------------------------------------------------------------ */
 int         swem_abi_version(void);          /* == SWEM_B200_ABI_VERSION                          */

@@ -7,6 +7,7 @@
 //
 //   upsample_add:  x = skip[b] + bilinear(lo_a [+ lo_b]) + bias      (also writes relu(x), the next conv's input)
 //   bias_add_act:  out = act(a [+ b] + bias)
+//   maxpool3x3s2:  the 3x3 / stride-2 pooling after both ResNet stems (ATen's NHWC pooling kernel runs at ~1 TB/s)
 //
 // `skip` is shared by the n objects of a batch element (the reference recomputes skip_conv per object), the biases of the
 // convolutions that produced lo_a / lo_b / skip are passed here as one per-channel vector (bilinear interpolation
@@ -77,6 +78,33 @@ __global__ void __launch_bounds__(256) bias_add_act_kernel(const float4* __restr
   out[idx] = relu ? f4relu(v) : v;
 }
 
+// 3x3 / stride 2 / padding 1 max pooling, NHWC (the stem of both ResNet trunks: torchvision resnet.py `maxpool`,
+// used by methods/basic_modules/networks.py:150 and mod_resnet.py); out-of-range taps are skipped (= -inf padding).
+__global__ void __launch_bounds__(256) maxpool3x3s2_kernel(const float4* __restrict__ in, int N, int H, int W, int C4, int Ho, int Wo,
+                                                           float4* __restrict__ out) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)N * Ho * Wo * C4;
+  if (idx >= total) return;
+  const int c4 = (int)(idx % C4);
+  const int px = (int)((idx / C4) % Wo);
+  const int py = (int)((idx / ((long long)C4 * Wo)) % Ho);
+  const int n = (int)(idx / ((long long)C4 * Wo * Ho));
+  float4 m = make_float4(-3.4e38f, -3.4e38f, -3.4e38f, -3.4e38f);
+#pragma unroll
+  for (int ky = -1; ky <= 1; ++ky) {
+    const int y = 2 * py + ky;
+    if (y < 0 || y >= H) continue;
+#pragma unroll
+    for (int kx = -1; kx <= 1; ++kx) {
+      const int x = 2 * px + kx;
+      if (x < 0 || x >= W) continue;
+      const float4 v = __ldg(in + (((long long)n * H + y) * W + x) * C4 + c4);
+      m = make_float4(fmaxf(m.x, v.x), fmaxf(m.y, v.y), fmaxf(m.z, v.z), fmaxf(m.w, v.w));
+    }
+  }
+  out[idx] = m;
+}
+
 }  // namespace swem
 
 using namespace swem;
@@ -107,6 +135,18 @@ int swem_bias_add_act(const float* a, const float* b, const float* bias, int64_t
   bias_add_act_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const float4*>(a), reinterpret_cast<const float4*>(b), reinterpret_cast<const float4*>(bias), total4, C / 4,
       relu, reinterpret_cast<float4*>(out));
+  SWEM_LAUNCH_CHECK();
+  return SWEM_OK;
+}
+
+int swem_maxpool3x3s2(const float* in, int32_t N, int32_t H, int32_t W, int32_t C, float* out, void* stream) {
+  reset_launch_count();
+  SWEM_CHECK_ARG(in && out, "NULL pointer");
+  SWEM_CHECK_ARG(N > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0, "bad sizes N=%d H=%d W=%d C=%d (C must be a multiple of 4)", N, H, W, C);
+  const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+  const long long total = (long long)N * Ho * Wo * (C / 4);
+  maxpool3x3s2_kernel<<<(unsigned)((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const float4*>(in), N, H, W, C / 4, Ho, Wo, reinterpret_cast<float4*>(out));
   SWEM_LAUNCH_CHECK();
   return SWEM_OK;
 }

@@ -587,3 +587,30 @@ def test_generic_family_is_bit_reproducible():
             else:
                 for a, b in zip(out, ref[key]):
                     assert torch.equal(a, b), f'rep {rep}: generic kernels are not reproducible'
+
+
+def test_decoder_glue_kernels_match_torch():
+    """swem_upsample_add / swem_bias_add_act / swem_maxpool3x3s2 (NHWC, C ABI) vs the torch ops they replace
+    (networks.py:192-196, :25-32, the ResNet stem pooling), odd sizes included."""
+    import torch.nn.functional as F
+    from swem_b200 import SWEM, make_config
+    from swem_b200.engine import FrameEngine
+    eng = FrameEngine(SWEM(make_config(keydim=64, n_bases=16, n_iters=1, topl=8, backbone='resnet18')).eval())
+    g = torch.Generator().manual_seed(0)
+    cl = lambda t: t.to(DEV).contiguous(memory_format=torch.channels_last)
+    for (B, n, C, h, w, H, W) in [(1, 5, 256, 60, 108, 120, 216), (2, 3, 64, 7, 9, 14, 18), (1, 2, 8, 5, 6, 9, 11)]:
+        lo_a, lo_b = cl(torch.randn(B * n, C, h, w, generator=g)), cl(torch.randn(B * n, C, h, w, generator=g))
+        skip, bias = cl(torch.randn(B, C, H, W, generator=g)), torch.randn(C, generator=g).to(DEV)
+        for lb in (lo_b, None):
+            x, xr = eng._upsample_add(lo_a, lb, bias, skip, n)
+            lo = lo_a if lb is None else lo_a + lb
+            want = F.interpolate(lo, size=(H, W), mode='bilinear', align_corners=False).view(B, n, C, H, W) \
+                + skip.unsqueeze(1) + bias.view(1, 1, C, 1, 1)
+            want = want.flatten(end_dim=1)
+            check('upsample_add', maxrel(x, want), 1e-6)
+            assert torch.equal(xr, torch.relu(x)) and x.is_contiguous(memory_format=torch.channels_last)
+        a, b = cl(torch.randn(B * n, C, H, W, generator=g)), cl(torch.randn(B * n, C, H, W, generator=g))
+        assert torch.equal(eng._bias_add_relu(a, b, bias), torch.relu(a + b + bias.view(1, C, 1, 1)))
+        for (hh, ww) in ((H, W), (H + 1, W + 1)):
+            t = cl(torch.randn(B * n, C, hh, ww, generator=g))
+            assert torch.equal(eng._maxpool(t), F.max_pool2d(t, 3, stride=2, padding=1))
