@@ -160,6 +160,12 @@ int swem_upsample_add(const float* lo_a, const float* lo_b, const float* bias, c
                       int32_t h, int32_t w, int32_t H, int32_t W, int32_t C, float* x, float* x_relu, void* stream);
 int swem_bias_add_act(const float* a, const float* b, const float* bias, int64_t pixels, int32_t C, int32_t relu,
                       float* out, void* stream);
+/* Input of a ResNet stem in space-to-depth form (see stages.cu): frame [B, 3, H, W]; masks [B, N+1, H, W] or NULL;
+ * mean3 / std3: HOST pointers to the 3 normalisation constants (networks.py:72-73); planes = 3 (key encoder, N = 1),
+ * 4 (+ object mask, single-object value encoder) or 5 (+ mask of the other objects, networks.py:115-117);
+ * out [B*N, H/2+3, W/2+3, Cpad] NHWC, Cpad >= 4*planes, zero border and zero pad channels.                         */
+int swem_stem_input(const float* frame, const float* masks, const float* mean3, const float* std3, int32_t B, int32_t N,
+                    int32_t planes, int32_t H, int32_t W, int32_t Cpad, float* out, void* stream);
 /* 3x3 / stride 2 / padding 1 max pooling of the ResNet stems (networks.py:150, mod_resnet.py), NHWC:
  * in [N, H, W, C] -> out [N, (H-1)/2+1, (W-1)/2+1, C].                                                           */
 int swem_maxpool3x3s2(const float* in, int32_t N, int32_t H, int32_t W, int32_t C, float* out, void* stream);

@@ -20,6 +20,10 @@ inference (``eval()`` + ``no_grad`` only):
       write ``mem_out`` / ``S`` into a 640-channel buffer, the ``qv`` copy disappears;
     - decoder ``skip_conv`` of ``s8`` / ``s4`` (``networks.py:186-203``) computed once per frame instead
       of once per object, and the N-fold ``expand`` copies of ``s8`` / ``s4`` (``swem.py:93-94``) dropped;
+* both ResNet stems (7x7 / stride 2, 3-5 input planes) as a 4x4 conv over a space-to-depth input that one kernel
+  (``swem_stem_input``) builds from the frame and the masks -- normalisation, mask planes, the N-fold frame copy and
+  the ``torch.cat`` disappear, and cuDNN runs a tensor-core implicit GEMM instead of its scalar path for tiny Cin;
+  3x3 / stride-2 pooling by ``swem_maxpool3x3s2``;
 * decoder glue as single passes (``swem_upsample_add`` / ``swem_bias_add_act`` of the C ABI, NHWC): bias add +
   bilinear up-sampling + skip add + ReLU, and bias + residual add + ReLU -- the reference spends five to six
   full passes over (objects x 256 x H/4 x W/4) tensors on them.
@@ -31,6 +35,7 @@ of the memory kernels here: ``init`` / ``memorize`` / the readout go to ``SWEMCo
 """
 from __future__ import annotations
 
+import ctypes as C
 from typing import List, Optional, Tuple
 
 import torch
@@ -75,6 +80,42 @@ class FrameEngine:
     def _plain(self, conv) -> ConvP:
         return self._cp(conv.weight, conv.bias, conv.stride[0], conv.padding[0])
 
+    def _s2d_stem(self, conv, bn, owner):
+        """7x7 / stride-2 / padding-3 stem as a 4x4 / stride-1 conv over the space-to-depth input built by
+        ``swem_stem_input``: W4[co, 4*ci + 2*p + q, a + 2, b + 2] = W7[co, ci, 2*a + p + 3, 2*b + q + 3], a, b in -2..1."""
+        if conv.kernel_size != (7, 7) or conv.stride != (2, 2) or conv.padding != (3, 3):
+            return None
+        w7, bias = _fold_bn(conv, bn)
+        co, planes = w7.shape[:2]
+        if not 3 <= planes <= 5:
+            return None
+        cpad = (4 * planes + 7) // 8 * 8
+        w4 = torch.zeros(co, cpad, 4, 4, dtype=torch.float32, device=w7.device)
+        for ky in range(7):
+            a, p_ = divmod(ky - 3, 2)
+            for kx in range(7):
+                b, q = divmod(kx - 3, 2)
+                w4[:, p_ * 2 + q:4 * planes:4, a + 2, b + 2] = w7[:, :, ky, kx]
+        return {'w': self._w(w4), 'b': bias.detach().float().contiguous(), 'planes': planes, 'cpad': cpad,
+                'mean': (C.c_float * 3)(*owner.mean.flatten().tolist()), 'std': (C.c_float * 3)(*owner.std.flatten().tolist())}
+
+    def _stem_s2d(self, st, frame, masks, n):
+        """relu(bn(conv1(cat[normalised frame, mask planes]))) for n objects per frame -> (B*n, 64, H/2, W/2), or None when the
+        space-to-depth path does not apply (CPU tensors, odd sizes): the caller then runs the plain stem."""
+        if st is None or not self._glue_ok(frame, masks) or frame.shape[-2] % 2 or frame.shape[-1] % 2:
+            return None
+        bsz, _, h, w = frame.shape
+        frame = frame.contiguous()
+        masks = None if masks is None else masks.contiguous()
+        x2 = torch.empty((bsz * n, st['cpad'], h // 2 + 3, w // 2 + 3), device=frame.device, dtype=torch.float32,
+                         memory_format=torch.channels_last)
+        with torch.cuda.device(frame.device):
+            rc = _lib.load().swem_stem_input(frame.data_ptr(), None if masks is None else masks.data_ptr(), st['mean'], st['std'],
+                                             bsz, n, st['planes'], h, w, st['cpad'], x2.data_ptr(),
+                                             torch.cuda.current_stream(frame.device).cuda_stream)
+        _lib.check(rc, 'swem_stem_input')
+        return self._conv(x2, (st['w'], st['b'], 1, 0), relu=True)
+
     def _stage(self, stage) -> List[dict]:
         blocks = []
         for blk in stage:
@@ -96,12 +137,14 @@ class FrameEngine:
             raise RuntimeError('FrameEngine is inference-only: call model.eval() first')
         ke, ve, dec = m.key_encoder, m.value_encoder, m.decoder
         self.k_stem = self._folded(ke.conv1, ke.bn1)
+        self.k_stem_s2d = self._s2d_stem(ke.conv1, ke.bn1, ke)
         self.k_stages = [self._stage(s) for s in (ke.res2, ke.layer2, ke.layer3)]
         kp, kc = m.key_proj.key_proj, m.key_comp
         self.keydim = kp.out_channels
         self.k_heads = self._cp(torch.cat([kp.weight, kc.weight], 0), torch.cat([kp.bias, kc.bias], 0), 1, 1)
 
         self.v_stem = self._folded(ve.conv1, ve.bn1)
+        self.v_stem_s2d = self._s2d_stem(ve.conv1, ve.bn1, ve)
         self.v_stages = [self._stage(s) for s in (ve.layer1, ve.layer2, ve.layer3)]
         b1, b2 = ve.fuser.block1, ve.fuser.block2
         cx = ve.layer3[-1].conv2.out_channels                      # channels of the per-object half of cat[x, f16]
@@ -192,8 +235,9 @@ class FrameEngine:
             return out
         return F.max_pool2d(x, 3, stride=2, padding=1)
 
-    def _trunk(self, x, stem, stages, taps=False):
-        x = self._maxpool(self._conv(x, stem, relu=True))
+    def _trunk(self, y, stages, taps=False):
+        """y = the stem's output (conv1 + bn1 + relu) -> max-pool -> the three residual stages."""
+        x = self._maxpool(y)
         feats = []
         for st in stages:
             x = self._run_stage(x, st)
@@ -207,7 +251,10 @@ class FrameEngine:
         """frames (B,3,H,W) -> (qk16, qv16, f16, f8, f4), as SWEM.encode_key (swem.py:45-49)."""
         self._ready()
         ke = self.model.key_encoder
-        f4, f8, f16 = self._trunk((frames - ke.mean) / ke.std, self.k_stem, self.k_stages, taps=True)
+        y = self._stem_s2d(self.k_stem_s2d, frames, None, 1)
+        if y is None:
+            y = self._conv((frames - ke.mean) / ke.std, self.k_stem, relu=True)
+        f4, f8, f16 = self._trunk(y, self.k_stages, taps=True)
         heads = self._conv(f16, self.k_heads)
         return heads[:, :self.keydim], heads[:, self.keydim:], f16, f8, f4
 
@@ -217,15 +264,18 @@ class FrameEngine:
         m, ve = self.model, self.model.value_encoder
         n = masks.shape[1] - 1
         bsz = frame.shape[0]
-        image = ((frame - ve.mean) / ve.std).unsqueeze(1).expand(-1, n, -1, -1, -1)
-        planes = [image, masks[:, 1:].unsqueeze(2)]
-        if not m.single_object:
-            others = 1 - masks - masks[:, 0:1]
-            planes.append(others[:, 1:].unsqueeze(2))
-        x = torch.cat(planes, dim=2).flatten(end_dim=1)            # (B*N, 3 + extra, H, W)
-        if self.channels_last:
-            x = x.contiguous(memory_format=torch.channels_last)
-        x = self._trunk(x, self.v_stem, self.v_stages)             # (B*N, 256, H16, W16), post-ReLU
+        y = self._stem_s2d(self.v_stem_s2d, frame, masks.float(), n)
+        if y is None:
+            image = ((frame - ve.mean) / ve.std).unsqueeze(1).expand(-1, n, -1, -1, -1)
+            planes = [image, masks[:, 1:].unsqueeze(2)]
+            if not m.single_object:
+                others = 1 - masks - masks[:, 0:1]
+                planes.append(others[:, 1:].unsqueeze(2))
+            x = torch.cat(planes, dim=2).flatten(end_dim=1)        # (B*N, 3 + extra, H, W)
+            if self.channels_last:
+                x = x.contiguous(memory_format=torch.channels_last)
+            y = self._conv(x, self.v_stem, relu=True)
+        x = self._trunk(y, self.v_stages)                          # (B*N, 256, H16, W16), post-ReLU
         # fuser.block1 on cat[x, f16]: both halves are post-ReLU, so block1's leading ReLU is the identity
         shared = self._conv(s16, self.f_shared)                    # (B, 1024, H16, W16): [conv1 | downsample] of the f16 half
         y = self._conv(x, self.f_obj)
