@@ -131,6 +131,26 @@ typedef struct SwemReadArgs {
 size_t swem_readout_workspace_bytes(const SwemDims* dims, int32_t path);
 int    swem_readout_forward(const SwemReadArgs* args, void* stream);
 
+/* ---- backward of the readout (training).  Reference: autograd through modules.py:232-293 -- gradient to the raw query
+ * key (through l2norm :282, affinity, exp, both the attention P and the sorted-prefix feature S :198-208) and to the
+ * memory values nu of every bank; the memory keys carry no gradient.  The forward is recomputed (nothing is saved).
+ * grad_out has the layout of SwemReadArgs.out ([B*N, out_channels, HW]; only the mem_out and S channels are read).   */
+typedef struct SwemReadBwdArgs {
+  SwemDims dims;
+  const float* qk;           /* [B, Ck, HW]  raw query key of the forward                                   */
+  const float* kappa[2];     /* per bank [B, N, 2, Ck, L]                                                    */
+  const float* nu[2];        /* per bank [B, N, 2, Cv, L]                                                    */
+  const float* grad_out;     /* [B*N, out_channels, HW]                                                      */
+  int32_t out_channels, mem_channel, s_channel;
+  float* grad_qk;            /* out [B, Ck, HW]            (NULL = skip)                                     */
+  float* grad_nu[2];         /* out per bank [B, N, 2, Cv, L] (NULL = skip)                                  */
+  void*  workspace;          /* >= swem_readout_backward_workspace_bytes(&dims)                              */
+  size_t workspace_bytes;
+} SwemReadBwdArgs;
+
+size_t swem_readout_backward_workspace_bytes(const SwemDims* dims);
+int    swem_readout_backward(const SwemReadBwdArgs* args, void* stream);
+
 /* ---- mask prep of SWEM.memorize, swem.py:80-84 ------------------------------------------------
  * hard: [B, N+1, Hm, Wm] int64 one-hot (channel 0 = background, skipped), nearest-resized;
  * soft: [B, N+1, Hs, Ws] fp32 probabilities, bilinear-resized (align_corners = false);
@@ -184,6 +204,8 @@ int         swem_readout_fused_supported(const SwemDims* dims);
 int         swem_set_profile_buffer(void* dev, size_t bytes);
 /* number of kernel launches the last call on this thread issued (for bench.py's gpu_launches)   */
 int         swem_last_launch_count(void);
+/* kernel / memset launches issued by every call on this thread since the library was loaded (monotonic)  */
+long long   swem_total_launch_count(void);
 
 #ifdef __cplusplus
 }

@@ -14,11 +14,11 @@ LIB_PATH = os.path.join(_HERE, 'libswem_b200.so')
 PATH_AUTO, PATH_GENERIC, PATH_FUSED = 0, 1, 2
 
 EXPORTS = (
-    'swem_abi_version', 'swem_last_error', 'swem_device_check', 'swem_last_launch_count',
+    'swem_abi_version', 'swem_last_error', 'swem_device_check', 'swem_last_launch_count', 'swem_total_launch_count',
     'swem_em_workspace_bytes', 'swem_em_forward', 'swem_em_fused_supported',
     'swem_readout_workspace_bytes', 'swem_readout_forward', 'swem_readout_fused_supported',
     'swem_em_masks', 'swem_decode_tail', 'swem_set_profile_buffer',
-    'swem_em_backward_workspace_bytes', 'swem_em_backward', 'swem_upsample_add', 'swem_bias_add_act', 'swem_maxpool3x3s2', 'swem_stem_input',
+    'swem_em_backward_workspace_bytes', 'swem_em_backward', 'swem_readout_backward_workspace_bytes', 'swem_readout_backward', 'swem_upsample_add', 'swem_bias_add_act', 'swem_maxpool3x3s2', 'swem_stem_input',
 )
 
 
@@ -55,6 +55,14 @@ class SwemReadArgs(C.Structure):
                 ('path', C.c_int32)]
 
 
+class SwemReadBwdArgs(C.Structure):
+    _fields_ = [('dims', SwemDims),
+                ('qk', C.c_void_p), ('kappa', C.c_void_p * 2), ('nu', C.c_void_p * 2), ('grad_out', C.c_void_p),
+                ('out_channels', C.c_int32), ('mem_channel', C.c_int32), ('s_channel', C.c_int32),
+                ('grad_qk', C.c_void_p), ('grad_nu', C.c_void_p * 2),
+                ('workspace', C.c_void_p), ('workspace_bytes', C.c_size_t)]
+
+
 _lib = None
 
 
@@ -72,6 +80,7 @@ def load() -> C.CDLL:
     lib.swem_last_error.restype = C.c_char_p
     lib.swem_device_check.argtypes = [C.c_int]
     lib.swem_last_launch_count.restype = C.c_int
+    lib.swem_total_launch_count.restype = C.c_longlong
     lib.swem_em_workspace_bytes.argtypes = [C.POINTER(SwemDims), C.c_int32]
     lib.swem_em_workspace_bytes.restype = C.c_size_t
     lib.swem_em_forward.argtypes = [C.POINTER(SwemEmArgs), C.c_void_p]
@@ -79,6 +88,9 @@ def load() -> C.CDLL:
     lib.swem_em_backward_workspace_bytes.argtypes = [C.POINTER(SwemDims)]
     lib.swem_em_backward_workspace_bytes.restype = C.c_size_t
     lib.swem_em_backward.argtypes = [C.POINTER(SwemEmBwdArgs), C.c_void_p]
+    lib.swem_readout_backward_workspace_bytes.argtypes = [C.POINTER(SwemDims)]
+    lib.swem_readout_backward_workspace_bytes.restype = C.c_size_t
+    lib.swem_readout_backward.argtypes = [C.POINTER(SwemReadBwdArgs), C.c_void_p]
     lib.swem_readout_workspace_bytes.argtypes = [C.POINTER(SwemDims), C.c_int32]
     lib.swem_readout_workspace_bytes.restype = C.c_size_t
     lib.swem_readout_forward.argtypes = [C.POINTER(SwemReadArgs), C.c_void_p]

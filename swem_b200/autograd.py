@@ -8,9 +8,9 @@ What is differentiable in the reference (verified on its autograd graph):
   with ``z_last`` saved; backward = ``swem_em_backward`` of the C ABI (two batched GEMMs + a scale kernel).
 * ``matching`` (:278-293): gradient flows to the raw query key ``qk`` (through l2norm :282, affinity, exp,
   both the attention ``P`` and the sorted-prefix feature ``S``) and to the memory values ``nu`` of both banks;
-  the memory keys are constants.  Forward = the CUDA readout kernels.  Backward, this round, re-evaluates the
-  readout of the affected units with torch ops on the GPU (cuBLAS GEMMs, ``topk``, ``cumsum``) and
-  differentiates that -- a library backward, not yet a hand-written kernel.
+  the memory keys are constants.  Forward = the CUDA readout kernels.  Backward = ``swem_readout_backward`` of the C
+  ABI (forward recomputed; batched GEMMs + sorted-prefix, softmax and l2norm backward kernels, fp32).  A torch
+  re-evaluation (``readout_torch``) is kept as the cross-check of the tests (``ReadoutFunction.native_backward``).
 
 ``qv`` and the fusion conv stay in torch autograd (``SWEMCore.matching`` concatenates with ``torch.cat`` when
 gradients are needed).
@@ -107,6 +107,10 @@ class ReadoutFunction(torch.autograd.Function):
         ctx.save_for_backward(qk, *kappas, *nus)
         return out
 
+    #: True: `swem_readout_backward` of the C ABI (hand-written kernels).  False: differentiate `readout_torch` (kept as the
+    #: cross-check the tests compare against).
+    native_backward = True
+
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, gout):
@@ -115,12 +119,42 @@ class ReadoutFunction(torch.autograd.Function):
         kappas, nus = rest[:nb], rest[nb:]
         need_q = ctx.needs_input_grad[1]
         need_nu = [ctx.needs_input_grad[3 + nb + k] for k in range(nb)]
-        with torch.enable_grad():
-            q_ = qk.detach().requires_grad_(need_q)
-            nus_ = [n.detach().requires_grad_(need_nu[k]) for k, n in enumerate(nus)]
-            out = readout_torch(q_, [k.detach() for k in kappas], nus_, ctx.tau, ctx.topl)
-            wrt = ([q_] if need_q else []) + [n for k, n in enumerate(nus_) if need_nu[k]]
-            grads = list(torch.autograd.grad(out, wrt, gout)) if wrt else []
-        gq = grads.pop(0) if need_q else None
-        gn = [grads.pop(0) if need_nu[k] else None for k in range(nb)]
+        if not (need_q or any(need_nu)):
+            return (None,) * (3 + 2 * nb)
+        if ReadoutFunction.native_backward:
+            gq, gn = _readout_backward_native(ctx, qk, kappas, nus, gout.float().contiguous(), need_q, need_nu)
+        else:
+            with torch.enable_grad():
+                q_ = qk.detach().requires_grad_(need_q)
+                nus_ = [n.detach().requires_grad_(need_nu[k]) for k, n in enumerate(nus)]
+                out = readout_torch(q_, [k.detach() for k in kappas], nus_, ctx.tau, ctx.topl)
+                wrt = ([q_] if need_q else []) + [n for k, n in enumerate(nus_) if need_nu[k]]
+                grads = list(torch.autograd.grad(out, wrt, gout))
+            gq = grads.pop(0) if need_q else None
+            gn = [grads.pop(0) if need_nu[k] else None for k in range(nb)]
         return (None, gq, None) + (None,) * nb + tuple(gn)
+
+
+def _readout_backward_native(ctx, qk, kappas, nus, gout, need_q, need_nu):
+    from .core import _WORKSPACE, _invoke
+    nb = ctx.n_banks
+    B, Ck, H, W = qk.shape
+    _, N, _, Cv, L = nus[0].shape
+    dev = qk.device
+    chans = gout.shape[1]
+    gq = torch.empty_like(qk) if need_q else None
+    gn = [torch.empty_like(nus[k]) if need_nu[k] else None for k in range(nb)]
+    lib = _lib.load()
+    dims = _lib.SwemDims(B, N, Ck, Cv, H * W, L, 0, nb, ctx.topl, ctx.tau)
+    ws = _WORKSPACE.get(dev, lib.swem_readout_backward_workspace_bytes(C.byref(dims)))
+    ptr = lambda t: None if t is None else t.data_ptr()
+    pad = [None] * (2 - nb)
+    args = _lib.SwemReadBwdArgs(dims, qk.data_ptr(),
+                                (C.c_void_p * 2)(*[ptr(k) for k in kappas] + pad), (C.c_void_p * 2)(*[ptr(n) for n in nus] + pad),
+                                gout.data_ptr(), chans, 0, Cv, ptr(gq), (C.c_void_p * 2)(*[ptr(g) for g in gn] + pad),
+                                ws.data_ptr(), ws.numel())
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        rc = _invoke('readout_backward', lambda: lib.swem_readout_backward(C.byref(args), stream))
+    _lib.check(rc, 'swem_readout_backward')
+    return gq, gn

@@ -8,6 +8,7 @@ namespace swem {
 
 static thread_local char g_err[512] = "";
 static thread_local int g_launches = 0;
+static thread_local long long g_total_launches = 0;
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -15,7 +16,10 @@ void set_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
-void count_launch(int n) { g_launches += n; }
+void count_launch(int n) {
+  g_launches += n;
+  g_total_launches += n;
+}
 void reset_launch_count() { g_launches = 0; }
 
 static int check_dims(const SwemDims& d, bool em) {
@@ -123,6 +127,7 @@ extern "C" {
 int swem_abi_version(void) { return SWEM_B200_ABI_VERSION; }
 const char* swem_last_error(void) { return g_err; }
 int swem_last_launch_count(void) { return g_launches; }
+long long swem_total_launch_count(void) { return g_total_launches; }
 
 int swem_device_check(int device) {
   cudaDeviceProp prop;
@@ -229,6 +234,33 @@ int swem_readout_forward(const SwemReadArgs* a, void* stream) {
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   return use_fused_readout(d, a->path) ? fused_readout_forward(*a, st) : generic_readout_forward(*a, st);
+}
+
+size_t swem_readout_backward_workspace_bytes(const SwemDims* d) {
+  if (!d || check_dims(*d, false)) return 0;
+  return generic_readout_backward_workspace(*d);
+}
+
+int swem_readout_backward(const SwemReadBwdArgs* a, void* stream) {
+  reset_launch_count();
+  SWEM_CHECK_ARG(a != nullptr, "args is NULL");
+  if (int rc = check_dims(a->dims, false)) return rc;
+  const SwemDims& d = a->dims;
+  SWEM_CHECK_ARG(a->qk && a->grad_out, "qk/grad_out pointer is NULL");
+  for (int k = 0; k < d.n_banks; ++k) SWEM_CHECK_ARG(a->kappa[k] && a->nu[k], "bank %d pointer is NULL", k);
+  SWEM_CHECK_ARG(a->mem_channel >= 0 && a->mem_channel + d.Cv <= a->out_channels &&
+                 a->s_channel >= 0 && a->s_channel + 2 * d.topl <= a->out_channels,
+                 "channel placement outside out_channels=%d", a->out_channels);
+  if (d.topl > 64 || d.L * d.n_banks > 1024) {
+    set_error("readout backward: topl=%d / Lt=%d unsupported", d.topl, d.L * d.n_banks);
+    return SWEM_ERR_UNSUPPORTED;
+  }
+  const size_t need = swem_readout_backward_workspace_bytes(&d);
+  if (!a->workspace || a->workspace_bytes < need || (reinterpret_cast<uintptr_t>(a->workspace) & 255)) {
+    set_error("readout backward workspace: need %zu bytes 256-aligned, got %zu at %p", need, a->workspace_bytes, a->workspace);
+    return SWEM_ERR_WORKSPACE;
+  }
+  return generic_readout_backward(*a, static_cast<cudaStream_t>(stream));
 }
 
 int swem_em_masks(const int64_t* hard, int32_t Hm, int32_t Wm, const float* soft, int32_t Hs, int32_t Ws,

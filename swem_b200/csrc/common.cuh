@@ -67,6 +67,8 @@ size_t generic_em_workspace(const SwemDims& d);
 int generic_em_forward(const SwemEmArgs& a, cudaStream_t st);
 size_t generic_em_backward_workspace(const SwemDims& d);
 int generic_em_backward(const SwemEmBwdArgs& a, cudaStream_t st);
+size_t generic_readout_backward_workspace(const SwemDims& d);
+int generic_readout_backward(const SwemReadBwdArgs& a, cudaStream_t st);
 size_t generic_readout_workspace(const SwemDims& d);
 int generic_readout_forward(const SwemReadArgs& a, cudaStream_t st);
 

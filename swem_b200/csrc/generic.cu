@@ -600,4 +600,261 @@ int generic_readout_forward(const SwemReadArgs& a, cudaStream_t st) {
   return launch_perm_inv(P, U, d.HW, Lt, d.topl, a.out, a.out_channels, a.s_channel, st);
 }
 
+
+// ------------------------------------------------------------------------------------------
+// readout, backward (training).  Reference: autograd through modules.py:232-293 -- gradient to the raw query key
+// (through the l2norm :282, the affinity, exp, both the attention P and the sorted-prefix feature S) and to the memory
+// values nu of every bank; the memory keys are constants.  With a = khat^T qhat, P = softmax over (side, j) of a / tau:
+//   gP      = nu^T g_mem  (+ the gradient of S, below)                  batched GEMM + perm_inv_backward_kernel
+//   g_nu    = g_mem P^T                                                  batched GEMM
+//   g_a     = P (gP - sum_j P gP) / tau                                  softmax_backward_rows_kernel
+//   g_qhat  = sum over objects, sides, banks of khat g_a                 batched GEMMs, accumulated
+//   g_q     = g_qhat / d - q (q . g_qhat) / (n d^2),  n = ||q||, d = n + eps      l2norm_backward_kernel
+// S depends on the exp-affinities only through ratios, so it is the same function of P; its gradient is taken with
+// respect to P and joins gP before the softmax backward (the max-subtraction cancels analytically).
+// ------------------------------------------------------------------------------------------
+// One warp per (u, p): redo the descending sort of both sides (same packed-key network as the forward), then
+//   f_r = c0_r / (c0_r + c1_r),  g_f[r] = gS[r] - gS[topl + r]   (S = [f, 1 - f])
+//   g_c0[r] = g_f c1 / (c0 + c1)^2,  g_c1[r] = -g_f c0 / (c0 + c1)^2
+//   g_e(side, rank r) = sum_{r' >= r} g_c(side, r')   (the running sum at r' contains every rank <= r')
+// and add it to gP at the column that holds rank r.
+template <int NPL>
+__global__ void __launch_bounds__(256) perm_inv_backward_kernel(const float* __restrict__ P, int U, int HW, int Lt, int topl,
+                                                                const float* __restrict__ gout, int out_channels, int s_channel,
+                                                                float* __restrict__ gP) {
+  constexpr int N = 32 * NPL;
+  constexpr int IDXB = (NPL == 1 ? 5 : NPL == 2 ? 6 : NPL == 4 ? 7 : NPL == 8 ? 8 : NPL == 16 ? 9 : 10);
+  __shared__ uint32_t top[8][128];
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long w = (long long)blockIdx.x * 8 + wid;
+  if (w >= (long long)U * HW) return;
+  const int u = (int)(w / HW), p = (int)(w % HW);
+  const float* row = P + ((long long)u * HW + p) * (2 * Lt);
+  uint32_t a[NPL], b[NPL];
+#pragma unroll
+  for (int k = 0; k < NPL; ++k) {
+    const int i = lane * NPL + k;
+    const uint32_t va = i < Lt ? __float_as_uint(row[i]) : 0u;
+    const uint32_t vb = i < Lt ? __float_as_uint(row[Lt + i]) : 0u;
+    a[k] = ((va >> (IDXB - 1)) << IDXB) | (uint32_t)i;
+    b[k] = ((vb >> (IDXB - 1)) << IDXB) | (uint32_t)i;
+  }
+  bitonic_desc2<NPL>(a, b, lane);
+  uint32_t* mytop = top[wid];
+#pragma unroll
+  for (int k = 0; k < NPL; ++k) {
+    const int r = lane * NPL + k;
+    if (r < 64) {
+      mytop[r] = a[k];
+      mytop[64 + r] = b[k];
+    }
+  }
+  __syncwarp();
+  // lane handles ranks lane and lane + 32 (as the forward): inclusive running sums c0, c1
+  float c0[2], c1[2];
+  int i0[2], i1[2];
+#pragma unroll
+  for (int hlf = 0; hlf < 2; ++hlf) {
+    const int r = lane + 32 * hlf;
+    float x0 = 0.f, x1 = 0.f;
+    i0[hlf] = i1[hlf] = -1;
+    if (r < topl) {
+      const int j0 = mytop[r] & (N - 1), j1 = mytop[64 + r] & (N - 1);
+      if (j0 < Lt) { x0 = row[j0]; i0[hlf] = j0; }
+      if (j1 < Lt) { x1 = row[Lt + j1]; i1[hlf] = j1; }
+    }
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const float y0 = __shfl_up_sync(0xffffffffu, x0, o);
+      const float y1 = __shfl_up_sync(0xffffffffu, x1, o);
+      if (lane >= o) { x0 += y0; x1 += y1; }
+    }
+    c0[hlf] = x0;
+    c1[hlf] = x1;
+  }
+  const float t0 = __shfl_sync(0xffffffffu, c0[0], 31), t1 = __shfl_sync(0xffffffffu, c1[0], 31);
+  c0[1] += t0;
+  c1[1] += t1;
+  // gradients of the running sums, then suffix sums over rank (ranks 32..63 first, their total joins ranks 0..31)
+  float g0[2], g1[2];
+#pragma unroll
+  for (int hlf = 0; hlf < 2; ++hlf) {
+    const int r = lane + 32 * hlf;
+    g0[hlf] = g1[hlf] = 0.f;
+    if (r < topl) {
+      const float* gs = gout + ((long long)u * out_channels + s_channel) * HW + p;
+      const float gf = gs[(long long)r * HW] - gs[(long long)(topl + r) * HW];
+      const float den = c0[hlf] + c1[hlf];
+      const float inv2 = 1.f / (den * den);
+      g0[hlf] = gf * c1[hlf] * inv2;
+      g1[hlf] = -gf * c0[hlf] * inv2;
+    }
+  }
+#pragma unroll
+  for (int hlf = 1; hlf >= 0; --hlf) {
+    float x0 = g0[hlf], x1 = g1[hlf];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const float y0 = __shfl_down_sync(0xffffffffu, x0, o);
+      const float y1 = __shfl_down_sync(0xffffffffu, x1, o);
+      if (lane + o < 32) { x0 += y0; x1 += y1; }
+    }
+    g0[hlf] = x0;
+    g1[hlf] = x1;
+  }
+  const float h0 = __shfl_sync(0xffffffffu, g0[1], 0), h1 = __shfl_sync(0xffffffffu, g1[1], 0);
+  g0[0] += h0;
+  g1[0] += h1;
+  float* grow = gP + ((long long)u * HW + p) * (2 * Lt);
+#pragma unroll
+  for (int hlf = 0; hlf < 2; ++hlf) {
+    if (i0[hlf] >= 0) grow[i0[hlf]] += g0[hlf];            // distinct columns per lane: no race
+    if (i1[hlf] >= 0) grow[Lt + i1[hlf]] += g1[hlf];
+  }
+}
+
+// One warp per (u, p): gP row [2Lt] -> g_a = P (gP - sum P gP) / tau, in place.
+__global__ void softmax_backward_rows_kernel(const float* __restrict__ P, float* __restrict__ gP, int U, int HW, int W2,
+                                             float inv_tau) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= U * HW) return;
+  const float* prow = P + (long long)warp * W2;
+  float* grow = gP + (long long)warp * W2;
+  float dot = 0.f;
+  for (int j = lane; j < W2; j += 32) dot = fmaf(prow[j], grow[j], dot);
+  dot = warp_sum(dot);
+  for (int j = lane; j < W2; j += 32) grow[j] = prow[j] * (grow[j] - dot) * inv_tau;
+}
+
+// g_q[b][c][p] = g_qhat / d - q (q . g_qhat) / (n d^2)   (l2norm of modules.py:7-9 along the channel axis)
+__global__ void l2norm_backward_kernel(const float* __restrict__ q, const float* __restrict__ gqh, float* __restrict__ gq,
+                                       int B, int C, int HW) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * HW) return;
+  const int b = i / HW, p = i % HW;
+  const float* qp = q + (long long)b * C * HW + p;
+  const float* gp = gqh + (long long)b * C * HW + p;
+  float ss = 0.f, dot = 0.f;
+  for (int c = 0; c < C; ++c) {
+    const float t = qp[(long long)c * HW];
+    ss = fmaf(t, t, ss);
+    dot = fmaf(t, gp[(long long)c * HW], dot);
+  }
+  const float n = sqrtf(ss), d = n + kEpsNorm;
+  const float k = n > 0.f ? dot / (n * d * d) : 0.f;
+  float* op = gq + (long long)b * C * HW + p;
+  for (int c = 0; c < C; ++c) op[(long long)c * HW] = gp[(long long)c * HW] / d - qp[(long long)c * HW] * k;
+}
+
+size_t generic_readout_backward_workspace(const SwemDims& d) {
+  const size_t U = (size_t)d.B * d.N, G = U * 2;
+  const size_t Lt = (size_t)d.L * d.n_banks;
+  size_t bytes = 0;
+  bytes += 2 * align_up(U * d.HW * 2 * Lt * 4, 256);          // P, gP
+  bytes += align_up(G * d.Ck * d.L * 4, 256) * d.n_banks;     // khat per bank
+  bytes += align_up((size_t)d.B * d.HW * 4, 256);             // inv ||q||
+  bytes += align_up((size_t)d.B * d.Ck * d.HW * 4, 256);      // g_qhat
+  return bytes + 256;
+}
+
+int generic_readout_backward(const SwemReadBwdArgs& a, cudaStream_t st) {
+  const SwemDims& d = a.dims;
+  const int U = d.B * d.N, G = U * 2;
+  const int Lt = d.L * d.n_banks, W2 = 2 * Lt;
+  Arena ws(a.workspace);
+  float* P = ws.take<float>((size_t)U * d.HW * W2);
+  float* gP = ws.take<float>((size_t)U * d.HW * W2);
+  float* khat[2] = {nullptr, nullptr};
+  for (int k = 0; k < d.n_banks; ++k) khat[k] = ws.take<float>((size_t)G * d.Ck * d.L);
+  float* inv_nq = ws.take<float>((size_t)d.B * d.HW);
+  float* gqh = ws.take<float>((size_t)d.B * d.Ck * d.HW);
+  const float* g_mem = a.grad_out + (size_t)a.mem_channel * d.HW;
+  const long long so = (long long)a.out_channels * d.HW;       // per-unit stride of grad_out
+
+  // ---- recompute P (as generic_readout_forward) ----
+  pixel_inv_norm_kernel<<<(d.B * d.HW + 255) / 256, 256, 0, st>>>(a.qk, inv_nq, d.B, d.Ck, d.HW);
+  SWEM_LAUNCH_CHECK();
+  for (int k = 0; k < d.n_banks; ++k) {
+    kappa_unit_kernel<<<(G * d.L + 127) / 128, 128, 0, st>>>(a.kappa[k], khat[k], G, d.Ck, d.L);
+    SWEM_LAUNCH_CHECK();
+    GemmShape g{};
+    g.M = d.HW; g.N = d.L; g.K = d.Ck;
+    g.sAm = 1; g.sAk = d.HW; g.sBk = d.L; g.sBn = 1; g.sCm = W2; g.sCn = 1;
+    g.n0 = d.B; g.n1 = d.N; g.n2 = 2;
+    g.bA[0] = (long long)d.Ck * d.HW; g.bA[1] = 0; g.bA[2] = 0;
+    g.bB[0] = (long long)d.N * 2 * d.Ck * d.L; g.bB[1] = 2LL * d.Ck * d.L; g.bB[2] = (long long)d.Ck * d.L;
+    g.bC[0] = (long long)d.N * d.HW * W2; g.bC[1] = (long long)d.HW * W2; g.bC[2] = Lt;
+    if (int rc = launch_gemm(a.qk, khat[k], P + (size_t)k * d.L, g, st)) return rc;
+  }
+  {
+    const long long threads = (long long)U * d.HW * 32;
+    readout_rows_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(P, inv_nq, U, d.N, d.HW, W2, 1.f / d.tau);
+    SWEM_LAUNCH_CHECK();
+  }
+  // ---- gP = nu^T g_mem ;  g_nu = g_mem P^T ----
+  for (int s = 0; s < 2; ++s)
+    for (int k = 0; k < d.n_banks; ++k) {
+      const float* nu_sk = a.nu[k] + (size_t)s * d.Cv * d.L;
+      float* col = gP + (size_t)s * Lt + (size_t)k * d.L;
+      {  // gP[u][p][col + l] = sum_dch g_mem[u][dch][p] nu_k[u,s][dch][l]
+        GemmShape g{};
+        g.M = d.HW; g.N = d.L; g.K = d.Cv;
+        g.sAm = 1; g.sAk = d.HW; g.sBk = d.L; g.sBn = 1; g.sCm = W2; g.sCn = 1;
+        g.n0 = d.B; g.n1 = d.N; g.n2 = 1;
+        g.bA[0] = (long long)d.N * so; g.bA[1] = so; g.bA[2] = 0;
+        g.bB[0] = (long long)d.N * 2 * d.Cv * d.L; g.bB[1] = 2LL * d.Cv * d.L; g.bB[2] = 0;
+        g.bC[0] = (long long)d.N * d.HW * W2; g.bC[1] = (long long)d.HW * W2; g.bC[2] = 0;
+        if (int rc = launch_gemm(g_mem, nu_sk, col, g, st)) return rc;
+      }
+      if (a.grad_nu[k] != nullptr) {  // g_nu_k[u,s][dch][l] = sum_p g_mem[u][dch][p] P[u][p][col + l]
+        GemmShape g{};
+        g.M = d.Cv; g.N = d.L; g.K = d.HW;
+        g.sAm = d.HW; g.sAk = 1; g.sBk = W2; g.sBn = 1; g.sCm = d.L; g.sCn = 1;
+        g.n0 = d.B; g.n1 = d.N; g.n2 = 1;
+        g.bA[0] = (long long)d.N * so; g.bA[1] = so; g.bA[2] = 0;
+        g.bB[0] = (long long)d.N * d.HW * W2; g.bB[1] = (long long)d.HW * W2; g.bB[2] = 0;
+        g.bC[0] = (long long)d.N * 2 * d.Cv * d.L; g.bC[1] = 2LL * d.Cv * d.L; g.bC[2] = 0;
+        if (int rc = launch_gemm(g_mem, P + (size_t)s * Lt + (size_t)k * d.L, a.grad_nu[k] + (size_t)s * d.Cv * d.L, g, st)) return rc;
+      }
+    }
+  if (a.grad_qk == nullptr) return SWEM_OK;
+  // ---- + gradient of S, softmax backward ----
+  {
+    const long long warps = (long long)U * d.HW;
+    const int npl = (Lt + 31) / 32;
+    const unsigned grid = (unsigned)((warps + 7) / 8);
+#define SWEM_PIB(NPL_) perm_inv_backward_kernel<NPL_><<<grid, 256, 0, st>>>(P, U, d.HW, Lt, d.topl, a.grad_out, a.out_channels, a.s_channel, gP)
+    if (npl <= 1) SWEM_PIB(1);
+    else if (npl <= 2) SWEM_PIB(2);
+    else if (npl <= 4) SWEM_PIB(4);
+    else if (npl <= 8) SWEM_PIB(8);
+    else if (npl <= 16) SWEM_PIB(16);
+    else SWEM_PIB(32);
+#undef SWEM_PIB
+    SWEM_LAUNCH_CHECK();
+    softmax_backward_rows_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(P, gP, U, d.HW, W2, 1.f / d.tau);
+    SWEM_LAUNCH_CHECK();
+  }
+  // ---- g_qhat[b][c][p] = sum_{n,s,k,l} khat_k[b,n,s][c][l] g_a[b,n][p][s*Lt + k*L + l] (objects accumulate serially) ----
+  bool first = true;
+  for (int n = 0; n < d.N; ++n)
+    for (int s = 0; s < 2; ++s)
+      for (int k = 0; k < d.n_banks; ++k) {
+        GemmShape g{};
+        g.M = d.Ck; g.N = d.HW; g.K = d.L;
+        g.sAm = d.L; g.sAk = 1; g.sBk = 1; g.sBn = W2; g.sCm = d.HW; g.sCn = 1;
+        g.n0 = d.B; g.n1 = 1; g.n2 = 1;
+        g.bA[0] = (long long)d.N * 2 * d.Ck * d.L; g.bB[0] = (long long)d.N * d.HW * W2; g.bC[0] = (long long)d.Ck * d.HW;
+        g.accumulate = first ? 0 : 1;
+        first = false;
+        if (int rc = launch_gemm(khat[k] + ((size_t)n * 2 + s) * d.Ck * d.L,
+                                 gP + (size_t)n * d.HW * W2 + (size_t)s * Lt + (size_t)k * d.L, gqh, g, st))
+          return rc;
+      }
+  l2norm_backward_kernel<<<(d.B * d.HW + 255) / 256, 256, 0, st>>>(a.qk, gqh, a.grad_qk, d.B, d.Ck, d.HW);
+  SWEM_LAUNCH_CHECK();
+  return SWEM_OK;
+}
+
 }  // namespace swem

@@ -23,7 +23,7 @@ def lib():
 def test_header_symbols_are_exported(lib):
     from swem_b200 import _lib
     header = open(os.path.join(ROOT, 'include', 'swem_b200.h')).read()
-    declared = set(re.findall(r'^\s*(?:int|size_t|const char\*)\s+(swem_\w+)\s*\(', header, flags=re.M))
+    declared = set(re.findall(r'^\s*(?:int|size_t|long long|const char\*)\s+(swem_\w+)\s*\(', header, flags=re.M))
     assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
     for sym in declared:
         assert getattr(lib, sym) is not None

@@ -108,6 +108,21 @@ def test_readout_backward(shape, family):
     check('grad_qv', maxrel(qvg.grad, qv64.grad), 1e-5)
     for k in range(2):
         check(f'grad_nu{k}', maxrel(bg[k]['nu'].grad, nu64[k].grad), 1e-3)
+    # the torch re-evaluation of the backward must tell the same story as the kernels
+    from swem_b200.autograd import ReadoutFunction
+    native = (qg.grad.clone(), [b['nu'].grad.clone() for b in bg])
+    qg.grad = None
+    for b in bg:
+        b['nu'].grad = None
+    ReadoutFunction.native_backward = False
+    try:
+        feats2, _ = core.matching_features(qg, qvg)
+        (feats2 * G.to(DEV)).sum().backward()
+    finally:
+        ReadoutFunction.native_backward = True
+    check('grad_qk_vs_torch', maxrel(native[0], qg.grad), 1e-3)
+    for k in range(2):
+        check(f'grad_nu{k}_vs_torch', maxrel(native[1][k], bg[k]['nu'].grad), 1e-3)
 
 
 def test_training_step_runs_end_to_end():

@@ -31,20 +31,3 @@ for e in rows[:70]:
     print(f'{e.self_device_time_total / 3:10.1f} {e.count / 3:6.1f}  {e.key:34s} {str(e.input_shapes)[:150]}')
 print('total self CUDA us per frame', sum(e.self_device_time_total for e in rows) / 3)
 
-# stem conv: 5 input planes vs zero-padded to 8
-import torch.nn.functional as F
-def t(fn, n=20):
-    for _ in range(3): fn()
-    torch.cuda.synchronize(); a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    for _ in range(n): fn()
-    b.record(); torch.cuda.synchronize(); return a.elapsed_time(b) / n * 1e3
-for cin in (5, 8):
-    x = torch.randn(5, cin, 480, 864, device=dev).contiguous(memory_format=torch.channels_last)
-    w = torch.randn(64, cin, 7, 7, device=dev).contiguous(memory_format=torch.channels_last)
-    bias = torch.zeros(64, device=dev)
-    print('stem conv cin', cin, 'fused relu', t(lambda: torch.cudnn_convolution_relu(x, w, bias, (2, 2), (3, 3), (1, 1), 1)), 'us; plain', t(lambda: F.conv2d(x, w, bias, 2, 3)), 'us')
-    xn = x.contiguous()
-    wn = w.contiguous()
-    print('   NCHW plain', t(lambda: F.conv2d(xn, wn, bias, 2, 3)), 'us')
-

@@ -106,7 +106,7 @@ def main():
         print(json.dumps({'workload': f'train_step_b{args.batch}_t3_n2_{args.size}x{args.size}', 'n_gpus': world, 'steps': args.steps,
                           'ms_per_step': ms.item() / args.steps, 'clips_per_s': world * args.batch * args.steps / (ms.item() / 1e3),
                           'loss_first': float(losses[0]), 'loss_last': float(losses[-1]),
-                          'memory': 'fused EM + readout kernels forward, swem_em_backward + torch readout backward'}), flush=True)
+                          'memory': 'fused EM + readout kernels forward, swem_em_backward + swem_readout_backward'}), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
