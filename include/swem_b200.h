@@ -180,6 +180,11 @@ int swem_upsample_add(const float* lo_a, const float* lo_b, const float* bias, c
                       int32_t h, int32_t w, int32_t H, int32_t W, int32_t C, float* x, float* x_relu, void* stream);
 int swem_bias_add_act(const float* a, const float* b, const float* bias, int64_t pixels, int32_t C, int32_t relu,
                       float* out, void* stream);
+/* Tail of the decoder: out[bn, y, x] = bp + sum_{dy, dx, c} wp[dy][dx][c] * relu(a + b + bias[c])[bn, y+dy-1, x+dx-1, c]
+ * -- the residual add of the last ResBlock (networks.py:25-32), the ReLU and the 3x3 `pred` conv to one logit plane
+ * (networks.py:205-213) in one pass.  a, b: [BN, H, W, C] NHWC; wp: [3, 3, C]; out: [BN, H, W]; C % 32 == 0.          */
+int swem_resblock_tail_pred(const float* a, const float* b, const float* bias, const float* wp, float bp, int32_t BN,
+                            int32_t H, int32_t W, int32_t C, float* out, void* stream);
 /* Input of a ResNet stem in space-to-depth form (see stages.cu): frame [B, 3, H, W]; masks [B, N+1, H, W] or NULL;
  * mean3 / std3: HOST pointers to the 3 normalisation constants (networks.py:72-73); planes = 3 (key encoder, N = 1),
  * 4 (+ object mask, single-object value encoder) or 5 (+ mask of the other objects, networks.py:115-117);

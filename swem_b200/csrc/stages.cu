@@ -105,6 +105,57 @@ __global__ void __launch_bounds__(256) maxpool3x3s2_kernel(const float4* __restr
   out[idx] = m;
 }
 
+// Tail of the decoder in one pass: the last ResBlock's residual add (networks.py:25-32), the ReLU and the 3x3 `pred`
+// conv to ONE logit plane (networks.py:205-213):  out[y, x] = bp + sum_{dy,dx,c} wp[dy][dx][c] relu(a + b + bias)[y+dy-1, x+dx-1, c]
+// (zero padding).  A 256 -> 1 conv is pure bandwidth (cuDNN: 106 us for 133 MB at 480p / 5 objects) on top of the 133 MB
+// write + read of its input; here a and b are read once (+ halo) and nothing but the logit plane is written.
+// CTA = 16 x 32 output pixels (2 per thread), channels in chunks of 32 through a swizzled smem tile of the 18 x 34 halo.
+constexpr int kTpTH = 16, kTpTW = 32, kTpHalo = (kTpTH + 2) * (kTpTW + 2);
+__global__ void __launch_bounds__(256, 2) resblock_tail_pred_kernel(const float4* __restrict__ a, const float4* __restrict__ b,
+                                                                    const float4* __restrict__ bias, const float4* __restrict__ wp,
+                                                                    float bp, int H, int W, int C4, float* __restrict__ out) {
+  extern __shared__ float4 tp_smem[];
+  float4* tile = tp_smem;                    // [kTpHalo][8] float4, slot (c4 + px) & 7
+  float4* wsm = tp_smem + kTpHalo * 8;       // [9][8] float4 of the current channel chunk
+  const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+  const int x0 = blockIdx.x * kTpTW, y0 = blockIdx.y * kTpTH, bn = blockIdx.z;
+  const long long img = (long long)bn * H * W;
+  float acc0 = 0.f, acc1 = 0.f;
+  for (int ch = 0; ch < C4; ch += 8) {
+    for (int i = tid; i < kTpHalo * 8; i += 256) {
+      const int px = i >> 3, c4 = i & 7;
+      const int y = y0 - 1 + px / (kTpTW + 2), x = x0 - 1 + px % (kTpTW + 2);
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (y >= 0 && y < H && x >= 0 && x < W) {
+        const long long g = (img + (long long)y * W + x) * C4 + ch + c4;
+        v = f4relu(f4add(f4add(__ldg(a + g), __ldg(b + g)), __ldg(bias + ch + c4)));
+      }
+      tile[px * 8 + ((c4 + px) & 7)] = v;
+    }
+    if (tid < 72) wsm[tid] = __ldg(wp + (tid >> 3) * C4 + ch + (tid & 7));
+    __syncthreads();
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        const int p0 = (ty + dy) * (kTpTW + 2) + tx + dx, p1 = p0 + 8 * (kTpTW + 2);
+#pragma unroll
+        for (int c4 = 0; c4 < 8; ++c4) {
+          const float4 w = wsm[(dy * 3 + dx) * 8 + c4];
+          const float4 v0 = tile[p0 * 8 + ((c4 + p0) & 7)], v1 = tile[p1 * 8 + ((c4 + p1) & 7)];
+          acc0 = fmaf(w.x, v0.x, fmaf(w.y, v0.y, fmaf(w.z, v0.z, fmaf(w.w, v0.w, acc0))));
+          acc1 = fmaf(w.x, v1.x, fmaf(w.y, v1.y, fmaf(w.z, v1.z, fmaf(w.w, v1.w, acc1))));
+        }
+      }
+    __syncthreads();
+  }
+  const int x = x0 + tx;
+  if (x < W) {
+    if (y0 + ty < H) out[img + (long long)(y0 + ty) * W + x] = acc0 + bp;
+    if (y0 + ty + 8 < H) out[img + (long long)(y0 + ty + 8) * W + x] = acc1 + bp;
+  }
+}
+
 // Input of a ResNet stem (7x7 / stride 2 / padding 3 conv) in "space-to-depth" form, NHWC with a zero border:
 //   out[n, Y, X, 4*ci + 2*p + q] = plane_ci[2*(Y - 2) + p, 2*(X - 2) + q]        (0 outside the image / for pad channels)
 // over planes ci = 0..2: (frame - mean) / std  (networks.py:77, :115, :154), ci = 3: the object's mask, ci = 4: the mask
@@ -176,6 +227,26 @@ int swem_bias_add_act(const float* a, const float* b, const float* bias, int64_t
   bias_add_act_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const float4*>(a), reinterpret_cast<const float4*>(b), reinterpret_cast<const float4*>(bias), total4, C / 4,
       relu, reinterpret_cast<float4*>(out));
+  SWEM_LAUNCH_CHECK();
+  return SWEM_OK;
+}
+
+int swem_resblock_tail_pred(const float* a, const float* b, const float* bias, const float* wp, float bp, int32_t BN, int32_t H,
+                            int32_t W, int32_t C, float* out, void* stream) {
+  reset_launch_count();
+  SWEM_CHECK_ARG(a && b && bias && wp && out, "NULL pointer");
+  SWEM_CHECK_ARG(BN > 0 && BN <= 65535 && H > 0 && W > 0 && C > 0 && C % 32 == 0, "bad sizes BN=%d H=%d W=%d C=%d (C must be a multiple of 32)",
+                 BN, H, W, C);
+  const size_t smem = (size_t)(kTpHalo * 8 + 72) * sizeof(float4);
+  static bool attr_set = false;
+  if (!attr_set) {
+    SWEM_CUDA(cudaFuncSetAttribute(resblock_tail_pred_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  dim3 grid((W + kTpTW - 1) / kTpTW, (H + kTpTH - 1) / kTpTH, BN);
+  resblock_tail_pred_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const float4*>(a), reinterpret_cast<const float4*>(b), reinterpret_cast<const float4*>(bias),
+      reinterpret_cast<const float4*>(wp), bp, H, W, C / 4, out);
   SWEM_LAUNCH_CHECK();
   return SWEM_OK;
 }

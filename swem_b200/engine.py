@@ -177,6 +177,8 @@ class FrameEngine:
                  'down': None if rb.downsample is None else self._plain(rb.downsample)}
             self.d_up.append(d)
         self.d_pred = self._plain(dec.pred)
+        self.d_pred_w = dec.pred.weight.detach().float()[0].permute(1, 2, 0).contiguous()      # [3, 3, C] for the fused tail
+        self.d_pred_b = float(dec.pred.bias.detach().float()[0]) if dec.pred.out_channels == 1 else None
         # per-channel constants handed to the fused glue kernels instead of separate bias passes: the biases of the convs
         # that feed each up-sampling (conv2 [+ downsample] of the previous ResBlock, skip_conv of this level), and of the last ResBlock
         def bias_of(p: ConvP):
@@ -356,8 +358,23 @@ class FrameEngine:
             x, xr = self._upsample_add(lo_a, lo_b, bias, skip, n)
             lo_a = self._conv(self._conv(xr, d['c1'], relu=True), self._nobias(d['c2']))
             lo_b = x if d['down'] is None else self._conv(x, self._nobias(d['down']))
-        lr = self._conv(self._bias_add_relu(lo_a, lo_b, self.d_bias[-1]), self.d_pred)      # (B*n, 1, Hl, Wl)
+        lr = self._tail_pred(lo_a, lo_b, self.d_bias[-1])                                     # (B*n, 1, Hl, Wl)
         return self.model.decode_from_lowres(lr, n, valid_obj, out_size)
+
+    def _tail_pred(self, a, b, bias):
+        """pred(relu(a + b + bias)): residual tail of the last ResBlock + ReLU + the 3x3 conv to one logit plane."""
+        if (self._glue_ok(a, b) and a.shape[1] % 32 == 0 and self.d_pred_b is not None and a.shape[0] <= 65535
+                and self.d_pred[2] == 1 and self.d_pred[3] == 1):
+            a, b = self._cl(a), self._cl(b)
+            bn, c, h, w = a.shape
+            out = torch.empty((bn, 1, h, w), device=a.device, dtype=torch.float32)
+            with torch.cuda.device(a.device):
+                rc = _lib.load().swem_resblock_tail_pred(a.data_ptr(), b.data_ptr(), bias.data_ptr(), self.d_pred_w.data_ptr(),
+                                                         self.d_pred_b, bn, h, w, c, out.data_ptr(),
+                                                         torch.cuda.current_stream(a.device).cuda_stream)
+            _lib.check(rc, 'swem_resblock_tail_pred')
+            return out
+        return self._conv(self._bias_add_relu(a, b, bias), self.d_pred)
 
     _MODES = {'encode_key': 'encode_key', 'encode_value': 'encode_value', 'match': 'match', 'segment': 'decode'}
 

@@ -160,3 +160,42 @@ class GraphedSequenceRunner(SequenceRunner):
         self._frame.copy_(frame, non_blocking=True)
         self._graph.replay()
         return self._pred
+
+
+class FrameUploader:
+    """Double-buffered host -> device upload of frames on a side stream, so that the copy of frame k+1 from pinned host
+    memory overlaps the processing of frame k (what a streaming caller of the runners does; bench.py's end-to-end leg).
+
+        up = FrameUploader((1, 3, h, w), device)
+        up.submit(0, host[0])
+        for k in range(n):
+            if k + 1 < n: up.submit(k + 1, host[k + 1])
+            mask = runner.step(up.get(k))
+            up.release(k)
+    """
+
+    def __init__(self, shape, device, depth: int = 2):
+        self.device = torch.device(device)
+        self.stream = torch.cuda.Stream(self.device)
+        self.bufs = [torch.empty(shape, device=self.device) for _ in range(depth)]
+        self.ready = [torch.cuda.Event() for _ in range(depth)]
+        self.free = [None] * depth
+        self.stream.wait_stream(torch.cuda.current_stream(self.device))     # nothing is copied before the caller's "now"
+
+    def submit(self, k: int, host_frame: torch.Tensor) -> None:
+        i = k % len(self.bufs)
+        with torch.cuda.stream(self.stream):
+            if self.free[i] is not None:
+                self.stream.wait_event(self.free[i])                        # the consumer of the previous occupant is done
+            self.bufs[i].copy_(host_frame, non_blocking=True)
+            self.ready[i].record(self.stream)
+
+    def get(self, k: int) -> torch.Tensor:
+        i = k % len(self.bufs)
+        torch.cuda.current_stream(self.device).wait_event(self.ready[i])
+        return self.bufs[i]
+
+    def release(self, k: int) -> None:
+        i = k % len(self.bufs)
+        self.free[i] = torch.cuda.Event()
+        self.free[i].record(torch.cuda.current_stream(self.device))

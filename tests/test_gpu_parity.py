@@ -595,7 +595,9 @@ def test_decoder_glue_kernels_match_torch():
     import torch.nn.functional as F
     from swem_b200 import SWEM, make_config
     from swem_b200.engine import FrameEngine
-    eng = FrameEngine(SWEM(make_config(keydim=64, n_bases=16, n_iters=1, topl=8, backbone='resnet18')).eval())
+    torch.manual_seed(0)
+    eng = FrameEngine(SWEM(make_config(keydim=64, n_bases=16, n_iters=1, topl=8, backbone='resnet18')).eval().to(DEV))
+    eng.refresh()
     g = torch.Generator().manual_seed(0)
     cl = lambda t: t.to(DEV).contiguous(memory_format=torch.channels_last)
     for (B, n, C, h, w, H, W) in [(1, 5, 256, 60, 108, 120, 216), (2, 3, 64, 7, 9, 14, 18), (1, 2, 8, 5, 6, 9, 11)]:
@@ -614,3 +616,14 @@ def test_decoder_glue_kernels_match_torch():
         for (hh, ww) in ((H, W), (H + 1, W + 1)):
             t = cl(torch.randn(B * n, C, hh, ww, generator=g))
             assert torch.equal(eng._maxpool(t), F.max_pool2d(t, 3, stride=2, padding=1))
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        pred = eng.model.decoder.pred
+        for (bn, hh, ww) in ((5, 120, 216), (2, 19, 45)):
+            a, b = cl(torch.randn(bn, 256, hh, ww, generator=g)), cl(torch.randn(bn, 256, hh, ww, generator=g))
+            bias = torch.randn(256, generator=g).to(DEV)
+            want = pred(torch.relu(a + b + bias.view(1, -1, 1, 1)))
+            check('tail_pred', maxrel(eng._tail_pred(a, b, bias), want), 1e-5)
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
