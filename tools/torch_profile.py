@@ -31,3 +31,8 @@ for e in rows[:70]:
     print(f'{e.self_device_time_total / 3:10.1f} {e.count / 3:6.1f}  {e.key:34s} {str(e.input_shapes)[:150]}')
 print('total self CUDA us per frame', sum(e.self_device_time_total for e in rows) / 3)
 
+ks = [e for e in prof.key_averages() if 'swem::' in e.key]
+ks.sort(key=lambda e: -e.self_device_time_total)
+print('library kernels: self CUDA us per frame | calls per frame | kernel')
+for e in ks:
+    print(f'{e.self_device_time_total / 3:10.1f} {e.count / 3:6.1f}  {e.key[:110]}')
