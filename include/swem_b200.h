@@ -126,6 +126,8 @@ typedef struct SwemReadArgs {
   void*  workspace;          /* >= swem_readout_workspace_bytes(&dims, path)                      */
   size_t workspace_bytes;
   int32_t path;              /* SwemPath                                                          */
+  int32_t out_pixel_major;   /* 0: out is [B*N, out_channels, HW] (reference, NCHW); 1: [B*N, HW, out_channels] (NHWC,
+                                what a channels-last fusion conv consumes without a layout copy)          */
 } SwemReadArgs;
 
 size_t swem_readout_workspace_bytes(const SwemDims* dims, int32_t path);

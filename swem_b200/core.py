@@ -237,7 +237,8 @@ class SWEMCore(nn.Module):
 
     def readout_into(self, qk, feats, mem_channel: int, s_channel: int) -> torch.Tensor:
         """Readout kernels only (no autograd): write ``mem_out`` into channels [mem_channel, +Cv) and ``S`` into
-        channels [s_channel, +2*topl) of the caller's contiguous fp32 buffer ``feats`` (B*N, C, H, W).  The reference
+        channels [s_channel, +2*topl) of the caller's fp32 buffer ``feats`` (B*N, C, H, W), which is either contiguous
+        (NCHW, the reference layout) or channels-last (NHWC; the kernels then write pixel-major).  The reference
         layout is ``matching_features``; inference engines that split the fusion conv use a narrower buffer."""
         banks = self._banks()
         if not banks:
@@ -253,7 +254,9 @@ class SWEMCore(nn.Module):
         _, N, _, Cv, L = nus[0].shape
         dev = qk.device
         chans = feats.shape[1]
-        if (not feats.is_cuda or feats.dtype != torch.float32 or not feats.is_contiguous()
+        pixel_major = 0 if feats.is_contiguous() else 1
+        if (not feats.is_cuda or feats.dtype != torch.float32
+                or not (feats.is_contiguous() or feats.is_contiguous(memory_format=torch.channels_last))
                 or feats.shape != (B * N, chans, H, W) or mem_channel < 0 or mem_channel + Cv > chans
                 or s_channel < 0 or s_channel + 2 * self.topl > chans):
             raise RuntimeError(f'readout: bad output buffer {tuple(feats.shape)} {feats.dtype} for B*N={B * N}, '
@@ -267,7 +270,7 @@ class SWEMCore(nn.Module):
                                  (C.c_void_p * 2)(*[k.data_ptr() for k in kap] + [None] * (2 - len(kap))),
                                  (C.c_void_p * 2)(*[n.data_ptr() for n in nus] + [None] * (2 - len(nus))),
                                  feats.data_ptr(), chans, mem_channel, s_channel,
-                                 ws.data_ptr(), ws.numel(), self.readout_path)
+                                 ws.data_ptr(), ws.numel(), self.readout_path, pixel_major)
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev).cuda_stream
             rc = _invoke('readout', lambda: lib.swem_readout_forward(C.byref(args), stream))

@@ -84,6 +84,6 @@ int fused_readout_forward(const SwemReadArgs& a, cudaStream_t st);
 // shared between families: sorted top-l prefix feature from normalised attention rows
 // P: [U, HW, 2*Lt] fp32 (row per pixel, column = side*Lt + j) -> out channels [s_channel, +2*topl)
 int launch_perm_inv(const float* P, int U, int HW, int Lt, int topl, float* out, int out_channels,
-                    int s_channel, cudaStream_t st);
+                    int s_channel, int pixel_major, cudaStream_t st);
 
 }  // namespace swem

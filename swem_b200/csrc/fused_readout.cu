@@ -70,7 +70,7 @@ struct ReadoutFusedParams {
   float* out;             // [U][out_channels][HW]
   float* escratch;        // [U][HW][2*Lt] fp32 un-normalised E (for the top-l feature)
   long long* prof;        // optional phase stamps of CTA 0 (slots 128..), see swem_set_profile_buffer
-  int N, HW, T, n_banks, out_channels, mem_channel;
+  int N, HW, T, n_banks, out_channels, mem_channel, pixel_major;
   float c1s;              // log2(e) / (tau * kKScale)
 };
 
@@ -374,15 +374,31 @@ __global__ void __launch_bounds__(256, 1) readout_fused_kernel(const ReadoutFuse
   {
     const int nh = warp >> 2;
     const float scale = inv_total;             // the 2^10 of E cancels against the row sum of the same operand
-    float* obase = p.out + ((size_t)u * p.out_channels + p.mem_channel + h * kDH + nh * 128) * HW + p0 + px;
     const bool in_range = p0 + px < HW;
-    for (int q = 0; q < 4; ++q) {
-      uint32_t r[32];
-      tmem_ld32(tmem_addr(tmem, lane_base, 128 + nh * 256 + q * 32), r);
-      tmem_ld_wait();
-      if (in_range) {
+    if (p.pixel_major) {
+      // [U][HW][out_channels]: a thread owns 128 consecutive channels of its pixel -> 16-byte stores
+      float4* obase = reinterpret_cast<float4*>(p.out + ((size_t)u * HW + p0 + px) * p.out_channels + p.mem_channel + h * kDH + nh * 128);
+      for (int q = 0; q < 4; ++q) {
+        uint32_t r[32];
+        tmem_ld32(tmem_addr(tmem, lane_base, 128 + nh * 256 + q * 32), r);
+        tmem_ld_wait();
+        if (in_range) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) obase[(size_t)(q * 32 + j) * HW] = __uint_as_float(r[j]) * scale;
+          for (int j = 0; j < 8; ++j)
+            obase[q * 8 + j] = make_float4(__uint_as_float(r[4 * j]) * scale, __uint_as_float(r[4 * j + 1]) * scale,
+                                           __uint_as_float(r[4 * j + 2]) * scale, __uint_as_float(r[4 * j + 3]) * scale);
+        }
+      }
+    } else {
+      float* obase = p.out + ((size_t)u * p.out_channels + p.mem_channel + h * kDH + nh * 128) * HW + p0 + px;
+      for (int q = 0; q < 4; ++q) {
+        uint32_t r[32];
+        tmem_ld32(tmem_addr(tmem, lane_base, 128 + nh * 256 + q * 32), r);
+        tmem_ld_wait();
+        if (in_range) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) obase[(size_t)(q * 32 + j) * HW] = __uint_as_float(r[j]) * scale;
+        }
       }
     }
   }
@@ -438,12 +454,13 @@ int fused_readout_forward(const SwemReadArgs& a, cudaStream_t st) {
   ReadoutFusedParams p{};
   p.qk = a.qk; p.kblob = kblob; p.vblob = vblob; p.out = a.out; p.escratch = escr;
   p.N = d.N; p.HW = d.HW; p.T = T; p.n_banks = nb; p.out_channels = a.out_channels; p.mem_channel = a.mem_channel;
+  p.pixel_major = a.out_pixel_major;
   p.c1s = kLog2e / (d.tau * ro::kKScale);
   p.prof = get_profile_buffer();
   if (nb == 1) readout_fused_kernel<1><<<U * T * 2, 256, ro::kSmemBytes, st>>>(p);
   else readout_fused_kernel<2><<<U * T * 2, 256, ro::kSmemBytes, st>>>(p);
   SWEM_LAUNCH_CHECK();
-  return launch_perm_inv(escr, U, d.HW, Lt, d.topl, a.out, a.out_channels, a.s_channel, st);
+  return launch_perm_inv(escr, U, d.HW, Lt, d.topl, a.out, a.out_channels, a.s_channel, a.out_pixel_major, st);
 }
 
 }  // namespace swem

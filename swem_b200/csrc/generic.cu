@@ -298,7 +298,7 @@ __device__ __forceinline__ void bitonic_desc2(uint32_t (&a)[NPL], uint32_t (&b)[
 template <int NPL>
 __global__ void __launch_bounds__(256) perm_inv_kernel(const float* __restrict__ P, int U, int HW, int Lt,
                                                        int topl, float* __restrict__ out, int out_channels,
-                                                       int s_channel) {
+                                                       int s_channel, int pixel_major) {
   constexpr int N = 32 * NPL;
   constexpr int IDXB = (NPL == 1 ? 5 : NPL == 2 ? 6 : NPL == 4 ? 7 : NPL == 8 ? 8 : NPL == 16 ? 9 : 10);
   constexpr int PXB = 8;                                        // pixels per block: one per warp (many small blocks balance the SMs)
@@ -368,14 +368,21 @@ __global__ void __launch_bounds__(256) perm_inv_kernel(const float* __restrict__
   }
   __syncthreads();
   const int npx = min(PXB, HW - p_base);
-  for (int e = threadIdx.x; e < 2 * topl * PXB; e += blockDim.x) {
-    const int ch = e / PXB, q = e % PXB;
-    if (q < npx) out[((long long)u * out_channels + s_channel + ch) * HW + p_base + q] = tile[ch * (PXB + 1) + q];
+  if (pixel_major) {                                            // [U][HW][out_channels]: channels of a pixel are contiguous
+    for (int e = threadIdx.x; e < 2 * topl * PXB; e += blockDim.x) {
+      const int q = e / (2 * topl), ch = e % (2 * topl);
+      if (q < npx) out[((long long)u * HW + p_base + q) * out_channels + s_channel + ch] = tile[ch * (PXB + 1) + q];
+    }
+  } else {
+    for (int e = threadIdx.x; e < 2 * topl * PXB; e += blockDim.x) {
+      const int ch = e / PXB, q = e % PXB;
+      if (q < npx) out[((long long)u * out_channels + s_channel + ch) * HW + p_base + q] = tile[ch * (PXB + 1) + q];
+    }
   }
 }
 
 int launch_perm_inv(const float* P, int U, int HW, int Lt, int topl, float* out, int out_channels,
-                    int s_channel, cudaStream_t st) {
+                    int s_channel, int pixel_major, cudaStream_t st) {
   if (topl > 64) {
     set_error("perm_inv: topl=%d > 64 unsupported", topl);
     return SWEM_ERR_UNSUPPORTED;
@@ -383,7 +390,7 @@ int launch_perm_inv(const float* P, int U, int HW, int Lt, int topl, float* out,
   dim3 grid((HW + 7) / 8, U);
   const size_t smem = (size_t)2 * topl * 9 * sizeof(float) + 8 * 128 * sizeof(uint32_t);
   const int npl = (Lt + 31) / 32;
-#define SWEM_PI(NPL_) perm_inv_kernel<NPL_><<<grid, 256, smem, st>>>(P, U, HW, Lt, topl, out, out_channels, s_channel)
+#define SWEM_PI(NPL_) perm_inv_kernel<NPL_><<<grid, 256, smem, st>>>(P, U, HW, Lt, topl, out, out_channels, s_channel, pixel_major)
   if (npl <= 1) SWEM_PI(1);
   else if (npl <= 2) SWEM_PI(2);
   else if (npl <= 4) SWEM_PI(4);
@@ -586,7 +593,8 @@ int generic_readout_forward(const SwemReadArgs& a, cudaStream_t st) {
     for (int k = 0; k < d.n_banks; ++k) {
       GemmShape g{};
       g.M = d.Cv; g.N = d.HW; g.K = d.L;
-      g.sAm = d.L; g.sAk = 1; g.sBk = 1; g.sBn = W2; g.sCm = d.HW; g.sCn = 1;
+      g.sAm = d.L; g.sAk = 1; g.sBk = 1; g.sBn = W2;
+      g.sCm = a.out_pixel_major ? 1 : d.HW; g.sCn = a.out_pixel_major ? a.out_channels : 1;
       g.n0 = d.B; g.n1 = d.N; g.n2 = 1;
       g.bA[0] = (long long)d.N * 2 * d.Cv * d.L; g.bA[1] = 2LL * d.Cv * d.L; g.bA[2] = 0;
       g.bB[0] = (long long)d.N * d.HW * W2; g.bB[1] = (long long)d.HW * W2; g.bB[2] = 0;
@@ -594,10 +602,10 @@ int generic_readout_forward(const SwemReadArgs& a, cudaStream_t st) {
       g.accumulate = first ? 0 : 1;
       first = false;
       if (int rc = launch_gemm(a.nu[k] + (size_t)s * d.Cv * d.L, P + (size_t)s * Lt + (size_t)k * d.L,
-                               a.out + (size_t)a.mem_channel * d.HW, g, st))
+                               a.out + (a.out_pixel_major ? (size_t)a.mem_channel : (size_t)a.mem_channel * d.HW), g, st))
         return rc;
     }
-  return launch_perm_inv(P, U, d.HW, Lt, d.topl, a.out, a.out_channels, a.s_channel, st);
+  return launch_perm_inv(P, U, d.HW, Lt, d.topl, a.out, a.out_channels, a.s_channel, a.out_pixel_major, st);
 }
 
 

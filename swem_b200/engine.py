@@ -298,8 +298,9 @@ class FrameEngine:
         core = self.model.swem_core
         n, cv = core._readout_objects()
         bsz, _, h, w = qk16.shape
-        feats = torch.empty(bsz * n, cv + 2 * core.topl, h, w, device=qk16.device, dtype=torch.float32)
-        core.readout_into(qk16, feats, 0, cv)                      # [mem_out | S]
+        feats = torch.empty((bsz * n, cv + 2 * core.topl, h, w), device=qk16.device, dtype=torch.float32,
+                            memory_format=torch.channels_last if self.channels_last else torch.contiguous_format)
+        core.readout_into(qk16, feats, 0, cv)                      # [mem_out | S], written NHWC for the channels-last conv
         shared = self._conv(qv16, self.g_shared)                   # (B, 1024, H, W): [layer_f | layer_a] of the qv third
         y = self._conv(feats, self.g_obj)
         y = y.view(bsz, n, *y.shape[1:]).add_(shared.unsqueeze(1)).flatten(end_dim=1)

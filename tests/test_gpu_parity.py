@@ -627,3 +627,25 @@ def test_decoder_glue_kernels_match_torch():
             check('tail_pred', maxrel(eng._tail_pred(a, b, bias), want), 1e-5)
     finally:
         torch.backends.cudnn.allow_tf32 = old
+
+
+@pytest.mark.parametrize('family', ['generic', 'fused'])
+def test_readout_pixel_major_output_matches_nchw(family):
+    """SwemReadArgs.out_pixel_major: the same readout written into a channels-last (NHWC) buffer, narrow layout
+    [mem_out | S] as FrameEngine uses it; ragged HW (30 x 53)."""
+    B, N, Ck, Cv, L, H, W, topl = 1, 3, 64, 512, 128, 30, 53, 64
+    _skip_unless_covered(family, B=B, N=N, Ck=Ck, Cv=Cv, HW=H * W, L=L, topl=topl, what='readout')
+    core = _core(dict(L=L, Cv=Cv, n_iters=1, tau=0.05, topl=topl), family)
+    g = torch.Generator().manual_seed(2)
+    for name in ('first', 'update'):
+        k, _, _ = O.random_init(B, N, Ck, L, Cv, generator=g)
+        core.memories[name].bases = _to({'kappa': k, 'nu': torch.randn(B, N, 2, Cv, L, generator=g), 'zita': torch.ones(B, N, 2, 1, L)}, DEV)
+    core.memories['first'].n_objs = N
+    qk = (torch.randn(B, Ck, H, W, generator=g) * 2.3).to(DEV)
+    chans = Cv + 2 * topl
+    with torch.no_grad():
+        a = core.readout_into(qk, torch.full((B * N, chans, H, W), float('nan'), device=DEV), 0, Cv)
+        b = torch.full((B * N, chans, H, W), float('nan'), device=DEV).contiguous(memory_format=torch.channels_last)
+        b = core.readout_into(qk, b, 0, Cv)
+    assert b.is_contiguous(memory_format=torch.channels_last) and not b.is_contiguous()
+    assert torch.isfinite(a).all() and torch.equal(a, b.contiguous())
