@@ -176,12 +176,18 @@ int swem_decode_tail(const float* logits_lr, int32_t B, int32_t N, int32_t Hl, i
  *                       lo_a, lo_b: [BN, h, w, C]; skip: [BN / n, H, W, C]; x, x_relu: [BN, H, W, C]; bilinear with
  *                       align_corners = false (ATen index arithmetic); `bias` carries the per-channel biases of the
  *                       convolutions that produced lo_a / lo_b / skip (interpolation reproduces constants).
- *   swem_bias_add_act : out = act(a (+ b) (+ bias[c])) over `pixels` x C, act = relu or identity.
+ *   swem_bias_add_act : out = act(a (+ b) (+ c_shared) (+ bias[ch])); a, b, out: [images, pixels, C]; c_shared:
+ *                       [images / n_share, pixels, C] (one row block per n_share consecutive images); act = relu or identity.
+ *   swem_glu_gate     : FeatureFusionLayer.forward (modules.py:13-26) on stacked pre-activations y = [layer_f | layer_a]:
+ *                       out[.., ch] = (y_f + s_f + b_f) * sigmoid(y_a + s_a + b_a); y: [images, pixels, 2C]; shared:
+ *                       [images / n_share, pixels, 2C]; bias: [2C]; out: [images, pixels, C].
  * C must be a multiple of 4; optional pointers may be NULL.                                                       */
 int swem_upsample_add(const float* lo_a, const float* lo_b, const float* bias, const float* skip, int32_t BN, int32_t n,
                       int32_t h, int32_t w, int32_t H, int32_t W, int32_t C, float* x, float* x_relu, void* stream);
-int swem_bias_add_act(const float* a, const float* b, const float* bias, int64_t pixels, int32_t C, int32_t relu,
-                      float* out, void* stream);
+int swem_bias_add_act(const float* a, const float* b, const float* c_shared, const float* bias, int32_t images,
+                      int32_t n_share, int64_t pixels, int32_t C, int32_t relu, float* out, void* stream);
+int swem_glu_gate(const float* y, const float* shared, const float* bias, int32_t images, int32_t n_share, int64_t pixels,
+                  int32_t C, float* out, void* stream);
 /* Tail of the decoder: out[bn, y, x] = bp + sum_{dy, dx, c} wp[dy][dx][c] * relu(a + b + bias[c])[bn, y+dy-1, x+dx-1, c]
  * -- the residual add of the last ResBlock (networks.py:25-32), the ReLU and the 3x3 `pred` conv to one logit plane
  * (networks.py:205-213) in one pass.  a, b: [BN, H, W, C] NHWC; wp: [3, 3, C]; out: [BN, H, W]; C % 32 == 0.          */

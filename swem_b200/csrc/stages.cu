@@ -6,7 +6,8 @@
 // objects.  These two kernels do the same arithmetic in one pass each:
 //
 //   upsample_add:  x = skip[b] + bilinear(lo_a [+ lo_b]) + bias      (also writes relu(x), the next conv's input)
-//   bias_add_act:  out = act(a [+ b] + bias)
+//   bias_add_act:  out = act(a [+ b] [+ c shared by the n objects] + bias)
+//   glu_gate:      the GLU of the fusion layer on [layer_f | layer_a] pre-activations, object-independent part added in
 //   maxpool3x3s2:  the 3x3 / stride-2 pooling after both ResNet stems (ATen's NHWC pooling kernel runs at ~1 TB/s)
 //
 // `skip` is shared by the n objects of a batch element (the reference recomputes skip_conv per object), the biases of the
@@ -68,14 +69,39 @@ __global__ void __launch_bounds__(256) upsample_add_kernel(const float4* __restr
 }
 
 __global__ void __launch_bounds__(256) bias_add_act_kernel(const float4* __restrict__ a, const float4* __restrict__ b,
-                                                           const float4* __restrict__ bias, long long total4, int C4, int relu,
+                                                           const float4* __restrict__ c, const float4* __restrict__ bias,
+                                                           long long total4, long long per_image4, int n_share, int C4, int relu,
                                                            float4* __restrict__ out) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total4) return;
   float4 v = __ldg(a + idx);
   if (b != nullptr) v = f4add(v, __ldg(b + idx));
+  if (c != nullptr) v = f4add(v, __ldg(c + (idx / (per_image4 * n_share)) * per_image4 + idx % per_image4));   // shared by n_share images
   if (bias != nullptr) v = f4add(v, __ldg(bias + (int)(idx % C4)));
   out[idx] = relu ? f4relu(v) : v;
+}
+
+// GLU gate of the fusion layer (modules.py:13-26): y [BN, pixels, 2C] = [layer_f | layer_a] pre-activations of the
+// per-object conv, `shared` [BN / n, pixels, 2C] the object-independent part (+ bias [2C]):
+//   out[bn, p, c] = (y_f + s_f + b_f) * sigmoid(y_a + s_a + b_a)
+__global__ void __launch_bounds__(256) glu_gate_kernel(const float4* __restrict__ y, const float4* __restrict__ shared,
+                                                       const float4* __restrict__ bias, long long total4, long long pixels, int n,
+                                                       int C4, float4* __restrict__ out) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // over [BN][pixels][C4]
+  if (idx >= total4) return;
+  const int c4 = (int)(idx % C4);
+  const long long px = idx / C4;                                               // bn * pixels + p
+  const long long spx = (px / (pixels * n)) * pixels + px % pixels;
+  float4 f = __ldg(y + px * 2 * C4 + c4), g = __ldg(y + px * 2 * C4 + C4 + c4);
+  if (shared != nullptr) {
+    f = f4add(f, __ldg(shared + spx * 2 * C4 + c4));
+    g = f4add(g, __ldg(shared + spx * 2 * C4 + C4 + c4));
+  }
+  if (bias != nullptr) {
+    f = f4add(f, __ldg(bias + c4));
+    g = f4add(g, __ldg(bias + C4 + c4));
+  }
+  out[idx] = make_float4(f.x / (1.f + expf(-g.x)), f.y / (1.f + expf(-g.y)), f.z / (1.f + expf(-g.z)), f.w / (1.f + expf(-g.w)));
 }
 
 // 3x3 / stride 2 / padding 1 max pooling, NHWC (the stem of both ResNet trunks: torchvision resnet.py `maxpool`,
@@ -218,15 +244,30 @@ int swem_upsample_add(const float* lo_a, const float* lo_b, const float* bias, c
   return SWEM_OK;
 }
 
-int swem_bias_add_act(const float* a, const float* b, const float* bias, int64_t pixels, int32_t C, int32_t relu, float* out,
-                      void* stream) {
+int swem_bias_add_act(const float* a, const float* b, const float* c_shared, const float* bias, int32_t images, int32_t n_share,
+                      int64_t pixels, int32_t C, int32_t relu, float* out, void* stream) {
   reset_launch_count();
   SWEM_CHECK_ARG(a && out, "NULL pointer");
-  SWEM_CHECK_ARG(pixels > 0 && C > 0 && C % 4 == 0, "bad sizes pixels=%lld C=%d (C must be a multiple of 4)", (long long)pixels, C);
-  const long long total4 = (long long)pixels * (C / 4);
+  SWEM_CHECK_ARG(images > 0 && n_share > 0 && images % n_share == 0 && pixels > 0 && C > 0 && C % 4 == 0,
+                 "bad sizes images=%d n_share=%d pixels=%lld C=%d (C must be a multiple of 4)", images, n_share, (long long)pixels, C);
+  const long long per_image4 = (long long)pixels * (C / 4), total4 = per_image4 * images;
   bias_add_act_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const float4*>(a), reinterpret_cast<const float4*>(b), reinterpret_cast<const float4*>(bias), total4, C / 4,
-      relu, reinterpret_cast<float4*>(out));
+      reinterpret_cast<const float4*>(a), reinterpret_cast<const float4*>(b), reinterpret_cast<const float4*>(c_shared),
+      reinterpret_cast<const float4*>(bias), total4, per_image4, n_share, C / 4, relu, reinterpret_cast<float4*>(out));
+  SWEM_LAUNCH_CHECK();
+  return SWEM_OK;
+}
+
+int swem_glu_gate(const float* y, const float* shared, const float* bias, int32_t images, int32_t n_share, int64_t pixels, int32_t C,
+                  float* out, void* stream) {
+  reset_launch_count();
+  SWEM_CHECK_ARG(y && out, "NULL pointer");
+  SWEM_CHECK_ARG(images > 0 && n_share > 0 && images % n_share == 0 && pixels > 0 && C > 0 && C % 4 == 0,
+                 "bad sizes images=%d n_share=%d pixels=%lld C=%d (C must be a multiple of 4)", images, n_share, (long long)pixels, C);
+  const long long total4 = (long long)images * pixels * (C / 4);
+  glu_gate_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const float4*>(y), reinterpret_cast<const float4*>(shared), reinterpret_cast<const float4*>(bias), total4,
+      pixels, n_share, C / 4, reinterpret_cast<float4*>(out));
   SWEM_LAUNCH_CHECK();
   return SWEM_OK;
 }

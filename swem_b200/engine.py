@@ -119,13 +119,22 @@ class FrameEngine:
     def _stage(self, stage) -> List[dict]:
         blocks = []
         for blk in stage:
-            d = {'kind': 'bottle' if isinstance(blk, _Bottle) else 'basic',
-                 'c1': self._folded(blk.conv1, blk.bn1), 'c2': self._folded(blk.conv2, blk.bn2),
-                 'down': None if blk.downsample is None else self._folded(blk.downsample[0], blk.downsample[1])}
-            if isinstance(blk, _Bottle):
-                d['c3'] = self._folded(blk.conv3, blk.bn3)
-            else:
+            last_conv, last_bn = (blk.conv3, blk.bn3) if isinstance(blk, _Bottle) else (blk.conv2, blk.bn2)
+            if not isinstance(blk, _Bottle):
                 assert isinstance(blk, _Basic)
+            w_last, b_last = _fold_bn(last_conv, last_bn)
+            down = None
+            if blk.downsample is not None:
+                # relu(last(y) + b_last + down(x) + b_down): the shortcut's bias rides on the last conv's fused bias,
+                # so the shortcut conv needs no bias pass of its own
+                w_down, b_down = _fold_bn(blk.downsample[0], blk.downsample[1])
+                b_last = b_last + b_down
+                down = self._cp(w_down, None, blk.downsample[0].stride[0], blk.downsample[0].padding[0])
+            d = {'kind': 'bottle' if isinstance(blk, _Bottle) else 'basic',
+                 'c1': self._folded(blk.conv1, blk.bn1), 'down': down,
+                 'last': self._cp(w_last, b_last, last_conv.stride[0], last_conv.padding[0])}
+            if isinstance(blk, _Bottle):
+                d['c2'] = self._folded(blk.conv2, blk.bn2)
             blocks.append(d)
         return blocks
 
@@ -149,22 +158,29 @@ class FrameEngine:
         b1, b2 = ve.fuser.block1, ve.fuser.block2
         cx = ve.layer3[-1].conv2.out_channels                      # channels of the per-object half of cat[x, f16]
         self.f_has_down = b1.downsample is not None                 # reference R50: 1280 -> 512, yes; R18 trunk: 512 -> 512, no
-        convs = [b1.conv1] + ([b1.downsample] if self.f_has_down else [])
-        w = torch.cat([c.weight for c in convs], 0)                 # [2*512, 1280, 3, 3]: rows = [conv1 | downsample]
-        b = torch.cat([c.bias for c in convs], 0)
-        self.f_obj = self._cp(w[:, :cx], None, 1, 1)                # per object, bias carried by the shared half
-        self.f_shared = self._cp(w[:, cx:], b, 1, 1)                # once per frame
-        self.f_mid = b1.conv1.out_channels
-        self.f_b1c2 = self._plain(b1.conv2)
-        self.f_b2c1, self.f_b2c2 = self._plain(b2.conv1), self._plain(b2.conv2)
+        # block1's conv1 (and its downsample) over cat[x_obj, f16], split by linearity: per-object half without bias,
+        # f16 half once per frame; the biases go to the glue kernel that adds the halves
+        self.f_c1_obj = self._cp(b1.conv1.weight[:, :cx], None, 1, 1)
+        self.f_c1_sh = self._cp(b1.conv1.weight[:, cx:], None, 1, 1)
+        self.f_c1_bias = b1.conv1.bias.detach().float().contiguous()
+        if self.f_has_down:
+            self.f_dn_obj = self._cp(b1.downsample.weight[:, :cx], None, 1, 1)
+            self.f_dn_sh = self._cp(b1.downsample.weight[:, cx:], None, 1, 1)
+            self.f_b1_tail_bias = (b1.conv2.bias + b1.downsample.bias).detach().float().contiguous()
+        else:
+            self.f_b1_tail_bias = b1.conv2.bias.detach().float().contiguous()
+        self.f_b1c2 = self._cp(b1.conv2.weight, None, 1, 1)
+        self.f_b2c1 = self._plain(b2.conv1)
+        self.f_b2c2 = self._cp(b2.conv2.weight, None, 1, 1)
+        self.f_b2_tail_bias = b2.conv2.bias.detach().float().contiguous()
 
         core = m.swem_core
         fl = core.fusion_layer
         cv, tl = core.valdim, core.topl
         w = torch.cat([fl.layer_f.weight, fl.layer_a.weight], 0)   # [2*512, 2*Cv + 2*topl, 3, 3]
-        b = torch.cat([fl.layer_f.bias, fl.layer_a.bias], 0)
         self.g_obj = self._cp(torch.cat([w[:, :cv], w[:, 2 * cv:]], 1), None, 1, 1)     # [mem_out | S] channels
-        self.g_shared = self._cp(w[:, cv:2 * cv], b, 1, 1)                               # qv channels
+        self.g_shared = self._cp(w[:, cv:2 * cv], None, 1, 1)                            # qv channels, once per frame
+        self.g_bias = torch.cat([fl.layer_f.bias, fl.layer_a.bias], 0).detach().float().contiguous()
         self.g_out = fl.layer_f.out_channels
 
         if dec.compress.downsample is not None:
@@ -216,11 +232,8 @@ class FrameEngine:
             y = self._conv(x, d['c1'], relu=True)
             if d['kind'] == 'bottle':
                 y = self._conv(y, d['c2'], relu=True)
-                last = d['c3']
-            else:
-                last = d['c2']
             skip = x if d['down'] is None else self._conv(x, d['down'])
-            x = self._conv(y, last, relu=True, add=skip)
+            x = self._conv(y, d['last'], relu=True, add=skip)
         return x
 
     def _maxpool(self, x):
@@ -279,17 +292,16 @@ class FrameEngine:
             y = self._conv(x, self.v_stem, relu=True)
         x = self._trunk(y, self.v_stages)                          # (B*N, 256, H16, W16), post-ReLU
         # fuser.block1 on cat[x, f16]: both halves are post-ReLU, so block1's leading ReLU is the identity
-        shared = self._conv(s16, self.f_shared)                    # (B, 1024, H16, W16): [conv1 | downsample] of the f16 half
-        y = self._conv(x, self.f_obj)
-        y = y.view(bsz, n, *y.shape[1:]).add_(shared.unsqueeze(1)).flatten(end_dim=1)
-        r = self._conv(F.relu(y[:, :self.f_mid]), self.f_b1c2)
+        h1 = self._add_act(self._conv(x, self.f_c1_obj), None, self._conv(s16, self.f_c1_sh), self.f_c1_bias, n, relu=True)
+        r = self._conv(h1, self.f_b1c2)
         if self.f_has_down:
-            x = r.add_(y[:, self.f_mid:])
+            x = self._add_act(r, self._conv(x, self.f_dn_obj), self._conv(s16, self.f_dn_sh), self.f_b1_tail_bias, n, relu=False)
         else:
-            x = r.add_(torch.cat([x.view(bsz, n, *x.shape[1:]), s16.unsqueeze(1).expand(-1, n, -1, -1, -1)], 2).flatten(end_dim=1))
+            skip = torch.cat([x.view(bsz, n, *x.shape[1:]), s16.unsqueeze(1).expand(-1, n, -1, -1, -1)], 2).flatten(end_dim=1)
+            x = self._add_act(r, skip, None, self.f_b1_tail_bias, n, relu=False)
         x = x + ve.fuser.attention(x)
         r = self._conv(self._conv(F.relu(x), self.f_b2c1, relu=True), self.f_b2c2)
-        x = r.add_(x)
+        x = self._add_act(r, x, None, self.f_b2_tail_bias, n, relu=False)
         return x.view(bsz, n, *x.shape[1:])
 
     def match(self, qk16, qv16):
@@ -302,9 +314,7 @@ class FrameEngine:
                             memory_format=torch.channels_last if self.channels_last else torch.contiguous_format)
         core.readout_into(qk16, feats, 0, cv)                      # [mem_out | S], written NHWC for the channels-last conv
         shared = self._conv(qv16, self.g_shared)                   # (B, 1024, H, W): [layer_f | layer_a] of the qv third
-        y = self._conv(feats, self.g_obj)
-        y = y.view(bsz, n, *y.shape[1:]).add_(shared.unsqueeze(1)).flatten(end_dim=1)
-        return y[:, :self.g_out] * torch.sigmoid(y[:, self.g_out:]), n
+        return self._glu(self._conv(feats, self.g_obj), shared, self.g_bias, n), n
 
     @staticmethod
     def _nobias(p: ConvP) -> ConvP:
@@ -336,17 +346,41 @@ class FrameEngine:
         x = up.view(-1, n, *up.shape[1:]).add_(skip.unsqueeze(1)).flatten(end_dim=1).add_(bias.view(1, -1, 1, 1))
         return x, F.relu(x)
 
-    def _bias_add_relu(self, a, b, bias):
-        """relu(a + b + bias): the residual tail of ResBlock.forward (networks.py:25-32) + the ReLU that follows it."""
-        if self._glue_ok(a, b) and a.shape[1] % 4 == 0:
-            a, b = self._cl(a), self._cl(b)
+    def _add_act(self, a, b, shared, bias, n, relu):
+        """act(a + b + shared[image // n] + bias): bias pass, object-independent half, residual add and ReLU in one kernel."""
+        if self._glue_ok(a, b, shared) and a.shape[1] % 4 == 0:
+            a = self._cl(a)
+            b = None if b is None else self._cl(b)
+            shared = None if shared is None else self._cl(shared)
             out = torch.empty_like(a)
+            ptr = lambda t: None if t is None else t.data_ptr()
             with torch.cuda.device(a.device):
-                rc = _lib.load().swem_bias_add_act(a.data_ptr(), b.data_ptr(), bias.data_ptr(), a.shape[0] * a.shape[2] * a.shape[3],
-                                                   a.shape[1], 1, out.data_ptr(), torch.cuda.current_stream(a.device).cuda_stream)
+                rc = _lib.load().swem_bias_add_act(a.data_ptr(), ptr(b), ptr(shared), ptr(bias), a.shape[0], n if shared is not None else 1,
+                                                   a.shape[2] * a.shape[3], a.shape[1], int(relu), out.data_ptr(),
+                                                   torch.cuda.current_stream(a.device).cuda_stream)
             _lib.check(rc, 'swem_bias_add_act')
             return out
-        return F.relu_(a + b + bias.view(1, -1, 1, 1))
+        out = a if b is None else a + b
+        if shared is not None:
+            out = (out.view(-1, n, *out.shape[1:]) + shared.unsqueeze(1)).flatten(end_dim=1)
+        if bias is not None:
+            out = out + bias.view(1, -1, 1, 1)
+        return F.relu(out) if relu else out
+
+    def _glu(self, y, shared, bias, n):
+        """(y_f + s_f + b_f) * sigmoid(y_a + s_a + b_a) on stacked [layer_f | layer_a] pre-activations (modules.py:13-26)."""
+        c = y.shape[1] // 2
+        if self._glue_ok(y, shared) and c % 4 == 0:
+            y, shared = self._cl(y), self._cl(shared)
+            out = torch.empty((y.shape[0], c, y.shape[2], y.shape[3]), device=y.device, dtype=torch.float32,
+                              memory_format=torch.channels_last)
+            with torch.cuda.device(y.device):
+                rc = _lib.load().swem_glu_gate(y.data_ptr(), shared.data_ptr(), bias.data_ptr(), y.shape[0], n, y.shape[2] * y.shape[3], c,
+                                               out.data_ptr(), torch.cuda.current_stream(y.device).cuda_stream)
+            _lib.check(rc, 'swem_glu_gate')
+            return out
+        t = (y.view(-1, n, *y.shape[1:]) + shared.unsqueeze(1)).flatten(end_dim=1) + bias.view(1, -1, 1, 1)
+        return t[:, :c] * torch.sigmoid(t[:, c:])
 
     def decode(self, n, context, s8, s4, valid_obj, out_size):
         """-> (logits, prob) (B, N+1, H, W), as SWEM.decode (swem.py:92-108).  Convolutions whose output only feeds an
@@ -359,10 +393,10 @@ class FrameEngine:
             x, xr = self._upsample_add(lo_a, lo_b, bias, skip, n)
             lo_a = self._conv(self._conv(xr, d['c1'], relu=True), self._nobias(d['c2']))
             lo_b = x if d['down'] is None else self._conv(x, self._nobias(d['down']))
-        lr = self._tail_pred(lo_a, lo_b, self.d_bias[-1])                                     # (B*n, 1, Hl, Wl)
+        lr = self._tail_pred(lo_a, lo_b, self.d_bias[-1], n)                                     # (B*n, 1, Hl, Wl)
         return self.model.decode_from_lowres(lr, n, valid_obj, out_size)
 
-    def _tail_pred(self, a, b, bias):
+    def _tail_pred(self, a, b, bias, n):
         """pred(relu(a + b + bias)): residual tail of the last ResBlock + ReLU + the 3x3 conv to one logit plane."""
         if (self._glue_ok(a, b) and a.shape[1] % 32 == 0 and self.d_pred_b is not None and a.shape[0] <= 65535
                 and self.d_pred[2] == 1 and self.d_pred[3] == 1):
@@ -375,7 +409,7 @@ class FrameEngine:
                                                          torch.cuda.current_stream(a.device).cuda_stream)
             _lib.check(rc, 'swem_resblock_tail_pred')
             return out
-        return self._conv(self._bias_add_relu(a, b, bias), self.d_pred)
+        return self._conv(self._add_act(a, b, None, bias, n, relu=True), self.d_pred)
 
     _MODES = {'encode_key': 'encode_key', 'encode_value': 'encode_value', 'match': 'match', 'segment': 'decode'}
 

@@ -612,7 +612,13 @@ def test_decoder_glue_kernels_match_torch():
             check('upsample_add', maxrel(x, want), 1e-6)
             assert torch.equal(xr, torch.relu(x)) and x.is_contiguous(memory_format=torch.channels_last)
         a, b = cl(torch.randn(B * n, C, H, W, generator=g)), cl(torch.randn(B * n, C, H, W, generator=g))
-        assert torch.equal(eng._bias_add_relu(a, b, bias), torch.relu(a + b + bias.view(1, C, 1, 1)))
+        assert torch.equal(eng._add_act(a, b, None, bias, n, relu=True), torch.relu(a + b + bias.view(1, C, 1, 1)))
+        sh = cl(torch.randn(B, C, H, W, generator=g))
+        want = (a + b).view(B, n, C, H, W) + sh.unsqueeze(1) + bias.view(1, 1, C, 1, 1)
+        check('add_act_shared', maxrel(eng._add_act(a, b, sh, bias, n, relu=False), want.flatten(end_dim=1)), 1e-6)
+        if C % 8 == 0:
+            t = (a.view(B, n, C, H, W) + sh.unsqueeze(1) + bias.view(1, 1, C, 1, 1)).flatten(end_dim=1)
+            check('glu', maxrel(eng._glu(a, sh, bias, n), t[:, :C // 2] * torch.sigmoid(t[:, C // 2:])), 1e-6)
         for (hh, ww) in ((H, W), (H + 1, W + 1)):
             t = cl(torch.randn(B * n, C, hh, ww, generator=g))
             assert torch.equal(eng._maxpool(t), F.max_pool2d(t, 3, stride=2, padding=1))
@@ -624,7 +630,7 @@ def test_decoder_glue_kernels_match_torch():
             a, b = cl(torch.randn(bn, 256, hh, ww, generator=g)), cl(torch.randn(bn, 256, hh, ww, generator=g))
             bias = torch.randn(256, generator=g).to(DEV)
             want = pred(torch.relu(a + b + bias.view(1, -1, 1, 1)))
-            check('tail_pred', maxrel(eng._tail_pred(a, b, bias), want), 1e-5)
+            check('tail_pred', maxrel(eng._tail_pred(a, b, bias, 1), want), 1e-5)
     finally:
         torch.backends.cudnn.allow_tf32 = old
 
