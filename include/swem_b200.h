@@ -188,6 +188,17 @@ int swem_bias_add_act(const float* a, const float* b, const float* c_shared, con
                       int32_t n_share, int64_t pixels, int32_t C, int32_t relu, float* out, void* stream);
 int swem_glu_gate(const float* y, const float* shared, const float* bias, int32_t images, int32_t n_share, int64_t pixels,
                   int32_t C, float* out, void* stream);
+/* CBAM of the value encoder's fuser (attentions.py:22-85; networks.py:35-52), NHWC x [images, pixels, C]:
+ *   swem_cbam_channel_gate : gate[img, c] = sigmoid(mlp(avg_p x) + mlp(max_p x)), mlp = Linear(C, R) -> ReLU -> Linear(R, C)
+ *                            (w1 [R, C], b1 [R], w2 [C, R], b2 [C]); stats: scratch [2, images, C]
+ *   swem_cbam_spatial_pool : pooled[img, 0, p] = max_c (x gate), pooled[img, 1, p] = mean_c (x gate)   (input of the 7x7 conv)
+ *   swem_cbam_apply        : out = x * (1 + gate[img, c] * sigmoid(spatial_logit[img, p]))  = x + CBAM(x)                */
+int swem_cbam_channel_gate(const float* x, const float* w1, const float* b1, const float* w2, const float* b2, int32_t images,
+                           int64_t pixels, int32_t C, int32_t R, float* stats, float* gate, void* stream);
+int swem_cbam_spatial_pool(const float* x, const float* gate, int32_t images, int64_t pixels, int32_t C, float* pooled,
+                           void* stream);
+int swem_cbam_apply(const float* x, const float* gate, const float* spatial_logit, int32_t images, int64_t pixels, int32_t C,
+                    float* out, void* stream);
 /* Tail of the decoder: out[bn, y, x] = bp + sum_{dy, dx, c} wp[dy][dx][c] * relu(a + b + bias[c])[bn, y+dy-1, x+dx-1, c]
  * -- the residual add of the last ResBlock (networks.py:25-32), the ReLU and the 3x3 `pred` conv to one logit plane
  * (networks.py:205-213) in one pass.  a, b: [BN, H, W, C] NHWC; wp: [3, 3, C]; out: [BN, H, W]; C % 32 == 0.          */

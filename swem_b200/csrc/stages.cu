@@ -182,6 +182,116 @@ __global__ void __launch_bounds__(256, 2) resblock_tail_pred_kernel(const float4
   }
 }
 
+// ------------------------------------------------------------------------------------------------------
+// CBAM of the value encoder's fuser (methods/basic_modules/attentions.py:22-85, used at networks.py:35-52):
+//   channel gate  g_c = sigmoid(mlp(avg_HW x) + mlp(max_HW x)),  mlp = Linear(C, C/16) -> ReLU -> Linear(C/16, C)
+//   spatial gate  g_p = sigmoid(conv7x7([max_c (x g_c), mean_c (x g_c)]))
+//   out = x + x g_c g_p            (the fuser adds the attention output to its input, networks.py:49)
+// The reference spends ~14 launches on [objects, 512, H/16, W/16]; here: channel statistics, the tiny MLP, the
+// per-pixel channel pooling and the final gate are one pass each (the 2 -> 1 channel 7x7 conv stays cuDNN).  NHWC.
+// ------------------------------------------------------------------------------------------------------
+// grid (C/32, images), 256 threads = 32 pixel lanes x 8 float4: mean / max over the pixels of 32 channels of one image
+__global__ void __launch_bounds__(256) cbam_channel_stats_kernel(const float4* __restrict__ x, int pixels, int C4,
+                                                                 float* __restrict__ mean, float* __restrict__ mx) {
+  __shared__ float4 ssum[32][8], smax[32][8];
+  const int c4 = blockIdx.x * 8 + (threadIdx.x & 7), pl = threadIdx.x >> 3, img = blockIdx.y;
+  const float4* xp = x + (long long)img * pixels * C4 + c4;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f), m = make_float4(-3.4e38f, -3.4e38f, -3.4e38f, -3.4e38f);
+  for (int p = pl; p < pixels; p += 32) {
+    const float4 v = __ldg(xp + (long long)p * C4);
+    s = f4add(s, v);
+    m = make_float4(fmaxf(m.x, v.x), fmaxf(m.y, v.y), fmaxf(m.z, v.z), fmaxf(m.w, v.w));
+  }
+  ssum[pl][threadIdx.x & 7] = s;
+  smax[pl][threadIdx.x & 7] = m;
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    for (int i = 1; i < 32; ++i) {
+      const float4 a = ssum[i][threadIdx.x], b = smax[i][threadIdx.x];
+      s = f4add(s, a);
+      m = make_float4(fmaxf(m.x, b.x), fmaxf(m.y, b.y), fmaxf(m.z, b.z), fmaxf(m.w, b.w));
+    }
+    const float inv = 1.f / (float)pixels;
+    const int c = (blockIdx.x * 8 + threadIdx.x) * 4;
+    float* mo = mean + (long long)img * C4 * 4 + c;
+    float* xo = mx + (long long)img * C4 * 4 + c;
+    mo[0] = s.x * inv; mo[1] = s.y * inv; mo[2] = s.z * inv; mo[3] = s.w * inv;
+    xo[0] = m.x; xo[1] = m.y; xo[2] = m.z; xo[3] = m.w;
+  }
+}
+
+// one block per image: gate[c] = sigmoid(W2 (relu(W1 avg + b1) + relu(W1 max + b1)) + 2 b2);  W1 [R][C], W2 [C][R], R <= 64
+__global__ void __launch_bounds__(256) cbam_channel_mlp_kernel(const float* __restrict__ mean, const float* __restrict__ mx,
+                                                               const float* __restrict__ w1, const float* __restrict__ b1,
+                                                               const float* __restrict__ w2, const float* __restrict__ b2, int C, int R,
+                                                               float* __restrict__ gate) {
+  __shared__ float hid[64];
+  const int img = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float* a = mean + (long long)img * C;
+  const float* m = mx + (long long)img * C;
+  for (int j = warp; j < R; j += 8) {                    // one warp per hidden unit
+    float sa = 0.f, sm = 0.f;
+    for (int c = lane; c < C; c += 32) {
+      const float w = __ldg(w1 + (long long)j * C + c);
+      sa = fmaf(w, a[c], sa);
+      sm = fmaf(w, m[c], sm);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      sa += __shfl_xor_sync(0xffffffffu, sa, o);
+      sm += __shfl_xor_sync(0xffffffffu, sm, o);
+    }
+    if (lane == 0) hid[j] = fmaxf(sa + b1[j], 0.f) + fmaxf(sm + b1[j], 0.f);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += 256) {
+    float t = 2.f * b2[c];
+    for (int j = 0; j < R; ++j) t = fmaf(__ldg(w2 + (long long)c * R + j), hid[j], t);
+    gate[(long long)img * C + c] = 1.f / (1.f + expf(-t));
+  }
+}
+
+// one warp per pixel: pooled[img][0][p] = max_c (x g_c), pooled[img][1][p] = mean_c (x g_c)   (NCHW, the 7x7 conv's input)
+__global__ void __launch_bounds__(256) cbam_spatial_stats_kernel(const float4* __restrict__ x, const float4* __restrict__ gate,
+                                                                 long long total_px, int pixels, int C4, float* __restrict__ pooled) {
+  const long long wp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (wp >= total_px) return;
+  const int img = (int)(wp / pixels), p = (int)(wp % pixels);
+  const float4* xp = x + wp * C4;
+  const float4* gp = gate + (long long)img * C4;
+  float s = 0.f, m = -3.4e38f;
+  for (int c4 = lane; c4 < C4; c4 += 32) {
+    const float4 v = __ldg(xp + c4), g = __ldg(gp + c4);
+    const float a = v.x * g.x, b = v.y * g.y, c = v.z * g.z, d = v.w * g.w;
+    s += (a + b) + (c + d);
+    m = fmaxf(fmaxf(m, fmaxf(a, b)), fmaxf(c, d));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  }
+  if (lane == 0) {
+    pooled[((long long)img * 2 + 0) * pixels + p] = m;
+    pooled[((long long)img * 2 + 1) * pixels + p] = s / (float)(C4 * 4);
+  }
+}
+
+// out = x (1 + g_c sigmoid(sp_p))
+__global__ void __launch_bounds__(256) cbam_apply_kernel(const float4* __restrict__ x, const float4* __restrict__ gate,
+                                                         const float* __restrict__ sp, long long total4, int pixels, int C4,
+                                                         float4* __restrict__ out) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total4) return;
+  const int c4 = (int)(idx % C4);
+  const long long px = idx / C4;
+  const int img = (int)(px / pixels);
+  const float gs = 1.f / (1.f + expf(-__ldg(sp + px)));
+  const float4 v = __ldg(x + idx), g = __ldg(gate + (long long)img * C4 + c4);
+  out[idx] = make_float4(v.x * fmaf(g.x, gs, 1.f), v.y * fmaf(g.y, gs, 1.f), v.z * fmaf(g.z, gs, 1.f), v.w * fmaf(g.w, gs, 1.f));
+}
+
 // Input of a ResNet stem (7x7 / stride 2 / padding 3 conv) in "space-to-depth" form, NHWC with a zero border:
 //   out[n, Y, X, 4*ci + 2*p + q] = plane_ci[2*(Y - 2) + p, 2*(X - 2) + q]        (0 outside the image / for pad channels)
 // over planes ci = 0..2: (frame - mean) / std  (networks.py:77, :115, :154), ci = 3: the object's mask, ci = 4: the mask
@@ -288,6 +398,46 @@ int swem_resblock_tail_pred(const float* a, const float* b, const float* bias, c
   resblock_tail_pred_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const float4*>(a), reinterpret_cast<const float4*>(b), reinterpret_cast<const float4*>(bias),
       reinterpret_cast<const float4*>(wp), bp, H, W, C / 4, out);
+  SWEM_LAUNCH_CHECK();
+  return SWEM_OK;
+}
+
+int swem_cbam_channel_gate(const float* x, const float* w1, const float* b1, const float* w2, const float* b2, int32_t images,
+                           int64_t pixels, int32_t C, int32_t R, float* stats, float* gate, void* stream) {
+  reset_launch_count();
+  SWEM_CHECK_ARG(x && w1 && b1 && w2 && b2 && stats && gate, "NULL pointer");
+  SWEM_CHECK_ARG(images > 0 && images <= 65535 && pixels > 0 && C > 0 && C % 32 == 0 && R > 0 && R <= 64,
+                 "bad sizes images=%d pixels=%lld C=%d R=%d (C %% 32 == 0, R <= 64)", images, (long long)pixels, C, R);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float* mean = stats;
+  float* mx = stats + (size_t)images * C;
+  cbam_channel_stats_kernel<<<dim3(C / 32, images), 256, 0, st>>>(reinterpret_cast<const float4*>(x), (int)pixels, C / 4, mean, mx);
+  SWEM_LAUNCH_CHECK();
+  cbam_channel_mlp_kernel<<<images, 256, 0, st>>>(mean, mx, w1, b1, w2, b2, C, R, gate);
+  SWEM_LAUNCH_CHECK();
+  return SWEM_OK;
+}
+
+int swem_cbam_spatial_pool(const float* x, const float* gate, int32_t images, int64_t pixels, int32_t C, float* pooled, void* stream) {
+  reset_launch_count();
+  SWEM_CHECK_ARG(x && gate && pooled, "NULL pointer");
+  SWEM_CHECK_ARG(images > 0 && pixels > 0 && C > 0 && C % 4 == 0, "bad sizes images=%d pixels=%lld C=%d", images, (long long)pixels, C);
+  const long long total_px = (long long)images * pixels;
+  cbam_spatial_stats_kernel<<<(unsigned)((total_px * 32 + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const float4*>(x), reinterpret_cast<const float4*>(gate), total_px, (int)pixels, C / 4, pooled);
+  SWEM_LAUNCH_CHECK();
+  return SWEM_OK;
+}
+
+int swem_cbam_apply(const float* x, const float* gate, const float* spatial_logit, int32_t images, int64_t pixels, int32_t C,
+                    float* out, void* stream) {
+  reset_launch_count();
+  SWEM_CHECK_ARG(x && gate && spatial_logit && out, "NULL pointer");
+  SWEM_CHECK_ARG(images > 0 && pixels > 0 && C > 0 && C % 4 == 0, "bad sizes images=%d pixels=%lld C=%d", images, (long long)pixels, C);
+  const long long total4 = (long long)images * pixels * (C / 4);
+  cbam_apply_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const float4*>(x), reinterpret_cast<const float4*>(gate), spatial_logit, total4, (int)pixels, C / 4,
+      reinterpret_cast<float4*>(out));
   SWEM_LAUNCH_CHECK();
   return SWEM_OK;
 }

@@ -299,7 +299,7 @@ class FrameEngine:
         else:
             skip = torch.cat([x.view(bsz, n, *x.shape[1:]), s16.unsqueeze(1).expand(-1, n, -1, -1, -1)], 2).flatten(end_dim=1)
             x = self._add_act(r, skip, None, self.f_b1_tail_bias, n, relu=False)
-        x = x + ve.fuser.attention(x)
+        x = self._cbam_residual(x, ve.fuser.attention)
         r = self._conv(self._conv(F.relu(x), self.f_b2c1, relu=True), self.f_b2c2)
         x = self._add_act(r, x, None, self.f_b2_tail_bias, n, relu=False)
         return x.view(bsz, n, *x.shape[1:])
@@ -366,6 +366,34 @@ class FrameEngine:
         if bias is not None:
             out = out + bias.view(1, -1, 1, 1)
         return F.relu(out) if relu else out
+
+    def _cbam_residual(self, x, cbam):
+        """x + CBAM(x) (networks.py:49; attentions.py:22-85): channel statistics + MLP, channel pooling per pixel and the
+        final gate as one kernel each; only the 2 -> 1 channel 7x7 conv of the spatial gate stays cuDNN."""
+        mlp = cbam.ChannelGate.mlp
+        lin1, lin2 = mlp[1], mlp[3]
+        c, r = x.shape[1], lin1.out_features
+        if not (self._glue_ok(x) and c % 32 == 0 and r <= 64 and x.shape[0] <= 65535):
+            return x + cbam(x)
+        x = self._cl(x)
+        bn, _, h, w = x.shape
+        dev = x.device
+        stats = torch.empty(2, bn, c, device=dev, dtype=torch.float32)
+        gate = torch.empty(bn, c, device=dev, dtype=torch.float32)
+        pooled = torch.empty(bn, 2, h, w, device=dev, dtype=torch.float32)
+        out = torch.empty_like(x)
+        lib = _lib.load()
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            _lib.check(lib.swem_cbam_channel_gate(x.data_ptr(), lin1.weight.data_ptr(), lin1.bias.data_ptr(), lin2.weight.data_ptr(),
+                                                  lin2.bias.data_ptr(), bn, h * w, c, r, stats.data_ptr(), gate.data_ptr(), stream),
+                       'swem_cbam_channel_gate')
+            _lib.check(lib.swem_cbam_spatial_pool(x.data_ptr(), gate.data_ptr(), bn, h * w, c, pooled.data_ptr(), stream),
+                       'swem_cbam_spatial_pool')
+            logit = cbam.SpatialGate.spatial(pooled).contiguous()                  # (bn, 1, h, w)
+            _lib.check(lib.swem_cbam_apply(x.data_ptr(), gate.data_ptr(), logit.data_ptr(), bn, h * w, c, out.data_ptr(), stream),
+                       'swem_cbam_apply')
+        return out
 
     def _glu(self, y, shared, bias, n):
         """(y_f + s_f + b_f) * sigmoid(y_a + s_a + b_a) on stacked [layer_f | layer_a] pre-activations (modules.py:13-26)."""

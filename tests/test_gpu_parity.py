@@ -625,6 +625,10 @@ def test_decoder_glue_kernels_match_torch():
     old = torch.backends.cudnn.allow_tf32
     torch.backends.cudnn.allow_tf32 = False
     try:
+        cbam = eng.model.value_encoder.fuser.attention
+        for (bn, hh, ww) in ((5, 30, 54), (3, 7, 9)):
+            t = cl(torch.randn(bn, 512, hh, ww, generator=g))
+            check('cbam', maxrel(eng._cbam_residual(t, cbam), t + cbam(t)), 1e-5)
         pred = eng.model.decoder.pred
         for (bn, hh, ww) in ((5, 120, 216), (2, 19, 45)):
             a, b = cl(torch.randn(bn, 256, hh, ww, generator=g)), cl(torch.randn(bn, 256, hh, ww, generator=g))
