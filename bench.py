@@ -194,7 +194,7 @@ def run_reference(args, rank, world):
 def run_b200(args, rank, world, local_rank):
     import torch.distributed as dist
     from swem_b200 import _lib
-    from swem_b200.evaluator import FrameUploader, GraphedSequenceRunner, SequenceRunner
+    from swem_b200.evaluator import FrameUploader, GraphedSequenceRunner, PipelinedSequenceRunner, SequenceRunner
 
     assert torch.cuda.is_available(), 'bench.py needs a CUDA device (no CPU fallback)'
     torch.cuda.set_device(local_rank)
@@ -214,7 +214,8 @@ def run_b200(args, rank, world, local_rank):
         Wm = max(Wm, 3)            # frames 1-2 run eagerly, frame 3 captures the step graph: all inside the warm-up
     model = build_model(dev)
     core = model.swem_core
-    frames, init = make_sequence(1 + Wm + K, n_obj, seed=1 + rank)
+    use_pipe = use_graph and os.environ.get('SWEM_PIPELINE', '1') == '1'     # key encoder one frame ahead on a side stream
+    frames, init = make_sequence(2 + Wm + K, n_obj, seed=1 + rank)            # (+1: the look-ahead frame of the last step)
     frames_pinned = frames[0].pin_memory()                       # (T,3,H,W) host
     init_dev = init.to(dev)
     hw = (H // 16) * (W // 16)
@@ -241,15 +242,20 @@ def run_b200(args, rank, world, local_rank):
                              fused_conv=os.environ.get('SWEM_FUSED_CONV', '1') == '1')
 
     def run_phase(host_io, graphed):
-        """start on frame 0, Wm warm-up steps, then K timed steps; returns (ms, clocks, masks checksum)."""
-        runner = (GraphedSequenceRunner if graphed else SequenceRunner)(stages, (H, W))
+        """start on frame 0, Wm warm-up steps, then K timed steps; returns (ms, clocks, masks checksum).  Step k segments and
+        memorizes frame 1 + Wm + k; with the pipelined runner it also encodes the key of frame 2 + Wm + k meanwhile."""
+        pipe = graphed and use_pipe
+        runner = (PipelinedSequenceRunner if pipe else GraphedSequenceRunner if graphed else SequenceRunner)(stages, (H, W))
         core.static_banks = False
         mask_host = torch.empty(K, H, W, dtype=torch.uint8).pin_memory()
         resident = None if host_io else frames_pinned.to(dev)
         torch.manual_seed(1234 + rank)
         runner.start(frames_pinned[0:1].to(dev), init_dev)
+        la = 1 if pipe else 0                                    # frame a step consumes = the one it segments + la
+        if pipe:
+            runner.prime(frames_pinned[1:2].to(dev))
         for i in range(1, 1 + Wm):
-            runner.step(frames_pinned[i:i + 1].to(dev))
+            runner.step(frames_pinned[i + la:i + la + 1].to(dev))
         for b in ev.values():
             b.clear()
         launches[0] = lib.swem_total_launch_count()
@@ -257,11 +263,12 @@ def run_b200(args, rank, world, local_rank):
         barrier()
         with ClockSampler(local_rank) as clk:
             t0.record()
+            first = 1 + Wm + la
             if host_io:                                          # every frame is uploaded inside the timed region (side stream:
-                up = FrameUploader((1, 3, H, W), dev)            # frame k+1 travels while frame k is processed)
-                up.submit(0, frames_pinned[1 + Wm:2 + Wm])
+                up = FrameUploader((1, 3, H, W), dev)            # the next frame travels while the current one is processed)
+                up.submit(0, frames_pinned[first:first + 1])
             for k in range(K):
-                i = 1 + Wm + k
+                i = first + k
                 if host_io:
                     if k + 1 < K:
                         up.submit(k + 1, frames_pinned[i + 1:i + 2])
@@ -309,7 +316,9 @@ def run_b200(args, rank, world, local_rank):
         'ms_per_step': ms_res / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'f32 I/O; EM/readout contractions ' + ('f16 hi+lo split, f32 accumulate' if 'fused' in family['em'] else 'f32'),
         'data': 'synthetic',
-        'config': workload_config(n_obj, {'kernel_family': family, 'frame_step': 'CUDA graph replay' if use_graph else 'eager',
+        'config': workload_config(n_obj, {'kernel_family': family,
+                                          'frame_step': ('CUDA graph replay, key encoder of the next frame on a second stream' if use_pipe
+                                                         else 'CUDA graph replay' if use_graph else 'eager'),
                                           'eager_ms_per_step': ms_eager / K, 'l2': 'every step reads a new 5 MB frame and '
                                           '>230 MB of fp32 weights + activations (> 126 MB L2); no explicit flush',
                                           'torch_convs': 'cudnn, allow_tf32 default, channels_last=' + os.environ.get('SWEM_CHANNELS_LAST', '1'),

@@ -199,3 +199,95 @@ class FrameUploader:
         i = k % len(self.bufs)
         self.free[i] = torch.cuda.Event()
         self.free[i].record(torch.cuda.current_stream(self.device))
+
+
+class PipelinedSequenceRunner(SequenceRunner):
+    """Frame loop with the key encoder running one frame ahead on a second stream.
+
+    In the reference loop (swem_evaluator.py:73-93) ``encode_key(frame i+1)`` depends on nothing computed for frame i,
+    but it is ~60 small single-image kernels (a ResNet-50 at batch 1) that leave most of the GPU idle when they run on
+    their own.  Here step i runs two branches that join at its end:
+
+        main stream : match -> segment -> encode_value -> memorize          of frame i   (features from the previous step)
+        side stream : encode_key                                             of frame i+1
+
+    so the small kernels fill the gaps of the large ones.  Results are those of :class:`SequenceRunner` (same calls, same
+    order per frame); only the schedule differs.  With ``use_graph`` the whole two-branch step is captured once into a
+    CUDA graph (fork / join inside the capture) and replayed, like :class:`GraphedSequenceRunner`.
+
+        runner.start(frame0, init_mask); runner.prime(frame1)
+        for i in range(1, T):
+            mask_i = runner.step(frames[i + 1] if i + 1 < T else None)     # None: no look-ahead (last frame)
+    """
+
+    def __init__(self, model, out_size, use_graph: bool = True, eager_steps: int = 2):
+        super().__init__(model, out_size)
+        self.use_graph, self.eager_steps = use_graph, max(2, eager_steps)
+        self._side = None
+        self._reset()
+
+    def _reset(self):
+        self._seen, self._graph, self._cur, self._cur_frame, self._next_in, self._pred = 0, None, None, None, None, None
+
+    @torch.no_grad()
+    def start(self, frame0, init_mask):
+        self._reset()
+        self.model.swem_core.static_banks = False
+        if self._side is None:
+            self._side = torch.cuda.Stream(frame0.device)
+        super().start(frame0, init_mask)
+
+    @torch.no_grad()
+    def prime(self, frame):
+        """Encode the first frame to be segmented (what the side branch does for every later frame)."""
+        self._cur = [t.clone(memory_format=torch.preserve_format) for t in self.model('encode_key', frame)]
+        self._cur_frame = frame.clone()
+
+    def _heavy(self, memorize: bool):
+        qk16, qv16, s16, s8, s4 = self._cur
+        h, w = self._cur_frame.shape[-2:]
+        context, n = self.model('match', qk16, qv16)
+        _, pred_mask = self.model('segment', n, context, s8, s4, None, self.out_size)
+        pred, hard = hard_masks_from_scores(pred_mask)
+        if memorize:
+            soft = _to_frame_size(pred_mask, h, w)
+            mv16 = self.model('encode_value', self._cur_frame, soft, s16)
+            self.model('memorize', qk16, mv16, hard, soft)
+        return pred[:, 0]
+
+    def _two_branch_step(self, next_frame, memorize: bool):
+        main = torch.cuda.current_stream(next_frame.device)
+        self._side.wait_stream(main)
+        with torch.cuda.stream(self._side):
+            nxt = list(self.model('encode_key', next_frame))
+        pred = self._heavy(memorize)
+        main.wait_stream(self._side)
+        capturing = torch.cuda.is_current_stream_capturing()
+        for cur, new in zip(self._cur, nxt):                 # rotate: the look-ahead features become the current ones
+            if not capturing:
+                new.record_stream(main)                      # allocated on the side stream, read here on the main one
+            cur.copy_(new)
+        self._cur_frame.copy_(next_frame)
+        return pred
+
+    @torch.no_grad()
+    def step(self, next_frame, memorize: bool = True):
+        """Segment (and memorize) the current frame; ``next_frame`` is encoded meanwhile.  Returns (B,H,W) int64."""
+        if self._cur is None:
+            raise RuntimeError('PipelinedSequenceRunner.step() before prime()')
+        if next_frame is None:
+            return self._heavy(memorize)
+        if not self.use_graph or self._seen < self.eager_steps:
+            self._seen += 1
+            return self._two_branch_step(next_frame, memorize)
+        if self._graph is None:
+            self.model.swem_core.static_banks = True
+            self._next_in = next_frame.clone()
+            torch.cuda.synchronize(next_frame.device)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                self._pred = self._two_branch_step(self._next_in, memorize)
+            self._graph = graph
+        self._next_in.copy_(next_frame, non_blocking=True)
+        self._graph.replay()
+        return self._pred
