@@ -273,7 +273,19 @@ class FrameEngine:
         heads = self._conv(f16, self.k_heads)
         return heads[:, :self.keydim], heads[:, self.keydim:], f16, f8, f4
 
-    def encode_value(self, frame, masks, s16):
+    def shared_parts(self, qv16, s16, s8, s4) -> dict:
+        """The object-independent convolutions of a frame -- the f16 halves of the fuser's first block, the qv third of the
+        GLU fusion conv and the decoder's skip convs: functions of the key encoder's outputs only.  ``match`` /
+        ``encode_value`` / ``segment`` compute them on demand; a runner that encodes keys ahead of time (see
+        ``PipelinedSequenceRunner``) computes them there too and passes them in as ``shared=``."""
+        self._ready()
+        parts = {'g': self._conv(qv16, self.g_shared), 'f_c1': self._conv(s16, self.f_c1_sh),
+                 'skip': [self._conv(f, self._nobias(d['skip'])) for d, f in zip(self.d_up, (s8, s4))]}
+        if self.f_has_down:
+            parts['f_dn'] = self._conv(s16, self.f_dn_sh)
+        return parts
+
+    def encode_value(self, frame, masks, s16, shared=None):
         """frame (B,3,H,W), masks (B,N+1,H,W), s16 = f16 of the same frame -> (B,N,Cv,H16,W16) (swem.py:51-62)."""
         self._ready()
         m, ve = self.model, self.model.value_encoder
@@ -292,10 +304,12 @@ class FrameEngine:
             y = self._conv(x, self.v_stem, relu=True)
         x = self._trunk(y, self.v_stages)                          # (B*N, 256, H16, W16), post-ReLU
         # fuser.block1 on cat[x, f16]: both halves are post-ReLU, so block1's leading ReLU is the identity
-        h1 = self._add_act(self._conv(x, self.f_c1_obj), None, self._conv(s16, self.f_c1_sh), self.f_c1_bias, n, relu=True)
+        f_c1 = shared['f_c1'] if shared is not None else self._conv(s16, self.f_c1_sh)
+        h1 = self._add_act(self._conv(x, self.f_c1_obj), None, f_c1, self.f_c1_bias, n, relu=True)
         r = self._conv(h1, self.f_b1c2)
         if self.f_has_down:
-            x = self._add_act(r, self._conv(x, self.f_dn_obj), self._conv(s16, self.f_dn_sh), self.f_b1_tail_bias, n, relu=False)
+            f_dn = shared['f_dn'] if shared is not None else self._conv(s16, self.f_dn_sh)
+            x = self._add_act(r, self._conv(x, self.f_dn_obj), f_dn, self.f_b1_tail_bias, n, relu=False)
         else:
             skip = torch.cat([x.view(bsz, n, *x.shape[1:]), s16.unsqueeze(1).expand(-1, n, -1, -1, -1)], 2).flatten(end_dim=1)
             x = self._add_act(r, skip, None, self.f_b1_tail_bias, n, relu=False)
@@ -304,7 +318,7 @@ class FrameEngine:
         x = self._add_act(r, x, None, self.f_b2_tail_bias, n, relu=False)
         return x.view(bsz, n, *x.shape[1:])
 
-    def match(self, qk16, qv16):
+    def match(self, qk16, qv16, shared=None):
         """Readout + GLU fusion: (context (B*N, Cv, H, W), N), as SWEMCore.matching (modules.py:278-293)."""
         self._ready()
         core = self.model.swem_core
@@ -313,8 +327,8 @@ class FrameEngine:
         feats = torch.empty((bsz * n, cv + 2 * core.topl, h, w), device=qk16.device, dtype=torch.float32,
                             memory_format=torch.channels_last if self.channels_last else torch.contiguous_format)
         core.readout_into(qk16, feats, 0, cv)                      # [mem_out | S], written NHWC for the channels-last conv
-        shared = self._conv(qv16, self.g_shared)                   # (B, 1024, H, W): [layer_f | layer_a] of the qv third
-        return self._glu(self._conv(feats, self.g_obj), shared, self.g_bias, n), n
+        g = shared['g'] if shared is not None else self._conv(qv16, self.g_shared)   # (B, 1024, H, W): [layer_f | layer_a] of the qv third
+        return self._glu(self._conv(feats, self.g_obj), g, self.g_bias, n), n
 
     @staticmethod
     def _nobias(p: ConvP) -> ConvP:
@@ -410,14 +424,14 @@ class FrameEngine:
         t = (y.view(-1, n, *y.shape[1:]) + shared.unsqueeze(1)).flatten(end_dim=1) + bias.view(1, -1, 1, 1)
         return t[:, :c] * torch.sigmoid(t[:, c:])
 
-    def decode(self, n, context, s8, s4, valid_obj, out_size):
+    def decode(self, n, context, s8, s4, valid_obj, out_size, shared=None):
         """-> (logits, prob) (B, N+1, H, W), as SWEM.decode (swem.py:92-108).  Convolutions whose output only feeds an
         up-sampling or a residual add run without their bias pass; the constants go to the glue kernels (`d_bias`)."""
         self._ready()
         lo_a = self._conv(self._conv(F.relu(context), self.d_c1, relu=True), self._nobias(self.d_c2))
         lo_b = context
-        for d, skip_f, bias in zip(self.d_up, (s8, s4), self.d_bias):
-            skip = self._conv(skip_f, self._nobias(d['skip']))        # once per frame, not per object
+        for lvl, (d, skip_f, bias) in enumerate(zip(self.d_up, (s8, s4), self.d_bias)):
+            skip = shared['skip'][lvl] if shared is not None else self._conv(skip_f, self._nobias(d['skip']))   # once per frame
             x, xr = self._upsample_add(lo_a, lo_b, bias, skip, n)
             lo_a = self._conv(self._conv(xr, d['c1'], relu=True), self._nobias(d['c2']))
             lo_b = x if d['down'] is None else self._conv(x, self._nobias(d['down']))

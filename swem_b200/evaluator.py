@@ -211,8 +211,9 @@ class PipelinedSequenceRunner(SequenceRunner):
         main stream : match -> segment -> encode_value -> memorize          of frame i   (features from the previous step)
         side stream : encode_key                                             of frame i+1
 
-    so the small kernels fill the gaps of the large ones.  Results are those of :class:`SequenceRunner` (same calls, same
-    order per frame); only the schedule differs.  With ``use_graph`` the whole two-branch step is captured once into a
+    so the small kernels fill the gaps of the large ones; with a ``FrameEngine`` the side branch also runs the frame's
+    object-independent convolutions (``FrameEngine.shared_parts``).  Results are those of :class:`SequenceRunner` (same
+    calls, same order per frame); only the schedule differs.  With ``use_graph`` the whole two-branch step is captured once into a
     CUDA graph (fork / join inside the capture) and replayed, like :class:`GraphedSequenceRunner`.
 
         runner.start(frame0, init_mask); runner.prime(frame1)
@@ -228,6 +229,24 @@ class PipelinedSequenceRunner(SequenceRunner):
 
     def _reset(self):
         self._seen, self._graph, self._cur, self._cur_frame, self._next_in, self._pred = 0, None, None, None, None, None
+        self._cur_shared = None
+
+    def _encode(self, frame):
+        """Key features of a frame + (FrameEngine only) its object-independent convolutions, as a flat tensor list."""
+        feats = list(self.model('encode_key', frame))
+        if hasattr(self.model, 'shared_parts'):
+            sh = self.model.shared_parts(feats[1], feats[2], feats[3], feats[4])
+            feats += [sh['g'], sh['f_c1']] + list(sh['skip']) + ([sh['f_dn']] if 'f_dn' in sh else [])
+        return feats
+
+    def _shared_kw(self):
+        ex = self._cur[5:]                                   # [g, f_c1, skip8, skip4 (, f_dn)]
+        if not ex:
+            return {}
+        sh = {'g': ex[0], 'f_c1': ex[1], 'skip': ex[2:4]}
+        if len(ex) > 4:
+            sh['f_dn'] = ex[4]
+        return {'shared': sh}
 
     @torch.no_grad()
     def start(self, frame0, init_mask):
@@ -240,18 +259,19 @@ class PipelinedSequenceRunner(SequenceRunner):
     @torch.no_grad()
     def prime(self, frame):
         """Encode the first frame to be segmented (what the side branch does for every later frame)."""
-        self._cur = [t.clone(memory_format=torch.preserve_format) for t in self.model('encode_key', frame)]
+        self._cur = [t.clone(memory_format=torch.preserve_format) for t in self._encode(frame)]
         self._cur_frame = frame.clone()
 
     def _heavy(self, memorize: bool):
-        qk16, qv16, s16, s8, s4 = self._cur
+        qk16, qv16, s16, s8, s4 = self._cur[:5]
+        kw = self._shared_kw()
         h, w = self._cur_frame.shape[-2:]
-        context, n = self.model('match', qk16, qv16)
-        _, pred_mask = self.model('segment', n, context, s8, s4, None, self.out_size)
+        context, n = self.model('match', qk16, qv16, **kw)
+        _, pred_mask = self.model('segment', n, context, s8, s4, None, self.out_size, **kw)
         pred, hard = hard_masks_from_scores(pred_mask)
         if memorize:
             soft = _to_frame_size(pred_mask, h, w)
-            mv16 = self.model('encode_value', self._cur_frame, soft, s16)
+            mv16 = self.model('encode_value', self._cur_frame, soft, s16, **kw)
             self.model('memorize', qk16, mv16, hard, soft)
         return pred[:, 0]
 
@@ -259,7 +279,7 @@ class PipelinedSequenceRunner(SequenceRunner):
         main = torch.cuda.current_stream(next_frame.device)
         self._side.wait_stream(main)
         with torch.cuda.stream(self._side):
-            nxt = list(self.model('encode_key', next_frame))
+            nxt = self._encode(next_frame)
         pred = self._heavy(memorize)
         main.wait_stream(self._side)
         capturing = torch.cuda.is_current_stream_capturing()
