@@ -39,10 +39,8 @@ using namespace tc05;
 
 namespace em {
 constexpr int kTP = 128;    // pixels per CTA
-constexpr int kCk = 64;
 constexpr int kL = 128;     // bases per side = rows owned by one CTA
 constexpr int kCv = 512;
-constexpr uint32_t kAccBytes = (kCk + 1) * kL * 4; // M-step accumulator of one (unit, iteration, side): [64 kappa sums + zita sum][128 l]
 constexpr float kKScale = 256.f;
 constexpr float kZScale = 16384.f;
 constexpr uint32_t kStageBytes = 32768;            // one V operand image: [256 d][32 px] fp16, hi plane then lo plane
@@ -50,22 +48,35 @@ constexpr uint32_t kVPlane = 16384;
 constexpr int kChunks = 8;                         // images per tile: 2 channel halves x 4 pixel quarters
 constexpr int kStages = 3;                         // bulk-copy ring, one image per stage
 
-// ---- shared memory map (bytes) ---------------------------------------------------------------
-// XH : [c 0..79][p] : byte = (c%8)*16 + (c/8)*2048 + (p/8)*128 + (p%8)*2      (row 64 = ones, 65..79 = 0)
-// XL : [c 0..63][p]   E-step A (MN-major, r=p, k=c): SBO=128, LBO=2048; M-step B (K-major, r=c, k=p): SBO=2048, LBO=128
+// ---- shared memory map (bytes), key channels CK = 64 (BASELINE) or 128 (the reference's CLI default) ------------
+// XH : [c 0..CK+15][p] : byte = (c%8)*16 + (c/8)*2048 + (p/8)*128 + (p%8)*2      (row CK = ones, CK+1.. = 0)
+// XL : [c 0..CK-1][p]   E-step A (MN-major, r=p, k=c): SBO=128, LBO=2048; M-step B (K-major, r=c, k=p): SBO=2048, LBO=128
 // KH/KL : [l 0..127][c] K-major: byte = (l%8)*16 + (l/8)*128 + (c/8)*2048 + (c%8)*2   -> SBO=128, LBO=2048
 // Z  : [l 0..127][p] MN-major A: byte = (l%8)*2 + (p%8)*16 + (l/8)*2048 + (p/8)*128   -> SBO=2048, LBO=128
 // ZL : lo half of z (aliases KH/KL: khat is dead between the logits GEMM and the finalize)
 // VS : ring of V operand images, each [d 0..255][p 0..31] K-major: byte = (d%8)*16 + (d/8)*128 + (p/8)*4096 + (p%8)*2
-//      -> SBO=128, LBO=4096; hi plane then lo plane.  The nu drain staging (2 x 32 KB fp32) aliases the ring.
-constexpr uint32_t kOffXH = 0;
-constexpr uint32_t kOffXL = kOffXH + 10 * 2048;
-constexpr uint32_t kOffKH = kOffXL + 8 * 2048;
-constexpr uint32_t kOffKL = kOffKH + 8 * 2048;
-constexpr uint32_t kOffZ = kOffKL + 8 * 2048;
-constexpr uint32_t kOffZL = kOffKH;
-constexpr uint32_t kOffVS = kOffZ + 16 * 2048;
-constexpr uint32_t kOffMisc = kOffVS + kStages * kStageBytes;
+//      -> SBO=128, LBO=4096; hi plane then lo plane.  CK = 64: three stages of their own.  CK = 128 (X and khat twice as
+//      large): one stage of its own + two in the X region, which is dead once the last M-step GEMM has completed.
+//      The nu drain staging (2 x 32 KB fp32) uses the same two/three buffers.
+template <int CK>
+struct Lay {
+  static constexpr int kG = CK / 8;                               // 16-byte channel groups
+  static constexpr uint32_t kOffXH = 0;
+  static constexpr uint32_t kOffXL = kOffXH + (kG + 2) * 2048;
+  static constexpr uint32_t kOffKH = kOffXL + kG * 2048;
+  static constexpr uint32_t kOffKL = kOffKH + kG * 2048;
+  static constexpr uint32_t kOffZ = kOffKL + kG * 2048;
+  static constexpr uint32_t kOffZL = kOffKH;
+  static constexpr uint32_t kOffVS = kOffZ + 16 * 2048;
+  static constexpr int kOwnStages = (CK == 64) ? 3 : 1;
+  static constexpr uint32_t kOffMisc = kOffVS + kOwnStages * kStageBytes;
+  static constexpr uint32_t kAccBytes = (CK + 1) * kL * 4;        // M-step accumulator of one (unit, iteration, side): [CK sums + zita sum][128 l]
+  static_assert(2 * kG * 2048 >= 16 * 2048, "ZL must fit over KH/KL");
+  static_assert(CK == 64 || (2 * kG + 2) * 2048 >= 2 * kStageBytes, "two ring stages must fit in the X region");
+  __host__ __device__ static constexpr uint32_t stage_off(int st) {
+    return (st < kOwnStages) ? kOffVS + st * kStageBytes : kOffXH + (st - kOwnStages) * kStageBytes;
+  }
+};
 struct Misc {
   float inv_nx[kTP];
   float mask[kTP];
@@ -79,13 +90,14 @@ struct Misc {
   uint32_t tmem_base;
   int abort_flag;
 };
-constexpr uint32_t kSmemBytes = kOffMisc + sizeof(Misc) + 128;
-static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
+template <int CK>
+constexpr uint32_t smem_bytes() { return Lay<CK>::kOffMisc + sizeof(Misc) + 128; }
+static_assert(smem_bytes<64>() <= 227 * 1024 && smem_bytes<128>() <= 227 * 1024, "shared memory budget");
 
 // TMEM columns
-constexpr uint32_t kColE = 0;      // [128 px][128]  E / W logits of this side
-constexpr uint32_t kColM = 128;    // [128 l][80]    M-step sums
-constexpr uint32_t kColNu = 0;     // [128 l][512 d] nu sums (after the last M-step partial has been read out)
+constexpr uint32_t kColE = 0;      // [128 px][128]     E / W logits of this side
+constexpr uint32_t kColM = 128;    // [128 l][CK + 16]  M-step sums
+constexpr uint32_t kColNu = 0;     // [128 l][512 d]    nu sums (after the last M-step partial has been read out)
 }  // namespace em
 
 struct EmPairParams {
@@ -100,7 +112,7 @@ struct EmPairParams {
   float* zita;
   float* z_last;
   uint8_t* vblob;        // [U][T][8][32 KB] scratch: operand images of V (written in set-up, read after the last E-step)
-  float* acc_k;          // [U][n_iters][2][65][128], zeroed before launch
+  float* acc_k;          // [U][n_iters][2][CK + 1][128], zeroed before launch
   float* acc_nu;         // [U][2][512][128], zeroed before launch
   unsigned* counters;    // [U][n_iters][2], zeroed before launch
   int* status;
@@ -170,8 +182,13 @@ __device__ __forceinline__ void convert_v_chunk(const float* __restrict__ vsrc /
 }
 
 // ------------------------------------------------------------------------------------------------------
+template <int CK>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) em_pair_kernel(const EmPairParams p) {
   using namespace em;
+  using LY = Lay<CK>;
+  constexpr int kCk = CK;
+  constexpr uint32_t kOffXH = LY::kOffXH, kOffXL = LY::kOffXL, kOffKH = LY::kOffKH, kOffKL = LY::kOffKL, kOffZ = LY::kOffZ,
+                     kOffZL = LY::kOffZL, kOffMisc = LY::kOffMisc;
   extern __shared__ __align__(1024) uint8_t smem[];
   Misc& ms = *reinterpret_cast<Misc*>(smem + kOffMisc);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -221,7 +238,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) em_pair_kern
     for (int c = 0; c < kCk; ++c) ss = fmaf(kap[c], kap[c], ss);
     const float sc = kKScale / (sqrtf(ss) + kEpsNorm);
 #pragma unroll
-    for (int g = 0; g < 8; ++g) {
+    for (int g = 0; g < kCk / 8; ++g) {
       __align__(16) __half hi[8];
       __align__(16) __half lo[8];
 #pragma unroll
@@ -251,9 +268,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) em_pair_kern
     ms.inv_nx[q] = 1.f / (sqrtf(ss) + kEpsNorm);
     ms.mask[q] = px < HW ? __ldg(p.masks + (size_t)gs * HW + px) : 0.f;
   }
-  // X tile -> fp16 hi/lo chunks.  thread -> (channel c = tid/4, 4 pixel groups of 8)
-  {
-    const int c = tid >> 2;
+  // X tile -> fp16 hi/lo chunks.  thread -> (channel c = tid/4 (+64), 4 pixel groups of 8)
+#pragma unroll
+  for (int cc = 0; cc < kCk / 64; ++cc) {
+    const int c = cc * 64 + (tid >> 2);
     const float* xrow = p.x + ((size_t)b * kCk + c) * HW;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -270,15 +288,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) em_pair_kern
       *reinterpret_cast<uint4*>(smem + kOffXH + off) = *reinterpret_cast<uint4*>(hi);
       *reinterpret_cast<uint4*>(smem + kOffXL + off) = *reinterpret_cast<uint4*>(lo);
     }
-    for (int i = tid; i < 16 * 16; i += 256) {          // augmented rows 64..79 of XH: row 64 = 1 (-> zita), rest 0
-      const int r = 64 + (i >> 4), pg = i & 15;
-      const __half one = __float2half_rn(r == 64 ? 1.f : 0.f);
+  }
+  auto stage_aug_rows = [&]() {       // augmented rows CK..CK+15 of XH: row CK = 1 (-> zita), rest 0
+    for (int i = tid; i < 16 * 16; i += 256) {
+      const int r = kCk + (i >> 4), pg = i & 15;
+      const __half one = __float2half_rn(r == kCk ? 1.f : 0.f);
       __align__(16) __half vals[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) vals[e] = one;
       *reinterpret_cast<uint4*>(smem + kOffXH + (r % 8) * 16 + (r / 8) * 2048 + pg * 128) = *reinterpret_cast<uint4*>(vals);
     }
-  }
+  };
+  stage_aug_rows();
   if (row_thread) stage_khat(kap0);
   tc_fence_before_sync();
   cluster_arrive();                   // both CTAs of the pair are running before any remote shared-memory store,
@@ -287,11 +308,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) em_pair_kern
   auto load_image = [&](int k) {       // ring stage k % kStages <- image k of the tile
     const int st = k % kStages;
     mbar_expect_tx(&ms.bar_full[st], kStageBytes);
-    bulk_g2s(smem + kOffVS + st * kStageBytes, vimg + (size_t)k * kStageBytes, kStageBytes, &ms.bar_full[st]);
+    bulk_g2s(smem + LY::stage_off(st), vimg + (size_t)k * kStageBytes, kStageBytes, &ms.bar_full[st]);
   };
-  auto prefetch_images = [&]() {       // the first kStages images start flying; they are consumed after the last E-step
+  // the images that have a stage of their own start flying early (they are consumed after the last E-step); stages that
+  // live in the X region (CK = 128) are filled by the consumer once the last M-step GEMM has released it
+  auto prefetch_images = [&]() {
     asm volatile("fence.proxy.async;" ::: "memory");
-    for (int k = 0; k < kStages; ++k) load_image(k);
+    for (int k = 0; k < LY::kOwnStages; ++k) load_image(k);
   };
   if (I == 1 && tid == 0) prefetch_images();
   const uint32_t tmem = ms.tmem_base;
@@ -300,8 +323,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) em_pair_kern
   EM_STAMP();                        // setup done
 
   const uint32_t idesc_e = make_idesc(128, 128, kFmtF16, kFmtF16, kMajorMN, kMajorK);
-  const uint32_t idesc_m80 = make_idesc(128, 80, kFmtF16, kFmtF16, kMajorMN, kMajorK);
-  const uint32_t idesc_m64 = make_idesc(128, 64, kFmtF16, kFmtF16, kMajorMN, kMajorK);
+  const uint32_t idesc_mhi = make_idesc(128, kCk + 16, kFmtF16, kFmtF16, kMajorMN, kMajorK);
+  const uint32_t idesc_mlo = make_idesc(128, kCk, kFmtF16, kFmtF16, kMajorMN, kMajorK);
   const uint32_t idesc_nu = make_idesc(128, 256, kFmtF16, kFmtF16, kMajorMN, kMajorK);
   const uint32_t peer_mbox = map_to_peer(smem_u32(&ms.mbox[0][0][0]), (uint32_t)(sd ^ 1));
 
@@ -319,7 +342,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) em_pair_kern
           const uint32_t xa = sbase + (term == 2 ? kOffXL : kOffXH);
           const uint32_t kb = sbase + (term == 1 ? kOffKL : kOffKH);
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {
+          for (int kk = 0; kk < kCk / 16; ++kk) {
             const uint64_t ad = make_sdesc(xa + kk * 2 * 2048, /*lbo*/ 2048, /*sbo*/ 128);
             const uint64_t bd = make_sdesc(kb + kk * 2 * 2048, /*lbo*/ 2048, /*sbo*/ 128);
             mma_f16_ss(tmem + kColE, ad, bd, idesc_e, (term | kk) ? 1u : 0u);
@@ -422,9 +445,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) em_pair_kern
           const uint64_t al = make_sdesc(sbase + kOffZL + kk * 2 * 128, /*lbo*/ 128, /*sbo*/ 2048);
           const uint64_t bh = make_sdesc(sbase + kOffXH + kk * 2 * 128, /*lbo*/ 128, /*sbo*/ 2048);
           const uint64_t bl = make_sdesc(sbase + kOffXL + kk * 2 * 128, /*lbo*/ 128, /*sbo*/ 2048);
-          mma_f16_ss(tmem + kColM, ad, bh, idesc_m80, kk ? 1u : 0u);   // z_hi x_hi (+ zita column)
-          mma_f16_ss(tmem + kColM, ad, bl, idesc_m64, 1u);             // z_hi x_lo
-          mma_f16_ss(tmem + kColM, al, bh, idesc_m80, 1u);             // z_lo x_hi
+          mma_f16_ss(tmem + kColM, ad, bh, idesc_mhi, kk ? 1u : 0u);   // z_hi x_hi (+ zita column)
+          mma_f16_ss(tmem + kColM, ad, bl, idesc_mlo, 1u);             // z_hi x_lo
+          mma_f16_ss(tmem + kColM, al, bh, idesc_mhi, 1u);             // z_lo x_hi
         }
         mma_commit(&ms.bar_mma);
       }
@@ -435,22 +458,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) em_pair_kern
     tc_fence_after_sync();
     EM_STAMP();                      // M GEMM done
 
-    float part[kCk + 1];              // partial of this tile for row l = tid (row threads only)
+    // partial of this tile for row l = tid -> fp32 reductions straight from TMEM into the L2-resident accumulator
+    // [c][l] (coalesced over l; fire-and-forget, the fence comes later so that they fly during what follows)
+    float* acc = p.acc_k + ((size_t)(u * I + it) * 2 + sd) * ((kCk + 1) * kL);
     if (row_thread) {
-      uint32_t r[32];
       const uint32_t base = tmem_addr(tmem, (warp & 3) * 32, kColM);
-      tmem_ld32(base, r);
-      tmem_ld_wait();
 #pragma unroll
-      for (int j = 0; j < 32; ++j) part[j] = __uint_as_float(r[j]);
-      tmem_ld32(base + 32, r);
-      tmem_ld_wait();
+      for (int q = 0; q < kCk / 32; ++q) {
+        uint32_t r[32];
+        tmem_ld32(base + q * 32, r);
+        tmem_ld_wait();
 #pragma unroll
-      for (int j = 0; j < 32; ++j) part[32 + j] = __uint_as_float(r[j]);
+        for (int j = 0; j < 32; ++j) atomicAdd(acc + (q * 32 + j) * kL + tid, __uint_as_float(r[j]));
+      }
       uint32_t r16[16];
-      tmem_ld16(base + 64, r16);
+      tmem_ld16(base + kCk, r16);
       tmem_ld_wait();
-      part[64] = __uint_as_float(r16[0]);
+      atomicAdd(acc + kCk * kL + tid, __uint_as_float(r16[0]));
     }
     tc_fence_before_sync();
 
@@ -461,13 +485,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) em_pair_kern
       tc_fence_after_sync();
       if (warp == 0) {
         if (lane == 0) {
+          for (int k = LY::kOwnStages; k < kStages; ++k) load_image(k);   // (CK = 128) stages in the X region, free now
 #pragma unroll 1
           for (int seq = 0; seq < kChunks; ++seq) {
             const int st = seq % kStages;
             if (!mbar_wait(&ms.bar_full[st], (seq / kStages) & 1)) ms.abort_flag = 1;
             tc_fence_after_sync();
             const int h = seq >> 2, q = seq & 3;
-            const uint32_t vb = sbase + kOffVS + st * kStageBytes;
+            const uint32_t vb = sbase + LY::stage_off(st);
 #pragma unroll
             for (int kk = 0; kk < 2; ++kk) {
               const uint64_t ad = make_sdesc(sbase + kOffZ + (q * 2 + kk) * 2 * 128, /*lbo*/ 128, /*sbo*/ 2048);
@@ -504,7 +529,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) em_pair_kern
         const int l = (warp & 3) * 32 + lane, cg = warp >> 2;
 #pragma unroll 1
         for (int q = 0; q < 8; ++q) {
-          float* ns = reinterpret_cast<float*>(smem + kOffVS + (q & 1) * kStageBytes);
+          float* ns = reinterpret_cast<float*>(smem + LY::stage_off(kStages - 1 - (q & 1)));
           if (q >= 2) {
             if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
             __syncthreads();
@@ -535,23 +560,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) em_pair_kern
       EM_STAMP();                    // nu drained
     }
 
-    // ---- (4) cross-tile reduction of the M-step partial: fire-and-forget fp32 reductions straight from registers into
-    // the L2-resident accumulator [c][l] (coalesced over l), fence, arrive; after the last tile arrived every CTA
-    // reads the total back the same way.
-    float* acc = p.acc_k + ((size_t)(u * I + it) * 2 + sd) * ((kCk + 1) * kL);
+    // ---- (4) cross-tile reduction of the M-step partial: fence the reductions issued above, arrive; after the last tile
+    // arrived every CTA reads the total back the same way it was accumulated.
     unsigned* counter = p.counters + ((size_t)u * I + it) * 2 + sd;
-    float kpr[kCk];                   // prior row: loads fly during the cross-tile wait
     if (row_thread) {                 // warps 0-3; they synchronise among themselves on named barrier 1
-#pragma unroll
-      for (int c = 0; c <= kCk; ++c) atomicAdd(acc + c * kL + tid, part[c]);
       __threadfence();                // (the prior-row loads come after it: a fence waits for every earlier access)
       asm volatile("bar.sync 1, 128;" ::: "memory");
       if (tid == 0) {
         EM_STAMP();                   // partial reduce-added
         atomicAdd(counter, 1u);
       }
+      float kap[kCk];                 // prior row first: the loads fly during the cross-tile wait (CK = 64; 128 would not fit)
+      if constexpr (kCk == 64) {
 #pragma unroll
-      for (int c = 0; c < kCk; ++c) kpr[c] = __ldg(kprior + (size_t)c * kL);
+        for (int c = 0; c < kCk; ++c) kap[c] = __ldg(kprior + (size_t)c * kL);
+      }
       if (tid == 0) {
         const bool arrived = wait_counter(counter, (unsigned)p.T);
         EM_STAMP();                   // all tiles arrived
@@ -562,13 +585,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) em_pair_kern
       // ---- (5) finalize row l = tid from the prior (reference :125-126) -------------------------------------
       if (!ms.abort_flag) {
         constexpr float kInvZ = 1.f / kZScale;
-        float kap[kCk];
-#pragma unroll
-        for (int c = 0; c < kCk; ++c) kap[c] = __ldcg(acc + c * kL + tid);
         const float zita_cur = zita_p + __ldcg(acc + kCk * kL + tid) * kInvZ;
         const float rz = 1.f / zita_cur;
 #pragma unroll
-        for (int c = 0; c < kCk; ++c) kap[c] = (zita_p * kpr[c] + kap[c] * kInvZ) * rz;
+        for (int c = 0; c < kCk; ++c) {
+          const float prior = (kCk == 64) ? kap[c] : __ldg(kprior + (size_t)c * kL);
+          kap[c] = (zita_p * prior + __ldcg(acc + c * kL + tid) * kInvZ) * rz;
+        }
         if (last) {
           ms.hsum[0][tid] = rz;       // (dead E-step scratch) 1 / zita and the prior zita of row l, for the nu slice below
           ms.hsum[1][tid] = zita_p;
@@ -635,14 +658,15 @@ static long long* g_prof = nullptr;
 void set_profile_buffer(void* dev) { g_prof = static_cast<long long*>(dev); }
 long long* get_profile_buffer() { return g_prof; }
 
+template <int CK>
 static int max_pairs_resident() {
   static int n = -1;
   if (n < 0) {
-    cudaFuncSetAttribute(em_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)em::kSmemBytes);
+    cudaFuncSetAttribute(em_pair_kernel<CK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)em::smem_bytes<CK>());
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2, 1, 1);
     cfg.blockDim = dim3(256, 1, 1);
-    cfg.dynamicSmemBytes = em::kSmemBytes;
+    cfg.dynamicSmemBytes = em::smem_bytes<CK>();
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2;
@@ -651,7 +675,7 @@ static int max_pairs_resident() {
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     int clusters = 0;
-    if (cudaOccupancyMaxActiveClusters(&clusters, em_pair_kernel, &cfg) != cudaSuccess || clusters <= 0) {
+    if (cudaOccupancyMaxActiveClusters(&clusters, em_pair_kernel<CK>, &cfg) != cudaSuccess || clusters <= 0) {
       cudaGetLastError();
       int dev = 0, sms = 0;
       cudaGetDevice(&dev);
@@ -664,7 +688,7 @@ static int max_pairs_resident() {
 }
 
 bool fused_em_supported(const SwemDims& d) {
-  if (d.Ck != em::kCk || d.L != em::kL || d.Cv != em::kCv || d.n_iters < 1 || d.n_iters > 16) return false;
+  if ((d.Ck != 64 && d.Ck != 128) || d.L != em::kL || d.Cv != em::kCv || d.n_iters < 1 || d.n_iters > 16) return false;
   const int T = (d.HW + em::kTP - 1) / em::kTP;
   return T >= 1 && T <= 64;            // all pairs of one unit must be co-resident (74 pairs on a B200)
 }
@@ -673,19 +697,20 @@ size_t fused_em_workspace(const SwemDims& d) {
   const size_t U = (size_t)d.B * d.N;
   const size_t T = (d.HW + em::kTP - 1) / em::kTP;
   size_t bytes = 0;
-  bytes += align_up(U * d.n_iters * 2 * em::kAccBytes, 256);
+  bytes += align_up(U * d.n_iters * 2 * (size_t)(d.Ck + 1) * em::kL * 4, 256);
   bytes += align_up(U * 2 * em::kCv * em::kL * 4, 256);
   bytes += align_up(U * d.n_iters * 2 * 4 + 4, 256);
   bytes += align_up(U * T * em::kChunks * em::kStageBytes, 256);
   return bytes + 256;
 }
 
-int fused_em_forward(const SwemEmArgs& a, cudaStream_t st) {
+template <int CK>
+static int fused_em_forward_t(const SwemEmArgs& a, cudaStream_t st) {
   const SwemDims& d = a.dims;
   const int U = d.B * d.N;
   const int T = (d.HW + em::kTP - 1) / em::kTP;
   Arena ws(a.workspace);
-  float* acc_k = ws.take<float>((size_t)U * d.n_iters * 2 * (em::kAccBytes / 4));
+  float* acc_k = ws.take<float>((size_t)U * d.n_iters * 2 * (CK + 1) * em::kL);
   float* acc_nu = ws.take<float>((size_t)U * 2 * em::kCv * em::kL);
   unsigned* counters = ws.take<unsigned>((size_t)U * d.n_iters * 2 + 1);
   int* status = reinterpret_cast<int*>(counters + (size_t)U * d.n_iters * 2);
@@ -695,7 +720,7 @@ int fused_em_forward(const SwemEmArgs& a, cudaStream_t st) {
 
   static bool attr_set = false;
   if (!attr_set) {
-    SWEM_CUDA(cudaFuncSetAttribute(em_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)em::kSmemBytes));
+    SWEM_CUDA(cudaFuncSetAttribute(em_pair_kernel<CK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)em::smem_bytes<CK>()));
     attr_set = true;
   }
   EmPairParams p{};
@@ -709,16 +734,20 @@ int fused_em_forward(const SwemEmArgs& a, cudaStream_t st) {
   p.prof = get_profile_buffer();
   // all CTAs of a launch spin on each other: every launch must be co-resident (1 CTA per SM, 2-CTA clusters);
   // units that do not fit are spread evenly over the fewest launches
-  const int upl_max = max_pairs_resident() / T > 0 ? max_pairs_resident() / T : 1;
+  const int upl_max = max_pairs_resident<CK>() / T > 0 ? max_pairs_resident<CK>() / T : 1;
   const int n_launch = (U + upl_max - 1) / upl_max;
   const int upl = (U + n_launch - 1) / n_launch;
   for (int u0 = 0; u0 < U; u0 += upl) {
     const int nu = (U - u0 < upl) ? (U - u0) : upl;
     p.u0 = u0;
-    em_pair_kernel<<<nu * T * 2, 256, em::kSmemBytes, st>>>(p);
+    em_pair_kernel<CK><<<nu * T * 2, 256, em::smem_bytes<CK>(), st>>>(p);
     SWEM_LAUNCH_CHECK();
   }
   return SWEM_OK;
+}
+
+int fused_em_forward(const SwemEmArgs& a, cudaStream_t st) {
+  return a.dims.Ck == 128 ? fused_em_forward_t<128>(a, st) : fused_em_forward_t<64>(a, st);
 }
 
 }  // namespace swem

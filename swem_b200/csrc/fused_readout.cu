@@ -32,7 +32,6 @@ using namespace tc05;
 
 namespace ro {
 constexpr int kTP = 128;
-constexpr int kCk = 64;
 constexpr int kL = 128;
 constexpr int kCv = 512;
 constexpr int kDH = 256;                 // value channels per CTA
@@ -41,13 +40,20 @@ constexpr float kEScale = 1024.f;        // E (<= 1) staged as E*2^10
 constexpr int kStages = 8;
 constexpr uint32_t kStageBytes = 16384;  // one k-step of nu: [256 d][16 j] fp16 hi (8 KB) + lo (8 KB)
 
-// shared memory map
-constexpr uint32_t kOffQH = 0;                         // [c 64][p 128] chunks, 16 KB (MN-major A: SBO 128, LBO 2048)
-constexpr uint32_t kOffQL = kOffQH + 8 * 2048;
-constexpr uint32_t kOffKB = kOffQL + 8 * 2048;         // 2 sides x (hi 32 KB + lo 32 KB) khat blobs; later the nu ring
-constexpr uint32_t kKBSide = 65536;
-constexpr uint32_t kOffRing = kOffKB;                  // 8 x 16 KB, aliases the khat blobs once the scores are done
-constexpr uint32_t kOffMisc = kOffKB + 2 * kKBSide;
+// shared memory map, key channels CK = 64 or 128
+//   QH/QL : [c CK][p 128] chunks (MN-major A: SBO 128, LBO 2048), CK/8 * 2048 bytes each
+//   KB    : khat blobs (hi + lo planes, banks * CK/64 * 32 KB per side).  CK = 64: both sides resident; CK = 128: one side
+//           at a time (the second side is loaded once the MMAs of the first have retired); later the nu ring (8 x 16 KB)
+template <int CK>
+struct Lay {
+  static constexpr uint32_t kOffQH = 0;
+  static constexpr uint32_t kOffQL = kOffQH + (CK / 8) * 2048;
+  static constexpr uint32_t kOffKB = kOffQL + (CK / 8) * 2048;
+  static constexpr uint32_t kKBSide = 65536 * (CK / 64);       // room for 2 banks
+  static constexpr int kSidesResident = (CK == 64) ? 2 : 1;
+  static constexpr uint32_t kOffRing = kOffKB;                 // 8 x 16 KB, aliases the khat blobs once the scores are done
+  static constexpr uint32_t kOffMisc = kOffKB + 131072;
+};
 struct Misc {
   float inv_nq[kTP];
   float ex_max[2][kTP];
@@ -59,8 +65,9 @@ struct Misc {
   uint32_t tmem_base;
   int abort_flag;
 };
-constexpr uint32_t kSmemBytes = kOffMisc + sizeof(Misc) + 128;
-static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
+template <int CK>
+constexpr uint32_t smem_bytes() { return Lay<CK>::kOffMisc + sizeof(Misc) + 128; }
+static_assert(smem_bytes<64>() <= 227 * 1024 && smem_bytes<128>() <= 227 * 1024, "shared memory budget");
 }  // namespace ro
 
 struct ReadoutFusedParams {
@@ -82,6 +89,7 @@ struct ReadoutFusedParams {
 // ---- prep: banks -> operand blobs ------------------------------------------------------------------
 // khat blob of (u, s): K-major rows j = bank*128 + l, byte = (j%8)*16 + (j/8)*128 + (c/8)*LBO + (c%8)*2,
 // LBO = n_banks*2048; hi plane then lo plane.
+template <int kCk>
 __global__ void readout_prep_kappa_kernel(const float* __restrict__ k0, const float* __restrict__ k1, int U, int n_banks,
                                           uint8_t* __restrict__ kblob) {
   using namespace ro;
@@ -97,12 +105,12 @@ __global__ void readout_prep_kappa_kernel(const float* __restrict__ k0, const fl
     ss = fmaf(v[c], v[c], ss);
   }
   const float sc = kKScale / (sqrtf(ss) + kEpsNorm);
-  const uint32_t plane = n_banks * 16384;                     // bytes of one (hi or lo) plane
+  const uint32_t plane = n_banks * 16384 * (kCk / 64);        // bytes of one (hi or lo) plane
   const uint32_t lbo = n_banks * 2048;
   uint8_t* base = kblob + ((size_t)u * 2 + s) * 2 * plane;
   const int j = bank * kL + l;
 #pragma unroll
-  for (int g = 0; g < 8; ++g) {
+  for (int g = 0; g < kCk / 8; ++g) {
     __align__(16) __half hi[8];
     __align__(16) __half lo[8];
 #pragma unroll
@@ -145,9 +153,13 @@ __global__ void readout_prep_nu_kernel(const float* __restrict__ n0, const float
 }
 
 // ---- main kernel --------------------------------------------------------------------------------------
-template <int NB>   // number of banks read (1 or 2): fixes every loop count, so the MMA issue loops unroll
+template <int NB, int CK>   // banks read (1 or 2) and key channels (64 or 128): fix every loop count, so the MMA issue loops unroll
 __global__ void __launch_bounds__(256, 1) readout_fused_kernel(const ReadoutFusedParams p) {
   using namespace ro;
+  using LY = Lay<CK>;
+  constexpr int kCk = CK;
+  constexpr uint32_t kOffQH = LY::kOffQH, kOffQL = LY::kOffQL, kOffKB = LY::kOffKB, kKBSide = LY::kKBSide, kOffRing = LY::kOffRing,
+                     kOffMisc = LY::kOffMisc;
   extern __shared__ __align__(1024) uint8_t smem[];
   Misc& ms = *reinterpret_cast<Misc*>(smem + kOffMisc);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -162,7 +174,7 @@ __global__ void __launch_bounds__(256, 1) readout_fused_kernel(const ReadoutFuse
   constexpr int ks_side = Lt / 16;        // PV k-steps per side
   constexpr int ks2 = 2 * ks_side;
   const uint32_t sbase = smem_u32(smem);
-  constexpr uint32_t kplane = nb * 16384; // bytes of one khat plane (hi or lo) of one side
+  constexpr uint32_t kplane = nb * 16384 * (CK / 64); // bytes of one khat plane (hi or lo) of one side
   int n_stamp = 0;
   RO_STAMP();
 
@@ -177,8 +189,8 @@ __global__ void __launch_bounds__(256, 1) readout_fused_kernel(const ReadoutFuse
     }
     ms.abort_flag = 0;
     fence_mbar_init();
-    // khat blobs of both sides (hi + lo planes are contiguous): two bulk copies
-    for (int s = 0; s < 2; ++s) {
+    // khat blobs (hi + lo planes are contiguous): one bulk copy per resident side
+    for (int s = 0; s < LY::kSidesResident; ++s) {
       mbar_expect_tx(&ms.bar_k[s], 2 * kplane);
       bulk_g2s(smem + kOffKB + s * kKBSide, p.kblob + ((size_t)u * 2 + s) * 2 * kplane, 2 * kplane, &ms.bar_k[s]);
     }
@@ -197,8 +209,9 @@ __global__ void __launch_bounds__(256, 1) readout_fused_kernel(const ReadoutFuse
     }
     ms.inv_nq[tid] = 1.f / (sqrtf(ss) + kEpsNorm);
   }
-  {
-    const int c = tid >> 2;
+#pragma unroll
+  for (int cc = 0; cc < kCk / 64; ++cc) {
+    const int c = cc * 64 + (tid >> 2);
     const float* qrow = p.qk + ((size_t)b * kCk + c) * HW;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -231,14 +244,24 @@ __global__ void __launch_bounds__(256, 1) readout_fused_kernel(const ReadoutFuse
     const uint32_t idesc = make_idesc(128, Lt, kFmtF16, kFmtF16, kMajorMN, kMajorK);
     constexpr uint32_t lbo_k = nb * 2048;
     for (int s = 0; s < 2; ++s) {
-      ok = mbar_wait(&ms.bar_k[s], 0) && ok;
-      const uint32_t kb = sbase + kOffKB + s * kKBSide;
+      const int slot = (LY::kSidesResident == 2) ? s : 0;
+      if (LY::kSidesResident == 1 && s == 1) {
+        // one side resident: wait until the MMAs that read side 0 have retired, then reuse its buffer (bar_k[1] tracks both)
+        mma_commit(&ms.bar_k[1]);
+        ok = mbar_wait(&ms.bar_k[1], 0) && ok;
+        mbar_expect_tx(&ms.bar_k[1], 2 * kplane);
+        bulk_g2s(smem + kOffKB, p.kblob + ((size_t)u * 2 + 1) * 2 * kplane, 2 * kplane, &ms.bar_k[1]);
+        ok = mbar_wait(&ms.bar_k[1], 1) && ok;
+      } else {
+        ok = mbar_wait(&ms.bar_k[s], 0) && ok;
+      }
+      const uint32_t kb = sbase + kOffKB + slot * kKBSide;
 #pragma unroll
       for (int term = 0; term < 3; ++term) {
         const uint32_t qa = sbase + (term == 2 ? kOffQL : kOffQH);
         const uint32_t kbt = kb + (term == 1 ? kplane : 0);
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
+        for (int kk = 0; kk < kCk / 16; ++kk) {
           const uint64_t ad = make_sdesc(qa + kk * 2 * 2048, /*lbo*/ 2048, /*sbo*/ 128);
           const uint64_t bd = make_sdesc(kbt + kk * 2 * lbo_k, /*lbo*/ lbo_k, /*sbo*/ 128);
           mma_f16_ss(tmem + s * 256, ad, bd, idesc, (term | kk) ? 1u : 0u);
@@ -414,7 +437,7 @@ __global__ void __launch_bounds__(256, 1) readout_fused_kernel(const ReadoutFuse
 // host side
 // ------------------------------------------------------------------------------------------------------
 bool fused_readout_supported(const SwemDims& d) {
-  return d.Ck == ro::kCk && d.L == ro::kL && d.Cv == ro::kCv && (d.n_banks == 1 || d.n_banks == 2) && d.topl >= 1 &&
+  return (d.Ck == 64 || d.Ck == 128) && d.L == ro::kL && d.Cv == ro::kCv && (d.n_banks == 1 || d.n_banks == 2) && d.topl >= 1 &&
          d.topl <= 64 && d.HW >= 1;
 }
 
@@ -422,7 +445,7 @@ size_t fused_readout_workspace(const SwemDims& d) {
   const size_t U = (size_t)d.B * d.N;
   const size_t Lt = (size_t)d.L * d.n_banks;
   size_t bytes = 0;
-  bytes += align_up(U * 2 * 2 * d.n_banks * 16384, 256);                 // khat blobs
+  bytes += align_up(U * 2 * 2 * d.n_banks * 16384 * (size_t)(d.Ck / 64), 256);   // khat blobs
   bytes += align_up(U * 2 * (2 * Lt / 16) * ro::kStageBytes, 256);       // nu blobs
   bytes += align_up(U * d.HW * 2 * Lt * 4, 256);                         // E scratch
   return bytes + 256;
@@ -433,13 +456,14 @@ int fused_readout_forward(const SwemReadArgs& a, cudaStream_t st) {
   const int U = d.B * d.N, nb = d.n_banks, Lt = d.L * nb;
   const int T = (d.HW + ro::kTP - 1) / ro::kTP;
   Arena ws(a.workspace);
-  uint8_t* kblob = ws.take<uint8_t>((size_t)U * 2 * 2 * nb * 16384);
+  uint8_t* kblob = ws.take<uint8_t>((size_t)U * 2 * 2 * nb * 16384 * (d.Ck / 64));
   uint8_t* vblob = ws.take<uint8_t>((size_t)U * 2 * (2 * Lt / 16) * ro::kStageBytes);
   float* escr = ws.take<float>((size_t)U * d.HW * 2 * Lt);
 
   {
     const int n = U * 2 * nb * ro::kL;
-    readout_prep_kappa_kernel<<<(n + 127) / 128, 128, 0, st>>>(a.kappa[0], a.kappa[nb - 1], U, nb, kblob);
+    if (d.Ck == 64) readout_prep_kappa_kernel<64><<<(n + 127) / 128, 128, 0, st>>>(a.kappa[0], a.kappa[nb - 1], U, nb, kblob);
+    else readout_prep_kappa_kernel<128><<<(n + 127) / 128, 128, 0, st>>>(a.kappa[0], a.kappa[nb - 1], U, nb, kblob);
     SWEM_LAUNCH_CHECK();
     const long long m = (long long)U * 2 * nb * ro::kCv * (ro::kL / 8);
     readout_prep_nu_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(a.nu[0], a.nu[nb - 1], U, nb, vblob);
@@ -447,8 +471,10 @@ int fused_readout_forward(const SwemReadArgs& a, cudaStream_t st) {
   }
   static bool attr_set = false;
   if (!attr_set) {
-    SWEM_CUDA(cudaFuncSetAttribute(readout_fused_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ro::kSmemBytes));
-    SWEM_CUDA(cudaFuncSetAttribute(readout_fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ro::kSmemBytes));
+    SWEM_CUDA(cudaFuncSetAttribute(readout_fused_kernel<1, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ro::smem_bytes<64>()));
+    SWEM_CUDA(cudaFuncSetAttribute(readout_fused_kernel<2, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ro::smem_bytes<64>()));
+    SWEM_CUDA(cudaFuncSetAttribute(readout_fused_kernel<1, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ro::smem_bytes<128>()));
+    SWEM_CUDA(cudaFuncSetAttribute(readout_fused_kernel<2, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ro::smem_bytes<128>()));
     attr_set = true;
   }
   ReadoutFusedParams p{};
@@ -457,8 +483,13 @@ int fused_readout_forward(const SwemReadArgs& a, cudaStream_t st) {
   p.pixel_major = a.out_pixel_major;
   p.c1s = kLog2e / (d.tau * ro::kKScale);
   p.prof = get_profile_buffer();
-  if (nb == 1) readout_fused_kernel<1><<<U * T * 2, 256, ro::kSmemBytes, st>>>(p);
-  else readout_fused_kernel<2><<<U * T * 2, 256, ro::kSmemBytes, st>>>(p);
+  if (d.Ck == 64) {
+    if (nb == 1) readout_fused_kernel<1, 64><<<U * T * 2, 256, ro::smem_bytes<64>(), st>>>(p);
+    else readout_fused_kernel<2, 64><<<U * T * 2, 256, ro::smem_bytes<64>(), st>>>(p);
+  } else {
+    if (nb == 1) readout_fused_kernel<1, 128><<<U * T * 2, 256, ro::smem_bytes<128>(), st>>>(p);
+    else readout_fused_kernel<2, 128><<<U * T * 2, 256, ro::smem_bytes<128>(), st>>>(p);
+  }
   SWEM_LAUNCH_CHECK();
   return launch_perm_inv(escr, U, d.HW, Lt, d.topl, a.out, a.out_channels, a.s_channel, a.out_pixel_major, st);
 }

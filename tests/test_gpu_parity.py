@@ -172,6 +172,8 @@ SHAPES = [
     (1, 6, 64, 512, 256, 30, 54, 4),
     (1, 2, 128, 512, 256, 17, 29, 1),
     (1, 1, 64, 512, 512, 12, 20, 4),
+    (1, 3, 128, 512, 128, 30, 54, 4),                     # the reference's CLI defaults (--key_dim 128 --num_bases 128)
+    (2, 2, 128, 512, 128, 24, 23, 1),
 ]
 
 
