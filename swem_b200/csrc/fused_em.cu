@@ -1,8 +1,8 @@
 // Fused sequential-weighted-EM kernel for sm_100a (tcgen05 + TMEM + bulk-async copies), one launch per memorize call:
 // one CTA per (unit u = (b,n), pixel tile of 128 px, side s), the two sides of a tile forming a 2-CTA cluster.
 //
-// Covers the BASELINE shape family: Ck = 64, L = 128 bases per side, Cv = 512, any HW up to 128 x (#SMs / 2) pixels,
-// any B*N.  Reference semantics: methods/SWEM/modules.py:129-168 (swem), :112-120 (E), :122-127 (M), :93-110 (W),
+// Covers Ck = 64 (BASELINE) or 128 (the reference's CLI default), L = 128 or 64 bases per side (64: half of the rows /
+// columns are zero padding), Cv = 512, any HW up to 128 x 64 pixels, any B*N.  Reference semantics: methods/SWEM/modules.py:129-168 (swem), :112-120 (E), :122-127 (M), :93-110 (W),
 // :164-165 (nu).  Arithmetic: operands fp16 with x, the unit bases, the responsibilities and v split into hi + lo
 // halves (3 MMAs per product: hi*hi + hi*lo + lo*hi ~ fp32-accurate), fp32 accumulation in TMEM, fp32 softmax /
 // normalisation.  The W-step logits l2norm(x).khat equal the E-step logits x.khat / (||x_p|| + eps) -- same khat --
@@ -118,6 +118,7 @@ struct EmPairParams {
   int* status;
   long long* prof;
   int N, HW, T, n_iters, u0;
+  int L;                 // bases per side in global memory (64 or 128); a CTA always works on 128 rows, the rest are zero
   float c1s;             // log2(e) / (tau * kKScale)
 };
 
@@ -229,9 +230,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) em_pair_kern
   asm volatile("fence.proxy.async;" ::: "memory");     // generic-proxy global stores -> visible to the bulk-copy (async proxy) reads
   // rows: thread tid < 128 <-> basis l = tid of side sd (finalize steps)
   const bool row_thread = tid < kL;
+  const int L = p.L;                                    // L = 64: rows / columns 64..127 of every operand are zero padding
+  const bool valid_row = tid < L;
   const int gs = u * 2 + sd;                            // (b, n, s) index
-  const float zita_p = row_thread ? __ldg(p.zita_prior + (size_t)gs * kL + tid) : 0.f;
-  const float* kprior = p.kappa_prior + ((size_t)gs * kCk) * kL + (tid & (kL - 1));   // + c*kL
+  const float zita_p = valid_row ? __ldg(p.zita_prior + (size_t)gs * L + tid) : 0.f;
+  const float* kprior = p.kappa_prior + ((size_t)gs * kCk) * L + (valid_row ? tid : 0);   // + c*L
   auto stage_khat = [&](const float (&kap)[kCk]) {      // khat = l2norm(kappa) * 256 -> fp16 hi/lo K-major rows (reference :115)
     float ss = 0.f;
 #pragma unroll
@@ -251,7 +254,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) em_pair_kern
   float kap0[kCk];
   if (row_thread) {
 #pragma unroll
-    for (int c = 0; c < kCk; ++c) kap0[c] = __ldg(kprior + (size_t)c * kL);
+    for (int c = 0; c < kCk; ++c) kap0[c] = valid_row ? __ldg(kprior + (size_t)c * L) : 0.f;
   }
   // pixel norms + this side's mask (threads 128..255 <-> pixel, so they overlap with the prior loads of the row threads)
   if (!row_thread) {
@@ -370,6 +373,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) em_pair_kern
 #pragma unroll
         for (int j = 0; j < 32; ++j) a[q * 32 + j] = __uint_as_float(r[j]);
       }
+      const bool active = hb * 64 < L;                  // L = 64: the second half of the columns is padding
+      if (!active) {
+#pragma unroll
+        for (int i = 0; i < 64; ++i) a[i] = -3.0e38f;   // exp2((a - max) * c) underflows to exactly 0 everywhere below
+      }
       float mx = a[0];
 #pragma unroll
       for (int i = 1; i < 64; ++i) mx = fmaxf(mx, a[i]);
@@ -423,8 +431,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) em_pair_kern
         *reinterpret_cast<uint4*>(smem + kOffZ + off) = *reinterpret_cast<uint4*>(hi);
         *reinterpret_cast<uint4*>(smem + kOffZL + off) = *reinterpret_cast<uint4*>(lo);
       }
-      if (p.z_last != nullptr && it == I - 1 && p0 + px < HW) {
-        float4* dst = reinterpret_cast<float4*>(p.z_last + ((size_t)gs * HW + p0 + px) * kL + hb * 64);
+      if (p.z_last != nullptr && it == I - 1 && p0 + px < HW && active) {
+        float4* dst = reinterpret_cast<float4*>(p.z_last + ((size_t)gs * HW + p0 + px) * L + hb * 64);
 #pragma unroll
         for (int g = 0; g < 16; ++g)
           dst[g] = make_float4(a[g * 4] * scale, a[g * 4 + 1] * scale, a[g * 4 + 2] * scale, a[g * 4 + 3] * scale);
@@ -573,7 +581,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) em_pair_kern
       float kap[kCk];                 // prior row first: the loads fly during the cross-tile wait (CK = 64; 128 would not fit)
       if constexpr (kCk == 64) {
 #pragma unroll
-        for (int c = 0; c < kCk; ++c) kap[c] = __ldg(kprior + (size_t)c * kL);
+        for (int c = 0; c < kCk; ++c) kap[c] = valid_row ? __ldg(kprior + (size_t)c * L) : 0.f;
       }
       if (tid == 0) {
         const bool arrived = wait_counter(counter, (unsigned)p.T);
@@ -586,20 +594,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) em_pair_kern
       if (!ms.abort_flag) {
         constexpr float kInvZ = 1.f / kZScale;
         const float zita_cur = zita_p + __ldcg(acc + kCk * kL + tid) * kInvZ;
-        const float rz = 1.f / zita_cur;
+        const float rz = valid_row ? 1.f / zita_cur : 0.f;
 #pragma unroll
         for (int c = 0; c < kCk; ++c) {
-          const float prior = (kCk == 64) ? kap[c] : __ldg(kprior + (size_t)c * kL);
+          const float prior = (kCk == 64) ? kap[c] : (valid_row ? __ldg(kprior + (size_t)c * L) : 0.f);
           kap[c] = (zita_p * prior + __ldcg(acc + c * kL + tid) * kInvZ) * rz;
         }
         if (last) {
           ms.hsum[0][tid] = rz;       // (dead E-step scratch) 1 / zita and the prior zita of row l, for the nu slice below
           ms.hsum[1][tid] = zita_p;
-          if (tile == 0) {
-            p.zita[(size_t)gs * kL + tid] = zita_cur;
-            float* kout = p.kappa + ((size_t)gs * kCk) * kL + tid;
+          if (tile == 0 && valid_row) {
+            p.zita[(size_t)gs * L + tid] = zita_cur;
+            float* kout = p.kappa + ((size_t)gs * kCk) * L + tid;
 #pragma unroll
-            for (int c = 0; c < kCk; ++c) kout[(size_t)c * kL] = kap[c];
+            for (int c = 0; c < kCk; ++c) kout[(size_t)c * L] = kap[c];
           }
         } else {
           stage_khat(kap);
@@ -625,12 +633,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) em_pair_kern
       const int dper = (kCv + p.T - 1) / p.T;
       const int d0 = tile * dper, d1 = min(kCv, d0 + dper);
       constexpr float kInvZ = 1.f / kZScale;
-      const float4* acc4 = reinterpret_cast<const float4*>(p.acc_nu + (size_t)gs * kCv * kL);
-      const float4* pri4 = reinterpret_cast<const float4*>(p.nu_prior + (size_t)gs * kCv * kL);
-      float4* out4 = reinterpret_cast<float4*>(p.nu + (size_t)gs * kCv * kL);
-      for (int i = d0 * (kL / 4) + tid; i < d1 * (kL / 4); i += 256) {
-        const int l = (i % (kL / 4)) * 4;
-        const float4 a = __ldcg(acc4 + i);
+      const float4* acc4 = reinterpret_cast<const float4*>(p.acc_nu + (size_t)gs * kCv * kL);     // [d][128]
+      const float4* pri4 = reinterpret_cast<const float4*>(p.nu_prior + (size_t)gs * kCv * L);    // [d][L]
+      float4* out4 = reinterpret_cast<float4*>(p.nu + (size_t)gs * kCv * L);
+      const int l4n = L / 4;
+      for (int i = d0 * l4n + tid; i < d1 * l4n; i += 256) {
+        const int d = i / l4n, l4 = i % l4n, l = l4 * 4;
+        const float4 a = __ldcg(acc4 + d * (kL / 4) + l4);
         const float4 pr = __ldg(pri4 + i);
         float4 o;
         o.x = (ms.hsum[1][l + 0] * pr.x + a.x * kInvZ) * ms.hsum[0][l + 0];
@@ -688,7 +697,7 @@ static int max_pairs_resident() {
 }
 
 bool fused_em_supported(const SwemDims& d) {
-  if ((d.Ck != 64 && d.Ck != 128) || d.L != em::kL || d.Cv != em::kCv || d.n_iters < 1 || d.n_iters > 16) return false;
+  if ((d.Ck != 64 && d.Ck != 128) || (d.L != 64 && d.L != em::kL) || d.Cv != em::kCv || d.n_iters < 1 || d.n_iters > 16) return false;
   const int T = (d.HW + em::kTP - 1) / em::kTP;
   return T >= 1 && T <= 64;            // all pairs of one unit must be co-resident (74 pairs on a B200)
 }
@@ -729,7 +738,7 @@ static int fused_em_forward_t(const SwemEmArgs& a, cudaStream_t st) {
   p.kappa = a.kappa; p.nu = a.nu; p.zita = a.zita; p.z_last = a.z_last;
   p.vblob = vblob;
   p.acc_k = acc_k; p.acc_nu = acc_nu; p.counters = counters; p.status = status;
-  p.N = d.N; p.HW = d.HW; p.T = T; p.n_iters = d.n_iters;
+  p.N = d.N; p.HW = d.HW; p.T = T; p.n_iters = d.n_iters; p.L = d.L;
   p.c1s = kLog2e / (d.tau * em::kKScale);
   p.prof = get_profile_buffer();
   // all CTAs of a launch spin on each other: every launch must be co-resident (1 CTA per SM, 2-CTA clusters);

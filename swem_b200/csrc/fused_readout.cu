@@ -32,7 +32,6 @@ using namespace tc05;
 
 namespace ro {
 constexpr int kTP = 128;
-constexpr int kL = 128;
 constexpr int kCv = 512;
 constexpr int kDH = 256;                 // value channels per CTA
 constexpr float kKScale = 256.f;         // khat staged as khat*256 (lo half stays normal fp16)
@@ -88,9 +87,9 @@ struct ReadoutFusedParams {
 
 // ---- prep: banks -> operand blobs ------------------------------------------------------------------
 // khat blob of (u, s): K-major rows j = bank*128 + l, byte = (j%8)*16 + (j/8)*128 + (c/8)*LBO + (c%8)*2,
-// LBO = n_banks*2048; hi plane then lo plane.
+// LBO = n_banks*L*16; hi plane then lo plane.
 template <int kCk>
-__global__ void readout_prep_kappa_kernel(const float* __restrict__ k0, const float* __restrict__ k1, int U, int n_banks,
+__global__ void readout_prep_kappa_kernel(const float* __restrict__ k0, const float* __restrict__ k1, int U, int n_banks, int kL,
                                           uint8_t* __restrict__ kblob) {
   using namespace ro;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;       // (u, s, bank, l)
@@ -105,8 +104,8 @@ __global__ void readout_prep_kappa_kernel(const float* __restrict__ k0, const fl
     ss = fmaf(v[c], v[c], ss);
   }
   const float sc = kKScale / (sqrtf(ss) + kEpsNorm);
-  const uint32_t plane = n_banks * 16384 * (kCk / 64);        // bytes of one (hi or lo) plane
-  const uint32_t lbo = n_banks * 2048;
+  const uint32_t plane = n_banks * kL * kCk * 2;               // bytes of one (hi or lo) plane
+  const uint32_t lbo = n_banks * kL * 16;
   uint8_t* base = kblob + ((size_t)u * 2 + s) * 2 * plane;
   const int j = bank * kL + l;
 #pragma unroll
@@ -123,7 +122,7 @@ __global__ void readout_prep_kappa_kernel(const float* __restrict__ k0, const fl
 
 // nu blob of (u, half h, k-step kk): rows d (256), 16 columns j = 16*kk..; byte = (d%8)*16 + (d/8)*128 +
 // (jj/8)*4096 + (jj%8)*2; hi plane (8 KB) then lo plane.  Column order j = s*Lt + bank*128 + l (:272, :295-306).
-__global__ void readout_prep_nu_kernel(const float* __restrict__ n0, const float* __restrict__ n1, int U, int n_banks,
+__global__ void readout_prep_nu_kernel(const float* __restrict__ n0, const float* __restrict__ n1, int U, int n_banks, int kL,
                                        uint8_t* __restrict__ vblob) {
   using namespace ro;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // (u, s, bank, d, l-group of 8)
@@ -153,7 +152,7 @@ __global__ void readout_prep_nu_kernel(const float* __restrict__ n0, const float
 }
 
 // ---- main kernel --------------------------------------------------------------------------------------
-template <int NB, int CK>   // banks read (1 or 2) and key channels (64 or 128): fix every loop count, so the MMA issue loops unroll
+template <int LT, int CK>   // columns per side (banks x L: 64, 128 or 256) and key channels (64 or 128) fix every loop count, so the MMA issue loops unroll
 __global__ void __launch_bounds__(256, 1) readout_fused_kernel(const ReadoutFusedParams p) {
   using namespace ro;
   using LY = Lay<CK>;
@@ -169,12 +168,11 @@ __global__ void __launch_bounds__(256, 1) readout_fused_kernel(const ReadoutFuse
   const int b = u / p.N;
   const int p0 = tile * kTP;
   const int HW = p.HW;
-  constexpr int nb = NB;
-  constexpr int Lt = nb * kL;             // columns per side
+  constexpr int Lt = LT;                  // columns per side = banks x bases per bank
   constexpr int ks_side = Lt / 16;        // PV k-steps per side
   constexpr int ks2 = 2 * ks_side;
   const uint32_t sbase = smem_u32(smem);
-  constexpr uint32_t kplane = nb * 16384 * (CK / 64); // bytes of one khat plane (hi or lo) of one side
+  constexpr uint32_t kplane = Lt * CK * 2;   // bytes of one khat plane (hi or lo) of one side: [Lt rows][CK] fp16
   int n_stamp = 0;
   RO_STAMP();
 
@@ -242,7 +240,7 @@ __global__ void __launch_bounds__(256, 1) readout_fused_kernel(const ReadoutFuse
   if (warp == 0) {
     if (lane == 0) {
     const uint32_t idesc = make_idesc(128, Lt, kFmtF16, kFmtF16, kMajorMN, kMajorK);
-    constexpr uint32_t lbo_k = nb * 2048;
+    constexpr uint32_t lbo_k = Lt * 16;
     for (int s = 0; s < 2; ++s) {
       const int slot = (LY::kSidesResident == 2) ? s : 0;
       if (LY::kSidesResident == 1 && s == 1) {
@@ -437,7 +435,7 @@ __global__ void __launch_bounds__(256, 1) readout_fused_kernel(const ReadoutFuse
 // host side
 // ------------------------------------------------------------------------------------------------------
 bool fused_readout_supported(const SwemDims& d) {
-  return (d.Ck == 64 || d.Ck == 128) && d.L == ro::kL && d.Cv == ro::kCv && (d.n_banks == 1 || d.n_banks == 2) && d.topl >= 1 &&
+  return (d.Ck == 64 || d.Ck == 128) && (d.L == 64 || d.L == 128) && d.Cv == ro::kCv && (d.n_banks == 1 || d.n_banks == 2) && d.topl >= 1 &&
          d.topl <= 64 && d.HW >= 1;
 }
 
@@ -445,7 +443,7 @@ size_t fused_readout_workspace(const SwemDims& d) {
   const size_t U = (size_t)d.B * d.N;
   const size_t Lt = (size_t)d.L * d.n_banks;
   size_t bytes = 0;
-  bytes += align_up(U * 2 * 2 * d.n_banks * 16384 * (size_t)(d.Ck / 64), 256);   // khat blobs
+  bytes += align_up(U * 2 * 2 * Lt * d.Ck * 2, 256);                     // khat blobs
   bytes += align_up(U * 2 * (2 * Lt / 16) * ro::kStageBytes, 256);       // nu blobs
   bytes += align_up(U * d.HW * 2 * Lt * 4, 256);                         // E scratch
   return bytes + 256;
@@ -456,40 +454,45 @@ int fused_readout_forward(const SwemReadArgs& a, cudaStream_t st) {
   const int U = d.B * d.N, nb = d.n_banks, Lt = d.L * nb;
   const int T = (d.HW + ro::kTP - 1) / ro::kTP;
   Arena ws(a.workspace);
-  uint8_t* kblob = ws.take<uint8_t>((size_t)U * 2 * 2 * nb * 16384 * (d.Ck / 64));
+  uint8_t* kblob = ws.take<uint8_t>((size_t)U * 2 * 2 * Lt * d.Ck * 2);
   uint8_t* vblob = ws.take<uint8_t>((size_t)U * 2 * (2 * Lt / 16) * ro::kStageBytes);
   float* escr = ws.take<float>((size_t)U * d.HW * 2 * Lt);
 
   {
-    const int n = U * 2 * nb * ro::kL;
-    if (d.Ck == 64) readout_prep_kappa_kernel<64><<<(n + 127) / 128, 128, 0, st>>>(a.kappa[0], a.kappa[nb - 1], U, nb, kblob);
-    else readout_prep_kappa_kernel<128><<<(n + 127) / 128, 128, 0, st>>>(a.kappa[0], a.kappa[nb - 1], U, nb, kblob);
+    const int n = U * 2 * nb * d.L;
+    if (d.Ck == 64) readout_prep_kappa_kernel<64><<<(n + 127) / 128, 128, 0, st>>>(a.kappa[0], a.kappa[nb - 1], U, nb, d.L, kblob);
+    else readout_prep_kappa_kernel<128><<<(n + 127) / 128, 128, 0, st>>>(a.kappa[0], a.kappa[nb - 1], U, nb, d.L, kblob);
     SWEM_LAUNCH_CHECK();
-    const long long m = (long long)U * 2 * nb * ro::kCv * (ro::kL / 8);
-    readout_prep_nu_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(a.nu[0], a.nu[nb - 1], U, nb, vblob);
+    const long long m = (long long)U * 2 * nb * ro::kCv * (d.L / 8);
+    readout_prep_nu_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(a.nu[0], a.nu[nb - 1], U, nb, d.L, vblob);
     SWEM_LAUNCH_CHECK();
   }
+#define SWEM_RO_ATTR(LT_, CK_) \
+  SWEM_CUDA(cudaFuncSetAttribute(readout_fused_kernel<LT_, CK_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ro::smem_bytes<CK_>()))
   static bool attr_set = false;
   if (!attr_set) {
-    SWEM_CUDA(cudaFuncSetAttribute(readout_fused_kernel<1, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ro::smem_bytes<64>()));
-    SWEM_CUDA(cudaFuncSetAttribute(readout_fused_kernel<2, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ro::smem_bytes<64>()));
-    SWEM_CUDA(cudaFuncSetAttribute(readout_fused_kernel<1, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ro::smem_bytes<128>()));
-    SWEM_CUDA(cudaFuncSetAttribute(readout_fused_kernel<2, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ro::smem_bytes<128>()));
+    SWEM_RO_ATTR(64, 64); SWEM_RO_ATTR(128, 64); SWEM_RO_ATTR(256, 64);
+    SWEM_RO_ATTR(64, 128); SWEM_RO_ATTR(128, 128); SWEM_RO_ATTR(256, 128);
     attr_set = true;
   }
+#undef SWEM_RO_ATTR
   ReadoutFusedParams p{};
   p.qk = a.qk; p.kblob = kblob; p.vblob = vblob; p.out = a.out; p.escratch = escr;
   p.N = d.N; p.HW = d.HW; p.T = T; p.n_banks = nb; p.out_channels = a.out_channels; p.mem_channel = a.mem_channel;
   p.pixel_major = a.out_pixel_major;
   p.c1s = kLog2e / (d.tau * ro::kKScale);
   p.prof = get_profile_buffer();
+#define SWEM_RO_LAUNCH(LT_, CK_) readout_fused_kernel<LT_, CK_><<<U * T * 2, 256, ro::smem_bytes<CK_>(), st>>>(p)
   if (d.Ck == 64) {
-    if (nb == 1) readout_fused_kernel<1, 64><<<U * T * 2, 256, ro::smem_bytes<64>(), st>>>(p);
-    else readout_fused_kernel<2, 64><<<U * T * 2, 256, ro::smem_bytes<64>(), st>>>(p);
+    if (Lt == 64) SWEM_RO_LAUNCH(64, 64);
+    else if (Lt == 128) SWEM_RO_LAUNCH(128, 64);
+    else SWEM_RO_LAUNCH(256, 64);
   } else {
-    if (nb == 1) readout_fused_kernel<1, 128><<<U * T * 2, 256, ro::smem_bytes<128>(), st>>>(p);
-    else readout_fused_kernel<2, 128><<<U * T * 2, 256, ro::smem_bytes<128>(), st>>>(p);
+    if (Lt == 64) SWEM_RO_LAUNCH(64, 128);
+    else if (Lt == 128) SWEM_RO_LAUNCH(128, 128);
+    else SWEM_RO_LAUNCH(256, 128);
   }
+#undef SWEM_RO_LAUNCH
   SWEM_LAUNCH_CHECK();
   return launch_perm_inv(escr, U, d.HW, Lt, d.topl, a.out, a.out_channels, a.s_channel, a.out_pixel_major, st);
 }

@@ -22,7 +22,7 @@ import torch  # noqa: E402
 from swem_b200 import SWEMCore, _lib  # noqa: E402
 from swem_b200.synthetic import em_inputs  # noqa: E402
 
-CK, CV, N = 64, 512, 5
+CK, CV, N = 64, 512, 5      # CK is overridden by --ck
 
 
 def peak_tflops():
@@ -58,7 +58,10 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--reps', type=int, default=100)
     ap.add_argument('--quick', action='store_true', help='HW=1620 only, I in {1,4}')
+    ap.add_argument('--ck', type=int, default=64, help='key channels (64 = BASELINE, 128 = reference CLI default)')
     args = ap.parse_args()
+    global CK
+    CK = args.ck
     dev = torch.device('cuda:0')
     lib = _lib.load()
     peak = peak_tflops()
