@@ -77,22 +77,25 @@ struct Lay {
     return (st < kOwnStages) ? kOffVS + st * kStageBytes : kOffXH + (st - kOwnStages) * kStageBytes;
   }
 };
+template <int LB>
 struct Misc {
   float inv_nx[kTP];
   float mask[kTP];
   float hmax[2][kTP];
   float hsum[2][kTP];
   float hew[2][kTP];
-  float2 mbox[2][2][kTP];   // [iteration parity][side][pixel] = (side max of the logits, side sum of W-step exps)
+  float2 mbox[2][2][kTP];   // LB = 1: [iteration parity][side][pixel] = (side max of the logits, side sum of W-step exps)
+  float4 mbox4[LB > 1 ? 2 : 1][LB > 1 ? 2 * LB : 1][LB > 1 ? kTP : 1];   // LB > 1: [parity][cluster rank][pixel] = (max, E-step sum, W-step sum, -)
   uint64_t bar_mma;
   uint64_t bar_full[kStages];
   uint64_t bar_empty[kStages];
   uint32_t tmem_base;
   int abort_flag;
 };
-template <int CK>
-constexpr uint32_t smem_bytes() { return Lay<CK>::kOffMisc + sizeof(Misc) + 128; }
-static_assert(smem_bytes<64>() <= 227 * 1024 && smem_bytes<128>() <= 227 * 1024, "shared memory budget");
+template <int CK, int LB>
+constexpr uint32_t smem_bytes() { return Lay<CK>::kOffMisc + sizeof(Misc<LB>) + 128; }
+static_assert(smem_bytes<64, 1>() <= 227 * 1024 && smem_bytes<128, 1>() <= 227 * 1024 && smem_bytes<64, 2>() <= 227 * 1024 &&
+              smem_bytes<128, 2>() <= 227 * 1024, "shared memory budget");
 
 // TMEM columns
 constexpr uint32_t kColE = 0;      // [128 px][128]     E / W logits of this side
@@ -112,9 +115,9 @@ struct EmPairParams {
   float* zita;
   float* z_last;
   uint8_t* vblob;        // [U][T][8][32 KB] scratch: operand images of V (written in set-up, read after the last E-step)
-  float* acc_k;          // [U][n_iters][2][CK + 1][128], zeroed before launch
-  float* acc_nu;         // [U][2][512][128], zeroed before launch
-  unsigned* counters;    // [U][n_iters][2], zeroed before launch
+  float* acc_k;          // [U][n_iters][2][LB][CK + 1][128], zeroed before launch   (LB = basis blocks of 128 per side)
+  float* acc_nu;         // [U][2][LB][512][128], zeroed before launch
+  unsigned* counters;    // [U][n_iters][2][LB], zeroed before launch
   int* status;
   long long* prof;
   int N, HW, T, n_iters, u0;
@@ -133,6 +136,9 @@ __device__ __forceinline__ uint32_t map_to_peer(uint32_t smem_addr, uint32_t ran
   uint32_t r;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
   return r;
+}
+__device__ __forceinline__ void st_cluster_f4(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 __device__ __forceinline__ void st_cluster_f2(uint32_t addr, float a, float b) {
   asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(a), "f"(b) : "memory");
@@ -183,18 +189,21 @@ __device__ __forceinline__ void convert_v_chunk(const float* __restrict__ vsrc /
 }
 
 // ------------------------------------------------------------------------------------------------------
-template <int CK>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) em_pair_kernel(const EmPairParams p) {
+template <int CK, int LB>   // key channels; basis blocks of 128 per side (L = 64 / 128: 1, L = 256: 2) -> cluster of 2 * LB CTAs
+__global__ void __cluster_dims__(2 * LB, 1, 1) __launch_bounds__(256, 1) em_pair_kernel(const EmPairParams p) {
   using namespace em;
   using LY = Lay<CK>;
   constexpr int kCk = CK;
+  constexpr int CS = 2 * LB;
   constexpr uint32_t kOffXH = LY::kOffXH, kOffXL = LY::kOffXL, kOffKH = LY::kOffKH, kOffKL = LY::kOffKL, kOffZ = LY::kOffZ,
                      kOffZL = LY::kOffZL, kOffMisc = LY::kOffMisc;
   extern __shared__ __align__(1024) uint8_t smem[];
-  Misc& ms = *reinterpret_cast<Misc*>(smem + kOffMisc);
+  Misc<LB>& ms = *reinterpret_cast<Misc<LB>*>(smem + kOffMisc);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int sd = (int)cluster_ctarank();                // side handled by this CTA (0 = background, 1 = foreground)
-  const int pair = blockIdx.x >> 1;
+  const int rank = (int)cluster_ctarank();
+  const int sd = rank & 1;                              // side handled by this CTA (0 = background, 1 = foreground)
+  const int lb = rank >> 1;                             // block of 128 bases of that side
+  const int pair = blockIdx.x / CS;
   const int tile = pair % p.T;
   const int u = p.u0 + pair / p.T;
   const int b = u / p.N;
@@ -222,19 +231,26 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) em_pair_kern
   // (warps 0-3) run the cross-tile reduction and the finalize -- the conversion is HBM-bound and would otherwise be
   // 6 us of exposed set-up.  The W-step cluster barrier of the last iteration publishes all of them to the pair.
   uint8_t* const vimg = p.vblob + ((size_t)u * p.T + tile) * kChunks * kStageBytes;
-  const float* const vhalf = p.v + ((size_t)u * kCv + sd * 256) * HW;
-  uint8_t* const my_images = vimg + (size_t)sd * 4 * kStageBytes;
-  int chunks_done = (I >= 4) ? 1 : 5 - I;               // I = 1 -> 4 (no later barrier), 2 -> 3, 3 -> 2, >= 4 -> 1
-  for (int q = 0; q < chunks_done; ++q) convert_v_chunk<8>(vhalf, my_images + (size_t)q * kStageBytes, p0 + q * 32, HW, warp, lane);
+  constexpr int kMine = kChunks / CS;                   // images converted by this CTA: rank * kMine + j, image c = (half c/4, quarter c%4)
+  auto convert_mine = [&](int j, bool whole_cta) {
+    const int c = rank * kMine + j;
+    const float* src = p.v + ((size_t)u * kCv + (c >> 2) * 256) * HW;
+    if (whole_cta) convert_v_chunk<8>(src, vimg + (size_t)c * kStageBytes, p0 + (c & 3) * 32, HW, warp, lane);
+    else convert_v_chunk<4>(src, vimg + (size_t)c * kStageBytes, p0 + (c & 3) * 32, HW, warp - 4, lane);
+  };
+  int chunks_done = (I - 1 >= kMine - 1) ? 1 : kMine - (I - 1);   // what cannot be hidden behind iterations 0 .. I-2 is done here
+  for (int j = 0; j < chunks_done; ++j) convert_mine(j, true);
   __threadfence();
   asm volatile("fence.proxy.async;" ::: "memory");     // generic-proxy global stores -> visible to the bulk-copy (async proxy) reads
   // rows: thread tid < 128 <-> basis l = tid of side sd (finalize steps)
   const bool row_thread = tid < kL;
   const int L = p.L;                                    // L = 64: rows / columns 64..127 of every operand are zero padding
-  const bool valid_row = tid < L;
+  const int lrow = lb * kL + tid;                       // this row thread's basis inside the side
+  const bool valid_row = lrow < L;
   const int gs = u * 2 + sd;                            // (b, n, s) index
-  const float zita_p = valid_row ? __ldg(p.zita_prior + (size_t)gs * L + tid) : 0.f;
-  const float* kprior = p.kappa_prior + ((size_t)gs * kCk) * L + (valid_row ? tid : 0);   // + c*L
+  const int gsl = gs * LB + lb;                         // (b, n, s, basis block): index of this CTA's accumulators
+  const float zita_p = valid_row ? __ldg(p.zita_prior + (size_t)gs * L + lrow) : 0.f;
+  const float* kprior = p.kappa_prior + ((size_t)gs * kCk) * L + (valid_row ? lrow : 0);   // + c*L
   auto stage_khat = [&](const float (&kap)[kCk]) {      // khat = l2norm(kappa) * 256 -> fp16 hi/lo K-major rows (reference :115)
     float ss = 0.f;
 #pragma unroll
@@ -319,7 +335,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) em_pair_kern
     asm volatile("fence.proxy.async;" ::: "memory");
     for (int k = 0; k < LY::kOwnStages; ++k) load_image(k);
   };
-  if (I == 1 && tid == 0) prefetch_images();
+  if (LB == 1 && I == 1 && tid == 0) prefetch_images();   // (LB > 1: every iteration has a cluster barrier, see the epilogue)
   const uint32_t tmem = ms.tmem_base;
   uint32_t ph_mma = 0;
   bool failed = false;
@@ -329,7 +345,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) em_pair_kern
   const uint32_t idesc_mhi = make_idesc(128, kCk + 16, kFmtF16, kFmtF16, kMajorMN, kMajorK);
   const uint32_t idesc_mlo = make_idesc(128, kCk, kFmtF16, kFmtF16, kMajorMN, kMajorK);
   const uint32_t idesc_nu = make_idesc(128, 256, kFmtF16, kFmtF16, kMajorMN, kMajorK);
-  const uint32_t peer_mbox = map_to_peer(smem_u32(&ms.mbox[0][0][0]), (uint32_t)(sd ^ 1));
+  const uint32_t peer_mbox = map_to_peer(smem_u32(&ms.mbox[0][0][0]), (uint32_t)(rank ^ 1));
 
   for (int it = 0; it < I; ++it) {
     fence_proxy_async_smem();
@@ -373,7 +389,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) em_pair_kern
 #pragma unroll
         for (int j = 0; j < 32; ++j) a[q * 32 + j] = __uint_as_float(r[j]);
       }
-      const bool active = hb * 64 < L;                  // L = 64: the second half of the columns is padding
+      const bool active = lb * kL + hb * 64 < L;        // L = 64: the second half of the columns is padding
       if (!active) {
 #pragma unroll
         for (int i = 0; i < 64; ++i) a[i] = -3.0e38f;   // exp2((a - max) * c) underflows to exactly 0 everywhere below
@@ -388,36 +404,81 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) em_pair_kern
       // against its own max and the pair rescales after the exchange: exp(t - M) = exp(t - m_s) * exp(m_s - M).
       const float cw = ms.inv_nx[px] * p.c1s;
       const int par = it & 1;
-      if (do_w) {                                       // W-step sums first: the exchange flies while the E-step exps run
-        float e = 0.f;
+      float sum = 0.f, w = ms.mask[px];
+      if constexpr (LB == 1) {
+        if (do_w) {                                     // W-step sums first: the exchange flies while the E-step exps run
+          float e = 0.f;
 #pragma unroll
-        for (int i = 0; i < 64; ++i) e += fast_exp2((a[i] - mx) * cw);
+          for (int i = 0; i < 64; ++i) e += fast_exp2((a[i] - mx) * cw);
+          ms.hew[hb][px] = e;
+          __syncthreads();
+          if (hb == 0) {
+            const float es = ms.hew[0][px] + ms.hew[1][px];
+            ms.mbox[par][sd][px] = make_float2(mx, es);
+            st_cluster_f2(peer_mbox + (uint32_t)(((par * 2 + sd) * kTP + px) * sizeof(float2)), mx, es);
+          }
+          cluster_arrive();
+        }
+#pragma unroll
+        for (int i = 0; i < 64; ++i) {
+          a[i] = fast_exp2((a[i] - mx) * p.c1s);
+          sum += a[i];
+        }
+        ms.hsum[hb][px] = sum;
+        __syncthreads();
+        sum = ms.hsum[0][px] + ms.hsum[1][px];
+        if (do_w) {
+          cluster_wait();
+          if (it == I - 1 && tid == 0) prefetch_images();  // every chunk of the pair was converted before this barrier
+          const float2 m0 = ms.mbox[par][0][px], m1 = ms.mbox[par][1][px];
+          const float gm = fmaxf(m0.x, m1.x);
+          const float e0 = m0.y * fast_exp2((m0.x - gm) * cw), e1 = m1.y * fast_exp2((m1.x - gm) * cw);
+          w *= 1.f - (sd ? e1 : e0) / (e0 + e1);
+        }
+      } else {
+        // L = 128 * LB: the bases of a side are spread over LB CTAs.  Every CTA works against the max m of ITS 128
+        // columns, publishes (m, E-step sum, W-step sum) to the whole cluster, and rescales after one barrier:
+        //   softmax denominator of the side = sum_c s_c 2^((m_c - M_side) c1),  z *= 2^((m_own - M_side) c1)
+        float e = 0.f;
+        if (do_w) {
+#pragma unroll
+          for (int i = 0; i < 64; ++i) e += fast_exp2((a[i] - mx) * cw);
+        }
+#pragma unroll
+        for (int i = 0; i < 64; ++i) {
+          a[i] = fast_exp2((a[i] - mx) * p.c1s);
+          sum += a[i];
+        }
+        ms.hsum[hb][px] = sum;
         ms.hew[hb][px] = e;
         __syncthreads();
-        if (hb == 0) {
-          const float es = ms.hew[0][px] + ms.hew[1][px];
-          ms.mbox[par][sd][px] = make_float2(mx, es);
-          st_cluster_f2(peer_mbox + (uint32_t)(((par * 2 + sd) * kTP + px) * sizeof(float2)), mx, es);
+        {
+          const float sc = ms.hsum[0][px] + ms.hsum[1][px], ec = ms.hew[0][px] + ms.hew[1][px];
+          const uint32_t slot = smem_u32(&ms.mbox4[par][rank][px]);
+          for (int rr = hb; rr < CS; rr += 2)             // the two threads of a pixel share the CS destinations
+            st_cluster_f4(map_to_peer(slot, (uint32_t)rr), mx, sc, ec, 0.f);
         }
         cluster_arrive();
-      }
-      float sum = 0.f;
-#pragma unroll
-      for (int i = 0; i < 64; ++i) {
-        a[i] = fast_exp2((a[i] - mx) * p.c1s);
-        sum += a[i];
-      }
-      ms.hsum[hb][px] = sum;
-      __syncthreads();
-      sum = ms.hsum[0][px] + ms.hsum[1][px];
-      float w = ms.mask[px];
-      if (do_w) {
         cluster_wait();
-        if (it == I - 1 && tid == 0) prefetch_images();  // every chunk of the pair was converted before this barrier
-        const float2 m0 = ms.mbox[par][0][px], m1 = ms.mbox[par][1][px];
-        const float gm = fmaxf(m0.x, m1.x);
-        const float e0 = m0.y * fast_exp2((m0.x - gm) * cw), e1 = m1.y * fast_exp2((m1.x - gm) * cw);
-        w *= 1.f - (sd ? e1 : e0) / (e0 + e1);
+        if (it == I - 1 && tid == 0) prefetch_images();    // every chunk of the cluster was converted before this barrier
+        float Ms = -3.0e38f, gm = -3.0e38f;
+#pragma unroll
+        for (int rr = 0; rr < CS; ++rr) {
+          const float m = ms.mbox4[par][rr][px].x;
+          gm = fmaxf(gm, m);
+          if ((rr & 1) == sd) Ms = fmaxf(Ms, m);
+        }
+        float S = 0.f, e0 = 0.f, e1 = 0.f;
+#pragma unroll
+        for (int rr = 0; rr < CS; ++rr) {
+          const float4 t = ms.mbox4[par][rr][px];
+          if ((rr & 1) == sd) S += t.y * fast_exp2((t.x - Ms) * p.c1s);
+          const float ew = t.z * fast_exp2((t.x - gm) * cw);
+          if (rr & 1) e1 += ew; else e0 += ew;
+        }
+        if (do_w) w *= 1.f - (sd ? e1 : e0) / (e0 + e1);
+        sum = S;
+        w *= fast_exp2((mx - Ms) * p.c1s);                 // this CTA's exps were taken against its own max
       }
       const float scale = w / sum;
       const float zs = scale * kZScale;
@@ -432,7 +493,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) em_pair_kern
         *reinterpret_cast<uint4*>(smem + kOffZL + off) = *reinterpret_cast<uint4*>(lo);
       }
       if (p.z_last != nullptr && it == I - 1 && p0 + px < HW && active) {
-        float4* dst = reinterpret_cast<float4*>(p.z_last + ((size_t)gs * HW + p0 + px) * L + hb * 64);
+        float4* dst = reinterpret_cast<float4*>(p.z_last + ((size_t)gs * HW + p0 + px) * L + lb * kL + hb * 64);
 #pragma unroll
         for (int g = 0; g < 16; ++g)
           dst[g] = make_float4(a[g * 4] * scale, a[g * 4 + 1] * scale, a[g * 4 + 2] * scale, a[g * 4 + 3] * scale);
@@ -468,7 +529,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) em_pair_kern
 
     // partial of this tile for row l = tid -> fp32 reductions straight from TMEM into the L2-resident accumulator
     // [c][l] (coalesced over l; fire-and-forget, the fence comes later so that they fly during what follows)
-    float* acc = p.acc_k + ((size_t)(u * I + it) * 2 + sd) * ((kCk + 1) * kL);
+    float* acc = p.acc_k + ((size_t)((u * I + it) * 2 + sd) * LB + lb) * ((kCk + 1) * kL);
     if (row_thread) {
       const uint32_t base = tmem_addr(tmem, (warp & 3) * 32, kColM);
 #pragma unroll
@@ -552,7 +613,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) em_pair_kern
           fence_proxy_async_smem();
           __syncthreads();
           if (tid == 0) {
-            float* dst = p.acc_nu + ((size_t)gs * kCv + q * 64) * kL;
+            float* dst = p.acc_nu + ((size_t)gsl * kCv + q * 64) * kL;
             asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(dst),
                          "r"(smem_u32(ns)), "r"(64 * 128 * 4)
                          : "memory");
@@ -570,7 +631,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) em_pair_kern
 
     // ---- (4) cross-tile reduction of the M-step partial: fence the reductions issued above, arrive; after the last tile
     // arrived every CTA reads the total back the same way it was accumulated.
-    unsigned* counter = p.counters + ((size_t)u * I + it) * 2 + sd;
+    unsigned* counter = p.counters + (((size_t)u * I + it) * 2 + sd) * LB + lb;
     if (row_thread) {                 // warps 0-3; they synchronise among themselves on named barrier 1
       __threadfence();                // (the prior-row loads come after it: a fence waits for every earlier access)
       asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -604,8 +665,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) em_pair_kern
           ms.hsum[0][tid] = rz;       // (dead E-step scratch) 1 / zita and the prior zita of row l, for the nu slice below
           ms.hsum[1][tid] = zita_p;
           if (tile == 0 && valid_row) {
-            p.zita[(size_t)gs * L + tid] = zita_cur;
-            float* kout = p.kappa + ((size_t)gs * kCk) * L + tid;
+            p.zita[(size_t)gs * L + lrow] = zita_cur;
+            float* kout = p.kappa + ((size_t)gs * kCk) * L + lrow;
 #pragma unroll
             for (int c = 0; c < kCk; ++c) kout[(size_t)c * L] = kap[c];
           }
@@ -613,13 +674,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) em_pair_kern
           stage_khat(kap);
         }
       }
-    } else if (chunks_done < 4 && !last) {
+    } else if (chunks_done < kMine && !last) {
       // warps 4-7: one more V chunk, hidden behind the row threads' reduction, cross-tile wait and finalize
-      convert_v_chunk<4>(vhalf, my_images + (size_t)chunks_done * kStageBytes, p0 + chunks_done * 32, HW, warp - 4, lane);
+      convert_mine(chunks_done, false);
       __threadfence();
       asm volatile("fence.proxy.async;" ::: "memory");
     }
-    if (chunks_done < 4 && !last) ++chunks_done;
+    if (chunks_done < kMine && !last) ++chunks_done;
     __syncthreads();
     if (ms.abort_flag) {
       if (tid == 0) atomicExch(p.status, 1 + it);
@@ -633,12 +694,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) em_pair_kern
       const int dper = (kCv + p.T - 1) / p.T;
       const int d0 = tile * dper, d1 = min(kCv, d0 + dper);
       constexpr float kInvZ = 1.f / kZScale;
-      const float4* acc4 = reinterpret_cast<const float4*>(p.acc_nu + (size_t)gs * kCv * kL);     // [d][128]
+      const float4* acc4 = reinterpret_cast<const float4*>(p.acc_nu + (size_t)gsl * kCv * kL);    // [d][128] of this basis block
       const float4* pri4 = reinterpret_cast<const float4*>(p.nu_prior + (size_t)gs * kCv * L);    // [d][L]
       float4* out4 = reinterpret_cast<float4*>(p.nu + (size_t)gs * kCv * L);
-      const int l4n = L / 4;
-      for (int i = d0 * l4n + tid; i < d1 * l4n; i += 256) {
-        const int d = i / l4n, l4 = i % l4n, l = l4 * 4;
+      const int l4n = (L < kL ? L : kL) / 4;              // float4 columns of this block that exist
+      for (int k = d0 * l4n + tid; k < d1 * l4n; k += 256) {
+        const int d = k / l4n, l4 = k % l4n, l = l4 * 4;
+        const int i = d * (L / 4) + lb * (kL / 4) + l4;   // position in the [d][L] tensors
         const float4 a = __ldcg(acc4 + d * (kL / 4) + l4);
         const float4 pr = __ldg(pri4 + i);
         float4 o;
@@ -667,29 +729,29 @@ static long long* g_prof = nullptr;
 void set_profile_buffer(void* dev) { g_prof = static_cast<long long*>(dev); }
 long long* get_profile_buffer() { return g_prof; }
 
-template <int CK>
-static int max_pairs_resident() {
+template <int CK, int LB>
+static int max_clusters_resident() {
   static int n = -1;
   if (n < 0) {
-    cudaFuncSetAttribute(em_pair_kernel<CK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)em::smem_bytes<CK>());
+    cudaFuncSetAttribute(em_pair_kernel<CK, LB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)em::smem_bytes<CK, LB>());
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(2, 1, 1);
+    cfg.gridDim = dim3(2 * LB, 1, 1);
     cfg.blockDim = dim3(256, 1, 1);
-    cfg.dynamicSmemBytes = em::smem_bytes<CK>();
+    cfg.dynamicSmemBytes = em::smem_bytes<CK, LB>();
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.x = 2 * LB;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     int clusters = 0;
-    if (cudaOccupancyMaxActiveClusters(&clusters, em_pair_kernel<CK>, &cfg) != cudaSuccess || clusters <= 0) {
+    if (cudaOccupancyMaxActiveClusters(&clusters, em_pair_kernel<CK, LB>, &cfg) != cudaSuccess || clusters <= 0) {
       cudaGetLastError();
       int dev = 0, sms = 0;
       cudaGetDevice(&dev);
       cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-      clusters = sms / 2 - 2;                          // conservative guess
+      clusters = sms / (2 * LB) - 4;                   // conservative guess
     }
     n = clusters;
   }
@@ -697,39 +759,41 @@ static int max_pairs_resident() {
 }
 
 bool fused_em_supported(const SwemDims& d) {
-  if ((d.Ck != 64 && d.Ck != 128) || (d.L != 64 && d.L != em::kL) || d.Cv != em::kCv || d.n_iters < 1 || d.n_iters > 16) return false;
+  if ((d.Ck != 64 && d.Ck != 128) || (d.L != 64 && d.L != 128 && d.L != 256) || d.Cv != em::kCv || d.n_iters < 1 || d.n_iters > 16)
+    return false;
   const int T = (d.HW + em::kTP - 1) / em::kTP;
-  return T >= 1 && T <= 64;            // all pairs of one unit must be co-resident (74 pairs on a B200)
+  return T >= 1 && T <= (d.L == 256 ? 28 : 64);   // all clusters of one unit must be co-resident (74 pairs / ~32 quads on a B200)
 }
 
 size_t fused_em_workspace(const SwemDims& d) {
   const size_t U = (size_t)d.B * d.N;
   const size_t T = (d.HW + em::kTP - 1) / em::kTP;
   size_t bytes = 0;
-  bytes += align_up(U * d.n_iters * 2 * (size_t)(d.Ck + 1) * em::kL * 4, 256);
-  bytes += align_up(U * 2 * em::kCv * em::kL * 4, 256);
-  bytes += align_up(U * d.n_iters * 2 * 4 + 4, 256);
+  const size_t LB = d.L > 128 ? d.L / 128 : 1;
+  bytes += align_up(U * d.n_iters * 2 * LB * (size_t)(d.Ck + 1) * em::kL * 4, 256);
+  bytes += align_up(U * 2 * LB * em::kCv * em::kL * 4, 256);
+  bytes += align_up(U * d.n_iters * 2 * LB * 4 + 4, 256);
   bytes += align_up(U * T * em::kChunks * em::kStageBytes, 256);
   return bytes + 256;
 }
 
-template <int CK>
+template <int CK, int LB>
 static int fused_em_forward_t(const SwemEmArgs& a, cudaStream_t st) {
   const SwemDims& d = a.dims;
   const int U = d.B * d.N;
   const int T = (d.HW + em::kTP - 1) / em::kTP;
   Arena ws(a.workspace);
-  float* acc_k = ws.take<float>((size_t)U * d.n_iters * 2 * (CK + 1) * em::kL);
-  float* acc_nu = ws.take<float>((size_t)U * 2 * em::kCv * em::kL);
-  unsigned* counters = ws.take<unsigned>((size_t)U * d.n_iters * 2 + 1);
-  int* status = reinterpret_cast<int*>(counters + (size_t)U * d.n_iters * 2);
+  float* acc_k = ws.take<float>((size_t)U * d.n_iters * 2 * LB * (CK + 1) * em::kL);
+  float* acc_nu = ws.take<float>((size_t)U * 2 * LB * em::kCv * em::kL);
+  unsigned* counters = ws.take<unsigned>((size_t)U * d.n_iters * 2 * LB + 1);
+  int* status = reinterpret_cast<int*>(counters + (size_t)U * d.n_iters * 2 * LB);
   SWEM_CUDA(cudaMemsetAsync(a.workspace, 0, ws.off, st));
   count_launch();
   uint8_t* vblob = ws.take<uint8_t>((size_t)U * T * em::kChunks * em::kStageBytes);
 
   static bool attr_set = false;
   if (!attr_set) {
-    SWEM_CUDA(cudaFuncSetAttribute(em_pair_kernel<CK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)em::smem_bytes<CK>()));
+    SWEM_CUDA(cudaFuncSetAttribute(em_pair_kernel<CK, LB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)em::smem_bytes<CK, LB>()));
     attr_set = true;
   }
   EmPairParams p{};
@@ -743,20 +807,25 @@ static int fused_em_forward_t(const SwemEmArgs& a, cudaStream_t st) {
   p.prof = get_profile_buffer();
   // all CTAs of a launch spin on each other: every launch must be co-resident (1 CTA per SM, 2-CTA clusters);
   // units that do not fit are spread evenly over the fewest launches
-  const int upl_max = max_pairs_resident<CK>() / T > 0 ? max_pairs_resident<CK>() / T : 1;
+  if (max_clusters_resident<CK, LB>() < T) {
+    set_error("fused EM: %d clusters of %d CTAs cannot be co-resident (limit %d)", T, 2 * LB, max_clusters_resident<CK, LB>());
+    return SWEM_ERR_UNSUPPORTED;
+  }
+  const int upl_max = max_clusters_resident<CK, LB>() / T;
   const int n_launch = (U + upl_max - 1) / upl_max;
   const int upl = (U + n_launch - 1) / n_launch;
   for (int u0 = 0; u0 < U; u0 += upl) {
     const int nu = (U - u0 < upl) ? (U - u0) : upl;
     p.u0 = u0;
-    em_pair_kernel<CK><<<nu * T * 2, 256, em::smem_bytes<CK>(), st>>>(p);
+    em_pair_kernel<CK, LB><<<nu * T * 2 * LB, 256, em::smem_bytes<CK, LB>(), st>>>(p);
     SWEM_LAUNCH_CHECK();
   }
   return SWEM_OK;
 }
 
 int fused_em_forward(const SwemEmArgs& a, cudaStream_t st) {
-  return a.dims.Ck == 128 ? fused_em_forward_t<128>(a, st) : fused_em_forward_t<64>(a, st);
+  if (a.dims.L == 256) return a.dims.Ck == 128 ? fused_em_forward_t<128, 2>(a, st) : fused_em_forward_t<64, 2>(a, st);
+  return a.dims.Ck == 128 ? fused_em_forward_t<128, 1>(a, st) : fused_em_forward_t<64, 1>(a, st);
 }
 
 }  // namespace swem
