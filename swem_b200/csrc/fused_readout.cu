@@ -1,6 +1,8 @@
 // Fused readout (attention from query pixels to the memory bases) for sm_100a: tcgen05 + TMEM + TMA.
 //
-// Covers Ck = 64, L = 128, Cv = 512, 1 or 2 banks, any HW / B*N.  Reference semantics:
+// Covers Ck = 64 / 128, Cv = 512, Lt = banks x L columns per side in {64, 128, 256, 512}, any HW / B*N.  Lt = 512
+// (L = 256 with both banks) runs as 2-CTA clusters: each CTA takes 256 columns of either side, the pair exchanges
+// the row max / row sum and the halves of the un-normalised output over distributed shared memory.  Reference semantics:
 // methods/SWEM/modules.py:278-293 (matching), :232-276 (get_affinity), :198-208 (perm_inv_feat).
 //
 // Two launches + the shared top-l kernel:
@@ -57,6 +59,8 @@ struct Misc {
   float inv_nq[kTP];
   float ex_max[2][kTP];
   float ex_sum[2][kTP];
+  float peer_max[kTP];      // (column-split clusters) row max / row sum of the peer CTA's columns, written by the peer
+  float peer_sum[kTP];
   uint64_t bar_k[2];
   uint64_t bar_mma;
   uint64_t bar_full[kStages];
@@ -71,12 +75,13 @@ static_assert(smem_bytes<64>() <= 227 * 1024 && smem_bytes<128>() <= 227 * 1024,
 
 struct ReadoutFusedParams {
   const float* qk;        // [B][64][HW]
-  const uint8_t* kblob;   // [U][2 sides][hi | lo] each n_banks*16 KB
+  const uint8_t* kblob;   // [U][2 sides][column blocks][hi | lo planes of min(Lt, 256) rows]
   const uint8_t* vblob;   // [U][2 halves][KS2 k-steps][16 KB]
   float* out;             // [U][out_channels][HW]
   float* escratch;        // [U][HW][2*Lt] fp32 un-normalised E (for the top-l feature)
   long long* prof;        // optional phase stamps of CTA 0 (slots 128..), see swem_set_profile_buffer
   int N, HW, T, n_banks, out_channels, mem_channel, pixel_major;
+  int Lt_total;           // columns per side in memory (= columns per side of one CTA x column blocks)
   float c1s;              // log2(e) / (tau * kKScale)
 };
 
@@ -86,8 +91,8 @@ struct ReadoutFusedParams {
   } while (0)
 
 // ---- prep: banks -> operand blobs ------------------------------------------------------------------
-// khat blob of (u, s): K-major rows j = bank*128 + l, byte = (j%8)*16 + (j/8)*128 + (c/8)*LBO + (c%8)*2,
-// LBO = n_banks*L*16; hi plane then lo plane.
+// khat blob of (u, s, column block): K-major rows jl = (bank*L + l) % R, R = min(Lt, 256) rows per block,
+// byte = (jl%8)*16 + (jl/8)*128 + (c/8)*LBO + (c%8)*2, LBO = R*16; hi plane then lo plane.
 template <int kCk>
 __global__ void readout_prep_kappa_kernel(const float* __restrict__ k0, const float* __restrict__ k1, int U, int n_banks, int kL,
                                           uint8_t* __restrict__ kblob) {
@@ -104,10 +109,12 @@ __global__ void readout_prep_kappa_kernel(const float* __restrict__ k0, const fl
     ss = fmaf(v[c], v[c], ss);
   }
   const float sc = kKScale / (sqrtf(ss) + kEpsNorm);
-  const uint32_t plane = n_banks * kL * kCk * 2;               // bytes of one (hi or lo) plane
-  const uint32_t lbo = n_banks * kL * 16;
-  uint8_t* base = kblob + ((size_t)u * 2 + s) * 2 * plane;
-  const int j = bank * kL + l;
+  const int Lt = n_banks * kL, R = Lt < 256 ? Lt : 256, nblk = Lt / R;
+  const uint32_t plane = R * kCk * 2;                          // bytes of one (hi or lo) plane of a block
+  const uint32_t lbo = R * 16;
+  const int jt = bank * kL + l;
+  uint8_t* base = kblob + (((size_t)u * 2 + s) * nblk + jt / R) * 2 * plane;
+  const int j = jt % R;
 #pragma unroll
   for (int g = 0; g < kCk / 8; ++g) {
     __align__(16) __half hi[8];
@@ -152,7 +159,11 @@ __global__ void readout_prep_nu_kernel(const float* __restrict__ n0, const float
 }
 
 // ---- main kernel --------------------------------------------------------------------------------------
-template <int LT, int CK>   // columns per side (banks x L: 64, 128 or 256) and key channels (64 or 128) fix every loop count, so the MMA issue loops unroll
+// LT = columns per side handled by one CTA (64, 128 or 256), CK = key channels (64 or 128): they fix every loop count, so
+// the MMA issue loops unroll.  NS = column blocks = CTAs per cluster (1; 2 when banks x L = 512, launched with a cluster
+// attribute): CTA `rank` takes columns [rank * LT, +LT) of either side and finalises value channels [rank * 128, +128)
+// of its half.
+template <int LT, int CK, int NS>
 __global__ void __launch_bounds__(256, 1) readout_fused_kernel(const ReadoutFusedParams p) {
   using namespace ro;
   using LY = Lay<CK>;
@@ -162,9 +173,12 @@ __global__ void __launch_bounds__(256, 1) readout_fused_kernel(const ReadoutFuse
   extern __shared__ __align__(1024) uint8_t smem[];
   Misc& ms = *reinterpret_cast<Misc*>(smem + kOffMisc);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int h = blockIdx.x & 1;
-  const int tile = (blockIdx.x >> 1) % p.T;
-  const int u = (blockIdx.x >> 1) / p.T;
+  const int rank = (NS == 1) ? 0 : (int)cluster_ctarank();
+  const int bid = blockIdx.x / NS;
+  const int h = bid & 1;
+  const int tile = (bid >> 1) % p.T;
+  const int u = (bid >> 1) / p.T;
+  constexpr int kRing = (NS == 1) ? kStages : 4;   // NS = 2: the other 64 KB of the ring region receive the peer's partial
   const int b = u / p.N;
   const int p0 = tile * kTP;
   const int HW = p.HW;
@@ -190,9 +204,10 @@ __global__ void __launch_bounds__(256, 1) readout_fused_kernel(const ReadoutFuse
     // khat blobs (hi + lo planes are contiguous): one bulk copy per resident side
     for (int s = 0; s < LY::kSidesResident; ++s) {
       mbar_expect_tx(&ms.bar_k[s], 2 * kplane);
-      bulk_g2s(smem + kOffKB + s * kKBSide, p.kblob + ((size_t)u * 2 + s) * 2 * kplane, 2 * kplane, &ms.bar_k[s]);
+      bulk_g2s(smem + kOffKB + s * kKBSide, p.kblob + (((size_t)u * 2 + s) * NS + rank) * 2 * kplane, 2 * kplane, &ms.bar_k[s]);
     }
   }
+  if constexpr (NS > 1) cluster_arrive();   // the peer must be running before anything is stored into its shared memory
   // query tile: norms (thread <-> pixel) and fp16 hi/lo MN-major A operand
   if (tid < kTP) {
     const int px = p0 + tid;
@@ -248,7 +263,7 @@ __global__ void __launch_bounds__(256, 1) readout_fused_kernel(const ReadoutFuse
         mma_commit(&ms.bar_k[1]);
         ok = mbar_wait(&ms.bar_k[1], 0) && ok;
         mbar_expect_tx(&ms.bar_k[1], 2 * kplane);
-        bulk_g2s(smem + kOffKB, p.kblob + ((size_t)u * 2 + 1) * 2 * kplane, 2 * kplane, &ms.bar_k[1]);
+        bulk_g2s(smem + kOffKB, p.kblob + (((size_t)u * 2 + 1) * NS + rank) * 2 * kplane, 2 * kplane, &ms.bar_k[1]);
         ok = mbar_wait(&ms.bar_k[1], 1) && ok;
       } else {
         ok = mbar_wait(&ms.bar_k[s], 0) && ok;
@@ -275,13 +290,16 @@ __global__ void __launch_bounds__(256, 1) readout_fused_kernel(const ReadoutFuse
   RO_STAMP();   // scores done
 
   // the khat blobs are dead: start streaming nu k-steps into the ring (aliases them)
-  const uint8_t* vsrc = p.vblob + ((size_t)u * 2 + h) * ks2 * kStageBytes;
+  // (k-steps of the blob follow the memory's column order j = s * Lt_total + ...; this CTA's k-step kk is number
+  //  src_step(kk) of it)
+  const uint8_t* vsrc = p.vblob + ((size_t)u * 2 + h) * (ks2 * NS) * kStageBytes;
+  auto src_step = [&](int kk) { return (kk / ks_side) * (ks_side * NS) + rank * ks_side + kk % ks_side; };
   if (tid == 0) {
     fence_proxy_async_smem();
 #pragma unroll
-    for (int kk = 0; kk < kStages && kk < ks2; ++kk) {
+    for (int kk = 0; kk < kRing && kk < ks2; ++kk) {
       mbar_expect_tx(&ms.bar_full[kk], kStageBytes);
-      bulk_g2s(smem + kOffRing + kk * kStageBytes, vsrc + (size_t)kk * kStageBytes, kStageBytes, &ms.bar_full[kk]);
+      bulk_g2s(smem + kOffRing + kk * kStageBytes, vsrc + (size_t)src_step(kk) * kStageBytes, kStageBytes, &ms.bar_full[kk]);
     }
   }
 
@@ -302,7 +320,14 @@ __global__ void __launch_bounds__(256, 1) readout_fused_kernel(const ReadoutFuse
     ms.ex_max[sd][px] = mx;
     __syncthreads();
     RO_STAMP(); // max pass
-    const float gm = fmaxf(ms.ex_max[0][px], ms.ex_max[1][px]);     // inv_nq > 0: max of a*inv = inv * max a
+    float gm = fmaxf(ms.ex_max[0][px], ms.ex_max[1][px]);           // inv_nq > 0: max of a*inv = inv * max a
+    if constexpr (NS > 1) {     // joint max over the column blocks: one float per pixel through the peer's shared memory
+      cluster_wait();           // (start-up barrier: the peer is resident)
+      if (sd == 0) st_cluster_f32(map_to_peer(smem_u32(&ms.peer_max[px]), (uint32_t)(rank ^ 1)), gm);
+      cluster_arrive();
+      cluster_wait();
+      gm = fmaxf(gm, ms.peer_max[px]);
+    }
     const float cw = ms.inv_nq[px] * p.c1s;
     float sum = 0.f;
     for (int q = 0; q < nchunk; ++q) {
@@ -337,7 +362,7 @@ __global__ void __launch_bounds__(256, 1) readout_fused_kernel(const ReadoutFuse
           const int pxr = p0 + (warp & 3) * 32 + row;
           const float4 val = tbuf[row * 8 + (c4 ^ (row & 7))];
           if (pxr < HW)
-            *reinterpret_cast<float4*>(p.escratch + ((size_t)u * HW + pxr) * (2 * Lt) + sd * Lt + q * 32 + c4 * 4) = val;
+            *reinterpret_cast<float4*>(p.escratch + ((size_t)u * HW + pxr) * (2 * p.Lt_total) + sd * p.Lt_total + rank * Lt + q * 32 + c4 * 4) = val;
         }
         __syncwarp();
       }
@@ -349,7 +374,12 @@ __global__ void __launch_bounds__(256, 1) readout_fused_kernel(const ReadoutFuse
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
-    inv_total = 1.f / (ms.ex_sum[0][px] + ms.ex_sum[1][px]);
+    inv_total = ms.ex_sum[0][px] + ms.ex_sum[1][px];               // (NS = 1: inverted right here)
+    if constexpr (NS > 1) {
+      if (sd == 0) st_cluster_f32(map_to_peer(smem_u32(&ms.peer_sum[px]), (uint32_t)(rank ^ 1)), inv_total);
+    } else {
+      inv_total = 1.f / inv_total;
+    }
   }
   RO_STAMP();   // exp pass + E packed
 
@@ -359,12 +389,12 @@ __global__ void __launch_bounds__(256, 1) readout_fused_kernel(const ReadoutFuse
     const uint32_t idesc = make_idesc(128, 128, kFmtF16, kFmtF16, kMajorK, kMajorK);
     // One thread issues everything, so this loop is latency-bound on its own instruction stream: keep it
     // lean (descriptors advanced by constant adds, every index a compile-time constant after unrolling).
-    constexpr int kLag = 3;     // refill the stage consumed kLag steps ago: its MMAs have retired, no issue stall
+    constexpr int kLag = (NS == 1) ? 3 : 2;   // refill the stage consumed kLag steps ago: its MMAs have retired, no issue stall
     const uint64_t bdesc0 = make_sdesc(sbase + kOffRing, /*lbo*/ 4096, /*sbo*/ 128);
 #pragma unroll
     for (int kk = 0; kk < ks2; ++kk) {
-      const int st = kk % kStages;
-      ok = mbar_wait(&ms.bar_full[st], (kk / kStages) & 1) && ok;
+      const int st = kk % kRing;
+      ok = mbar_wait(&ms.bar_full[st], (kk / kRing) & 1) && ok;
       tc_fence_after_sync();
       const uint32_t a_tmem = tmem + (kk / ks_side) * 256 + (kk % ks_side) * 8;
 #pragma unroll
@@ -374,12 +404,12 @@ __global__ void __launch_bounds__(256, 1) readout_fused_kernel(const ReadoutFuse
           mma_f16_ts(tmem + 128 + nh * 256, a_tmem, bdesc0 + ((st * kStageBytes + term * 8192 + nh * 2048) >> 4), idesc,
                      (kk | term) ? 1u : 0u);
       mma_commit(&ms.bar_empty[st]);
-      if (kk >= kLag && kk - kLag + kStages < ks2) {
-        const int prev = kk - kLag, nxt = prev + kStages;
-        const int ps = prev % kStages;
-        ok = mbar_wait(&ms.bar_empty[ps], (prev / kStages) & 1) && ok;
+      if (kk >= kLag && kk - kLag + kRing < ks2) {
+        const int prev = kk - kLag, nxt = prev + kRing;
+        const int ps = prev % kRing;
+        ok = mbar_wait(&ms.bar_empty[ps], (prev / kRing) & 1) && ok;
         mbar_expect_tx(&ms.bar_full[ps], kStageBytes);
-        bulk_g2s(smem + kOffRing + ps * kStageBytes, vsrc + (size_t)nxt * kStageBytes, kStageBytes, &ms.bar_full[ps]);
+        bulk_g2s(smem + kOffRing + ps * kStageBytes, vsrc + (size_t)src_step(nxt) * kStageBytes, kStageBytes, &ms.bar_full[ps]);
       }
     }
     mma_commit(&ms.bar_mma);
@@ -391,8 +421,53 @@ __global__ void __launch_bounds__(256, 1) readout_fused_kernel(const ReadoutFuse
   tc_fence_after_sync();
   RO_STAMP();   // PV done
 
-  // ---- normalise and store: warps 0-3 -> channels [0,128) of this half, warps 4-7 -> [128,256) ---------------
-  {
+  if constexpr (NS > 1) {
+    // ---- column-split cluster: out = (O_0 + O_1) / (sum_0 + sum_1).  CTA `rank` finalises channels [rank * 128, +128) of
+    // this half: the other 128 channels of its partial go to the peer's receive buffer [ch 128][px 128] (the upper
+    // 64 KB of the ring region: dead since the peer's score MMAs, which it waited for before the max exchange).
+    const int nh = warp >> 2;
+    const bool in_range = p0 + px < HW;
+    float* rbuf = reinterpret_cast<float*>(smem + kOffRing + 4 * kStageBytes);
+    if (nh != rank) {
+      const uint32_t dst = map_to_peer(smem_u32(rbuf), (uint32_t)(rank ^ 1)) + px * 4;
+      for (int q = 0; q < 4; ++q) {
+        uint32_t r[32];
+        tmem_ld32(tmem_addr(tmem, lane_base, 128 + nh * 256 + q * 32), r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) st_cluster_f32(dst + (q * 32 + j) * (kTP * 4), __uint_as_float(r[j]));
+      }
+    }
+    cluster_arrive();
+    cluster_wait();
+    // all 8 warps: pixel px, 64 of the 128 channels (warps 0-3 the first 64, warps 4-7 the rest)
+    const float scale = 1.f / (ms.ex_sum[0][px] + ms.ex_sum[1][px] + ms.peer_sum[px]);
+    const int cbase = nh * 64;
+    for (int q = 0; q < 2; ++q) {
+      uint32_t r[32];
+      tmem_ld32(tmem_addr(tmem, lane_base, 128 + rank * 256 + cbase + q * 32), r);
+      tmem_ld_wait();
+      if (in_range) {
+        if (p.pixel_major) {
+          float4* o4 = reinterpret_cast<float4*>(p.out + ((size_t)u * HW + p0 + px) * p.out_channels + p.mem_channel + h * kDH + rank * 128 + cbase + q * 32);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int c = cbase + q * 32 + 4 * j;
+            o4[j] = make_float4((__uint_as_float(r[4 * j]) + rbuf[(c + 0) * kTP + px]) * scale,
+                                (__uint_as_float(r[4 * j + 1]) + rbuf[(c + 1) * kTP + px]) * scale,
+                                (__uint_as_float(r[4 * j + 2]) + rbuf[(c + 2) * kTP + px]) * scale,
+                                (__uint_as_float(r[4 * j + 3]) + rbuf[(c + 3) * kTP + px]) * scale);
+          }
+        } else {
+          float* obase = p.out + ((size_t)u * p.out_channels + p.mem_channel + h * kDH + rank * 128 + cbase + q * 32) * HW + p0 + px;
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            obase[(size_t)j * HW] = (__uint_as_float(r[j]) + rbuf[(cbase + q * 32 + j) * kTP + px]) * scale;
+        }
+      }
+    }
+  } else {
+    // ---- normalise and store: warps 0-3 -> channels [0,128) of this half, warps 4-7 -> [128,256) ---------------
     const int nh = warp >> 2;
     const float scale = inv_total;             // the 2^10 of E cancels against the row sum of the same operand
     const bool in_range = p0 + px < HW;
@@ -435,8 +510,9 @@ __global__ void __launch_bounds__(256, 1) readout_fused_kernel(const ReadoutFuse
 // host side
 // ------------------------------------------------------------------------------------------------------
 bool fused_readout_supported(const SwemDims& d) {
-  return (d.Ck == 64 || d.Ck == 128) && (d.L == 64 || d.L == 128) && d.Cv == ro::kCv && (d.n_banks == 1 || d.n_banks == 2) && d.topl >= 1 &&
-         d.topl <= 64 && d.HW >= 1;
+  const int Lt = d.L * d.n_banks;
+  return (d.Ck == 64 || d.Ck == 128) && (d.L == 64 || d.L == 128 || d.L == 256) && (Lt == 64 || Lt == 128 || Lt == 256 || Lt == 512) &&
+         d.Cv == ro::kCv && (d.n_banks == 1 || d.n_banks == 2) && d.topl >= 1 && d.topl <= 64 && d.HW >= 1;
 }
 
 size_t fused_readout_workspace(const SwemDims& d) {
@@ -467,12 +543,12 @@ int fused_readout_forward(const SwemReadArgs& a, cudaStream_t st) {
     readout_prep_nu_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(a.nu[0], a.nu[nb - 1], U, nb, d.L, vblob);
     SWEM_LAUNCH_CHECK();
   }
-#define SWEM_RO_ATTR(LT_, CK_) \
-  SWEM_CUDA(cudaFuncSetAttribute(readout_fused_kernel<LT_, CK_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ro::smem_bytes<CK_>()))
+#define SWEM_RO_ATTR(LT_, CK_, NS_) \
+  SWEM_CUDA(cudaFuncSetAttribute(readout_fused_kernel<LT_, CK_, NS_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ro::smem_bytes<CK_>()))
   static bool attr_set = false;
   if (!attr_set) {
-    SWEM_RO_ATTR(64, 64); SWEM_RO_ATTR(128, 64); SWEM_RO_ATTR(256, 64);
-    SWEM_RO_ATTR(64, 128); SWEM_RO_ATTR(128, 128); SWEM_RO_ATTR(256, 128);
+    SWEM_RO_ATTR(64, 64, 1); SWEM_RO_ATTR(128, 64, 1); SWEM_RO_ATTR(256, 64, 1); SWEM_RO_ATTR(256, 64, 2);
+    SWEM_RO_ATTR(64, 128, 1); SWEM_RO_ATTR(128, 128, 1); SWEM_RO_ATTR(256, 128, 1); SWEM_RO_ATTR(256, 128, 2);
     attr_set = true;
   }
 #undef SWEM_RO_ATTR
@@ -480,10 +556,28 @@ int fused_readout_forward(const SwemReadArgs& a, cudaStream_t st) {
   p.qk = a.qk; p.kblob = kblob; p.vblob = vblob; p.out = a.out; p.escratch = escr;
   p.N = d.N; p.HW = d.HW; p.T = T; p.n_banks = nb; p.out_channels = a.out_channels; p.mem_channel = a.mem_channel;
   p.pixel_major = a.out_pixel_major;
+  p.Lt_total = Lt;
   p.c1s = kLog2e / (d.tau * ro::kKScale);
   p.prof = get_profile_buffer();
-#define SWEM_RO_LAUNCH(LT_, CK_) readout_fused_kernel<LT_, CK_><<<U * T * 2, 256, ro::smem_bytes<CK_>(), st>>>(p)
-  if (d.Ck == 64) {
+#define SWEM_RO_LAUNCH(LT_, CK_) readout_fused_kernel<LT_, CK_, 1><<<U * T * 2, 256, ro::smem_bytes<CK_>(), st>>>(p)
+  if (Lt == 512) {
+    // 2-CTA clusters (column blocks of 256 per side); CTAs of a cluster only wait for each other, so any number of
+    // clusters may be queued
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(U * T * 2 * 2), 1, 1);
+    cfg.blockDim = dim3(256, 1, 1);
+    cfg.dynamicSmemBytes = d.Ck == 64 ? ro::smem_bytes<64>() : ro::smem_bytes<128>();
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (d.Ck == 64) SWEM_CUDA(cudaLaunchKernelEx(&cfg, readout_fused_kernel<256, 64, 2>, p));
+    else SWEM_CUDA(cudaLaunchKernelEx(&cfg, readout_fused_kernel<256, 128, 2>, p));
+  } else if (d.Ck == 64) {
     if (Lt == 64) SWEM_RO_LAUNCH(64, 64);
     else if (Lt == 128) SWEM_RO_LAUNCH(128, 64);
     else SWEM_RO_LAUNCH(256, 64);

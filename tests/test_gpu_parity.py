@@ -279,11 +279,13 @@ def test_encoder_features_teacher_forced(encoder_features, family):
 
 
 @pytest.mark.parametrize('family', ['generic', 'fused'])
-def test_readout_properties_full_size(family):
+@pytest.mark.parametrize('L', [128, 256])
+def test_readout_properties_full_size(family, L):
     """Size-independent properties at the DAVIS-17 shape: rows of P sum to one (constant values are
-    reproduced), S ranks pair up to one, the readout ignores the scale of the query key."""
+    reproduced), S ranks pair up to one, the readout ignores the scale of the query key.  L = 256: Lt = 512
+    columns per side, the column-split cluster form of the fused kernel."""
     from swem_b200.synthetic import em_inputs
-    B, N, Ck, Cv, L, H, W = 1, 5, 64, 512, 128, 30, 54
+    B, N, Ck, Cv, H, W = 1, 5, 64, 512, 30, 54
     _skip_unless_covered(family, B=B, N=N, Ck=Ck, Cv=Cv, HW=H * W, L=L, what='readout')
     core = _core(dict(L=L, Cv=Cv, n_iters=4, tau=0.05, topl=64), family)
     g = torch.Generator().manual_seed(5)
@@ -643,10 +645,11 @@ def test_decoder_glue_kernels_match_torch():
 
 
 @pytest.mark.parametrize('family', ['generic', 'fused'])
-def test_readout_pixel_major_output_matches_nchw(family):
+@pytest.mark.parametrize('L', [128, 256])
+def test_readout_pixel_major_output_matches_nchw(family, L):
     """SwemReadArgs.out_pixel_major: the same readout written into a channels-last (NHWC) buffer, narrow layout
     [mem_out | S] as FrameEngine uses it; ragged HW (30 x 53)."""
-    B, N, Ck, Cv, L, H, W, topl = 1, 3, 64, 512, 128, 30, 53, 64
+    B, N, Ck, Cv, H, W, topl = 1, 3, 64, 512, 30, 53, 64
     _skip_unless_covered(family, B=B, N=N, Ck=Ck, Cv=Cv, HW=H * W, L=L, topl=topl, what='readout')
     core = _core(dict(L=L, Cv=Cv, n_iters=1, tau=0.05, topl=topl), family)
     g = torch.Generator().manual_seed(2)
