@@ -1,5 +1,6 @@
 """Per-sequence inference loops on tensors -- the host-side mirror of the reference's
-``SWEMEvaluator.evaluate_davis_seq`` / ``evaluate_ytvos_seq`` (methods/SWEM/swem_evaluator.py:59-148).
+``SWEMEvaluator.evaluate_davis_seq`` / ``evaluate_davis_seq_ms`` / ``evaluate_ytvos_seq``
+(methods/SWEM/swem_evaluator.py:34-148).
 
 Dataset loading, PNG dumping and J&F scoring of the reference's ``BasicEvaluator`` are out of
 scope; these loops take frames and first-frame masks as tensors
@@ -55,6 +56,27 @@ def evaluate_davis_seq(model, frames: torch.Tensor, init_masks: List[Optional[to
         if on_frame is not None:
             on_frame(i, pred[:, 0])
     return preds, scores
+
+
+@torch.no_grad()
+def evaluate_davis_seq_ms(model, frames: torch.Tensor, init_masks: List[Optional[torch.Tensor]], out_size,
+                          scales=(480,), is_flip: bool = False):
+    """Multi-scale / horizontal-flip test-time augmentation (``SWEMEvaluator.evaluate_davis_seq_ms``,
+    swem_evaluator.py:34-57): the sequence is re-run at every scale (bicubic resize to (s, s/480*864)) and, with
+    ``is_flip``, once more mirrored; the per-frame scores are averaged (flip pair first, then over scales) and the
+    argmax of the average is returned as a list of T-1 tensors (B,H_o,W_o).  Scale 960 gives HW = 6480 key pixels."""
+    assert len(scales) > 0
+    total = [0 for _ in range(frames.shape[1] - 1)]
+    for scale in scales:
+        h, w = scale, int((scale / 480) * 864)
+        resized = F.interpolate(frames[0], size=(h, w), mode='bicubic', align_corners=False).unsqueeze(0)
+        _, scores = evaluate_davis_seq(model, resized, init_masks, out_size)
+        if is_flip:
+            masks_flip = [torch.flip(m, dims=[-1]) for m in init_masks if m is not None]
+            _, scores_flip = evaluate_davis_seq(model, torch.flip(resized, dims=[-1]), masks_flip, out_size)
+            scores = [(a + torch.flip(b, dims=[-1])) / 2 for a, b in zip(scores, scores_flip)]
+        total = [acc + sc / len(scales) for acc, sc in zip(total, scores)]
+    return [torch.argmax(sc, dim=1, keepdim=False) for sc in total]
 
 
 @torch.no_grad()

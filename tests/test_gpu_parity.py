@@ -700,3 +700,33 @@ def test_pipelined_runner_matches_sequential_runner():
             assert torch.equal(got, want), f'use_graph={use_graph}'
     finally:
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def test_multiscale_flip_evaluation_matches_its_definition():
+    """evaluate_davis_seq_ms (swem_evaluator.py:34-57): one scale without flip is the plain loop; two scales with
+    flip equal the hand-assembled average of four plain runs (flip pair first, then the scales)."""
+    import torch.nn.functional as F
+    from swem_b200 import SWEM, make_config, _lib
+    from swem_b200.evaluator import evaluate_davis_seq, evaluate_davis_seq_ms
+    from swem_b200.synthetic import davis_sequence
+    T, N, h, w = 4, 2, 240, 432
+    torch.manual_seed(0)
+    model = SWEM(make_config(keydim=64, n_bases=128, n_iters=2, topl=64)).eval().to(DEV)
+    model.swem_core.em_path = model.swem_core.readout_path = _lib.PATH_GENERIC      # bit-reproducible family
+    prior = O.random_init(1, N, 64, 128, 512, generator=torch.Generator().manual_seed(4))
+    model.swem_core.random_init = lambda size, norm_dim=-2, dtype=None, device=None: tuple(t.to(device) for t in prior)
+    frames, init = davis_sequence(T, N, seed=1, size=(h, w))
+    frames, masks = frames.to(DEV), [init.to(DEV)] + [None] * (T - 1)
+    base, _ = evaluate_davis_seq(model, F.interpolate(frames[0], size=(480, 864), mode='bicubic', align_corners=False)[None], masks, (h, w))
+    one = evaluate_davis_seq_ms(model, frames, masks, (h, w), scales=(480,), is_flip=False)
+    assert all(torch.equal(a, b) for a, b in zip(base, one))
+    scales = (240, 320)
+    want = [0] * (T - 1)
+    for s in scales:
+        fr = F.interpolate(frames[0], size=(s, int(s / 480 * 864)), mode='bicubic', align_corners=False)[None]
+        _, a = evaluate_davis_seq(model, fr, masks, (h, w))
+        _, b = evaluate_davis_seq(model, torch.flip(fr, dims=[-1]), [torch.flip(init.to(DEV), dims=[-1])], (h, w))
+        want = [acc + (x + torch.flip(y, dims=[-1])) / 2 / len(scales) for acc, x, y in zip(want, a, b)]
+    got = evaluate_davis_seq_ms(model, frames, masks, (h, w), scales=scales, is_flip=True)
+    assert len(got) == T - 1 and got[0].shape == (1, h, w)
+    assert all(torch.equal(g, torch.argmax(wv, dim=1)) for g, wv in zip(got, want))
