@@ -84,8 +84,8 @@ struct Misc {
   float hmax[2][kTP];
   float hsum[2][kTP];
   float hew[2][kTP];
-  float2 mbox[2][2][kTP];   // LB = 1: [iteration parity][side][pixel] = (side max of the logits, side sum of W-step exps)
-  float4 mbox4[LB > 1 ? 2 : 1][LB > 1 ? 2 * LB : 1][LB > 1 ? kTP : 1];   // LB > 1: [parity][cluster rank][pixel] = (max, E-step sum, W-step sum, -)
+  float2 mbox[LB == 1 ? 2 : 1][LB == 1 ? 2 : 1][LB == 1 ? kTP : 1];   // LB = 1: [iteration parity][side][pixel] = (side max of the logits, side sum of W-step exps)
+  float mstat[LB > 1 ? 2 : 1][3][LB > 1 ? 2 * LB : 1][LB > 1 ? kTP : 1];   // LB > 1: [parity][max | E-step sum | W-step sum][cluster rank][pixel]
   uint64_t bar_mma;
   uint64_t bar_full[kStages];
   uint64_t bar_empty[kStages];
@@ -95,7 +95,8 @@ struct Misc {
 template <int CK, int LB>
 constexpr uint32_t smem_bytes() { return Lay<CK>::kOffMisc + sizeof(Misc<LB>) + 128; }
 static_assert(smem_bytes<64, 1>() <= 227 * 1024 && smem_bytes<128, 1>() <= 227 * 1024 && smem_bytes<64, 2>() <= 227 * 1024 &&
-              smem_bytes<128, 2>() <= 227 * 1024, "shared memory budget");
+              smem_bytes<128, 2>() <= 227 * 1024 && smem_bytes<64, 4>() <= 227 * 1024 && smem_bytes<128, 4>() <= 227 * 1024,
+              "shared memory budget");
 
 // TMEM columns
 constexpr uint32_t kColE = 0;      // [128 px][128]     E / W logits of this side
@@ -326,7 +327,7 @@ __global__ void __cluster_dims__(2 * LB, 1, 1) __launch_bounds__(256, 1) em_pair
   const uint32_t idesc_mhi = make_idesc(128, kCk + 16, kFmtF16, kFmtF16, kMajorMN, kMajorK);
   const uint32_t idesc_mlo = make_idesc(128, kCk, kFmtF16, kFmtF16, kMajorMN, kMajorK);
   const uint32_t idesc_nu = make_idesc(128, 256, kFmtF16, kFmtF16, kMajorMN, kMajorK);
-  const uint32_t peer_mbox = map_to_peer(smem_u32(&ms.mbox[0][0][0]), (uint32_t)(rank ^ 1));
+  const uint32_t peer_mbox = map_to_peer(smem_u32(&ms.mbox[0][0][0]), (uint32_t)(rank ^ 1));   // (LB = 1 only)
 
   for (int it = 0; it < I; ++it) {
     fence_proxy_async_smem();
@@ -435,9 +436,14 @@ __global__ void __cluster_dims__(2 * LB, 1, 1) __launch_bounds__(256, 1) em_pair
         __syncthreads();
         {
           const float sc = ms.hsum[0][px] + ms.hsum[1][px], ec = ms.hew[0][px] + ms.hew[1][px];
-          const uint32_t slot = smem_u32(&ms.mbox4[par][rank][px]);
-          for (int rr = hb; rr < CS; rr += 2)             // the two threads of a pixel share the CS destinations
-            st_cluster_f4(map_to_peer(slot, (uint32_t)rr), mx, sc, ec, 0.f);
+          const uint32_t slot = smem_u32(&ms.mstat[par][0][rank][px]);
+          constexpr uint32_t kPlane = CS * kTP * sizeof(float);
+          for (int rr = hb; rr < CS; rr += 2) {           // the two threads of a pixel share the CS destinations
+            const uint32_t dst = map_to_peer(slot, (uint32_t)rr);
+            st_cluster_f32(dst, mx);
+            st_cluster_f32(dst + kPlane, sc);
+            st_cluster_f32(dst + 2 * kPlane, ec);
+          }
         }
         cluster_arrive();
         cluster_wait();
@@ -445,16 +451,16 @@ __global__ void __cluster_dims__(2 * LB, 1, 1) __launch_bounds__(256, 1) em_pair
         float Ms = -3.0e38f, gm = -3.0e38f;
 #pragma unroll
         for (int rr = 0; rr < CS; ++rr) {
-          const float m = ms.mbox4[par][rr][px].x;
+          const float m = ms.mstat[par][0][rr][px];
           gm = fmaxf(gm, m);
           if ((rr & 1) == sd) Ms = fmaxf(Ms, m);
         }
         float S = 0.f, e0 = 0.f, e1 = 0.f;
 #pragma unroll
         for (int rr = 0; rr < CS; ++rr) {
-          const float4 t = ms.mbox4[par][rr][px];
-          if ((rr & 1) == sd) S += t.y * fast_exp2((t.x - Ms) * p.c1s);
-          const float ew = t.z * fast_exp2((t.x - gm) * cw);
+          const float tm = ms.mstat[par][0][rr][px];
+          if ((rr & 1) == sd) S += ms.mstat[par][1][rr][px] * fast_exp2((tm - Ms) * p.c1s);
+          const float ew = ms.mstat[par][2][rr][px] * fast_exp2((tm - gm) * cw);
           if (rr & 1) e1 += ew; else e0 += ew;
         }
         if (do_w) w *= 1.f - (sd ? e1 : e0) / (e0 + e1);
@@ -739,11 +745,24 @@ static int max_clusters_resident() {
   return n;
 }
 
+template <int CK>
+static int clusters_resident(int LB) {
+  return LB == 4 ? max_clusters_resident<CK, 4>() : LB == 2 ? max_clusters_resident<CK, 2>() : max_clusters_resident<CK, 1>();
+}
+
 bool fused_em_supported(const SwemDims& d) {
-  if ((d.Ck != 64 && d.Ck != 128) || (d.L != 64 && d.L != 128 && d.L != 256) || d.Cv != em::kCv || d.n_iters < 1 || d.n_iters > 16)
+  if ((d.Ck != 64 && d.Ck != 128) || (d.L != 64 && d.L != 128 && d.L != 256 && d.L != 512) || d.Cv != em::kCv || d.n_iters < 1 ||
+      d.n_iters > 16)
     return false;
   const int T = (d.HW + em::kTP - 1) / em::kTP;
-  return T >= 1 && T <= (d.L == 256 ? 28 : 64);   // all clusters of one unit must be co-resident (74 pairs / ~32 quads on a B200)
+  const int LB = d.L > 128 ? d.L / 128 : 1;
+  // all clusters of one unit must be co-resident: 74 pairs / ~34 quads / ~16 octets on a B200.  With a device present
+  // the occupancy query decides (it is what the launch checks); without one (host-only tests) these figures do.
+  int limit = LB == 4 ? 14 : LB == 2 ? 28 : 64;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) == cudaSuccess && ndev > 0) limit = d.Ck == 128 ? clusters_resident<128>(LB) : clusters_resident<64>(LB);
+  else cudaGetLastError();
+  return T >= 1 && T <= limit;
 }
 
 size_t fused_em_workspace(const SwemDims& d) {
@@ -805,6 +824,7 @@ static int fused_em_forward_t(const SwemEmArgs& a, cudaStream_t st) {
 }
 
 int fused_em_forward(const SwemEmArgs& a, cudaStream_t st) {
+  if (a.dims.L == 512) return a.dims.Ck == 128 ? fused_em_forward_t<128, 4>(a, st) : fused_em_forward_t<64, 4>(a, st);
   if (a.dims.L == 256) return a.dims.Ck == 128 ? fused_em_forward_t<128, 2>(a, st) : fused_em_forward_t<64, 2>(a, st);
   return a.dims.Ck == 128 ? fused_em_forward_t<128, 1>(a, st) : fused_em_forward_t<64, 1>(a, st);
 }

@@ -1,8 +1,8 @@
 // Fused readout (attention from query pixels to the memory bases) for sm_100a: tcgen05 + TMEM + TMA.
 //
-// Covers Ck = 64 / 128, Cv = 512, Lt = banks x L columns per side in {64, 128, 256, 512}, any HW / B*N.  Lt = 512
-// (L = 256 with both banks) runs as 2-CTA clusters: each CTA takes 256 columns of either side, the pair exchanges
-// the row max / row sum and the halves of the un-normalised output over distributed shared memory.  Reference semantics:
+// Covers Ck = 64 / 128, Cv = 512, Lt = banks x L columns per side in {64, 128, 256, 512, 1024}, any HW / B*N.  Lt = 512 /
+// 1024 (L = 256 / 512 with both banks) run as 2- / 4-CTA clusters: each CTA takes 256 columns of either side, the cluster
+// exchanges the row max / row sum and the un-normalised output chunks over distributed shared memory.  Reference semantics:
 // methods/SWEM/modules.py:278-293 (matching), :232-276 (get_affinity), :198-208 (perm_inv_feat).
 //
 // Two launches + the shared top-l kernel:
@@ -59,8 +59,8 @@ struct Misc {
   float inv_nq[kTP];
   float ex_max[2][kTP];
   float ex_sum[2][kTP];
-  float peer_max[kTP];      // (column-split clusters) row max / row sum of the peer CTA's columns, written by the peer
-  float peer_sum[kTP];
+  float peer_max[3][kTP];   // (column-split clusters) row max / row sum of the peer CTAs' columns, written by the peers
+  float peer_sum[3][kTP];
   uint64_t bar_k[2];
   uint64_t bar_mma;
   uint64_t bar_full[kStages];
@@ -160,9 +160,9 @@ __global__ void readout_prep_nu_kernel(const float* __restrict__ n0, const float
 
 // ---- main kernel --------------------------------------------------------------------------------------
 // LT = columns per side handled by one CTA (64, 128 or 256), CK = key channels (64 or 128): they fix every loop count, so
-// the MMA issue loops unroll.  NS = column blocks = CTAs per cluster (1; 2 when banks x L = 512, launched with a cluster
-// attribute): CTA `rank` takes columns [rank * LT, +LT) of either side and finalises value channels [rank * 128, +128)
-// of its half.
+// the MMA issue loops unroll.  NS = column blocks = CTAs per cluster (1; 2 / 4 when banks x L = 512 / 1024, launched with a
+// cluster attribute): CTA `rank` takes columns [rank * LT, +LT) of either side and finalises value channels
+// [rank * 256 / NS, +256 / NS) of its half.
 template <int LT, int CK, int NS>
 __global__ void __launch_bounds__(256, 1) readout_fused_kernel(const ReadoutFusedParams p) {
   using namespace ro;
@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(256, 1) readout_fused_kernel(const ReadoutFuse
   const int h = bid & 1;
   const int tile = (bid >> 1) % p.T;
   const int u = (bid >> 1) / p.T;
-  constexpr int kRing = (NS == 1) ? kStages : 4;   // NS = 2: the other 64 KB of the ring region receive the peer's partial
+  constexpr int kRing = kStages / NS;              // NS > 1: the rest of the 128 KB ring region receives the peers' partials (64 / 96 KB)
   const int b = u / p.N;
   const int p0 = tile * kTP;
   const int HW = p.HW;
@@ -323,10 +323,12 @@ __global__ void __launch_bounds__(256, 1) readout_fused_kernel(const ReadoutFuse
     float gm = fmaxf(ms.ex_max[0][px], ms.ex_max[1][px]);           // inv_nq > 0: max of a*inv = inv * max a
     if constexpr (NS > 1) {     // joint max over the column blocks: one float per pixel through the peer's shared memory
       cluster_wait();           // (start-up barrier: the peer is resident)
-      if (sd == 0) st_cluster_f32(map_to_peer(smem_u32(&ms.peer_max[px]), (uint32_t)(rank ^ 1)), gm);
+      for (int k = sd; k < NS - 1; k += 2)   // peer rank + 1 + k receives into its slot k (the two threads of a pixel share the peers)
+        st_cluster_f32(map_to_peer(smem_u32(&ms.peer_max[k][px]), (uint32_t)((rank + 1 + k) % NS)), gm);
       cluster_arrive();
       cluster_wait();
-      gm = fmaxf(gm, ms.peer_max[px]);
+#pragma unroll
+      for (int k = 0; k < NS - 1; ++k) gm = fmaxf(gm, ms.peer_max[k][px]);
     }
     const float cw = ms.inv_nq[px] * p.c1s;
     float sum = 0.f;
@@ -376,7 +378,8 @@ __global__ void __launch_bounds__(256, 1) readout_fused_kernel(const ReadoutFuse
     tc_fence_after_sync();
     inv_total = ms.ex_sum[0][px] + ms.ex_sum[1][px];               // (NS = 1: inverted right here)
     if constexpr (NS > 1) {
-      if (sd == 0) st_cluster_f32(map_to_peer(smem_u32(&ms.peer_sum[px]), (uint32_t)(rank ^ 1)), inv_total);
+      for (int k = sd; k < NS - 1; k += 2)
+        st_cluster_f32(map_to_peer(smem_u32(&ms.peer_sum[k][px]), (uint32_t)((rank + 1 + k) % NS)), inv_total);
     } else {
       inv_total = 1.f / inv_total;
     }
@@ -389,7 +392,7 @@ __global__ void __launch_bounds__(256, 1) readout_fused_kernel(const ReadoutFuse
     const uint32_t idesc = make_idesc(128, 128, kFmtF16, kFmtF16, kMajorK, kMajorK);
     // One thread issues everything, so this loop is latency-bound on its own instruction stream: keep it
     // lean (descriptors advanced by constant adds, every index a compile-time constant after unrolling).
-    constexpr int kLag = (NS == 1) ? 3 : 2;   // refill the stage consumed kLag steps ago: its MMAs have retired, no issue stall
+    constexpr int kLag = (NS == 1) ? 3 : (NS == 2) ? 2 : 1;   // refill the stage consumed kLag steps ago: its MMAs have retired, no issue stall
     const uint64_t bdesc0 = make_sdesc(sbase + kOffRing, /*lbo*/ 4096, /*sbo*/ 128);
 #pragma unroll
     for (int kk = 0; kk < ks2; ++kk) {
@@ -422,47 +425,63 @@ __global__ void __launch_bounds__(256, 1) readout_fused_kernel(const ReadoutFuse
   RO_STAMP();   // PV done
 
   if constexpr (NS > 1) {
-    // ---- column-split cluster: out = (O_0 + O_1) / (sum_0 + sum_1).  CTA `rank` finalises channels [rank * 128, +128) of
-    // this half: the other 128 channels of its partial go to the peer's receive buffer [ch 128][px 128] (the upper
-    // 64 KB of the ring region: dead since the peer's score MMAs, which it waited for before the max exchange).
+    // ---- column-split cluster: out = sum_r O_r / sum_r rowsum_r.  CTA `rank` finalises kChunk = 256 / NS value channels of
+    // this half, [rank * kChunk, +kChunk); the other chunks of its partial go to their owners' receive buffers
+    // [sender slot][ch][px 128] (the upper part of the ring region: dead since the owner's score MMAs, which it waited for
+    // before the max exchange).
+    constexpr int kChunk = kDH / NS;
     const int nh = warp >> 2;
     const bool in_range = p0 + px < HW;
-    float* rbuf = reinterpret_cast<float*>(smem + kOffRing + 4 * kStageBytes);
-    if (nh != rank) {
-      const uint32_t dst = map_to_peer(smem_u32(rbuf), (uint32_t)(rank ^ 1)) + px * 4;
-      for (int q = 0; q < 4; ++q) {
-        uint32_t r[32];
-        tmem_ld32(tmem_addr(tmem, lane_base, 128 + nh * 256 + q * 32), r);
-        tmem_ld_wait();
+    float* rbuf = reinterpret_cast<float*>(smem + kOffRing + kRing * kStageBytes);
+    const uint32_t rbuf_u32 = smem_u32(rbuf);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) st_cluster_f32(dst + (q * 32 + j) * (kTP * 4), __uint_as_float(r[j]));
+    for (int cc = 0; cc < NS / 2; ++cc) {
+      const int c = nh * (NS / 2) + cc;                      // chunk held by this thread in TMEM columns 128 + nh * 256 + cc * kChunk
+      if (c != rank) {
+        const int slot = ((rank - c + NS) % NS) - 1;
+        const uint32_t dst = map_to_peer(rbuf_u32, (uint32_t)c) + (uint32_t)((slot * kChunk * kTP + px) * 4);
+#pragma unroll
+        for (int q = 0; q < kChunk / 32; ++q) {
+          uint32_t r[32];
+          tmem_ld32(tmem_addr(tmem, lane_base, 128 + nh * 256 + cc * kChunk + q * 32), r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) st_cluster_f32(dst + (q * 32 + j) * (kTP * 4), __uint_as_float(r[j]));
+        }
       }
     }
     cluster_arrive();
     cluster_wait();
-    // all 8 warps: pixel px, 64 of the 128 channels (warps 0-3 the first 64, warps 4-7 the rest)
-    const float scale = 1.f / (ms.ex_sum[0][px] + ms.ex_sum[1][px] + ms.peer_sum[px]);
-    const int cbase = nh * 64;
-    for (int q = 0; q < 2; ++q) {
+    // all 8 warps: pixel px, half of the chunk's channels (warps 0-3 the first half, warps 4-7 the rest)
+    float total = ms.ex_sum[0][px] + ms.ex_sum[1][px];
+#pragma unroll
+    for (int k = 0; k < NS - 1; ++k) total += ms.peer_sum[k][px];
+    const float scale = 1.f / total;
+    const int cbase = nh * (kChunk / 2);                     // first channel (inside the chunk) of this thread
+    const uint32_t tcol = 128 + ((rank * kChunk) / 128) * 256 + (rank * kChunk) % 128 + cbase;
+#pragma unroll
+    for (int q = 0; q < kChunk / 64; ++q) {
       uint32_t r[32];
-      tmem_ld32(tmem_addr(tmem, lane_base, 128 + rank * 256 + cbase + q * 32), r);
+      tmem_ld32(tmem_addr(tmem, lane_base, tcol + q * 32), r);
       tmem_ld_wait();
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        float acc = __uint_as_float(r[j]);
+#pragma unroll
+        for (int k = 0; k < NS - 1; ++k) acc += rbuf[(k * kChunk + cbase + q * 32 + j) * kTP + px];
+        v[j] = acc * scale;
+      }
       if (in_range) {
+        const int ch0 = p.mem_channel + h * kDH + rank * kChunk + cbase + q * 32;
         if (p.pixel_major) {
-          float4* o4 = reinterpret_cast<float4*>(p.out + ((size_t)u * HW + p0 + px) * p.out_channels + p.mem_channel + h * kDH + rank * 128 + cbase + q * 32);
+          float4* o4 = reinterpret_cast<float4*>(p.out + ((size_t)u * HW + p0 + px) * p.out_channels + ch0);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int c = cbase + q * 32 + 4 * j;
-            o4[j] = make_float4((__uint_as_float(r[4 * j]) + rbuf[(c + 0) * kTP + px]) * scale,
-                                (__uint_as_float(r[4 * j + 1]) + rbuf[(c + 1) * kTP + px]) * scale,
-                                (__uint_as_float(r[4 * j + 2]) + rbuf[(c + 2) * kTP + px]) * scale,
-                                (__uint_as_float(r[4 * j + 3]) + rbuf[(c + 3) * kTP + px]) * scale);
-          }
+          for (int j = 0; j < 8; ++j) o4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         } else {
-          float* obase = p.out + ((size_t)u * p.out_channels + p.mem_channel + h * kDH + rank * 128 + cbase + q * 32) * HW + p0 + px;
+          float* obase = p.out + ((size_t)u * p.out_channels + ch0) * HW + p0 + px;
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            obase[(size_t)j * HW] = (__uint_as_float(r[j]) + rbuf[(cbase + q * 32 + j) * kTP + px]) * scale;
+          for (int j = 0; j < 32; ++j) obase[(size_t)j * HW] = v[j];
         }
       }
     }
@@ -511,7 +530,8 @@ __global__ void __launch_bounds__(256, 1) readout_fused_kernel(const ReadoutFuse
 // ------------------------------------------------------------------------------------------------------
 bool fused_readout_supported(const SwemDims& d) {
   const int Lt = d.L * d.n_banks;
-  return (d.Ck == 64 || d.Ck == 128) && (d.L == 64 || d.L == 128 || d.L == 256) && (Lt == 64 || Lt == 128 || Lt == 256 || Lt == 512) &&
+  return (d.Ck == 64 || d.Ck == 128) && (d.L == 64 || d.L == 128 || d.L == 256 || d.L == 512) &&
+         (Lt == 64 || Lt == 128 || Lt == 256 || Lt == 512 || Lt == 1024) &&
          d.Cv == ro::kCv && (d.n_banks == 1 || d.n_banks == 2) && d.topl >= 1 && d.topl <= 64 && d.HW >= 1;
 }
 
@@ -547,8 +567,8 @@ int fused_readout_forward(const SwemReadArgs& a, cudaStream_t st) {
   SWEM_CUDA(cudaFuncSetAttribute(readout_fused_kernel<LT_, CK_, NS_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ro::smem_bytes<CK_>()))
   static bool attr_set = false;
   if (!attr_set) {
-    SWEM_RO_ATTR(64, 64, 1); SWEM_RO_ATTR(128, 64, 1); SWEM_RO_ATTR(256, 64, 1); SWEM_RO_ATTR(256, 64, 2);
-    SWEM_RO_ATTR(64, 128, 1); SWEM_RO_ATTR(128, 128, 1); SWEM_RO_ATTR(256, 128, 1); SWEM_RO_ATTR(256, 128, 2);
+    SWEM_RO_ATTR(64, 64, 1); SWEM_RO_ATTR(128, 64, 1); SWEM_RO_ATTR(256, 64, 1); SWEM_RO_ATTR(256, 64, 2); SWEM_RO_ATTR(256, 64, 4);
+    SWEM_RO_ATTR(64, 128, 1); SWEM_RO_ATTR(128, 128, 1); SWEM_RO_ATTR(256, 128, 1); SWEM_RO_ATTR(256, 128, 2); SWEM_RO_ATTR(256, 128, 4);
     attr_set = true;
   }
 #undef SWEM_RO_ATTR
@@ -560,23 +580,26 @@ int fused_readout_forward(const SwemReadArgs& a, cudaStream_t st) {
   p.c1s = kLog2e / (d.tau * ro::kKScale);
   p.prof = get_profile_buffer();
 #define SWEM_RO_LAUNCH(LT_, CK_) readout_fused_kernel<LT_, CK_, 1><<<U * T * 2, 256, ro::smem_bytes<CK_>(), st>>>(p)
-  if (Lt == 512) {
-    // 2-CTA clusters (column blocks of 256 per side); CTAs of a cluster only wait for each other, so any number of
+  if (Lt >= 512) {
+    // 2- / 4-CTA clusters (column blocks of 256 per side); CTAs of a cluster only wait for each other, so any number of
     // clusters may be queued
+    const unsigned ns = (unsigned)(Lt / 256);
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(U * T * 2 * 2), 1, 1);
+    cfg.gridDim = dim3((unsigned)(U * T * 2) * ns, 1, 1);
     cfg.blockDim = dim3(256, 1, 1);
     cfg.dynamicSmemBytes = d.Ck == 64 ? ro::smem_bytes<64>() : ro::smem_bytes<128>();
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.x = ns;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    if (d.Ck == 64) SWEM_CUDA(cudaLaunchKernelEx(&cfg, readout_fused_kernel<256, 64, 2>, p));
-    else SWEM_CUDA(cudaLaunchKernelEx(&cfg, readout_fused_kernel<256, 128, 2>, p));
+    if (d.Ck == 64 && ns == 2) SWEM_CUDA(cudaLaunchKernelEx(&cfg, readout_fused_kernel<256, 64, 2>, p));
+    else if (d.Ck == 64) SWEM_CUDA(cudaLaunchKernelEx(&cfg, readout_fused_kernel<256, 64, 4>, p));
+    else if (ns == 2) SWEM_CUDA(cudaLaunchKernelEx(&cfg, readout_fused_kernel<256, 128, 2>, p));
+    else SWEM_CUDA(cudaLaunchKernelEx(&cfg, readout_fused_kernel<256, 128, 4>, p));
   } else if (d.Ck == 64) {
     if (Lt == 64) SWEM_RO_LAUNCH(64, 64);
     else if (Lt == 128) SWEM_RO_LAUNCH(128, 64);

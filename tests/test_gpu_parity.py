@@ -172,6 +172,7 @@ SHAPES = [
     (1, 6, 64, 512, 256, 30, 54, 4),
     (1, 2, 128, 512, 256, 17, 29, 1),
     (1, 1, 64, 512, 512, 12, 20, 4),
+    (1, 2, 64, 512, 512, 30, 54, 2),                      # 8-CTA EM clusters, 4-CTA readout clusters at full tile count
     (1, 3, 128, 512, 128, 30, 54, 4),                     # the reference's CLI defaults (--key_dim 128 --num_bases 128)
     (2, 2, 128, 512, 128, 24, 23, 1),
 ]
@@ -279,7 +280,7 @@ def test_encoder_features_teacher_forced(encoder_features, family):
 
 
 @pytest.mark.parametrize('family', ['generic', 'fused'])
-@pytest.mark.parametrize('L', [128, 256])
+@pytest.mark.parametrize('L', [128, 256, 512])
 def test_readout_properties_full_size(family, L):
     """Size-independent properties at the DAVIS-17 shape: rows of P sum to one (constant values are
     reproduced), S ranks pair up to one, the readout ignores the scale of the query key.  L = 256: Lt = 512
@@ -645,7 +646,7 @@ def test_decoder_glue_kernels_match_torch():
 
 
 @pytest.mark.parametrize('family', ['generic', 'fused'])
-@pytest.mark.parametrize('L', [128, 256])
+@pytest.mark.parametrize('L', [128, 256, 512])
 def test_readout_pixel_major_output_matches_nchw(family, L):
     """SwemReadArgs.out_pixel_major: the same readout written into a channels-last (NHWC) buffer, narrow layout
     [mem_out | S] as FrameEngine uses it; ragged HW (30 x 53)."""
