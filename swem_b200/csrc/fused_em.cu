@@ -1,8 +1,10 @@
 // Fused sequential-weighted-EM kernel for sm_100a (tcgen05 + TMEM + bulk-async copies), one launch per memorize call:
 // one CTA per (unit u = (b,n), pixel tile of 128 px, side s), the two sides of a tile forming a 2-CTA cluster.
 //
-// Covers Ck = 64 (BASELINE) or 128 (the reference's CLI default), L = 128 or 64 bases per side (64: half of the rows /
-// columns are zero padding), Cv = 512, any HW up to 128 x 64 pixels, any B*N.  Reference semantics: methods/SWEM/modules.py:129-168 (swem), :112-120 (E), :122-127 (M), :93-110 (W),
+// Covers Ck = 64 (BASELINE) or 128 (the reference's CLI default), L = 64 / 128 bases per side (64: half of the rows /
+// columns are zero padding) and L = 256 / 512 (a side's bases spread over LB = L / 128 CTAs: clusters of 2 * LB CTAs
+// that exchange their softmax statistics, see the epilogue), Cv = 512, any B*N, any HW whose clusters are co-resident
+// (128 x 64 / ~34 / ~16 pixels for L <= 128 / 256 / 512 on a B200).  Reference semantics: methods/SWEM/modules.py:129-168 (swem), :112-120 (E), :122-127 (M), :93-110 (W),
 // :164-165 (nu).  Arithmetic: operands fp16 with x, the unit bases, the responsibilities and v split into hi + lo
 // halves (3 MMAs per product: hi*hi + hi*lo + lo*hi ~ fp32-accurate), fp32 accumulation in TMEM, fp32 softmax /
 // normalisation.  The W-step logits l2norm(x).khat equal the E-step logits x.khat / (||x_p|| + eps) -- same khat --
@@ -122,6 +124,9 @@ struct EmPairParams {
   int* status;
   long long* prof;
   int N, HW, T, n_iters, u0;
+  int windowed;          // 0: the whole EM in one co-resident launch (cross-tile waits on the arrival counters);
+  int it_begin;          // 1: one launch per iteration -- this launch finalises iteration it_begin - 1 from its completed
+                         //    accumulators, then runs iteration it_begin up to the reduce-adds (it_begin = n_iters: outputs only)
   int L;                 // bases per side in global memory (64 or 128); a CTA always works on 128 rows, the rest are zero
   float c1s;             // log2(e) / (tau * kKScale)
 };
@@ -221,6 +226,9 @@ __global__ void __cluster_dims__(2 * LB, 1, 1) __launch_bounds__(256, 1) em_pair
     else convert_v_chunk<4>(src, vimg + (size_t)c * kStageBytes, p0 + (c & 3) * 32, HW, warp - 4, lane);
   };
   int chunks_done = (I - 1 >= kMine - 1) ? 1 : kMine - (I - 1);   // what cannot be hidden behind iterations 0 .. I-2 is done here
+  const bool windowed = p.windowed != 0;
+  const bool fin_only = windowed && p.it_begin >= I;              // windowed: outputs-only launch
+  if (windowed) chunks_done = (p.it_begin == I - 1) ? kMine : 0;  // the launch of the last iteration converts its images
   for (int j = 0; j < chunks_done; ++j) convert_mine(j, true);
   __threadfence();
   asm volatile("fence.proxy.async;" ::: "memory");     // generic-proxy global stores -> visible to the bulk-copy (async proxy) reads
@@ -253,9 +261,28 @@ __global__ void __cluster_dims__(2 * LB, 1, 1) __launch_bounds__(256, 1) em_pair
   if (row_thread) {
 #pragma unroll
     for (int c = 0; c < kCk; ++c) kap0[c] = valid_row ? __ldg(kprior + (size_t)c * L) : 0.f;
+    if (windowed && p.it_begin > 0) {
+      // kappa of iteration it_begin - 1 from the prior and the totals the previous launch left in acc_k (reference :125-126)
+      constexpr float kInvZ = 1.f / kZScale;
+      const float* accp = p.acc_k + ((size_t)((u * I + p.it_begin - 1) * 2 + sd) * LB + lb) * ((kCk + 1) * kL);
+      const float zita_cur = zita_p + __ldcg(accp + kCk * kL + tid) * kInvZ;
+      const float rz = valid_row ? 1.f / zita_cur : 0.f;
+#pragma unroll
+      for (int c = 0; c < kCk; ++c) kap0[c] = (zita_p * kap0[c] + __ldcg(accp + c * kL + tid) * kInvZ) * rz;
+      if (fin_only) {
+        ms.hsum[0][tid] = rz;         // for the nu slice
+        ms.hsum[1][tid] = zita_p;
+        if (tile == 0 && valid_row) {
+          p.zita[(size_t)gs * L + lrow] = zita_cur;
+          float* kout = p.kappa + ((size_t)gs * kCk) * L + lrow;
+#pragma unroll
+          for (int c = 0; c < kCk; ++c) kout[(size_t)c * L] = kap0[c];
+        }
+      }
+    }
   }
   // pixel norms + this side's mask (threads 128..255 <-> pixel, so they overlap with the prior loads of the row threads)
-  if (!row_thread) {
+  if (!row_thread && !fin_only) {
     const int q = tid - kL, px = p0 + q;
     float ss = 0.f;
     if (px < HW) {
@@ -271,7 +298,7 @@ __global__ void __cluster_dims__(2 * LB, 1, 1) __launch_bounds__(256, 1) em_pair
   }
   // X tile -> fp16 hi/lo chunks.  thread -> (channel c = tid/4 (+64), 4 pixel groups of 8)
 #pragma unroll
-  for (int cc = 0; cc < kCk / 64; ++cc) {
+  for (int cc = 0; cc < (fin_only ? 0 : kCk / 64); ++cc) {
     const int c = cc * 64 + (tid >> 2);
     const float* xrow = p.x + ((size_t)b * kCk + c) * HW;
 #pragma unroll
@@ -317,7 +344,7 @@ __global__ void __cluster_dims__(2 * LB, 1, 1) __launch_bounds__(256, 1) em_pair
     asm volatile("fence.proxy.async;" ::: "memory");
     for (int k = 0; k < LY::kOwnStages; ++k) load_image(k);
   };
-  if (LB == 1 && I == 1 && tid == 0) prefetch_images();   // (LB > 1: every iteration has a cluster barrier, see the epilogue)
+  if (LB == 1 && I == 1 && tid == 0 && !fin_only) prefetch_images();   // (LB > 1: every iteration has a cluster barrier, see the epilogue)
   const uint32_t tmem = ms.tmem_base;
   uint32_t ph_mma = 0;
   bool failed = false;
@@ -329,7 +356,32 @@ __global__ void __cluster_dims__(2 * LB, 1, 1) __launch_bounds__(256, 1) em_pair
   const uint32_t idesc_nu = make_idesc(128, 256, kFmtF16, kFmtF16, kMajorMN, kMajorK);
   const uint32_t peer_mbox = map_to_peer(smem_u32(&ms.mbox[0][0][0]), (uint32_t)(rank ^ 1));   // (LB = 1 only)
 
-  for (int it = 0; it < I; ++it) {
+  auto nu_slice = [&]() {
+    // ---- nu = (zita_ nu_ + sum / 2^14) / zita (reference :164-165) for this tile's slice of value channels: the counter
+    // wait above ordered every tile's nu reduce-adds (completed before its arrival) before these loads.
+    const int dper = (kCv + p.T - 1) / p.T;
+    const int d0 = tile * dper, d1 = min(kCv, d0 + dper);
+    constexpr float kInvZ = 1.f / kZScale;
+    const float4* acc4 = reinterpret_cast<const float4*>(p.acc_nu + (size_t)gsl * kCv * kL);    // [d][128] of this basis block
+    const float4* pri4 = reinterpret_cast<const float4*>(p.nu_prior + (size_t)gs * kCv * L);    // [d][L]
+    float4* out4 = reinterpret_cast<float4*>(p.nu + (size_t)gs * kCv * L);
+    const int l4n = (L < kL ? L : kL) / 4;              // float4 columns of this block that exist
+    for (int k = d0 * l4n + tid; k < d1 * l4n; k += 256) {
+      const int d = k / l4n, l4 = k % l4n, l = l4 * 4;
+      const int i = d * (L / 4) + lb * (kL / 4) + l4;   // position in the [d][L] tensors
+      const float4 a = __ldcg(acc4 + d * (kL / 4) + l4);
+      const float4 pr = __ldg(pri4 + i);
+      float4 o;
+      o.x = (ms.hsum[1][l + 0] * pr.x + a.x * kInvZ) * ms.hsum[0][l + 0];
+      o.y = (ms.hsum[1][l + 1] * pr.y + a.y * kInvZ) * ms.hsum[0][l + 1];
+      o.z = (ms.hsum[1][l + 2] * pr.z + a.z * kInvZ) * ms.hsum[0][l + 2];
+      o.w = (ms.hsum[1][l + 3] * pr.w + a.w * kInvZ) * ms.hsum[0][l + 3];
+      out4[i] = o;
+    }
+    EM_STAMP();                    // nu slice written
+  };
+  const int it_first = windowed ? p.it_begin : 0, it_stop = windowed ? (fin_only ? I : p.it_begin + 1) : I;
+  for (int it = it_first; it < it_stop; ++it) {
     fence_proxy_async_smem();
     tc_fence_before_sync();
     __syncthreads();
@@ -619,7 +671,9 @@ __global__ void __cluster_dims__(2 * LB, 1, 1) __launch_bounds__(256, 1) em_pair
     // ---- (4) cross-tile reduction of the M-step partial: fence the reductions issued above, arrive; after the last tile
     // arrived every CTA reads the total back the same way it was accumulated.
     unsigned* counter = p.counters + (((size_t)u * I + it) * 2 + sd) * LB + lb;
-    if (row_thread) {                 // warps 0-3; they synchronise among themselves on named barrier 1
+    if (windowed) {
+      // the kernel boundary is the cross-tile barrier: the next launch finalises this iteration from acc_k / acc_nu
+    } else if (row_thread) {          // warps 0-3; they synchronise among themselves on named barrier 1
       __threadfence();                // (the prior-row loads come after it: a fence waits for every earlier access)
       asm volatile("bar.sync 1, 128;" ::: "memory");
       if (tid == 0) {
@@ -661,7 +715,7 @@ __global__ void __cluster_dims__(2 * LB, 1, 1) __launch_bounds__(256, 1) em_pair
           stage_khat(kap);
         }
       }
-    } else if (chunks_done < kMine && !last) {
+    } else if (chunks_done < kMine && !last) {   // (never in windowed mode: chunks_done is 0 or kMine there, see set-up)
       // warps 4-7: one more V chunk, hidden behind the row threads' reduction, cross-tile wait and finalize
       convert_mine(chunks_done, false);
       __threadfence();
@@ -675,32 +729,10 @@ __global__ void __cluster_dims__(2 * LB, 1, 1) __launch_bounds__(256, 1) em_pair
       break;
     }
     EM_STAMP();                      // finalize done
-    if (last) {
-      // ---- nu = (zita_ nu_ + sum / 2^14) / zita (reference :164-165) for this tile's slice of value channels: the counter
-      // wait above ordered every tile's nu reduce-adds (completed before its arrival) before these loads.
-      const int dper = (kCv + p.T - 1) / p.T;
-      const int d0 = tile * dper, d1 = min(kCv, d0 + dper);
-      constexpr float kInvZ = 1.f / kZScale;
-      const float4* acc4 = reinterpret_cast<const float4*>(p.acc_nu + (size_t)gsl * kCv * kL);    // [d][128] of this basis block
-      const float4* pri4 = reinterpret_cast<const float4*>(p.nu_prior + (size_t)gs * kCv * L);    // [d][L]
-      float4* out4 = reinterpret_cast<float4*>(p.nu + (size_t)gs * kCv * L);
-      const int l4n = (L < kL ? L : kL) / 4;              // float4 columns of this block that exist
-      for (int k = d0 * l4n + tid; k < d1 * l4n; k += 256) {
-        const int d = k / l4n, l4 = k % l4n, l = l4 * 4;
-        const int i = d * (L / 4) + lb * (kL / 4) + l4;   // position in the [d][L] tensors
-        const float4 a = __ldcg(acc4 + d * (kL / 4) + l4);
-        const float4 pr = __ldg(pri4 + i);
-        float4 o;
-        o.x = (ms.hsum[1][l + 0] * pr.x + a.x * kInvZ) * ms.hsum[0][l + 0];
-        o.y = (ms.hsum[1][l + 1] * pr.y + a.y * kInvZ) * ms.hsum[0][l + 1];
-        o.z = (ms.hsum[1][l + 2] * pr.z + a.z * kInvZ) * ms.hsum[0][l + 2];
-        o.w = (ms.hsum[1][l + 3] * pr.w + a.w * kInvZ) * ms.hsum[0][l + 3];
-        out4[i] = o;
-      }
-      EM_STAMP();                    // nu slice written
-    }
+    if (last && !windowed) nu_slice();
   }
 
+  if (fin_only) nu_slice();           // windowed mode, last launch: the totals of every tile are complete
   tc_fence_before_sync();
   __syncthreads();
   EM_STAMP();
@@ -745,24 +777,14 @@ static int max_clusters_resident() {
   return n;
 }
 
-template <int CK>
-static int clusters_resident(int LB) {
-  return LB == 4 ? max_clusters_resident<CK, 4>() : LB == 2 ? max_clusters_resident<CK, 2>() : max_clusters_resident<CK, 1>();
-}
-
 bool fused_em_supported(const SwemDims& d) {
   if ((d.Ck != 64 && d.Ck != 128) || (d.L != 64 && d.L != 128 && d.L != 256 && d.L != 512) || d.Cv != em::kCv || d.n_iters < 1 ||
       d.n_iters > 16)
     return false;
   const int T = (d.HW + em::kTP - 1) / em::kTP;
-  const int LB = d.L > 128 ? d.L / 128 : 1;
-  // all clusters of one unit must be co-resident: 74 pairs / ~34 quads / ~16 octets on a B200.  With a device present
-  // the occupancy query decides (it is what the launch checks); without one (host-only tests) these figures do.
-  int limit = LB == 4 ? 14 : LB == 2 ? 28 : 64;
-  int ndev = 0;
-  if (cudaGetDeviceCount(&ndev) == cudaSuccess && ndev > 0) limit = d.Ck == 128 ? clusters_resident<128>(LB) : clusters_resident<64>(LB);
-  else cudaGetLastError();
-  return T >= 1 && T <= limit;
+  // Up to the co-residency limit of a unit's clusters (74 pairs / ~34 quads / ~16 octets on a B200, asked from the
+  // occupancy API at launch) the whole EM is one launch; beyond it the windowed form (one launch per iteration) runs.
+  return T >= 1 && T <= 4096;
 }
 
 size_t fused_em_workspace(const SwemDims& d) {
@@ -805,12 +827,21 @@ static int fused_em_forward_t(const SwemEmArgs& a, cudaStream_t st) {
   p.N = d.N; p.HW = d.HW; p.T = T; p.n_iters = d.n_iters; p.L = d.L;
   p.c1s = kLog2e / (d.tau * em::kKScale);
   p.prof = get_profile_buffer();
-  // all CTAs of a launch spin on each other: every launch must be co-resident (1 CTA per SM, 2-CTA clusters);
-  // units that do not fit are spread evenly over the fewest launches
-  if (max_clusters_resident<CK, LB>() < T) {
-    set_error("fused EM: %d clusters of %d CTAs cannot be co-resident (limit %d)", T, 2 * LB, max_clusters_resident<CK, LB>());
-    return SWEM_ERR_UNSUPPORTED;
+  // Windowed form (one launch per EM iteration + one for the outputs; the kernel boundary is the cross-tile barrier):
+  // taken when the clusters of a unit cannot all be co-resident (large HW x L), or forced by SWEM_EM_WINDOWED=1 (tests).
+  const char* force_w = getenv("SWEM_EM_WINDOWED");
+  if (max_clusters_resident<CK, LB>() < T || (force_w != nullptr && force_w[0] == '1')) {
+    p.windowed = 1;
+    p.u0 = 0;
+    for (int it = 0; it <= d.n_iters; ++it) {
+      p.it_begin = it;
+      em_pair_kernel<CK, LB><<<U * T * 2 * LB, 256, em::smem_bytes<CK, LB>(), st>>>(p);
+      SWEM_LAUNCH_CHECK();
+    }
+    return SWEM_OK;
   }
+  // Single-launch form: all CTAs of a launch spin on each other, so every launch must be co-resident (1 CTA per SM);
+  // units that do not fit are spread evenly over the fewest launches
   const int upl_max = max_clusters_resident<CK, LB>() / T;
   const int n_launch = (U + upl_max - 1) / upl_max;
   const int upl = (U + n_launch - 1) / n_launch;

@@ -731,3 +731,36 @@ def test_multiscale_flip_evaluation_matches_its_definition():
     got = evaluate_davis_seq_ms(model, frames, masks, (h, w), scales=scales, is_flip=True)
     assert len(got) == T - 1 and got[0].shape == (1, h, w)
     assert all(torch.equal(g, torch.argmax(wv, dim=1)) for g, wv in zip(got, want))
+
+
+WINDOWED_SHAPES = [
+    # B, N, Ck,  Cv,  L,   H,  W, iters
+    (1, 3, 64, 512, 128, 30, 54, 4),
+    (1, 2, 64, 512, 64, 24, 23, 1),
+    (1, 2, 128, 512, 256, 30, 54, 3),
+    (1, 1, 64, 512, 512, 24, 24, 2),
+    (1, 1, 64, 512, 256, 60, 108, 2),                     # HW = 6480: 51 quads cannot be co-resident -> windowed by itself
+]
+
+
+@pytest.mark.parametrize('shape', WINDOWED_SHAPES, ids=lambda s: 'x'.join(map(str, s)))
+def test_windowed_em_vs_oracle(shape, monkeypatch):
+    """The fused EM kernel's windowed form (one launch per iteration, the kernel boundary as the cross-tile barrier;
+    what large HW x L shapes dispatch to) against the oracle, forced by SWEM_EM_WINDOWED=1 on shapes that would
+    otherwise take the single-launch form -- and left to the dispatcher on the shape that needs it."""
+    from swem_b200.synthetic import em_inputs
+    B, N, Ck, Cv, L, H, W, I = shape
+    _skip_unless_covered('fused', B=B, N=N, Ck=Ck, Cv=Cv, HW=H * W, L=L, n_iters=I)
+    if H * W < 6000:
+        monkeypatch.setenv('SWEM_EM_WINDOWED', '1')
+    core = _core(dict(L=L, Cv=Cv, n_iters=I, tau=0.05, topl=64), 'fused')
+    x, v, masks = em_inputs(B, N, Ck, Cv, H, W, seed=21)
+    prior = dict(zip(('kappa', 'nu', 'zita'), O.random_init(B, N, Ck, L, Cv, generator=torch.Generator().manual_seed(22))))
+    prior['zita'] = prior['zita'] + torch.rand(prior['zita'].shape, generator=torch.Generator().manual_seed(23)) * 3
+    prior['nu'] = torch.randn(prior['nu'].shape, generator=torch.Generator().manual_seed(24))
+    want = O.em_memorize(x, v, masks, prior, L, I, 0.05)
+    with torch.no_grad():
+        got = core.swem(x.to(DEV), v.to(DEV), masks.to(DEV), _to(prior, DEV), return_z=True)
+    em_check(got, want, x, v, masks, prior, L, I, 0.05, TOL['fused']['bases'], SLACK['fused'])
+    colsum = got['z'].sum(dim=3).view_as(got['zita'])
+    check('zita_colsum', maxrel(got['zita'] - prior['zita'].to(DEV), colsum), 1e-4)
