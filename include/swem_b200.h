@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define SWEM_B200_ABI_VERSION 1
+#define SWEM_B200_ABI_VERSION 2
 
 typedef enum SwemStatus {
   SWEM_OK = 0,
@@ -87,6 +87,8 @@ typedef struct SwemEmArgs {
   void*  workspace;          /* >= swem_em_workspace_bytes(&dims, path) bytes, 256-byte aligned  */
   size_t workspace_bytes;
   int32_t path;              /* SwemPath                                                          */
+  int32_t v_pixel_major;     /* 1: `v` is [B, N, HW, Cv] (channels-last, as a cuDNN NHWC value encoder leaves it) -- fused
+                                family only (the generic family returns SWEM_ERR_UNSUPPORTED); 0: [B, N, Cv, HW] */
 } SwemEmArgs;
 
 size_t swem_em_workspace_bytes(const SwemDims* dims, int32_t path);

@@ -36,7 +36,7 @@ class SwemEmArgs(C.Structure):
                 ('kappa', C.c_void_p), ('nu', C.c_void_p), ('zita', C.c_void_p),
                 ('z_last', C.c_void_p),
                 ('workspace', C.c_void_p), ('workspace_bytes', C.c_size_t),
-                ('path', C.c_int32)]
+                ('path', C.c_int32), ('v_pixel_major', C.c_int32)]
 
 
 class SwemEmBwdArgs(C.Structure):
@@ -109,8 +109,8 @@ def load() -> C.CDLL:
     lib.swem_cbam_apply.argtypes = [C.c_void_p] * 3 + [C.c_int32, C.c_int64, C.c_int32] + [C.c_void_p] * 2
     lib.swem_bias_add_act.argtypes = [C.c_void_p] * 4 + [C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
     lib.swem_glu_gate.argtypes = [C.c_void_p] * 3 + [C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]
-    if lib.swem_abi_version() != 1:
-        raise RuntimeError(f'libswem_b200.so ABI version {lib.swem_abi_version()} != 1')
+    if lib.swem_abi_version() != 2:
+        raise RuntimeError(f'libswem_b200.so ABI version {lib.swem_abi_version()} != 2')
     _lib = lib
     return lib
 

@@ -150,7 +150,11 @@ class SWEMCore(nn.Module):
 
         x, masks = _f32c(x.detach(), 'x'), _f32c(masks.detach(), 'masks')
         kappa_, zita_ = _f32c(kappa_.detach(), 'kappa'), _f32c(zita_.detach(), 'zita')
-        v, nu_ = _f32c(v, 'v'), _f32c(nu_, 'nu')
+        nu_ = _f32c(nu_, 'nu')
+        if not (_wants_grad(v, nu_) or return_z) and self._takes_pixel_major(v, B, N, Ck, H * W):
+            v = v.detach()                # channels-last values go to the kernel as they are (no layout copy)
+        else:
+            v = _f32c(v, 'v')
         if _wants_grad(v, nu_):
             from .autograd import EMFunction
             kappa, nu, zita = EMFunction.apply(self, x, v, masks, kappa_, nu_, zita_)
@@ -161,8 +165,20 @@ class SWEMCore(nn.Module):
             bases['z'] = z
         return bases
 
+    def _takes_pixel_major(self, v, B, N, Ck, HW) -> bool:
+        """True when ``v`` (B,N,Cv,H,W) is dense in channels-last order per object -- what a cuDNN NHWC value encoder
+        (``FrameEngine``) hands over -- and the fused EM kernels, which read that layout directly, will run."""
+        if not (v.is_cuda and v.dtype == torch.float32 and v.dim() == 5 and self.em_path != _lib.PATH_GENERIC):
+            return False
+        _, _, Cv, H, W = v.shape
+        if v.stride() != (N * HW * Cv, HW * Cv, 1, W * Cv, Cv) or v.data_ptr() % 16:
+            return False
+        dims = _lib.SwemDims(B, N, Ck, Cv, HW, self.n_bases, self.n_iters, 0, 0, self.tau)
+        return bool(_lib.load().swem_em_fused_supported(C.byref(dims)))
+
     def _em_launch(self, x, v, masks, kappa_, nu_, zita_, return_z: bool):
-        """One ``swem_em_forward`` call on contiguous fp32 CUDA tensors -> (kappa, nu, zita, z_last | None)."""
+        """One ``swem_em_forward`` call on fp32 CUDA tensors (contiguous; ``v`` possibly channels-last, see
+        ``_takes_pixel_major``) -> (kappa, nu, zita, z_last | None)."""
         B, Ck, H, W = x.shape
         N, L, Cv = masks.shape[1], self.n_bases, v.shape[2]
         if v.shape[:2] != (B, N) or v.shape[-2:] != (H, W) or kappa_.shape != (B, N, 2, Ck, L) \
@@ -183,7 +199,7 @@ class SWEMCore(nn.Module):
                                kappa_.data_ptr(), nu_.data_ptr(), zita_.data_ptr(),
                                kappa.data_ptr(), nu.data_ptr(), zita.data_ptr(),
                                z_last.data_ptr() if return_z else None,
-                               ws.data_ptr(), ws.numel(), self.em_path)
+                               ws.data_ptr(), ws.numel(), self.em_path, 0 if v.is_contiguous() else 1)
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev).cuda_stream
             rc = _invoke('em', lambda: lib.swem_em_forward(C.byref(args), stream))

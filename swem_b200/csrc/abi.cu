@@ -182,6 +182,10 @@ int swem_em_forward(const SwemEmArgs* a, void* stream) {
     return SWEM_ERR_WORKSPACE;
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (a->v_pixel_major && !use_fused_em(a->dims, a->path)) {
+    set_error("v_pixel_major is implemented by the fused EM kernels only (Ck=%d Cv=%d L=%d path=%d)", a->dims.Ck, a->dims.Cv, a->dims.L, a->path);
+    return SWEM_ERR_UNSUPPORTED;
+  }
   return use_fused_em(a->dims, a->path) ? fused_em_forward(*a, st) : generic_em_forward(*a, st);
 }
 

@@ -124,6 +124,7 @@ struct EmPairParams {
   int* status;
   long long* prof;
   int N, HW, T, n_iters, u0;
+  int v_pixel_major;     // v is [U][HW][512] (NHWC) instead of [U][512][HW]
   int windowed;          // 0: the whole EM in one co-resident launch (cross-tile waits on the arrival counters);
   int it_begin;          // 1: one launch per iteration -- this launch finalises iteration it_begin - 1 from its completed
                          //    accumulators, then runs iteration it_begin up to the reduce-adds (it_begin = n_iters: outputs only)
@@ -175,6 +176,36 @@ __device__ __forceinline__ void convert_v_chunk(const float* __restrict__ vsrc /
   }
 }
 
+// Same image from a pixel-major (NHWC) value tensor: `vsrc` = [HW][512] rows of the unit, channels [dbase, dbase + 256).
+// A warp step takes 8 pixels x 128 channels: 8 float4 loads per lane (512 contiguous bytes per pixel and warp), the lane
+// then owns 4 channels x 8 pixels = four 16-byte operand units per plane, contiguous across the warp.
+template <int NW>
+__device__ __forceinline__ void convert_v_chunk_nhwc(const float* __restrict__ vsrc, int dbase, uint8_t* __restrict__ image,
+                                                     int px_base, int HW, int w, int lane) {
+  using namespace em;
+#pragma unroll
+  for (int step = w; step < 8; step += NW) {
+    const int g = step >> 1, dh = step & 1;               // pixel group of 8, half of the image's 256 channels
+    const int d = dh * 128 + lane * 4;
+    float4 f[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int px = px_base + g * 8 + e;
+      f[e] = px < HW ? __ldg(reinterpret_cast<const float4*>(vsrc + (size_t)px * kCv + dbase + d)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    uint8_t* dst = image + d * 16 + g * 4096;             // (d % 8) * 16 + (d / 8) * 128 = d * 16
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      __align__(16) __half hi[8];
+      __align__(16) __half lo[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) split_half(k == 0 ? f[e].x : k == 1 ? f[e].y : k == 2 ? f[e].z : f[e].w, hi[e], lo[e]);
+      *reinterpret_cast<uint4*>(dst + k * 16) = *reinterpret_cast<uint4*>(hi);
+      *reinterpret_cast<uint4*>(dst + kVPlane + k * 16) = *reinterpret_cast<uint4*>(lo);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------------
 template <int CK, int LB>   // key channels; basis blocks of 128 per side (L = 64 / 128: 1, L = 256: 2) -> cluster of 2 * LB CTAs
 __global__ void __cluster_dims__(2 * LB, 1, 1) __launch_bounds__(256, 1) em_pair_kernel(const EmPairParams p) {
@@ -221,6 +252,12 @@ __global__ void __cluster_dims__(2 * LB, 1, 1) __launch_bounds__(256, 1) em_pair
   constexpr int kMine = kChunks / CS;                   // images converted by this CTA: rank * kMine + j, image c = (half c/4, quarter c%4)
   auto convert_mine = [&](int j, bool whole_cta) {
     const int c = rank * kMine + j;
+    if (p.v_pixel_major) {
+      const float* src = p.v + (size_t)u * HW * kCv;
+      if (whole_cta) convert_v_chunk_nhwc<8>(src, (c >> 2) * 256, vimg + (size_t)c * kStageBytes, p0 + (c & 3) * 32, HW, warp, lane);
+      else convert_v_chunk_nhwc<4>(src, (c >> 2) * 256, vimg + (size_t)c * kStageBytes, p0 + (c & 3) * 32, HW, warp - 4, lane);
+      return;
+    }
     const float* src = p.v + ((size_t)u * kCv + (c >> 2) * 256) * HW;
     if (whole_cta) convert_v_chunk<8>(src, vimg + (size_t)c * kStageBytes, p0 + (c & 3) * 32, HW, warp, lane);
     else convert_v_chunk<4>(src, vimg + (size_t)c * kStageBytes, p0 + (c & 3) * 32, HW, warp - 4, lane);
@@ -825,6 +862,7 @@ static int fused_em_forward_t(const SwemEmArgs& a, cudaStream_t st) {
   p.vblob = vblob;
   p.acc_k = acc_k; p.acc_nu = acc_nu; p.counters = counters; p.status = status;
   p.N = d.N; p.HW = d.HW; p.T = T; p.n_iters = d.n_iters; p.L = d.L;
+  p.v_pixel_major = a.v_pixel_major;
   p.c1s = kLog2e / (d.tau * em::kKScale);
   p.prof = get_profile_buffer();
   // Windowed form (one launch per EM iteration + one for the outputs; the kernel boundary is the cross-tile barrier):

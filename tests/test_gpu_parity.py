@@ -764,3 +764,33 @@ def test_windowed_em_vs_oracle(shape, monkeypatch):
     em_check(got, want, x, v, masks, prior, L, I, 0.05, TOL['fused']['bases'], SLACK['fused'])
     colsum = got['z'].sum(dim=3).view_as(got['zita'])
     check('zita_colsum', maxrel(got['zita'] - prior['zita'].to(DEV), colsum), 1e-4)
+
+
+@pytest.mark.parametrize('shape', [(1, 3, 64, 30, 53, 128, 1), (2, 2, 128, 24, 24, 256, 2), (1, 2, 64, 30, 54, 64, 4)],
+                         ids=lambda s: 'x'.join(map(str, s)))
+def test_em_reads_channels_last_values_in_place(shape):
+    """SwemEmArgs.v_pixel_major: a channels-last value tensor (what the NHWC value encoder of FrameEngine produces) goes to
+    the fused EM kernel as it is; same bases as from the NCHW copy (ragged HW, both cluster widths), and the generic
+    family refuses the layout loudly."""
+    from swem_b200 import _lib
+    from swem_b200.synthetic import em_inputs
+    B, N, Ck, H, W, L, I = shape
+    Cv = 512
+    core = _core(dict(L=L, Cv=Cv, n_iters=I, tau=0.05, topl=64), 'fused')
+    x, v, masks = em_inputs(B, N, Ck, Cv, H, W, seed=31)
+    prior = _to(dict(zip(('kappa', 'nu', 'zita'), O.random_init(B, N, Ck, L, Cv, generator=torch.Generator().manual_seed(32)))), DEV)
+    x, v, masks = x.to(DEV), v.to(DEV), masks.to(DEV)
+    v_cl = v.flatten(end_dim=1).contiguous(memory_format=torch.channels_last).view(B, N, Cv, H, W)
+    assert not v_cl.is_contiguous() and core._takes_pixel_major(v_cl, B, N, Ck, H * W)
+    seen = []
+    real = core._em_launch
+    core._em_launch = lambda x_, v_, *a: (seen.append(v_.data_ptr()), real(x_, v_, *a))[1]
+    with torch.no_grad():
+        a = core.swem(x, v, masks, prior)
+        b = core.swem(x, v_cl, masks, prior)
+    assert seen == [v.data_ptr(), v_cl.data_ptr()]                    # no layout copy on the second call
+    live = a['zita'] > 1e-3
+    for key in ('zita', 'kappa', 'nu'):
+        check(key + '_nhwc', maxrel(b[key], a[key], None if key == 'zita' else live.cpu()), 1e-5 if I == 1 else 1e-2)
+    core.em_path = _lib.PATH_GENERIC
+    assert not core._takes_pixel_major(v_cl, B, N, Ck, H * W)         # the generic family gets the NCHW copy instead
