@@ -26,17 +26,16 @@ __device__ __forceinline__ float4 f4relu(float4 a) {
   return make_float4(fmaxf(a.x, 0.f), fmaxf(a.y, 0.f), fmaxf(a.z, 0.f), fmaxf(a.w, 0.f));
 }
 
+// grid (ceil(W * C4 / 256), H, BN): the row and the image come from the block index, so a thread's index arithmetic is
+// one 32-bit division (the flat 64-bit index of the first version cost four 64-bit div/mods per float4: ALU-bound at 2.5 TB/s)
 __global__ void __launch_bounds__(256) upsample_add_kernel(const float4* __restrict__ lo_a, const float4* __restrict__ lo_b,
                                                            const float4* __restrict__ bias, const float4* __restrict__ skip,
                                                            int BN, int n, int h, int w, int H, int W, int C4,
                                                            float4* __restrict__ x, float4* __restrict__ xr) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long total = (long long)BN * H * W * C4;
-  if (idx >= total) return;
-  const int c4 = (int)(idx % C4);
-  const int X = (int)((idx / C4) % W);
-  const int Y = (int)((idx / ((long long)C4 * W)) % H);
-  const int bn = (int)(idx / ((long long)C4 * W * H));
+  const int t = blockIdx.x * 256 + threadIdx.x;
+  if (t >= W * C4) return;
+  const int X = t / C4, c4 = t - X * C4;
+  const int Y = blockIdx.y, bn = blockIdx.z;
   const float sh = (float)h / (float)H, sw = (float)w / (float)W;
   float sy = sh * (Y + 0.5f) - 0.5f, sx = sw * (X + 0.5f) - 0.5f;
   sy = sy < 0.f ? 0.f : sy;
@@ -44,15 +43,15 @@ __global__ void __launch_bounds__(256) upsample_add_kernel(const float4* __restr
   const int y0 = min((int)sy, h - 1), x0 = min((int)sx, w - 1);
   const int y1 = y0 + (y0 < h - 1 ? 1 : 0), x1 = x0 + (x0 < w - 1 ? 1 : 0);
   const float ly = sy - y0, lx = sx - x0, my = 1.f - ly, mx = 1.f - lx;
-  const long long base = (long long)bn * h * w;
-  const long long i00 = ((base + (long long)y0 * w + x0) * C4) + c4, i01 = ((base + (long long)y0 * w + x1) * C4) + c4;
-  const long long i10 = ((base + (long long)y1 * w + x0) * C4) + c4, i11 = ((base + (long long)y1 * w + x1) * C4) + c4;
-  float4 v00 = __ldg(lo_a + i00), v01 = __ldg(lo_a + i01), v10 = __ldg(lo_a + i10), v11 = __ldg(lo_a + i11);
+  const float4* pa = lo_a + (long long)bn * h * w * C4 + c4;
+  const int o00 = (y0 * w + x0) * C4, o01 = (y0 * w + x1) * C4, o10 = (y1 * w + x0) * C4, o11 = (y1 * w + x1) * C4;
+  float4 v00 = __ldg(pa + o00), v01 = __ldg(pa + o01), v10 = __ldg(pa + o10), v11 = __ldg(pa + o11);
   if (lo_b != nullptr) {
-    v00 = f4add(v00, __ldg(lo_b + i00));
-    v01 = f4add(v01, __ldg(lo_b + i01));
-    v10 = f4add(v10, __ldg(lo_b + i10));
-    v11 = f4add(v11, __ldg(lo_b + i11));
+    const float4* pb = lo_b + (long long)bn * h * w * C4 + c4;
+    v00 = f4add(v00, __ldg(pb + o00));
+    v01 = f4add(v01, __ldg(pb + o01));
+    v10 = f4add(v10, __ldg(pb + o10));
+    v11 = f4add(v11, __ldg(pb + o11));
   }
   // my * (mx * v00 + lx * v01) + ly * (mx * v10 + lx * v11), in ATen's order
   float4 top = make_float4(mx * v00.x, mx * v00.y, mx * v00.z, mx * v00.w);
@@ -62,10 +61,67 @@ __global__ void __launch_bounds__(256) upsample_add_kernel(const float4* __restr
   float4 out = make_float4(my * top.x, my * top.y, my * top.z, my * top.w);
   out = f4fma(ly, bot, out);
   const int b = bn / n;
-  out = f4add(out, __ldg(skip + (((long long)b * H + Y) * W + X) * C4 + c4));
+  out = f4add(out, __ldg(skip + ((long long)b * H + Y) * W * C4 + t));
   if (bias != nullptr) out = f4add(out, __ldg(bias + c4));
+  const long long idx = ((long long)bn * H + Y) * W * C4 + t;
   x[idx] = out;
   if (xr != nullptr) xr[idx] = f4relu(out);
+}
+
+// Exact 2x up-sampling (H = 2h, W = 2w -- both decoder stages): output rows {2i+1, 2i+2} x columns {2j+1, 2j+2} read the
+// same four low-resolution pixels (i, i+1) x (j, j+1) with weights 3/4 and 1/4, so a thread computes that 2 x 2 block from
+// 4 (+4) loads instead of 16 (+16): grid (ceil((w+1) * C4 / 256), h + 1, BN), block row i = blockIdx.y - 1.  Same
+// operation order as the general kernel (the weights 0.25 / 0.75 are what its index arithmetic produces), so the results
+// are identical.
+__global__ void __launch_bounds__(256) upsample2x_add_kernel(const float4* __restrict__ lo_a, const float4* __restrict__ lo_b,
+                                                             const float4* __restrict__ bias, const float4* __restrict__ skip,
+                                                             int n, int h, int w, int C4, float4* __restrict__ x,
+                                                             float4* __restrict__ xr) {
+  const int t = blockIdx.x * 256 + threadIdx.x;
+  if (t >= (w + 1) * C4) return;
+  const int jb = t / C4, c4 = t - jb * C4;
+  const int i = (int)blockIdx.y - 1, j = jb - 1, bn = blockIdx.z;
+  const int H = 2 * h, W = 2 * w;
+  const int ya = max(i, 0), yb = min(i + 1, h - 1), xa = max(j, 0), xb = min(j + 1, w - 1);
+  const long long lbase = (long long)bn * h * w * C4 + c4;
+  const int oaa = (ya * w + xa) * C4, oab = (ya * w + xb) * C4, oba = (yb * w + xa) * C4, obb = (yb * w + xb) * C4;
+  float4 vaa = __ldg(lo_a + lbase + oaa), vab = __ldg(lo_a + lbase + oab), vba = __ldg(lo_a + lbase + oba), vbb = __ldg(lo_a + lbase + obb);
+  if (lo_b != nullptr) {
+    vaa = f4add(vaa, __ldg(lo_b + lbase + oaa));
+    vab = f4add(vab, __ldg(lo_b + lbase + oab));
+    vba = f4add(vba, __ldg(lo_b + lbase + oba));
+    vbb = f4add(vbb, __ldg(lo_b + lbase + obb));
+  }
+  const float4 bs = bias != nullptr ? __ldg(bias + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+  const int b = bn / n;
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int Y = 2 * i + 1 + r;
+    if (Y < 0 || Y >= H) continue;
+    // general kernel at this row: sy = max(i + 0.25 + 0.5 r, 0) -> weight 0 at Y = 0 (clamped); at Y = H - 1 both source
+    // rows are row h - 1 (ya = yb) with weights 3/4 + 1/4, as there
+    const float ly = (Y == 0) ? 0.f : (r ? 0.75f : 0.25f), my = 1.f - ly;
+    const float4 r0a = vaa, r0b = vab;                   // source row y0 (left, right)
+    const float4 r1a = vba, r1b = vbb;                   // source row y1
+#pragma unroll
+    for (int cidx = 0; cidx < 2; ++cidx) {
+      const int X = 2 * j + 1 + cidx;
+      if (X < 0 || X >= W) continue;
+      const float lx = (X == 0) ? 0.f : (cidx ? 0.75f : 0.25f), mx = 1.f - lx;
+      const float4 v00 = r0a, v01 = r0b, v10 = r1a, v11 = r1b;
+      float4 top = make_float4(mx * v00.x, mx * v00.y, mx * v00.z, mx * v00.w);
+      top = f4fma(lx, v01, top);
+      float4 bot = make_float4(mx * v10.x, mx * v10.y, mx * v10.z, mx * v10.w);
+      bot = f4fma(lx, v11, bot);
+      float4 out = make_float4(my * top.x, my * top.y, my * top.z, my * top.w);
+      out = f4fma(ly, bot, out);
+      out = f4add(out, __ldg(skip + (((long long)b * H + Y) * W + X) * C4 + c4));
+      if (bias != nullptr) out = f4add(out, bs);
+      const long long idx = (((long long)bn * H + Y) * W + X) * C4 + c4;
+      x[idx] = out;
+      if (xr != nullptr) xr[idx] = f4relu(out);
+    }
+  }
 }
 
 __global__ void __launch_bounds__(256) bias_add_act_kernel(const float4* __restrict__ a, const float4* __restrict__ b,
@@ -108,13 +164,12 @@ __global__ void __launch_bounds__(256) glu_gate_kernel(const float4* __restrict_
 // used by methods/basic_modules/networks.py:150 and mod_resnet.py); out-of-range taps are skipped (= -inf padding).
 __global__ void __launch_bounds__(256) maxpool3x3s2_kernel(const float4* __restrict__ in, int N, int H, int W, int C4, int Ho, int Wo,
                                                            float4* __restrict__ out) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long total = (long long)N * Ho * Wo * C4;
-  if (idx >= total) return;
-  const int c4 = (int)(idx % C4);
-  const int px = (int)((idx / C4) % Wo);
-  const int py = (int)((idx / ((long long)C4 * Wo)) % Ho);
-  const int n = (int)(idx / ((long long)C4 * Wo * Ho));
+  // grid (ceil(Wo * C4 / 256), Ho, N): row and image from the block index, one 32-bit division per thread
+  const int t = blockIdx.x * 256 + threadIdx.x;
+  if (t >= Wo * C4) return;
+  const int px = t / C4, c4 = t - px * C4;
+  const int py = blockIdx.y, n = blockIdx.z;
+  const long long idx = ((long long)n * Ho + py) * Wo * C4 + t;
   float4 m = make_float4(-3.4e38f, -3.4e38f, -3.4e38f, -3.4e38f);
 #pragma unroll
   for (int ky = -1; ky <= 1; ++ky) {
@@ -135,50 +190,84 @@ __global__ void __launch_bounds__(256) maxpool3x3s2_kernel(const float4* __restr
 // conv to ONE logit plane (networks.py:205-213):  out[y, x] = bp + sum_{dy,dx,c} wp[dy][dx][c] relu(a + b + bias)[y+dy-1, x+dx-1, c]
 // (zero padding).  A 256 -> 1 conv is pure bandwidth (cuDNN: 106 us for 133 MB at 480p / 5 objects) on top of the 133 MB
 // write + read of its input; here a and b are read once (+ halo) and nothing but the logit plane is written.
-// CTA = 16 x 32 output pixels (2 per thread), channels in chunks of 32 through a swizzled smem tile of the 18 x 34 halo.
-constexpr int kTpTH = 16, kTpTW = 32, kTpHalo = (kTpTH + 2) * (kTpTW + 2);
+// CTA = 16 x 32 output pixels.  Stage 1 streams the 18 x 34 halo tile once: 8 lanes share a pixel (lane slot s takes the
+// float4 channel groups s, s + 8, ...), four pixels per lane group in flight; every value is used straight from registers
+// for its nine tap products (weights: 9 x C floats in shared memory, one broadcast LDS.128 per 16 FMAs), the lane group
+// reduces the 4 x 9 partial dot products by shuffles and leaves them in shared memory [halo pixel][9].  Stage 2: each
+// output pixel adds its nine neighbours' partials.  HBM-bound (the first version kept activations in shared memory
+// and re-read them per tap: 143 us, LDS-bound).
+constexpr int kTpTH = 16, kTpTW = 32, kTpHW = kTpTW + 2, kTpHalo = (kTpTH + 2) * kTpHW;
 __global__ void __launch_bounds__(256, 2) resblock_tail_pred_kernel(const float4* __restrict__ a, const float4* __restrict__ b,
                                                                     const float4* __restrict__ bias, const float4* __restrict__ wp,
                                                                     float bp, int H, int W, int C4, float* __restrict__ out) {
   extern __shared__ float4 tp_smem[];
-  float4* tile = tp_smem;                    // [kTpHalo][8] float4, slot (c4 + px) & 7
-  float4* wsm = tp_smem + kTpHalo * 8;       // [9][8] float4 of the current channel chunk
-  const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+  float4* wsm = tp_smem;                                         // [9][C4] tap weights
+  float* part = reinterpret_cast<float*>(tp_smem + 9 * C4);      // [kTpHalo][9] partial dot products
+  const int tid = threadIdx.x, slot = tid & 7, grp = tid >> 3;   // 32 lane groups of 8
   const int x0 = blockIdx.x * kTpTW, y0 = blockIdx.y * kTpTH, bn = blockIdx.z;
   const long long img = (long long)bn * H * W;
-  float acc0 = 0.f, acc1 = 0.f;
-  for (int ch = 0; ch < C4; ch += 8) {
-    for (int i = tid; i < kTpHalo * 8; i += 256) {
-      const int px = i >> 3, c4 = i & 7;
-      const int y = y0 - 1 + px / (kTpTW + 2), x = x0 - 1 + px % (kTpTW + 2);
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (y >= 0 && y < H && x >= 0 && x < W) {
-        const long long g = (img + (long long)y * W + x) * C4 + ch + c4;
-        v = f4relu(f4add(f4add(__ldg(a + g), __ldg(b + g)), __ldg(bias + ch + c4)));
-      }
-      tile[px * 8 + ((c4 + px) & 7)] = v;
+  for (int i = tid; i < 9 * C4; i += 256) wsm[i] = __ldg(wp + i);
+  __syncthreads();
+  constexpr int P = 4;
+  for (int base = 0; base < kTpHalo; base += 32 * P) {
+    float acc[P][9];
+    long long g[P];
+    bool ok[P];
+#pragma unroll
+    for (int i = 0; i < P; ++i) {
+      const int px = base + i * 32 + grp;
+      const int y = y0 - 1 + px / kTpHW, x = x0 - 1 + px % kTpHW;
+      ok[i] = px < kTpHalo && y >= 0 && y < H && x >= 0 && x < W;
+      g[i] = (img + (long long)y * W + x) * C4 + slot;
+#pragma unroll
+      for (int t = 0; t < 9; ++t) acc[i][t] = 0.f;
     }
-    if (tid < 72) wsm[tid] = __ldg(wp + (tid >> 3) * C4 + ch + (tid & 7));
-    __syncthreads();
+#pragma unroll 2
+    for (int c4 = slot; c4 < C4; c4 += 8) {
+      float4 v[P];
+      const float4 bs = __ldg(bias + c4);
+#pragma unroll
+      for (int i = 0; i < P; ++i) {
+        v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ok[i]) v[i] = f4relu(f4add(f4add(__ldg(a + g[i] + (c4 - slot)), __ldg(b + g[i] + (c4 - slot))), bs));
+      }
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        const float4 w = wsm[t * C4 + c4];
+#pragma unroll
+        for (int i = 0; i < P; ++i)
+          acc[i][t] = fmaf(w.x, v[i].x, fmaf(w.y, v[i].y, fmaf(w.z, v[i].z, fmaf(w.w, v[i].w, acc[i][t]))));
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < P; ++i) {
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        float r = acc[i][t];
+        r += __shfl_xor_sync(0xffffffffu, r, 1);
+        r += __shfl_xor_sync(0xffffffffu, r, 2);
+        r += __shfl_xor_sync(0xffffffffu, r, 4);
+        acc[i][t] = r;
+      }
+      const int px = base + i * 32 + grp;
+      if (px < kTpHalo) {
+#pragma unroll
+        for (int t = 0; t < 9; ++t)
+          if ((t & 7) == slot) part[px * 9 + t] = acc[i][t];
+      }
+    }
+  }
+  __syncthreads();
+  const int tx = tid & 31, ty = tid >> 5;
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const int oy = ty + 8 * half;
+    float r = bp;
 #pragma unroll
     for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
-      for (int dx = 0; dx < 3; ++dx) {
-        const int p0 = (ty + dy) * (kTpTW + 2) + tx + dx, p1 = p0 + 8 * (kTpTW + 2);
-#pragma unroll
-        for (int c4 = 0; c4 < 8; ++c4) {
-          const float4 w = wsm[(dy * 3 + dx) * 8 + c4];
-          const float4 v0 = tile[p0 * 8 + ((c4 + p0) & 7)], v1 = tile[p1 * 8 + ((c4 + p1) & 7)];
-          acc0 = fmaf(w.x, v0.x, fmaf(w.y, v0.y, fmaf(w.z, v0.z, fmaf(w.w, v0.w, acc0))));
-          acc1 = fmaf(w.x, v1.x, fmaf(w.y, v1.y, fmaf(w.z, v1.z, fmaf(w.w, v1.w, acc1))));
-        }
-      }
-    __syncthreads();
-  }
-  const int x = x0 + tx;
-  if (x < W) {
-    if (y0 + ty < H) out[img + (long long)(y0 + ty) * W + x] = acc0 + bp;
-    if (y0 + ty + 8 < H) out[img + (long long)(y0 + ty + 8) * W + x] = acc1 + bp;
+      for (int dx = 0; dx < 3; ++dx) r += part[((oy + dy) * kTpHW + tx + dx) * 9 + dy * 3 + dx];
+    if (x0 + tx < W && y0 + oy < H) out[img + (long long)(y0 + oy) * W + x0 + tx] = r;
   }
 }
 
@@ -345,8 +434,17 @@ int swem_upsample_add(const float* lo_a, const float* lo_b, const float* bias, c
   SWEM_CHECK_ARG(lo_a && skip && x, "NULL pointer");
   SWEM_CHECK_ARG(BN > 0 && n > 0 && BN % n == 0 && h > 0 && w > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0,
                  "bad sizes BN=%d n=%d h=%d w=%d H=%d W=%d C=%d (C must be a multiple of 4)", BN, n, h, w, H, W, C);
-  const long long total = (long long)BN * H * W * (C / 4);
-  upsample_add_kernel<<<(unsigned)((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  SWEM_CHECK_ARG(H <= 65535 && BN <= 65535 && (long long)h * w * (C / 4) < (1ll << 31) && (long long)W * (C / 4) < (1ll << 31),
+                 "sizes beyond the kernel's index range (H=%d BN=%d)", H, BN);
+  if (H == 2 * h && W == 2 * w && h >= 2 && w >= 2) {
+    upsample2x_add_kernel<<<dim3((unsigned)(((w + 1) * (C / 4) + 255) / 256), (unsigned)(h + 1), (unsigned)BN), 256, 0,
+                            static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const float4*>(lo_a), reinterpret_cast<const float4*>(lo_b), reinterpret_cast<const float4*>(bias),
+        reinterpret_cast<const float4*>(skip), n, h, w, C / 4, reinterpret_cast<float4*>(x), reinterpret_cast<float4*>(x_relu));
+    SWEM_LAUNCH_CHECK();
+    return SWEM_OK;
+  }
+  upsample_add_kernel<<<dim3((unsigned)((W * (C / 4) + 255) / 256), (unsigned)H, (unsigned)BN), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const float4*>(lo_a), reinterpret_cast<const float4*>(lo_b), reinterpret_cast<const float4*>(bias),
       reinterpret_cast<const float4*>(skip), BN, n, h, w, H, W, C / 4, reinterpret_cast<float4*>(x),
       reinterpret_cast<float4*>(x_relu));
@@ -388,10 +486,11 @@ int swem_resblock_tail_pred(const float* a, const float* b, const float* bias, c
   SWEM_CHECK_ARG(a && b && bias && wp && out, "NULL pointer");
   SWEM_CHECK_ARG(BN > 0 && BN <= 65535 && H > 0 && W > 0 && C > 0 && C % 32 == 0, "bad sizes BN=%d H=%d W=%d C=%d (C must be a multiple of 32)",
                  BN, H, W, C);
-  const size_t smem = (size_t)(kTpHalo * 8 + 72) * sizeof(float4);
+  const size_t smem = (size_t)9 * (C / 4) * sizeof(float4) + (size_t)kTpHalo * 9 * sizeof(float);
+  SWEM_CHECK_ARG(smem <= 96 * 1024, "C=%d too large for the weight tile", C);
   static bool attr_set = false;
   if (!attr_set) {
-    SWEM_CUDA(cudaFuncSetAttribute(resblock_tail_pred_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SWEM_CUDA(cudaFuncSetAttribute(resblock_tail_pred_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     attr_set = true;
   }
   dim3 grid((W + kTpTW - 1) / kTpTW, (H + kTpTH - 1) / kTpTH, BN);
@@ -462,8 +561,8 @@ int swem_maxpool3x3s2(const float* in, int32_t N, int32_t H, int32_t W, int32_t 
   SWEM_CHECK_ARG(in && out, "NULL pointer");
   SWEM_CHECK_ARG(N > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0, "bad sizes N=%d H=%d W=%d C=%d (C must be a multiple of 4)", N, H, W, C);
   const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
-  const long long total = (long long)N * Ho * Wo * (C / 4);
-  maxpool3x3s2_kernel<<<(unsigned)((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  SWEM_CHECK_ARG(Ho <= 65535 && N <= 65535 && (long long)Wo * (C / 4) < (1ll << 31), "sizes beyond the kernel's index range (H=%d N=%d)", H, N);
+  maxpool3x3s2_kernel<<<dim3((unsigned)((Wo * (C / 4) + 255) / 256), (unsigned)Ho, (unsigned)N), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const float4*>(in), N, H, W, C / 4, Ho, Wo, reinterpret_cast<float4*>(out));
   SWEM_LAUNCH_CHECK();
   return SWEM_OK;
