@@ -209,6 +209,13 @@ def run_b200(args, rank, world, local_rank):
         torch.cuda.synchronize(dev)
 
     K, Wm, n_obj = args.steps, args.warmup, args.objects
+    # cuDNN picks its conv kernels by heuristic unless asked to time the candidates (once per shape, during the eager warm-up
+    # frames, before the step graph is captured)
+    cudnn_autotune = os.environ.get('SWEM_CUDNN_BENCHMARK', '1') == '1'
+    torch.backends.cudnn.benchmark = cudnn_autotune
+    conv_tf32 = os.environ.get('SWEM_CONV_TF32', '1') == '1'
+    torch.backends.cudnn.allow_tf32 = conv_tf32
+    torch.backends.cuda.matmul.allow_tf32 = conv_tf32
     use_graph = os.environ.get('SWEM_CUDA_GRAPH', '1') == '1'
     if use_graph:
         Wm = max(Wm, 3)            # frames 1-2 run eagerly, frame 3 captures the step graph: all inside the warm-up
@@ -241,7 +248,7 @@ def run_b200(args, rank, world, local_rank):
         stages = FrameEngine(model, channels_last=os.environ.get('SWEM_CHANNELS_LAST', '1') == '1',
                              fused_conv=os.environ.get('SWEM_FUSED_CONV', '1') == '1')
 
-    def run_phase(host_io, graphed):
+    def run_phase(host_io, graphed, K=K):
         """start on frame 0, Wm warm-up steps, then K timed steps; returns (ms, clocks, masks checksum).  Step k segments and
         memorizes frame 1 + Wm + k; with the pipelined runner it also encodes the key of frame 2 + Wm + k meanwhile."""
         pipe = graphed and use_pipe
@@ -302,6 +309,19 @@ def run_b200(args, rank, world, local_rank):
 
     fps = world * K / (ms_res / 1e3)
     fps_e2e = world * K / (ms_e2e / 1e3)
+    # pass 4 (N = 1 only, short): the same step with the torch convolutions in IEEE fp32 instead of torch's cuDNN default
+    # (TF32) -- the arithmetic in which the >= 99.9 % mask agreement with the fp32 CPU oracle is demonstrated
+    # (tests/test_gpu_parity.py; profiles/r1_agreement.txt has both modes, for the plain torch modules too)
+    fp32_convs = None
+    if world == 1 and conv_tf32 and not args.no_cpu_baseline:
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
+        k4 = min(K, 5)
+        ms_fp32, _, _ = run_phase(host_io=False, graphed=use_graph, K=k4)
+        torch.backends.cudnn.allow_tf32 = True
+        torch.backends.cuda.matmul.allow_tf32 = True
+        fp32_convs = {'value': k4 / (ms_fp32 / 1e3), 'unit': UNIT, 'steps': k4, 'ms_per_step': ms_fp32 / k4,
+                      'note': 'same step, cuDNN convolutions in IEEE fp32 (no tensor cores): the mode of the mask-parity tests'}
     peaks = measured_peaks()
     f_mem, f_read = hot_path_flops(n_obj, hw, 2 * CFG['n_bases'])
     b_mem, b_read = hot_path_bytes(n_obj, hw, 2 * CFG['n_bases'])
@@ -321,7 +341,12 @@ def run_b200(args, rank, world, local_rank):
                                                          else 'CUDA graph replay' if use_graph else 'eager'),
                                           'eager_ms_per_step': ms_eager / K, 'l2': 'every step reads a new 5 MB frame and '
                                           '>230 MB of fp32 weights + activations (> 126 MB L2); no explicit flush',
-                                          'torch_convs': 'cudnn, allow_tf32 default, channels_last=' + os.environ.get('SWEM_CHANNELS_LAST', '1'),
+                                          'torch_convs': ('cudnn ' + ('TF32 (torch default allow_tf32)' if conv_tf32 else 'IEEE fp32')
+                                                          + (', autotuned (cudnn.benchmark)' if cudnn_autotune else ', heuristic algos')
+                                                          + ', channels_last=' + os.environ.get('SWEM_CHANNELS_LAST', '1')),
+                                          'mask_agreement_vs_fp32_cpu_oracle': 'fp32 convs: >= 99.94 % per frame; TF32 convs: 80-92 % for '
+                                          'FrameEngine AND for the plain torch modules with all-fp32 memory kernels (random-init decoder: argmax '
+                                          'margins at TF32 noise level) -- profiles/r1_agreement.txt',
                                           'torch_stages': ('FrameEngine (BN folded, fused conv+bias+relu=' + os.environ.get('SWEM_FUSED_CONV', '1')
                                                            + ', object-independent conv halves computed once per frame)') if use_engine
                                                           else 'plain nn.Modules'}),
@@ -342,6 +367,8 @@ def run_b200(args, rank, world, local_rank):
                                   'hbm_gbs': (b_mem + b_read) / hot_s / 1e9, 'hbm_frac': (b_mem + b_read) / hot_s / 1e9 / peaks['hbm'],
                                   'share_of_eager_step': (em_ms + read_ms) / (ms_eager / K)}},
     }
+    if fp32_convs is not None:
+        line['fp32_convs'] = fp32_convs
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         steps = args.cpu_steps
         fps_cpu, dt, cores = cpu_reference_fps(n_obj, steps, 1)

@@ -124,7 +124,6 @@ struct EmPairParams {
   int* status;
   long long* prof;
   int N, HW, T, n_iters, u0;
-  int v_pixel_major;     // v is [U][HW][512] (NHWC) instead of [U][512][HW]
   int windowed;          // 0: the whole EM in one co-resident launch (cross-tile waits on the arrival counters);
   int it_begin;          // 1: one launch per iteration -- this launch finalises iteration it_begin - 1 from its completed
                          //    accumulators, then runs iteration it_begin up to the reduce-adds (it_begin = n_iters: outputs only)
@@ -207,7 +206,9 @@ __device__ __forceinline__ void convert_v_chunk_nhwc(const float* __restrict__ v
 }
 
 // ------------------------------------------------------------------------------------------------------
-template <int CK, int LB>   // key channels; basis blocks of 128 per side (L = 64 / 128: 1, L = 256: 2) -> cluster of 2 * LB CTAs
+// CK key channels; LB basis blocks of 128 per side (L = 64 / 128: 1, L = 256: 2, L = 512: 4) -> cluster of 2 * LB CTAs;
+// VPM: value features pixel-major (NHWC)
+template <int CK, int LB, bool VPM>
 __global__ void __cluster_dims__(2 * LB, 1, 1) __launch_bounds__(256, 1) em_pair_kernel(const EmPairParams p) {
   using namespace em;
   using LY = Lay<CK>;
@@ -252,15 +253,15 @@ __global__ void __cluster_dims__(2 * LB, 1, 1) __launch_bounds__(256, 1) em_pair
   constexpr int kMine = kChunks / CS;                   // images converted by this CTA: rank * kMine + j, image c = (half c/4, quarter c%4)
   auto convert_mine = [&](int j, bool whole_cta) {
     const int c = rank * kMine + j;
-    if (p.v_pixel_major) {
+    if constexpr (VPM) {
       const float* src = p.v + (size_t)u * HW * kCv;
       if (whole_cta) convert_v_chunk_nhwc<8>(src, (c >> 2) * 256, vimg + (size_t)c * kStageBytes, p0 + (c & 3) * 32, HW, warp, lane);
       else convert_v_chunk_nhwc<4>(src, (c >> 2) * 256, vimg + (size_t)c * kStageBytes, p0 + (c & 3) * 32, HW, warp - 4, lane);
-      return;
+    } else {
+      const float* src = p.v + ((size_t)u * kCv + (c >> 2) * 256) * HW;
+      if (whole_cta) convert_v_chunk<8>(src, vimg + (size_t)c * kStageBytes, p0 + (c & 3) * 32, HW, warp, lane);
+      else convert_v_chunk<4>(src, vimg + (size_t)c * kStageBytes, p0 + (c & 3) * 32, HW, warp - 4, lane);
     }
-    const float* src = p.v + ((size_t)u * kCv + (c >> 2) * 256) * HW;
-    if (whole_cta) convert_v_chunk<8>(src, vimg + (size_t)c * kStageBytes, p0 + (c & 3) * 32, HW, warp, lane);
-    else convert_v_chunk<4>(src, vimg + (size_t)c * kStageBytes, p0 + (c & 3) * 32, HW, warp - 4, lane);
   };
   int chunks_done = (I - 1 >= kMine - 1) ? 1 : kMine - (I - 1);   // what cannot be hidden behind iterations 0 .. I-2 is done here
   const bool windowed = p.windowed != 0;
@@ -785,11 +786,11 @@ static long long* g_prof = nullptr;
 void set_profile_buffer(void* dev) { g_prof = static_cast<long long*>(dev); }
 long long* get_profile_buffer() { return g_prof; }
 
-template <int CK, int LB>
+template <int CK, int LB, bool VPM>
 static int max_clusters_resident() {
   static int n = -1;
   if (n < 0) {
-    cudaFuncSetAttribute(em_pair_kernel<CK, LB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)em::smem_bytes<CK, LB>());
+    cudaFuncSetAttribute(em_pair_kernel<CK, LB, VPM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)em::smem_bytes<CK, LB>());
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * LB, 1, 1);
     cfg.blockDim = dim3(256, 1, 1);
@@ -802,7 +803,7 @@ static int max_clusters_resident() {
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     int clusters = 0;
-    if (cudaOccupancyMaxActiveClusters(&clusters, em_pair_kernel<CK, LB>, &cfg) != cudaSuccess || clusters <= 0) {
+    if (cudaOccupancyMaxActiveClusters(&clusters, em_pair_kernel<CK, LB, VPM>, &cfg) != cudaSuccess || clusters <= 0) {
       cudaGetLastError();
       int dev = 0, sms = 0;
       cudaGetDevice(&dev);
@@ -836,7 +837,7 @@ size_t fused_em_workspace(const SwemDims& d) {
   return bytes + 256;
 }
 
-template <int CK, int LB>
+template <int CK, int LB, bool VPM>
 static int fused_em_forward_t(const SwemEmArgs& a, cudaStream_t st) {
   const SwemDims& d = a.dims;
   const int U = d.B * d.N;
@@ -852,7 +853,7 @@ static int fused_em_forward_t(const SwemEmArgs& a, cudaStream_t st) {
 
   static bool attr_set = false;
   if (!attr_set) {
-    SWEM_CUDA(cudaFuncSetAttribute(em_pair_kernel<CK, LB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)em::smem_bytes<CK, LB>()));
+    SWEM_CUDA(cudaFuncSetAttribute(em_pair_kernel<CK, LB, VPM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)em::smem_bytes<CK, LB>()));
     attr_set = true;
   }
   EmPairParams p{};
@@ -862,40 +863,44 @@ static int fused_em_forward_t(const SwemEmArgs& a, cudaStream_t st) {
   p.vblob = vblob;
   p.acc_k = acc_k; p.acc_nu = acc_nu; p.counters = counters; p.status = status;
   p.N = d.N; p.HW = d.HW; p.T = T; p.n_iters = d.n_iters; p.L = d.L;
-  p.v_pixel_major = a.v_pixel_major;
   p.c1s = kLog2e / (d.tau * em::kKScale);
   p.prof = get_profile_buffer();
   // Windowed form (one launch per EM iteration + one for the outputs; the kernel boundary is the cross-tile barrier):
   // taken when the clusters of a unit cannot all be co-resident (large HW x L), or forced by SWEM_EM_WINDOWED=1 (tests).
   const char* force_w = getenv("SWEM_EM_WINDOWED");
-  if (max_clusters_resident<CK, LB>() < T || (force_w != nullptr && force_w[0] == '1')) {
+  if (max_clusters_resident<CK, LB, VPM>() < T || (force_w != nullptr && force_w[0] == '1')) {
     p.windowed = 1;
     p.u0 = 0;
     for (int it = 0; it <= d.n_iters; ++it) {
       p.it_begin = it;
-      em_pair_kernel<CK, LB><<<U * T * 2 * LB, 256, em::smem_bytes<CK, LB>(), st>>>(p);
+      em_pair_kernel<CK, LB, VPM><<<U * T * 2 * LB, 256, em::smem_bytes<CK, LB>(), st>>>(p);
       SWEM_LAUNCH_CHECK();
     }
     return SWEM_OK;
   }
   // Single-launch form: all CTAs of a launch spin on each other, so every launch must be co-resident (1 CTA per SM);
   // units that do not fit are spread evenly over the fewest launches
-  const int upl_max = max_clusters_resident<CK, LB>() / T;
+  const int upl_max = max_clusters_resident<CK, LB, VPM>() / T;
   const int n_launch = (U + upl_max - 1) / upl_max;
   const int upl = (U + n_launch - 1) / n_launch;
   for (int u0 = 0; u0 < U; u0 += upl) {
     const int nu = (U - u0 < upl) ? (U - u0) : upl;
     p.u0 = u0;
-    em_pair_kernel<CK, LB><<<nu * T * 2 * LB, 256, em::smem_bytes<CK, LB>(), st>>>(p);
+    em_pair_kernel<CK, LB, VPM><<<nu * T * 2 * LB, 256, em::smem_bytes<CK, LB>(), st>>>(p);
     SWEM_LAUNCH_CHECK();
   }
   return SWEM_OK;
 }
 
+template <bool VPM>
+static int fused_em_forward_v(const SwemEmArgs& a, cudaStream_t st) {
+  if (a.dims.L == 512) return a.dims.Ck == 128 ? fused_em_forward_t<128, 4, VPM>(a, st) : fused_em_forward_t<64, 4, VPM>(a, st);
+  if (a.dims.L == 256) return a.dims.Ck == 128 ? fused_em_forward_t<128, 2, VPM>(a, st) : fused_em_forward_t<64, 2, VPM>(a, st);
+  return a.dims.Ck == 128 ? fused_em_forward_t<128, 1, VPM>(a, st) : fused_em_forward_t<64, 1, VPM>(a, st);
+}
+
 int fused_em_forward(const SwemEmArgs& a, cudaStream_t st) {
-  if (a.dims.L == 512) return a.dims.Ck == 128 ? fused_em_forward_t<128, 4>(a, st) : fused_em_forward_t<64, 4>(a, st);
-  if (a.dims.L == 256) return a.dims.Ck == 128 ? fused_em_forward_t<128, 2>(a, st) : fused_em_forward_t<64, 2>(a, st);
-  return a.dims.Ck == 128 ? fused_em_forward_t<128, 1>(a, st) : fused_em_forward_t<64, 1>(a, st);
+  return a.v_pixel_major ? fused_em_forward_v<true>(a, st) : fused_em_forward_v<false>(a, st);
 }
 
 }  // namespace swem

@@ -1,4 +1,5 @@
-"""Run-to-run spread of the free-running mask agreement vs the CPU oracle (fused kernels: L2-atomic reduction order)."""
+"""Run-to-run spread of the free-running mask agreement vs the fp32 CPU oracle (fused kernels: L2-atomic reduction order),
+with the torch convolutions in fp32, in TF32 (torch's cuDNN default, what bench.py runs) and in TF32 with cuDNN autotuning."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -24,12 +25,21 @@ O.random_init = lambda *a, **k: (prior['kappa'], prior['nu'], prior['zita'])
 want = torch.stack(O.run_davis_sequence(oracle, frames, init, (h, w)))
 O.random_init = real
 fr, im = frames.to(DEV), init.to(DEV)
-for name, stages, path in (('engine+fused', FrameEngine(model), _lib.PATH_AUTO), ('modules+fused', model, _lib.PATH_AUTO),
-                           ('engine+generic', FrameEngine(model), _lib.PATH_GENERIC)):
-    model.swem_core.em_path = model.swem_core.readout_path = path
-    for rep in range(4):
-        with torch.no_grad():
-            got, _ = evaluate_davis_seq(stages, fr, [im] + [None] * (T - 1), (h, w))
-        got = torch.stack(got).cpu()
-        dis = 1 - (got == want).flatten(1).float().mean(dim=1)
-        print(f'{name:16s} rep {rep}: per-frame disagreement ' + ' '.join(f'{d:.1e}' for d in dis.tolist()) + f' | pooled {dis.mean():.1e} max {dis.max():.1e}', flush=True)
+modes = (('fp32 convs', False, False), ('fp32 convs + cudnn.benchmark', False, True),
+         ('tf32 convs (torch default)', True, False), ('tf32 convs + cudnn.benchmark', True, True))
+for conv_name, tf32, bench in modes:
+    torch.backends.cudnn.allow_tf32 = tf32
+    torch.backends.cuda.matmul.allow_tf32 = tf32
+    torch.backends.cudnn.benchmark = bench
+    print(f'== {conv_name}', flush=True)
+    for name, stages, path in (('engine+fused', FrameEngine(model), _lib.PATH_AUTO), ('modules+fused', model, _lib.PATH_AUTO),
+                               ('modules+generic', model, _lib.PATH_GENERIC), ('engine+generic', FrameEngine(model), _lib.PATH_GENERIC)):
+        if bench and name != 'engine+fused':
+            continue
+        model.swem_core.em_path = model.swem_core.readout_path = path
+        for rep in range(2):
+            with torch.no_grad():
+                got, _ = evaluate_davis_seq(stages, fr, [im] + [None] * (T - 1), (h, w))
+            got = torch.stack(got).cpu()
+            dis = 1 - (got == want).flatten(1).float().mean(dim=1)
+            print(f'{name:16s} rep {rep}: per-frame disagreement ' + ' '.join(f'{d:.1e}' for d in dis.tolist()) + f' | pooled {dis.mean():.1e} max {dis.max():.1e}', flush=True)

@@ -1,8 +1,8 @@
 #!/bin/bash
-# ncu evidence: launch list of the bench command + one --set full capture per hot kernel.  Output -> gpurun_out/
+# ncu evidence: launch list of the bench command (cuDNN autotuning off: its trial launches would flood the list) + one --set full capture per hot kernel.  Output -> gpurun_out/
 cd "$(dirname "$0")/.."
 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/r1_launches.csv \
-    python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
+    env SWEM_CUDNN_BENCHMARK=0 python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
 for k in em_pair_kernel readout_fused_kernel perm_inv_kernel; do
   ncu --set full --clock-control none --import-source on -k regex:$k -s 2 -c 1 -f -o gpurun_out/r1_$k \
       python tools/run_once.py > gpurun_out/ncu_$k.log 2>&1
