@@ -246,9 +246,10 @@ def run_b200(args, rank, world, local_rank):
     if use_engine:                                               # inference form of the torch stages (same weights, same function)
         from swem_b200.engine import FrameEngine
         stages = FrameEngine(model, channels_last=os.environ.get('SWEM_CHANNELS_LAST', '1') == '1',
-                             fused_conv=os.environ.get('SWEM_FUSED_CONV', '1') == '1')
+                             fused_conv=os.environ.get('SWEM_FUSED_CONV', '1') == '1',
+                             split_tf32=os.environ.get('SWEM_SPLIT_TF32', '0') == '1')
 
-    def run_phase(host_io, graphed, K=K):
+    def run_phase(host_io, graphed, K=K, stages=stages):
         """start on frame 0, Wm warm-up steps, then K timed steps; returns (ms, clocks, masks checksum).  Step k segments and
         memorizes frame 1 + Wm + k; with the pipelined runner it also encodes the key of frame 2 + Wm + k meanwhile."""
         pipe = graphed and use_pipe
@@ -309,19 +310,31 @@ def run_b200(args, rank, world, local_rank):
 
     fps = world * K / (ms_res / 1e3)
     fps_e2e = world * K / (ms_e2e / 1e3)
-    # pass 4 (N = 1 only, short): the same step with the torch convolutions in IEEE fp32 instead of torch's cuDNN default
-    # (TF32) -- the arithmetic in which the >= 99.9 % mask agreement with the fp32 CPU oracle is demonstrated
-    # (tests/test_gpu_parity.py; profiles/r1_agreement.txt has both modes, for the plain torch modules too)
-    fp32_convs = None
-    if world == 1 and conv_tf32 and not args.no_cpu_baseline:
+    # passes 4-5 (N = 1 only, short): the same step in the arithmetic of the mask-parity tests (tests/test_gpu_parity.py;
+    # profiles/r1_agreement.txt has every mode, for the plain torch modules too) -- convolutions at fp32 accuracy instead of
+    # torch's cuDNN default (TF32):  (4) FrameEngine(split_tf32=True): each conv as one TF32 tensor-core conv over
+    # [hi | hi | lo] operand splits, fp32-accurate;  (5) cuDNN's own IEEE-fp32 convolutions (no tensor cores on sm_100).
+    parity_mode, fp32_convs = None, None
+    if world == 1 and conv_tf32 and use_engine and not args.no_cpu_baseline:
+        from swem_b200.engine import FrameEngine
         torch.backends.cudnn.allow_tf32 = False
         torch.backends.cuda.matmul.allow_tf32 = False
-        k4 = min(K, 5)
-        ms_fp32, _, _ = run_phase(host_io=False, graphed=use_graph, K=k4)
+        split_stages = FrameEngine(model, channels_last=os.environ.get('SWEM_CHANNELS_LAST', '1') == '1',
+                                   fused_conv=os.environ.get('SWEM_FUSED_CONV', '1') == '1', split_tf32=True)
+        k4 = min(K, 10)
+        ms_split, _, _ = run_phase(host_io=False, graphed=use_graph, K=k4, stages=split_stages)
+        ms_split_e2e, _, _ = run_phase(host_io=True, graphed=use_graph, K=k4, stages=split_stages)
+        parity_mode = {'value': k4 / (ms_split / 1e3), 'unit': UNIT, 'steps': k4, 'ms_per_step': ms_split / k4,
+                       'e2e': {'value': k4 / (ms_split_e2e / 1e3), 'unit': UNIT, 'ms_per_step': ms_split_e2e / k4},
+                       'convs': 'FrameEngine(split_tf32=True): x = hi + lo, w = hi + lo on the TF32 grid, one cuDNN TF32 conv over '
+                                '[xh|xh|xl] x [wh;wl;wh] = conv(x, w) to 2^-22 (fp32 accumulate)',
+                       'mask_agreement_vs_fp32_cpu_oracle': '>= 99.95 % per frame (test_frame_engine_free_running_masks_vs_oracle[split_tf32])'}
+        k5 = min(K, 5)
+        ms_fp32, _, _ = run_phase(host_io=False, graphed=use_graph, K=k5)
         torch.backends.cudnn.allow_tf32 = True
         torch.backends.cuda.matmul.allow_tf32 = True
-        fp32_convs = {'value': k4 / (ms_fp32 / 1e3), 'unit': UNIT, 'steps': k4, 'ms_per_step': ms_fp32 / k4,
-                      'note': 'same step, cuDNN convolutions in IEEE fp32 (no tensor cores): the mode of the mask-parity tests'}
+        fp32_convs = {'value': k5 / (ms_fp32 / 1e3), 'unit': UNIT, 'steps': k5, 'ms_per_step': ms_fp32 / k5,
+                      'note': 'same step, cuDNN convolutions in IEEE fp32 (no tensor cores)'}
     peaks = measured_peaks()
     f_mem, f_read = hot_path_flops(n_obj, hw, 2 * CFG['n_bases'])
     b_mem, b_read = hot_path_bytes(n_obj, hw, 2 * CFG['n_bases'])
@@ -344,9 +357,10 @@ def run_b200(args, rank, world, local_rank):
                                           'torch_convs': ('cudnn ' + ('TF32 (torch default allow_tf32)' if conv_tf32 else 'IEEE fp32')
                                                           + (', autotuned (cudnn.benchmark)' if cudnn_autotune else ', heuristic algos')
                                                           + ', channels_last=' + os.environ.get('SWEM_CHANNELS_LAST', '1')),
-                                          'mask_agreement_vs_fp32_cpu_oracle': 'fp32 convs: >= 99.94 % per frame; TF32 convs: 80-92 % for '
-                                          'FrameEngine AND for the plain torch modules with all-fp32 memory kernels (random-init decoder: argmax '
-                                          'margins at TF32 noise level) -- profiles/r1_agreement.txt',
+                                          'mask_agreement_vs_fp32_cpu_oracle': 'fp32-accurate convs (parity_mode / fp32_convs below): >= 99.94 % per '
+                                          'frame; TF32 convs (this headline, torch default = what the reference does on a GPU): 80-92 % for FrameEngine '
+                                          'AND for the plain torch modules with all-fp32 memory kernels (random-init decoder: argmax margins at TF32 '
+                                          'noise level) -- profiles/r1_agreement.txt',
                                           'torch_stages': ('FrameEngine (BN folded, fused conv+bias+relu=' + os.environ.get('SWEM_FUSED_CONV', '1')
                                                            + ', object-independent conv halves computed once per frame)') if use_engine
                                                           else 'plain nn.Modules'}),
@@ -367,7 +381,8 @@ def run_b200(args, rank, world, local_rank):
                                   'hbm_gbs': (b_mem + b_read) / hot_s / 1e9, 'hbm_frac': (b_mem + b_read) / hot_s / 1e9 / peaks['hbm'],
                                   'share_of_eager_step': (em_ms + read_ms) / (ms_eager / K)}},
     }
-    if fp32_convs is not None:
+    if parity_mode is not None:
+        line['parity_mode'] = parity_mode
         line['fp32_convs'] = fp32_convs
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         steps = args.cpu_steps

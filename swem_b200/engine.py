@@ -56,11 +56,15 @@ def _fold_bn(conv, bn) -> Tuple[torch.Tensor, torch.Tensor]:
 
 
 class FrameEngine:
-    def __init__(self, model, channels_last: bool = True, fused_conv: bool = True, stage_kernels: bool = True):
+    def __init__(self, model, channels_last: bool = True, fused_conv: bool = True, stage_kernels: bool = True,
+                 split_tf32: bool = False):
         self.model = model
         self.channels_last = channels_last
         self.fused_conv = fused_conv
         self.stage_kernels = stage_kernels and channels_last     # the decoder glue kernels of libswem_b200 are NHWC
+        # fp32-accurate convolutions ON the tensor cores: every conv as three TF32 convs over hi / lo splits (see _conv_split)
+        self.split_tf32 = split_tf32
+        self._wsplit_cache = {}
         self._built = False
 
     # ------------------------------------------------------------------------------------------
@@ -144,6 +148,7 @@ class FrameEngine:
         m = self.model
         if m.training:
             raise RuntimeError('FrameEngine is inference-only: call model.eval() first')
+        self._wsplit_cache.clear()
         ke, ve, dec = m.key_encoder, m.value_encoder, m.decoder
         self.k_stem = self._folded(ke.conv1, ke.bn1)
         self.k_stem_s2d = self._s2d_stem(ke.conv1, ke.bn1, ke)
@@ -216,7 +221,52 @@ class FrameEngine:
     # ------------------------------------------------------------------------------------------
     # conv helpers
     # ------------------------------------------------------------------------------------------
+    @staticmethod
+    def _tf32_split(t: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        """t = hi + lo with hi exactly representable in TF32 (10 mantissa bits, round to nearest) and lo the fp32 residual."""
+        hi = ((t.view(torch.int32) + 0x1000) & -0x2000).view(torch.float32)
+        return hi, t - hi
+
+    def _split3(self, x: torch.Tensor) -> torch.Tensor:
+        """x (N,C,H,W) -> (N,3C,H,W) = [hi | hi | lo] along the channels (``swem_tf32_split3`` for NHWC tensors)."""
+        n, c, h, w = x.shape
+        if self._glue_ok(x) and c % 4 == 0 and x.is_contiguous(memory_format=torch.channels_last):
+            out = torch.empty((n, 3 * c, h, w), device=x.device, dtype=torch.float32, memory_format=torch.channels_last)
+            with torch.cuda.device(x.device):
+                rc = _lib.load().swem_tf32_split3(x.data_ptr(), n * h * w, c, out.data_ptr(),
+                                                  torch.cuda.current_stream(x.device).cuda_stream)
+            _lib.check(rc, 'swem_tf32_split3')
+            return out
+        hi, lo = self._tf32_split(x)
+        out = torch.cat([hi, hi, lo], dim=1)
+        return out.contiguous(memory_format=torch.channels_last) if self.channels_last else out
+
+    def _conv_split(self, x, p: ConvP, relu: bool, add: Optional[torch.Tensor]):
+        """conv(x, w) to fp32 accuracy on the tensor cores: x = xh + xl, w = wh + wl (hi parts exactly representable in
+        TF32), conv(x, w) = conv(xh, wh) + conv(xh, wl) + conv(xl, wh) + O(2^-22) -- the hi x hi products are exact in the
+        fp32 accumulator, the cross terms carry a relative rounding of 2^-11 on a term that is 2^-11 of the result.  Issued
+        as ONE cuDNN TF32 convolution over the input channels [xh | xh | xl] against [wh ; wl ; wh], so the three terms add
+        up inside the MMA accumulator and the fused bias / residual / ReLU epilogues stay.  cuDNN's IEEE-fp32 path has no
+        tensor cores on sm_100 (100x slower than TF32 with its heuristic algorithms, 18x autotuned); this costs 3-4x."""
+        w, b, s, pad = p
+        key = w.data_ptr()
+        if key not in self._wsplit_cache:
+            wh, wl = self._tf32_split(w)
+            self._wsplit_cache[key] = (w, self._w(torch.cat([wh, wl, wh], dim=1)))   # (keeps `w` alive: the pointer stays unique)
+        w3 = self._wsplit_cache[key][1]
+        old = torch.backends.cudnn.allow_tf32
+        torch.backends.cudnn.allow_tf32 = True
+        try:
+            return self._conv_plain(self._split3(x), (w3, b, s, pad), relu, add)
+        finally:
+            torch.backends.cudnn.allow_tf32 = old
+
     def _conv(self, x, p: ConvP, relu: bool = False, add: Optional[torch.Tensor] = None):
+        if self.split_tf32 and x.is_cuda:
+            return self._conv_split(x, p, relu, add)
+        return self._conv_plain(x, p, relu, add)
+
+    def _conv_plain(self, x, p: ConvP, relu: bool = False, add: Optional[torch.Tensor] = None):
         w, b, s, pad = p
         if self.fused_conv and relu and x.is_cuda and b is not None:
             if add is None:

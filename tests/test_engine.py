@@ -69,3 +69,22 @@ def test_engine_is_inference_only():
     eng = FrameEngine(model.eval(), channels_last=False)
     with pytest.raises(RuntimeError):
         eng('encode_key', torch.rand(1, 3, 32, 32))        # grad mode on
+
+
+def test_tf32_split_conv_identity():
+    """The algebra behind FrameEngine(split_tf32=True): with x = xh + xl, w = wh + wl (hi parts on the TF32 grid),
+    conv([xh | xh | xl], [wh ; wl ; wh]) = conv(x, w) - conv(xl, wl), i.e. fp32-accurate; the hi parts have 13 zero
+    low mantissa bits (a TF32 tensor core takes them unchanged) and hi + lo reproduces the input exactly."""
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(2, 8, 9, 11, generator=g) * 3
+    w = torch.randn(6, 8, 3, 3, generator=g) * 0.2
+    xh, xl = FrameEngine._tf32_split(x)
+    wh, wl = FrameEngine._tf32_split(w)
+    assert torch.equal(xh + xl, x) and torch.equal(wh + wl, w)
+    assert int((xh.view(torch.int32) & 0x1fff).abs().max()) == 0 and int((wh.view(torch.int32) & 0x1fff).abs().max()) == 0
+    assert (xl.abs() <= x.abs() * 2.0 ** -11 + 1e-30).all()
+    conv = torch.nn.functional.conv2d
+    want = conv(x.double(), w.double(), padding=1)
+    got = conv(torch.cat([xh, xh, xl], 1).double(), torch.cat([wh, wl, wh], 1).double(), padding=1)
+    assert _rel(got, want) < 2.0 ** -20
+    assert _rel(conv(xh.double(), wh.double(), padding=1), want) > 2.0 ** -14      # a single TF32 conv is 1e-4 .. 1e-3 off

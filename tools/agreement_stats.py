@@ -25,6 +25,16 @@ O.random_init = lambda *a, **k: (prior['kappa'], prior['nu'], prior['zita'])
 want = torch.stack(O.run_davis_sequence(oracle, frames, init, (h, w)))
 O.random_init = real
 fr, im = frames.to(DEV), init.to(DEV)
+torch.backends.cudnn.benchmark = True
+print('== split-TF32 convs (3 TF32 convs over hi/lo splits, FrameEngine(split_tf32=True)) + cudnn.benchmark', flush=True)
+eng = FrameEngine(model, split_tf32=True)
+for rep in range(3):
+    with torch.no_grad():
+        got, _ = evaluate_davis_seq(eng, fr, [im] + [None] * (T - 1), (h, w))
+    got = torch.stack(got).cpu()
+    dis = 1 - (got == want).flatten(1).float().mean(dim=1)
+    print(f'engine+fused     rep {rep}: per-frame disagreement ' + ' '.join(f'{d:.1e}' for d in dis.tolist()) + f' | pooled {dis.mean():.1e} max {dis.max():.1e}', flush=True)
+torch.backends.cudnn.benchmark = False
 modes = (('fp32 convs', False, False), ('fp32 convs + cudnn.benchmark', False, True),
          ('tf32 convs (torch default)', True, False), ('tf32 convs + cudnn.benchmark', True, True))
 for conv_name, tf32, bench in modes:
