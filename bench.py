@@ -326,8 +326,8 @@ def run_b200(args, rank, world, local_rank):
         ms_split_e2e, _, _ = run_phase(host_io=True, graphed=use_graph, K=k4, stages=split_stages)
         parity_mode = {'value': k4 / (ms_split / 1e3), 'unit': UNIT, 'steps': k4, 'ms_per_step': ms_split / k4,
                        'e2e': {'value': k4 / (ms_split_e2e / 1e3), 'unit': UNIT, 'ms_per_step': ms_split_e2e / k4},
-                       'convs': 'FrameEngine(split_tf32=True): x = hi + lo, w = hi + lo on the TF32 grid, one cuDNN TF32 conv over '
-                                '[xh|xh|xl] x [wh;wl;wh] = conv(x, w) to 2^-22 (fp32 accumulate)',
+                       'convs': 'FrameEngine(split_tf32=True): x = hi + lo, w = hi + lo on the TF32 grid, conv(x, w) = cuDNN TF32 '
+                                'conv(xh, wh) + conv([xh|xl], [wl;wh]) to 2^-22 (fp32 accumulate, cross terms summed on their own)',
                        'mask_agreement_vs_fp32_cpu_oracle': '>= 99.95 % per frame (test_frame_engine_free_running_masks_vs_oracle[split_tf32])'}
         k5 = min(K, 5)
         ms_fp32, _, _ = run_phase(host_io=False, graphed=use_graph, K=k5)

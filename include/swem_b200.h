@@ -216,10 +216,10 @@ int swem_stem_input(const float* frame, const float* masks, const float* mean3, 
  * in [N, H, W, C] -> out [N, (H-1)/2+1, (W-1)/2+1, C].                                                           */
 int swem_maxpool3x3s2(const float* in, int32_t N, int32_t H, int32_t W, int32_t C, float* out, void* stream);
 /* Operand split for fp32-accurate convolutions on the TF32 tensor cores (FrameEngine(split_tf32=True)): per pixel of an NHWC
- * tensor x [pixels, C] writes out [pixels, 3C] = [hi | hi | lo] with hi = x rounded to TF32 (10 mantissa bits, nearest) and
- * lo = x - hi, so that ONE cuDNN TF32 convolution against the weights stacked along the input channels [w_hi ; w_lo ; w_hi]
- * accumulates x_hi w_hi + x_hi w_lo + x_lo w_hi in its fp32 accumulator (= conv(x, w) up to 2^-22).  C % 4 == 0.           */
-int swem_tf32_split3(const float* x, int64_t pixels, int32_t C, float* out, void* stream);
+ * tensor x [pixels, C] writes hi [pixels, C] = x rounded to TF32 (10 mantissa bits, nearest) and hl [pixels, 2C] = [hi | lo],
+ * lo = x - hi.  conv(x, w) = conv(hi, w_hi) + conv([hi | lo], [w_lo ; w_hi]) + O(2^-22): two cuDNN TF32 convolutions, the
+ * small cross terms accumulated on their own (added to the main term in fp32 by the fused conv + add epilogue).  C % 4 == 0. */
+int swem_tf32_split(const float* x, int64_t pixels, int32_t C, float* hi, float* hl, void* stream);
 
 /* ---- misc ------------------------------------------------------------------------------------ */
 int         swem_abi_version(void);          /* == SWEM_B200_ABI_VERSION                          */

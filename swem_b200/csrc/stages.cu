@@ -124,21 +124,21 @@ __global__ void __launch_bounds__(256) upsample2x_add_kernel(const float4* __res
   }
 }
 
-// x [pixels][C4] -> out [pixels][3 C4] = [hi | hi | lo], hi = x rounded to TF32 (sign-magnitude bit pattern + half ulp,
-// low 13 mantissa bits cleared), lo = x - hi (exact in fp32)
+// x [pixels][C4] -> hi [pixels][C4] and hl [pixels][2 C4] = [hi | lo]; hi = x rounded to TF32 (sign-magnitude bit pattern +
+// half ulp, low 13 mantissa bits cleared), lo = x - hi (exact in fp32)
 __device__ __forceinline__ float tf32_hi(float v) { return __int_as_float((__float_as_int(v) + 0x1000) & ~0x1fff); }
-__global__ void __launch_bounds__(256) tf32_split3_kernel(const float4* __restrict__ x, long long total4, int C4,
-                                                          float4* __restrict__ out) {
+__global__ void __launch_bounds__(256) tf32_split_kernel(const float4* __restrict__ x, long long total4, int C4,
+                                                         float4* __restrict__ hi_out, float4* __restrict__ hl_out) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total4) return;
   const long long px = idx / C4;
   const int c4 = (int)(idx - px * C4);
   const float4 v = __ldg(x + idx);
   const float4 hi = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
-  float4* o = out + px * 3 * C4 + c4;
+  hi_out[idx] = hi;
+  float4* o = hl_out + px * 2 * C4 + c4;
   o[0] = hi;
-  o[C4] = hi;
-  o[2 * C4] = make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w);
+  o[C4] = make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w);
 }
 
 __global__ void __launch_bounds__(256) bias_add_act_kernel(const float4* __restrict__ a, const float4* __restrict__ b,
@@ -585,14 +585,14 @@ int swem_maxpool3x3s2(const float* in, int32_t N, int32_t H, int32_t W, int32_t 
   return SWEM_OK;
 }
 
-int swem_tf32_split3(const float* x, int64_t pixels, int32_t C, float* out, void* stream) {
+int swem_tf32_split(const float* x, int64_t pixels, int32_t C, float* hi, float* hl, void* stream) {
   reset_launch_count();
-  SWEM_CHECK_ARG(x && out, "NULL pointer");
+  SWEM_CHECK_ARG(x && hi && hl, "NULL pointer");
   SWEM_CHECK_ARG(pixels > 0 && C > 0 && C % 4 == 0 && pixels * (C / 4) < (1ll << 40), "bad sizes pixels=%lld C=%d (C must be a multiple of 4)",
                  (long long)pixels, C);
   const long long total4 = pixels * (C / 4);
-  tf32_split3_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const float4*>(x), total4, C / 4, reinterpret_cast<float4*>(out));
+  tf32_split_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const float4*>(x), total4, C / 4, reinterpret_cast<float4*>(hi), reinterpret_cast<float4*>(hl));
   SWEM_LAUNCH_CHECK();
   return SWEM_OK;
 }

@@ -227,37 +227,48 @@ class FrameEngine:
         hi = ((t.view(torch.int32) + 0x1000) & -0x2000).view(torch.float32)
         return hi, t - hi
 
-    def _split3(self, x: torch.Tensor) -> torch.Tensor:
-        """x (N,C,H,W) -> (N,3C,H,W) = [hi | hi | lo] along the channels (``swem_tf32_split3`` for NHWC tensors)."""
+    def _split(self, x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        """x (N,C,H,W) -> hi (N,C,H,W), [hi | lo] (N,2C,H,W)  (``swem_tf32_split`` for NHWC tensors)."""
         n, c, h, w = x.shape
         if self._glue_ok(x) and c % 4 == 0 and x.is_contiguous(memory_format=torch.channels_last):
-            out = torch.empty((n, 3 * c, h, w), device=x.device, dtype=torch.float32, memory_format=torch.channels_last)
+            hi = torch.empty_like(x)
+            hl = torch.empty((n, 2 * c, h, w), device=x.device, dtype=torch.float32, memory_format=torch.channels_last)
             with torch.cuda.device(x.device):
-                rc = _lib.load().swem_tf32_split3(x.data_ptr(), n * h * w, c, out.data_ptr(),
-                                                  torch.cuda.current_stream(x.device).cuda_stream)
-            _lib.check(rc, 'swem_tf32_split3')
-            return out
+                rc = _lib.load().swem_tf32_split(x.data_ptr(), n * h * w, c, hi.data_ptr(), hl.data_ptr(),
+                                                 torch.cuda.current_stream(x.device).cuda_stream)
+            _lib.check(rc, 'swem_tf32_split')
+            return hi, hl
         hi, lo = self._tf32_split(x)
-        out = torch.cat([hi, hi, lo], dim=1)
-        return out.contiguous(memory_format=torch.channels_last) if self.channels_last else out
+        hl = torch.cat([hi, lo], dim=1)
+        return (self._cl(hi), self._cl(hl)) if self.channels_last else (hi, hl)
 
     def _conv_split(self, x, p: ConvP, relu: bool, add: Optional[torch.Tensor]):
         """conv(x, w) to fp32 accuracy on the tensor cores: x = xh + xl, w = wh + wl (hi parts exactly representable in
-        TF32), conv(x, w) = conv(xh, wh) + conv(xh, wl) + conv(xl, wh) + O(2^-22) -- the hi x hi products are exact in the
+        TF32), conv(x, w) = conv(xh, wh) + [conv(xh, wl) + conv(xl, wh)] + O(2^-22) -- the hi x hi products are exact in the
         fp32 accumulator, the cross terms carry a relative rounding of 2^-11 on a term that is 2^-11 of the result.  Issued
-        as ONE cuDNN TF32 convolution over the input channels [xh | xh | xl] against [wh ; wl ; wh], so the three terms add
-        up inside the MMA accumulator and the fused bias / residual / ReLU epilogues stay.  cuDNN's IEEE-fp32 path has no
-        tensor cores on sm_100 (100x slower than TF32 with its heuristic algorithms, 18x autotuned); this costs 3-4x."""
+        as TWO cuDNN TF32 convolutions: the cross terms as one conv over [xh | xl] against [wl ; wh], then the main term
+        with the cross sum (and the residual, bias, ReLU) in its fused epilogue.  Cross terms accumulate on their own: fed
+        through the same accumulator as the main term (one conv over [xh | xh | xl]) every small product is truncated at the
+        big sum's ulp -- 3x the error, enough to cost 0.3 % of the masks (tools/split_conv_probe.py).  cuDNN's IEEE-fp32
+        path has no tensor cores on sm_100 (100x slower than TF32 with its heuristic algorithms, 18x autotuned)."""
         w, b, s, pad = p
         key = w.data_ptr()
         if key not in self._wsplit_cache:
             wh, wl = self._tf32_split(w)
-            self._wsplit_cache[key] = (w, self._w(torch.cat([wh, wl, wh], dim=1)))   # (keeps `w` alive: the pointer stays unique)
-        w3 = self._wsplit_cache[key][1]
+            zero = torch.zeros(w.shape[0], device=w.device, dtype=torch.float32)
+            self._wsplit_cache[key] = (w, self._w(wh), self._w(torch.cat([wl, wh], dim=1)), zero)   # (keeps `w` alive: unique pointer)
+        _, wh, wc, zero = self._wsplit_cache[key]
+        hi, hl = self._split(x)
         old = torch.backends.cudnn.allow_tf32
         torch.backends.cudnn.allow_tf32 = True
         try:
-            return self._conv_plain(self._split3(x), (w3, b, s, pad), relu, add)
+            cross = F.conv2d(hl, wc, None, stride=s, padding=pad)
+            if add is not None:
+                cross.add_(add)
+            if relu and self.fused_conv and x.is_cuda:
+                return torch.cudnn_convolution_add_relu(hi, wh, cross, 1.0, zero if b is None else b, (s, s), (pad, pad), (1, 1), 1)
+            y = F.conv2d(hi, wh, b, stride=s, padding=pad).add_(cross)
+            return F.relu_(y) if relu else y
         finally:
             torch.backends.cudnn.allow_tf32 = old
 

@@ -73,7 +73,7 @@ def test_engine_is_inference_only():
 
 def test_tf32_split_conv_identity():
     """The algebra behind FrameEngine(split_tf32=True): with x = xh + xl, w = wh + wl (hi parts on the TF32 grid),
-    conv([xh | xh | xl], [wh ; wl ; wh]) = conv(x, w) - conv(xl, wl), i.e. fp32-accurate; the hi parts have 13 zero
+    conv(xh, wh) + conv([xh | xl], [wl ; wh]) = conv(x, w) - conv(xl, wl), i.e. fp32-accurate; the hi parts have 13 zero
     low mantissa bits (a TF32 tensor core takes them unchanged) and hi + lo reproduces the input exactly."""
     g = torch.Generator().manual_seed(0)
     x = torch.randn(2, 8, 9, 11, generator=g) * 3
@@ -85,6 +85,6 @@ def test_tf32_split_conv_identity():
     assert (xl.abs() <= x.abs() * 2.0 ** -11 + 1e-30).all()
     conv = torch.nn.functional.conv2d
     want = conv(x.double(), w.double(), padding=1)
-    got = conv(torch.cat([xh, xh, xl], 1).double(), torch.cat([wh, wl, wh], 1).double(), padding=1)
+    got = conv(xh.double(), wh.double(), padding=1) + conv(torch.cat([xh, xl], 1).double(), torch.cat([wl, wh], 1).double(), padding=1)
     assert _rel(got, want) < 2.0 ** -20
     assert _rel(conv(xh.double(), wh.double(), padding=1), want) > 2.0 ** -14      # a single TF32 conv is 1e-4 .. 1e-3 off

@@ -504,8 +504,8 @@ def test_frame_engine_matches_modules(fused_conv, split):
                 m.running_var.copy_(torch.rand(m.num_features, generator=g) * 0.5 + 0.75)
         eng = FrameEngine(model, channels_last=True, fused_conv=fused_conv, split_tf32=split)
         # split_tf32: products are exact, but a tensor core's fp32 accumulator truncates where an FFMA chain rounds --
-        # 1e-4 after ~50 layers of K = 576 .. 9216 (a single TF32 conv per layer is at 1e-2 there)
-        tol = 1e-3 if split else 1e-4
+        # 5e-5 after ~50 layers of K = 576 .. 9216 (a single TF32 conv per layer is at 1e-2 there)
+        tol = 3e-4 if split else 1e-4
         N, h, w = 3, 240, 432
         frames, init = davis_sequence(3, N, seed=2, size=(h, w))
         frames, init = frames.to(DEV), init.to(DEV)

@@ -47,16 +47,21 @@ def main():
     mine = assign_sequences(costs, world)[rank]
     data = {i: ytvos_materialise(specs[i]) for i in mine}              # host tensors, built before the clock starts
 
-    def run(i):
+    def run(i, max_t=None):
         frames, init = data[i]
+        if max_t is not None:
+            frames, init = frames[:, :max_t], init[:max_t]
         init = [None if m is None else m.to(dev) for m in init]
         torch.manual_seed(100 + i)
         preds = evaluate_ytvos_seq(engine, frames.to(dev), init, (specs[i]['h'], specs[i]['w']))
         return {'frames': len(preds), 'checksum': int(sum(int(p.sum()) for p in preds))}
 
+    # cuDNN times its candidate algorithms once per conv shape (frame size x object count): the warm-up below meets every
+    # shape of this rank's sequences (first frames + the frames around a late object) before the clock starts
+    torch.backends.cudnn.benchmark = os.environ.get('SWEM_CUDNN_BENCHMARK', '1') == '1'
     with torch.no_grad():
-        if mine:
-            run(mine[0])                                               # warm-up: cuDNN heuristics, allocator, lazy module load
+        for i in mine:                                                 # warm-up: cuDNN algorithms, allocator, lazy module load
+            run(i, max_t=min(specs[i]['t'], specs[i]['late_frame'] + 3))
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
