@@ -26,7 +26,7 @@ want = torch.stack(O.run_davis_sequence(oracle, frames, init, (h, w)))
 O.random_init = real
 fr, im = frames.to(DEV), init.to(DEV)
 torch.backends.cudnn.benchmark = True
-print('== split-TF32 convs (3 TF32 convs over hi/lo splits, FrameEngine(split_tf32=True)) + cudnn.benchmark', flush=True)
+print('== split-TF32 convs (main + cross-term TF32 convs over hi/lo splits, FrameEngine(split_tf32=True)) + cudnn.benchmark', flush=True)
 eng = FrameEngine(model, split_tf32=True)
 for rep in range(3):
     with torch.no_grad():

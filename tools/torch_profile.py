@@ -11,7 +11,11 @@ from swem_b200.synthetic import davis_sequence
 dev = torch.device('cuda:0')
 torch.manual_seed(0)
 model = SWEM(make_config(keydim=64, n_bases=128, n_iters=4, topl=64)).eval().to(dev).to(memory_format=torch.channels_last)
-eng = FrameEngine(model)
+split = os.environ.get('SWEM_SPLIT_TF32', '0') == '1'           # parity mode: fp32-accurate convs as two TF32 convs
+torch.backends.cudnn.benchmark = os.environ.get('SWEM_CUDNN_BENCHMARK', '1') == '1'
+if split:
+    torch.backends.cudnn.allow_tf32 = False
+eng = FrameEngine(model, split_tf32=split)
 frames, init = davis_sequence(8, 5, seed=1)
 frames, init = frames.to(dev), init.to(dev)
 runner = SequenceRunner(eng, (480, 864))
