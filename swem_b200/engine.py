@@ -65,6 +65,7 @@ class FrameEngine:
         # fp32-accurate convolutions ON the tensor cores: every conv as three TF32 convs over hi / lo splits (see _conv_split)
         self.split_tf32 = split_tf32
         self._wsplit_cache = {}
+        self._split_memo = []                                     # the last two split activations: (tensor, version, hi, [hi | lo])
         self._built = False
 
     # ------------------------------------------------------------------------------------------
@@ -149,6 +150,7 @@ class FrameEngine:
         if m.training:
             raise RuntimeError('FrameEngine is inference-only: call model.eval() first')
         self._wsplit_cache.clear()
+        self._split_memo = []
         ke, ve, dec = m.key_encoder, m.value_encoder, m.decoder
         self.k_stem = self._folded(ke.conv1, ke.bn1)
         self.k_stem_s2d = self._s2d_stem(ke.conv1, ke.bn1, ke)
@@ -228,7 +230,16 @@ class FrameEngine:
         return hi, t - hi
 
     def _split(self, x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
-        """x (N,C,H,W) -> hi (N,C,H,W), [hi | lo] (N,2C,H,W)  (``swem_tf32_split`` for NHWC tensors)."""
+        """x (N,C,H,W) -> hi (N,C,H,W), [hi | lo] (N,2C,H,W)  (``swem_tf32_split`` for NHWC tensors).  A block input feeds
+        two convolutions (conv1 and the shortcut; the object-independent halves of the fuser): the last two splits are kept."""
+        for ref, ver, hi, hl in self._split_memo:
+            if ref is x and ver == x._version:
+                return hi, hl
+        hi, hl = self._split_uncached(x)
+        self._split_memo = self._split_memo[-1:] + [(x, x._version, hi, hl)]
+        return hi, hl
+
+    def _split_uncached(self, x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
         n, c, h, w = x.shape
         if self._glue_ok(x) and c % 4 == 0 and x.is_contiguous(memory_format=torch.channels_last):
             hi = torch.empty_like(x)

@@ -482,6 +482,38 @@ def test_cuda_graph_runner_matches_eager_runner():
     assert torch.equal(outs[0], outs[1])
 
 
+def test_cuda_graph_runner_captures_cluster_launches():
+    """L = 256: the EM kernel runs as 4-CTA clusters and the readout as 2-CTA clusters launched with a cluster attribute
+    (cudaLaunchKernelEx); both must survive stream capture and replay.  The fused family carries its reduction-order
+    noise, so the graphed run is held to the eager run's masks on >= 99.5 % of the pixels of every frame."""
+    from swem_b200 import SWEM, make_config
+    from swem_b200.evaluator import GraphedSequenceRunner, SequenceRunner
+    from swem_b200.synthetic import davis_sequence
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        torch.manual_seed(0)
+        model = SWEM(make_config(keydim=64, n_bases=256, n_iters=3, topl=64)).eval().to(DEV)
+        assert _fused_covers(B=1, N=3, Ck=64, Cv=512, HW=15 * 27, L=256, n_iters=3) and \
+            _fused_covers(B=1, N=3, Ck=64, Cv=512, HW=15 * 27, L=256, n_iters=3, what='readout')
+        T, N, h, w = 7, 3, 240, 432
+        frames, init = davis_sequence(T, N, seed=2, size=(h, w))
+        frames, init = frames.to(DEV), init.to(DEV)
+        prior = O.random_init(1, N, 64, 256, 512, generator=torch.Generator().manual_seed(4))
+        model.swem_core.random_init = lambda size, norm_dim=-2, dtype=None, device=None: tuple(t.to(device) for t in prior)
+        outs = []
+        for cls in (SequenceRunner, GraphedSequenceRunner):
+            runner = cls(model, (h, w))
+            runner.start(frames[:, 0], init)
+            outs.append(torch.stack([runner.step(frames[:, i]).clone() for i in range(1, T)]).cpu())
+            model.swem_core.static_banks = False
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    agree = (outs[0] == outs[1]).flatten(1).float().mean(dim=1)
+    check('graph_vs_eager', 1.0 - agree.min().item(), 5e-3)
+
+
 @pytest.mark.parametrize('fused_conv,split', [(False, False), (True, False), (True, True)], ids=['plain', 'fused', 'split_tf32'])
 def test_frame_engine_matches_modules(fused_conv, split):
     """FrameEngine (BN folded, fused cuDNN conv+bias+relu, object-independent conv halves shared, readout into the
