@@ -247,7 +247,8 @@ def run_b200(args, rank, world, local_rank):
         from swem_b200.engine import FrameEngine
         stages = FrameEngine(model, channels_last=os.environ.get('SWEM_CHANNELS_LAST', '1') == '1',
                              fused_conv=os.environ.get('SWEM_FUSED_CONV', '1') == '1',
-                             split_tf32=os.environ.get('SWEM_SPLIT_TF32', '0') == '1')
+                             split_tf32=os.environ.get('SWEM_SPLIT_TF32', '0') == '1',
+                             cross_bf16=os.environ.get('SWEM_CROSS_BF16', '1') == '1')
 
     def run_phase(host_io, graphed, K=K, stages=stages):
         """start on frame 0, Wm warm-up steps, then K timed steps; returns (ms, clocks, masks checksum).  Step k segments and
@@ -320,15 +321,18 @@ def run_b200(args, rank, world, local_rank):
         torch.backends.cudnn.allow_tf32 = False
         torch.backends.cuda.matmul.allow_tf32 = False
         split_stages = FrameEngine(model, channels_last=os.environ.get('SWEM_CHANNELS_LAST', '1') == '1',
-                                   fused_conv=os.environ.get('SWEM_FUSED_CONV', '1') == '1', split_tf32=True)
+                                   fused_conv=os.environ.get('SWEM_FUSED_CONV', '1') == '1', split_tf32=True,
+                                   cross_bf16=os.environ.get('SWEM_CROSS_BF16', '1') == '1')
         k4 = min(K, 10)
         ms_split, _, _ = run_phase(host_io=False, graphed=use_graph, K=k4, stages=split_stages)
         ms_split_e2e, _, _ = run_phase(host_io=True, graphed=use_graph, K=k4, stages=split_stages)
         parity_mode = {'value': k4 / (ms_split / 1e3), 'unit': UNIT, 'steps': k4, 'ms_per_step': ms_split / k4,
                        'e2e': {'value': k4 / (ms_split_e2e / 1e3), 'unit': UNIT, 'ms_per_step': ms_split_e2e / k4},
-                       'convs': 'FrameEngine(split_tf32=True): x = hi + lo, w = hi + lo on the TF32 grid, conv(x, w) = cuDNN TF32 '
-                                'conv(xh, wh) + conv([xh|xl], [wl;wh]) to 2^-22 (fp32 accumulate, cross terms summed on their own)',
-                       'mask_agreement_vs_fp32_cpu_oracle': '>= 99.95 % per frame (test_frame_engine_free_running_masks_vs_oracle[split_tf32])'}
+                       'convs': 'FrameEngine(split_tf32=True, cross_bf16=' + os.environ.get('SWEM_CROSS_BF16', '1') + '): x = hi + lo, w = hi + lo '
+                                'on the TF32 grid, conv(x, w) = cuDNN TF32 conv(xh, wh) + cross terms conv([x|xl], [wl;wh]) (bf16 operands when '
+                                'cross_bf16: they are 2^-11 of the result) -- 2e-6 .. 1e-5 of fp64 per conv like cuDNN fp32 (tools/split_conv_probe.py)',
+                       'mask_agreement_vs_fp32_cpu_oracle': '>= 99.93 % per frame (test_frame_engine_free_running_masks_vs_oracle'
+                                                            '[split_tf32 / split_tf32_bf16cross])'}
         k5 = min(K, 5)
         ms_fp32, _, _ = run_phase(host_io=False, graphed=use_graph, K=k5)
         torch.backends.cudnn.allow_tf32 = True

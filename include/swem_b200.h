@@ -220,6 +220,10 @@ int swem_maxpool3x3s2(const float* in, int32_t N, int32_t H, int32_t W, int32_t 
  * lo = x - hi.  conv(x, w) = conv(hi, w_hi) + conv([hi | lo], [w_lo ; w_hi]) + O(2^-22): two cuDNN TF32 convolutions, the
  * small cross terms accumulated on their own (added to the main term in fp32 by the fused conv + add epilogue).  C % 4 == 0. */
 int swem_tf32_split(const float* x, int64_t pixels, int32_t C, float* hi, float* hl, void* stream);
+/* Same split with the cross-term operand in bf16: xl [pixels, 2C] bf16 = [bf16(x) | bf16(x - hi)].  The cross terms are
+ * 2^-11 of the result, so 8 mantissa bits on their operands (and on their bf16 sum) still leave it at 2^-20, and their
+ * convolution runs at twice the TF32 rate on half the bytes.                                                              */
+int swem_tf32_split_bf16(const float* x, int64_t pixels, int32_t C, float* hi, void* xl_bf16, void* stream);
 
 /* ---- misc ------------------------------------------------------------------------------------ */
 int         swem_abi_version(void);          /* == SWEM_B200_ABI_VERSION                          */

@@ -14,6 +14,8 @@
 // convolutions that produced lo_a / lo_b / skip are passed here as one per-channel vector (bilinear interpolation
 // reproduces constants), so those convolutions run without a bias pass.  Index arithmetic of the interpolation follows
 // ATen's upsample_bilinear2d with align_corners = false.  HBM-bound: one thread per (pixel, 4 channels), float4 accesses.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace swem {
@@ -139,6 +141,24 @@ __global__ void __launch_bounds__(256) tf32_split_kernel(const float4* __restric
   float4* o = hl_out + px * 2 * C4 + c4;
   o[0] = hi;
   o[C4] = make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w);
+}
+
+__global__ void __launch_bounds__(256) tf32_split_bf16_kernel(const float4* __restrict__ x, long long total4, int C4,
+                                                              float4* __restrict__ hi_out, uint2* __restrict__ xl_out) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total4) return;
+  const long long px = idx / C4;
+  const int c4 = (int)(idx - px * C4);
+  const float4 v = __ldg(x + idx);
+  const float4 hi = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+  hi_out[idx] = hi;
+  auto pack = [](float a, float b, float c, float d) {
+    const __nv_bfloat162 p0 = __floats2bfloat162_rn(a, b), p1 = __floats2bfloat162_rn(c, d);
+    return make_uint2(*reinterpret_cast<const uint32_t*>(&p0), *reinterpret_cast<const uint32_t*>(&p1));
+  };
+  uint2* o = xl_out + px * 2 * C4 + c4;
+  o[0] = pack(v.x, v.y, v.z, v.w);
+  o[C4] = pack(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w);
 }
 
 __global__ void __launch_bounds__(256) bias_add_act_kernel(const float4* __restrict__ a, const float4* __restrict__ b,
@@ -593,6 +613,18 @@ int swem_tf32_split(const float* x, int64_t pixels, int32_t C, float* hi, float*
   const long long total4 = pixels * (C / 4);
   tf32_split_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const float4*>(x), total4, C / 4, reinterpret_cast<float4*>(hi), reinterpret_cast<float4*>(hl));
+  SWEM_LAUNCH_CHECK();
+  return SWEM_OK;
+}
+
+int swem_tf32_split_bf16(const float* x, int64_t pixels, int32_t C, float* hi, void* xl_bf16, void* stream) {
+  reset_launch_count();
+  SWEM_CHECK_ARG(x && hi && xl_bf16, "NULL pointer");
+  SWEM_CHECK_ARG(pixels > 0 && C > 0 && C % 4 == 0 && pixels * (C / 4) < (1ll << 40), "bad sizes pixels=%lld C=%d (C must be a multiple of 4)",
+                 (long long)pixels, C);
+  const long long total4 = pixels * (C / 4);
+  tf32_split_bf16_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const float4*>(x), total4, C / 4, reinterpret_cast<float4*>(hi), reinterpret_cast<uint2*>(xl_bf16));
   SWEM_LAUNCH_CHECK();
   return SWEM_OK;
 }

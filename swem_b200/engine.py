@@ -57,13 +57,14 @@ def _fold_bn(conv, bn) -> Tuple[torch.Tensor, torch.Tensor]:
 
 class FrameEngine:
     def __init__(self, model, channels_last: bool = True, fused_conv: bool = True, stage_kernels: bool = True,
-                 split_tf32: bool = False):
+                 split_tf32: bool = False, cross_bf16: bool = False):
         self.model = model
         self.channels_last = channels_last
         self.fused_conv = fused_conv
         self.stage_kernels = stage_kernels and channels_last     # the decoder glue kernels of libswem_b200 are NHWC
         # fp32-accurate convolutions ON the tensor cores: every conv as three TF32 convs over hi / lo splits (see _conv_split)
         self.split_tf32 = split_tf32
+        self.cross_bf16 = cross_bf16                              # (with split_tf32) the cross-term convolution in bf16
         self._wsplit_cache = {}
         self._split_memo = []                                     # the last two split activations: (tensor, version, hi, [hi | lo])
         self._built = False
@@ -243,14 +244,15 @@ class FrameEngine:
         n, c, h, w = x.shape
         if self._glue_ok(x) and c % 4 == 0 and x.is_contiguous(memory_format=torch.channels_last):
             hi = torch.empty_like(x)
-            hl = torch.empty((n, 2 * c, h, w), device=x.device, dtype=torch.float32, memory_format=torch.channels_last)
+            hl = torch.empty((n, 2 * c, h, w), device=x.device, dtype=torch.bfloat16 if self.cross_bf16 else torch.float32,
+                             memory_format=torch.channels_last)
+            fn = _lib.load().swem_tf32_split_bf16 if self.cross_bf16 else _lib.load().swem_tf32_split
             with torch.cuda.device(x.device):
-                rc = _lib.load().swem_tf32_split(x.data_ptr(), n * h * w, c, hi.data_ptr(), hl.data_ptr(),
-                                                 torch.cuda.current_stream(x.device).cuda_stream)
+                rc = fn(x.data_ptr(), n * h * w, c, hi.data_ptr(), hl.data_ptr(), torch.cuda.current_stream(x.device).cuda_stream)
             _lib.check(rc, 'swem_tf32_split')
             return hi, hl
         hi, lo = self._tf32_split(x)
-        hl = torch.cat([hi, lo], dim=1)
+        hl = torch.cat([x, lo], dim=1).bfloat16() if self.cross_bf16 else torch.cat([hi, lo], dim=1)
         return (self._cl(hi), self._cl(hl)) if self.channels_last else (hi, hl)
 
     def _conv_split(self, x, p: ConvP, relu: bool, add: Optional[torch.Tensor]):
@@ -267,13 +269,18 @@ class FrameEngine:
         if key not in self._wsplit_cache:
             wh, wl = self._tf32_split(w)
             zero = torch.zeros(w.shape[0], device=w.device, dtype=torch.float32)
-            self._wsplit_cache[key] = (w, self._w(wh), self._w(torch.cat([wl, wh], dim=1)), zero)   # (keeps `w` alive: unique pointer)
+            wc = self._w(torch.cat([wl, wh], dim=1))
+            if self.cross_bf16:            # cross terms are 2^-11 of the result: 8 mantissa bits on their operands leave it at 2^-20
+                wc = wc.bfloat16()
+            self._wsplit_cache[key] = (w, self._w(wh), wc, zero)    # (keeps `w` alive: unique pointer)
         _, wh, wc, zero = self._wsplit_cache[key]
         hi, hl = self._split(x)
         old = torch.backends.cudnn.allow_tf32
         torch.backends.cudnn.allow_tf32 = True
         try:
             cross = F.conv2d(hl, wc, None, stride=s, padding=pad)
+            if self.cross_bf16:
+                cross = cross.float()
             if add is not None:
                 cross.add_(add)
             if relu and self.fused_conv and x.is_cuda:

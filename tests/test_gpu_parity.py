@@ -565,8 +565,8 @@ def test_frame_engine_matches_modules(fused_conv, split):
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
 
 
-@pytest.mark.parametrize('autotune,split', [(False, False), (True, False), (True, True)],
-                         ids=['heuristic', 'cudnn_benchmark', 'split_tf32'])
+@pytest.mark.parametrize('autotune,split', [(False, False), (True, False), (True, True), (True, 'bf16')],
+                         ids=['heuristic', 'cudnn_benchmark', 'split_tf32', 'split_tf32_bf16cross'])
 def test_frame_engine_free_running_masks_vs_oracle(autotune, split):
     """North-star mask agreement (>= 99.9 % per frame, 480p, 5 objects) with the whole per-frame loop in its
     production form: FrameEngine stages + fused kernels, against the CPU oracle on the plain modules.  The torch
@@ -600,7 +600,8 @@ def test_frame_engine_free_running_masks_vs_oracle(autotune, split):
             want = torch.stack(O.run_davis_sequence(oracle, frames, init, (h, w)))
         finally:
             O.random_init = real_init
-        got, _ = evaluate_davis_seq(FrameEngine(model, split_tf32=split), frames.to(DEV), [init.to(DEV)] + [None] * (T - 1), (h, w))
+        got, _ = evaluate_davis_seq(FrameEngine(model, split_tf32=bool(split), cross_bf16=split == 'bf16'), frames.to(DEV),
+                                    [init.to(DEV)] + [None] * (T - 1), (h, w))
         got = torch.stack(got).cpu()
     finally:
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark = old

@@ -31,6 +31,8 @@ for (n, ci, co, h, w, k) in ((5, 256, 256, 120, 216, 3), (1, 1024, 256, 30, 54, 
         e_1b = rel(y1b[:1], want)
         y2 = F.conv2d(xh, cl(wh), padding=k // 2) + F.conv2d(cl(torch.cat([xh, xl], 1)), cl(torch.cat([wl, wh], 1)), padding=k // 2)
         e_2 = rel(y2[:1], want)
+        yb = F.conv2d(xh, cl(wh), padding=k // 2) + F.conv2d(cl(torch.cat([x, xl], 1).bfloat16()), cl(torch.cat([wl, wh], 1)).bfloat16(), padding=k // 2).float()
+        e_b = rel(yb[:1], want)
         e_hh = rel(F.conv2d(xh, cl(wh), padding=k // 2)[:1], want)
         print(f'N={n} {ci}->{co} {k}x{k} {h}x{w} autotune={int(bench)}: fp32 {e_fp32:.1e}  tf32 {e_tf32:.1e}  hi.hi only {e_hh:.1e}  '
-              f'3 convs {e_3:.1e}  main + cross {e_2:.1e}  stacked [hi|hi|lo] {e_1:.1e}  stacked [lo|hi|hi] {e_1b:.1e}', flush=True)
+              f'3 convs {e_3:.1e}  main + cross {e_2:.1e}  main + bf16 cross {e_b:.1e}  stacked [hi|hi|lo] {e_1:.1e}  stacked [lo|hi|hi] {e_1b:.1e}', flush=True)
