@@ -126,3 +126,66 @@ def test_product_never_imports_the_oracle():
         for f in files:
             if f.endswith(('.py', '.cu', '.cuh', '.h')):
                 assert 'oracle' not in open(os.path.join(dirpath, f)).read().replace('use oracle/ for CPU checking', '')
+
+
+def test_fused_family_coverage_predicates(lib):
+    """What SWEM_PATH_AUTO dispatches to the tcgen05 family: Ck in {64, 128}, L in {64, 128, 256, 512}, Cv = 512 at any
+    frame size (the EM kernel goes windowed when a unit's clusters cannot be co-resident); anything else is generic."""
+    from swem_b200 import _lib
+    dims = lambda ck, cv, hw, l, banks=2: _lib.SwemDims(1, 5, ck, cv, hw, l, 4, banks, min(l, 64), 0.05)
+    for ck in (64, 128):
+        for l in (64, 128, 256, 512):
+            for hw in (240, 1620, 6480):
+                assert lib.swem_em_fused_supported(C.byref(dims(ck, 512, hw, l))) == 1, (ck, l, hw)
+                for banks in (1, 2):
+                    assert lib.swem_readout_fused_supported(C.byref(dims(ck, 512, hw, l, banks))) == 1, (ck, l, hw, banks)
+    for bad in (dims(32, 512, 1620, 128), dims(64, 256, 1620, 128), dims(64, 512, 1620, 384), dims(64, 512, 1620, 1024)):
+        assert lib.swem_em_fused_supported(C.byref(bad)) == 0
+        assert lib.swem_readout_fused_supported(C.byref(bad)) == 0
+        assert lib.swem_em_workspace_bytes(C.byref(bad), _lib.PATH_GENERIC) > 0
+
+
+def test_pixel_major_values_are_only_taken_when_the_fused_kernels_run():
+    from swem_b200 import SWEMCore
+    core = SWEMCore(n_bases=128, valdim=512, n_iters=4, tau=0.05, topl=64)
+    v = torch.randn(3, 512, 6, 8).contiguous(memory_format=torch.channels_last).view(1, 3, 512, 6, 8)
+    assert not core._takes_pixel_major(v, 1, 3, 64, 48)               # CPU tensor: never (and swem() raises on it anyway)
+    with pytest.raises(RuntimeError):
+        core.swem(torch.randn(1, 64, 6, 8), v, torch.rand(1, 3, 2, 6, 8))
+
+
+def test_multiscale_flip_evaluation_with_a_stub_model():
+    """evaluate_davis_seq_ms (swem_evaluator.py:34-57) on a stub model whose scores are a fixed function of the frame:
+    scores are averaged over the flip pair (un-flipped first) and then over the scales, argmax last."""
+    import torch.nn.functional as F
+    from swem_b200.evaluator import evaluate_davis_seq, evaluate_davis_seq_ms
+
+    class Stub:
+        def __call__(self, mode, *a):
+            if mode == 'encode_key':
+                f = a[0]
+                return f, f, f, f, f
+            if mode == 'match':
+                return a[0], 2
+            if mode == 'segment':
+                n, ctx, out_size = a[0], a[1], a[5]
+                g = F.interpolate(ctx, size=out_size, mode='bilinear', align_corners=False)
+                ramp = torch.linspace(0, 1, out_size[1]).view(1, 1, 1, -1)       # not flip-symmetric
+                prob = torch.softmax(torch.cat([g[:, :1] * 0 + 0.3, g[:, :2] * (1 + ramp)], 1) * 5, dim=1)
+                return None, prob
+            return a[0] if a else None                                           # encode_value / init / memorize
+
+    frames = torch.rand(1, 4, 3, 48, 80, generator=torch.Generator().manual_seed(0))
+    init = [torch.zeros(1, 3, 48, 80)] + [None] * 3
+    out = (48, 80)
+    scales = (240, 480)
+    want = [0] * 3
+    for s_ in scales:
+        fr = F.interpolate(frames[0], size=(s_, int(s_ / 480 * 864)), mode='bicubic', align_corners=False)[None]
+        _, a = evaluate_davis_seq(Stub(), fr, init, out)
+        _, b = evaluate_davis_seq(Stub(), torch.flip(fr, dims=[-1]), [torch.flip(init[0], dims=[-1])], out)
+        want = [acc + (x + torch.flip(y, dims=[-1])) / 2 / len(scales) for acc, x, y in zip(want, a, b)]
+    got = evaluate_davis_seq_ms(Stub(), frames, init, out, scales=scales, is_flip=True)
+    assert len(got) == 3 and all(torch.equal(g, torch.argmax(w, dim=1)) for g, w in zip(got, want))
+    plain, _ = evaluate_davis_seq(Stub(), F.interpolate(frames[0], size=(480, 864), mode='bicubic', align_corners=False)[None], init, out)
+    assert all(torch.equal(a, b) for a, b in zip(plain, evaluate_davis_seq_ms(Stub(), frames, init, out)))
