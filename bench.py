@@ -213,6 +213,8 @@ def run_b200(args, rank, world, local_rank):
     # frames, before the step graph is captured)
     cudnn_autotune = os.environ.get('SWEM_CUDNN_BENCHMARK', '1') == '1'
     torch.backends.cudnn.benchmark = cudnn_autotune
+    if 'SWEM_CUDNN_BENCH_LIMIT' in os.environ:                  # candidates timed per shape (torch default 10; 0 = all)
+        torch.backends.cudnn.benchmark_limit = int(os.environ['SWEM_CUDNN_BENCH_LIMIT'])
     conv_tf32 = os.environ.get('SWEM_CONV_TF32', '1') == '1'
     torch.backends.cudnn.allow_tf32 = conv_tf32
     torch.backends.cuda.matmul.allow_tf32 = conv_tf32
