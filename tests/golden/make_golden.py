@@ -5,7 +5,7 @@ Run in the authoring container only (needs /root/reference):
     python tests/golden/make_golden.py
 
 Writes ``core_small.pt``, ``core_prod.pt``, ``steps_small.pt``, ``model_tiny.pt`` next to this
-file.  Each fixture holds the seeded inputs and the reference's outputs; tests replay the inputs
+file (``--wide``: only ``core_wide.pt``, the reference's class default of 256 bases per side).  Each fixture holds the seeded inputs and the reference's outputs; tests replay the inputs
 through ``oracle/swem_oracle.py`` (CPU) and through the CUDA library (GPU).
 """
 from __future__ import annotations
@@ -113,6 +113,10 @@ def main():
     assert ref_shim.available(), 'reference checkout not found'
     torch.set_num_threads(1)                       # fixed reduction order inside ATen
     ref = ref_shim.load_modules()
+    if '--wide' in sys.argv:                       # added later: only this fixture is (re)generated
+        core_case(ref, 'core_wide', B=1, n_seq=[1, 1], Ck=64, Cv=512, L=256, H=6, W=10, n_iters=3, tau=0.05,
+                  topl=64, seed=31)
+        return
     core_case(ref, 'core_small', B=2, n_seq=[2, 2, 3], Ck=16, Cv=24, L=8, H=5, W=7, n_iters=3, tau=0.05,
               topl=4, seed=11, empty_obj=(1, 1))
     core_case(ref, 'core_prod', B=1, n_seq=[1, 1], Ck=64, Cv=512, L=128, H=6, W=10, n_iters=4, tau=0.05,

@@ -103,7 +103,7 @@ def _cpu_random_init(core):
 
 
 @pytest.mark.parametrize('family', ['generic', 'fused'])
-@pytest.mark.parametrize('name', ['core_small', 'core_prod'])
+@pytest.mark.parametrize('name', ['core_small', 'core_prod', 'core_wide'])
 def test_golden_sequences_teacher_forced(golden, name, family):
     """Each memorize call starts from the REFERENCE's previous bases (teacher forcing), readout too."""
     fx = golden(name)
