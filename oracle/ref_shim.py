@@ -13,6 +13,7 @@ loads with random-init torchvision state dicts.  The reference sources are not t
 """
 from __future__ import annotations
 
+import contextlib
 import importlib
 import importlib.util
 import os
@@ -35,22 +36,16 @@ def load_modules():
     return mod
 
 
-def load_swem():
-    """Return (SWEM class, modules module) of the reference with weight loading neutralised."""
+@contextlib.contextmanager
+def patched_weight_loads():
+    """While active, the reference's weight loads (``torch.load`` of a local ResNet checkpoint in ``KeyEncoder``,
+    ``model_zoo.load_url`` in the value encoders) are answered with random-init torchvision state dicts.  Everything is
+    restored on exit, so later ``torch.load`` calls of the same process (the golden fixtures!) see the real function."""
     import torch
     import torchvision
 
-    if REF not in sys.path:
-        sys.path.insert(0, REF)
-    for name, rel in (('methods', 'methods'), ('methods.SWEM', 'methods/SWEM'),
-                      ('methods.basic_modules', 'methods/basic_modules')):
-        if name not in sys.modules:
-            pkg = types.ModuleType(name)
-            pkg.__path__ = [os.path.join(REF, rel)]
-            sys.modules[name] = pkg
     mr = importlib.import_module('methods.basic_modules.mod_resnet')
-    mr.model_dirs = {'resnet50': '__r50__', 'resnet18': '__r18__'}
-    real_load = torch.load
+    real_load, real_url = torch.load, mr.model_zoo.load_url
 
     def fake_load(path, *a, **k):
         if path == '__r50__':
@@ -62,11 +57,40 @@ def load_swem():
     torch.load = fake_load
     mr.model_zoo.load_url = lambda *a, **k: torchvision.models.resnet18(weights=None).state_dict()
     try:
+        yield
+    finally:
+        torch.load = real_load
+        mr.model_zoo.load_url = real_url
+
+
+class _PatchedFactory:
+    """Calls the reference class with the weight loads patched for the duration of the construction only."""
+
+    def __init__(self, cls):
+        self.cls = cls
+
+    def __call__(self, *args, **kwargs):
+        with patched_weight_loads():
+            return self.cls(*args, **kwargs)
+
+
+def load_swem():
+    """Return (factory of the reference's SWEM, its modules module).  ``factory(cfg)`` builds the unmodified model with
+    weight loading neutralised; nothing stays patched afterwards."""
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    for name, rel in (('methods', 'methods'), ('methods.SWEM', 'methods/SWEM'),
+                      ('methods.basic_modules', 'methods/basic_modules')):
+        if name not in sys.modules:
+            pkg = types.ModuleType(name)
+            pkg.__path__ = [os.path.join(REF, rel)]
+            sys.modules[name] = pkg
+    mr = importlib.import_module('methods.basic_modules.mod_resnet')
+    mr.model_dirs = {'resnet50': '__r50__', 'resnet18': '__r18__'}     # networks.py:8 expects this name
+    with patched_weight_loads():
         swem_mod = importlib.import_module('methods.SWEM.swem')
         modules_mod = importlib.import_module('methods.SWEM.modules')
-    finally:
-        pass   # torch.load stays wrapped: KeyEncoder.__init__ calls it at construction time
-    return swem_mod.SWEM, modules_mod
+    return _PatchedFactory(swem_mod.SWEM), modules_mod
 
 
 def model_config(keydim=64, valdim=512, n_bases=128, n_iters=4, tau=0.05, topl=64,

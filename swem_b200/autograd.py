@@ -56,8 +56,8 @@ class EMFunction(torch.autograd.Function):
         gp = torch.empty_like(gnu) if need_p else None
         lib = _lib.load()
         dims = _lib.SwemDims(B, N, 0, Cv, HW, L, 0, 0, 0, 1.0)
-        from .core import _WORKSPACE, _invoke
-        ws = _WORKSPACE.get(dev, lib.swem_em_backward_workspace_bytes(C.byref(dims)))
+        from .core import _invoke
+        ws = ctx.core._workspace.get(dev, lib.swem_em_backward_workspace_bytes(C.byref(dims)), 'bwd')
         args = _lib.SwemEmBwdArgs(dims, z.data_ptr(), zita_.data_ptr(), zita.data_ptr(), gnu.data_ptr(),
                                   gv.data_ptr() if need_v else None, gp.data_ptr() if need_p else None,
                                   ws.data_ptr(), ws.numel())
@@ -104,6 +104,7 @@ class ReadoutFunction(torch.autograd.Function):
         out = torch.empty(B * N, Cv + 2 * core.topl, H, W, device=qk.device, dtype=torch.float32)
         core._readout_launch(qk, kappas, nus, out, 0, Cv)
         ctx.tau, ctx.topl, ctx.n_banks = core.tau, core.topl, n_banks
+        ctx.core = core
         ctx.save_for_backward(qk, *kappas, *nus)
         return out
 
@@ -136,7 +137,7 @@ class ReadoutFunction(torch.autograd.Function):
 
 
 def _readout_backward_native(ctx, qk, kappas, nus, gout, need_q, need_nu):
-    from .core import _WORKSPACE, _invoke
+    from .core import _invoke
     nb = ctx.n_banks
     B, Ck, H, W = qk.shape
     _, N, _, Cv, L = nus[0].shape
@@ -146,7 +147,7 @@ def _readout_backward_native(ctx, qk, kappas, nus, gout, need_q, need_nu):
     gn = [torch.empty_like(nus[k]) if need_nu[k] else None for k in range(nb)]
     lib = _lib.load()
     dims = _lib.SwemDims(B, N, Ck, Cv, H * W, L, 0, nb, ctx.topl, ctx.tau)
-    ws = _WORKSPACE.get(dev, lib.swem_readout_backward_workspace_bytes(C.byref(dims)))
+    ws = ctx.core._workspace.get(dev, lib.swem_readout_backward_workspace_bytes(C.byref(dims)), 'bwd')
     ptr = lambda t: None if t is None else t.data_ptr()
     pad = [None] * (2 - nb)
     args = _lib.SwemReadBwdArgs(dims, qk.data_ptr(),

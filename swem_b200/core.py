@@ -58,20 +58,35 @@ class MemoryBank:
 
 
 class _Workspace:
-    """Per-device scratch buffer handed to the kernels (grown on demand, never shrunk)."""
+    """Scratch buffers handed to the kernels, owned by ONE ``SWEMCore`` and keyed by (purpose, device, stream): two cores,
+    two streams or a forward and a backward never share (or regrow) each other's scratch.
+
+    A buffer whose address has been baked into a CUDA graph must outlive that graph: while the owner is ``pinned`` (a
+    runner is capturing / replaying, ``SWEMCore.static_banks``) a request that does not fit raises instead of
+    reallocating, and a buffer that was ever handed out while pinned is retired (kept alive), never freed, when a later
+    un-pinned call needs a bigger one."""
 
     def __init__(self):
-        self._buf: Dict[torch.device, torch.Tensor] = {}
+        self._buf: Dict[tuple, torch.Tensor] = {}
+        self._seen_pinned: Dict[tuple, bool] = {}
+        self._retired = []
+        self.pinned = False
 
-    def get(self, device: torch.device, nbytes: int) -> torch.Tensor:
-        buf = self._buf.get(device)
+    def get(self, device: torch.device, nbytes: int, purpose: str = 'fwd') -> torch.Tensor:
+        key = (purpose, device, torch.cuda.current_stream(device).cuda_stream)
+        buf = self._buf.get(key)
         if buf is None or buf.numel() < nbytes:
+            if buf is not None and self.pinned:
+                raise RuntimeError(f'swem_b200: the kernels need a {nbytes}-byte workspace but the {buf.numel()}-byte one is '
+                                   'referenced by a captured CUDA graph (static_banks); re-capture for the larger shape')
+            if buf is not None and self._seen_pinned.get(key):
+                self._retired.append(buf)
             buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
-            self._buf[device] = buf
+            self._buf[key] = buf
+            self._seen_pinned[key] = False
+        if self.pinned:
+            self._seen_pinned[key] = True
         return buf
-
-
-_WORKSPACE = _Workspace()
 
 
 def _f32c(t: torch.Tensor, name: str) -> torch.Tensor:
@@ -97,9 +112,19 @@ class SWEMCore(nn.Module):
     # SWEM_PATH_* of the C ABI per entry point; tests flip these to exercise both kernel families
     em_path = _lib.PATH_AUTO
     readout_path = _lib.PATH_AUTO
-    #: True: the 'update' bank keeps its tensors and is overwritten in place (needed when the frame step is
-    #: replayed from a CUDA graph, where every address is baked in).  False: replaced wholesale like the reference.
-    static_banks = False
+    _static_banks = False
+
+    @property
+    def static_banks(self) -> bool:
+        """True: the 'update' bank keeps its tensors and is overwritten in place, and the kernels' workspace may not be
+        reallocated (needed when the frame step is replayed from a CUDA graph, where every address is baked in).
+        False: bases are replaced wholesale like the reference."""
+        return self._static_banks
+
+    @static_banks.setter
+    def static_banks(self, value: bool) -> None:
+        self._static_banks = bool(value)
+        self._workspace.pinned = bool(value)
 
     def __init__(self, n_bases=256, valdim=512, n_iters=4, tau=0.05, topl=64):
         super().__init__()
@@ -110,6 +135,7 @@ class SWEMCore(nn.Module):
         self.topl = int(min(n_bases, topl))
         self.fusion_layer = FeatureFusionLayer(valdim * 2 + self.topl * 2, valdim)
         self.launches = 0          # kernels launched by this object's last memorize/matching call
+        self._workspace = _Workspace()
 
     # -- bank state ------------------------------------------------------------------------
     def empty(self):
@@ -194,7 +220,7 @@ class SWEMCore(nn.Module):
         lib = _lib.load()
         dims = _lib.SwemDims(B, N, Ck, Cv, H * W, L, self.n_iters, 0, 0, self.tau)
         need = lib.swem_em_workspace_bytes(C.byref(dims), self.em_path)
-        ws = _WORKSPACE.get(dev, need)
+        ws = self._workspace.get(dev, need)
         args = _lib.SwemEmArgs(dims, x.data_ptr(), v.data_ptr(), masks.data_ptr(),
                                kappa_.data_ptr(), nu_.data_ptr(), zita_.data_ptr(),
                                kappa.data_ptr(), nu.data_ptr(), zita.data_ptr(),
@@ -281,7 +307,7 @@ class SWEMCore(nn.Module):
         lib = _lib.load()
         dims = _lib.SwemDims(B, N, Ck, Cv, H * W, L, 0, len(nus), self.topl, self.tau)
         need = lib.swem_readout_workspace_bytes(C.byref(dims), self.readout_path)
-        ws = _WORKSPACE.get(dev, need)
+        ws = self._workspace.get(dev, need)
         args = _lib.SwemReadArgs(dims, qk.data_ptr(),
                                  (C.c_void_p * 2)(*[k.data_ptr() for k in kap] + [None] * (2 - len(kap))),
                                  (C.c_void_p * 2)(*[n.data_ptr() for n in nus] + [None] * (2 - len(nus))),

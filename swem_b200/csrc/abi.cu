@@ -151,16 +151,15 @@ int swem_set_profile_buffer(void* dev, size_t bytes) {
 int swem_em_fused_supported(const SwemDims* d) { return d && fused_em_supported(*d) ? 1 : 0; }
 int swem_readout_fused_supported(const SwemDims* d) { return d && fused_readout_supported(*d) ? 1 : 0; }
 
-static bool use_fused_em(const SwemDims& d, int path) {
-  return path == SWEM_PATH_FUSED || (path == SWEM_PATH_AUTO && fused_em_supported(d));
-}
-static bool use_fused_readout(const SwemDims& d, int path) {
-  return path == SWEM_PATH_FUSED || (path == SWEM_PATH_AUTO && fused_readout_supported(d));
-}
+// SWEM_PATH_AUTO is the product path: the tcgen05 family, or SWEM_ERR_UNSUPPORTED when it does not cover the shape (SURVEY
+// section 8(b): unsupported shapes fail loudly, nothing is dispatched silently to a slower family).  The generic fp32 family
+// runs only when SWEM_PATH_GENERIC is asked for by name (tests, debugging, training shapes outside the fused coverage).
+static bool use_fused_em(const SwemDims&, int path) { return path != SWEM_PATH_GENERIC; }
+static bool use_fused_readout(const SwemDims&, int path) { return path != SWEM_PATH_GENERIC; }
 
 size_t swem_em_workspace_bytes(const SwemDims* d, int32_t path) {
   if (!d || check_dims(*d, true)) return 0;
-  if (path == SWEM_PATH_FUSED && !fused_em_supported(*d)) return 0;
+  if (path != SWEM_PATH_GENERIC && !fused_em_supported(*d)) return 0;
   return use_fused_em(*d, path) ? fused_em_workspace(*d) : generic_em_workspace(*d);
 }
 
@@ -172,8 +171,9 @@ int swem_em_forward(const SwemEmArgs* a, void* stream) {
                  "a required input pointer is NULL");
   SWEM_CHECK_ARG(a->kappa && a->nu && a->zita, "a required output pointer is NULL");
   SWEM_CHECK_ARG(a->path >= SWEM_PATH_AUTO && a->path <= SWEM_PATH_FUSED, "bad path %d", a->path);
-  if (a->path == SWEM_PATH_FUSED && !fused_em_supported(a->dims)) {
-    set_error("fused EM kernels do not cover Ck=%d Cv=%d L=%d HW=%d", a->dims.Ck, a->dims.Cv, a->dims.L, a->dims.HW);
+  if (a->path != SWEM_PATH_GENERIC && !fused_em_supported(a->dims)) {
+    set_error("the tcgen05 EM kernels do not cover Ck=%d Cv=%d L=%d HW=%d n_iters=%d (Ck in {64,128}, L in {64,128,256,512}, Cv=512); "
+              "the generic fp32 family runs only on request (SWEM_PATH_GENERIC)", a->dims.Ck, a->dims.Cv, a->dims.L, a->dims.HW, a->dims.n_iters);
     return SWEM_ERR_UNSUPPORTED;
   }
   const size_t need = swem_em_workspace_bytes(&a->dims, a->path);
@@ -212,7 +212,7 @@ int swem_em_backward(const SwemEmBwdArgs* a, void* stream) {
 
 size_t swem_readout_workspace_bytes(const SwemDims* d, int32_t path) {
   if (!d || check_dims(*d, false)) return 0;
-  if (path == SWEM_PATH_FUSED && !fused_readout_supported(*d)) return 0;
+  if (path != SWEM_PATH_GENERIC && !fused_readout_supported(*d)) return 0;
   return use_fused_readout(*d, path) ? fused_readout_workspace(*d) : generic_readout_workspace(*d);
 }
 
@@ -229,8 +229,9 @@ int swem_readout_forward(const SwemReadArgs* a, void* stream) {
   SWEM_CHECK_ARG(a->path >= SWEM_PATH_AUTO && a->path <= SWEM_PATH_FUSED, "bad path %d", a->path);
   SWEM_CHECK_ARG(a->out_pixel_major == 0 || (a->out_pixel_major == 1 && a->out_channels % 4 == 0 && a->mem_channel % 4 == 0),
                  "out_pixel_major=%d needs out_channels and mem_channel to be multiples of 4", a->out_pixel_major);
-  if (a->path == SWEM_PATH_FUSED && !fused_readout_supported(d)) {
-    set_error("fused readout kernels do not cover Ck=%d Cv=%d L=%d banks=%d", d.Ck, d.Cv, d.L, d.n_banks);
+  if (a->path != SWEM_PATH_GENERIC && !fused_readout_supported(d)) {
+    set_error("the tcgen05 readout kernels do not cover Ck=%d Cv=%d L=%d banks=%d topl=%d (Ck in {64,128}, L in {64,128,256,512}, Cv=512, "
+              "topl<=64); the generic fp32 family runs only on request (SWEM_PATH_GENERIC)", d.Ck, d.Cv, d.L, d.n_banks, d.topl);
     return SWEM_ERR_UNSUPPORTED;
   }
   const size_t need = swem_readout_workspace_bytes(&d, a->path);

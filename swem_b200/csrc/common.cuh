@@ -2,6 +2,7 @@
 #pragma once
 
 #include <cuda_runtime.h>
+#include <mutex>
 #include <stdint.h>
 #include <stdio.h>
 
@@ -47,6 +48,23 @@ void reset_launch_count();
   } while (0)
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// Per-device, thread-safe "done once" state for function attributes and occupancy queries: cudaFuncSetAttribute and
+// cudaOccupancyMaxActiveClusters are per device, so a process that drives several GPUs must repeat them on each one.
+constexpr int kMaxDevices = 64;
+struct PerDevice {
+  std::mutex mu;
+  int value[kMaxDevices];
+  bool done[kMaxDevices];
+  PerDevice() {
+    for (int i = 0; i < kMaxDevices; ++i) { value[i] = -1; done[i] = false; }
+  }
+};
+inline int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return (dev >= 0 && dev < kMaxDevices) ? dev : 0;
+}
 
 // Bump allocator over the caller's workspace.
 struct Arena {

@@ -788,7 +788,10 @@ long long* get_profile_buffer() { return g_prof; }
 
 template <int CK, int LB, bool VPM>
 static int max_clusters_resident() {
-  static int n = -1;
+  static PerDevice cache;                                // occupancy and the shared-memory attribute are per device
+  const int dev_id = current_device();
+  std::lock_guard<std::mutex> lock(cache.mu);
+  int& n = cache.value[dev_id];
   if (n < 0) {
     cudaFuncSetAttribute(em_pair_kernel<CK, LB, VPM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)em::smem_bytes<CK, LB>());
     cudaLaunchConfig_t cfg = {};
@@ -851,11 +854,7 @@ static int fused_em_forward_t(const SwemEmArgs& a, cudaStream_t st) {
   count_launch();
   uint8_t* vblob = ws.take<uint8_t>((size_t)U * T * em::kChunks * em::kStageBytes);
 
-  static bool attr_set = false;
-  if (!attr_set) {
-    SWEM_CUDA(cudaFuncSetAttribute(em_pair_kernel<CK, LB, VPM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)em::smem_bytes<CK, LB>()));
-    attr_set = true;
-  }
+  (void)max_clusters_resident<CK, LB, VPM>();            // sets the shared-memory attribute on this device (once per device)
   EmPairParams p{};
   p.x = a.x; p.v = a.v; p.masks = a.masks;
   p.kappa_prior = a.kappa_prior; p.nu_prior = a.nu_prior; p.zita_prior = a.zita_prior;

@@ -565,11 +565,15 @@ int fused_readout_forward(const SwemReadArgs& a, cudaStream_t st) {
   }
 #define SWEM_RO_ATTR(LT_, CK_, NS_) \
   SWEM_CUDA(cudaFuncSetAttribute(readout_fused_kernel<LT_, CK_, NS_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ro::smem_bytes<CK_>()))
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDevice once;                                 // function attributes are per device
+  const int dev_id = current_device();
+  {
+  std::lock_guard<std::mutex> once_lock(once.mu);
+  if (!once.done[dev_id]) {
     SWEM_RO_ATTR(64, 64, 1); SWEM_RO_ATTR(128, 64, 1); SWEM_RO_ATTR(256, 64, 1); SWEM_RO_ATTR(256, 64, 2); SWEM_RO_ATTR(256, 64, 4);
     SWEM_RO_ATTR(64, 128, 1); SWEM_RO_ATTR(128, 128, 1); SWEM_RO_ATTR(256, 128, 1); SWEM_RO_ATTR(256, 128, 2); SWEM_RO_ATTR(256, 128, 4);
-    attr_set = true;
+    once.done[dev_id] = true;
+  }
   }
 #undef SWEM_RO_ATTR
   ReadoutFusedParams p{};

@@ -525,10 +525,14 @@ int swem_resblock_tail_pred(const float* a, const float* b, const float* bias, c
                  BN, H, W, C);
   const size_t smem = (size_t)9 * (C / 4) * sizeof(float4) + (size_t)kTpHalo * 9 * sizeof(float);
   SWEM_CHECK_ARG(smem <= 96 * 1024, "C=%d too large for the weight tile", C);
-  static bool attr_set = false;
-  if (!attr_set) {
-    SWEM_CUDA(cudaFuncSetAttribute(resblock_tail_pred_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    attr_set = true;
+  {
+    static PerDevice once;                               // the attribute is per device: one set per GPU this process uses
+    const int dev = current_device();
+    std::lock_guard<std::mutex> lock(once.mu);
+    if (!once.done[dev]) {
+      SWEM_CUDA(cudaFuncSetAttribute(resblock_tail_pred_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+      once.done[dev] = true;
+    }
   }
   dim3 grid((W + kTpTW - 1) / kTpTW, (H + kTpTH - 1) / kTpTH, BN);
   resblock_tail_pred_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(

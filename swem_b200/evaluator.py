@@ -139,6 +139,16 @@ class SequenceRunner:
         return pred[:, 0]
 
 
+def _graph_key(core, frame, memorize: bool):
+    """What a captured frame step is specific to: the memorize flag, the frame shape, the object count -- and both banks
+    must exist (the 'update' bank is created by the second memorize; a graph captured before that would bake in tensors
+    that are then replaced).  None = not capturable yet."""
+    first, upd = core.memories['first'].bases, core.memories['update'].bases
+    if first is None or upd is None:
+        return None
+    return (bool(memorize), tuple(frame.shape), int(first['kappa'].shape[1]), int(upd['kappa'].shape[1]))
+
+
 class GraphedSequenceRunner(SequenceRunner):
     """:class:`SequenceRunner` whose steady-state step is captured once into a CUDA graph and replayed.
 
@@ -155,19 +165,24 @@ class GraphedSequenceRunner(SequenceRunner):
         self.eager_steps = max(2, eager_steps)
         self._seen = 0
         self._graph = None
+        self._key = None
         self._frame = None
         self._pred = None
 
     @torch.no_grad()
     def start(self, frame0, init_mask):
-        self._seen, self._graph = 0, None
+        self._seen, self._graph, self._key = 0, None, None
         self.model.swem_core.static_banks = False
         super().start(frame0, init_mask)
 
     @torch.no_grad()
     def step(self, frame, memorize: bool = True):
+        key = _graph_key(self.model.swem_core, frame, memorize)
+        if self._graph is not None and key != self._key:         # another step than the captured one: drop the graph
+            self._graph, self._key = None, None
+            self.model.swem_core.static_banks = False
         if self._graph is None:
-            if self._seen < self.eager_steps:
+            if self._seen < self.eager_steps or key is None:     # (key None: a bank is still missing -> not capturable)
                 self._seen += 1
                 return super().step(frame, memorize)
             core = self.model.swem_core                          # (FrameEngine forwards .swem_core to its model)
@@ -177,7 +192,7 @@ class GraphedSequenceRunner(SequenceRunner):
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
                 self._pred = super().step(self._frame, memorize)
-            self._graph = graph
+            self._graph, self._key = graph, key
             # capture does not execute: run the captured step once for this frame
         self._frame.copy_(frame, non_blocking=True)
         self._graph.replay()
@@ -252,6 +267,7 @@ class PipelinedSequenceRunner(SequenceRunner):
     def _reset(self):
         self._seen, self._graph, self._cur, self._cur_frame, self._next_in, self._pred = 0, None, None, None, None, None
         self._cur_shared = None
+        self._key = None
 
     def _encode(self, frame):
         """Key features of a frame + (FrameEngine only) its object-independent convolutions, as a flat tensor list."""
@@ -319,7 +335,11 @@ class PipelinedSequenceRunner(SequenceRunner):
             raise RuntimeError('PipelinedSequenceRunner.step() before prime()')
         if next_frame is None:
             return self._heavy(memorize)
-        if not self.use_graph or self._seen < self.eager_steps:
+        key = _graph_key(self.model.swem_core, next_frame, memorize)
+        if self._graph is not None and key != self._key:         # another step than the captured one: drop the graph
+            self._graph, self._key = None, None
+            self.model.swem_core.static_banks = False
+        if not self.use_graph or self._seen < self.eager_steps or key is None:
             self._seen += 1
             return self._two_branch_step(next_frame, memorize)
         if self._graph is None:
@@ -329,7 +349,7 @@ class PipelinedSequenceRunner(SequenceRunner):
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
                 self._pred = self._two_branch_step(self._next_in, memorize)
-            self._graph = graph
+            self._graph, self._key = graph, key
         self._next_in.copy_(next_frame, non_blocking=True)
         self._graph.replay()
         return self._pred

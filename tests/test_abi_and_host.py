@@ -129,8 +129,10 @@ def test_product_never_imports_the_oracle():
 
 
 def test_fused_family_coverage_predicates(lib):
-    """What SWEM_PATH_AUTO dispatches to the tcgen05 family: Ck in {64, 128}, L in {64, 128, 256, 512}, Cv = 512 at any
-    frame size (the EM kernel goes windowed when a unit's clusters cannot be co-resident); anything else is generic."""
+    """What SWEM_PATH_AUTO runs = the tcgen05 family: Ck in {64, 128}, L in {64, 128, 256, 512}, Cv = 512 at any frame
+    size (the EM kernel goes windowed when a unit's clusters cannot be co-resident).  Anything else is refused under AUTO
+    (workspace query 0, forward SWEM_ERR_UNSUPPORTED -- SURVEY 8(b): fail loudly); the generic fp32 family runs only when
+    SWEM_PATH_GENERIC is asked for by name."""
     from swem_b200 import _lib
     dims = lambda ck, cv, hw, l, banks=2: _lib.SwemDims(1, 5, ck, cv, hw, l, 4, banks, min(l, 64), 0.05)
     for ck in (64, 128):
@@ -143,6 +145,9 @@ def test_fused_family_coverage_predicates(lib):
         assert lib.swem_em_fused_supported(C.byref(bad)) == 0
         assert lib.swem_readout_fused_supported(C.byref(bad)) == 0
         assert lib.swem_em_workspace_bytes(C.byref(bad), _lib.PATH_GENERIC) > 0
+        assert lib.swem_em_workspace_bytes(C.byref(bad), _lib.PATH_AUTO) == 0
+        assert lib.swem_readout_workspace_bytes(C.byref(bad), _lib.PATH_AUTO) == 0
+        assert lib.swem_readout_workspace_bytes(C.byref(bad), _lib.PATH_GENERIC) > 0
 
 
 def test_pixel_major_values_are_only_taken_when_the_fused_kernels_run():

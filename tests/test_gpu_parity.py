@@ -348,6 +348,19 @@ def test_errors_are_loud():
     core = core.to(DEV)
     with pytest.raises(RuntimeError, match='memory is empty'):
         core.matching(x.to(DEV), torch.randn(1, 32, 4, 4, device=DEV))
+    # a shape the tcgen05 kernels do not cover is refused under SWEM_PATH_AUTO (no silent dispatch to the slow family) ...
+    args = (x.to(DEV), torch.randn(1, 1, 32, 4, 4, device=DEV), torch.rand(1, 1, 2, 4, 4, device=DEV))
+    with pytest.raises(RuntimeError, match='SWEM_PATH_GENERIC'):
+        core.swem(*args)
+    # ... and runs on the generic family only when that is asked for by name
+    from swem_b200 import _lib
+    core.em_path = core.readout_path = _lib.PATH_GENERIC
+    bases = core.swem(*args)
+    assert torch.isfinite(bases['kappa']).all()
+    core.memories['first'].update(bases)
+    core.readout_path = _lib.PATH_AUTO
+    with pytest.raises(RuntimeError, match='SWEM_PATH_GENERIC'):
+        core.matching_features(x.to(DEV), torch.randn(1, 32, 4, 4, device=DEV))
 
 
 @pytest.mark.parametrize('case', ['davis480p_5obj', 'small240p_3obj'])
