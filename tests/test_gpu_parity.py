@@ -60,7 +60,7 @@ def em_check(got, want32, x, v, masks, prior, L, n_iters, tau, tol, slack=4.0):
         m = None if key == 'zita' else live
         floor = maxrel(want32[key], want64[key], m)
         err = maxrel(got[key], want64[key], m)
-        check(f'{key}(floor {floor:.1e})', err, max(tol, slack * floor))
+        check(f'{key}(floor {floor:.1e})', err, min(max(tol, slack * floor), 1e-2))     # never looser than the north-star 1e-2
     assert torch.isfinite(got['kappa']).all() and torch.isfinite(got['nu']).all()
 
 
@@ -181,8 +181,11 @@ SHAPES = [
 @pytest.mark.parametrize('family', ['generic', 'fused'])
 @pytest.mark.parametrize('shape', SHAPES, ids=lambda s: 'x'.join(map(str, s)))
 def test_memorize_and_readout_vs_oracle(shape, family):
-    """Two chained memorize calls + readout (Lt = 2L) against the fp32 oracle, teacher-forced."""
-    from swem_b200.synthetic import em_inputs
+    """Two chained memorize calls + readout (Lt = 2L) against the fp32 oracle, teacher-forced.  Keys have encoder-like
+    statistics (clustered, ||x|| ~ 18: synthetic.clustered_em_inputs), so the multi-iteration EM is well conditioned
+    (fp32-vs-fp64 floor <= 1.4e-4 on every row, measured on the oracle) and the 1e-2 / 2e-4 tolerances are the real bounds
+    at every L in {64, 128, 256, 512} x Ck in {64, 128}."""
+    from swem_b200.synthetic import clustered_em_inputs, em_inputs
     B, N, Ck, Cv, L, H, W, I = shape
     topl = min(L, 64)
     _skip_unless_covered(family, B=B, N=N, Ck=Ck, Cv=Cv, HW=H * W, L=L, n_iters=I, topl=topl)
@@ -193,7 +196,7 @@ def test_memorize_and_readout_vs_oracle(shape, family):
     gen = torch.Generator().manual_seed(123)
     with torch.no_grad():
         for call in range(2):
-            x, v, masks = em_inputs(B, N, Ck, Cv, H, W, seed=10 + call)
+            x, v, masks = clustered_em_inputs(B, N, Ck, Cv, H, W, seed=10 + call)
             if N > 1:
                 masks[0, N - 1, 1] = 0                        # an empty object
             prior = ref.banks.prior()
@@ -212,6 +215,37 @@ def test_memorize_and_readout_vs_oracle(shape, family):
         check('mem_out', maxrel(feats[:, :Cv], want_feats[:, :Cv]), tol['feat'])
         check('S', maxrel(feats[:, 2 * Cv:], want_feats[:, 2 * Cv:]), tol['feat'])
         assert torch.equal(feats[:, Cv:2 * Cv].cpu(), want_feats[:, Cv:2 * Cv])
+
+
+@pytest.mark.parametrize('family', ['generic', 'fused'])
+@pytest.mark.parametrize('shape', [(1, 3, 64, 128, 30, 54), (1, 2, 128, 256, 24, 24)], ids=['ck64_L128', 'ck128_L256'])
+def test_per_iteration_trace(shape, family):
+    """The EM iterations one by one on the kernels under test: runs with n_iters = 1, 2, 3, 4 from the same prior must
+    reproduce the oracle's per-iteration kappa (`trace['kappa'][i]`) and last responsibilities z (`trace['z'][i]`, which
+    carry the W-step weights of iteration i) -- so an error in any single E / M / W step shows up at its own iteration
+    instead of being averaged into the final bases."""
+    from swem_b200.synthetic import clustered_em_inputs
+    B, N, Ck, L, H, W = shape
+    Cv, I = 512, 4
+    _skip_unless_covered(family, B=B, N=N, Ck=Ck, Cv=Cv, HW=H * W, L=L, n_iters=I)
+    x, v, masks = clustered_em_inputs(B, N, Ck, Cv, H, W, seed=3)
+    prior = dict(zip(('kappa', 'nu', 'zita'), O.random_init(B, N, Ck, L, Cv, generator=torch.Generator().manual_seed(5))))
+    first = O.em_memorize(x, v, masks, prior, L, I, 0.05)                    # a realistic prior: the output of one call
+    x, v, masks = clustered_em_inputs(B, N, Ck, Cv, H, W, seed=4)
+    trace = {}
+    d = lambda t: t.double()
+    O.em_memorize(d(x), d(v), d(masks), {k: d(t) for k, t in first.items()}, L, I, 0.05, trace=trace)
+    tol = 2e-4 if family == 'generic' else 3e-3
+    for it in range(1, I + 1):
+        core = _core(dict(L=L, Cv=Cv, n_iters=it, tau=0.05, topl=64), family)
+        with torch.no_grad():
+            got = core.swem(x.to(DEV), v.to(DEV), masks.to(DEV), _to(first, DEV), return_z=True)
+        want_k, want_z = trace['kappa'][it - 1], trace['z'][it - 1]
+        zita = first['zita'].double() + want_z.sum(dim=-2, keepdim=True)
+        live = zita > 1e-3
+        check(f'kappa_it{it}', maxrel(got['kappa'], want_k, live), tol)
+        check(f'z_it{it}', maxrel(got['z'], want_z), tol)
+        check(f'zita_it{it}', maxrel(got['zita'], zita), tol)
 
 
 @pytest.mark.parametrize('family', ['generic', 'fused'])
@@ -852,3 +886,30 @@ def test_em_reads_channels_last_values_in_place(shape):
         check(key + '_nhwc', maxrel(b[key], a[key], None if key == 'zita' else live.cpu()), 1e-5 if I == 1 else 1e-2)
     core.em_path = _lib.PATH_GENERIC
     assert not core._takes_pixel_major(v_cl, B, N, Ck, H * W)         # the generic family gets the NCHW copy instead
+
+
+def test_bench_configuration_passes_the_mask_gate():
+    """The EXACT configuration bench.py times (same env defaults: FrameEngine parity convolutions = TF32 main term + bf16
+    cross terms, autotuned cuDNN, pipelined CUDA-graph runner, tcgen05 EM / readout) through the north-star gate: >= 99.9 %
+    per-frame argmax agreement with the fp32 CPU oracle on the bench's own frames (BASELINE configs[1]: 480x864, 5 objects).
+    This is the function bench.py itself calls to fill `parity.min_frame_agreement`."""
+    import argparse
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if root not in sys.path:
+        sys.path.insert(0, root)
+    import bench
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark)
+    try:
+        args = argparse.Namespace(steps=20, warmup=3, objects=5, gpus=1)
+        bn = bench.Bench(args, rank=0, world=1, local_rank=0)
+        stages = bn.set_conv_mode('parity')
+        frames, init = bench.make_sequence(bench.POOL, 5, seed=1)
+        prior = bench.fixed_prior(5)
+        ref = bench.reference_run(5, 6, 1, device='cpu', seed=1, prior=prior, keep_masks=True)
+        want = torch.stack(ref['masks'])
+        per_frame = bn.mask_agreement(stages, frames[0].pin_memory(), init.to(DEV), prior, want)
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark = old
+    assert per_frame.numel() == 7
+    check('min_agree', 1.0 - per_frame.min().item(), 1.0 - bench.GATE)
