@@ -221,7 +221,7 @@ def reference_run(n_obj, steps, warmup, device='cpu', seed=1, prior=None, keep_m
                 _, pm = model.segment(n, ctx, s8, s4, (H, W))
                 pred, hard = O.one_hot_from_argmax(pm)
                 if keep_masks:
-                    masks.append(pred[:, 0].to('cpu', torch.uint8))
+                    masks.append(pred[0, 0].to('cpu', torch.uint8))          # (H, W)
                 soft = F.interpolate(pm, size=(H, W), mode='bilinear', align_corners=False)
                 mv16 = model.encode_value(frames[:, i], soft, s16)
                 em_masks = O.build_em_masks(hard, soft, *qk16.shape[-2:])

@@ -74,4 +74,45 @@ __device__ __forceinline__ void st_cluster_f32(uint32_t addr, float a) {
   asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(a) : "memory");
 }
 
+
+// ---- named barriers (ids 1..15; 0 is __syncthreads) -------------------------------------------
+__device__ __forceinline__ void bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+
+// ---- mbarriers across a cluster: arrive on a peer CTA's barrier (release at cluster scope: the st.shared::cluster
+// stores issued before it are visible to the waiter), wait with acquire at cluster scope -----------------------------
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster_scope(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cta.b64 _, [%0];" ::"r"(tc05::smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(tc05::smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok;
+}
+__device__ __forceinline__ bool mbar_wait_cluster(uint64_t* bar, uint32_t parity, uint32_t max_spins = (1u << 24)) {
+  if (mbar_try_wait_cluster(bar, parity)) return true;
+#pragma unroll 1
+  for (uint32_t i = 0; i < max_spins; ++i)
+    if (mbar_try_wait_cluster(bar, parity)) return true;
+  return false;
+}
+// one lane polls, the warp parks on the shuffle (polling with every thread starves the thread that issues the MMAs)
+__device__ __forceinline__ bool warp_wait(uint64_t* bar, uint32_t parity) {
+  int ok = 1;
+  if ((threadIdx.x & 31) == 0) ok = tc05::mbar_wait(bar, parity) ? 1 : 0;
+  return __shfl_sync(0xffffffffu, ok, 0) != 0;
+}
+__device__ __forceinline__ void red_release_add(unsigned* p, unsigned v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
 }  // namespace swem
