@@ -95,6 +95,8 @@ long long* get_profile_buffer();
 bool fused_em_supported(const SwemDims& d);
 size_t fused_em_workspace(const SwemDims& d);
 int fused_em_forward(const SwemEmArgs& a, cudaStream_t st);
+bool fused_em_res_covers(const SwemDims& d, bool v_pixel_major);   // V-resident kernel (fused_em_res.cu): Ck = 64, L <= 128
+int fused_em_res_forward(const SwemEmArgs& a, cudaStream_t st);
 bool fused_readout_supported(const SwemDims& d);
 size_t fused_readout_workspace(const SwemDims& d);
 int fused_readout_forward(const SwemReadArgs& a, cudaStream_t st);

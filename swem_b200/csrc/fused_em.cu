@@ -899,6 +899,7 @@ static int fused_em_forward_v(const SwemEmArgs& a, cudaStream_t st) {
 }
 
 int fused_em_forward(const SwemEmArgs& a, cudaStream_t st) {
+  if (fused_em_res_covers(a.dims, a.v_pixel_major != 0)) return fused_em_res_forward(a, st);
   return a.v_pixel_major ? fused_em_forward_v<true>(a, st) : fused_em_forward_v<false>(a, st);
 }
 

@@ -1,0 +1,769 @@
+// Sequential weighted EM for sm_100a, "V-resident" kernel: the BASELINE shape family Ck = 64, L = 64 / 128 bases per side,
+// Cv = 512 (every other covered shape runs em_pair_kernel, fused_em.cu).  Reference semantics: methods/SWEM/modules.py
+// :129-168 (swem), :112-120 (E-step), :122-127 (M-step), :93-110 (W-step), :164-165 (nu).
+//
+// One launch per memorize call, one CTA of 16 warps per (unit u = (b, n), 128-pixel tile, side), the two sides of a tile
+// forming a 2-CTA cluster.  What changed against em_pair_kernel (profiles/r1_phases_em_pair.txt -> r2_phases_em_res.txt):
+//
+//   * nu = Z^T V^T is a single-pass fp16 product (z and v rounded once; measured on the oracle: nu error 4e-4 against the
+//     1e-2 bar, kappa / zita unaffected -- they keep the hi/lo split products, tools/precision_study.py).  The pair splits
+//     it by VALUE CHANNEL, not by side: CTA `rank` owns channels [256 rank, +256) for both sides, so every V element is read
+//     from HBM exactly once, converted in registers and kept in shared memory as the B operand -- no operand images in global
+//     memory, no copy ring.  The conversion runs in the shadow of the cross-tile barriers of the first iterations (loads issued
+//     before the arrival, converted while the barrier completes).  The peer's responsibilities of the last E-step are pushed
+//     over distributed shared memory by the epilogue that produces them.
+//   * 16 warps: the softmax epilogue holds 32 logits per thread (4 threads per pixel, exps against the thread's own max and
+//     one rescale -- no max exchange before the exps); the pixel statistics of the two sides meet through a remote mbarrier
+//     (128 arrivals) instead of a full cluster barrier.
+//   * M-step partials: all 16 warps reduce-add their 16 columns straight from TMEM; the prior term zita_ * kappa_ is added
+//     once, by the CTA of tile 0, so the finalize is kappa = total / zita_total with no prior reloads, done by 4 threads per
+//     row (16 channels each, norm through two shuffles).
+//   * the kappa all-reduce of the last iteration completes under the nu GEMMs; the nu partial of the CTA's own side drains
+//     while the tensor core is still busy with the peer side.
+//
+// Cross-tile sums still go through L2-resident accumulators with per-(unit, iteration, side) arrival counters (bounded
+// spin; every CTA of a launch is co-resident, see the host side).
+#include <cuda_fp16.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "tc05.cuh"
+#include "fused_common.cuh"
+
+namespace swem {
+
+using namespace tc05;
+
+namespace emr {
+constexpr int kTP = 128;      // pixels per CTA
+constexpr int kL = 128;       // basis rows per CTA (L = 64: the upper half is zero padding)
+constexpr int kCk = 64;
+constexpr int kCv = 512;
+constexpr int kDH = 256;      // value channels per CTA in the nu phase
+constexpr int kThreads = 512;
+constexpr float kKScale = 256.f;
+constexpr float kZScale = 16384.f;
+
+// ---- shared memory map (bytes).  Operand layouts as in fused_em.cu:
+// XH : [c 0..79][p]  byte = (c%8)*16 + (c/8)*2048 + (p/8)*128 + (p%8)*2   (row 64 = ones -> zita column, 65.. = 0)
+// XL : [c 0..63][p]
+// KH/KL : [l][c] K-major: byte = (l%8)*16 + (l/8)*128 + (c/8)*2048 + (c%8)*2
+// Z / ZL / ZP : [l][p] MN-major A: byte = (l%8)*2 + (p%8)*16 + (l/8)*2048 + (p/8)*128   (ZL aliases KH/KL; ZP = the peer side's z)
+// V  : [d 0..255][p 0..127] K-major B: byte = (d%8)*16 + (d/8)*128 + (p/8)*4096 + (p%8)*2
+constexpr uint32_t kOffXH = 0;
+constexpr uint32_t kOffXL = kOffXH + 10 * 2048;
+constexpr uint32_t kOffKH = kOffXL + 8 * 2048;
+constexpr uint32_t kOffKL = kOffKH + 8 * 2048;
+constexpr uint32_t kOffZ = kOffKL + 8 * 2048;
+constexpr uint32_t kOffZL = kOffKH;
+constexpr uint32_t kOffZP = kOffZ + 16 * 2048;
+constexpr uint32_t kOffV = kOffZP + 16 * 2048;
+constexpr uint32_t kOffMisc = kOffV + 16 * 4096;
+constexpr uint32_t kStageBytes = 32768;        // nu drain staging: 2 buffers over the (dead) X / khat region
+static_assert(kOffZ >= 2 * kStageBytes, "drain staging must fit below Z");
+
+struct Misc {
+  float inv_nx[kTP];
+  float mask[kTP];
+  float hmax[4][kTP];
+  float hsum[4][kTP];
+  float hew[4][kTP];
+  float2 mbox[2][kTP];          // [iteration parity][pixel] = (max of the PEER side's logits, its W-step exp sum), written by the peer
+  float rz[kL];
+  float zp[kL];
+  uint64_t bar_mma;
+  uint64_t bar_nu[2];
+  uint64_t bar_w;
+  uint64_t bar_zp;
+  uint32_t tmem_base;
+  int abort_flag;
+};
+constexpr uint32_t kSmemBytes = kOffMisc + sizeof(Misc) + 128;
+static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
+
+constexpr uint32_t kColE = 0;      // [128 px][128]   logits of this side
+constexpr uint32_t kColM = 128;    // [128 l][80]     M-step sums
+                                   // nu: [128 l][256 d] of side s at columns 256 s
+}  // namespace emr
+
+struct EmResParams {
+  const float* x;
+  const float* v;
+  const float* masks;
+  const float* kappa_prior;
+  const float* nu_prior;
+  const float* zita_prior;
+  float* kappa;
+  float* nu;
+  float* zita;
+  float* z_last;
+  float* acc_k;          // [U][n_iters][2][65][128], zeroed before launch
+  float* acc_nu;         // [U][2][512][128], zeroed before launch
+  unsigned* counters;    // [U][n_iters][2] then [U] (nu), zeroed before launch
+  int* status;
+  long long* prof;
+  int N, HW, T, n_iters, u0, L;
+  int U;                 // units of the whole call (the nu counters follow the U * n_iters * 2 M-step counters)
+  float c1s;             // log2(e) / (tau * kKScale)
+};
+
+// labelled time stamps of CTA 0: prof[0] = -count, prof[1 + k] = (ns << 8) | label
+#define EMR_STAMP(id)                                                                                               \
+  do {                                                                                                              \
+    if (p.prof != nullptr && blockIdx.x == 0 && tid == 0 && n_stamp < 120) p.prof[1 + n_stamp++] = (global_ns() << 8) | (id); \
+  } while (0)
+
+__device__ __forceinline__ void st_cluster_u4(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+// remote store + transaction-count arrival on the destination CTA's mbarrier (no fence on either side: the data is visible
+// to whoever observes the phase completion)
+__device__ __forceinline__ void st_async_f2(uint32_t addr, float a, float b, uint32_t bar) {
+  asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [%0], {%1, %2}, [%3];" ::"r"(addr), "f"(a), "f"(b), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void st_async_u4(uint32_t addr, const uint4& v, uint32_t bar) {
+  asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(addr), "r"(v.x), "r"(v.y),
+               "r"(v.z), "r"(v.w), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ bool warp_wait(uint64_t* bar, uint32_t parity, int) {
+  int ok = 1;
+  if ((threadIdx.x & 31) == 0) ok = tc05::mbar_wait(bar, parity) ? 1 : 0;
+  return __shfl_sync(0xffffffffu, ok, 0) != 0;
+}
+// cross-tile wait: one thread polls the arrival counter back to back (bounded)
+__device__ __forceinline__ bool wait_counter_fast(const unsigned* counter, unsigned target) {
+#pragma unroll 1
+  for (unsigned i = 0; i < (1u << 22); ++i)
+    if (ld_acquire_u32(counter) >= target) return true;
+  return false;
+}
+__device__ __forceinline__ bool warp_wait_cluster(uint64_t* bar, uint32_t parity) {
+  int ok = 1;
+  if ((threadIdx.x & 31) == 0) ok = mbar_wait_cluster(bar, parity) ? 1 : 0;
+  return __shfl_sync(0xffffffffu, ok, 0) != 0;
+}
+
+template <bool VPM>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(emr::kThreads, 1) em_res_kernel(const EmResParams p) {
+  using namespace emr;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  Misc& ms = *reinterpret_cast<Misc*>(smem + kOffMisc);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int rank = (int)cluster_ctarank();
+  const int sd = rank;                                  // side of the E / M steps (0 = background, 1 = foreground); value-channel half of the nu phase
+  const int pair = blockIdx.x >> 1;
+  const int tile = pair % p.T;
+  const int u = p.u0 + pair / p.T;
+  const int b = u / p.N;
+  const int p0 = tile * kTP;
+  const int HW = p.HW, I = p.n_iters, L = p.L;
+  const uint32_t sbase = smem_u32(smem);
+  int n_stamp = 0;
+  EMR_STAMP(0);
+
+  // thread roles
+  const int q = warp & 3, cb = warp >> 2;               // TMEM lane quadrant, column block
+  const int px = q * 32 + lane;                         // epilogue: pixel (32 logits columns [32 cb, +32)); reduce-add: row l (16 columns [16 cb, +16))
+  const int frow = tid >> 2, fcg = tid & 3;             // finalize: basis row, block of 16 key channels
+  const int gs = u * 2 + sd;
+
+  if (warp == 0) tmem_alloc(&ms.tmem_base, 512);
+  if (tid == 0) {
+    mbar_init(&ms.bar_mma, 1);
+    mbar_init(&ms.bar_nu[0], 1);
+    mbar_init(&ms.bar_nu[1], 1);
+    mbar_init(&ms.bar_w, 1);                           // + transaction bytes: the peer's st.async stores
+    mbar_init(&ms.bar_zp, 1);
+    ms.abort_flag = 0;
+    fence_mbar_init();
+  }
+  cluster_arrive();                                     // (waited for below: the peer is running and its barriers exist before any remote access)
+
+  // ---- V -> fp16 B operand, in rounds of one warp step per warp (2 rounds cover the CTA's [256 d][128 px]) -------------------
+  // load phase (8 x 16 bytes per lane in flight) and convert / store phase are separate calls so that the loads overlap a barrier
+  float4 vf[8];
+  auto v_load = [&](int round) {
+    const int s = round * 16 + warp;                    // warp step 0..31
+    if constexpr (VPM) {                                // v [U][HW][512]: 8 pixels x 128 channels per step, the lane owns 4 channels
+      const int g = s >> 1, d = (s & 1) * 128 + lane * 4;
+      const float* src = p.v + ((size_t)u * HW) * kCv + rank * kDH + d;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int pp = p0 + g * 8 + e;
+        vf[e] = pp < HW ? __ldg(reinterpret_cast<const float4*>(src + (size_t)pp * kCv)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    } else {                                            // v [U][512][HW]: 32 channels x 32 pixels per step, the lane owns 4 x (1 channel, 8 pixels)
+      const int cblk = s >> 2, pq = s & 3;
+      const int pp0 = p0 + pq * 32 + (lane & 3) * 8;
+      const bool vec = ((HW & 3) == 0) && (pp0 + 7 < HW);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int d = cblk * 32 + j * 8 + (lane >> 2);
+        const float* src = p.v + ((size_t)u * kCv + rank * kDH + d) * HW + pp0;
+        if (vec) {
+          vf[2 * j] = __ldg(reinterpret_cast<const float4*>(src));
+          vf[2 * j + 1] = __ldg(reinterpret_cast<const float4*>(src) + 1);
+        } else {
+          float t[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) t[e] = (pp0 + e < HW) ? __ldg(src + e) : 0.f;
+          vf[2 * j] = make_float4(t[0], t[1], t[2], t[3]);
+          vf[2 * j + 1] = make_float4(t[4], t[5], t[6], t[7]);
+        }
+      }
+    }
+  };
+  auto v_store = [&](int round) {
+    const int s = round * 16 + warp;
+    if constexpr (VPM) {
+      const int g = s >> 1, d = (s & 1) * 128 + lane * 4;
+      uint8_t* dst = smem + kOffV + d * 16 + g * 4096;  // (d % 8) * 16 + (d / 8) * 128 = d * 16
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        __align__(16) __half hv[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) hv[e] = __float2half_rn(k == 0 ? vf[e].x : k == 1 ? vf[e].y : k == 2 ? vf[e].z : vf[e].w);
+        *reinterpret_cast<uint4*>(dst + k * 16) = *reinterpret_cast<uint4*>(hv);
+      }
+    } else {
+      const int cblk = s >> 2, pq = s & 3;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int d = cblk * 32 + j * 8 + (lane >> 2);
+        __align__(16) __half hv[8];
+        hv[0] = __float2half_rn(vf[2 * j].x); hv[1] = __float2half_rn(vf[2 * j].y);
+        hv[2] = __float2half_rn(vf[2 * j].z); hv[3] = __float2half_rn(vf[2 * j].w);
+        hv[4] = __float2half_rn(vf[2 * j + 1].x); hv[5] = __float2half_rn(vf[2 * j + 1].y);
+        hv[6] = __float2half_rn(vf[2 * j + 1].z); hv[7] = __float2half_rn(vf[2 * j + 1].w);
+        *reinterpret_cast<uint4*>(smem + kOffV + d * 16 + (pq * 4 + (lane & 3)) * 4096) = *reinterpret_cast<uint4*>(hv);
+      }
+    }
+  };
+  // rounds that cannot hide behind the barriers of iterations 0 .. I-2 are done during set-up
+  int v_round = 0;
+  const int v_setup = (I - 1 >= 2) ? 0 : 2 - (I - 1);
+  if (v_setup > 0) v_load(0);                           // in flight across the X / khat staging
+
+  // ---- khat = l2norm(kappa) * 256 -> fp16 hi/lo K-major rows (reference :115); 4 threads per row, 16 channels each --------
+  const bool valid_row = frow < L;
+  auto stage_khat = [&](const float (&kap)[16]) {
+    float ss = 0.f;
+#pragma unroll
+    for (int c = 0; c < 16; ++c) ss = fmaf(kap[c], kap[c], ss);
+    ss += __shfl_xor_sync(0xffffffffu, ss, 1);
+    ss += __shfl_xor_sync(0xffffffffu, ss, 2);
+    const float sc = kKScale / (sqrtf(ss) + kEpsNorm);
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+      __align__(16) __half hi[8];
+      __align__(16) __half lo[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) split_half(kap[g * 8 + e] * sc, hi[e], lo[e]);
+      const uint32_t off = (frow % 8) * 16 + (frow / 8) * 128 + (fcg * 2 + g) * 2048;
+      *reinterpret_cast<uint4*>(smem + kOffKH + off) = *reinterpret_cast<uint4*>(hi);
+      *reinterpret_cast<uint4*>(smem + kOffKL + off) = *reinterpret_cast<uint4*>(lo);
+    }
+  };
+  {
+    float kap0[16];
+    const float* kprior = p.kappa_prior + ((size_t)gs * kCk + fcg * 16) * L + (valid_row ? frow : 0);
+#pragma unroll
+    for (int c = 0; c < 16; ++c) kap0[c] = valid_row ? __ldg(kprior + (size_t)c * L) : 0.f;
+    stage_khat(kap0);
+  }
+  // prior term of the M-step, added once per (unit, side) by the CTA of tile 0: zita_ * kappa_ (and zita_ itself), scaled like
+  // the tensor-core sums; held by the reduce-add thread of (row px, columns [16 cb, +16))
+  float pri[16], pri_z = 0.f;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) pri[j] = 0.f;
+  const float zita_prior_f = (frow < L) ? __ldg(p.zita_prior + (size_t)gs * L + frow) : 0.f;   // finalize mapping (zita_ of row frow)
+  if (tile == 0 && px < L) {
+    const float zp = __ldg(p.zita_prior + (size_t)gs * L + px) * kZScale;
+    const float* kprior = p.kappa_prior + ((size_t)gs * kCk + cb * 16) * L + px;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) pri[j] = zp * __ldg(kprior + (size_t)j * L);
+    pri_z = zp;
+  }
+  // pixel norms (4 threads per pixel, 16 channels each) + this side's mask
+  {
+    const int pq = tid & 127, cq = tid >> 7, pp = p0 + pq;
+    float ss = 0.f;
+    if (pp < HW) {
+      const float* xp = p.x + ((size_t)b * kCk + cq * 16) * HW + pp;
+#pragma unroll
+      for (int c = 0; c < 16; ++c) {
+        const float t = __ldg(xp + (size_t)c * HW);
+        ss = fmaf(t, t, ss);
+      }
+    }
+    ms.hew[cq][pq] = ss;
+    if (cq == 0) ms.mask[pq] = pp < HW ? __ldg(p.masks + (size_t)gs * HW + pp) : 0.f;
+  }
+  // X tile -> fp16 hi/lo chunks: thread -> (channel c = tid / 8, 2 pixel groups of 8)
+  {
+    const int c = tid >> 3;
+    const float* xrow = p.x + ((size_t)b * kCk + c) * HW;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int pg = (tid & 7) * 2 + j;
+      const int pp0 = p0 + pg * 8;
+      float t[8];
+      if (((HW & 3) == 0) && pp0 + 7 < HW) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(xrow + pp0));
+        const float4 bq = __ldg(reinterpret_cast<const float4*>(xrow + pp0) + 1);
+        t[0] = a.x; t[1] = a.y; t[2] = a.z; t[3] = a.w; t[4] = bq.x; t[5] = bq.y; t[6] = bq.z; t[7] = bq.w;
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) t[e] = (pp0 + e < HW) ? __ldg(xrow + pp0 + e) : 0.f;
+      }
+      __align__(16) __half hi[8];
+      __align__(16) __half lo[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) split_half(t[e], hi[e], lo[e]);
+      const uint32_t off = (c % 8) * 16 + (c / 8) * 2048 + pg * 128;
+      *reinterpret_cast<uint4*>(smem + kOffXH + off) = *reinterpret_cast<uint4*>(hi);
+      *reinterpret_cast<uint4*>(smem + kOffXL + off) = *reinterpret_cast<uint4*>(lo);
+    }
+  }
+  if (tid < 256) {                    // augmented rows 64..79 of XH: row 64 = 1 (-> zita), rest 0
+    const int r = kCk + (tid >> 4), pg = tid & 15;
+    const __half one = __float2half_rn(r == kCk ? 1.f : 0.f);
+    __align__(16) __half vals[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) vals[e] = one;
+    *reinterpret_cast<uint4*>(smem + kOffXH + (r % 8) * 16 + (r / 8) * 2048 + pg * 128) = *reinterpret_cast<uint4*>(vals);
+  }
+  for (; v_round < v_setup; ++v_round) {
+    v_store(v_round);
+    if (v_round + 1 < v_setup) v_load(v_round + 1);
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  if (tid < kTP) ms.inv_nx[tid] = 1.f / (sqrtf(ms.hew[0][tid] + ms.hew[1][tid] + ms.hew[2][tid] + ms.hew[3][tid]) + kEpsNorm);
+  cluster_wait();
+  const uint32_t tmem = ms.tmem_base;
+  uint32_t ph_mma = 0, ph_w = 0;
+  bool failed = false;
+  EMR_STAMP(1);                      // set-up done
+
+  const uint32_t idesc_e = make_idesc(128, 128, kFmtF16, kFmtF16, kMajorMN, kMajorK);
+  const uint32_t idesc_mhi = make_idesc(128, kCk + 16, kFmtF16, kFmtF16, kMajorMN, kMajorK);
+  const uint32_t idesc_mlo = make_idesc(128, kCk, kFmtF16, kFmtF16, kMajorMN, kMajorK);
+  const uint32_t idesc_nu = make_idesc(128, 256, kFmtF16, kFmtF16, kMajorMN, kMajorK);
+  const uint32_t peer = (uint32_t)(rank ^ 1);
+  const uint32_t peer_mbox = map_to_peer(smem_u32(&ms.mbox[0][0]), peer);
+  const uint32_t peer_bar_w = map_to_peer(smem_u32(&ms.bar_w), peer);
+  const uint32_t peer_bar_zp = map_to_peer(smem_u32(&ms.bar_zp), peer);
+  const uint32_t peer_zp = map_to_peer(sbase + kOffZP, peer);
+  const bool mma_thread = (tid == 32);                  // (thread 0 runs the cross-tile barriers, which block in fences)
+  constexpr float kInvZ = 1.f / kZScale;
+
+  // finalize from the completed totals of iteration `it`: kappa = total / zita_total (the prior is part of the totals)
+  auto finalize = [&](const float* acc, bool last) {
+    const float zt = __ldcg(acc + kCk * kL + frow);
+    const float rz = valid_row ? 1.f / zt : 0.f;
+    float kap[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) kap[c] = __ldcg(acc + (fcg * 16 + c) * kL + frow) * rz;
+    if (last) {
+      if (fcg == 0) {
+        ms.rz[frow] = valid_row ? kZScale * rz : 0.f;   // 1 / zita in true units
+        ms.zp[frow] = zita_prior_f;
+      }
+      if (tile == 0 && valid_row) {
+        if (fcg == 0) p.zita[(size_t)gs * L + frow] = zt * kInvZ;
+        float* kout = p.kappa + ((size_t)gs * kCk + fcg * 16) * L + frow;
+#pragma unroll
+        for (int c = 0; c < 16; ++c) kout[(size_t)c * L] = kap[c];
+      }
+    } else {
+      stage_khat(kap);
+    }
+  };
+
+  // column block leader (warp 4 cb, lane 0): reduce-add the block's 8 KB of the staged M-step partial, then arrive
+  auto reduce_block_and_arrive = [&](float* acc, unsigned* counter) {
+    bar_sync(5 + cb, 128);                              // the 4 warps of this column block have staged their rows
+    if (q == 0 && lane == 0) {
+      asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(acc + cb * 16 * kL),
+                   "r"(sbase + kOffKH + (uint32_t)(cb * 16 * kL * 4)), "r"(16 * kL * 4)
+                   : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+      __threadfence();
+      atomicAdd(counter, 1u);
+    }
+  };
+
+  for (int it = 0; it < I; ++it) {
+    const bool last = (it == I - 1);
+    fence_proxy_async_smem();
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+
+    // ---- (1) logits of this side: a[p, l] = x_p . khat_l (hi/lo split, 3 products) ----------------------------------
+    if (mma_thread) {
+#pragma unroll
+      for (int term = 0; term < 3; ++term) {
+        const uint32_t xa = sbase + (term == 2 ? kOffXL : kOffXH);
+        const uint32_t kb = sbase + (term == 1 ? kOffKL : kOffKH);
+#pragma unroll
+        for (int kk = 0; kk < kCk / 16; ++kk) {
+          const uint64_t ad = make_sdesc(xa + kk * 2 * 2048, /*lbo*/ 2048, /*sbo*/ 128);
+          const uint64_t bd = make_sdesc(kb + kk * 2 * 2048, /*lbo*/ 2048, /*sbo*/ 128);
+          mma_f16_ss(tmem + kColE, ad, bd, idesc_e, (term | kk) ? 1u : 0u);
+        }
+      }
+      mma_commit(&ms.bar_mma);
+    }
+    SWEM_CTA_WAIT(&ms.bar_mma, ph_mma, ms.abort_flag);
+    ph_mma ^= 1;
+    tc_fence_after_sync();
+    EMR_STAMP(2);                    // logits GEMM done
+
+    // ---- (2) epilogue: thread <-> (pixel px, columns [32 cb, +32) of this side's bases) -------------------------------
+    {
+      const bool do_w = it > 0;
+      const bool active = cb * 32 < L;                  // L = 64: the upper half of the columns is padding
+      if (tid == 0) {                                   // arm the receive barriers of this iteration
+        if (do_w) mbar_expect_tx(&ms.bar_w, kTP * sizeof(float2));
+        if (last) mbar_expect_tx(&ms.bar_zp, 16 * 2048);
+      }
+      float a[32];
+      {
+        uint32_t r[32];
+        tmem_ld32(tmem_addr(tmem, q * 32, kColE + cb * 32), r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) a[j] = __uint_as_float(r[j]);
+      }
+      // exps against the thread's own max; the blocks of a pixel are rescaled onto the side max afterwards:
+      // exp(t - M) = exp(t - m) * exp(m - M).  W-step (reference :93-110): same logits times 1 / ||x_p||.
+      const float cw = ms.inv_nx[px] * p.c1s;
+      float mloc = -3.0e38f, se = 0.f, ew = 0.f;
+      if (active) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) mloc = fmaxf(mloc, a[j]);
+        if (do_w) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) ew += fast_exp2((a[j] - mloc) * cw);
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          a[j] = fast_exp2((a[j] - mloc) * p.c1s);
+          se += a[j];
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) a[j] = 0.f;
+      }
+      ms.hmax[cb][px] = mloc;
+      ms.hsum[cb][px] = se;
+      ms.hew[cb][px] = ew;
+      bar_sync(1 + q, 128);                             // the 4 warps that share this lane quadrant
+      float m_side = fmaxf(fmaxf(ms.hmax[0][px], ms.hmax[1][px]), fmaxf(ms.hmax[2][px], ms.hmax[3][px]));
+      float S = 0.f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) S += ms.hsum[k][px] * fast_exp2((ms.hmax[k][px] - m_side) * p.c1s);
+      float w = ms.mask[px];
+      if (do_w) {
+        float EW = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) EW += ms.hew[k][px] * fast_exp2((ms.hmax[k][px] - m_side) * cw);
+        const int par = it & 1;
+        if (cb == 0) st_async_f2(peer_mbox + (uint32_t)((par * kTP + px) * sizeof(float2)), m_side, EW, peer_bar_w);
+        if (!warp_wait(&ms.bar_w, ph_w, 0)) ms.abort_flag = 1;
+        ph_w ^= 1;
+        const float2 o = ms.mbox[par][px];              // the peer side's (max, W-step sum)
+        const float gm = fmaxf(m_side, o.x);
+        const float e_own = EW * fast_exp2((m_side - gm) * cw), e_peer = o.y * fast_exp2((o.x - gm) * cw);
+        w *= 1.f - e_own / (e_own + e_peer);
+      }
+      const float scale = active ? (w / S) * fast_exp2((mloc - m_side) * p.c1s) : 0.f;
+      const float zs = scale * kZScale;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        __align__(16) __half hi[8];
+        __align__(16) __half lo[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) split_half(a[g * 8 + k] * zs, hi[k], lo[k]);
+        const uint32_t off = (px % 8) * 16 + (px / 8) * 128 + (cb * 4 + g) * 2048;
+        *reinterpret_cast<uint4*>(smem + kOffZ + off) = *reinterpret_cast<uint4*>(hi);
+        *reinterpret_cast<uint4*>(smem + kOffZL + off) = *reinterpret_cast<uint4*>(lo);
+        if (last) st_async_u4(peer_zp + off, *reinterpret_cast<uint4*>(hi), peer_bar_zp);
+      }
+      if (p.z_last != nullptr && last && p0 + px < HW && active) {
+        float4* dst = reinterpret_cast<float4*>(p.z_last + ((size_t)gs * HW + p0 + px) * L + cb * 32);
+#pragma unroll
+        for (int g = 0; g < 8; ++g)
+          dst[g] = make_float4(a[g * 4] * scale, a[g * 4 + 1] * scale, a[g * 4 + 2] * scale, a[g * 4 + 3] * scale);
+      }
+    }
+    fence_proxy_async_smem();
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    EMR_STAMP(3);                    // epilogue done
+
+    // ---- (3) M-step GEMM: [sum_p z x | sum_p z] for this side's 128 bases (3 products) ----------------------------------
+    if (mma_thread) {
+#pragma unroll
+      for (int kk = 0; kk < 8; ++kk) {
+        const uint64_t ad = make_sdesc(sbase + kOffZ + kk * 2 * 128, /*lbo*/ 128, /*sbo*/ 2048);
+        const uint64_t al = make_sdesc(sbase + kOffZL + kk * 2 * 128, /*lbo*/ 128, /*sbo*/ 2048);
+        const uint64_t bh = make_sdesc(sbase + kOffXH + kk * 2 * 128, /*lbo*/ 128, /*sbo*/ 2048);
+        const uint64_t bl = make_sdesc(sbase + kOffXL + kk * 2 * 128, /*lbo*/ 128, /*sbo*/ 2048);
+        mma_f16_ss(tmem + kColM, ad, bh, idesc_mhi, kk ? 1u : 0u);   // z_hi x_hi (+ zita column)
+        mma_f16_ss(tmem + kColM, ad, bl, idesc_mlo, 1u);             // z_hi x_lo
+        mma_f16_ss(tmem + kColM, al, bh, idesc_mhi, 1u);             // z_lo x_hi
+      }
+      mma_commit(&ms.bar_mma);
+    }
+    SWEM_CTA_WAIT(&ms.bar_mma, ph_mma, ms.abort_flag);
+    ph_mma ^= 1;
+    tc_fence_after_sync();
+    EMR_STAMP(4);                    // M GEMM done
+
+    // ---- (4) partial of this tile -> fp32 reductions straight from TMEM into the L2-resident accumulator [c][l] ----------
+    float* acc = p.acc_k + ((size_t)((u * I + it) * 2 + sd)) * ((kCk + 1) * kL);
+    // (staged in the khat / z_lo region -- dead between the M-step GEMM and the finalize -- and reduce-added by the bulk-copy
+    //  engine in four 8 KB pieces, one per column block: far fewer L2 atomic transactions than per-lane reductions)
+    unsigned* counter = p.counters + ((size_t)u * I + it) * 2 + sd;
+    {
+      uint32_t r[16];
+      tmem_ld16(tmem_addr(tmem, q * 32, kColM + cb * 16), r);
+      uint32_t rz16[16];
+      if (cb == 0) tmem_ld16(tmem_addr(tmem, q * 32, kColM + kCk), rz16);
+      tmem_ld_wait();
+      float* ns = reinterpret_cast<float*>(smem + kOffKH);        // [64 c][128 l] fp32
+#pragma unroll
+      for (int j = 0; j < 16; ++j) ns[(cb * 16 + j) * kL + px] = __uint_as_float(r[j]) + pri[j];
+      if (cb == 0) atomicAdd(acc + kCk * kL + px, __uint_as_float(rz16[0]) + pri_z);
+      fence_proxy_async_smem();
+    }
+    if (!last) {
+      const bool conv = v_round < 2;
+      if (conv) v_load(v_round);                        // loads fly across the arrival
+      tc_fence_before_sync();
+      EMR_STAMP(5);                                     // partial staged
+      reduce_block_and_arrive(acc, counter);
+      EMR_STAMP(6);                                     // reduce-added + arrived
+      if (conv) {
+        v_store(v_round);
+        ++v_round;
+      }
+      if (tid == 0) {
+        if (!wait_counter_fast(counter, 4u * (unsigned)p.T)) ms.abort_flag = 1;
+        EMR_STAMP(7);                                   // all tiles arrived
+      }
+      __syncthreads();
+      if (!ms.abort_flag) finalize(acc, false);
+      EMR_STAMP(8);                                     // finalize done (before the loop-top barrier)
+    } else {
+      // ---- last iteration: kappa all-reduce under the nu GEMMs, own-side drain under the peer-side GEMM ----------------
+      tc_fence_before_sync();
+      __syncthreads();                                  // every warp has read its M-step columns: TMEM is free for nu
+      tc_fence_after_sync();
+      if (mma_thread) {
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+          const uint64_t ad = make_sdesc(sbase + kOffZ + ks * 2 * 128, /*lbo*/ 128, /*sbo*/ 2048);
+          const uint64_t bd = make_sdesc(sbase + kOffV + ks * 2 * 4096, /*lbo*/ 4096, /*sbo*/ 128);
+          mma_f16_ss(tmem + sd * 256, ad, bd, idesc_nu, ks ? 1u : 0u);
+        }
+        mma_commit(&ms.bar_nu[0]);
+      }
+      EMR_STAMP(5);
+      reduce_block_and_arrive(acc, counter);            // (before the issuing thread blocks on the peer's z: it is part of a block barrier)
+      EMR_STAMP(6);
+      if (mma_thread) {
+        if (!mbar_wait(&ms.bar_zp, 0)) ms.abort_flag = 1;   // the peer's z has landed in ZP
+        asm volatile("fence.proxy.async;" ::: "memory");
+        tc_fence_after_sync();
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+          const uint64_t ad = make_sdesc(sbase + kOffZP + ks * 2 * 128, /*lbo*/ 128, /*sbo*/ 2048);
+          const uint64_t bd = make_sdesc(sbase + kOffV + ks * 2 * 4096, /*lbo*/ 4096, /*sbo*/ 128);
+          mma_f16_ss(tmem + (sd ^ 1) * 256, ad, bd, idesc_nu, ks ? 1u : 0u);
+        }
+        mma_commit(&ms.bar_nu[1]);
+      }
+      if (tid == 0) {
+        if (!wait_counter_fast(counter, 4u * (unsigned)p.T)) ms.abort_flag = 1;
+        EMR_STAMP(7);
+      }
+      __syncthreads();
+      if (!ms.abort_flag) finalize(acc, true);
+      EMR_STAMP(8);
+      // drain: TMEM [128 l][256 d] of side s -> smem [64 d][128 l] fp32 -> bulk reduce-add into acc_nu; 4 rounds per side, two
+      // staging buffers over the X / khat region (dead: the M-step GEMM has completed)
+#pragma unroll 1
+      for (int rr = 0; rr < 8; ++rr) {
+        const int sidx = (rr < 4) ? sd : (sd ^ 1);
+        if (rr == 0 || rr == 4) {
+          SWEM_CTA_WAIT(&ms.bar_nu[rr >> 2], 0, ms.abort_flag);
+          tc_fence_after_sync();
+          EMR_STAMP(9 + (rr >> 2));                     // nu GEMM of the own / peer side done
+        }
+        float* ns = reinterpret_cast<float*>(smem + (rr & 1) * kStageBytes);
+        if (rr >= 2) {
+          if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          __syncthreads();
+        }
+        {
+          uint32_t r[16];
+          tmem_ld16(tmem_addr(tmem, q * 32, sidx * 256 + (rr & 3) * 64 + cb * 16), r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) ns[(cb * 16 + j) * kL + px] = __uint_as_float(r[j]);
+        }
+        fence_proxy_async_smem();
+        __syncthreads();
+        if (tid == 0) {
+          float* dst = p.acc_nu + (((size_t)u * 2 + sidx) * kCv + rank * kDH + (rr & 3) * 64) * kL;
+          asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(dst),
+                       "r"(smem_u32(ns)), "r"(kStageBytes)
+                       : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+      }
+      unsigned* counter_nu = p.counters + (size_t)p.U * I * 2 + u;
+      if (tid == 0) {
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // full completion (not just .read) before the arrival
+        EMR_STAMP(11);                                  // nu drained
+        __threadfence();
+        atomicAdd(counter_nu, 1u);
+        if (!wait_counter_fast(counter_nu, 2u * (unsigned)p.T)) ms.abort_flag = 1;
+        EMR_STAMP(12);                                  // every CTA of the unit has drained
+      }
+      tc_fence_before_sync();
+      __syncthreads();
+    }
+    if (ms.abort_flag) {
+      if (tid == 0) atomicExch(p.status, 1 + it);
+      failed = true;
+      break;
+    }
+  }
+
+  if (!failed) {
+    // ---- nu = (zita_ nu_ + sum / 2^14) / zita (reference :164-165) for side sd, this tile's slice of value channels --------
+    const int dper = (kCv + p.T - 1) / p.T;
+    const int d0 = tile * dper, d1 = min(kCv, d0 + dper);
+    const float4* acc4 = reinterpret_cast<const float4*>(p.acc_nu + (size_t)gs * kCv * kL);     // [d][128]
+    const float4* pri4 = reinterpret_cast<const float4*>(p.nu_prior + (size_t)gs * kCv * L);    // [d][L]
+    float4* out4 = reinterpret_cast<float4*>(p.nu + (size_t)gs * kCv * L);
+    const int l4n = (L < kL ? L : kL) / 4;
+    for (int k = d0 * l4n + tid; k < d1 * l4n; k += kThreads) {
+      const int d = k / l4n, l4 = k % l4n, l = l4 * 4;
+      const int i = d * (L / 4) + l4;
+      const float4 a = __ldcg(acc4 + d * (kL / 4) + l4);
+      const float4 pr = __ldg(pri4 + i);
+      float4 o;
+      o.x = (ms.zp[l + 0] * pr.x + a.x * kInvZ) * ms.rz[l + 0];
+      o.y = (ms.zp[l + 1] * pr.y + a.y * kInvZ) * ms.rz[l + 1];
+      o.z = (ms.zp[l + 2] * pr.z + a.z * kInvZ) * ms.rz[l + 2];
+      o.w = (ms.zp[l + 3] * pr.w + a.w * kInvZ) * ms.rz[l + 3];
+      out4[i] = o;
+    }
+    EMR_STAMP(13);                   // nu slice written
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (p.prof != nullptr && blockIdx.x == 0 && tid == 0) p.prof[0] = -(long long)n_stamp;
+  if (warp == 0) tmem_dealloc(tmem, 512);
+  cluster_arrive();                  // a CTA must not exit while its peer may still write into its shared memory
+  cluster_wait();
+  if (failed || ms.abort_flag) __trap();
+}
+
+// ------------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------------
+template <bool VPM>
+static int res_clusters_resident() {
+  static PerDevice cache;                                // occupancy and the shared-memory attribute are per device
+  const int dev_id = current_device();
+  std::lock_guard<std::mutex> lock(cache.mu);
+  int& n = cache.value[dev_id];
+  if (n < 0) {
+    cudaFuncSetAttribute(em_res_kernel<VPM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)emr::kSmemBytes);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2, 1, 1);
+    cfg.blockDim = dim3(emr::kThreads, 1, 1);
+    cfg.dynamicSmemBytes = emr::kSmemBytes;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int clusters = 0;
+    if (cudaOccupancyMaxActiveClusters(&clusters, em_res_kernel<VPM>, &cfg) != cudaSuccess || clusters <= 0) {
+      cudaGetLastError();
+      int dev = 0, sms = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      clusters = sms / 2 - 4;                            // conservative guess
+    }
+    n = clusters;
+  }
+  return n;
+}
+
+// Shapes of the V-resident kernel: Ck = 64, L <= 128, and a unit's tile pairs co-resident (single-launch form)
+bool fused_em_res_covers(const SwemDims& d, bool v_pixel_major) {
+  if (d.Ck != emr::kCk || (d.L != 64 && d.L != 128) || d.Cv != emr::kCv || d.n_iters < 1 || d.n_iters > 16) return false;
+  const char* off = getenv("SWEM_EM_RES");
+  if (off != nullptr && off[0] == '0') return false;     // A/B switch: SWEM_EM_RES=0 runs em_pair_kernel on these shapes too
+  const char* force_w = getenv("SWEM_EM_WINDOWED");
+  if (force_w != nullptr && force_w[0] == '1') return false;
+  const int T = (d.HW + emr::kTP - 1) / emr::kTP;
+  const int resident = v_pixel_major ? res_clusters_resident<true>() : res_clusters_resident<false>();
+  return T >= 1 && T <= resident;
+}
+
+template <bool VPM>
+static int fused_em_res_forward_t(const SwemEmArgs& a, cudaStream_t st) {
+  const SwemDims& d = a.dims;
+  const int U = d.B * d.N;
+  const int T = (d.HW + emr::kTP - 1) / emr::kTP;
+  Arena ws(a.workspace);
+  float* acc_k = ws.take<float>((size_t)U * d.n_iters * 2 * (emr::kCk + 1) * emr::kL);
+  float* acc_nu = ws.take<float>((size_t)U * 2 * emr::kCv * emr::kL);
+  unsigned* counters = ws.take<unsigned>((size_t)U * d.n_iters * 2 + U + 1);
+  int* status = reinterpret_cast<int*>(counters + (size_t)U * d.n_iters * 2 + U);
+  SWEM_CUDA(cudaMemsetAsync(a.workspace, 0, ws.off, st));
+  count_launch();
+
+  EmResParams p{};
+  p.x = a.x; p.v = a.v; p.masks = a.masks;
+  p.kappa_prior = a.kappa_prior; p.nu_prior = a.nu_prior; p.zita_prior = a.zita_prior;
+  p.kappa = a.kappa; p.nu = a.nu; p.zita = a.zita; p.z_last = a.z_last;
+  p.acc_k = acc_k; p.acc_nu = acc_nu; p.counters = counters; p.status = status;
+  p.N = d.N; p.HW = d.HW; p.T = T; p.n_iters = d.n_iters; p.L = d.L; p.U = U;
+  p.c1s = kLog2e / (d.tau * emr::kKScale);
+  p.prof = get_profile_buffer();
+  // all CTAs of a launch spin on each other, so every launch must be co-resident (1 CTA per SM); units that do not fit are
+  // spread evenly over the fewest launches
+  const int upl_max = res_clusters_resident<VPM>() / T;
+  const int n_launch = (U + upl_max - 1) / upl_max;
+  const int upl = (U + n_launch - 1) / n_launch;
+  for (int u0 = 0; u0 < U; u0 += upl) {
+    const int nu = (U - u0 < upl) ? (U - u0) : upl;
+    p.u0 = u0;
+    em_res_kernel<VPM><<<nu * T * 2, emr::kThreads, emr::kSmemBytes, st>>>(p);
+    SWEM_LAUNCH_CHECK();
+  }
+  return SWEM_OK;
+}
+
+int fused_em_res_forward(const SwemEmArgs& a, cudaStream_t st) {
+  return a.v_pixel_major ? fused_em_res_forward_t<true>(a, st) : fused_em_res_forward_t<false>(a, st);
+}
+
+}  // namespace swem

@@ -1,0 +1,13 @@
+#!/bin/bash
+# Round-2 EM bring-up: EM parity tests on the V-resident kernel, phase profile, A/B against em_pair_kernel.  Output -> gpurun_out/
+cd "$(dirname "$0")/.."
+TAG=${TAG:-r2em}
+rm -f gpurun_out/parity_report.txt
+timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "${TESTS:-fused or golden or iteration or responsibilities or encoder}" 2>&1 | tail -25 > gpurun_out/${TAG}_tests.log
+cp gpurun_out/parity_report.txt gpurun_out/${TAG}_parity_report.txt 2>/dev/null
+tail -8 gpurun_out/${TAG}_tests.log
+timeout 300 python tools/profile_phases.py > gpurun_out/${TAG}_phases.log 2>&1
+SWEM_EM_RES=0 timeout 300 python tools/profile_phases.py > gpurun_out/${TAG}_phases_pair.log 2>&1
+grep -v "^  " gpurun_out/${TAG}_phases.log | head -30
+sed -n 1,60p gpurun_out/${TAG}_phases.log
+grep "memorize" gpurun_out/${TAG}_phases_pair.log

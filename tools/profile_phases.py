@@ -24,8 +24,21 @@ def main(N=5, H=30, W=54, I=4, reps=50):
         lib.swem_set_profile_buffer(None, 0)
         st = buf.cpu().tolist()
         n = st[0]
+        if n < 0:                         # labelled stamps of em_res_kernel: (ns << 8) | label
+            LABELS = {0: 'start', 1: 'setup', 2: 'logits GEMM', 3: 'epilogue', 4: 'M GEMM', 5: 'reduce-add issued', 6: 'fence + arrive',
+                      7: 'wait tiles', 8: 'finalize', 9: 'nu GEMM own side', 10: 'nu GEMM peer side', 11: 'nu drain', 12: 'wait nu',
+                      13: 'nu slice'}
+            n = -n
+            raw = st[1:1 + n]
+            t = [r >> 8 for r in raw]
+            ids = [r & 255 for r in raw]
+            print(f'N={N} HW={H*W} I={I}: em_res_kernel, {n} stamps, total {(t[-1]-t[0])/1e3:.1f} us')
+            for k in range(1, n):
+                print(f'  {LABELS.get(ids[k], "?"):24s} {(t[k]-t[k-1])/1e3:8.2f} us')
+            n = 0
         t = st[1:1 + n]
-        print(f'N={N} HW={H*W} I={I}: {n} stamps, total {(t[-1]-t[0])/1e3:.1f} us')
+        if n:
+            print(f'N={N} HW={H*W} I={I}: {n} stamps, total {(t[-1]-t[0])/1e3:.1f} us')
         names = ['setup']
         for it in range(I):
             names += [f'it{it} logits GEMM', f'it{it} epilogue', f'it{it} M GEMM']
