@@ -71,6 +71,7 @@ struct Misc {
   float2 mbox[2][kTP];          // [iteration parity][pixel] = (max of the PEER side's logits, its W-step exp sum), written by the peer
   float rz[kL];
   float zp[kL];
+  __align__(16) float zrow[kL];  // staged zita column of the M-step partial
   uint64_t bar_mma;
   uint64_t bar_nu[2];
   uint64_t bar_w;
@@ -82,7 +83,8 @@ constexpr uint32_t kSmemBytes = kOffMisc + sizeof(Misc) + 128;
 static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 
 constexpr uint32_t kColE = 0;      // [128 px][128]   logits of this side
-constexpr uint32_t kColM = 128;    // [128 l][80]     M-step sums
+                                   // [128 l][80]     M-step sums at column 384 (side 0) / 128 (side 1): inside the PEER side's nu
+                                   //                 columns, so the own-side nu GEMM can follow the last M-step GEMM directly
                                    // nu: [128 l][256 d] of side s at columns 256 s
 }  // namespace emr
 
@@ -97,12 +99,14 @@ struct EmResParams {
   float* nu;
   float* zita;
   float* z_last;
-  float* acc_k;          // [U][n_iters][2][65][128], zeroed before launch
-  float* acc_nu;         // [U][2][512][128], zeroed before launch
-  unsigned* counters;    // [U][n_iters][2] then [U] (nu), zeroed before launch
+  float* acc_k;          // [U][n_iters][2][65][128]   (zeroed by the kernel itself, see "accumulators" below)
+  float* acc_nu;         // [U][2][512][128]
+  unsigned* counters;    // library-owned, zero between launches: [U][n_iters][2] M-step arrivals, then [U] accumulators zeroed,
+                         // [U] nu drained, [U] departed (the last CTA of a unit to leave clears the unit's words again)
   int* status;
   long long* prof;
   int N, HW, T, n_iters, u0, L;
+  int dbg;               // measurement switches (SWEM_EM_DBG): 4 = gpu-scope fence between the completed bulk reduction and the arrival
   int U;                 // units of the whole call (the nu counters follow the U * n_iters * 2 M-step counters)
   float c1s;             // log2(e) / (tau * kKScale)
 };
@@ -164,8 +168,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(emr::kThreads, 1) em
 
   // thread roles
   const int q = warp & 3, cb = warp >> 2;               // TMEM lane quadrant, column block
-  const int px = q * 32 + lane;                         // epilogue: pixel (32 logits columns [32 cb, +32)); reduce-add: row l (16 columns [16 cb, +16))
-  const int frow = tid >> 2, fcg = tid & 3;             // finalize: basis row, block of 16 key channels
+  const int px = q * 32 + lane;                         // epilogue: pixel (32 logits columns [32 cb, +32)); reduce-add / finalize: row l (16 columns [16 cb, +16))
   const int gs = u * 2 + sd;
 
   if (warp == 0) tmem_alloc(&ms.tmem_base, 512);
@@ -179,6 +182,36 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(emr::kThreads, 1) em
     fence_mbar_init();
   }
   cluster_arrive();                                     // (waited for below: the peer is running and its barriers exist before any remote access)
+
+  // ---- accumulators: every CTA clears its slice of the unit's L2 accumulators (the rows of acc_k it would finalize for every
+  // iteration of its side, the value channels of acc_nu it finalizes at the end) with bulk stores from a zeroed shared-memory
+  // buffer, waits for their completion at the end of the set-up and arrives on the unit's "zeroed" counter; nobody reduce-adds
+  // before all 2 T CTAs of the unit have arrived.  No memset launch in front of the kernel.
+  const int rows_per = (kCk + 1 + p.T - 1) / p.T;       // acc_k rows [c][128] per tile
+  const int dper = (kCv + p.T - 1) / p.T;               // acc_nu value channels per tile
+  const int d0 = tile * dper, d1 = min(kCv, d0 + dper);
+  {
+    constexpr uint32_t kZeroBytes = 16384;
+    for (int i = tid; i < (int)(kZeroBytes / 16); i += kThreads) reinterpret_cast<uint4*>(smem + kOffZ)[i] = make_uint4(0u, 0u, 0u, 0u);
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      auto zero_range = [&](float* dst, uint32_t bytes) {
+        for (uint32_t o = 0; o < bytes; o += kZeroBytes) {
+          const uint32_t n = min(kZeroBytes, bytes - o);
+          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(reinterpret_cast<uint8_t*>(dst) + o),
+                       "r"(sbase + kOffZ), "r"(n)
+                       : "memory");
+        }
+      };
+      const int r0 = tile * rows_per, r1 = min(kCk + 1, r0 + rows_per);
+      if (r1 > r0)
+        for (int it = 0; it < I; ++it)
+          zero_range(p.acc_k + ((size_t)((u * I + it) * 2 + sd)) * ((kCk + 1) * kL) + (size_t)r0 * kL, (uint32_t)(r1 - r0) * kL * 4);
+      if (d1 > d0) zero_range(p.acc_nu + ((size_t)gs * kCv + d0) * kL, (uint32_t)(d1 - d0) * kL * 4);
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+  }
 
   // ---- V -> fp16 B operand, in rounds of one warp step per warp (2 rounds cover the CTA's [256 d][128 px]) -------------------
   // load phase (8 x 16 bytes per lane in flight) and convert / store phase are separate calls so that the loads overlap a barrier
@@ -240,19 +273,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(emr::kThreads, 1) em
       }
     }
   };
-  // rounds that cannot hide behind the barriers of iterations 0 .. I-2 are done during set-up
-  int v_round = 0;
-  const int v_setup = (I - 1 >= 2) ? 0 : 2 - (I - 1);
-  if (v_setup > 0) v_load(0);                           // in flight across the X / khat staging
+  // round 0: loads issued here, in flight across the X / khat staging of the set-up; round 1: issued at the top of iteration 0 and
+  // stored after its logits GEMM (I = 1: also during set-up) -- never next to the cross-tile reductions, whose bulk reduce-adds
+  // they would delay by ~1 us (profiles/r2_em_res_phases.txt)
+  v_load(0);
 
-  // ---- khat = l2norm(kappa) * 256 -> fp16 hi/lo K-major rows (reference :115); 4 threads per row, 16 channels each --------
-  const bool valid_row = frow < L;
+  // ---- khat = l2norm(kappa) * 256 -> fp16 hi/lo K-major rows (reference :115).  Thread <-> (row px, channels [16 cb, +16)):
+  // global accesses are coalesced over the rows, the squared norm meets in shared memory across the 4 warps of a lane quadrant
+  const bool valid_row = px < L;
   auto stage_khat = [&](const float (&kap)[16]) {
     float ss = 0.f;
 #pragma unroll
     for (int c = 0; c < 16; ++c) ss = fmaf(kap[c], kap[c], ss);
-    ss += __shfl_xor_sync(0xffffffffu, ss, 1);
-    ss += __shfl_xor_sync(0xffffffffu, ss, 2);
+    ms.hsum[cb][px] = ss;
+    bar_sync(9 + q, 128);
+    ss = (ms.hsum[0][px] + ms.hsum[1][px]) + (ms.hsum[2][px] + ms.hsum[3][px]);
     const float sc = kKScale / (sqrtf(ss) + kEpsNorm);
 #pragma unroll
     for (int g = 0; g < 2; ++g) {
@@ -260,30 +295,25 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(emr::kThreads, 1) em
       __align__(16) __half lo[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) split_half(kap[g * 8 + e] * sc, hi[e], lo[e]);
-      const uint32_t off = (frow % 8) * 16 + (frow / 8) * 128 + (fcg * 2 + g) * 2048;
+      const uint32_t off = (px % 8) * 16 + (px / 8) * 128 + (cb * 2 + g) * 2048;
       *reinterpret_cast<uint4*>(smem + kOffKH + off) = *reinterpret_cast<uint4*>(hi);
       *reinterpret_cast<uint4*>(smem + kOffKL + off) = *reinterpret_cast<uint4*>(lo);
     }
   };
+  // prior term of the M-step, added once per (unit, side) by the CTA of tile 0: zita_ * kappa_ (and zita_ itself), scaled like
+  // the tensor-core sums (same thread mapping as the reduce-add)
+  float pri[16], pri_z = 0.f;
+  const float zita_prior_f = valid_row ? __ldg(p.zita_prior + (size_t)gs * L + px) : 0.f;
   {
     float kap0[16];
-    const float* kprior = p.kappa_prior + ((size_t)gs * kCk + fcg * 16) * L + (valid_row ? frow : 0);
+    const float* kprior = p.kappa_prior + ((size_t)gs * kCk + cb * 16) * L + (valid_row ? px : 0);
 #pragma unroll
     for (int c = 0; c < 16; ++c) kap0[c] = valid_row ? __ldg(kprior + (size_t)c * L) : 0.f;
-    stage_khat(kap0);
-  }
-  // prior term of the M-step, added once per (unit, side) by the CTA of tile 0: zita_ * kappa_ (and zita_ itself), scaled like
-  // the tensor-core sums; held by the reduce-add thread of (row px, columns [16 cb, +16))
-  float pri[16], pri_z = 0.f;
+    const float zp = (tile == 0) ? zita_prior_f * kZScale : 0.f;
 #pragma unroll
-  for (int j = 0; j < 16; ++j) pri[j] = 0.f;
-  const float zita_prior_f = (frow < L) ? __ldg(p.zita_prior + (size_t)gs * L + frow) : 0.f;   // finalize mapping (zita_ of row frow)
-  if (tile == 0 && px < L) {
-    const float zp = __ldg(p.zita_prior + (size_t)gs * L + px) * kZScale;
-    const float* kprior = p.kappa_prior + ((size_t)gs * kCk + cb * 16) * L + px;
-#pragma unroll
-    for (int j = 0; j < 16; ++j) pri[j] = zp * __ldg(kprior + (size_t)j * L);
+    for (int j = 0; j < 16; ++j) pri[j] = zp * kap0[j];
     pri_z = zp;
+    stage_khat(kap0);
   }
   // pixel norms (4 threads per pixel, 16 channels each) + this side's mask
   {
@@ -334,9 +364,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(emr::kThreads, 1) em
     for (int e = 0; e < 8; ++e) vals[e] = one;
     *reinterpret_cast<uint4*>(smem + kOffXH + (r % 8) * 16 + (r / 8) * 2048 + pg * 128) = *reinterpret_cast<uint4*>(vals);
   }
-  for (; v_round < v_setup; ++v_round) {
-    v_store(v_round);
-    if (v_round + 1 < v_setup) v_load(v_round + 1);
+  v_store(0);
+  v_load(1);                                            // second half: in flight until after the first logits GEMM (I = 1: stored right away)
+  if (I == 1) v_store(1);
+  unsigned* const cnt_m = p.counters + (size_t)u * I * 2 + sd;            // + 2 it
+  unsigned* const cnt_zero = p.counters + (size_t)p.U * I * 2 + u;
+  unsigned* const cnt_nu = cnt_zero + p.U;
+  unsigned* const cnt_dep = cnt_nu + p.U;
+  if (tid == 0) {
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");             // this CTA's slices are zero at L2
+    atomicAdd(cnt_zero, 1u);                                              // (waited for under the first logits GEMM)
   }
   tc_fence_before_sync();
   __syncthreads();
@@ -357,24 +394,28 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(emr::kThreads, 1) em
   const uint32_t peer_bar_w = map_to_peer(smem_u32(&ms.bar_w), peer);
   const uint32_t peer_bar_zp = map_to_peer(smem_u32(&ms.bar_zp), peer);
   const uint32_t peer_zp = map_to_peer(sbase + kOffZP, peer);
+  const uint32_t col_m = sd == 0 ? 384u : 128u;
   const bool mma_thread = (tid == 32);                  // (thread 0 runs the cross-tile barriers, which block in fences)
   constexpr float kInvZ = 1.f / kZScale;
 
   // finalize from the completed totals of iteration `it`: kappa = total / zita_total (the prior is part of the totals)
   auto finalize = [&](const float* acc, bool last) {
-    const float zt = __ldcg(acc + kCk * kL + frow);
-    const float rz = valid_row ? 1.f / zt : 0.f;
+    const float zt = __ldcg(acc + kCk * kL + px);
     float kap[16];
 #pragma unroll
-    for (int c = 0; c < 16; ++c) kap[c] = __ldcg(acc + (fcg * 16 + c) * kL + frow) * rz;
+    for (int c = 0; c < 16; ++c) kap[c] = __ldcg(acc + (cb * 16 + c) * kL + px);
+    const float rz = valid_row ? 1.f / zt : 0.f;
+#pragma unroll
+    for (int c = 0; c < 16; ++c) kap[c] *= rz;
+    EMR_STAMP(23);                                      // totals loaded
     if (last) {
-      if (fcg == 0) {
-        ms.rz[frow] = valid_row ? kZScale * rz : 0.f;   // 1 / zita in true units
-        ms.zp[frow] = zita_prior_f;
+      if (cb == 0) {
+        ms.rz[px] = valid_row ? kZScale * rz : 0.f;     // 1 / zita in true units
+        ms.zp[px] = zita_prior_f;
       }
       if (tile == 0 && valid_row) {
-        if (fcg == 0) p.zita[(size_t)gs * L + frow] = zt * kInvZ;
-        float* kout = p.kappa + ((size_t)gs * kCk + fcg * 16) * L + frow;
+        if (cb == 0) p.zita[(size_t)gs * L + px] = zt * kInvZ;
+        float* kout = p.kappa + ((size_t)gs * kCk + cb * 16) * L + px;
 #pragma unroll
         for (int c = 0; c < 16; ++c) kout[(size_t)c * L] = kap[c];
       }
@@ -383,20 +424,37 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(emr::kThreads, 1) em
     }
   };
 
-  // column block leader (warp 4 cb, lane 0): reduce-add the block's 8 KB of the staged M-step partial, then arrive
-  auto reduce_block_and_arrive = [&](float* acc, unsigned* counter) {
+  // column block leader (warp 4 cb, lane 0): reduce-add the block's 8 KB of the staged M-step partial (block 0: and the zita
+  // row), wait for the reduction to complete and arrive.  Release: every byte goes through the bulk-copy engine and the arrival
+  // is issued only after `wait_group 0` has reported the reductions performed at L2, the point of coherence of the polling
+  // CTAs (ld.acquire.gpu + ld.global.cg); a gpu-scope fence in between costs a further L2 round trip (0.7 us, measured:
+  // profiles/r2_em_res_fence_ab.txt) and can be switched on for comparison with SWEM_EM_DBG=4.
+  auto reduce_issue = [&](float* acc) {
     bar_sync(5 + cb, 128);                              // the 4 warps of this column block have staged their rows
     if (q == 0 && lane == 0) {
       asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(acc + cb * 16 * kL),
                    "r"(sbase + kOffKH + (uint32_t)(cb * 16 * kL * 4)), "r"(16 * kL * 4)
                    : "memory");
+      if (cb == 0)
+        asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(acc + kCk * kL),
+                     "r"(smem_u32(&ms.zrow[0])), "r"(kL * 4)
+                     : "memory");
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-      __threadfence();
-      atomicAdd(counter, 1u);
+      EMR_STAMP(20);                                    // block staged (barrier) + bulk reduce issued
     }
   };
+  auto reduce_arrive = [&](unsigned* counter) {
+    if (q == 0 && lane == 0) {
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+      EMR_STAMP(21);                                    // bulk reduce complete
+      if (p.dbg & 4) asm volatile("fence.acq_rel.gpu;" ::: "memory");
+      atomicAdd(counter, 1u);
+      EMR_STAMP(22);                                    // arrived
+    }
+    __syncwarp();
+  };
 
+  float4 nu_pre[3];
   for (int it = 0; it < I; ++it) {
     const bool last = (it == I - 1);
     fence_proxy_async_smem();
@@ -405,6 +463,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(emr::kThreads, 1) em
     tc_fence_after_sync();
 
     // ---- (1) logits of this side: a[p, l] = x_p . khat_l (hi/lo split, 3 products) ----------------------------------
+    const bool v_now = (it == 0 && I > 1);              // second half of the V operand: loaded during set-up, stored after the GEMM
     if (mma_thread) {
 #pragma unroll
       for (int term = 0; term < 3; ++term) {
@@ -419,10 +478,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(emr::kThreads, 1) em
       }
       mma_commit(&ms.bar_mma);
     }
+    if (it == 0 && tid == 0) {       // every CTA of the unit has cleared its accumulator slices (polled under the GEMM; the CTAs
+      if (!wait_counter_fast(cnt_zero, 2u * (unsigned)p.T)) ms.abort_flag = 1;   // of a launch start together: no wait in practice)
+    }
     SWEM_CTA_WAIT(&ms.bar_mma, ph_mma, ms.abort_flag);
     ph_mma ^= 1;
     tc_fence_after_sync();
     EMR_STAMP(2);                    // logits GEMM done
+    if (v_now) v_store(1);
 
     // ---- (2) epilogue: thread <-> (pixel px, columns [32 cb, +32) of this side's bases) -------------------------------
     {
@@ -475,7 +538,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(emr::kThreads, 1) em
         for (int k = 0; k < 4; ++k) EW += ms.hew[k][px] * fast_exp2((ms.hmax[k][px] - m_side) * cw);
         const int par = it & 1;
         if (cb == 0) st_async_f2(peer_mbox + (uint32_t)((par * kTP + px) * sizeof(float2)), m_side, EW, peer_bar_w);
+        EMR_STAMP(25);                                  // own statistics sent
         if (!warp_wait(&ms.bar_w, ph_w, 0)) ms.abort_flag = 1;
+        EMR_STAMP(26);                                  // peer statistics received
         ph_w ^= 1;
         const float2 o = ms.mbox[par][px];              // the peer side's (max, W-step sum)
         const float gm = fmaxf(m_side, o.x);
@@ -516,11 +581,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(emr::kThreads, 1) em
         const uint64_t al = make_sdesc(sbase + kOffZL + kk * 2 * 128, /*lbo*/ 128, /*sbo*/ 2048);
         const uint64_t bh = make_sdesc(sbase + kOffXH + kk * 2 * 128, /*lbo*/ 128, /*sbo*/ 2048);
         const uint64_t bl = make_sdesc(sbase + kOffXL + kk * 2 * 128, /*lbo*/ 128, /*sbo*/ 2048);
-        mma_f16_ss(tmem + kColM, ad, bh, idesc_mhi, kk ? 1u : 0u);   // z_hi x_hi (+ zita column)
-        mma_f16_ss(tmem + kColM, ad, bl, idesc_mlo, 1u);             // z_hi x_lo
-        mma_f16_ss(tmem + kColM, al, bh, idesc_mhi, 1u);             // z_lo x_hi
+        mma_f16_ss(tmem + col_m, ad, bh, idesc_mhi, kk ? 1u : 0u);   // z_hi x_hi (+ zita column)
+        mma_f16_ss(tmem + col_m, ad, bl, idesc_mlo, 1u);             // z_hi x_lo
+        mma_f16_ss(tmem + col_m, al, bh, idesc_mhi, 1u);             // z_lo x_hi
       }
       mma_commit(&ms.bar_mma);
+      if (last) {                    // nu of the own side: z and V are in place, its columns are free
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+          const uint64_t ad = make_sdesc(sbase + kOffZ + ks * 2 * 128, /*lbo*/ 128, /*sbo*/ 2048);
+          const uint64_t bd = make_sdesc(sbase + kOffV + ks * 2 * 4096, /*lbo*/ 4096, /*sbo*/ 128);
+          mma_f16_ss(tmem + sd * 256, ad, bd, idesc_nu, ks ? 1u : 0u);
+        }
+        mma_commit(&ms.bar_nu[0]);
+      }
     }
     SWEM_CTA_WAIT(&ms.bar_mma, ph_mma, ms.abort_flag);
     ph_mma ^= 1;
@@ -531,35 +605,31 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(emr::kThreads, 1) em
     float* acc = p.acc_k + ((size_t)((u * I + it) * 2 + sd)) * ((kCk + 1) * kL);
     // (staged in the khat / z_lo region -- dead between the M-step GEMM and the finalize -- and reduce-added by the bulk-copy
     //  engine in four 8 KB pieces, one per column block: far fewer L2 atomic transactions than per-lane reductions)
-    unsigned* counter = p.counters + ((size_t)u * I + it) * 2 + sd;
+    unsigned* counter = cnt_m + 2 * it;
     {
       uint32_t r[16];
-      tmem_ld16(tmem_addr(tmem, q * 32, kColM + cb * 16), r);
+      tmem_ld16(tmem_addr(tmem, q * 32, col_m + cb * 16), r);
       uint32_t rz16[16];
-      if (cb == 0) tmem_ld16(tmem_addr(tmem, q * 32, kColM + kCk), rz16);
+      if (cb == 0) tmem_ld16(tmem_addr(tmem, q * 32, col_m + kCk), rz16);
       tmem_ld_wait();
       float* ns = reinterpret_cast<float*>(smem + kOffKH);        // [64 c][128 l] fp32
 #pragma unroll
       for (int j = 0; j < 16; ++j) ns[(cb * 16 + j) * kL + px] = __uint_as_float(r[j]) + pri[j];
-      if (cb == 0) atomicAdd(acc + kCk * kL + px, __uint_as_float(rz16[0]) + pri_z);
+      if (cb == 0) ms.zrow[px] = __uint_as_float(rz16[0]) + pri_z;
       fence_proxy_async_smem();
     }
     if (!last) {
-      const bool conv = v_round < 2;
-      if (conv) v_load(v_round);                        // loads fly across the arrival
       tc_fence_before_sync();
       EMR_STAMP(5);                                     // partial staged
-      reduce_block_and_arrive(acc, counter);
+      reduce_issue(acc);
+      reduce_arrive(counter);
       EMR_STAMP(6);                                     // reduce-added + arrived
-      if (conv) {
-        v_store(v_round);
-        ++v_round;
-      }
       if (tid == 0) {
         if (!wait_counter_fast(counter, 4u * (unsigned)p.T)) ms.abort_flag = 1;
         EMR_STAMP(7);                                   // all tiles arrived
       }
       __syncthreads();
+      EMR_STAMP(24);                                    // CTA released
       if (!ms.abort_flag) finalize(acc, false);
       EMR_STAMP(8);                                     // finalize done (before the loop-top barrier)
     } else {
@@ -567,17 +637,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(emr::kThreads, 1) em
       tc_fence_before_sync();
       __syncthreads();                                  // every warp has read its M-step columns: TMEM is free for nu
       tc_fence_after_sync();
-      if (mma_thread) {
-#pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {
-          const uint64_t ad = make_sdesc(sbase + kOffZ + ks * 2 * 128, /*lbo*/ 128, /*sbo*/ 2048);
-          const uint64_t bd = make_sdesc(sbase + kOffV + ks * 2 * 4096, /*lbo*/ 4096, /*sbo*/ 128);
-          mma_f16_ss(tmem + sd * 256, ad, bd, idesc_nu, ks ? 1u : 0u);
-        }
-        mma_commit(&ms.bar_nu[0]);
-      }
       EMR_STAMP(5);
-      reduce_block_and_arrive(acc, counter);            // (before the issuing thread blocks on the peer's z: it is part of a block barrier)
+      reduce_issue(acc);                                // (before the issuing thread blocks on the peer's z: it is part of a block barrier)
+      reduce_arrive(counter);
       EMR_STAMP(6);
       if (mma_thread) {
         if (!mbar_wait(&ms.bar_zp, 0)) ms.abort_flag = 1;   // the peer's z has landed in ZP
@@ -630,11 +692,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(emr::kThreads, 1) em
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
       }
-      unsigned* counter_nu = p.counters + (size_t)p.U * I * 2 + u;
+      unsigned* counter_nu = cnt_nu;
+      // prior rows of this CTA's nu slice: loaded now, under the wait for the other tiles' drains
+      {
+        const float4* pri4 = reinterpret_cast<const float4*>(p.nu_prior + (size_t)gs * kCv * L);
+        const int l4n = (L < kL ? L : kL) / 4;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          const int k = d0 * l4n + tid + j * kThreads;
+          nu_pre[j] = (k < d1 * l4n) ? __ldg(pri4 + (k / l4n) * (L / 4) + k % l4n) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
       if (tid == 0) {
         asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // full completion (not just .read) before the arrival
         EMR_STAMP(11);                                  // nu drained
-        __threadfence();
         atomicAdd(counter_nu, 1u);
         if (!wait_counter_fast(counter_nu, 2u * (unsigned)p.T)) ms.abort_flag = 1;
         EMR_STAMP(12);                                  // every CTA of the unit has drained
@@ -651,17 +722,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(emr::kThreads, 1) em
 
   if (!failed) {
     // ---- nu = (zita_ nu_ + sum / 2^14) / zita (reference :164-165) for side sd, this tile's slice of value channels --------
-    const int dper = (kCv + p.T - 1) / p.T;
-    const int d0 = tile * dper, d1 = min(kCv, d0 + dper);
     const float4* acc4 = reinterpret_cast<const float4*>(p.acc_nu + (size_t)gs * kCv * kL);     // [d][128]
     const float4* pri4 = reinterpret_cast<const float4*>(p.nu_prior + (size_t)gs * kCv * L);    // [d][L]
     float4* out4 = reinterpret_cast<float4*>(p.nu + (size_t)gs * kCv * L);
     const int l4n = (L < kL ? L : kL) / 4;
-    for (int k = d0 * l4n + tid; k < d1 * l4n; k += kThreads) {
+    int jj = 0;
+    for (int k = d0 * l4n + tid; k < d1 * l4n; k += kThreads, ++jj) {
       const int d = k / l4n, l4 = k % l4n, l = l4 * 4;
       const int i = d * (L / 4) + l4;
       const float4 a = __ldcg(acc4 + d * (kL / 4) + l4);
-      const float4 pr = __ldg(pri4 + i);
+      const float4 pr = jj == 0 ? nu_pre[0] : jj == 1 ? nu_pre[1] : jj == 2 ? nu_pre[2] : __ldg(pri4 + i);
       float4 o;
       o.x = (ms.zp[l + 0] * pr.x + a.x * kInvZ) * ms.rz[l + 0];
       o.y = (ms.zp[l + 1] * pr.y + a.y * kInvZ) * ms.rz[l + 1];
@@ -673,6 +743,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(emr::kThreads, 1) em
   }
   tc_fence_before_sync();
   __syncthreads();
+  if (tid == 0 && !failed) {
+    // the last CTA of the unit to get here clears the unit's counters for the next launch (every other CTA has passed its waits)
+    if (atomicAdd(cnt_dep, 1u) == 2u * (unsigned)p.T - 1u) {
+      for (int i = 0; i < I * 2; ++i) p.counters[(size_t)u * I * 2 + i] = 0u;
+      *cnt_zero = 0u;
+      *cnt_nu = 0u;
+      *cnt_dep = 0u;
+    }
+  }
   if (p.prof != nullptr && blockIdx.x == 0 && tid == 0) p.prof[0] = -(long long)n_stamp;
   if (warp == 0) tmem_dealloc(tmem, 512);
   cluster_arrive();                  // a CTA must not exit while its peer may still write into its shared memory
@@ -715,9 +794,13 @@ static int res_clusters_resident() {
   return n;
 }
 
+constexpr int kBarWords = 4096;
+static size_t bar_words_needed(const SwemDims& d) { return (size_t)d.B * d.N * (d.n_iters * 2 + 3) + 1; }
+
 // Shapes of the V-resident kernel: Ck = 64, L <= 128, and a unit's tile pairs co-resident (single-launch form)
 bool fused_em_res_covers(const SwemDims& d, bool v_pixel_major) {
   if (d.Ck != emr::kCk || (d.L != 64 && d.L != 128) || d.Cv != emr::kCv || d.n_iters < 1 || d.n_iters > 16) return false;
+  if (bar_words_needed(d) > (size_t)kBarWords) return false;
   const char* off = getenv("SWEM_EM_RES");
   if (off != nullptr && off[0] == '0') return false;     // A/B switch: SWEM_EM_RES=0 runs em_pair_kernel on these shapes too
   const char* force_w = getenv("SWEM_EM_WINDOWED");
@@ -727,6 +810,29 @@ bool fused_em_res_covers(const SwemDims& d, bool v_pixel_major) {
   return T >= 1 && T <= resident;
 }
 
+// ---- library-owned arrival counters ---------------------------------------------------------------------------------------
+// One zero-initialised buffer per device, cut into kBarRanges ranges of kBarWords counters; every EM call takes the next range
+// (calls in flight on different streams never share one) and its kernel leaves the words it used zero again, so there is no
+// memset in front of the kernel and nothing for the caller's workspace to preserve between calls.
+constexpr int kBarRanges = 16;
+static unsigned* bar_range(unsigned** base_out = nullptr) {
+  static std::mutex mu;
+  static unsigned* base[kMaxDevices] = {};
+  static unsigned ticket[kMaxDevices] = {};
+  const int dev = current_device();
+  std::lock_guard<std::mutex> lock(mu);
+  if (base[dev] == nullptr) {
+    unsigned* ptr = nullptr;
+    if (cudaMalloc(&ptr, (size_t)kBarRanges * kBarWords * sizeof(unsigned)) != cudaSuccess ||
+        cudaMemset(ptr, 0, (size_t)kBarRanges * kBarWords * sizeof(unsigned)) != cudaSuccess) {
+      cudaGetLastError();
+      return nullptr;                                    // (e.g. first call ever made under stream capture)
+    }
+    base[dev] = ptr;
+  }
+  if (base_out != nullptr) *base_out = base[dev];
+  return base[dev] + (size_t)(ticket[dev]++ % kBarRanges) * kBarWords;
+}
 template <bool VPM>
 static int fused_em_res_forward_t(const SwemEmArgs& a, cudaStream_t st) {
   const SwemDims& d = a.dims;
@@ -735,19 +841,25 @@ static int fused_em_res_forward_t(const SwemEmArgs& a, cudaStream_t st) {
   Arena ws(a.workspace);
   float* acc_k = ws.take<float>((size_t)U * d.n_iters * 2 * (emr::kCk + 1) * emr::kL);
   float* acc_nu = ws.take<float>((size_t)U * 2 * emr::kCv * emr::kL);
-  unsigned* counters = ws.take<unsigned>((size_t)U * d.n_iters * 2 + U + 1);
-  int* status = reinterpret_cast<int*>(counters + (size_t)U * d.n_iters * 2 + U);
-  SWEM_CUDA(cudaMemsetAsync(a.workspace, 0, ws.off, st));
-  count_launch();
+  unsigned* counters = bar_range();
+  if (counters == nullptr) {
+    set_error("fused EM: cannot allocate the arrival counters (the first swem_em_forward of a device must not run under stream capture)");
+    return SWEM_ERR_CUDA;
+  }
 
   EmResParams p{};
   p.x = a.x; p.v = a.v; p.masks = a.masks;
   p.kappa_prior = a.kappa_prior; p.nu_prior = a.nu_prior; p.zita_prior = a.zita_prior;
   p.kappa = a.kappa; p.nu = a.nu; p.zita = a.zita; p.z_last = a.z_last;
-  p.acc_k = acc_k; p.acc_nu = acc_nu; p.counters = counters; p.status = status;
+  p.acc_k = acc_k; p.acc_nu = acc_nu; p.counters = counters;
+  p.status = reinterpret_cast<int*>(counters + kBarWords - 1);
   p.N = d.N; p.HW = d.HW; p.T = T; p.n_iters = d.n_iters; p.L = d.L; p.U = U;
   p.c1s = kLog2e / (d.tau * emr::kKScale);
   p.prof = get_profile_buffer();
+  {
+    const char* dbg = getenv("SWEM_EM_DBG");
+    p.dbg = dbg ? atoi(dbg) : 0;
+  }
   // all CTAs of a launch spin on each other, so every launch must be co-resident (1 CTA per SM); units that do not fit are
   // spread evenly over the fewest launches
   const int upl_max = res_clusters_resident<VPM>() / T;

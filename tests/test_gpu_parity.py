@@ -891,6 +891,42 @@ def test_em_reads_channels_last_values_in_place(shape):
     assert not core._takes_pixel_major(v_cl, B, N, Ck, H * W)         # the generic family gets the NCHW copy instead
 
 
+def test_em_single_launch_is_stable_over_many_calls():
+    """em_res_kernel (Ck = 64, L <= 128): ONE launch per memorize call -- its arrival counters live in a library-owned buffer that
+    every launch leaves zero again, the L2 accumulators are cleared by the kernel itself, and the cross-tile arrivals are
+    released by the completion of the bulk reductions instead of a gpu-scope fence.  A race in any of the three shows up as a
+    wrong sum sooner or later: 300 back-to-back calls (two streams for the last 100, different object counts in between so that
+    the counter ranges are reused with other extents) must all reproduce the first answer to summation-order noise (the order of the L2 reductions differs from call to call: ~1e-6 on
+    kappa after one iteration, grown by the later iterations and the single-pass nu product to ~1e-4; a race gives O(1))."""
+    from swem_b200.synthetic import clustered_em_inputs
+    core = _core(dict(L=128, Cv=512, n_iters=4, tau=0.05, topl=64), 'fused')
+    B, N, Ck, Cv, H, W = 1, 5, 64, 512, 30, 54
+    x, v, masks = (t.to(DEV) for t in clustered_em_inputs(B, N, Ck, Cv, H, W, seed=77))
+    prior = _to(dict(zip(('kappa', 'nu', 'zita'), O.random_init(B, N, Ck, 128, Cv, generator=torch.Generator().manual_seed(78)))), DEV)
+    x2, v2, m2 = (t.to(DEV) for t in clustered_em_inputs(1, 2, Ck, Cv, 24, 23, seed=79))
+    with torch.no_grad():
+        first = core.swem(x, v, masks, prior)
+        assert core.launches == 1, core.launches
+        worst = {k: 0.0 for k in first}
+        for i in range(200):
+            if i % 17 == 0:
+                core.swem(x2, v2, m2, None)
+            got = core.swem(x, v, masks, prior)
+            for k in first:
+                worst[k] = max(worst[k], maxrel(got[k], first[k]))
+        side = torch.cuda.Stream()
+        for i in range(50):
+            with torch.cuda.stream(side):
+                other = core.swem(x2, v2, m2, None)
+            got = core.swem(x, v, masks, prior)
+            for k in first:
+                worst[k] = max(worst[k], maxrel(got[k], first[k]))
+        torch.cuda.synchronize()
+        assert torch.isfinite(other['nu']).all()
+    for k, e in worst.items():
+        check(k + '_repeat', e, 1e-3)
+
+
 def test_bench_configuration_passes_the_mask_gate():
     """The EXACT configuration bench.py times (same env defaults: FrameEngine parity convolutions = TF32 main term + bf16
     cross terms, autotuned cuDNN, pipelined CUDA-graph runner, tcgen05 EM / readout) through the north-star gate: >= 99.9 %
