@@ -5,13 +5,14 @@
 // One launch per memorize call, one CTA of 16 warps per (unit u = (b, n), 128-pixel tile, side), the two sides of a tile
 // forming a 2-CTA cluster.  What changed against em_pair_kernel (profiles/r1_phases_em_pair.txt -> r2_phases_em_res.txt):
 //
-//   * nu = Z^T V^T is a single-pass fp16 product (z and v rounded once; measured on the oracle: nu error 4e-4 against the
-//     1e-2 bar, kappa / zita unaffected -- they keep the hi/lo split products, tools/precision_study.py).  The pair splits
-//     it by VALUE CHANNEL, not by side: CTA `rank` owns channels [256 rank, +256) for both sides, so every V element is read
-//     from HBM exactly once, converted in registers and kept in shared memory as the B operand -- no operand images in global
-//     memory, no copy ring.  The conversion runs in the shadow of the cross-tile barriers of the first iterations (loads issued
-//     before the arrival, converted while the barrier completes).  The peer's responsibilities of the last E-step are pushed
-//     over distributed shared memory by the epilogue that produces them.
+//   * nu = Z^T V^T keeps the three split products (z_hi v_hi + z_hi v_lo + z_lo v_hi): a single-pass fp16 product leaves nu at
+//     4e-4 of the reference -- inside the 1e-2 feature bar, but measured to double the mask disagreement of free-running
+//     sequences and to push four mask tests over the 99.9 % gate (profiles/r2_single_pass_nu.txt) -- so precision is not traded.
+//     The operand images of V (fp16 hi/lo, 8 x 32 KB per tile) are converted once per pair -- each CTA its channel half, in two
+//     rounds of one warp step per warp placed where they do not delay latency-critical traffic -- into an L2-resident scratch
+//     and streamed back through a 3-stage bulk-copy ring; the first three stages are filled as soon as the images exist.
+//     (Converting straight into the ring with the warps as producers was measured at 12.7 us for the nu GEMM against 4.8 us:
+//     one warp step of loads in flight per warp cannot cover the L2 latency; profiles/r2_em_res_phases.txt.)
 //   * 16 warps: the softmax epilogue holds 32 logits per thread (4 threads per pixel, exps against the thread's own max and
 //     one rescale -- no max exchange before the exps); the pixel statistics of the two sides meet through a remote mbarrier
 //     (128 arrivals) instead of a full cluster barrier.
@@ -48,19 +49,21 @@ constexpr float kZScale = 16384.f;
 // XH : [c 0..79][p]  byte = (c%8)*16 + (c/8)*2048 + (p/8)*128 + (p%8)*2   (row 64 = ones -> zita column, 65.. = 0)
 // XL : [c 0..63][p]
 // KH/KL : [l][c] K-major: byte = (l%8)*16 + (l/8)*128 + (c/8)*2048 + (c%8)*2
-// Z / ZL / ZP : [l][p] MN-major A: byte = (l%8)*2 + (p%8)*16 + (l/8)*2048 + (p/8)*128   (ZL aliases KH/KL; ZP = the peer side's z)
-// V  : [d 0..255][p 0..127] K-major B: byte = (d%8)*16 + (d/8)*128 + (p/8)*4096 + (p%8)*2
+// Z / ZL : [l][p] MN-major A: byte = (l%8)*2 + (p%8)*16 + (l/8)*2048 + (p/8)*128   (ZL aliases KH/KL)
+// VS : ring of 3 V operand images [d 0..255][p 0..31] K-major B: byte = (d%8)*16 + (d/8)*128 + (p/8)*4096 + (p%8)*2, hi plane (16 KB) then lo
 constexpr uint32_t kOffXH = 0;
 constexpr uint32_t kOffXL = kOffXH + 10 * 2048;
 constexpr uint32_t kOffKH = kOffXL + 8 * 2048;
 constexpr uint32_t kOffKL = kOffKH + 8 * 2048;
 constexpr uint32_t kOffZ = kOffKL + 8 * 2048;
 constexpr uint32_t kOffZL = kOffKH;
-constexpr uint32_t kOffZP = kOffZ + 16 * 2048;
-constexpr uint32_t kOffV = kOffZP + 16 * 2048;
-constexpr uint32_t kOffMisc = kOffV + 16 * 4096;
-constexpr uint32_t kStageBytes = 32768;        // nu drain staging: 2 buffers over the (dead) X / khat region
-static_assert(kOffZ >= 2 * kStageBytes, "drain staging must fit below Z");
+constexpr uint32_t kOffVS = kOffZ + 16 * 2048;
+constexpr int kStages = 3;
+constexpr uint32_t kImgBytes = 32768;          // one V operand image: [256 d][32 px] fp16, hi plane then lo plane
+constexpr uint32_t kVPlane = 16384;
+constexpr int kImages = 8;                     // per tile: 2 channel halves x 4 pixel quarters
+constexpr uint32_t kOffMisc = kOffVS + kStages * kImgBytes;
+static_assert(kOffVS >= 3 * 32768, "nu drain staging: three 32 KB buffers below the ring");
 
 struct Misc {
   float inv_nx[kTP];
@@ -75,7 +78,9 @@ struct Misc {
   uint64_t bar_mma;
   uint64_t bar_nu[2];
   uint64_t bar_w;
-  uint64_t bar_zp;
+  uint64_t bar_full[kStages];
+  uint64_t bar_empty[kStages];
+  uint64_t bar_vready;          // the peer's images are complete (remote arrival)
   uint32_t tmem_base;
   int abort_flag;
 };
@@ -83,9 +88,8 @@ constexpr uint32_t kSmemBytes = kOffMisc + sizeof(Misc) + 128;
 static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 
 constexpr uint32_t kColE = 0;      // [128 px][128]   logits of this side
-                                   // [128 l][80]     M-step sums at column 384 (side 0) / 128 (side 1): inside the PEER side's nu
-                                   //                 columns, so the own-side nu GEMM can follow the last M-step GEMM directly
-                                   // nu: [128 l][256 d] of side s at columns 256 s
+                                   // [128 l][80]     M-step sums at column 128
+                                   // nu: [128 l][512 d] at columns 0..511 (after the last M-step partial has been read out)
 }  // namespace emr
 
 struct EmResParams {
@@ -99,6 +103,7 @@ struct EmResParams {
   float* nu;
   float* zita;
   float* z_last;
+  uint8_t* vblob;        // [U][T][8][32 KB] scratch: operand images of V
   float* acc_k;          // [U][n_iters][2][65][128]   (zeroed by the kernel itself, see "accumulators" below)
   float* acc_nu;         // [U][2][512][128]
   unsigned* counters;    // library-owned, zero between launches: [U][n_iters][2] M-step arrivals, then [U] accumulators zeroed,
@@ -177,7 +182,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(emr::kThreads, 1) em
     mbar_init(&ms.bar_nu[0], 1);
     mbar_init(&ms.bar_nu[1], 1);
     mbar_init(&ms.bar_w, 1);                           // + transaction bytes: the peer's st.async stores
-    mbar_init(&ms.bar_zp, 1);
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&ms.bar_full[i], 1);
+      mbar_init(&ms.bar_empty[i], 1);
+    }
+    mbar_init(&ms.bar_vready, 1);
     ms.abort_flag = 0;
     fence_mbar_init();
   }
@@ -213,27 +222,27 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(emr::kThreads, 1) em
     }
   }
 
-  // ---- V -> fp16 B operand, in rounds of one warp step per warp (2 rounds cover the CTA's [256 d][128 px]) -------------------
-  // load phase (8 x 16 bytes per lane in flight) and convert / store phase are separate calls so that the loads overlap a barrier
+  // ---- V -> fp16 hi/lo operand images in the L2-resident scratch.  Image k = (channel half k / 4, pixel quarter k % 4) takes 8 warp
+  // steps (w8 = 0 .. 7); this CTA converts its channel half, images 4 rank .. 4 rank + 3, in two rounds of 16 warp steps.  Load phase (8 x 16 bytes per lane in flight) and
+  // convert / store phase are separate calls so that the loads overlap whatever lies between them.
   float4 vf[8];
-  auto v_load = [&](int round) {
-    const int s = round * 16 + warp;                    // warp step 0..31
+  auto v_load = [&](int k, int w8) {
+    const int h = k >> 2, qd = k & 3;
     if constexpr (VPM) {                                // v [U][HW][512]: 8 pixels x 128 channels per step, the lane owns 4 channels
-      const int g = s >> 1, d = (s & 1) * 128 + lane * 4;
-      const float* src = p.v + ((size_t)u * HW) * kCv + rank * kDH + d;
+      const int g = w8 >> 1, d = (w8 & 1) * 128 + lane * 4;
+      const float* src = p.v + ((size_t)u * HW) * kCv + h * 256 + d;
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
-        const int pp = p0 + g * 8 + e;
+        const int pp = p0 + qd * 32 + g * 8 + e;
         vf[e] = pp < HW ? __ldg(reinterpret_cast<const float4*>(src + (size_t)pp * kCv)) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     } else {                                            // v [U][512][HW]: 32 channels x 32 pixels per step, the lane owns 4 x (1 channel, 8 pixels)
-      const int cblk = s >> 2, pq = s & 3;
-      const int pp0 = p0 + pq * 32 + (lane & 3) * 8;
+      const int pp0 = p0 + qd * 32 + (lane & 3) * 8;
       const bool vec = ((HW & 3) == 0) && (pp0 + 7 < HW);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const int d = cblk * 32 + j * 8 + (lane >> 2);
-        const float* src = p.v + ((size_t)u * kCv + rank * kDH + d) * HW + pp0;
+        const int d = w8 * 32 + j * 8 + (lane >> 2);
+        const float* src = p.v + ((size_t)u * kCv + h * 256 + d) * HW + pp0;
         if (vec) {
           vf[2 * j] = __ldg(reinterpret_cast<const float4*>(src));
           vf[2 * j + 1] = __ldg(reinterpret_cast<const float4*>(src) + 1);
@@ -247,37 +256,49 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(emr::kThreads, 1) em
       }
     }
   };
-  auto v_store = [&](int round) {
-    const int s = round * 16 + warp;
+  uint8_t* const vimg = p.vblob + ((size_t)u * p.T + tile) * kImages * kImgBytes;
+  auto v_store = [&](int k, int w8) {
+    uint8_t* img = vimg + (size_t)k * kImgBytes;
     if constexpr (VPM) {
-      const int g = s >> 1, d = (s & 1) * 128 + lane * 4;
-      uint8_t* dst = smem + kOffV + d * 16 + g * 4096;  // (d % 8) * 16 + (d / 8) * 128 = d * 16
+      const int g = w8 >> 1, d = (w8 & 1) * 128 + lane * 4;
+      uint8_t* dst = img + d * 16 + g * 4096;           // (d % 8) * 16 + (d / 8) * 128 = d * 16
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        __align__(16) __half hv[8];
+      for (int c = 0; c < 4; ++c) {
+        __align__(16) __half hi[8];
+        __align__(16) __half lo[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) hv[e] = __float2half_rn(k == 0 ? vf[e].x : k == 1 ? vf[e].y : k == 2 ? vf[e].z : vf[e].w);
-        *reinterpret_cast<uint4*>(dst + k * 16) = *reinterpret_cast<uint4*>(hv);
+        for (int e = 0; e < 8; ++e) split_half(c == 0 ? vf[e].x : c == 1 ? vf[e].y : c == 2 ? vf[e].z : vf[e].w, hi[e], lo[e]);
+        *reinterpret_cast<uint4*>(dst + c * 16) = *reinterpret_cast<uint4*>(hi);
+        *reinterpret_cast<uint4*>(dst + kVPlane + c * 16) = *reinterpret_cast<uint4*>(lo);
       }
     } else {
-      const int cblk = s >> 2, pq = s & 3;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const int d = cblk * 32 + j * 8 + (lane >> 2);
-        __align__(16) __half hv[8];
-        hv[0] = __float2half_rn(vf[2 * j].x); hv[1] = __float2half_rn(vf[2 * j].y);
-        hv[2] = __float2half_rn(vf[2 * j].z); hv[3] = __float2half_rn(vf[2 * j].w);
-        hv[4] = __float2half_rn(vf[2 * j + 1].x); hv[5] = __float2half_rn(vf[2 * j + 1].y);
-        hv[6] = __float2half_rn(vf[2 * j + 1].z); hv[7] = __float2half_rn(vf[2 * j + 1].w);
-        *reinterpret_cast<uint4*>(smem + kOffV + d * 16 + (pq * 4 + (lane & 3)) * 4096) = *reinterpret_cast<uint4*>(hv);
+        const int d = w8 * 32 + j * 8 + (lane >> 2);
+        const float t[8] = {vf[2 * j].x, vf[2 * j].y, vf[2 * j].z, vf[2 * j].w, vf[2 * j + 1].x, vf[2 * j + 1].y, vf[2 * j + 1].z, vf[2 * j + 1].w};
+        __align__(16) __half hi[8];
+        __align__(16) __half lo[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) split_half(t[e], hi[e], lo[e]);
+        uint8_t* dst = img + d * 16 + (lane & 3) * 4096;
+        *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<uint4*>(hi);
+        *reinterpret_cast<uint4*>(dst + kVPlane) = *reinterpret_cast<uint4*>(lo);
       }
     }
   };
-  // round 0: loads issued here, in flight across the X / khat staging of the set-up; round 1: issued at the top of iteration 0 and
-  // stored after its logits GEMM (I = 1: also during set-up) -- never next to the cross-tile reductions, whose bulk reduce-adds
-  // they would delay by ~1 us (profiles/r2_em_res_phases.txt)
-  v_load(0);
-
+  auto v_publish = [&]() {                              // generic-proxy global stores -> visible to the bulk copies (async proxy) of the pair
+    __threadfence();
+    asm volatile("fence.proxy.async;" ::: "memory");
+  };
+  auto load_image = [&](int seq) {                      // ring stage seq % 3 <- the seq-th image in consumption order (own channel half first)
+    const int k = (((seq >> 2) ^ rank) << 2) + (seq & 3);
+    mbar_expect_tx(&ms.bar_full[seq % kStages], kImgBytes);
+    bulk_g2s(smem + kOffVS + (seq % kStages) * kImgBytes, vimg + (size_t)k * kImgBytes, kImgBytes, &ms.bar_full[seq % kStages]);
+  };
+  const int vround_img = rank * 4 + (warp >> 3), vround_w8 = warp & 7;   // round r converts image vround_img + 2 r
+  // Round 0 is loaded at the end of the set-up and stored after the first logits GEMM, round 1 is loaded under the first M-step GEMM
+  // and stored while the first cross-tile reduction is in flight -- never ahead of the X / prior loads (they delay the first logits
+  // GEMM by 3 us) nor next to a cross-tile reduction (they delay its completion by 1 us; profiles/r2_em_res_phases.txt).
   // ---- khat = l2norm(kappa) * 256 -> fp16 hi/lo K-major rows (reference :115).  Thread <-> (row px, channels [16 cb, +16)):
   // global accesses are coalesced over the rows, the squared norm meets in shared memory across the 4 warps of a lane quadrant
   const bool valid_row = px < L;
@@ -315,6 +336,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(emr::kThreads, 1) em
     pri_z = zp;
     stage_khat(kap0);
   }
+  EMR_STAMP(31);                                       // prior khat staged
   // pixel norms (4 threads per pixel, 16 channels each) + this side's mask
   {
     const int pq = tid & 127, cq = tid >> 7, pp = p0 + pq;
@@ -364,9 +386,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(emr::kThreads, 1) em
     for (int e = 0; e < 8; ++e) vals[e] = one;
     *reinterpret_cast<uint4*>(smem + kOffXH + (r % 8) * 16 + (r / 8) * 2048 + pg * 128) = *reinterpret_cast<uint4*>(vals);
   }
-  v_store(0);
-  v_load(1);                                            // second half: in flight until after the first logits GEMM (I = 1: stored right away)
-  if (I == 1) v_store(1);
+  EMR_STAMP(32);                                       // X staged
+  v_load(vround_img, vround_w8);
   unsigned* const cnt_m = p.counters + (size_t)u * I * 2 + sd;            // + 2 it
   unsigned* const cnt_zero = p.counters + (size_t)p.U * I * 2 + u;
   unsigned* const cnt_nu = cnt_zero + p.U;
@@ -374,6 +395,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(emr::kThreads, 1) em
   if (tid == 0) {
     asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");             // this CTA's slices are zero at L2
     atomicAdd(cnt_zero, 1u);                                              // (waited for under the first logits GEMM)
+    EMR_STAMP(34);                                                        // clearing complete + arrived
   }
   tc_fence_before_sync();
   __syncthreads();
@@ -392,9 +414,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(emr::kThreads, 1) em
   const uint32_t peer = (uint32_t)(rank ^ 1);
   const uint32_t peer_mbox = map_to_peer(smem_u32(&ms.mbox[0][0]), peer);
   const uint32_t peer_bar_w = map_to_peer(smem_u32(&ms.bar_w), peer);
-  const uint32_t peer_bar_zp = map_to_peer(smem_u32(&ms.bar_zp), peer);
-  const uint32_t peer_zp = map_to_peer(sbase + kOffZP, peer);
-  const uint32_t col_m = sd == 0 ? 384u : 128u;
+  const uint32_t peer_bar_vready = map_to_peer(smem_u32(&ms.bar_vready), peer);
+  constexpr uint32_t col_m = 128;
   const bool mma_thread = (tid == 32);                  // (thread 0 runs the cross-tile barriers, which block in fences)
   constexpr float kInvZ = 1.f / kZScale;
 
@@ -429,11 +450,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(emr::kThreads, 1) em
   // is issued only after `wait_group 0` has reported the reductions performed at L2, the point of coherence of the polling
   // CTAs (ld.acquire.gpu + ld.global.cg); a gpu-scope fence in between costs a further L2 round trip (0.7 us, measured:
   // profiles/r2_em_res_fence_ab.txt) and can be switched on for comparison with SWEM_EM_DBG=4.
-  auto reduce_issue = [&](float* acc) {
+  auto reduce_issue = [&](float* acc, uint32_t stage_off) {
     bar_sync(5 + cb, 128);                              // the 4 warps of this column block have staged their rows
     if (q == 0 && lane == 0) {
       asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(acc + cb * 16 * kL),
-                   "r"(sbase + kOffKH + (uint32_t)(cb * 16 * kL * 4)), "r"(16 * kL * 4)
+                   "r"(sbase + stage_off + (uint32_t)(cb * 16 * kL * 4)), "r"(16 * kL * 4)
                    : "memory");
       if (cb == 0)
         asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(acc + kCk * kL),
@@ -463,7 +484,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(emr::kThreads, 1) em
     tc_fence_after_sync();
 
     // ---- (1) logits of this side: a[p, l] = x_p . khat_l (hi/lo split, 3 products) ----------------------------------
-    const bool v_now = (it == 0 && I > 1);              // second half of the V operand: loaded during set-up, stored after the GEMM
     if (mma_thread) {
 #pragma unroll
       for (int term = 0; term < 3; ++term) {
@@ -485,7 +505,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(emr::kThreads, 1) em
     ph_mma ^= 1;
     tc_fence_after_sync();
     EMR_STAMP(2);                    // logits GEMM done
-    if (v_now) v_store(1);
+    if (it == 0) {
+      v_store(vround_img, vround_w8);
+      if (I == 1) {                                     // (I = 1: round 1 cannot hide anywhere)
+        v_load(vround_img + 2, vround_w8);
+        v_store(vround_img + 2, vround_w8);
+        v_publish();
+      }
+    }
 
     // ---- (2) epilogue: thread <-> (pixel px, columns [32 cb, +32) of this side's bases) -------------------------------
     {
@@ -493,7 +520,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(emr::kThreads, 1) em
       const bool active = cb * 32 < L;                  // L = 64: the upper half of the columns is padding
       if (tid == 0) {                                   // arm the receive barriers of this iteration
         if (do_w) mbar_expect_tx(&ms.bar_w, kTP * sizeof(float2));
-        if (last) mbar_expect_tx(&ms.bar_zp, 16 * 2048);
       }
       float a[32];
       {
@@ -506,19 +532,29 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(emr::kThreads, 1) em
       // exps against the thread's own max; the blocks of a pixel are rescaled onto the side max afterwards:
       // exp(t - M) = exp(t - m) * exp(m - M).  W-step (reference :93-110): same logits times 1 / ||x_p||.
       const float cw = ms.inv_nx[px] * p.c1s;
-      float mloc = -3.0e38f, se = 0.f, ew = 0.f;
+      float mloc = -3.0e38f, se = 0.f, ew = 0.f, fix_e = 1.f;
       if (active) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) mloc = fmaxf(mloc, a[j]);
+        // one FFMA + one MUFU per exponential, four independent partial sums
+        // (the rounding of the offset -m c, up to 2^-24 of an exponent of several hundred, is recovered exactly by a second
+        //  FMA and applied to the sums / the final scale as the factor 2^residual)
+        float s4[4] = {0.f, 0.f, 0.f, 0.f};
         if (do_w) {
+          const float bw = -mloc * cw;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) ew += fast_exp2((a[j] - mloc) * cw);
+          for (int j = 0; j < 32; ++j) s4[j & 3] += fast_exp2(fmaf(a[j], cw, bw));
+          ew = ((s4[0] + s4[1]) + (s4[2] + s4[3])) * fast_exp2(fmaf(-mloc, cw, -bw));
+          s4[0] = s4[1] = s4[2] = s4[3] = 0.f;
         }
+        const float be = -mloc * p.c1s;
+        fix_e = fast_exp2(fmaf(-mloc, p.c1s, -be));
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          a[j] = fast_exp2((a[j] - mloc) * p.c1s);
-          se += a[j];
+          a[j] = fast_exp2(fmaf(a[j], p.c1s, be));
+          s4[j & 3] += a[j];
         }
+        se = ((s4[0] + s4[1]) + (s4[2] + s4[3])) * fix_e;
       } else {
 #pragma unroll
         for (int j = 0; j < 32; ++j) a[j] = 0.f;
@@ -547,7 +583,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(emr::kThreads, 1) em
         const float e_own = EW * fast_exp2((m_side - gm) * cw), e_peer = o.y * fast_exp2((o.x - gm) * cw);
         w *= 1.f - e_own / (e_own + e_peer);
       }
-      const float scale = active ? (w / S) * fast_exp2((mloc - m_side) * p.c1s) : 0.f;
+      const float scale = active ? (w / S) * fast_exp2((mloc - m_side) * p.c1s) * fix_e : 0.f;
       const float zs = scale * kZScale;
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
@@ -558,7 +594,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(emr::kThreads, 1) em
         const uint32_t off = (px % 8) * 16 + (px / 8) * 128 + (cb * 4 + g) * 2048;
         *reinterpret_cast<uint4*>(smem + kOffZ + off) = *reinterpret_cast<uint4*>(hi);
         *reinterpret_cast<uint4*>(smem + kOffZL + off) = *reinterpret_cast<uint4*>(lo);
-        if (last) st_async_u4(peer_zp + off, *reinterpret_cast<uint4*>(hi), peer_bar_zp);
       }
       if (p.z_last != nullptr && last && p0 + px < HW && active) {
         float4* dst = reinterpret_cast<float4*>(p.z_last + ((size_t)gs * HW + p0 + px) * L + cb * 32);
@@ -572,6 +607,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(emr::kThreads, 1) em
     __syncthreads();
     tc_fence_after_sync();
     EMR_STAMP(3);                    // epilogue done
+    if (it == (I == 1 ? 0 : 1)) {    // this CTA's images are complete and published: fill the ring, tell the peer
+      if (tid == 64) {
+        asm volatile("fence.proxy.async;" ::: "memory");
+        for (int seq = 0; seq < kStages; ++seq) load_image(seq);
+      }
+      if (tid == 0) mbar_arrive_remote(peer_bar_vready);
+    }
 
     // ---- (3) M-step GEMM: [sum_p z x | sum_p z] for this side's 128 bases (3 products) ----------------------------------
     if (mma_thread) {
@@ -586,16 +628,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(emr::kThreads, 1) em
         mma_f16_ss(tmem + col_m, al, bh, idesc_mhi, 1u);             // z_lo x_hi
       }
       mma_commit(&ms.bar_mma);
-      if (last) {                    // nu of the own side: z and V are in place, its columns are free
-#pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {
-          const uint64_t ad = make_sdesc(sbase + kOffZ + ks * 2 * 128, /*lbo*/ 128, /*sbo*/ 2048);
-          const uint64_t bd = make_sdesc(sbase + kOffV + ks * 2 * 4096, /*lbo*/ 4096, /*sbo*/ 128);
-          mma_f16_ss(tmem + sd * 256, ad, bd, idesc_nu, ks ? 1u : 0u);
-        }
-        mma_commit(&ms.bar_nu[0]);
-      }
     }
+    if (it == 0 && I > 1) v_load(vround_img + 2, vround_w8);
     SWEM_CTA_WAIT(&ms.bar_mma, ph_mma, ms.abort_flag);
     ph_mma ^= 1;
     tc_fence_after_sync();
@@ -612,7 +646,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(emr::kThreads, 1) em
       uint32_t rz16[16];
       if (cb == 0) tmem_ld16(tmem_addr(tmem, q * 32, col_m + kCk), rz16);
       tmem_ld_wait();
-      float* ns = reinterpret_cast<float*>(smem + kOffKH);        // [64 c][128 l] fp32
+      float* ns = reinterpret_cast<float*>(smem + (last ? kOffXH : kOffKH));   // [64 c][128 l] fp32 (last iteration: X is dead, z_lo is not)
 #pragma unroll
       for (int j = 0; j < 16; ++j) ns[(cb * 16 + j) * kL + px] = __uint_as_float(r[j]) + pri[j];
       if (cb == 0) ms.zrow[px] = __uint_as_float(rz16[0]) + pri_z;
@@ -621,9 +655,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(emr::kThreads, 1) em
     if (!last) {
       tc_fence_before_sync();
       EMR_STAMP(5);                                     // partial staged
-      reduce_issue(acc);
+      reduce_issue(acc, kOffKH);
       reduce_arrive(counter);
       EMR_STAMP(6);                                     // reduce-added + arrived
+      if (it == 0) {
+        v_store(vround_img + 2, vround_w8);
+        v_publish();
+      }
       if (tid == 0) {
         if (!wait_counter_fast(counter, 4u * (unsigned)p.T)) ms.abort_flag = 1;
         EMR_STAMP(7);                                   // all tiles arrived
@@ -633,26 +671,47 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(emr::kThreads, 1) em
       if (!ms.abort_flag) finalize(acc, false);
       EMR_STAMP(8);                                     // finalize done (before the loop-top barrier)
     } else {
-      // ---- last iteration: kappa all-reduce under the nu GEMMs, own-side drain under the peer-side GEMM ----------------
+      // ---- last iteration: nu = Z^T V^T for this side, one pass over the 8 operand images through the ring; the kappa
+      // all-reduce completes under it and the first channel half drains while the second is still being multiplied ----------
       tc_fence_before_sync();
       __syncthreads();                                  // every warp has read its M-step columns: TMEM is free for nu
       tc_fence_after_sync();
       EMR_STAMP(5);
-      reduce_issue(acc);                                // (before the issuing thread blocks on the peer's z: it is part of a block barrier)
+      reduce_issue(acc, kOffXH);
+      if (mma_thread) {
+#pragma unroll 1
+        for (int seq = 0; seq < kImages; ++seq) {
+          const int st = seq % kStages;
+          if (!mbar_wait(&ms.bar_full[st], (seq / kStages) & 1)) ms.abort_flag = 1;
+          tc_fence_after_sync();
+          const int h = (seq >> 2) ^ rank, qd = seq & 3;
+          const uint32_t vb = sbase + kOffVS + st * kImgBytes;
+#pragma unroll
+          for (int kk = 0; kk < 2; ++kk) {
+            const uint64_t ad = make_sdesc(sbase + kOffZ + (qd * 2 + kk) * 2 * 128, /*lbo*/ 128, /*sbo*/ 2048);
+            const uint64_t al = make_sdesc(sbase + kOffZL + (qd * 2 + kk) * 2 * 128, /*lbo*/ 128, /*sbo*/ 2048);
+            const uint64_t bh = make_sdesc(vb + kk * 2 * 4096, /*lbo*/ 4096, /*sbo*/ 128);
+            const uint64_t bl = make_sdesc(vb + kVPlane + kk * 2 * 4096, /*lbo*/ 4096, /*sbo*/ 128);
+            mma_f16_ss(tmem + h * 256, ad, bh, idesc_nu, (qd | kk) ? 1u : 0u);   // z_hi v_hi
+            mma_f16_ss(tmem + h * 256, ad, bl, idesc_nu, 1u);                    // z_hi v_lo
+            mma_f16_ss(tmem + h * 256, al, bh, idesc_nu, 1u);                    // z_lo v_hi
+          }
+          mma_commit(&ms.bar_empty[st]);                // -> the loader thread refills this stage
+          if (qd == 3) mma_commit(&ms.bar_nu[seq >> 2]);   // this channel half is complete
+        }
+      } else if (tid == 64) {         // loader: refill a stage as soon as the MMAs that read it have retired
+#pragma unroll 1
+        for (int seq = kStages; seq < kImages; ++seq) {
+          if (!mbar_wait(&ms.bar_empty[seq % kStages], ((seq - kStages) / kStages) & 1)) ms.abort_flag = 1;
+          if (seq == 4) {             // the peer's channel half
+            if (!mbar_wait_cluster(&ms.bar_vready, 0)) ms.abort_flag = 1;
+            asm volatile("fence.proxy.async;" ::: "memory");
+          }
+          load_image(seq);
+        }
+      }
       reduce_arrive(counter);
       EMR_STAMP(6);
-      if (mma_thread) {
-        if (!mbar_wait(&ms.bar_zp, 0)) ms.abort_flag = 1;   // the peer's z has landed in ZP
-        asm volatile("fence.proxy.async;" ::: "memory");
-        tc_fence_after_sync();
-#pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {
-          const uint64_t ad = make_sdesc(sbase + kOffZP + ks * 2 * 128, /*lbo*/ 128, /*sbo*/ 2048);
-          const uint64_t bd = make_sdesc(sbase + kOffV + ks * 2 * 4096, /*lbo*/ 4096, /*sbo*/ 128);
-          mma_f16_ss(tmem + (sd ^ 1) * 256, ad, bd, idesc_nu, ks ? 1u : 0u);
-        }
-        mma_commit(&ms.bar_nu[1]);
-      }
       if (tid == 0) {
         if (!wait_counter_fast(counter, 4u * (unsigned)p.T)) ms.abort_flag = 1;
         EMR_STAMP(7);
@@ -660,34 +719,36 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(emr::kThreads, 1) em
       __syncthreads();
       if (!ms.abort_flag) finalize(acc, true);
       EMR_STAMP(8);
-      // drain: TMEM [128 l][256 d] of side s -> smem [64 d][128 l] fp32 -> bulk reduce-add into acc_nu; 4 rounds per side, two
-      // staging buffers over the X / khat region (dead: the M-step GEMM has completed)
+      // drain: TMEM [128 l][512 d] -> smem [64 d][128 l] fp32 -> bulk reduce-add into acc_nu, 8 rounds of 32 KB.  Both halves of
+      // the GEMM have completed, so X, khat / z_lo, z and the ring are all dead: six staging buffers, no CTA-wide barrier inside
+      // the loop -- the 4 warps of a column block (16 channels) meet on a named barrier and their leader hands the block's 8 KB
+      // to the bulk-copy engine; rounds 6 and 7 reuse the first two buffers once the leader's copies of rounds 0 / 1 have been read.
+      if (!warp_wait(&ms.bar_nu[0], 0, 0)) ms.abort_flag = 1;
+      if (!warp_wait(&ms.bar_nu[1], 0, 0)) ms.abort_flag = 1;
+      tc_fence_after_sync();
+      EMR_STAMP(10);                                    // nu GEMM done
 #pragma unroll 1
       for (int rr = 0; rr < 8; ++rr) {
-        const int sidx = (rr < 4) ? sd : (sd ^ 1);
-        if (rr == 0 || rr == 4) {
-          SWEM_CTA_WAIT(&ms.bar_nu[rr >> 2], 0, ms.abort_flag);
-          tc_fence_after_sync();
-          EMR_STAMP(9 + (rr >> 2));                     // nu GEMM of the own / peer side done
-        }
-        float* ns = reinterpret_cast<float*>(smem + (rr & 1) * kStageBytes);
-        if (rr >= 2) {
-          if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-          __syncthreads();
+        const int dcol = rr * 64;                       // value channel = TMEM column
+        const uint32_t boff = rr < 3 ? rr * 32768u : rr < 6 ? kOffVS + (rr - 3) * 32768u : (rr - 6) * 32768u;
+        float* ns = reinterpret_cast<float*>(smem + boff);
+        if (rr >= 6) {
+          if (q == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 5;" ::: "memory");
+          bar_sync(9 + cb, 128);
         }
         {
           uint32_t r[16];
-          tmem_ld16(tmem_addr(tmem, q * 32, sidx * 256 + (rr & 3) * 64 + cb * 16), r);
+          tmem_ld16(tmem_addr(tmem, q * 32, dcol + cb * 16), r);
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 16; ++j) ns[(cb * 16 + j) * kL + px] = __uint_as_float(r[j]);
         }
         fence_proxy_async_smem();
-        __syncthreads();
-        if (tid == 0) {
-          float* dst = p.acc_nu + (((size_t)u * 2 + sidx) * kCv + rank * kDH + (rr & 3) * 64) * kL;
+        bar_sync(5 + cb, 128);
+        if (q == 0 && lane == 0) {
+          float* dst = p.acc_nu + ((size_t)gs * kCv + dcol + cb * 16) * kL;
           asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(dst),
-                       "r"(smem_u32(ns)), "r"(kStageBytes)
+                       "r"(smem_u32(ns + cb * 16 * kL)), "r"(16 * kL * 4)
                        : "memory");
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
@@ -703,11 +764,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(emr::kThreads, 1) em
           nu_pre[j] = (k < d1 * l4n) ? __ldg(pri4 + (k / l4n) * (L / 4) + k % l4n) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
-      if (tid == 0) {
+      if (q == 0 && lane == 0) {
         asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // full completion (not just .read) before the arrival
-        EMR_STAMP(11);                                  // nu drained
         atomicAdd(counter_nu, 1u);
-        if (!wait_counter_fast(counter_nu, 2u * (unsigned)p.T)) ms.abort_flag = 1;
+      }
+      __syncwarp();
+      if (tid == 0) {
+        EMR_STAMP(11);                                  // nu drained
+        if (!wait_counter_fast(counter_nu, 8u * (unsigned)p.T)) ms.abort_flag = 1;
         EMR_STAMP(12);                                  // every CTA of the unit has drained
       }
       tc_fence_before_sync();
@@ -841,6 +905,7 @@ static int fused_em_res_forward_t(const SwemEmArgs& a, cudaStream_t st) {
   Arena ws(a.workspace);
   float* acc_k = ws.take<float>((size_t)U * d.n_iters * 2 * (emr::kCk + 1) * emr::kL);
   float* acc_nu = ws.take<float>((size_t)U * 2 * emr::kCv * emr::kL);
+  uint8_t* vblob = ws.take<uint8_t>((size_t)U * T * emr::kImages * emr::kImgBytes);
   unsigned* counters = bar_range();
   if (counters == nullptr) {
     set_error("fused EM: cannot allocate the arrival counters (the first swem_em_forward of a device must not run under stream capture)");
@@ -851,7 +916,7 @@ static int fused_em_res_forward_t(const SwemEmArgs& a, cudaStream_t st) {
   p.x = a.x; p.v = a.v; p.masks = a.masks;
   p.kappa_prior = a.kappa_prior; p.nu_prior = a.nu_prior; p.zita_prior = a.zita_prior;
   p.kappa = a.kappa; p.nu = a.nu; p.zita = a.zita; p.z_last = a.z_last;
-  p.acc_k = acc_k; p.acc_nu = acc_nu; p.counters = counters;
+  p.acc_k = acc_k; p.acc_nu = acc_nu; p.counters = counters; p.vblob = vblob;
   p.status = reinterpret_cast<int*>(counters + kBarWords - 1);
   p.N = d.N; p.HW = d.HW; p.T = T; p.n_iters = d.n_iters; p.L = d.L; p.U = U;
   p.c1s = kLog2e / (d.tau * emr::kKScale);
