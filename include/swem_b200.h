@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define SWEM_B200_ABI_VERSION 2
+#define SWEM_B200_ABI_VERSION 3
 
 typedef enum SwemStatus {
   SWEM_OK = 0,
@@ -130,6 +130,12 @@ typedef struct SwemReadArgs {
   int32_t path;              /* SwemPath                                                          */
   int32_t out_pixel_major;   /* 0: out is [B*N, out_channels, HW] (reference, NCHW); 1: [B*N, HW, out_channels] (NHWC,
                                 what a channels-last fusion conv consumes without a layout copy)          */
+  int32_t bank_images_valid; /* bit k set: the tensor-core operand images of bank k (fp16 hi/lo of l2norm(kappa) and of nu) that an
+                                earlier swem_readout_forward call built in THIS workspace, for the same dims and the same,
+                                unmodified kappa[k] / nu[k], are still intact -- their conversion is skipped.  The reference
+                                never changes its 'first' bank while a sequence runs (modules.py:44-60), so a caller that keeps a
+                                workspace per sequence sets bit 0 from the second readout on.  0 = convert every bank (always
+                                safe); ignored by the generic family.                                                  */
 } SwemReadArgs;
 
 size_t swem_readout_workspace_bytes(const SwemDims* dims, int32_t path);

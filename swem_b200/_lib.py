@@ -53,7 +53,7 @@ class SwemReadArgs(C.Structure):
                 ('out', C.c_void_p),
                 ('out_channels', C.c_int32), ('mem_channel', C.c_int32), ('s_channel', C.c_int32),
                 ('workspace', C.c_void_p), ('workspace_bytes', C.c_size_t),
-                ('path', C.c_int32), ('out_pixel_major', C.c_int32)]
+                ('path', C.c_int32), ('out_pixel_major', C.c_int32), ('bank_images_valid', C.c_int32)]
 
 
 class SwemReadBwdArgs(C.Structure):
@@ -111,8 +111,8 @@ def load() -> C.CDLL:
     lib.swem_cbam_apply.argtypes = [C.c_void_p] * 3 + [C.c_int32, C.c_int64, C.c_int32] + [C.c_void_p] * 2
     lib.swem_bias_add_act.argtypes = [C.c_void_p] * 4 + [C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
     lib.swem_glu_gate.argtypes = [C.c_void_p] * 3 + [C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]
-    if lib.swem_abi_version() != 2:
-        raise RuntimeError(f'libswem_b200.so ABI version {lib.swem_abi_version()} != 2')
+    if lib.swem_abi_version() != 3:
+        raise RuntimeError(f'libswem_b200.so ABI version {lib.swem_abi_version()} != 3')
     _lib = lib
     return lib
 

@@ -136,11 +136,13 @@ class SWEMCore(nn.Module):
         self.fusion_layer = FeatureFusionLayer(valdim * 2 + self.topl * 2, valdim)
         self.launches = 0          # kernels launched by this object's last memorize/matching call
         self._workspace = _Workspace()
+        self._image_key = None     # what the bank images in the readout workspace were built from (see _readout_launch)
 
     # -- bank state ------------------------------------------------------------------------
     def empty(self):
         for bank in self.memories.values():
             bank.initial_memory()
+        self._image_key = None
 
     def get_mem(self) -> Tuple[torch.Tensor, torch.Tensor]:
         banks = [m.bases for m in self.memories.values() if m.bases is not None]
@@ -220,7 +222,7 @@ class SWEMCore(nn.Module):
         lib = _lib.load()
         dims = _lib.SwemDims(B, N, Ck, Cv, H * W, L, self.n_iters, 0, 0, self.tau)
         need = lib.swem_em_workspace_bytes(C.byref(dims), self.em_path)
-        ws = self._workspace.get(dev, need)
+        ws = self._workspace.get(dev, need, 'em')
         args = _lib.SwemEmArgs(dims, x.data_ptr(), v.data_ptr(), masks.data_ptr(),
                                kappa_.data_ptr(), nu_.data_ptr(), zita_.data_ptr(),
                                kappa.data_ptr(), nu.data_ptr(), zita.data_ptr(),
@@ -286,10 +288,13 @@ class SWEMCore(nn.Module):
         if not banks:
             raise RuntimeError('matching() before any memorize(): memory is empty')
         return self._readout_launch(_f32c(qk.detach(), 'qk'), [_f32c(b['kappa'].detach(), 'kappa') for b in banks],
-                                    [_f32c(b['nu'].detach(), 'nu') for b in banks], feats, mem_channel, s_channel)
+                                    [_f32c(b['nu'].detach(), 'nu') for b in banks], feats, mem_channel, s_channel,
+                                    first_bank=(banks[0]['kappa'], banks[0]['nu']))
 
-    def _readout_launch(self, qk, kap, nus, feats, mem_channel: int, s_channel: int) -> torch.Tensor:
-        """One ``swem_readout_forward`` call on contiguous fp32 CUDA tensors (kap / nus: one entry per bank)."""
+    def _readout_launch(self, qk, kap, nus, feats, mem_channel: int, s_channel: int, first_bank=None) -> torch.Tensor:
+        """One ``swem_readout_forward`` call on contiguous fp32 CUDA tensors (kap / nus: one entry per bank).  ``first_bank``:
+        the (kappa, nu) tensor OBJECTS of the 'first' bank as the bank holds them, or None when the caller cannot vouch for
+        them (training): lets the call reuse that bank's operand images, see below."""
         if self.training and self.p_drop > 0:
             raise NotImplementedError('swem_b200: memory dropout (p_drop > 0) is not implemented')
         B, Ck, H, W = qk.shape
@@ -307,12 +312,23 @@ class SWEMCore(nn.Module):
         lib = _lib.load()
         dims = _lib.SwemDims(B, N, Ck, Cv, H * W, L, 0, len(nus), self.topl, self.tau)
         need = lib.swem_readout_workspace_bytes(C.byref(dims), self.readout_path)
-        ws = self._workspace.get(dev, need)
+        ws = self._workspace.get(dev, need, 'readout')            # not shared with the EM: the bank images in it survive a memorize
+        # SwemReadArgs.bank_images_valid: the 'first' bank does not change while a sequence runs (modules.py:44-60); its
+        # operand images stay in this workspace, so from the second readout on only the 'update' bank is converted.  The
+        # images are keyed by everything they depend on: the workspace, the shapes, and the bank's tensor objects (held here,
+        # so their storage cannot be recycled for other data) with their version counters.
+        key = None
+        if first_bank is not None and len(nus) == 2 and self.readout_path != _lib.PATH_GENERIC:
+            key = (ws.data_ptr(), ws.numel(), B, N, Ck, Cv, L, first_bank[0]._version, first_bank[1]._version)
+        prev = self._image_key
+        valid = 1 if (key is not None and prev is not None and prev[0] == key and prev[1] is first_bank[0]
+                      and prev[2] is first_bank[1]) else 0
+        self._image_key = None if key is None else (key, first_bank[0], first_bank[1])
         args = _lib.SwemReadArgs(dims, qk.data_ptr(),
                                  (C.c_void_p * 2)(*[k.data_ptr() for k in kap] + [None] * (2 - len(kap))),
                                  (C.c_void_p * 2)(*[n.data_ptr() for n in nus] + [None] * (2 - len(nus))),
                                  feats.data_ptr(), chans, mem_channel, s_channel,
-                                 ws.data_ptr(), ws.numel(), self.readout_path, pixel_major)
+                                 ws.data_ptr(), ws.numel(), self.readout_path, pixel_major, valid)
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev).cuda_stream
             rc = _invoke('readout', lambda: lib.swem_readout_forward(C.byref(args), stream))

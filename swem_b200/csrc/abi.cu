@@ -227,6 +227,8 @@ int swem_readout_forward(const SwemReadArgs* a, void* stream) {
                  a->s_channel >= 0 && a->s_channel + 2 * d.topl <= a->out_channels,
                  "channel placement outside out_channels=%d", a->out_channels);
   SWEM_CHECK_ARG(a->path >= SWEM_PATH_AUTO && a->path <= SWEM_PATH_FUSED, "bad path %d", a->path);
+  SWEM_CHECK_ARG(a->bank_images_valid >= 0 && a->bank_images_valid < (1 << d.n_banks), "bank_images_valid=%d names a bank beyond n_banks=%d",
+                 a->bank_images_valid, d.n_banks);
   SWEM_CHECK_ARG(a->out_pixel_major == 0 || (a->out_pixel_major == 1 && a->out_channels % 4 == 0 && a->mem_channel % 4 == 0),
                  "out_pixel_major=%d needs out_channels and mem_channel to be multiples of 4", a->out_pixel_major);
   if (a->path != SWEM_PATH_GENERIC && !fused_readout_supported(d)) {

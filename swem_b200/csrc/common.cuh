@@ -100,6 +100,8 @@ int fused_em_res_forward(const SwemEmArgs& a, cudaStream_t st);
 bool fused_readout_supported(const SwemDims& d);
 size_t fused_readout_workspace(const SwemDims& d);
 int fused_readout_forward(const SwemReadArgs& a, cudaStream_t st);
+bool fused_readout_topl_covers(const SwemDims& d);             // readout with the in-kernel top-l feature (fused_readout_topl.cu): Ck = 64, Lt <= 256
+int fused_readout_topl_launch(const SwemReadArgs& a, const uint8_t* kblob, const uint8_t* vblob, cudaStream_t st);
 
 // shared between families: sorted top-l prefix feature from normalised attention rows
 // P: [U, HW, 2*Lt] fp32 (row per pixel, column = side*Lt + j) -> out channels [s_channel, +2*topl)

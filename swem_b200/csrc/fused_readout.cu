@@ -94,12 +94,12 @@ struct ReadoutFusedParams {
 // khat blob of (u, s, column block): K-major rows jl = (bank*L + l) % R, R = min(Lt, 256) rows per block,
 // byte = (jl%8)*16 + (jl/8)*128 + (c/8)*LBO + (c%8)*2, LBO = R*16; hi plane then lo plane.
 template <int kCk>
-__global__ void readout_prep_kappa_kernel(const float* __restrict__ k0, const float* __restrict__ k1, int U, int n_banks, int kL,
-                                          uint8_t* __restrict__ kblob) {
+__device__ __forceinline__ void prep_kappa_rows(const float* __restrict__ k0, const float* __restrict__ k1, int U, int n_banks, int bank0,
+                                                int kL, uint8_t* __restrict__ kblob, int i) {   // i <-> (u, s, bank - bank0, l)
   using namespace ro;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;       // (u, s, bank, l)
-  if (i >= U * 2 * n_banks * kL) return;
-  const int l = i % kL, bank = (i / kL) % n_banks, s = (i / (kL * n_banks)) % 2, u = i / (kL * n_banks * 2);
+  const int nbk = n_banks - bank0;
+  if (i >= U * 2 * nbk * kL) return;
+  const int l = i % kL, bank = bank0 + (i / kL) % nbk, s = (i / (kL * nbk)) % 2, u = i / (kL * nbk * 2);
   const float* kp = (bank ? k1 : k0) + (((size_t)u * 2 + s) * kCk) * kL + l;
   float v[kCk];
   float ss = 0.f;
@@ -129,17 +129,17 @@ __global__ void readout_prep_kappa_kernel(const float* __restrict__ k0, const fl
 
 // nu blob of (u, half h, k-step kk): rows d (256), 16 columns j = 16*kk..; byte = (d%8)*16 + (d/8)*128 +
 // (jj/8)*4096 + (jj%8)*2; hi plane (8 KB) then lo plane.  Column order j = s*Lt + bank*128 + l (:272, :295-306).
-__global__ void readout_prep_nu_kernel(const float* __restrict__ n0, const float* __restrict__ n1, int U, int n_banks, int kL,
-                                       uint8_t* __restrict__ vblob) {
+__device__ __forceinline__ void prep_nu_groups(const float* __restrict__ n0, const float* __restrict__ n1, int U, int n_banks, int bank0,
+                                               int kL, uint8_t* __restrict__ vblob, long long i) {   // i <-> (u, s, bank - bank0, d, l-group of 8)
   using namespace ro;
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // (u, s, bank, d, l-group of 8)
-  const long long total = (long long)U * 2 * n_banks * kCv * (kL / 8);
+  const int nbk = n_banks - bank0;
+  const long long total = (long long)U * 2 * nbk * kCv * (kL / 8);
   if (i >= total) return;
   const int lg = (int)(i % (kL / 8));
   const int d = (int)((i / (kL / 8)) % kCv);
-  const int bank = (int)((i / ((kL / 8) * kCv)) % n_banks);
-  const int s = (int)((i / ((long long)(kL / 8) * kCv * n_banks)) % 2);
-  const int u = (int)(i / ((long long)(kL / 8) * kCv * n_banks * 2));
+  const int bank = bank0 + (int)((i / ((kL / 8) * kCv)) % nbk);
+  const int s = (int)((i / ((long long)(kL / 8) * kCv * nbk)) % 2);
+  const int u = (int)(i / ((long long)(kL / 8) * kCv * nbk * 2));
   const float4* src = reinterpret_cast<const float4*>((bank ? n1 : n0) + (((size_t)u * 2 + s) * kCv + d) * kL + lg * 8);
   const float4 a = __ldg(src), b = __ldg(src + 1);
   const float vals[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
@@ -156,6 +156,19 @@ __global__ void readout_prep_nu_kernel(const float* __restrict__ n0, const float
   const uint32_t off = (dl % 8) * 16 + (dl / 8) * 128 + jg * 4096;
   *reinterpret_cast<uint4*>(base + off) = *reinterpret_cast<uint4*>(hi);
   *reinterpret_cast<uint4*>(base + 8192 + off) = *reinterpret_cast<uint4*>(lo);
+}
+
+// One launch for both conversions, banks [bank0, n_banks) only (SwemReadArgs.bank_images_valid: a bank whose images are still
+// in the workspace is skipped): the first `kappa_blocks` blocks convert khat rows, the rest nu column groups.
+template <int kCk>
+__global__ void __launch_bounds__(256) readout_prep_kernel(const float* __restrict__ k0, const float* __restrict__ k1,
+                                                           const float* __restrict__ n0, const float* __restrict__ n1, int U, int n_banks,
+                                                           int bank0, int kL, int kappa_blocks, uint8_t* __restrict__ kblob,
+                                                           uint8_t* __restrict__ vblob) {
+  if ((int)blockIdx.x < kappa_blocks)
+    prep_kappa_rows<kCk>(k0, k1, U, n_banks, bank0, kL, kblob, blockIdx.x * 256 + threadIdx.x);
+  else
+    prep_nu_groups(n0, n1, U, n_banks, bank0, kL, vblob, (long long)(blockIdx.x - kappa_blocks) * 256 + threadIdx.x);
 }
 
 // ---- main kernel --------------------------------------------------------------------------------------
@@ -555,14 +568,23 @@ int fused_readout_forward(const SwemReadArgs& a, cudaStream_t st) {
   float* escr = ws.take<float>((size_t)U * d.HW * 2 * Lt);
 
   {
-    const int n = U * 2 * nb * d.L;
-    if (d.Ck == 64) readout_prep_kappa_kernel<64><<<(n + 127) / 128, 128, 0, st>>>(a.kappa[0], a.kappa[nb - 1], U, nb, d.L, kblob);
-    else readout_prep_kappa_kernel<128><<<(n + 127) / 128, 128, 0, st>>>(a.kappa[0], a.kappa[nb - 1], U, nb, d.L, kblob);
-    SWEM_LAUNCH_CHECK();
-    const long long m = (long long)U * 2 * nb * ro::kCv * (d.L / 8);
-    readout_prep_nu_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(a.nu[0], a.nu[nb - 1], U, nb, d.L, vblob);
-    SWEM_LAUNCH_CHECK();
+    // operand images: banks whose images the caller vouches for (bank_images_valid) are skipped -- in a sequence that is the
+    // 'first' bank from the second readout on; the valid banks must form a prefix [0, bank0)
+    int bank0 = 0;
+    while (bank0 < nb && ((a.bank_images_valid >> bank0) & 1)) ++bank0;
+    if (bank0 < nb) {
+      const int nbk = nb - bank0;
+      const int kappa_blocks = (U * 2 * nbk * d.L + 255) / 256;
+      const long long m = (long long)U * 2 * nbk * ro::kCv * (d.L / 8);
+      const unsigned grid = (unsigned)kappa_blocks + (unsigned)((m + 255) / 256);
+      if (d.Ck == 64)
+        readout_prep_kernel<64><<<grid, 256, 0, st>>>(a.kappa[0], a.kappa[nb - 1], a.nu[0], a.nu[nb - 1], U, nb, bank0, d.L, kappa_blocks, kblob, vblob);
+      else
+        readout_prep_kernel<128><<<grid, 256, 0, st>>>(a.kappa[0], a.kappa[nb - 1], a.nu[0], a.nu[nb - 1], U, nb, bank0, d.L, kappa_blocks, kblob, vblob);
+      SWEM_LAUNCH_CHECK();
+    }
   }
+  if (fused_readout_topl_covers(d)) return fused_readout_topl_launch(a, kblob, vblob, st);   // one kernel: scores, softmax, PV and top-l
 #define SWEM_RO_ATTR(LT_, CK_, NS_) \
   SWEM_CUDA(cudaFuncSetAttribute(readout_fused_kernel<LT_, CK_, NS_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ro::smem_bytes<CK_>()))
   static PerDevice once;                                 // function attributes are per device

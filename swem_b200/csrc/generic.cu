@@ -21,6 +21,7 @@
 #include <float.h>
 
 #include "common.cuh"
+#include "topl.cuh"
 
 namespace swem {
 
@@ -259,42 +260,6 @@ __global__ void readout_rows_kernel(float* __restrict__ sc, const float* __restr
 // ranks when they agree to ~1e-4 relative, which perturbs a running sum by less than that times
 // the smaller of the two.  f is scale invariant, so any positive multiple of exp-affinity works.
 // ------------------------------------------------------------------------------------------
-template <int NPL>
-__device__ __forceinline__ void bitonic_desc2(uint32_t (&a)[NPL], uint32_t (&b)[NPL], int lane) {
-  constexpr int N = 32 * NPL;
-#pragma unroll
-  for (int sz = 2; sz <= N; sz <<= 1) {
-#pragma unroll
-    for (int d = sz >> 1; d > 0; d >>= 1) {
-      if (d < NPL) {            // partner lives in this lane
-#pragma unroll
-        for (int k = 0; k < NPL; ++k) {
-          if ((k & d) == 0) {
-            const bool desc = (sz < NPL) ? ((k & sz) == 0) : (((lane * NPL) & sz) == 0);
-            const uint32_t alo = min(a[k], a[k | d]), ahi = max(a[k], a[k | d]);
-            a[k] = desc ? ahi : alo;
-            a[k | d] = desc ? alo : ahi;
-            const uint32_t blo = min(b[k], b[k | d]), bhi = max(b[k], b[k | d]);
-            b[k] = desc ? bhi : blo;
-            b[k | d] = desc ? blo : bhi;
-          }
-        }
-      } else {                  // partner lives in lane ^ (d / NPL), same register
-        const int ld = d / NPL;
-        const bool desc = (((lane * NPL) & sz) == 0);
-        const bool take_max = (desc == ((lane & ld) == 0));
-#pragma unroll
-        for (int k = 0; k < NPL; ++k) {
-          const uint32_t ya = __shfl_xor_sync(0xffffffffu, a[k], ld);
-          const uint32_t yb = __shfl_xor_sync(0xffffffffu, b[k], ld);
-          a[k] = take_max ? max(a[k], ya) : min(a[k], ya);
-          b[k] = take_max ? max(b[k], yb) : min(b[k], yb);
-        }
-      }
-    }
-  }
-}
-
 template <int NPL>
 __global__ void __launch_bounds__(256) perm_inv_kernel(const float* __restrict__ P, int U, int HW, int Lt,
                                                        int topl, float* __restrict__ out, int out_channels,

@@ -27,7 +27,7 @@ def test_header_symbols_are_exported(lib):
     assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
     for sym in declared:
         assert getattr(lib, sym) is not None
-    assert lib.swem_abi_version() == 2
+    assert lib.swem_abi_version() == 3
 
 
 def test_struct_layouts_match_header(lib):

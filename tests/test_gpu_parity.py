@@ -927,6 +927,47 @@ def test_em_single_launch_is_stable_over_many_calls():
         check(k + '_repeat', e, 1e-3)
 
 
+def test_readout_reuses_first_bank_images_only_while_they_are_valid():
+    """SwemReadArgs.bank_images_valid (host side: SWEMCore._readout_launch): the operand images of the unchanged 'first' bank are
+    reused from the second readout on -- same features bit for bit as a full conversion, one kernel less work -- and never after
+    the bank changed: an in-place update (version counter) or a new tensor object must be seen by the next readout."""
+    from swem_b200.synthetic import clustered_em_inputs, em_inputs
+    B, N, Ck, Cv, H, W, L = 1, 3, 64, 512, 30, 54, 128
+    core = _core(dict(L=L, Cv=Cv, n_iters=2, tau=0.05, topl=64), 'fused')
+    ref = O.OracleSWEMCore(n_bases=L, valdim=Cv, n_iters=2, tau=0.05, topl=64)
+    seen = []
+    import swem_b200.core as core_mod
+    real_args = core_mod._lib.SwemReadArgs
+    def spy(*a):
+        seen.append(a[-1])
+        return real_args(*a)
+    with torch.no_grad():
+        for call in range(2):
+            x, v, masks = clustered_em_inputs(B, N, Ck, Cv, H, W, seed=50 + call)
+            core.memorize(x.to(DEV), v.to(DEV), masks.to(DEV))
+        q, qv, _ = em_inputs(B, 1, Ck, Cv, H, W, seed=60)
+        q, qv = q.to(DEV), qv[:, 0].to(DEV)
+        core_mod._lib.SwemReadArgs = spy
+        try:
+            f1, _ = core.matching_features(q, qv)          # builds both banks' images
+            f2, _ = core.matching_features(q, qv)          # reuses bank 0
+            assert seen == [0, 1] and torch.equal(f1, f2)
+            core.memories['first'].bases['nu'].mul_(2.0)   # in-place change of the first bank
+            f3, _ = core.matching_features(q, qv)
+            assert seen[-1] == 0
+            first = core.memories['first'].bases
+            core.memories['first'].bases = {k: t.clone() for k, t in first.items()}   # same values, new tensor objects
+            f4, _ = core.matching_features(q, qv)
+            assert seen[-1] == 0 and torch.equal(f3, f4)
+            f5, _ = core.matching_features(q, qv)
+            assert seen[-1] == 1 and torch.equal(f4, f5)
+        finally:
+            core_mod._lib.SwemReadArgs = real_args
+    # the doubled first-bank values show up in mem_out (a stale image would have reproduced f1)
+    check('stale_image', 1.0 - maxrel(f3[:, :Cv], f1[:, :Cv]), 0.999)
+    assert core.launches == 2, core.launches                # image conversion of the update bank + the fused readout kernel
+
+
 def test_bench_configuration_passes_the_mask_gate():
     """The EXACT configuration bench.py times (same env defaults: FrameEngine parity convolutions = TF32 main term + bf16
     cross terms, autotuned cuDNN, pipelined CUDA-graph runner, tcgen05 EM / readout) through the north-star gate: >= 99.9 %

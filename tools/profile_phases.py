@@ -55,12 +55,24 @@ def main(N=5, H=30, W=54, I=4, reps=50):
         st = buf.cpu().tolist()
         n = st[128]
         t = st[129:129 + n]
-        rn = ['setup', 'scores GEMM', 'max pass', 'exp pass', 'PV issue', 'PV drain wait', 'store']
+        rn = ['setup', 'scores GEMM', 'max pass', 'exp pass', 'PV issue (+ top-l sort)', 'PV drain wait', 'store']
         print(f'readout_fused CTA0: total {(t[-1]-t[0])/1e3:.1f} us')
         for k in range(1, n):
             print(f'  {rn[k-1] if k-1 < len(rn) else "?":24s} {(t[k]-t[k-1])/1e3:8.2f} us')
+        feats_cl = torch.empty(N, 2 * Cv + 128, H, W, device=dev).contiguous(memory_format=torch.channels_last)
+        _lib.check(lib.swem_set_profile_buffer(buf.data_ptr(), buf.numel() * 8), 'set_profile')
+        core.readout_into(x, feats_cl, 0, 2 * Cv)
+        torch.cuda.synchronize()
+        lib.swem_set_profile_buffer(None, 0)
+        st = buf.cpu().tolist()
+        n = st[128]
+        t = st[129:129 + n]
+        print(f'readout_fused CTA0, pixel-major output: total {(t[-1]-t[0])/1e3:.1f} us')
+        for k in range(1, n):
+            print(f'  {rn[k-1] if k-1 < len(rn) else "?":24s} {(t[k]-t[k-1])/1e3:8.2f} us')
         for name, fn in (('memorize(EM)', lambda: core.swem(x, v, masks, prior)),
-                         ('readout', lambda: core.matching_features(x, v[:, 0]))):
+                         ('readout', lambda: core.matching_features(x, v[:, 0])),
+                         ('readout (pixel-major out)', lambda: core.readout_into(x, feats_cl, 0, 2 * Cv))):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             for _ in range(5):
                 fn()
