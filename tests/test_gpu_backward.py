@@ -158,3 +158,101 @@ def test_training_step_runs_end_to_end():
                  'swem_core.fusion_layer.layer_f.weight', 'decoder.pred.weight'):
         gr = dict(model.named_parameters())[name].grad
         assert gr is not None and torch.isfinite(gr).all() and gr.abs().max() > 0, name
+
+
+def test_training_step_loss_and_grads_match_the_reference_autograd():
+    """BASELINE configs[4] / SURVEY section 8(d) config 5: ONE full training step (3-frame clip, 2 objects, the second one empty on
+    the first frame, swem_trainer.py:59-108 restated) through the CUDA memory -- forward kernels + swem_em_backward /
+    swem_readout_backward behind autograd -- against the same step with the oracle core under torch autograd on the same
+    device and parameters.  The oracle core gets the reference's gradient structure: E / M / W steps under no_grad
+    (modules.py:93,112,122), only nu = (zita_ nu_ + v z) / zita differentiable (:164-165).  Loss and the gradients of key_proj,
+    key_comp, the fusion layer and the encoders / decoder ends must agree."""
+    import torch.nn.functional as F
+    from oracle import swem_oracle as O
+    from swem_b200 import SWEM, make_config
+    from swem_b200.synthetic import davis_sequence
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        torch.manual_seed(0)
+        model = SWEM(make_config(keydim=64, n_bases=128, n_iters=4, topl=64)).to(DEV).train()
+        for m in model.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.eval()
+        T, N, h, w = 3, 2, 96, 96
+        frames, init = davis_sequence(T, N, seed=3, size=(h, w))
+        init[:, 0] += init[:, N]                              # the last object is empty (padded sample, video_dataset.py:334-335)
+        init[:, N] = 0
+        frames, init = frames.to(DEV), init.to(DEV)
+        label = init.argmax(dim=1)
+
+        def ref_memorize(core, qk, qv, masks):               # OracleSWEMCore.memorize with the reference's no_grad structure
+            prior = core.banks.prior()
+            B, Ck, H, W = qk.shape
+            Nn, Cv, L = masks.shape[1], qv.shape[2], core.n_bases
+            if prior is None:
+                kp, nup, zp = (t.to(qk.device) for t in O.random_init(B, Nn, Ck, L, Cv, generator=torch.Generator().manual_seed(11)))
+            else:
+                kp, nup, zp = prior['kappa'], prior['nu'], prior['zita']
+            with torch.no_grad():
+                xf = qk.flatten(start_dim=-2)[:, None, None]
+                x_t = xf.transpose(-2, -1)
+                mk = masks.flatten(start_dim=-2).unsqueeze(-1)
+                wts, kappa = mk.clone(), kp.clone()
+                for it in range(core.n_iters):
+                    z = O.e_step(x_t, kappa, wts, core.tau)
+                    kappa, zita = O.m_step(z, xf, kp, zp)
+                    if it < core.n_iters - 1:
+                        wts = O.w_step(kappa, x_t, mk, core.tau)
+            nu = (zp * nup + torch.matmul(qv.flatten(start_dim=-2).unsqueeze(2), z)) / zita
+            core.banks.commit({'kappa': kappa, 'nu': nu, 'zita': zita})
+
+        def step(use_kernels):
+            if use_kernels:
+                torch.manual_seed(11)
+                ri = model.swem_core.random_init
+                model.swem_core.random_init = lambda size, norm_dim=-2, dtype=None, device=None: tuple(
+                    t.to(device) for t in O.random_init(size[0], size[1], size[3], size[4], 512, generator=torch.Generator().manual_seed(11)))
+                enc_k = lambda f: model('encode_key', f)
+                enc_v = lambda f, m, s: model('encode_value', f, m, s)
+                init_f = lambda k, v, m: model('init', k, v, m.long())
+                mem_f = lambda k, v, hd, sf: model('memorize', k, v, hd, sf)
+                match = lambda k, v: model('match', k, v)
+                seg = lambda n, c, s8, s4: model('segment', n, c, s8, s4, None, (h, w))
+            else:
+                om = O.OracleSWEM(model, 128, 4, 0.05, 64)
+                enc_k, enc_v = om.encode_key, om.encode_value
+                def mem_f(k, v, hd, sf):
+                    ref_memorize(om.core, k, v, O.build_em_masks(hd, sf, *k.shape[-2:]))
+                def init_f(k, v, m):
+                    om.core.empty()
+                    mem_f(k, v, m, m.float())
+                match = om.match
+                seg = lambda n, c, s8, s4: om.segment(n, c, s8, s4, (h, w))
+            model.zero_grad(set_to_none=True)
+            mk16, _, s16, _, _ = enc_k(frames[:, 0])
+            init_f(mk16, enc_v(frames[:, 0], init, s16), init)
+            loss = 0
+            for i in range(1, T):
+                qk16, qv16, s16, s8, s4 = enc_k(frames[:, i])
+                ctx, n = match(qk16, qv16)
+                logits, prob = seg(n, ctx, s8, s4)
+                loss = loss + F.cross_entropy(logits, label)
+                if i < T - 1:
+                    hard = F.one_hot(prob.argmax(1), N + 1).permute(0, 3, 1, 2)
+                    mem_f(qk16, enc_v(frames[:, i], prob, s16), hard, prob)
+            loss.backward()
+            if use_kernels:
+                model.swem_core.random_init = ri
+            return loss.detach(), {k: p.grad.detach().clone() for k, p in model.named_parameters() if p.grad is not None}
+
+        loss_k, grads_k = step(True)
+        loss_o, grads_o = step(False)
+    finally:
+        torch.backends.cudnn.allow_tf32 = True
+    check('train_loss', abs(loss_k.item() - loss_o.item()) / abs(loss_o.item()), 1e-4)
+    names = ['key_proj.key_proj.weight', 'key_comp.weight', 'swem_core.fusion_layer.layer_f.weight',
+             'swem_core.fusion_layer.layer_a.weight', 'key_encoder.conv1.weight', 'value_encoder.conv1.weight', 'decoder.pred.weight']
+    for name in names:
+        assert name in grads_k and name in grads_o, (name, sorted(grads_k)[:8])
+        check('grad ' + name, maxrel(grads_k[name], grads_o[name]), 2e-3)
