@@ -177,6 +177,12 @@ int swem_em_masks(const int64_t* hard, int32_t Hm, int32_t Wm,
  * logits_out, prob_out: [B, N+1, H, W].  N <= 16.                                                    */
 int swem_decode_tail(const float* logits_lr, int32_t B, int32_t N, int32_t Hl, int32_t Wl, int32_t H, int32_t W,
                      const float* valid_obj, float* logits_out, float* prob_out, void* stream);
+/* Same, plus the evaluator's next two ops on the probabilities just written (swem_evaluator.py:83-87):
+ * pred_out [B, 1, H, W] int64 = argmax over the N+1 classes (first maximum, like torch.argmax), hard_out [B, N+1, H, W] int64 =
+ * its one-hot -- what SWEM.memorize / swem_em_masks take as the hard masks.  Either may be NULL.                              */
+int swem_decode_tail_masks(const float* logits_lr, int32_t B, int32_t N, int32_t Hl, int32_t Wl, int32_t H, int32_t W,
+                           const float* valid_obj, float* logits_out, float* prob_out, int64_t* pred_out, int64_t* hard_out,
+                           void* stream);
 
 /* ---- decoder glue, channels-last (NHWC) fp32: UpsampleBlock.forward (networks.py:192-196) and the residual tail of
  * ResBlock.forward (:25-32) as single passes.

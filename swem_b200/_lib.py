@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, 'libswem_b200.so')
 PATH_AUTO, PATH_GENERIC, PATH_FUSED = 0, 1, 2
 
 EXPORTS = (
-    'swem_abi_version', 'swem_last_error', 'swem_device_check', 'swem_last_launch_count', 'swem_total_launch_count',
+    'swem_abi_version', 'swem_decode_tail_masks', 'swem_last_error', 'swem_device_check', 'swem_last_launch_count', 'swem_total_launch_count',
     'swem_em_workspace_bytes', 'swem_em_forward', 'swem_em_fused_supported',
     'swem_readout_workspace_bytes', 'swem_readout_forward', 'swem_readout_fused_supported',
     'swem_em_masks', 'swem_decode_tail', 'swem_set_profile_buffer',
@@ -99,6 +99,7 @@ def load() -> C.CDLL:
     lib.swem_em_masks.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32,
                                   C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
     lib.swem_decode_tail.argtypes = [C.c_void_p] + [C.c_int32] * 6 + [C.c_void_p] * 4
+    lib.swem_decode_tail_masks.argtypes = [C.c_void_p] + [C.c_int32] * 6 + [C.c_void_p] * 6
     lib.swem_set_profile_buffer.argtypes = [C.c_void_p, C.c_size_t]
     lib.swem_upsample_add.argtypes = [C.c_void_p] * 4 + [C.c_int32] * 7 + [C.c_void_p] * 3
     lib.swem_maxpool3x3s2.argtypes = [C.c_void_p] + [C.c_int32] * 4 + [C.c_void_p] * 2

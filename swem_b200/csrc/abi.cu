@@ -82,7 +82,8 @@ constexpr int kMaxTailObjs = 16;
 
 __global__ void decode_tail_kernel(const float* __restrict__ lr, int B, int N, int Hl, int Wl, int H, int W,
                                    const float* __restrict__ valid, float* __restrict__ logits_out,
-                                   float* __restrict__ prob_out) {
+                                   float* __restrict__ prob_out, long long* __restrict__ pred_out,
+                                   long long* __restrict__ hard_out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * H * W) return;
   const int x = i % W, y = (i / W) % H, b = i / (W * H);
@@ -117,7 +118,20 @@ __global__ void decode_tail_kernel(const float* __restrict__ lr, int B, int N, i
     prob[k] = expf(prob[k] - mxl);
     sum += prob[k];
   }
-  for (int k = 0; k <= N; ++k) prob_out[((size_t)(b * (N + 1) + k) * H + y) * W + x] = prob[k] / sum;
+  int best = 0;
+  float best_p = -1.f;
+  for (int k = 0; k <= N; ++k) {
+    const float pk = prob[k] / sum;
+    prob_out[((size_t)(b * (N + 1) + k) * H + y) * W + x] = pk;
+    if (pk > best_p) {                       // first maximum, like torch.argmax
+      best_p = pk;
+      best = k;
+    }
+  }
+  // the evaluator's next two ops (swem_evaluator.py:83-87: argmax over the classes, its one-hot) on the values just written
+  if (pred_out != nullptr) pred_out[((size_t)b * H + y) * W + x] = best;
+  if (hard_out != nullptr)
+    for (int k = 0; k <= N; ++k) hard_out[((size_t)(b * (N + 1) + k) * H + y) * W + x] = (k == best) ? 1 : 0;
 }
 
 }  // namespace swem
@@ -299,8 +313,9 @@ int swem_em_masks(const int64_t* hard, int32_t Hm, int32_t Wm, const float* soft
   return SWEM_OK;
 }
 
-int swem_decode_tail(const float* logits_lr, int32_t B, int32_t N, int32_t Hl, int32_t Wl, int32_t H, int32_t W,
-                     const float* valid_obj, float* logits_out, float* prob_out, void* stream) {
+int swem_decode_tail_masks(const float* logits_lr, int32_t B, int32_t N, int32_t Hl, int32_t Wl, int32_t H, int32_t W,
+                           const float* valid_obj, float* logits_out, float* prob_out, int64_t* pred_out, int64_t* hard_out,
+                           void* stream) {
   reset_launch_count();
   SWEM_CHECK_ARG(logits_lr && logits_out && prob_out, "NULL pointer");
   SWEM_CHECK_ARG(B > 0 && N > 0 && Hl > 0 && Wl > 0 && H > 0 && W > 0, "non-positive size");
@@ -309,10 +324,16 @@ int swem_decode_tail(const float* logits_lr, int32_t B, int32_t N, int32_t Hl, i
     return SWEM_ERR_UNSUPPORTED;
   }
   const int n = B * H * W;
-  decode_tail_kernel<<<(n + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(logits_lr, B, N, Hl, Wl, H, W, valid_obj,
-                                                                                     logits_out, prob_out);
+  decode_tail_kernel<<<(n + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      logits_lr, B, N, Hl, Wl, H, W, valid_obj, logits_out, prob_out, reinterpret_cast<long long*>(pred_out),
+      reinterpret_cast<long long*>(hard_out));
   SWEM_LAUNCH_CHECK();
   return SWEM_OK;
+}
+
+int swem_decode_tail(const float* logits_lr, int32_t B, int32_t N, int32_t Hl, int32_t Wl, int32_t H, int32_t W,
+                     const float* valid_obj, float* logits_out, float* prob_out, void* stream) {
+  return swem_decode_tail_masks(logits_lr, B, N, Hl, Wl, H, W, valid_obj, logits_out, prob_out, nullptr, nullptr, stream);
 }
 
 }  // extern "C"

@@ -24,7 +24,11 @@ def _to_frame_size(pred_mask: torch.Tensor, h: int, w: int) -> torch.Tensor:
 
 
 def hard_masks_from_scores(pred_mask: torch.Tensor):
-    """(B,N+1,H,W) scores -> argmax (B,1,H,W) and its int64 one-hot (B,N+1,H,W)."""
+    """(B,N+1,H,W) scores -> argmax (B,1,H,W) and its int64 one-hot (B,N+1,H,W).  Probabilities that come out of the fused decode
+    tail (``SWEM.decode_from_lowres`` -> ``swem_decode_tail_masks``) carry both already."""
+    fused = getattr(pred_mask, 'swem_hard_masks', None)
+    if fused is not None:
+        return fused
     pred = torch.argmax(pred_mask, dim=1, keepdim=True)
     idx = torch.arange(pred_mask.shape[1], dtype=pred.dtype, device=pred.device).view(1, -1, 1, 1)
     return pred, (pred == idx).type_as(pred)

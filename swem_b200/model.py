@@ -99,13 +99,18 @@ class SWEM(nn.Module):
         h, w = int(out_size[0]), int(out_size[1])
         logits = torch.empty(b, n + 1, h, w, device=lr.device, dtype=torch.float32)
         prob = torch.empty_like(logits)
+        pred = torch.empty(b, 1, h, w, device=lr.device, dtype=torch.int64)
+        hard = torch.empty(b, n + 1, h, w, device=lr.device, dtype=torch.int64)
         valid = None if valid_obj is None else valid_obj.float().contiguous()
         with torch.cuda.device(lr.device):
-            rc = _lib.load().swem_decode_tail(lr.data_ptr(), b, n, lr.shape[-2], lr.shape[-1], h, w,
-                                              None if valid is None else valid.data_ptr(),
-                                              logits.data_ptr(), prob.data_ptr(),
-                                              torch.cuda.current_stream(lr.device).cuda_stream)
-        _lib.check(rc, 'swem_decode_tail')
+            rc = _lib.load().swem_decode_tail_masks(lr.data_ptr(), b, n, lr.shape[-2], lr.shape[-1], h, w,
+                                                    None if valid is None else valid.data_ptr(),
+                                                    logits.data_ptr(), prob.data_ptr(), pred.data_ptr(), hard.data_ptr(),
+                                                    torch.cuda.current_stream(lr.device).cuda_stream)
+        _lib.check(rc, 'swem_decode_tail_masks')
+        # the evaluator's next two ops on `prob` (argmax over the classes + its one-hot, swem_evaluator.py:83-87) came out of the
+        # same kernel; evaluator.hard_masks_from_scores picks them up from the tensor instead of launching three ATen kernels
+        prob.swem_hard_masks = (pred, hard)
         return logits, prob
 
     def _aggregate_objects(self, preds, n, valid_obj):

@@ -501,6 +501,12 @@ def test_decode_tail_kernel_matches_torch():
                 assert (lg - lg0).abs().max().item() < 2e-3 * max(1.0, lg0.abs().max().item())
                 assert (pr - pr0).abs().max().item() < 1e-5
                 assert (pr.argmax(1) == pr0.argmax(1)).float().mean().item() > 0.9999
+                # swem_decode_tail_masks: the argmax and its one-hot of the probabilities it wrote, exactly
+                from swem_b200.evaluator import hard_masks_from_scores
+                pred, hard = hard_masks_from_scores(pr)
+                assert pred is pr.swem_hard_masks[0] and pred.dtype == hard.dtype == torch.int64
+                pred_t, hard_t = hard_masks_from_scores(pr.clone())           # (a clone carries no attachment: the torch ops)
+                assert torch.equal(pred, pred_t) and torch.equal(hard, hard_t)
 
 
 def test_cuda_graph_runner_matches_eager_runner():
