@@ -63,7 +63,7 @@ constexpr uint32_t kImgBytes = 32768;          // one V operand image: [256 d][3
 constexpr uint32_t kVPlane = 16384;
 constexpr int kImages = 8;                     // per tile: 2 channel halves x 4 pixel quarters
 constexpr uint32_t kOffMisc = kOffVS + kStages * kImgBytes;
-static_assert(kOffVS >= 3 * 32768, "nu drain staging: three 32 KB buffers below the ring");
+static_assert(kOffMisc >= 5 * 32768, "nu drain staging: five 32 KB buffers below the Misc block");
 
 struct Misc {
   float inv_nx[kTP];
@@ -175,6 +175,45 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(emr::kThreads, 1) em
   const int q = warp & 3, cb = warp >> 2;               // TMEM lane quadrant, column block
   const int px = q * 32 + lane;                         // epilogue: pixel (32 logits columns [32 cb, +32)); reduce-add / finalize: row l (16 columns [16 cb, +16))
   const int gs = u * 2 + sd;
+
+  // ---- every latency-critical global load of the set-up is issued first (prior kappa / zita, the pixel norms' channels, the X
+  // tile, the mask): ~1 us of L2 / HBM latency that then runs under the TMEM allocation, the barrier set-up and the clearing of
+  // the accumulators instead of after them (profiles/r2_phases.txt: set-up 5.5 -> 3.x us)
+  const bool valid_row = px < L;
+  float kap0[16], nrm[16];
+  float4 xa[2], xb[2];
+  const float zita_prior_f = valid_row ? __ldg(p.zita_prior + (size_t)gs * L + px) : 0.f;
+  {
+    const float* kprior = p.kappa_prior + ((size_t)gs * kCk + cb * 16) * L + (valid_row ? px : 0);
+#pragma unroll
+    for (int c = 0; c < 16; ++c) kap0[c] = valid_row ? __ldg(kprior + (size_t)c * L) : 0.f;
+  }
+  const int npq = tid & 127, ncq = tid >> 7;             // pixel norms: 4 threads per pixel, 16 channels each
+  {
+    const int pp = p0 + npq;
+    const float* xp = p.x + ((size_t)b * kCk + ncq * 16) * HW + pp;
+#pragma unroll
+    for (int c = 0; c < 16; ++c) nrm[c] = pp < HW ? __ldg(xp + (size_t)c * HW) : 0.f;
+  }
+  const float mask_px = (ncq == 0 && p0 + npq < HW) ? __ldg(p.masks + (size_t)gs * HW + p0 + npq) : 0.f;
+  const bool x_vec = (HW & 3) == 0;
+  {
+    const float* xrow = p.x + ((size_t)b * kCk + (tid >> 3)) * HW;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int pp0 = p0 + ((tid & 7) * 2 + j) * 8;
+      if (x_vec && pp0 + 7 < HW) {
+        xa[j] = __ldg(reinterpret_cast<const float4*>(xrow + pp0));
+        xb[j] = __ldg(reinterpret_cast<const float4*>(xrow + pp0) + 1);
+      } else {
+        float t[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) t[e] = (pp0 + e < HW) ? __ldg(xrow + pp0 + e) : 0.f;
+        xa[j] = make_float4(t[0], t[1], t[2], t[3]);
+        xb[j] = make_float4(t[4], t[5], t[6], t[7]);
+      }
+    }
+  }
 
   if (warp == 0) tmem_alloc(&ms.tmem_base, 512);
   if (tid == 0) {
@@ -301,7 +340,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(emr::kThreads, 1) em
   // GEMM by 3 us) nor next to a cross-tile reduction (they delay its completion by 1 us; profiles/r2_em_res_phases.txt).
   // ---- khat = l2norm(kappa) * 256 -> fp16 hi/lo K-major rows (reference :115).  Thread <-> (row px, channels [16 cb, +16)):
   // global accesses are coalesced over the rows, the squared norm meets in shared memory across the 4 warps of a lane quadrant
-  const bool valid_row = px < L;
   auto stage_khat = [&](const float (&kap)[16]) {
     float ss = 0.f;
 #pragma unroll
@@ -324,12 +362,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(emr::kThreads, 1) em
   // prior term of the M-step, added once per (unit, side) by the CTA of tile 0: zita_ * kappa_ (and zita_ itself), scaled like
   // the tensor-core sums (same thread mapping as the reduce-add)
   float pri[16], pri_z = 0.f;
-  const float zita_prior_f = valid_row ? __ldg(p.zita_prior + (size_t)gs * L + px) : 0.f;
   {
-    float kap0[16];
-    const float* kprior = p.kappa_prior + ((size_t)gs * kCk + cb * 16) * L + (valid_row ? px : 0);
-#pragma unroll
-    for (int c = 0; c < 16; ++c) kap0[c] = valid_row ? __ldg(kprior + (size_t)c * L) : 0.f;
     const float zp = (tile == 0) ? zita_prior_f * kZScale : 0.f;
 #pragma unroll
     for (int j = 0; j < 16; ++j) pri[j] = zp * kap0[j];
@@ -339,36 +372,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(emr::kThreads, 1) em
   EMR_STAMP(31);                                       // prior khat staged
   // pixel norms (4 threads per pixel, 16 channels each) + this side's mask
   {
-    const int pq = tid & 127, cq = tid >> 7, pp = p0 + pq;
     float ss = 0.f;
-    if (pp < HW) {
-      const float* xp = p.x + ((size_t)b * kCk + cq * 16) * HW + pp;
 #pragma unroll
-      for (int c = 0; c < 16; ++c) {
-        const float t = __ldg(xp + (size_t)c * HW);
-        ss = fmaf(t, t, ss);
-      }
-    }
-    ms.hew[cq][pq] = ss;
-    if (cq == 0) ms.mask[pq] = pp < HW ? __ldg(p.masks + (size_t)gs * HW + pp) : 0.f;
+    for (int c = 0; c < 16; ++c) ss = fmaf(nrm[c], nrm[c], ss);
+    ms.hew[ncq][npq] = ss;
+    if (ncq == 0) ms.mask[npq] = mask_px;
   }
   // X tile -> fp16 hi/lo chunks: thread -> (channel c = tid / 8, 2 pixel groups of 8)
   {
     const int c = tid >> 3;
-    const float* xrow = p.x + ((size_t)b * kCk + c) * HW;
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
       const int pg = (tid & 7) * 2 + j;
-      const int pp0 = p0 + pg * 8;
-      float t[8];
-      if (((HW & 3) == 0) && pp0 + 7 < HW) {
-        const float4 a = __ldg(reinterpret_cast<const float4*>(xrow + pp0));
-        const float4 bq = __ldg(reinterpret_cast<const float4*>(xrow + pp0) + 1);
-        t[0] = a.x; t[1] = a.y; t[2] = a.z; t[3] = a.w; t[4] = bq.x; t[5] = bq.y; t[6] = bq.z; t[7] = bq.w;
-      } else {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) t[e] = (pp0 + e < HW) ? __ldg(xrow + pp0 + e) : 0.f;
-      }
+      const float t[8] = {xa[j].x, xa[j].y, xa[j].z, xa[j].w, xb[j].x, xb[j].y, xb[j].z, xb[j].w};
       __align__(16) __half hi[8];
       __align__(16) __half lo[8];
 #pragma unroll
@@ -678,73 +694,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(emr::kThreads, 1) em
       tc_fence_after_sync();
       EMR_STAMP(5);
       reduce_issue(acc, kOffXH);
-      if (mma_thread) {
-#pragma unroll 1
-        for (int seq = 0; seq < kImages; ++seq) {
-          const int st = seq % kStages;
-          if (!mbar_wait(&ms.bar_full[st], (seq / kStages) & 1)) ms.abort_flag = 1;
-          tc_fence_after_sync();
-          const int h = (seq >> 2) ^ rank, qd = seq & 3;
-          const uint32_t vb = sbase + kOffVS + st * kImgBytes;
-#pragma unroll
-          for (int kk = 0; kk < 2; ++kk) {
-            const uint64_t ad = make_sdesc(sbase + kOffZ + (qd * 2 + kk) * 2 * 128, /*lbo*/ 128, /*sbo*/ 2048);
-            const uint64_t al = make_sdesc(sbase + kOffZL + (qd * 2 + kk) * 2 * 128, /*lbo*/ 128, /*sbo*/ 2048);
-            const uint64_t bh = make_sdesc(vb + kk * 2 * 4096, /*lbo*/ 4096, /*sbo*/ 128);
-            const uint64_t bl = make_sdesc(vb + kVPlane + kk * 2 * 4096, /*lbo*/ 4096, /*sbo*/ 128);
-            mma_f16_ss(tmem + h * 256, ad, bh, idesc_nu, (qd | kk) ? 1u : 0u);   // z_hi v_hi
-            mma_f16_ss(tmem + h * 256, ad, bl, idesc_nu, 1u);                    // z_hi v_lo
-            mma_f16_ss(tmem + h * 256, al, bh, idesc_nu, 1u);                    // z_lo v_hi
-          }
-          mma_commit(&ms.bar_empty[st]);                // -> the loader thread refills this stage
-          if (qd == 3) mma_commit(&ms.bar_nu[seq >> 2]);   // this channel half is complete
-        }
-      } else if (tid == 64) {         // loader: refill a stage as soon as the MMAs that read it have retired
-#pragma unroll 1
-        for (int seq = kStages; seq < kImages; ++seq) {
-          if (!mbar_wait(&ms.bar_empty[seq % kStages], ((seq - kStages) / kStages) & 1)) ms.abort_flag = 1;
-          if (seq == 4) {             // the peer's channel half
-            if (!mbar_wait_cluster(&ms.bar_vready, 0)) ms.abort_flag = 1;
-            asm volatile("fence.proxy.async;" ::: "memory");
-          }
-          load_image(seq);
-        }
-      }
       reduce_arrive(counter);
       EMR_STAMP(6);
-      if (tid == 0) {
-        if (!wait_counter_fast(counter, 4u * (unsigned)p.T)) ms.abort_flag = 1;
-        EMR_STAMP(7);
-      }
-      __syncthreads();
-      if (!ms.abort_flag) finalize(acc, true);
-      EMR_STAMP(8);
-      // drain: TMEM [128 l][512 d] -> smem [64 d][128 l] fp32 -> bulk reduce-add into acc_nu, 8 rounds of 32 KB.  Both halves of
-      // the GEMM have completed, so X, khat / z_lo, z and the ring are all dead: six staging buffers, no CTA-wide barrier inside
-      // the loop -- the 4 warps of a column block (16 channels) meet on a named barrier and their leader hands the block's 8 KB
-      // to the bulk-copy engine; rounds 6 and 7 reuse the first two buffers once the leader's copies of rounds 0 / 1 have been read.
-      if (!warp_wait(&ms.bar_nu[0], 0, 0)) ms.abort_flag = 1;
-      if (!warp_wait(&ms.bar_nu[1], 0, 0)) ms.abort_flag = 1;
-      tc_fence_after_sync();
-      EMR_STAMP(10);                                    // nu GEMM done
-#pragma unroll 1
-      for (int rr = 0; rr < 8; ++rr) {
-        const int dcol = rr * 64;                       // value channel = TMEM column
-        const uint32_t boff = rr < 3 ? rr * 32768u : rr < 6 ? kOffVS + (rr - 3) * 32768u : (rr - 6) * 32768u;
-        float* ns = reinterpret_cast<float*>(smem + boff);
-        if (rr >= 6) {
-          if (q == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 5;" ::: "memory");
-          bar_sync(9 + cb, 128);
-        }
-        {
-          uint32_t r[16];
-          tmem_ld16(tmem_addr(tmem, q * 32, dcol + cb * 16), r);
-          tmem_ld_wait();
+      // One thread of warp 1 issues the MMAs and refills the ring (the stage of image seq - 1 with image seq + 2, after the MMAs of
+      // seq - 1 have retired: those of seq are queued behind them, so the tensor core does not wait).  The other 15 warps drain
+      // the first channel half to complete -- the CTA's own -- while the second is still being multiplied.
+      auto drain_block = [&](int dcol, int blk, float* ns) {   // this warp's lane quadrant x the 16 channels of column block `blk`
+        uint32_t r[16];
+        tmem_ld16(tmem_addr(tmem, q * 32, dcol + blk * 16), r);
+        tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 16; ++j) ns[(cb * 16 + j) * kL + px] = __uint_as_float(r[j]);
-        }
-        fence_proxy_async_smem();
-        bar_sync(5 + cb, 128);
+        for (int j = 0; j < 16; ++j) ns[(blk * 16 + j) * kL + px] = __uint_as_float(r[j]);
+      };
+      auto drain_issue = [&](int dcol, float* ns) {            // leader of column block cb: its 8 KB -> acc_nu
         if (q == 0 && lane == 0) {
           float* dst = p.acc_nu + ((size_t)gs * kCv + dcol + cb * 16) * kL;
           asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(dst),
@@ -752,7 +714,85 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(emr::kThreads, 1) em
                        : "memory");
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
+      };
+      if (warp == 1) {
+        if (lane == 0) {
+          bool peer_ready = false;
+#pragma unroll 1
+          for (int seq = 0; seq < kImages; ++seq) {
+            const int st = seq % kStages;
+            if (!mbar_wait(&ms.bar_full[st], (seq / kStages) & 1)) ms.abort_flag = 1;
+            tc_fence_after_sync();
+            const int h = (seq >> 2) ^ rank, qd = seq & 3;
+            const uint32_t vb = sbase + kOffVS + st * kImgBytes;
+#pragma unroll
+            for (int kk = 0; kk < 2; ++kk) {
+              const uint64_t ad = make_sdesc(sbase + kOffZ + (qd * 2 + kk) * 2 * 128, /*lbo*/ 128, /*sbo*/ 2048);
+              const uint64_t al = make_sdesc(sbase + kOffZL + (qd * 2 + kk) * 2 * 128, /*lbo*/ 128, /*sbo*/ 2048);
+              const uint64_t bh = make_sdesc(vb + kk * 2 * 4096, /*lbo*/ 4096, /*sbo*/ 128);
+              const uint64_t bl = make_sdesc(vb + kVPlane + kk * 2 * 4096, /*lbo*/ 4096, /*sbo*/ 128);
+              mma_f16_ss(tmem + h * 256, ad, bh, idesc_nu, (qd | kk) ? 1u : 0u);   // z_hi v_hi
+              mma_f16_ss(tmem + h * 256, ad, bl, idesc_nu, 1u);                    // z_hi v_lo
+              mma_f16_ss(tmem + h * 256, al, bh, idesc_nu, 1u);                    // z_lo v_hi
+            }
+            mma_commit(&ms.bar_empty[st]);
+            if (qd == 3) mma_commit(&ms.bar_nu[seq >> 2]);   // this channel half is complete
+            if (seq >= 1 && seq + 2 < kImages) {
+              if (!mbar_wait(&ms.bar_empty[(seq - 1) % kStages], ((seq - 1) / kStages) & 1)) ms.abort_flag = 1;
+              if (seq + 2 >= 4 && !peer_ready) {           // images of the peer's channel half
+                if (!mbar_wait_cluster(&ms.bar_vready, 0)) ms.abort_flag = 1;
+                asm volatile("fence.proxy.async;" ::: "memory");
+                peer_ready = true;
+              }
+              load_image(seq + 2);
+            }
+          }
+        }
+        __syncwarp();
+      } else {
+        // rounds 0-3: the own channel half.  z, z_lo (= the khat region) and the ring are still operands: one 32 KB staging buffer
+        // in the X region, reused round after round (per column block: its leader waits for its copy to have been read).  Warp 5
+        // (quadrant 1 of block 1) also covers quadrant 1 of block 0, whose warp is issuing.
+        if (!warp_wait(&ms.bar_nu[0], 0, 0)) ms.abort_flag = 1;
+        tc_fence_after_sync();
+        EMR_STAMP(9);                                     // nu GEMM of the own channel half done
+        float* ns = reinterpret_cast<float*>(smem);
+#pragma unroll 1
+        for (int r4 = 0; r4 < 4; ++r4) {
+          const int dcol = rank * 256 + r4 * 64;
+          // (r4 = 0: the staged M-step partial of this iteration was read from the same 8 KB of the block)
+          if (q == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          bar_sync(9 + cb, 128);
+          if (warp == 5) bar_sync(9, 128);
+          drain_block(dcol, cb, ns);
+          if (warp == 5) drain_block(dcol, 0, ns);
+          fence_proxy_async_smem();
+          bar_sync(5 + cb, 128);
+          if (warp == 5) bar_sync(5, 128);
+          drain_issue(dcol, ns);
+        }
       }
+      __syncthreads();                                    // every MMA is issued; the issuing warp is back
+      // rounds 4-7: the peer's channel half, all 16 warps, a buffer per round (everything below the Misc block is dead by now)
+      if (!warp_wait(&ms.bar_nu[1], 0, 0)) ms.abort_flag = 1;
+      tc_fence_after_sync();
+      EMR_STAMP(10);                                      // nu GEMM done
+#pragma unroll 1
+      for (int r4 = 0; r4 < 4; ++r4) {
+        const int dcol = (rank ^ 1) * 256 + r4 * 64;
+        float* ns = reinterpret_cast<float*>(smem + 32768u * (1 + r4));
+        drain_block(dcol, cb, ns);
+        fence_proxy_async_smem();
+        bar_sync(5 + cb, 128);
+        drain_issue(dcol, ns);
+      }
+      if (tid == 0) {
+        if (!wait_counter_fast(counter, 4u * (unsigned)p.T)) ms.abort_flag = 1;   // the kappa all-reduce completed long ago
+        EMR_STAMP(7);
+      }
+      __syncthreads();
+      if (!ms.abort_flag) finalize(acc, true);
+      EMR_STAMP(8);
       unsigned* counter_nu = cnt_nu;
       // prior rows of this CTA's nu slice: loaded now, under the wait for the other tiles' drains
       {
