@@ -89,6 +89,14 @@ typedef struct SwemEmArgs {
   int32_t path;              /* SwemPath                                                          */
   int32_t v_pixel_major;     /* 1: `v` is [B, N, HW, Cv] (channels-last, as a cuDNN NHWC value encoder leaves it) -- fused
                                 family only (the generic family returns SWEM_ERR_UNSUPPORTED); 0: [B, N, Cv, HW] */
+  /* Optional (ABI v3): also leave the readout's tensor-core operand images of the bases this call produces in the workspace of
+   * the swem_readout_forward calls that will read them (same B, N, Ck, Cv, L; a memory of image_n_banks banks, these bases being
+   * bank image_bank), so that those calls can set bit image_bank of bank_images_valid and skip the conversion.  The EM kernel
+   * of the BASELINE shapes writes them from its finalize / nu slice; for every other shape the call appends the conversion
+   * launch itself.  image_workspace = NULL: nothing.                                                                      */
+  void*  image_workspace;
+  int32_t image_bank;
+  int32_t image_n_banks;
 } SwemEmArgs;
 
 size_t swem_em_workspace_bytes(const SwemDims* dims, int32_t path);

@@ -36,7 +36,8 @@ class SwemEmArgs(C.Structure):
                 ('kappa', C.c_void_p), ('nu', C.c_void_p), ('zita', C.c_void_p),
                 ('z_last', C.c_void_p),
                 ('workspace', C.c_void_p), ('workspace_bytes', C.c_size_t),
-                ('path', C.c_int32), ('v_pixel_major', C.c_int32)]
+                ('path', C.c_int32), ('v_pixel_major', C.c_int32),
+                ('image_workspace', C.c_void_p), ('image_bank', C.c_int32), ('image_n_banks', C.c_int32)]
 
 
 class SwemEmBwdArgs(C.Structure):

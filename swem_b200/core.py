@@ -137,12 +137,16 @@ class SWEMCore(nn.Module):
         self.launches = 0          # kernels launched by this object's last memorize/matching call
         self._workspace = _Workspace()
         self._image_key = None     # what the bank images in the readout workspace were built from (see _readout_launch)
+        self._image1_src = None    # the 'update' bank tensors whose images the last memorize emitted (see memorize / _em_launch)
+        self._emit_images = False
+        self._emitted = None
 
     # -- bank state ------------------------------------------------------------------------
     def empty(self):
         for bank in self.memories.values():
             bank.initial_memory()
         self._image_key = None
+        self._image1_src = None
 
     def get_mem(self) -> Tuple[torch.Tensor, torch.Tensor]:
         banks = [m.bases for m in self.memories.values() if m.bases is not None]
@@ -223,11 +227,23 @@ class SWEMCore(nn.Module):
         dims = _lib.SwemDims(B, N, Ck, Cv, H * W, L, self.n_iters, 0, 0, self.tau)
         need = lib.swem_em_workspace_bytes(C.byref(dims), self.em_path)
         ws = self._workspace.get(dev, need, 'em')
+        # SwemEmArgs.image_workspace: when this call produces the 'update' bank of a two-bank memory (memorize() says so), the
+        # kernel also leaves the readout's operand images of the new bases in the readout workspace: the next readout converts
+        # nothing (bank 0 cached, bank 1 emitted here)
+        img_ws = None
+        if self._emit_images and not return_z and self.readout_path != _lib.PATH_GENERIC:
+            rdims = _lib.SwemDims(B, N, Ck, Cv, H * W, L, 0, 2, self.topl, self.tau)
+            rneed = lib.swem_readout_workspace_bytes(C.byref(rdims), self.readout_path)
+            if rneed:
+                img_ws = self._workspace.get(dev, rneed, 'readout')
+        self._emit_images = False
         args = _lib.SwemEmArgs(dims, x.data_ptr(), v.data_ptr(), masks.data_ptr(),
                                kappa_.data_ptr(), nu_.data_ptr(), zita_.data_ptr(),
                                kappa.data_ptr(), nu.data_ptr(), zita.data_ptr(),
                                z_last.data_ptr() if return_z else None,
-                               ws.data_ptr(), ws.numel(), self.em_path, 0 if v.is_contiguous() else 1)
+                               ws.data_ptr(), ws.numel(), self.em_path, 0 if v.is_contiguous() else 1,
+                               None if img_ws is None else img_ws.data_ptr(), 1, 2)
+        self._emitted = None if img_ws is None else (img_ws.data_ptr(), img_ws.numel(), B, N, Ck, Cv, L)
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev).cuda_stream
             rc = _invoke('em', lambda: lib.swem_em_forward(C.byref(args), stream))
@@ -239,17 +255,30 @@ class SWEMCore(nn.Module):
         prior = self.memories['update'].bases
         if prior is None:
             prior = self.memories['first'].bases
+        # from the second memorize on the result is the 'update' bank of a two-bank memory (modules.py:183-193): ask the EM call
+        # for its readout operand images (see _em_launch)
+        self._emit_images = self.memories['first'].bases is not None and not torch.is_grad_enabled()
+        self._emitted = None
         bases = self.swem(qk, qv, masks, prior)
+        self._emit_images = False
         if self.memories['first'].bases is None:
             self.memories['first'].update(bases)
         else:
+            n_first = self.memories['first'].n_objs
             self.memories['first'].update(bases)
+            if self.memories['first'].n_objs != n_first or bases['kappa'].shape[1] != n_first:
+                self._image_key = None                      # new objects joined the 'first' bank: its images are stale
             upd = self.memories['update']
             if self.static_banks and upd.bases is not None and upd.bases['kappa'].shape == bases['kappa'].shape:
                 for key in ('kappa', 'nu', 'zita'):
                     upd.bases[key].copy_(bases[key])
             else:
                 upd.update(bases)
+            # the tensors that now hold the bank whose images the kernel emitted (static banks: the copies, same values)
+            self._image1_src = None
+            if self._emitted is not None:
+                k1, n1 = upd.bases['kappa'], upd.bases['nu']
+                self._image1_src = (self._emitted, k1, n1, k1._version, n1._version)
 
     # -- readout ---------------------------------------------------------------------------
     def matching_features(self, qk, qv) -> Tuple[torch.Tensor, int]:
@@ -289,9 +318,10 @@ class SWEMCore(nn.Module):
             raise RuntimeError('matching() before any memorize(): memory is empty')
         return self._readout_launch(_f32c(qk.detach(), 'qk'), [_f32c(b['kappa'].detach(), 'kappa') for b in banks],
                                     [_f32c(b['nu'].detach(), 'nu') for b in banks], feats, mem_channel, s_channel,
-                                    first_bank=(banks[0]['kappa'], banks[0]['nu']))
+                                    first_bank=(banks[0]['kappa'], banks[0]['nu']),
+                                    update_bank=(banks[1]['kappa'], banks[1]['nu']) if len(banks) == 2 else None)
 
-    def _readout_launch(self, qk, kap, nus, feats, mem_channel: int, s_channel: int, first_bank=None) -> torch.Tensor:
+    def _readout_launch(self, qk, kap, nus, feats, mem_channel: int, s_channel: int, first_bank=None, update_bank=None) -> torch.Tensor:
         """One ``swem_readout_forward`` call on contiguous fp32 CUDA tensors (kap / nus: one entry per bank).  ``first_bank``:
         the (kappa, nu) tensor OBJECTS of the 'first' bank as the bank holds them, or None when the caller cannot vouch for
         them (training): lets the call reuse that bank's operand images, see below."""
@@ -324,6 +354,11 @@ class SWEMCore(nn.Module):
         valid = 1 if (key is not None and prev is not None and prev[0] == key and prev[1] is first_bank[0]
                       and prev[2] is first_bank[1]) else 0
         self._image_key = None if key is None else (key, first_bank[0], first_bank[1])
+        src = self._image1_src                              # bank 1: images emitted by the memorize that produced it
+        if (src is not None and update_bank is not None and key is not None
+                and src[0] == (ws.data_ptr(), ws.numel(), B, N, Ck, Cv, L) and src[1] is update_bank[0] and src[2] is update_bank[1]
+                and src[3] == update_bank[0]._version and src[4] == update_bank[1]._version):
+            valid |= 2
         args = _lib.SwemReadArgs(dims, qk.data_ptr(),
                                  (C.c_void_p * 2)(*[k.data_ptr() for k in kap] + [None] * (2 - len(kap))),
                                  (C.c_void_p * 2)(*[n.data_ptr() for n in nus] + [None] * (2 - len(nus))),

@@ -212,7 +212,26 @@ int swem_em_forward(const SwemEmArgs* a, void* stream) {
     set_error("v_pixel_major is implemented by the fused EM kernels only (Ck=%d Cv=%d L=%d path=%d)", a->dims.Ck, a->dims.Cv, a->dims.L, a->path);
     return SWEM_ERR_UNSUPPORTED;
   }
-  return use_fused_em(a->dims, a->path) ? fused_em_forward(*a, st) : generic_em_forward(*a, st);
+  if (a->image_workspace != nullptr) {
+    SWEM_CHECK_ARG(a->image_n_banks >= 1 && a->image_n_banks <= 2 && a->image_bank >= 0 && a->image_bank < a->image_n_banks,
+                   "image_bank=%d / image_n_banks=%d", a->image_bank, a->image_n_banks);
+    SWEM_CHECK_ARG((reinterpret_cast<uintptr_t>(a->image_workspace) & 255) == 0, "image_workspace must be 256-byte aligned");
+  }
+  const int rc = use_fused_em(a->dims, a->path) ? fused_em_forward(*a, st) : generic_em_forward(*a, st);
+  if (rc != SWEM_OK || a->image_workspace == nullptr) return rc;
+  if (use_fused_em(a->dims, a->path) && fused_em_res_emits_images(*a)) return rc;          // written by the EM kernel itself
+  // every other kernel: append the conversion launch for this bank (same stream, after the bases are complete)
+  SwemDims rd = a->dims;
+  rd.n_banks = a->image_n_banks;
+  rd.topl = 1;                                                                                 // (irrelevant to the images)
+  if (!fused_readout_supported(rd)) return rc;                                               // (no tcgen05 readout will read images of this shape)
+  const ReadoutImages im = readout_image_layout(a->image_workspace, rd);
+  const float* kk[2] = {nullptr, nullptr};
+  const float* nn[2] = {nullptr, nullptr};
+  kk[a->image_bank] = a->kappa;
+  nn[a->image_bank] = a->nu;
+  const int rc2 = launch_bank_images(rd, kk, nn, a->image_bank, a->image_bank + 1, im, st);
+  return rc2;
 }
 
 size_t swem_em_backward_workspace_bytes(const SwemDims* d) {

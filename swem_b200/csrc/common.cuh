@@ -97,9 +97,18 @@ size_t fused_em_workspace(const SwemDims& d);
 int fused_em_forward(const SwemEmArgs& a, cudaStream_t st);
 bool fused_em_res_covers(const SwemDims& d, bool v_pixel_major);   // V-resident kernel (fused_em_res.cu): Ck = 64, L <= 128
 int fused_em_res_forward(const SwemEmArgs& a, cudaStream_t st);
+bool fused_em_res_emits_images(const SwemEmArgs& a);            // the kernel writes the readout's operand images of its output bases itself
 bool fused_readout_supported(const SwemDims& d);
 size_t fused_readout_workspace(const SwemDims& d);
 int fused_readout_forward(const SwemReadArgs& a, cudaStream_t st);
+struct ReadoutImages {        // tensor-core operand images of the memory banks inside a readout workspace (fused_readout.cu)
+  uint8_t* kblob;
+  uint8_t* vblob;
+  size_t end_offset;
+};
+ReadoutImages readout_image_layout(void* workspace, const SwemDims& d);
+int launch_bank_images(const SwemDims& d, const float* const kappa[2], const float* const nu[2], int bank0, int bank1,
+                       const ReadoutImages& im, cudaStream_t st);
 bool fused_readout_topl_covers(const SwemDims& d);             // readout with the in-kernel top-l feature (fused_readout_topl.cu): Ck = 64, Lt <= 256
 int fused_readout_topl_launch(const SwemReadArgs& a, const uint8_t* kblob, const uint8_t* vblob, cudaStream_t st);
 

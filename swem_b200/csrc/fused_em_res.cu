@@ -104,6 +104,9 @@ struct EmResParams {
   float* zita;
   float* z_last;
   uint8_t* vblob;        // [U][T][8][32 KB] scratch: operand images of V
+  uint8_t* img_k;        // optional: the readout's khat / nu operand images of the OUTPUT bases (SwemEmArgs.image_workspace), bank
+  uint8_t* img_v;        // img_bank of a memory of img_Lt / L banks; layouts of readout_prep_kernel (fused_readout.cu)
+  int img_bank, img_Lt;
   float* acc_k;          // [U][n_iters][2][65][128]   (zeroed by the kernel itself, see "accumulators" below)
   float* acc_nu;         // [U][2][512][128]
   unsigned* counters;    // library-owned, zero between launches: [U][n_iters][2] M-step arrivals, then [U] accumulators zeroed,
@@ -455,6 +458,32 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(emr::kThreads, 1) em
         float* kout = p.kappa + ((size_t)gs * kCk + cb * 16) * L + px;
 #pragma unroll
         for (int c = 0; c < 16; ++c) kout[(size_t)c * L] = kap[c];
+      }
+      if (tile == 0 && p.img_k != nullptr) {
+        // the readout's khat operand of these bases: l2norm(kappa) * 256 as fp16 hi/lo, K-major rows j = bank L + l of the
+        // [Lt rows][Ck] block of (u, side) (readout_prep_kernel's layout), straight from the registers that hold kappa
+        float ss = 0.f;
+#pragma unroll
+        for (int c = 0; c < 16; ++c) ss = fmaf(kap[c], kap[c], ss);
+        ms.hsum[cb][px] = ss;
+        bar_sync(9 + q, 128);
+        ss = (ms.hsum[0][px] + ms.hsum[1][px]) + (ms.hsum[2][px] + ms.hsum[3][px]);
+        if (valid_row) {
+          const float sc = kKScale / (sqrtf(ss) + kEpsNorm);
+          const int R = p.img_Lt;                         // (Lt <= 256: one block per side)
+          const uint32_t plane = (uint32_t)R * kCk * 2, lbo = (uint32_t)R * 16;
+          const int j = p.img_bank * L + px;
+          uint8_t* base = p.img_k + (size_t)gs * 2 * plane + (j % 8) * 16 + (j / 8) * 128;
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            __align__(16) __half hi[8];
+            __align__(16) __half lo[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) split_half(kap[g * 8 + e] * sc, hi[e], lo[e]);
+            *reinterpret_cast<uint4*>(base + (cb * 2 + g) * lbo) = *reinterpret_cast<uint4*>(hi);
+            *reinterpret_cast<uint4*>(base + plane + (cb * 2 + g) * lbo) = *reinterpret_cast<uint4*>(lo);
+          }
+        }
       }
     } else {
       stage_khat(kap);
@@ -842,6 +871,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(emr::kThreads, 1) em
       o.z = (ms.zp[l + 2] * pr.z + a.z * kInvZ) * ms.rz[l + 2];
       o.w = (ms.zp[l + 3] * pr.w + a.w * kInvZ) * ms.rz[l + 3];
       out4[i] = o;
+      if (p.img_v != nullptr) {
+        // the readout's nu operand of these bases: fp16 hi/lo, k-step kk = column / 16 of (u, channel half), [256 d][16 j] per step
+        const int j = sd * p.img_Lt + p.img_bank * L + l;                 // column of the memory (side-major, then bank)
+        const int ks2 = 2 * p.img_Lt / 16;
+        uint8_t* dst = p.img_v + (((size_t)u * 2 + (d >> 8)) * ks2 + (j >> 4)) * 16384 + ((d & 255) % 8) * 16 + ((d & 255) / 8) * 128 +
+                       ((j >> 3) & 1) * 4096 + (j & 7) * 2;
+        __align__(8) __half hi[4];
+        __align__(8) __half lo[4];
+        split_half(o.x, hi[0], lo[0]); split_half(o.y, hi[1], lo[1]); split_half(o.z, hi[2], lo[2]); split_half(o.w, hi[3], lo[3]);
+        *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<uint2*>(hi);
+        *reinterpret_cast<uint2*>(dst + 8192) = *reinterpret_cast<uint2*>(lo);
+      }
     }
     EMR_STAMP(13);                   // nu slice written
   }
@@ -901,6 +942,12 @@ static int res_clusters_resident() {
 constexpr int kBarWords = 4096;
 static size_t bar_words_needed(const SwemDims& d) { return (size_t)d.B * d.N * (d.n_iters * 2 + 3) + 1; }
 
+// SwemEmArgs.image_workspace: can the kernel write the readout's operand images itself?  (one block of rows per side: Lt <= 256)
+bool fused_em_res_emits_images(const SwemEmArgs& a) {
+  return a.image_workspace != nullptr && fused_em_res_covers(a.dims, a.v_pixel_major != 0) && a.image_n_banks >= 1 &&
+         a.image_n_banks * a.dims.L <= 256 && a.image_bank >= 0 && a.image_bank < a.image_n_banks;
+}
+
 // Shapes of the V-resident kernel: Ck = 64, L <= 128, and a unit's tile pairs co-resident (single-launch form)
 bool fused_em_res_covers(const SwemDims& d, bool v_pixel_major) {
   if (d.Ck != emr::kCk || (d.L != 64 && d.L != 128) || d.Cv != emr::kCv || d.n_iters < 1 || d.n_iters > 16) return false;
@@ -957,6 +1004,12 @@ static int fused_em_res_forward_t(const SwemEmArgs& a, cudaStream_t st) {
   p.kappa_prior = a.kappa_prior; p.nu_prior = a.nu_prior; p.zita_prior = a.zita_prior;
   p.kappa = a.kappa; p.nu = a.nu; p.zita = a.zita; p.z_last = a.z_last;
   p.acc_k = acc_k; p.acc_nu = acc_nu; p.counters = counters; p.vblob = vblob;
+  if (fused_em_res_emits_images(a)) {
+    SwemDims rd = d;
+    rd.n_banks = a.image_n_banks;
+    const ReadoutImages im = readout_image_layout(a.image_workspace, rd);
+    p.img_k = im.kblob; p.img_v = im.vblob; p.img_bank = a.image_bank; p.img_Lt = a.image_n_banks * d.L;
+  }
   p.status = reinterpret_cast<int*>(counters + kBarWords - 1);
   p.N = d.N; p.HW = d.HW; p.T = T; p.n_iters = d.n_iters; p.L = d.L; p.U = U;
   p.c1s = kLog2e / (d.tau * emr::kKScale);

@@ -95,19 +95,22 @@ struct ReadoutFusedParams {
 // byte = (jl%8)*16 + (jl/8)*128 + (c/8)*LBO + (c%8)*2, LBO = R*16; hi plane then lo plane.
 template <int kCk>
 __device__ __forceinline__ void prep_kappa_rows(const float* __restrict__ k0, const float* __restrict__ k1, int U, int n_banks, int bank0,
-                                                int kL, uint8_t* __restrict__ kblob, int i) {   // i <-> (u, s, bank - bank0, l)
+                                                int bank1, int kL, uint8_t* __restrict__ kblob, int i) {   // i <-> (u, s, bank - bank0, l)
   using namespace ro;
-  const int nbk = n_banks - bank0;
+  const int nbk = bank1 - bank0;
   if (i >= U * 2 * nbk * kL) return;
   const int l = i % kL, bank = bank0 + (i / kL) % nbk, s = (i / (kL * nbk)) % 2, u = i / (kL * nbk * 2);
   const float* kp = (bank ? k1 : k0) + (((size_t)u * 2 + s) * kCk) * kL + l;
   float v[kCk];
-  float ss = 0.f;
+  // squared norm as four quarter sums, (q0 + q1) + (q2 + q3): the order em_res_kernel uses when it emits these images itself
+  // (fused_em_res.cu, "khat operand of these bases") -- emitted and converted images are bit-identical
+  float qs[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
   for (int c = 0; c < kCk; ++c) {
     v[c] = __ldg(kp + (size_t)c * kL);
-    ss = fmaf(v[c], v[c], ss);
+    qs[c / (kCk / 4)] = fmaf(v[c], v[c], qs[c / (kCk / 4)]);
   }
+  const float ss = (qs[0] + qs[1]) + (qs[2] + qs[3]);
   const float sc = kKScale / (sqrtf(ss) + kEpsNorm);
   const int Lt = n_banks * kL, R = Lt < 256 ? Lt : 256, nblk = Lt / R;
   const uint32_t plane = R * kCk * 2;                          // bytes of one (hi or lo) plane of a block
@@ -130,9 +133,9 @@ __device__ __forceinline__ void prep_kappa_rows(const float* __restrict__ k0, co
 // nu blob of (u, half h, k-step kk): rows d (256), 16 columns j = 16*kk..; byte = (d%8)*16 + (d/8)*128 +
 // (jj/8)*4096 + (jj%8)*2; hi plane (8 KB) then lo plane.  Column order j = s*Lt + bank*128 + l (:272, :295-306).
 __device__ __forceinline__ void prep_nu_groups(const float* __restrict__ n0, const float* __restrict__ n1, int U, int n_banks, int bank0,
-                                               int kL, uint8_t* __restrict__ vblob, long long i) {   // i <-> (u, s, bank - bank0, d, l-group of 8)
+                                               int bank1, int kL, uint8_t* __restrict__ vblob, long long i) {   // i <-> (u, s, bank - bank0, d, l-group of 8)
   using namespace ro;
-  const int nbk = n_banks - bank0;
+  const int nbk = bank1 - bank0;
   const long long total = (long long)U * 2 * nbk * kCv * (kL / 8);
   if (i >= total) return;
   const int lg = (int)(i % (kL / 8));
@@ -158,17 +161,17 @@ __device__ __forceinline__ void prep_nu_groups(const float* __restrict__ n0, con
   *reinterpret_cast<uint4*>(base + 8192 + off) = *reinterpret_cast<uint4*>(lo);
 }
 
-// One launch for both conversions, banks [bank0, n_banks) only (SwemReadArgs.bank_images_valid: a bank whose images are still
+// One launch for both conversions, banks [bank0, bank1) only (SwemReadArgs.bank_images_valid: a bank whose images are still
 // in the workspace is skipped): the first `kappa_blocks` blocks convert khat rows, the rest nu column groups.
 template <int kCk>
 __global__ void __launch_bounds__(256) readout_prep_kernel(const float* __restrict__ k0, const float* __restrict__ k1,
                                                            const float* __restrict__ n0, const float* __restrict__ n1, int U, int n_banks,
-                                                           int bank0, int kL, int kappa_blocks, uint8_t* __restrict__ kblob,
+                                                           int bank0, int bank1, int kL, int kappa_blocks, uint8_t* __restrict__ kblob,
                                                            uint8_t* __restrict__ vblob) {
   if ((int)blockIdx.x < kappa_blocks)
-    prep_kappa_rows<kCk>(k0, k1, U, n_banks, bank0, kL, kblob, blockIdx.x * 256 + threadIdx.x);
+    prep_kappa_rows<kCk>(k0, k1, U, n_banks, bank0, bank1, kL, kblob, blockIdx.x * 256 + threadIdx.x);
   else
-    prep_nu_groups(n0, n1, U, n_banks, bank0, kL, vblob, (long long)(blockIdx.x - kappa_blocks) * 256 + threadIdx.x);
+    prep_nu_groups(n0, n1, U, n_banks, bank0, bank1, kL, vblob, (long long)(blockIdx.x - kappa_blocks) * 256 + threadIdx.x);
 }
 
 // ---- main kernel --------------------------------------------------------------------------------------
@@ -558,31 +561,55 @@ size_t fused_readout_workspace(const SwemDims& d) {
   return bytes + 256;
 }
 
+// Where the operand images of a memory of d.n_banks banks live in a readout workspace (one source of truth for the readout and for
+// the EM kernels that emit the images of the bases they produce)
+ReadoutImages readout_image_layout(void* workspace, const SwemDims& d) {
+  const size_t U = (size_t)d.B * d.N, Lt = (size_t)d.L * d.n_banks;
+  Arena ws(workspace);
+  ReadoutImages im;
+  im.kblob = ws.take<uint8_t>(U * 2 * 2 * Lt * d.Ck * 2);
+  im.vblob = ws.take<uint8_t>(U * 2 * (2 * Lt / 16) * ro::kStageBytes);
+  im.end_offset = ws.off;
+  return im;
+}
+
+// convert banks [bank0, bank1) of a memory of d.n_banks banks (kappa / nu: one pointer per bank, only those of the range are read)
+int launch_bank_images(const SwemDims& d, const float* const kappa[2], const float* const nu[2], int bank0, int bank1,
+                       const ReadoutImages& im, cudaStream_t st) {
+  if (bank0 >= bank1) return SWEM_OK;
+  const int U = d.B * d.N, nbk = bank1 - bank0;
+  const int kappa_blocks = (U * 2 * nbk * d.L + 255) / 256;
+  const long long m = (long long)U * 2 * nbk * ro::kCv * (d.L / 8);
+  const unsigned grid = (unsigned)kappa_blocks + (unsigned)((m + 255) / 256);
+  if (d.Ck == 64)
+    readout_prep_kernel<64><<<grid, 256, 0, st>>>(kappa[0], kappa[1], nu[0], nu[1], U, d.n_banks, bank0, bank1, d.L, kappa_blocks, im.kblob, im.vblob);
+  else
+    readout_prep_kernel<128><<<grid, 256, 0, st>>>(kappa[0], kappa[1], nu[0], nu[1], U, d.n_banks, bank0, bank1, d.L, kappa_blocks, im.kblob, im.vblob);
+  SWEM_LAUNCH_CHECK();
+  return SWEM_OK;
+}
+
 int fused_readout_forward(const SwemReadArgs& a, cudaStream_t st) {
   const SwemDims& d = a.dims;
   const int U = d.B * d.N, nb = d.n_banks, Lt = d.L * nb;
   const int T = (d.HW + ro::kTP - 1) / ro::kTP;
+  const ReadoutImages im = readout_image_layout(a.workspace, d);
+  uint8_t* kblob = im.kblob;
+  uint8_t* vblob = im.vblob;
   Arena ws(a.workspace);
-  uint8_t* kblob = ws.take<uint8_t>((size_t)U * 2 * 2 * Lt * d.Ck * 2);
-  uint8_t* vblob = ws.take<uint8_t>((size_t)U * 2 * (2 * Lt / 16) * ro::kStageBytes);
+  ws.off = im.end_offset;
   float* escr = ws.take<float>((size_t)U * d.HW * 2 * Lt);
 
   {
-    // operand images: banks whose images the caller vouches for (bank_images_valid) are skipped -- in a sequence that is the
-    // 'first' bank from the second readout on; the valid banks must form a prefix [0, bank0)
-    int bank0 = 0;
-    while (bank0 < nb && ((a.bank_images_valid >> bank0) & 1)) ++bank0;
-    if (bank0 < nb) {
-      const int nbk = nb - bank0;
-      const int kappa_blocks = (U * 2 * nbk * d.L + 255) / 256;
-      const long long m = (long long)U * 2 * nbk * ro::kCv * (d.L / 8);
-      const unsigned grid = (unsigned)kappa_blocks + (unsigned)((m + 255) / 256);
-      if (d.Ck == 64)
-        readout_prep_kernel<64><<<grid, 256, 0, st>>>(a.kappa[0], a.kappa[nb - 1], a.nu[0], a.nu[nb - 1], U, nb, bank0, d.L, kappa_blocks, kblob, vblob);
-      else
-        readout_prep_kernel<128><<<grid, 256, 0, st>>>(a.kappa[0], a.kappa[nb - 1], a.nu[0], a.nu[nb - 1], U, nb, bank0, d.L, kappa_blocks, kblob, vblob);
-      SWEM_LAUNCH_CHECK();
-    }
+    // operand images: banks whose images the caller vouches for (bank_images_valid: the reference's fixed 'first' bank from the
+    // second readout of a sequence on, a bank whose images the EM kernel emitted) are skipped; with two banks the banks to
+    // convert always form one range
+    int bank0 = 0, bank1 = nb;
+    while (bank0 < bank1 && ((a.bank_images_valid >> bank0) & 1)) ++bank0;
+    while (bank1 > bank0 && ((a.bank_images_valid >> (bank1 - 1)) & 1)) --bank1;
+    const float* const kk[2] = {a.kappa[0], a.kappa[1]};
+    const float* const nn[2] = {a.nu[0], a.nu[1]};
+    if (int rc = launch_bank_images(d, kk, nn, bank0, bank1, im, st)) return rc;
   }
   if (fused_readout_topl_covers(d)) return fused_readout_topl_launch(a, kblob, vblob, st);   // one kernel: scores, softmax, PV and top-l
 #define SWEM_RO_ATTR(LT_, CK_, NS_) \

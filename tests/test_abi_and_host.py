@@ -33,7 +33,7 @@ def test_header_symbols_are_exported(lib):
 def test_struct_layouts_match_header(lib):
     from swem_b200 import _lib
     assert C.sizeof(_lib.SwemDims) == 40
-    assert C.sizeof(_lib.SwemEmArgs) == 40 + 10 * 8 + 8 + 8 + 8      # dims, 10 pointers, ws ptr, size, path(+pad)
+    assert C.sizeof(_lib.SwemEmArgs) == 40 + 10 * 8 + 8 + 8 + 8 + 8 + 8      # dims, 10 pointers, ws ptr, size, path + layout, image ws, image bank + banks
     assert _lib.SwemReadArgs.out.offset == 40 + 8 + 16 + 16
 
 

@@ -933,14 +933,14 @@ def test_em_single_launch_is_stable_over_many_calls():
         check(k + '_repeat', e, 1e-3)
 
 
-def test_readout_reuses_first_bank_images_only_while_they_are_valid():
-    """SwemReadArgs.bank_images_valid (host side: SWEMCore._readout_launch): the operand images of the unchanged 'first' bank are
-    reused from the second readout on -- same features bit for bit as a full conversion, one kernel less work -- and never after
-    the bank changed: an in-place update (version counter) or a new tensor object must be seen by the next readout."""
+def test_readout_reuses_bank_images_only_while_they_are_valid():
+    """SwemReadArgs.bank_images_valid / SwemEmArgs.image_workspace (host side: SWEMCore.memorize / _readout_launch): the operand images
+    of the unchanged 'first' bank are reused from the second readout on, those of the 'update' bank are written by the EM kernel
+    that produces it -- same features bit for bit as a full conversion, no conversion launch -- and never after a bank changed: an
+    in-place update (version counter) or a new tensor object must be seen by the next readout."""
     from swem_b200.synthetic import clustered_em_inputs, em_inputs
     B, N, Ck, Cv, H, W, L = 1, 3, 64, 512, 30, 54, 128
     core = _core(dict(L=L, Cv=Cv, n_iters=2, tau=0.05, topl=64), 'fused')
-    ref = O.OracleSWEMCore(n_bases=L, valdim=Cv, n_iters=2, tau=0.05, topl=64)
     seen = []
     import swem_b200.core as core_mod
     real_args = core_mod._lib.SwemReadArgs
@@ -955,23 +955,39 @@ def test_readout_reuses_first_bank_images_only_while_they_are_valid():
         q, qv = q.to(DEV), qv[:, 0].to(DEV)
         core_mod._lib.SwemReadArgs = spy
         try:
-            f1, _ = core.matching_features(q, qv)          # builds both banks' images
-            f2, _ = core.matching_features(q, qv)          # reuses bank 0
-            assert seen == [0, 1] and torch.equal(f1, f2)
+            f1, _ = core.matching_features(q, qv)          # bank 1 emitted by the second memorize, bank 0 converted
+            f2, _ = core.matching_features(q, qv)          # nothing converted
+            assert seen == [2, 3] and torch.equal(f1, f2)
+            assert core.launches == 1, core.launches       # the fused readout kernel alone
+            core._image_key = core._image1_src = None      # forget both: full conversion
+            f0, _ = core.matching_features(q, qv)
+            assert seen[-1] == 0 and core.launches == 2
+            assert torch.equal(f0, f1), f'emitted vs converted images: features differ by {maxrel(f0, f1):.3e}'
             core.memories['first'].bases['nu'].mul_(2.0)   # in-place change of the first bank
             f3, _ = core.matching_features(q, qv)
-            assert seen[-1] == 0
+            assert seen[-1] == 0                           # (bank 1's emitted images were forgotten above)
             first = core.memories['first'].bases
             core.memories['first'].bases = {k: t.clone() for k, t in first.items()}   # same values, new tensor objects
             f4, _ = core.matching_features(q, qv)
             assert seen[-1] == 0 and torch.equal(f3, f4)
             f5, _ = core.matching_features(q, qv)
             assert seen[-1] == 1 and torch.equal(f4, f5)
+            x, v, masks = clustered_em_inputs(B, N, Ck, Cv, H, W, seed=52)
+            core.memorize(x.to(DEV), v.to(DEV), masks.to(DEV))     # a new update bank, images emitted again
+            f6, _ = core.matching_features(q, qv)
+            assert seen[-1] == 3 and core.launches == 1
+            core._image_key = core._image1_src = None
+            f7, _ = core.matching_features(q, qv)
+            assert seen[-1] == 0
+            assert torch.equal(f6, f7), f'emitted vs converted images (second time): features differ by {maxrel(f6, f7):.3e}'
+            core.memories['update'].bases['nu'].mul_(0.5)  # in-place change of the update bank
+            core.matching_features(q, qv)
+            core.matching_features(q, qv)
+            assert seen[-1] == 1                           # bank 0 cached, bank 1 never vouched for again
         finally:
             core_mod._lib.SwemReadArgs = real_args
     # the doubled first-bank values show up in mem_out (a stale image would have reproduced f1)
     check('stale_image', 1.0 - maxrel(f3[:, :Cv], f1[:, :Cv]), 0.999)
-    assert core.launches == 2, core.launches                # image conversion of the update bank + the fused readout kernel
 
 
 def test_bench_configuration_passes_the_mask_gate():

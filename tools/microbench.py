@@ -8,7 +8,11 @@ call.  CUDA-event timing over `--reps` back-to-back calls, once with the working
 fused tcgen05 where the shape is covered, generic fp32 otherwise), us per call and the fraction of the measured
 tensor peak for the algorithmic FLOPs F_mem = 4 N HW L [Ck (3I - 1) + Cv], F_read = 4 N HW Lt (Ck + Cv).
 
-    python tools/microbench.py [--reps 100] [--quick]
+    python tools/microbench.py [--reps 100] [--quick] [--eager]
+
+--eager adds the reference algorithm in eager PyTorch on the same device (the oracle core on CUDA tensors: what the unmodified
+modules.py does on a GPU) as two more columns -- the bar these kernels have to beat (SURVEY top of file).  Measurement tool:
+imports the oracle, like tools/precision_study.py; the product package never does.
 """
 import argparse
 import ctypes as C
@@ -59,6 +63,7 @@ def main():
     ap.add_argument('--reps', type=int, default=100)
     ap.add_argument('--quick', action='store_true', help='HW=1620 only, I in {1,4}')
     ap.add_argument('--ck', type=int, default=64, help='key channels (64 = BASELINE, 128 = reference CLI default)')
+    ap.add_argument('--eager', action='store_true', help='also time the oracle core on CUDA tensors (eager PyTorch reference)')
     args = ap.parse_args()
     global CK
     CK = args.ck
@@ -67,7 +72,7 @@ def main():
     peak = peak_tflops()
     flush = torch.zeros(64 << 20, device=dev)
     print(f'# EM / readout micro-benchmark, B=1 N={N} Ck={CK} Cv={CV}, {args.reps} reps, tensor peak {peak:.0f} TFLOP/s (measured bf16 sustained)')
-    print('#   HW     L  I  family(em/read)     em_us  em_us(L2 flushed)  em_TF/s  em_frac   read_us  read_us(flushed)  read_TF/s  read_frac')
+    print('#   HW     L  I  family(em/read)     em_us  em_us(L2 flushed)  em_TF/s  em_frac   read_us  read_us(flushed)  read_TF/s  read_frac' + ('  eager_em_us  eager_read_us  speedup(em/read)' if args.eager else ''))
     shapes = [(30, 54)] if args.quick else [(30, 54), (60, 108)]
     for (H, W) in shapes:
         HW = H * W
@@ -86,12 +91,26 @@ def main():
                     em = lambda: core.swem(x, v, masks, prior)
                     rd = lambda: core.matching_features(x, v[:, 0])
                     t_em, t_em_f = timed(em, args.reps), timed(em, max(10, args.reps // 4), flush)
+                    feats = torch.empty(N, 2 * CV + 2 * min(L, 64), H, W, device=dev).contiguous(memory_format=torch.channels_last)
+                    rd = lambda: core.readout_into(x, feats, 0, 2 * CV)          # kernels only, the engine's pixel-major layout
                     t_rd, t_rd_f = (timed(rd, args.reps), timed(rd, max(10, args.reps // 4), flush)) if I == 4 or args.quick else (float('nan'),) * 2
+                    t_eem = t_erd = float('nan')
+                    if args.eager:
+                        from oracle import swem_oracle as O
+                        ref = O.OracleSWEMCore(n_bases=L, valdim=CV, n_iters=I, tau=0.05, topl=64)
+                        ref.banks.first = {k: t.clone() for k, t in core.memories['first'].bases.items()}
+                        ref.banks.update = {k: t.clone() for k, t in prior.items()}
+                        ref.banks.first_n = N
+                        eprior = {k: t.reshape(1, N, 2, -1, L) if k == 'zita' else t for k, t in prior.items()}
+                        t_eem = timed(lambda: O.em_memorize(x, v, masks, eprior, L, I, 0.05), max(5, args.reps // 10))
+                        if I == 4 or args.quick:
+                            t_erd = timed(lambda: ref.matching_features(x, v[:, 0]), max(5, args.reps // 10))
                 f_mem = 4 * N * HW * L * (CK * (3 * I - 1) + CV)
                 f_read = 4 * N * HW * 2 * L * (CK + CV)
                 tf_em, tf_rd = f_mem / t_em / 1e6, f_read / t_rd / 1e6
                 print(f'  {HW:5d} {L:5d} {I:2d}  {fam[0] + "/" + fam[1]:16s} {t_em:9.1f} {t_em_f:14.1f} {tf_em:12.1f} {tf_em / peak:8.4f} '
-                      f'{t_rd:9.1f} {t_rd_f:14.1f} {tf_rd:12.1f} {tf_rd / peak:9.4f}', flush=True)
+                      f'{t_rd:9.1f} {t_rd_f:14.1f} {tf_rd:12.1f} {tf_rd / peak:9.4f}'
+                      + (f' {t_eem:12.1f} {t_erd:14.1f}   {t_eem / t_em:6.1f}x / {t_erd / t_rd:5.1f}x' if args.eager else ''), flush=True)
                 del core
 
 
