@@ -36,7 +36,7 @@ constexpr int kThreads = 512;
 constexpr float kKScale = 256.f;
 constexpr float kEScale = 1024.f;
 constexpr int kRing = 5;
-constexpr int kLag = 2;                  // refill the stage consumed kLag steps ago
+constexpr int kLag = 1;                  // refill the stage consumed kLag steps ago (1: four stages in flight; the MMAs of the current step are queued behind those waited for)
 constexpr uint32_t kStageBytes = 16384;  // one k-step of nu: [256 d][16 j] fp16 hi (8 KB) + lo (8 KB)
 constexpr int kOwn = 64;                 // pixels whose top-l feature this CTA computes
 
@@ -59,7 +59,7 @@ struct Misc {
   float inv_nq[kTP];
   float ex_max[4][kTP];
   float ex_sum[4][kTP];
-  uint32_t top[16][2][64];      // per warp: the top-l packed words of either side
+  __align__(16) uint32_t top[16][2][64];      // per warp: the top-l packed words of either side
   uint64_t bar_k[2];
   uint64_t bar_mma;
   uint64_t bar_full[kRing];
@@ -78,6 +78,7 @@ struct ReadoutToplParams {
   float* out;             // [U][out_channels][HW] or [U][HW][out_channels]
   long long* prof;
   int N, HW, T, out_channels, mem_channel, s_channel, pixel_major, topl;
+  int dbg;                // measurement switch (SWEM_RO_DBG): 1 = skip the top-l sort (S is garbage) -- times the PV product alone
   float c1s;              // log2(e) / (tau * kKScale)
 };
 
@@ -87,7 +88,7 @@ struct ReadoutToplParams {
   } while (0)
 
 template <int LT>
-__global__ void __block_size__((32, 16, 1)) readout_topl_kernel(const ReadoutToplParams p) {   // (fixed block shape: threadIdx.y is warp-uniform for ptxas)
+__global__ void __block_size__((32, 16, 1)) __maxnreg__(128) readout_topl_kernel(const ReadoutToplParams p) {   // (fixed block shape: threadIdx.y is warp-uniform for ptxas)
   using namespace rot;
   constexpr int Lt = LT;
   constexpr int ks_side = Lt / 16, ks2 = 2 * ks_side;
@@ -181,26 +182,30 @@ __global__ void __block_size__((32, 16, 1)) readout_topl_kernel(const ReadoutTop
   ROT_STAMP();   // setup (query tile staged)
 
   // ---- scores: side s -> TMEM columns [256 s, 256 s + Lt) ---------------------------------------------------------------
-  if (mma_thread) {
+  if (warp == 1) {                      // (converged warp, elected lane issues: see the PV product below)
     const uint32_t idesc = make_idesc(128, Lt, kFmtF16, kFmtF16, kMajorMN, kMajorK);
     constexpr uint32_t lbo_k = Lt * 16;
 #pragma unroll
     for (int s = 0; s < 2; ++s) {
       ok = mbar_wait(&ms.bar_k[s], 0) && ok;
       const uint32_t kb = sbase + kOffKB + s * kKBSide;
+      if (elect_one()) {
 #pragma unroll
-      for (int term = 0; term < 3; ++term) {
-        const uint32_t qa = sbase + (term == 2 ? kOffQL : kOffQH);
-        const uint32_t kbt = kb + (term == 1 ? kplane : 0);
+        for (int term = 0; term < 3; ++term) {
+          const uint32_t qa = sbase + (term == 2 ? kOffQL : kOffQH);
+          const uint32_t kbt = kb + (term == 1 ? kplane : 0);
 #pragma unroll
-        for (int kk = 0; kk < kCk / 16; ++kk) {
-          const uint64_t ad = make_sdesc(qa + kk * 2 * 2048, /*lbo*/ 2048, /*sbo*/ 128);
-          const uint64_t bd = make_sdesc(kbt + kk * 2 * lbo_k, /*lbo*/ lbo_k, /*sbo*/ 128);
-          mma_f16_ss(tmem + s * 256, ad, bd, idesc, (term | kk) ? 1u : 0u);
+          for (int kk = 0; kk < kCk / 16; ++kk) {
+            const uint64_t ad = make_sdesc(qa + kk * 2 * 2048, /*lbo*/ 2048, /*sbo*/ 128);
+            const uint64_t bd = make_sdesc(kbt + kk * 2 * lbo_k, /*lbo*/ lbo_k, /*sbo*/ 128);
+            mma_f16_ss(tmem + s * 256, ad, bd, idesc, (term | kk) ? 1u : 0u);
+          }
         }
       }
+      __syncwarp();
     }
-    mma_commit(&ms.bar_mma);
+    if (elect_one()) mma_commit(&ms.bar_mma);
+    __syncwarp();
   }
   if (tid == 0 && !mbar_wait(&ms.bar_mma, 0)) ms.abort_flag = 1;
   __syncthreads();
@@ -277,41 +282,55 @@ __global__ void __block_size__((32, 16, 1)) readout_topl_kernel(const ReadoutTop
   ROT_STAMP();   // exp pass + E packed
 
   if (warp == 1) {
-    if (lane == 0) {
     // ---- mem_out = E nu^T: A from TMEM (packed E), B from the ring; accumulators at columns 128.. and 384.. -----------------
+    // The whole warp runs the loop converged and one ELECTED lane issues: addresses and descriptors stay in uniform registers.
+    // (Issued from inside an `if (lane == 0)` branch every UTCHMMA was wrapped in an ELECT / R2UR.BROADCAST / BRA.U.ANY loop, ~100
+    //  instructions per k-step of a single thread that shares its scheduler with three sorting warps: the product ran at the
+    //  pace of that thread, 820 cycles per k-step against 520 for its four MMAs; profiles/r2_readout_phases.txt.)
     const uint32_t idesc = make_idesc(128, 128, kFmtF16, kFmtF16, kMajorK, kMajorK);
     const uint64_t bdesc0 = make_sdesc(sbase + kOffRing, /*lbo*/ 4096, /*sbo*/ 128);
-#pragma unroll
+#pragma unroll 1
     for (int kk = 0; kk < ks2; ++kk) {
       const int st = kk % kRing;
       ok = mbar_wait(&ms.bar_full[st], (kk / kRing) & 1) && ok;
       tc_fence_after_sync();
       const uint32_t a_tmem = tmem + (kk / ks_side) * 256 + (kk % ks_side) * 8;
-#pragma unroll
-      for (int term = 0; term < 2; ++term)
-#pragma unroll
-        for (int nh = 0; nh < 2; ++nh)
-          mma_f16_ts(tmem + 128 + nh * 256, a_tmem, bdesc0 + ((st * kStageBytes + term * 8192 + nh * 2048) >> 4), idesc,
-                     (kk | term) ? 1u : 0u);
-      mma_commit(&ms.bar_empty[st]);
+      const uint64_t bd = bdesc0 + ((uint32_t)(st * kStageBytes) >> 4);
+      if (elect_one()) {
+        mma_f16_ts(tmem + 128, a_tmem, bd, idesc, kk ? 1u : 0u);                            // E nu_hi, channels 0..127
+        mma_f16_ts(tmem + 384, a_tmem, bd + (2048 >> 4), idesc, kk ? 1u : 0u);              //          channels 128..255
+        mma_f16_ts(tmem + 128, a_tmem, bd + (8192 >> 4), idesc, 1u);                        // E nu_lo
+        mma_f16_ts(tmem + 384, a_tmem, bd + ((8192 + 2048) >> 4), idesc, 1u);
+        mma_commit(&ms.bar_empty[st]);
+      }
+      __syncwarp();
       if (kk >= kLag && kk - kLag + kRing < ks2) {
         const int prev = kk - kLag, nxt = prev + kRing;
         const int ps = prev % kRing;
         ok = mbar_wait(&ms.bar_empty[ps], (prev / kRing) & 1) && ok;
-        mbar_expect_tx(&ms.bar_full[ps], kStageBytes);
-        bulk_g2s(smem + kOffRing + ps * kStageBytes, vsrc + (size_t)nxt * kStageBytes, kStageBytes, &ms.bar_full[ps]);
+        if (elect_one()) {
+          mbar_expect_tx(&ms.bar_full[ps], kStageBytes);
+          bulk_g2s(smem + kOffRing + ps * kStageBytes, vsrc + (size_t)nxt * kStageBytes, kStageBytes, &ms.bar_full[ps]);
+        }
+        __syncwarp();
       }
     }
-    mma_commit(&ms.bar_mma);
+    if (elect_one()) mma_commit(&ms.bar_mma);
     if (!ok) ms.abort_flag = 1;
-    }
   } else {
     // ---- S: sorted top-l running sums of the own pixels (reference :198-208), one warp per pixel, under the PV product --------
-    const int pw = warp == 0 ? 0 : warp - 1;            // (warp 1 holds the issuing thread)
+    // Static split by scheduler (warp & 3), 16 pixels each: the scheduler that also hosts the issuing warp has three sorting
+    // warps (6 + 5 + 5 pixels) instead of four (4 each) -- the phase is bound by the min / max issue rate per scheduler.  (Pixel
+    // counts derived from threadIdx.y only: ptxas must see the loop as warp-uniform, or every shuffle below becomes a
+    // WARPSYNC.COLLECTIVE call.)
     const int topl = p.topl;
     uint32_t* mytop = &ms.top[warp][0][0];
+    const int sch = warp & 3, wj = warp >> 2;
+    const int px_first = sch * 16 + (sch == 1 ? (wj == 1 ? 0 : wj == 2 ? 6 : 11) : wj * 4);
+    const int px_count = sch == 1 ? (wj == 1 ? 6 : 5) : 4;
 #pragma unroll 1
-    for (int pl = pw; pl < kOwn; pl += 15) {
+    for (int pi = 0; pi < ((p.dbg & 1) ? 0 : px_count); ++pi) {
+      const int pl = px_first + pi;
       const int pp = p0 + h * kOwn + pl;
       if (pp >= HW) break;
       const float* row = etab + pl * kERow;
@@ -323,11 +342,18 @@ __global__ void __block_size__((32, 16, 1)) readout_topl_kernel(const ReadoutTop
         const int i = l16 + 16 * k;                     // (any assignment of columns to lanes does: the word carries the column)
         a[k] = __uint_as_float(((__float_as_uint(row[side * kESide + i]) >> (IDXB - 1)) << IDXB) | (uint32_t)i);
       }
-      sort_desc_half<R>(a, l16);
+      if constexpr (Lt == 256) {                        // selection network: the order of the other 192 words is never established
+        float t4[4];
+        top64_of_256_half(a, l16, t4);
+        *reinterpret_cast<uint4*>(mytop + side * 64 + top64_rank_base(l16)) =
+            make_uint4(__float_as_uint(t4[0]), __float_as_uint(t4[1]), __float_as_uint(t4[2]), __float_as_uint(t4[3]));
+      } else {
+        sort_desc_half<R>(a, l16);
 #pragma unroll
-      for (int k = 0; k < R; ++k) {
-        const int r = l16 * R + k;                      // rank r sits in lane16 r / R, register r % R
-        if (r < 64) mytop[side * 64 + r] = __float_as_uint(a[k]);
+        for (int k = 0; k < R; ++k) {
+          const int r = l16 * R + k;                    // rank r sits in lane16 r / R, register r % R
+          if (r < 64) mytop[side * 64 + r] = __float_as_uint(a[k]);
+        }
       }
       __syncwarp();
       // lane handles ranks lane and lane + 32: exact values, inclusive running sums over rank
@@ -453,6 +479,10 @@ int fused_readout_topl_launch(const SwemReadArgs& a, const uint8_t* kblob, const
   p.pixel_major = a.out_pixel_major; p.topl = d.topl;
   p.c1s = kLog2e / (d.tau * rot::kKScale);
   p.prof = get_profile_buffer();
+  {
+    const char* dbg = getenv("SWEM_RO_DBG");
+    p.dbg = dbg ? atoi(dbg) : 0;
+  }
   if (Lt == 64) readout_topl_kernel<64><<<U * T * 2, dim3(32, 16, 1), rot::kSmemBytes, st>>>(p);
   else if (Lt == 128) readout_topl_kernel<128><<<U * T * 2, dim3(32, 16, 1), rot::kSmemBytes, st>>>(p);
   else readout_topl_kernel<256><<<U * T * 2, dim3(32, 16, 1), rot::kSmemBytes, st>>>(p);

@@ -95,6 +95,20 @@ __device__ __forceinline__ uint64_t make_sdesc(uint32_t smem_addr, uint32_t lbo_
   return d;                // base_offset 0, lbo_mode 0, layout_type 0 (SWIZZLE_NONE)
 }
 
+// 64-bit shared-memory matrix descriptor of a K-major operand in the 128-byte-swizzled canonical layout: rows of 128 bytes (64
+// halfs of K), 8-row atoms of 1024 bytes in which the 16-byte chunk c of row i sits at chunk position c ^ i; the tile base must
+// be 1024-byte aligned, consecutive atoms along M / N are `sbo_bytes` apart (1024 when dense).  A K step of 16 halfs advances
+// the start address by 32 bytes inside the atom.  (Verified against a CPU GEMM by tools/umma_probe.cu tests 30-33.)
+__device__ __forceinline__ uint64_t make_sdesc_sw128(uint32_t smem_addr, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;                                   // LBO: unused for swizzled K-major operands
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;                                   // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                                   // layout_type: SWIZZLE_128B
+  return d;
+}
+
 // ---- MMA issue (ONE thread) -----------------------------------------------------------------
 __device__ __forceinline__ void mma_f16_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                            uint32_t accumulate) {

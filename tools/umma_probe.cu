@@ -22,6 +22,7 @@ struct Cfg {
   int swap;                   // swap LBO/SBO fields in the descriptors (alternative reading of the spec)
   uint32_t a_bytes, b_bytes;
   int repeat;                 // issue the whole K loop this many times (timing)
+  int swz;                    // 1: both operands K-major in the 128-byte-swizzled layout (rows of 64 halfs), SBO = 1024
 };
 
 __global__ void __launch_bounds__(128) probe(const uint8_t* a_img, const uint8_t* b_img, const __half* a_rowmajor,
@@ -66,10 +67,12 @@ __global__ void __launch_bounds__(128) probe(const uint8_t* a_img, const uint8_t
     const int kper = c.kind == 0 ? 16 : 8;
     for (int rep = 0; rep < c.repeat; ++rep)
       for (int k = 0; k < c.K / kper; ++k) {
-        const uint64_t ad = c.swap ? make_sdesc(smem_u32(sa) + k * c.a_kstep, c.a_sbo, c.a_lbo)
-                                   : make_sdesc(smem_u32(sa) + k * c.a_kstep, c.a_lbo, c.a_sbo);
-        const uint64_t bd = c.swap ? make_sdesc(smem_u32(sb) + k * c.b_kstep, c.b_sbo, c.b_lbo)
-                                   : make_sdesc(smem_u32(sb) + k * c.b_kstep, c.b_lbo, c.b_sbo);
+        const uint64_t ad = c.swz ? make_sdesc_sw128(smem_u32(sa) + k * c.a_kstep, c.a_sbo)
+                            : c.swap ? make_sdesc(smem_u32(sa) + k * c.a_kstep, c.a_sbo, c.a_lbo)
+                                     : make_sdesc(smem_u32(sa) + k * c.a_kstep, c.a_lbo, c.a_sbo);
+        const uint64_t bd = c.swz ? make_sdesc_sw128(smem_u32(sb) + k * c.b_kstep, c.b_sbo)
+                            : c.swap ? make_sdesc(smem_u32(sb) + k * c.b_kstep, c.b_sbo, c.b_lbo)
+                                     : make_sdesc(smem_u32(sb) + k * c.b_kstep, c.b_lbo, c.b_sbo);
         const uint32_t acc = (k > 0 || rep > 0) ? 1u : 0u;
         if (c.a_tmem) mma_f16_ts(tmem, tmem_addr(tmem, 0, a_col0 + k * c.a_kstep), bd, idesc, acc);
         else if (c.kind == 0) mma_f16_ss(tmem, ad, bd, idesc, acc);
@@ -172,6 +175,12 @@ static uint32_t off(int major, int kind, int r, int k, uint32_t lbo, uint32_t sb
   return (r % E) * es + (k % 8) * 16 + (r / E) * sbo + (k / 8) * lbo;
 }
 
+// byte offset of element (r, k) of a K-major f16 operand in the 128-byte-swizzled layout (K <= 64: one atom wide)
+static uint32_t off_sw128(int r, int k) {
+  const int chunk = (k * 2) / 16, i = r % 8;
+  return (r / 8) * 1024 + i * 128 + ((chunk ^ i) * 16) + (k * 2) % 16;
+}
+
 static void put(std::vector<uint8_t>& img, uint32_t o, int kind, float v) {
   if (kind == 0) {
     __half h = __float2half(v);
@@ -219,6 +228,14 @@ int main(int argc, char** argv) {
     case 11: name = "timing f16 K/K M128 N80 K128 x8"; kk_p1(128, 80, 128, 0); c.repeat = 8; break;
     case 12: name = "tf32 A MN-major (SBO=128,LBO=4096) B K-major M128 N64 K32"; kk_p1(128, 64, 32, 1);
       c.a_major = 1; c.a_sbo = 128; c.a_lbo = (128 / 4) * 128; c.a_kstep = c.a_lbo; break;
+    case 30: name = "f16 K/K 128B-swizzled M128 N256 K64 (k step +32 B)"; kk_p1(128, 256, 64, 0); c.swz = 1;
+      c.a_sbo = 1024; c.b_sbo = 1024; c.a_kstep = 32; c.b_kstep = 32; break;
+    case 31: name = "f16 K/K 128B-swizzled M128 N128 K64"; kk_p1(128, 128, 64, 0); c.swz = 1;
+      c.a_sbo = 1024; c.b_sbo = 1024; c.a_kstep = 32; c.b_kstep = 32; break;
+    case 32: name = "timing f16 K/K 128B-swizzled M128 N256 K64 x24"; kk_p1(128, 256, 64, 0); c.swz = 1; c.repeat = 24;
+      c.a_sbo = 1024; c.b_sbo = 1024; c.a_kstep = 32; c.b_kstep = 32; break;
+    case 33: name = "timing f16 K/K 128B-swizzled M128 N128 K64 x24"; kk_p1(128, 128, 64, 0); c.swz = 1; c.repeat = 24;
+      c.a_sbo = 1024; c.b_sbo = 1024; c.a_kstep = 32; c.b_kstep = 32; break;
     default: printf("no such test\n"); return 2;
   }
   const int Mrows = 128;  // image always sized for 128 rows
@@ -228,8 +245,8 @@ int main(int argc, char** argv) {
       for (int k = 0; k < c.K; ++k) mx = std::max(mx, off(major, c.kind, r, k, lbo, sbo));
     return ((mx + 16 + 15) / 16) * 16;
   };
-  c.a_bytes = span(c.a_major, Mrows, c.a_lbo, c.a_sbo);
-  c.b_bytes = span(c.b_major, c.N, c.b_lbo, c.b_sbo);
+  c.a_bytes = c.swz ? Mrows * 128 : span(c.a_major, Mrows, c.a_lbo, c.a_sbo);
+  c.b_bytes = c.swz ? c.N * 128 : span(c.b_major, c.N, c.b_lbo, c.b_sbo);
   std::vector<uint8_t> a_img(c.a_bytes, 0), b_img(c.b_bytes, 0);
   std::vector<float> A(Mrows * c.K), B(c.N * c.K);
   std::vector<__half> a_rm(Mrows * c.K);
@@ -239,13 +256,13 @@ int main(int argc, char** argv) {
       float v = (r < c.M) ? (float)(rand() % 5 - 2) : 0.f;
       A[r * c.K + k] = v;
       a_rm[r * c.K + k] = __float2half(v);
-      put(a_img, off(c.a_major, c.kind, r, k, c.a_lbo, c.a_sbo), c.kind, v);
+      put(a_img, c.swz ? off_sw128(r, k) : off(c.a_major, c.kind, r, k, c.a_lbo, c.a_sbo), c.kind, v);
     }
   for (int n = 0; n < c.N; ++n)
     for (int k = 0; k < c.K; ++k) {
       float v = (float)(rand() % 5 - 2);
       B[n * c.K + k] = v;
-      put(b_img, off(c.b_major, c.kind, n, k, c.b_lbo, c.b_sbo), c.kind, v);
+      put(b_img, c.swz ? off_sw128(n, k) : off(c.b_major, c.kind, n, k, c.b_lbo, c.b_sbo), c.kind, v);
     }
   uint8_t *da, *db;
   __half* darm;
