@@ -210,6 +210,24 @@ int swem_bias_add_act(const float* a, const float* b, const float* c_shared, con
                       int32_t n_share, int64_t pixels, int32_t C, int32_t relu, float* out, void* stream);
 int swem_glu_gate(const float* y, const float* shared, const float* bias, int32_t images, int32_t n_share, int64_t pixels,
                   int32_t C, float* out, void* stream);
+/* ---- GLU feature-fusion layer (FeatureFusionLayer, modules.py:13-26; input = cat[mem_out, qv, S], :291) as one implicit-GEMM
+ * 3x3 / padding-1 convolution on the tensor cores with the gate in its epilogue (csrc/fusion_conv.cu):
+ *   out[bn, p, c] = (conv_f(x)[c] + shared[bn / n_share, p, c] + bias[c]) * sigmoid(conv_a(x)[c] + shared[.., Cout + c] + bias[Cout + c])
+ * x = feats [BN, H, W, Cin] channels-last fp32 (what swem_readout_forward writes with out_pixel_major = 1: Cin = Cv + 2 topl);
+ * shared [BN / n_share, H, W, 2 Cout] (the convolution of the object-independent input channels, or NULL), bias [2 Cout] (or
+ * NULL), out [BN, H, W, Cout].  fp32-accurate: operands split into fp16 hi + lo, three products, fp32 accumulation.
+ *   swem_fusion_weight_bytes / swem_fusion_prepare_weights : once per model.  w = [2 Cout, Cin, 3, 3] (layer_f's weight stacked on
+ *       layer_a's, torch layout, only the input channels of `feats`); scale = a power of two with max|w| * scale in [2^8, 2^14]
+ *       (keeps the fp16 lo parts normal); the same scale is passed to swem_fusion_conv_glu.
+ *   swem_fusion_workspace_bytes / swem_fusion_conv_glu : two launches (operand images of x, convolution); the workspace needs no
+ *       initialisation and holds nothing between calls.
+ * Cin must be a multiple of 32, Cout a multiple of 128; anything else is SWEM_ERR_INVALID_ARG (no fallback).                  */
+size_t swem_fusion_weight_bytes(int32_t Cin, int32_t Cout);
+int swem_fusion_prepare_weights(const float* w, int32_t Cin, int32_t Cout, float scale, void* wblob, void* stream);
+size_t swem_fusion_workspace_bytes(int32_t BN, int32_t H, int32_t W, int32_t Cin);
+int swem_fusion_conv_glu(const float* feats, const void* wblob, float scale, const float* shared, const float* bias, int32_t BN,
+                         int32_t n_share, int32_t H, int32_t W, int32_t Cin, int32_t Cout, void* workspace, size_t workspace_bytes,
+                         float* out, void* stream);
 /* CBAM of the value encoder's fuser (attentions.py:22-85; networks.py:35-52), NHWC x [images, pixels, C]:
  *   swem_cbam_channel_gate : gate[img, c] = sigmoid(mlp(avg_p x) + mlp(max_p x)), mlp = Linear(C, R) -> ReLU -> Linear(R, C)
  *                            (w1 [R, C], b1 [R], w2 [C, R], b2 [C]); stats: scratch [2, images, C]

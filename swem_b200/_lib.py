@@ -20,6 +20,7 @@ EXPORTS = (
     'swem_em_masks', 'swem_decode_tail', 'swem_set_profile_buffer',
     'swem_em_backward_workspace_bytes', 'swem_em_backward', 'swem_readout_backward_workspace_bytes', 'swem_readout_backward', 'swem_upsample_add', 'swem_bias_add_act', 'swem_glu_gate', 'swem_maxpool3x3s2', 'swem_tf32_split', 'swem_tf32_split_bf16', 'swem_stem_input', 'swem_resblock_tail_pred',
     'swem_cbam_channel_gate', 'swem_cbam_spatial_pool', 'swem_cbam_apply',
+    'swem_fusion_weight_bytes', 'swem_fusion_prepare_weights', 'swem_fusion_workspace_bytes', 'swem_fusion_conv_glu',
 )
 
 
@@ -113,6 +114,13 @@ def load() -> C.CDLL:
     lib.swem_cbam_apply.argtypes = [C.c_void_p] * 3 + [C.c_int32, C.c_int64, C.c_int32] + [C.c_void_p] * 2
     lib.swem_bias_add_act.argtypes = [C.c_void_p] * 4 + [C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
     lib.swem_glu_gate.argtypes = [C.c_void_p] * 3 + [C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]
+    lib.swem_fusion_weight_bytes.restype = C.c_size_t
+    lib.swem_fusion_weight_bytes.argtypes = [C.c_int32, C.c_int32]
+    lib.swem_fusion_prepare_weights.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_void_p, C.c_void_p]
+    lib.swem_fusion_workspace_bytes.restype = C.c_size_t
+    lib.swem_fusion_workspace_bytes.argtypes = [C.c_int32] * 4
+    lib.swem_fusion_conv_glu.argtypes = ([C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p] + [C.c_int32] * 6 +
+                                         [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p])
     if lib.swem_abi_version() != 3:
         raise RuntimeError(f'libswem_b200.so ABI version {lib.swem_abi_version()} != 3')
     _lib = lib

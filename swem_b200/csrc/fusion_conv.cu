@@ -1,0 +1,376 @@
+// GLU feature-fusion layer of SWEMCore.matching as ONE implicit-GEMM 3x3 convolution on the sm_100a tensor cores, with the
+// gate in the epilogue.  Reference: methods/SWEM/modules.py:13-26 (FeatureFusionLayer: layer_f(x) *
+// sigmoid(layer_a(x)), two 3x3 / padding-1 convolutions over the same input), :291 (x = cat[mem_out, qv, S]).
+//
+// The engine (swem_b200/engine.py) splits the layer by linearity: the `qv` third of the input is the same for every object and
+// is convolved once per frame (`shared`); this kernel convolves the per-object channels [mem_out | S] (C_in = 640 at the
+// BASELINE shapes) that the readout kernel has just written channels-last, adds the shared term and the biases and applies the
+// gate -- the 1024-channel pre-activation tensor is never materialised.
+//
+// Arithmetic: fp32-accurate on the fp16 tensor cores.  (The two cross terms accumulate in TMEM columns of their own: every
+// tcgen05.mma truncates the fp32 accumulator once, 1080 accumulations into one 5760-term sum measured 2.1e-5 of fp64, the main
+// term alone -- 360 accumulations -- a third of that; the cross sum is 2^-11 of the result and its truncation does not matter.)  x = x_hi + x_lo, w 2^s = w_hi + w_lo (fp16 each, s a power of two chosen by
+// the host so that the weights sit in the upper normal range), conv = x_hi w_hi + x_hi w_lo + x_lo w_hi with fp32 accumulation in
+// TMEM: 2^-21 per product (the free-running masks need the convolutions of this model at fp32 accuracy: TF32 or bf16 convolutions
+// fail the 99.9 % gate, profiles/r1_agreement.txt).
+//
+// Implicit GEMM without im2col and without tensor maps: activations are laid out by padded-flat position p = h' Wp + w' (one zero
+// pixel around every image, row pitch Wp a multiple of 8), so that tap (dy, dx) of output rows [p0, p0 + 128) is the row window
+// [p0 + dy Wp + dx, +128) of the same matrix.  `fusion_act_images_kernel` writes that matrix three times, shifted by dx = -1, 0, +1,
+// as 128-byte-swizzled K-major operand rows (32 channels: 16-byte chunks 0-3 = fp16 hi, 4-7 = fp16 lo), so every window starts on
+// an 8-row swizzle atom and a 16 KB tile of one (tap, 32-channel block) is ONE contiguous bulk copy; the weights are prepared once
+// per model in the same form ([tap][32-channel block][n-tile][256 rows: 128 layer_f + 128 layer_a output channels][128 B]).
+//
+// Kernel: one CTA per (128 output positions, 256 output channels), 192 threads: warp 0 streams the operands through a 4-stage
+// ring of 48 KB (cp.async.bulk + transaction mbarriers), warp 1 issues 6 tcgen05.mma M128 N256 K16 per stage (elected lane,
+// descriptors in uniform registers), warps 2-5 run the epilogue from TMEM (layer_f in columns 0-127, layer_a in 128-255 of the
+// same row, cross terms 256 columns further: the gate needs no exchange).  Bound: the operand stream from L2 (48 KB per 6 MMAs = 131 FLOP / byte against the
+// chip-wide L2 -> SM rate of ~6.3 KB / cycle, B300 micro-architecture notes), then the tensor pipe (768 cycles per stage).
+#include <cuda_fp16.h>
+#include <math.h>
+
+#include "common.cuh"
+#include "fused_common.cuh"
+#include "tc05.cuh"
+
+namespace swem {
+
+using namespace tc05;
+
+namespace fc {
+constexpr int kTM = 128;                          // output positions per CTA
+constexpr int kTN = 256;                          // output channels per CTA: 128 of layer_f + the same 128 of layer_a
+constexpr int kKB = 32;                           // input channels per stage (one 128-byte operand row: hi | lo)
+constexpr int kStages = 4;
+constexpr uint32_t kABytes = kTM * 128;           // 16 KB
+constexpr uint32_t kBBytes = kTN * 128;           // 32 KB
+constexpr uint32_t kStageBytes = kABytes + kBBytes;
+constexpr int kThreads = 192;
+struct Misc {
+  uint64_t bar_full[kStages];
+  uint64_t bar_empty[kStages];
+  uint64_t bar_acc;
+  uint32_t tmem_base;
+  int abort_flag;
+};
+constexpr uint32_t kSmemBytes = kStages * kStageBytes + sizeof(Misc) + 1024;   // (+ slack to align the ring to 1024 bytes)
+static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
+}  // namespace fc
+
+struct FusionGeom {
+  int BN, n_share, H, W, Cin, Cout;
+  int Wp;        // row pitch of the padded image, multiple of 8
+  int Pimg;      // padded positions per image, multiple of 128 (every image starts on a tile)
+  int G;         // guard rows in front of / behind the images (>= Wp + 1, multiple of 8)
+  int Rtot;      // rows of one (dx, channel block) plane = G + BN Pimg + G
+  int KBn;       // Cin / 32
+  int NT;        // Cout / 128
+};
+
+static FusionGeom fusion_geom(int BN, int n_share, int H, int W, int Cin, int Cout) {
+  FusionGeom g{};
+  g.BN = BN; g.n_share = n_share; g.H = H; g.W = W; g.Cin = Cin; g.Cout = Cout;
+  g.Wp = (W + 2 + 7) / 8 * 8;
+  g.Pimg = ((H + 2) * g.Wp + fc::kTM - 1) / fc::kTM * fc::kTM;
+  g.G = g.Wp + 8;
+  g.Rtot = g.G + BN * g.Pimg + g.G;
+  g.KBn = Cin / fc::kKB;
+  g.NT = Cout / 128;
+  return g;
+}
+
+// ---- activations -> operand rows ---------------------------------------------------------------------------------------
+// thread <-> (dx, channel block kb, row r) with r fastest: row r of plane (dx, kb) holds the 32 channels of padded-flat position
+// r - G + dx - 1 (zero outside the images and on their one-pixel border): a warp writes 4 KB of consecutive rows.
+__global__ void __launch_bounds__(256) fusion_act_images_kernel(const float* __restrict__ feats, FusionGeom g, uint8_t* __restrict__ ablob) {
+  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+  const long long per_plane = g.Rtot;
+  if (idx >= 3LL * g.KBn * per_plane) return;
+  const int r = (int)(idx % per_plane);
+  const int kb = (int)((idx / per_plane) % g.KBn);
+  const int dx = (int)(idx / (per_plane * g.KBn));
+  const int a = r - g.G + dx - 1;                          // padded-flat position over all images
+  float v[32];
+  bool valid = false;
+  if (a >= 0 && a < g.BN * g.Pimg) {
+    const int img = a / g.Pimg, q = a - img * g.Pimg;
+    const int hp = q / g.Wp, wp = q - hp * g.Wp;
+    if (hp >= 1 && hp <= g.H && wp >= 1 && wp <= g.W) {
+      valid = true;
+      const float4* src = reinterpret_cast<const float4*>(feats + (((size_t)img * g.H + (hp - 1)) * g.W + (wp - 1)) * g.Cin + kb * 32);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 t = __ldg(src + j);
+        v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
+      }
+    }
+  }
+  uint8_t* row = ablob + (((size_t)dx * g.KBn + kb) * per_plane + r) * 128;
+  const int sw = r & 7;
+  if (!valid) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(row + c * 16) = make_uint4(0u, 0u, 0u, 0u);
+    return;
+  }
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    __align__(16) __half hi[8];
+    __align__(16) __half lo[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) split_half(v[c * 8 + e], hi[e], lo[e]);
+    *reinterpret_cast<uint4*>(row + ((c ^ sw) * 16)) = *reinterpret_cast<uint4*>(hi);
+    *reinterpret_cast<uint4*>(row + (((c + 4) ^ sw) * 16)) = *reinterpret_cast<uint4*>(lo);
+  }
+}
+
+// ---- weights -> operand rows (once per model) ------------------------------------------------------------------------------
+// w: [2 Cout][Cin][3][3] (layer_f stacked on layer_a, torch layout).  thread <-> (tap, kb, nt, row j, chunk c of 8 channels)
+__global__ void __launch_bounds__(256) fusion_weight_images_kernel(const float* __restrict__ w, int Cin, int Cout, float scale,
+                                                                   uint8_t* __restrict__ wblob) {
+  const int KBn = Cin / 32, NT = Cout / 128;
+  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (idx >= 9LL * KBn * NT * 256 * 8) return;
+  const int c = (int)(idx & 7);
+  const int j = (int)((idx >> 3) & 255);
+  const int nt = (int)((idx >> 11) % NT);
+  const int kb = (int)((idx / (2048LL * NT)) % KBn);
+  const int tap = (int)(idx / (2048LL * NT * KBn));
+  const int o = (j < 128) ? nt * 128 + j : Cout + nt * 128 + (j - 128);
+  const int ci0 = kb * 32 + (c & 3) * 8;
+  __align__(16) __half out[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const float v = w[((size_t)o * Cin + ci0 + e) * 9 + tap] * scale;
+    __half hi, lo;
+    split_half(v, hi, lo);
+    out[e] = (c < 4) ? hi : lo;
+  }
+  uint8_t* row = wblob + ((((size_t)tap * KBn + kb) * NT + nt) * 256 + j) * 128;
+  *reinterpret_cast<uint4*>(row + ((c ^ (j & 7)) * 16)) = *reinterpret_cast<uint4*>(out);
+}
+
+// ---- main kernel ---------------------------------------------------------------------------------------------------------------
+struct FusionConvParams {
+  const uint8_t* ablob;
+  const uint8_t* wblob;
+  const float* shared;     // [BN / n_share][H][W][2 Cout] or NULL
+  const float* bias;       // [2 Cout] or NULL
+  float* out;              // [BN][H][W][Cout]
+  FusionGeom g;
+  float inv_scale;
+  int* status;             // optional: set to 1 when a wait timed out (the kernel then traps)
+};
+
+__global__ void __launch_bounds__(fc::kThreads, 1) fusion_conv_glu_kernel(const FusionConvParams p) {
+  using namespace fc;
+  extern __shared__ uint8_t smem_raw[];
+  // (the swizzle pattern is a function of the shared-memory ADDRESS: the ring must start on a 1024-byte boundary of the window)
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* const smem = smem_raw + (sbase - smem_u32(smem_raw));
+  Misc& ms = *reinterpret_cast<Misc*>(smem + kStages * kStageBytes);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const FusionGeom& g = p.g;
+  const int nt = blockIdx.x % g.NT;
+  const int mt = blockIdx.x / g.NT;
+  const int tiles_per_img = g.Pimg / kTM;
+  const int img = mt / tiles_per_img;
+  const int p0 = (mt - img * tiles_per_img) * kTM;          // first padded-flat position of the tile inside its image
+  const int n_steps = 9 * g.KBn;
+
+  if (warp == 0) tmem_alloc(&ms.tmem_base, 512);
+  if (tid == 32) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&ms.bar_full[s], 1);
+      mbar_init(&ms.bar_empty[s], 1);
+    }
+    mbar_init(&ms.bar_acc, 1);
+    ms.abort_flag = 0;
+    fence_mbar_init();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = ms.tmem_base;
+
+  if (warp == 0) {
+    // ---- producer: operand tiles of step i = (tap, channel block) -> ring stage i % 4 ------------------------------------------
+    const size_t row0 = (size_t)img * g.Pimg + p0 + g.G;
+    bool ok = true;
+#pragma unroll 1
+    for (int i = 0; i < n_steps && ok; ++i) {
+      const int s = i % kStages;
+      if (i >= kStages) ok = mbar_wait(&ms.bar_empty[s], ((i / kStages) - 1) & 1);
+      const int tap = i / g.KBn, kb = i - tap * g.KBn;
+      const int dy = tap / 3 - 1, dxi = tap - (tap / 3) * 3;
+      const uint8_t* asrc = p.ablob + (((size_t)dxi * g.KBn + kb) * g.Rtot + (row0 + (long long)dy * g.Wp)) * 128;
+      const uint8_t* bsrc = p.wblob + (((size_t)tap * g.KBn + kb) * g.NT + nt) * kBBytes;
+      if (ok && elect_one()) {
+        mbar_expect_tx(&ms.bar_full[s], kStageBytes);
+        bulk_g2s(smem + s * kStageBytes, asrc, kABytes, &ms.bar_full[s]);
+        bulk_g2s(smem + s * kStageBytes + kABytes, bsrc, kBBytes, &ms.bar_full[s]);
+      }
+      __syncwarp();
+    }
+    if (!ok) ms.abort_flag = 1;
+  } else if (warp == 1) {
+    // ---- MMA issue: per stage and 16-channel step x_hi w_hi + x_hi w_lo + x_lo w_hi ------------------------------------------------
+    const uint32_t idesc = make_idesc(kTM, kTN, kFmtF16, kFmtF16, kMajorK, kMajorK);
+    bool ok = true;
+#pragma unroll 1
+    for (int i = 0; i < n_steps && ok; ++i) {
+      const int s = i % kStages;
+      ok = mbar_wait(&ms.bar_full[s], (i / kStages) & 1);
+      tc_fence_after_sync();
+      const uint32_t a0 = sbase + s * kStageBytes, b0 = a0 + kABytes;
+      if (ok && elect_one()) {
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const uint64_t ah = make_sdesc_sw128(a0 + 32 * k, 1024), al = make_sdesc_sw128(a0 + 64 + 32 * k, 1024);
+          const uint64_t bh = make_sdesc_sw128(b0 + 32 * k, 1024), bl = make_sdesc_sw128(b0 + 64 + 32 * k, 1024);
+          mma_f16_ss(tmem, ah, bh, idesc, (i | k) ? 1u : 0u);               // main term
+          mma_f16_ss(tmem + kTN, ah, bl, idesc, (i | k) ? 1u : 0u);         // cross terms: an accumulator of their own
+          mma_f16_ss(tmem + kTN, al, bh, idesc, 1u);
+        }
+        mma_commit(&ms.bar_empty[s]);
+        if (i == n_steps - 1) mma_commit(&ms.bar_acc);
+      }
+      __syncwarp();
+    }
+    if (!ok) ms.abort_flag = 1;
+  } else {
+    // ---- epilogue: thread <-> output position (TMEM lane); layer_f in columns [0, 128), layer_a in [128, 256) -------------------------
+    const int q = warp & 3;                                 // the TMEM lane quadrant this warp may read
+    const int row = q * 32 + lane;
+    const int pp = p0 + row;
+    const int hp = pp / g.Wp, wp = pp - hp * g.Wp;
+    const bool valid = hp >= 1 && hp <= g.H && wp >= 1 && wp <= g.W;
+    const size_t pix = valid ? ((size_t)(hp - 1) * g.W + (wp - 1)) : 0;
+    float* optr = p.out + (((size_t)img * g.H * g.W + pix) * g.Cout + nt * 128);
+    const float* sptr = p.shared ? p.shared + (((size_t)(img / g.n_share) * g.H * g.W + pix) * 2 * g.Cout + nt * 128) : nullptr;
+    const float* bptr = p.bias ? p.bias + nt * 128 : nullptr;
+    const bool ok = warp_wait(&ms.bar_acc, 0);
+    tc_fence_after_sync();
+    if (!ok) {
+      ms.abort_flag = 1;
+    } else {
+#pragma unroll 1
+      for (int c0 = 0; c0 < 128; c0 += 16) {
+        uint32_t rf[16], ra[16], xf[16], xa[16];
+        tmem_ld16(tmem_addr(tmem, q * 32, c0), rf);
+        tmem_ld16(tmem_addr(tmem, q * 32, 128 + c0), ra);
+        tmem_ld16(tmem_addr(tmem, q * 32, kTN + c0), xf);
+        tmem_ld16(tmem_addr(tmem, q * 32, kTN + 128 + c0), xa);
+        tmem_ld_wait();
+        if (valid) {
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            float f[4], a[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              f[e] = (__uint_as_float(rf[j4 * 4 + e]) + __uint_as_float(xf[j4 * 4 + e])) * p.inv_scale;
+              a[e] = (__uint_as_float(ra[j4 * 4 + e]) + __uint_as_float(xa[j4 * 4 + e])) * p.inv_scale;
+            }
+            if (sptr != nullptr) {
+              const float4 sf = __ldg(reinterpret_cast<const float4*>(sptr + c0) + j4);
+              const float4 sa = __ldg(reinterpret_cast<const float4*>(sptr + g.Cout + c0) + j4);
+              f[0] += sf.x; f[1] += sf.y; f[2] += sf.z; f[3] += sf.w;
+              a[0] += sa.x; a[1] += sa.y; a[2] += sa.z; a[3] += sa.w;
+            }
+            if (bptr != nullptr) {
+              const float4 bf = __ldg(reinterpret_cast<const float4*>(bptr + c0) + j4);
+              const float4 ba = __ldg(reinterpret_cast<const float4*>(bptr + g.Cout + c0) + j4);
+              f[0] += bf.x; f[1] += bf.y; f[2] += bf.z; f[3] += bf.w;
+              a[0] += ba.x; a[1] += ba.y; a[2] += ba.z; a[3] += ba.w;
+            }
+            reinterpret_cast<float4*>(optr + c0)[j4] = make_float4(f[0] / (1.f + expf(-a[0])), f[1] / (1.f + expf(-a[1])),
+                                                                   f[2] / (1.f + expf(-a[2])), f[3] / (1.f + expf(-a[3])));
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+  if (ms.abort_flag) {
+    if (tid == 0 && p.status != nullptr) *p.status = 1;
+    __trap();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------------
+static bool fusion_shape_ok(int BN, int n_share, int H, int W, int Cin, int Cout) {
+  return BN > 0 && n_share > 0 && BN % n_share == 0 && H > 0 && W > 0 && H <= 4096 && W <= 4096 && Cin > 0 && Cin % 32 == 0 &&
+         Cout > 0 && Cout % 128 == 0;
+}
+
+extern "C" {
+
+size_t swem_fusion_weight_bytes(int32_t Cin, int32_t Cout) {
+  if (Cin <= 0 || Cin % 32 || Cout <= 0 || Cout % 128) return 0;
+  return (size_t)9 * (Cin / 32) * (Cout / 128) * fc::kBBytes;
+}
+
+int swem_fusion_prepare_weights(const float* w, int32_t Cin, int32_t Cout, float scale, void* wblob, void* stream) {
+  reset_launch_count();
+  SWEM_CHECK_ARG(w && wblob, "NULL pointer");
+  SWEM_CHECK_ARG(swem_fusion_weight_bytes(Cin, Cout) != 0, "bad sizes Cin=%d (multiple of 32) Cout=%d (multiple of 128)", Cin, Cout);
+  SWEM_CHECK_ARG(scale > 0.f && isfinite(scale), "scale=%g", scale);
+  SWEM_CHECK_ARG((reinterpret_cast<uintptr_t>(wblob) & 127) == 0, "wblob must be 128-byte aligned");
+  const long long n = 9LL * (Cin / 32) * (Cout / 128) * 256 * 8;
+  fusion_weight_images_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(w, Cin, Cout, scale,
+                                                                                                        static_cast<uint8_t*>(wblob));
+  SWEM_LAUNCH_CHECK();
+  return SWEM_OK;
+}
+
+size_t swem_fusion_workspace_bytes(int32_t BN, int32_t H, int32_t W, int32_t Cin) {
+  if (!fusion_shape_ok(BN, 1, H, W, Cin, 128)) return 0;
+  const FusionGeom g = fusion_geom(BN, 1, H, W, Cin, 128);
+  return (size_t)3 * g.KBn * g.Rtot * 128 + 256;
+}
+
+int swem_fusion_conv_glu(const float* feats, const void* wblob, float scale, const float* shared, const float* bias, int32_t BN,
+                         int32_t n_share, int32_t H, int32_t W, int32_t Cin, int32_t Cout, void* workspace, size_t workspace_bytes,
+                         float* out, void* stream) {
+  reset_launch_count();
+  SWEM_CHECK_ARG(feats && wblob && workspace && out, "NULL pointer");
+  SWEM_CHECK_ARG(fusion_shape_ok(BN, n_share, H, W, Cin, Cout),
+                 "unsupported shape BN=%d n_share=%d H=%d W=%d Cin=%d (multiple of 32) Cout=%d (multiple of 128)", BN, n_share, H, W, Cin, Cout);
+  SWEM_CHECK_ARG(scale > 0.f && isfinite(scale), "scale=%g", scale);
+  SWEM_CHECK_ARG(workspace_bytes >= swem_fusion_workspace_bytes(BN, H, W, Cin), "workspace too small: %zu < %zu", workspace_bytes,
+                 swem_fusion_workspace_bytes(BN, H, W, Cin));
+  SWEM_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 127) == 0 && (reinterpret_cast<uintptr_t>(wblob) & 127) == 0 &&
+                     (reinterpret_cast<uintptr_t>(feats) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
+                     (reinterpret_cast<uintptr_t>(shared) & 15) == 0 && (reinterpret_cast<uintptr_t>(bias) & 15) == 0,
+                 "misaligned pointer (workspace / wblob: 128 bytes, tensors: 16 bytes)");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const FusionGeom g = fusion_geom(BN, n_share, H, W, Cin, Cout);
+  SWEM_CHECK_ARG((long long)BN * (g.Pimg / fc::kTM) * g.NT < (1LL << 31), "grid too large");
+  {
+    static PerDevice once;
+    const int dev = current_device();
+    std::lock_guard<std::mutex> lock(once.mu);
+    if (!once.done[dev]) {
+      SWEM_CUDA(cudaFuncSetAttribute(fusion_conv_glu_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fc::kSmemBytes));
+      once.done[dev] = true;
+    }
+  }
+  uint8_t* ablob = static_cast<uint8_t*>(workspace);
+  const long long n = 3LL * g.KBn * g.Rtot;
+  fusion_act_images_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(feats, g, ablob);
+  SWEM_LAUNCH_CHECK();
+  FusionConvParams p{};
+  p.ablob = ablob; p.wblob = static_cast<const uint8_t*>(wblob); p.shared = shared; p.bias = bias; p.out = out; p.g = g;
+  p.inv_scale = 1.f / scale;
+  p.status = nullptr;
+  fusion_conv_glu_kernel<<<(unsigned)(BN * (g.Pimg / fc::kTM) * g.NT), fc::kThreads, fc::kSmemBytes, st>>>(p);
+  SWEM_LAUNCH_CHECK();
+  return SWEM_OK;
+}
+
+}  // extern "C"
+
+}  // namespace swem

@@ -38,6 +38,9 @@ from __future__ import annotations
 import ctypes as C
 from typing import List, Optional, Tuple
 
+import math
+import os
+
 import torch
 import torch.nn.functional as F
 
@@ -57,8 +60,15 @@ def _fold_bn(conv, bn) -> Tuple[torch.Tensor, torch.Tensor]:
 
 class FrameEngine:
     def __init__(self, model, channels_last: bool = True, fused_conv: bool = True, stage_kernels: bool = True,
-                 split_tf32: bool = False, cross_bf16: bool = False):
+                 split_tf32: bool = False, cross_bf16: bool = False, fusion_kernel: Optional[bool] = None):
         self.model = model
+        # GLU fusion layer on libswem_b200's own tcgen05 implicit-GEMM kernel (swem_fusion_conv_glu: fp32-accurate, gate in the
+        # epilogue) instead of cuDNN main + cross-term convolutions + swem_glu_gate.  Default: whenever fp32 accuracy is asked for
+        # (split_tf32); a single cuDNN TF32 convolution is cheaper than three fp16 products when it is not.  SWEM_FUSION_KERNEL=0/1 overrides.
+        env = os.environ.get('SWEM_FUSION_KERNEL')
+        self.fusion_kernel = (split_tf32 if fusion_kernel is None else fusion_kernel) if env is None else env == '1'
+        self.g_fused = None
+        self._fusion_ws = None
         self.channels_last = channels_last
         self.fused_conv = fused_conv
         self.stage_kernels = stage_kernels and channels_last     # the decoder glue kernels of libswem_b200 are NHWC
@@ -190,6 +200,21 @@ class FrameEngine:
         self.g_shared = self._cp(w[:, cv:2 * cv], None, 1, 1)                            # qv channels, once per frame
         self.g_bias = torch.cat([fl.layer_f.bias, fl.layer_a.bias], 0).detach().float().contiguous()
         self.g_out = fl.layer_f.out_channels
+        self.g_fused = None
+        cin = cv + 2 * tl
+        if (self.fusion_kernel and self.stage_kernels and w.is_cuda and cin % 32 == 0 and self.g_out % 128 == 0
+                and _lib.load().swem_fusion_weight_bytes(cin, self.g_out)):
+            # operand images of the per-object input channels' weights, once per refresh (swem_fusion_prepare_weights)
+            lib = _lib.load()
+            w_obj = torch.cat([w[:, :cv], w[:, 2 * cv:]], 1).detach().float().contiguous()       # [2 Cout, Cin, 3, 3], torch layout
+            amax = float(w_obj.abs().max())
+            scale = 2.0 ** (11 - math.ceil(math.log2(amax))) if amax > 0 else 1.0               # max |w| * scale in (2^10, 2^11]
+            wblob = torch.empty(lib.swem_fusion_weight_bytes(cin, self.g_out), dtype=torch.uint8, device=w.device)
+            with torch.cuda.device(w.device):
+                rc = lib.swem_fusion_prepare_weights(w_obj.data_ptr(), cin, self.g_out, scale, wblob.data_ptr(),
+                                                     torch.cuda.current_stream(w.device).cuda_stream)
+            _lib.check(rc, 'swem_fusion_prepare_weights')
+            self.g_fused = (wblob, scale, cin)
 
         if dec.compress.downsample is not None:
             raise RuntimeError('FrameEngine expects Decoder.compress to keep its width (reference: 512 -> 512)')
@@ -407,7 +432,26 @@ class FrameEngine:
                             memory_format=torch.channels_last if self.channels_last else torch.contiguous_format)
         core.readout_into(qk16, feats, 0, cv)                      # [mem_out | S], written NHWC for the channels-last conv
         g = shared['g'] if shared is not None else self._conv(qv16, self.g_shared)   # (B, 1024, H, W): [layer_f | layer_a] of the qv third
+        if (self.g_fused is not None and feats.is_cuda and feats.shape[1] == self.g_fused[2]
+                and feats.is_contiguous(memory_format=torch.channels_last)):
+            return self._fusion_conv_glu(feats, g, bsz * n, n, h, w), n
         return self._glu(self._conv(feats, self.g_obj), g, self.g_bias, n), n
+
+    def _fusion_conv_glu(self, feats, g, bn, n, h, w):
+        """FeatureFusionLayer on the per-object channels + shared term + biases + gate in two launches (swem_fusion_conv_glu)."""
+        lib = _lib.load()
+        wblob, scale, cin = self.g_fused
+        g = self._cl(g)
+        need = lib.swem_fusion_workspace_bytes(bn, h, w, cin)
+        if self._fusion_ws is None or self._fusion_ws.numel() < need or self._fusion_ws.device != feats.device:
+            self._fusion_ws = torch.empty(need, dtype=torch.uint8, device=feats.device)
+        out = torch.empty((bn, self.g_out, h, w), device=feats.device, dtype=torch.float32, memory_format=torch.channels_last)
+        with torch.cuda.device(feats.device):
+            rc = lib.swem_fusion_conv_glu(feats.data_ptr(), wblob.data_ptr(), scale, g.data_ptr(), self.g_bias.data_ptr(), bn, n, h, w,
+                                          cin, self.g_out, self._fusion_ws.data_ptr(), self._fusion_ws.numel(), out.data_ptr(),
+                                          torch.cuda.current_stream(feats.device).cuda_stream)
+        _lib.check(rc, 'swem_fusion_conv_glu')
+        return out
 
     @staticmethod
     def _nobias(p: ConvP) -> ConvP:

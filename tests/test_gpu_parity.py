@@ -1015,3 +1015,81 @@ def test_bench_configuration_passes_the_mask_gate():
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark = old
     assert per_frame.numel() == 7
     check('min_agree', 1.0 - per_frame.min().item(), 1.0 - bench.GATE)
+
+
+def _fusion_call(feats, w, shared, bias, n_share):
+    """swem_fusion_prepare_weights + swem_fusion_conv_glu through the C ABI.  feats [BN, H, W, Cin], shared [BN / n_share, H, W,
+    2 Cout], all channels-last fp32 on the device; returns out [BN, H, W, Cout]."""
+    import math
+    from swem_b200 import _lib
+    lib = _lib.load()
+    BN, H, W, Cin = feats.shape
+    Cout = w.shape[0] // 2
+    scale = 2.0 ** (11 - math.ceil(math.log2(float(w.abs().max()))))
+    wblob = torch.empty(lib.swem_fusion_weight_bytes(Cin, Cout), dtype=torch.uint8, device=feats.device)
+    st = torch.cuda.current_stream().cuda_stream
+    _lib.check(lib.swem_fusion_prepare_weights(w.data_ptr(), Cin, Cout, scale, wblob.data_ptr(), st), 'prepare')
+    ws = torch.empty(lib.swem_fusion_workspace_bytes(BN, H, W, Cin), dtype=torch.uint8, device=feats.device)
+    ws.fill_(0x7b)                                           # the workspace needs no initialisation (NaN-ish garbage must not leak)
+    out = torch.full((BN, H, W, Cout), float('nan'), device=feats.device)
+    _lib.check(lib.swem_fusion_conv_glu(feats.data_ptr(), wblob.data_ptr(), scale, None if shared is None else shared.data_ptr(),
+                                        None if bias is None else bias.data_ptr(), BN, n_share, H, W, Cin, Cout, ws.data_ptr(), ws.numel(),
+                                        out.data_ptr(), st), 'fusion_conv_glu')
+    return out
+
+
+@pytest.mark.parametrize('shape', [(5, 5, 30, 54, 640, 512), (3, 3, 30, 53, 640, 512), (2, 1, 7, 9, 64, 128), (1, 1, 45, 80, 96, 256)],
+                         ids=lambda s: 'x'.join(map(str, s)))
+def test_fusion_conv_glu_kernel_vs_fp64(shape):
+    """FeatureFusionLayer (modules.py:13-26) on the tcgen05 implicit-GEMM kernel against the same layer in fp64: fp32-accurate
+    (fp16 hi / lo operand splits, three products), every border pixel, an image width that needs pitch padding (53 -> 56), a
+    shared term per batch element and one per image, small and non-BASELINE channel counts."""
+    BN, n_share, H, W, Cin, Cout = shape
+    g = torch.Generator().manual_seed(7)
+    feats = (torch.randn(BN, H, W, Cin, generator=g) * 1.5).to(DEV)
+    feats[..., -32:] = torch.rand(BN, H, W, 32, generator=g).to(DEV)           # S-like channels in [0, 1]
+    w = (torch.randn(2 * Cout, Cin, 3, 3, generator=g) * (1.0 / (9 * Cin)) ** 0.5).to(DEV)
+    shared = torch.randn(BN // n_share, H, W, 2 * Cout, generator=g).to(DEV)
+    bias = (0.1 * torch.randn(2 * Cout, generator=g)).to(DEV)
+    out = _fusion_call(feats, w, shared, bias, n_share)
+    torch.cuda.synchronize()
+    x64 = feats.double().permute(0, 3, 1, 2)
+    y = torch.nn.functional.conv2d(x64, w.double(), None, padding=1)
+    y = y + shared.double().permute(0, 3, 1, 2).repeat_interleave(n_share, dim=0) + bias.double().view(1, -1, 1, 1)
+    want = (y[:, :Cout] * torch.sigmoid(y[:, Cout:])).permute(0, 2, 3, 1)
+    assert torch.isfinite(out).all()
+    check('glu_out', maxrel(out, want), 5e-5)
+    # pre-activation accuracy (the gate hides errors of the saturated channels): no shared term / bias, weights of layer_a = 0
+    w0 = w.clone()
+    w0[Cout:] = 0
+    out0 = _fusion_call(feats, w0, None, None, n_share)
+    want0 = torch.nn.functional.conv2d(x64, w0.double()[:Cout], None, padding=1).permute(0, 2, 3, 1) * 0.5
+    check('conv_f', maxrel(out0, want0), 2e-5)
+
+
+def test_frame_engine_fusion_kernel_matches_cudnn_path():
+    """FrameEngine.match with the fusion layer on swem_fusion_conv_glu against the same engine on cuDNN (fp32 convolutions) +
+    swem_glu_gate: same context features to fp32 rounding."""
+    from swem_b200 import SWEM, make_config
+    from swem_b200.engine import FrameEngine
+    from swem_b200.synthetic import clustered_em_inputs, em_inputs
+    torch.manual_seed(0)
+    model = SWEM(make_config(keydim=64, n_bases=128, n_iters=2, topl=64, backbone='resnet18')).eval().to(DEV)
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            B, N, Ck, Cv, H, W = 1, 3, 64, 512, 30, 54
+            for call in range(2):
+                x, v, masks = clustered_em_inputs(B, N, Ck, Cv, H, W, seed=70 + call)
+                model.swem_core.memorize(x.to(DEV), v.to(DEV), masks.to(DEV))
+            q, qv, _ = em_inputs(B, 1, Ck, Cv, H, W, seed=72)
+            q, qv = q.to(DEV), qv[:, 0].to(DEV).contiguous(memory_format=torch.channels_last)
+            eng_k = FrameEngine(model, fusion_kernel=True)
+            eng_c = FrameEngine(model, fusion_kernel=False)
+            ck, n1 = eng_k.match(q, qv)
+            cc, n2 = eng_c.match(q, qv)
+            assert eng_k.g_fused is not None and eng_c.g_fused is None and n1 == n2 == N
+            check('context', maxrel(ck, cc), 2e-5)
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
