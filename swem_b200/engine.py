@@ -68,7 +68,6 @@ class FrameEngine:
         env = os.environ.get('SWEM_FUSION_KERNEL')
         self.fusion_kernel = (split_tf32 if fusion_kernel is None else fusion_kernel) if env is None else env == '1'
         self.g_fused = None
-        self._fusion_ws = None
         self.channels_last = channels_last
         self.fused_conv = fused_conv
         self.stage_kernels = stage_kernels and channels_last     # the decoder glue kernels of libswem_b200 are NHWC
@@ -443,12 +442,11 @@ class FrameEngine:
         wblob, scale, cin = self.g_fused
         g = self._cl(g)
         need = lib.swem_fusion_workspace_bytes(bn, h, w, cin)
-        if self._fusion_ws is None or self._fusion_ws.numel() < need or self._fusion_ws.device != feats.device:
-            self._fusion_ws = torch.empty(need, dtype=torch.uint8, device=feats.device)
+        ws = self.model.swem_core._workspace.get(feats.device, need, 'fusion')   # (the core's scratch: pinned while a graph references it)
         out = torch.empty((bn, self.g_out, h, w), device=feats.device, dtype=torch.float32, memory_format=torch.channels_last)
         with torch.cuda.device(feats.device):
             rc = lib.swem_fusion_conv_glu(feats.data_ptr(), wblob.data_ptr(), scale, g.data_ptr(), self.g_bias.data_ptr(), bn, n, h, w,
-                                          cin, self.g_out, self._fusion_ws.data_ptr(), self._fusion_ws.numel(), out.data_ptr(),
+                                          cin, self.g_out, ws.data_ptr(), ws.numel(), out.data_ptr(),
                                           torch.cuda.current_stream(feats.device).cuda_stream)
         _lib.check(rc, 'swem_fusion_conv_glu')
         return out
