@@ -218,7 +218,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(emr::kThreads, 1) em
     }
   }
 
+  EMR_STAMP(35);                                        // set-up loads issued
   if (warp == 0) tmem_alloc(&ms.tmem_base, 512);
+  EMR_STAMP(36);                                        // TMEM allocated
   if (tid == 0) {
     mbar_init(&ms.bar_mma, 1);
     mbar_init(&ms.bar_nu[0], 1);
@@ -246,6 +248,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(emr::kThreads, 1) em
     for (int i = tid; i < (int)(kZeroBytes / 16); i += kThreads) reinterpret_cast<uint4*>(smem + kOffZ)[i] = make_uint4(0u, 0u, 0u, 0u);
     fence_proxy_async_smem();
     __syncthreads();
+    EMR_STAMP(37);                                      // zero buffer ready (first CTA-wide barrier)
     if (tid == 0) {
       auto zero_range = [&](float* dst, uint32_t bytes) {
         for (uint32_t o = 0; o < bytes; o += kZeroBytes) {
@@ -261,6 +264,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(emr::kThreads, 1) em
           zero_range(p.acc_k + ((size_t)((u * I + it) * 2 + sd)) * ((kCk + 1) * kL) + (size_t)r0 * kL, (uint32_t)(r1 - r0) * kL * 4);
       if (d1 > d0) zero_range(p.acc_nu + ((size_t)gs * kCv + d0) * kL, (uint32_t)(d1 - d0) * kL * 4);
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      EMR_STAMP(30);                                    // clearing issued
     }
   }
 

@@ -80,44 +80,41 @@ static FusionGeom fusion_geom(int BN, int n_share, int H, int W, int Cin, int Co
 }
 
 // ---- activations -> operand rows ---------------------------------------------------------------------------------------
-// thread <-> (dx, channel block kb, row r) with r fastest: row r of plane (dx, kb) holds the 32 channels of padded-flat position
-// r - G + dx - 1 (zero outside the images and on their one-pixel border): a warp writes 4 KB of consecutive rows.
+// thread <-> (channel block kb, padded-flat source position a' = a + G, 8-channel chunk c): 4 threads read the 128 bytes of a
+// pixel's channel block once (zero outside the images and on their one-pixel border) and write its fp16 hi and lo chunks into
+// the three column-shifted planes -- row r = a' + 1 - dx of plane dx holds position r - G + dx - 1.  A warp reads 8 consecutive
+// pixels and writes 8 complete 128-byte rows per plane.  (The first version, one thread per destination row, ran at 2 TB/s with
+// half-used sectors on both sides: 34 us; profiles/r2z_fusion_act_images_kernel_ncu_full.txt.)
 __global__ void __launch_bounds__(256) fusion_act_images_kernel(const float* __restrict__ feats, FusionGeom g, uint8_t* __restrict__ ablob) {
   const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
   const long long per_plane = g.Rtot;
-  if (idx >= 3LL * g.KBn * per_plane) return;
-  const int r = (int)(idx % per_plane);
-  const int kb = (int)((idx / per_plane) % g.KBn);
-  const int dx = (int)(idx / (per_plane * g.KBn));
-  const int a = r - g.G + dx - 1;                          // padded-flat position over all images
-  float v[32];
-  bool valid = false;
+  if (idx >= 4LL * g.KBn * per_plane) return;
+  const int c = (int)(idx & 3);
+  const int ap = (int)((idx >> 2) % per_plane);
+  const int kb = (int)((idx >> 2) / per_plane);
+  const int a = ap - g.G;                                  // padded-flat position over all images
+  float v[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) v[e] = 0.f;
   if (a >= 0 && a < g.BN * g.Pimg) {
     const int img = a / g.Pimg, q = a - img * g.Pimg;
     const int hp = q / g.Wp, wp = q - hp * g.Wp;
     if (hp >= 1 && hp <= g.H && wp >= 1 && wp <= g.W) {
-      valid = true;
-      const float4* src = reinterpret_cast<const float4*>(feats + (((size_t)img * g.H + (hp - 1)) * g.W + (wp - 1)) * g.Cin + kb * 32);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float4 t = __ldg(src + j);
-        v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
-      }
+      const float4* src = reinterpret_cast<const float4*>(feats + (((size_t)img * g.H + (hp - 1)) * g.W + (wp - 1)) * g.Cin + kb * 32 + c * 8);
+      const float4 t0 = __ldg(src), t1 = __ldg(src + 1);
+      v[0] = t0.x; v[1] = t0.y; v[2] = t0.z; v[3] = t0.w; v[4] = t1.x; v[5] = t1.y; v[6] = t1.z; v[7] = t1.w;
     }
   }
-  uint8_t* row = ablob + (((size_t)dx * g.KBn + kb) * per_plane + r) * 128;
-  const int sw = r & 7;
-  if (!valid) {
+  __align__(16) __half hi[8];
+  __align__(16) __half lo[8];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(row + c * 16) = make_uint4(0u, 0u, 0u, 0u);
-    return;
-  }
+  for (int e = 0; e < 8; ++e) split_half(v[e], hi[e], lo[e]);
 #pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    __align__(16) __half hi[8];
-    __align__(16) __half lo[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) split_half(v[c * 8 + e], hi[e], lo[e]);
+  for (int dx = 0; dx < 3; ++dx) {
+    const int r = ap + 1 - dx;
+    if (r < 0 || r >= g.Rtot) continue;                    // (rows 0 / Rtot - 1 of the outer planes: never read by a window)
+    uint8_t* row = ablob + (((size_t)dx * g.KBn + kb) * per_plane + r) * 128;
+    const int sw = r & 7;
     *reinterpret_cast<uint4*>(row + ((c ^ sw) * 16)) = *reinterpret_cast<uint4*>(hi);
     *reinterpret_cast<uint4*>(row + (((c + 4) ^ sw) * 16)) = *reinterpret_cast<uint4*>(lo);
   }
@@ -359,7 +356,7 @@ int swem_fusion_conv_glu(const float* feats, const void* wblob, float scale, con
     }
   }
   uint8_t* ablob = static_cast<uint8_t*>(workspace);
-  const long long n = 3LL * g.KBn * g.Rtot;
+  const long long n = 4LL * g.KBn * g.Rtot;
   fusion_act_images_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(feats, g, ablob);
   SWEM_LAUNCH_CHECK();
   FusionConvParams p{};

@@ -27,7 +27,7 @@ def main(N=5, H=30, W=54, I=4, reps=50):
         if n < 0:                         # labelled stamps of em_res_kernel: (ns << 8) | label
             LABELS = {0: 'start', 1: 'setup', 2: 'logits GEMM', 3: 'epilogue', 4: 'M GEMM', 5: 'reduce-add issued', 6: 'fence + arrive',
                       7: 'wait tiles', 8: 'finalize', 9: 'nu GEMM own side', 10: 'nu GEMM peer side', 11: 'nu drain', 12: 'wait nu',
-                      13: 'nu slice', 20: '  staged + bulk issued', 21: '  bulk reduce complete', 22: '  arrived', 23: '  totals loaded', 24: '  CTA released', 30: '  clearing issued', 31: '  prior khat staged', 32: '  X staged', 33: '  V round 0 stored', 34: '  clearing complete', 25: '  W statistics sent', 26: '  W statistics received'}
+                      13: 'nu slice', 20: '  staged + bulk issued', 21: '  bulk reduce complete', 22: '  arrived', 23: '  totals loaded', 24: '  CTA released', 30: '  clearing issued', 35: '  set-up loads issued', 36: '  TMEM allocated', 37: '  zero buffer ready', 31: '  prior khat staged', 32: '  X staged', 33: '  V round 0 stored', 34: '  clearing complete', 25: '  W statistics sent', 26: '  W statistics received'}
             n = -n
             raw = st[1:1 + n]
             t = [r >> 8 for r in raw]
