@@ -465,7 +465,9 @@ def run_b200(args, rank, world, local_rank):
     conv_note = ('FrameEngine(split_tf32=True, cross_bf16=' + os.environ.get('SWEM_CROSS_BF16', '1') + '): x = hi + lo, w = hi + lo on the '
                  'TF32 grid, conv(x, w) = cuDNN TF32 conv(xh, wh) + cross terms conv([x|xl], [wl;wh]) in bf16 -- fp32-accurate '
                  '(2e-6 .. 1e-5 of fp64 per conv, like cuDNN fp32), on the tensor cores'
-                 + (', autotuned (cudnn.benchmark)' if bn.cudnn_autotune else ', heuristic algos'))
+                 + (', autotuned (cudnn.benchmark)' if bn.cudnn_autotune else ', heuristic algos')
+                 + ('; the GLU fusion layer (per-object channels) on swem_fusion_conv_glu: tcgen05 implicit GEMM, fp16 hi/lo x 3 products, '
+                    'gate in the epilogue' if os.environ.get('SWEM_FUSION_KERNEL', '1') == '1' else ''))
 
     if world > 1:
         # ---- BASELINE configs[2]: the sharded YouTube-VOS-shaped batch is the multi-GPU line --------------------------

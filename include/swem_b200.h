@@ -144,6 +144,13 @@ typedef struct SwemReadArgs {
                                 never changes its 'first' bank while a sequence runs (modules.py:44-60), so a caller that keeps a
                                 workspace per sequence sets bit 0 from the second readout on.  0 = convert every bank (always
                                 safe); ignored by the generic family.                                                  */
+  /* Kernelised memory (the reference's `gen_kernels` branch of get_affinity, modules.py:210-230,252-256; off by default there and
+   * here, inference only): mkm_kernels = n_kernel > 0 weights the attention of basis j at pixel p by
+   * exp(-min_k d^2(p, p_jk) / (2 sigma^2 tau)), p_jk the n_kernel pixels that basis j matches best, and normalises with + 1e-8; S is
+   * unchanged.  mkm_width = W of the H x W pixel grid (HW = H W).  SWEM_PATH_GENERIC only (anything else: SWEM_ERR_UNSUPPORTED).  */
+  int32_t mkm_kernels;       /* 0 (off) .. 16                                                      */
+  float   mkm_sigma;
+  int32_t mkm_width;
 } SwemReadArgs;
 
 size_t swem_readout_workspace_bytes(const SwemDims* dims, int32_t path);

@@ -189,11 +189,25 @@ def perm_inv_feat(e: torch.Tensor, topl: int) -> torch.Tensor:
     return torch.cat([f, 1 - f], dim=1)
 
 
+def kernel_weights(aff: torch.Tensor, H: int, W: int, n_kernel: int, sigma: float, tau: float) -> torch.Tensor:
+    """The reference's kernelised-memory weights (`gen_kernels`, :210-230; inference only, off by default): every basis
+    puts a Gaussian of width sigma on the n_kernel pixels it matches best, a pixel keeps the largest of them:
+    aff (B,N,2,Lt,HW) raw affinities -> exp(-min_k d^2(p, p_k) / (2 sigma^2) / tau) of the same shape."""
+    idx = torch.topk(aff, k=n_kernel, dim=-1)[1]                             # B,N,2,Lt,k  pixel indices
+    xk, yk = (idx % W).unsqueeze(-2), ((idx // W) % H).unsqueeze(-2)         # B,N,2,Lt,1,k
+    yy, xx = torch.meshgrid(torch.arange(H), torch.arange(W), indexing='ij')
+    xx = xx.reshape(1, 1, 1, 1, H * W, 1).to(aff.dtype)
+    yy = yy.reshape(1, 1, 1, 1, H * W, 1).to(aff.dtype)
+    g = -((xx - xk) ** 2 + (yy - yk) ** 2) / (2 * sigma ** 2)                # B,N,2,Lt,HW,k
+    return torch.exp(g.max(dim=-1)[0] / tau)
+
+
 def readout(qk_unit: torch.Tensor, mk_unit: torch.Tensor, mv: torch.Tensor, tau: float, topl: int,
-            trace: Optional[dict] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+            trace: Optional[dict] = None, n_kernel: int = 0, sigma: float = 7) -> Tuple[torch.Tensor, torch.Tensor]:
     """qk_unit (B,Ck,H,W) and mk_unit (B,N,2,Ck,Lt) already l2-normalised; mv (B,N,2,Cv,Lt).
 
-    Returns S (BN, 2*topl, H, W) and mem_out (B,N,Cv,H,W) (:232-276, n_kernel=0, p_drop=0 branch).
+    Returns S (BN, 2*topl, H, W) and mem_out (B,N,Cv,H,W) (:232-276; p_drop=0; n_kernel > 0: the kernelised branch :252-256,
+    in which the attention -- not S -- is weighted by `kernel_weights` and normalised with + 1e-8).
     """
     B, Ck, H, W = qk_unit.shape
     N, Lt = mk_unit.shape[1], mk_unit.shape[-1]
@@ -201,7 +215,11 @@ def readout(qk_unit: torch.Tensor, mk_unit: torch.Tensor, mv: torch.Tensor, tau:
     aff = torch.matmul(mk_unit.transpose(-2, -1), q)                        # B,N,2,Lt,HW
     peak = aff.max(dim=2, keepdim=True)[0].max(dim=3, keepdim=True)[0]      # B,N,1,1,HW
     e = torch.exp((aff - peak) / tau)
-    p = (e / e.sum(dim=[2, 3], keepdim=True)).flatten(start_dim=2, end_dim=3)   # B,N,2Lt,HW
+    if n_kernel > 0:
+        eg = (e * kernel_weights(aff, H, W, n_kernel, sigma, tau)).flatten(start_dim=2, end_dim=3)
+        p = eg / (eg.sum(dim=2, keepdim=True) + 1e-8)
+    else:
+        p = (e / e.sum(dim=[2, 3], keepdim=True)).flatten(start_dim=2, end_dim=3)   # B,N,2Lt,HW
     S = perm_inv_feat(e.view(B * N, 2, Lt, H, W), topl)
     vals = mv.transpose(2, 3).flatten(start_dim=-2)                         # B,N,Cv,2Lt  (column = side*Lt + j)
     mem_out = torch.matmul(vals, p).view(B, N, -1, H, W)

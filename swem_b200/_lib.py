@@ -55,7 +55,8 @@ class SwemReadArgs(C.Structure):
                 ('out', C.c_void_p),
                 ('out_channels', C.c_int32), ('mem_channel', C.c_int32), ('s_channel', C.c_int32),
                 ('workspace', C.c_void_p), ('workspace_bytes', C.c_size_t),
-                ('path', C.c_int32), ('out_pixel_major', C.c_int32), ('bank_images_valid', C.c_int32)]
+                ('path', C.c_int32), ('out_pixel_major', C.c_int32), ('bank_images_valid', C.c_int32),
+                ('mkm_kernels', C.c_int32), ('mkm_sigma', C.c_float), ('mkm_width', C.c_int32)]
 
 
 class SwemReadBwdArgs(C.Structure):

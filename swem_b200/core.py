@@ -371,6 +371,36 @@ class SWEMCore(nn.Module):
         self.launches = lib.swem_last_launch_count()
         return feats
 
+    @torch.no_grad()
+    def get_affinity(self, qk, mk, mv, n_kernel: int = 0, sigma: float = 7):
+        """The reference's ``get_affinity`` (modules.py:232-276) with its signature: ``qk`` (B,Ck,H,W) and ``mk`` (B,N,2,Ck,Lt)
+        l2-normalised as ``matching`` passes them (normalising again is the identity to 1e-6), ``mv`` (B,N,2,Cv,Lt) ->
+        ``(S (B*N, 2 topl, H, W), mem_out (B,N,Cv,H,W))``.  Inference only (the training path is ``matching``).  ``n_kernel > 0``:
+        the kernelised-memory branch (:252-256 with ``gen_kernels`` :210-230) -- off by default in the reference and never switched
+        on by its scripts; implemented by the generic kernel family only (one ``swem_readout_forward`` call with
+        ``SWEM_PATH_GENERIC``, ``mkm_kernels`` / ``mkm_sigma`` / ``mkm_width``).  In training mode the reference ignores ``n_kernel``
+        (:252); so does this."""
+        if self.training:
+            n_kernel = 0
+        qk, mk, mv = _f32c(qk, 'qk'), _f32c(mk, 'mk'), _f32c(mv, 'mv')
+        B, Ck, H, W = qk.shape
+        _, N, _, Cv, Lt = mv.shape
+        topl = self.topl
+        feats = torch.empty(B * N, Cv + 2 * topl, H, W, device=qk.device, dtype=torch.float32)
+        lib = _lib.load()
+        path = _lib.PATH_GENERIC if n_kernel > 0 else self.readout_path
+        dims = _lib.SwemDims(B, N, Ck, Cv, H * W, Lt, 0, 1, topl, self.tau)
+        ws = self._workspace.get(qk.device, lib.swem_readout_workspace_bytes(C.byref(dims), path), 'affinity')
+        args = _lib.SwemReadArgs(dims, qk.data_ptr(), (C.c_void_p * 2)(mk.data_ptr(), None), (C.c_void_p * 2)(mv.data_ptr(), None),
+                                 feats.data_ptr(), Cv + 2 * topl, 0, Cv, ws.data_ptr(), ws.numel(), path, 0, 0,
+                                 int(n_kernel), float(sigma), W)
+        with torch.cuda.device(qk.device):
+            stream = torch.cuda.current_stream(qk.device).cuda_stream
+            rc = _invoke('readout', lambda: lib.swem_readout_forward(C.byref(args), stream))
+        _lib.check(rc, 'swem_readout_forward')
+        self.launches = lib.swem_last_launch_count()
+        return feats[:, Cv:].contiguous(), feats[:, :Cv].reshape(B, N, Cv, H, W)
+
     def matching(self, qk, qv):
         feats, n = self.matching_features(qk, qv)
         return self.fusion_layer(feats), n

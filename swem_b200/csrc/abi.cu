@@ -278,6 +278,15 @@ int swem_readout_forward(const SwemReadArgs* a, void* stream) {
                  a->bank_images_valid, d.n_banks);
   SWEM_CHECK_ARG(a->out_pixel_major == 0 || (a->out_pixel_major == 1 && a->out_channels % 4 == 0 && a->mem_channel % 4 == 0),
                  "out_pixel_major=%d needs out_channels and mem_channel to be multiples of 4", a->out_pixel_major);
+  if (a->mkm_kernels != 0) {
+    SWEM_CHECK_ARG(a->mkm_kernels > 0 && a->mkm_kernels <= 16 && a->mkm_kernels <= d.HW, "mkm_kernels=%d (1..16, <= HW)", a->mkm_kernels);
+    SWEM_CHECK_ARG(a->mkm_sigma > 0.f && a->mkm_width > 0 && d.HW % a->mkm_width == 0, "mkm_sigma=%g mkm_width=%d (HW=%d)",
+                   a->mkm_sigma, a->mkm_width, d.HW);
+    if (a->path != SWEM_PATH_GENERIC) {
+      set_error("the kernelised-memory readout (mkm_kernels=%d) is implemented by the generic family only: ask for SWEM_PATH_GENERIC", a->mkm_kernels);
+      return SWEM_ERR_UNSUPPORTED;
+    }
+  }
   if (a->path != SWEM_PATH_GENERIC && !fused_readout_supported(d)) {
     set_error("the tcgen05 readout kernels do not cover Ck=%d Cv=%d L=%d banks=%d topl=%d (Ck in {64,128}, L in {64,128,256,512}, Cv=512, "
               "topl<=64); the generic fp32 family runs only on request (SWEM_PATH_GENERIC)", d.Ck, d.Cv, d.L, d.n_banks, d.topl);

@@ -235,7 +235,7 @@ __global__ void bases_finalize_kernel(const float* __restrict__ prior, const flo
 
 // One warp per (u, p): scores row [2Lt] -> P = softmax over both sides of (score/||q||)/tau, in place.
 __global__ void readout_rows_kernel(float* __restrict__ sc, const float* __restrict__ inv_nq, int U, int N,
-                                    int HW, int W2, float inv_tau) {
+                                    int HW, int W2, float inv_tau, float* __restrict__ zsum = nullptr) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= U * HW) return;
@@ -249,6 +249,82 @@ __global__ void readout_rows_kernel(float* __restrict__ sc, const float* __restr
   for (int j = lane; j < W2; j += 32) sum += expf((row[j] * inv - mx) * inv_tau);
   sum = warp_sum(sum);
   for (int j = lane; j < W2; j += 32) row[j] = expf((row[j] * inv - mx) * inv_tau) / sum;
+  if (zsum != nullptr && lane == 0) zsum[(long long)u * HW + p] = sum;       // row sum of the exp-affinities (max = 1)
+}
+
+// ---- kernelised memory (reference gen_kernels, modules.py:210-230; inference only, off by default) -----------------------------
+// One warp per (u, column j of the 2 Lt bases): the K pixels with the largest affinity a[p] = score[p][j] / ||q_p|| (:213; ties: the
+// lower pixel index).  Every lane keeps the K best of its pixels p = lane, lane + 32, ... in a sorted register list, then K rounds of
+// a warp arg-max pop the winners.
+constexpr int kMkmMax = 16;
+__global__ void __launch_bounds__(256) mkm_topk_kernel(const float* __restrict__ sc, const float* __restrict__ inv_nq, int U, int N, int HW,
+                                                       int W2, int K, int* __restrict__ centers) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= U * W2) return;
+  const int u = warp / W2, j = warp % W2, b = u / N;
+  float val[kMkmMax];
+  int idx[kMkmMax];
+#pragma unroll
+  for (int k = 0; k < kMkmMax; ++k) { val[k] = -FLT_MAX; idx[k] = 0x7fffffff; }
+  for (int p = lane; p < HW; p += 32) {
+    float v = sc[((long long)u * HW + p) * W2 + j] * inv_nq[b * HW + p];
+    int pi = p;
+#pragma unroll
+    for (int k = 0; k < kMkmMax; ++k) {              // insertion into the descending list (pixels arrive in ascending order: strict >)
+      if (k < K && v > val[k]) {
+        const float tv = val[k]; const int ti = idx[k];
+        val[k] = v; idx[k] = pi;
+        v = tv; pi = ti;
+      }
+    }
+  }
+  for (int r = 0; r < K; ++r) {
+    const float head = val[0];
+    const int hidx = idx[0];
+    float best = head;
+    int bidx = hidx;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+      if (ov > best || (ov == best && oi < bidx)) { best = ov; bidx = oi; }
+    }
+    if (hidx == bidx) {                              // this lane held the winner: pop it
+#pragma unroll
+      for (int k = 0; k + 1 < kMkmMax; ++k) { val[k] = val[k + 1]; idx[k] = idx[k + 1]; }
+      val[kMkmMax - 1] = -FLT_MAX; idx[kMkmMax - 1] = 0x7fffffff;
+    }
+    if (lane == 0) centers[((long long)u * W2 + j) * kMkmMax + r] = bidx;
+  }
+}
+
+// One warp per (u, p): P[j] <- P[j] G[j] / (sum_j P[j] G[j] + 1e-8 / Z), G[j] = exp(-min_k d^2(p, center_jk) / (2 sigma^2 tau)), Z the row
+// sum of the exp-affinities -- i.e. E G / (sum E G + 1e-8) of the reference (:254-256) written on the normalised P = E / Z.
+__global__ void __launch_bounds__(256) mkm_apply_kernel(float* __restrict__ P, const float* __restrict__ zsum, const int* __restrict__ centers,
+                                                        int U, int HW, int W2, int K, int width, float inv_2s2tau) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= U * HW) return;
+  const int u = warp / HW, p = warp % HW;
+  const float px = (float)(p % width), py = (float)(p / width);
+  float* row = P + ((long long)u * HW + p) * W2;
+  float sum = 0.f;
+  for (int j = lane; j < W2; j += 32) {
+    const int* c = centers + ((long long)u * W2 + j) * kMkmMax;
+    float d2 = FLT_MAX;
+    for (int k = 0; k < K; ++k) {
+      const int q = c[k];
+      const float dx = px - (float)(q % width), dy = py - (float)(q / width);
+      d2 = fminf(d2, dx * dx + dy * dy);
+    }
+    const float w = row[j] * expf(-d2 * inv_2s2tau);
+    row[j] = w;
+    sum += w;
+  }
+  sum = warp_sum(sum);
+  const float inv = 1.f / (sum + 1e-8f / zsum[(long long)u * HW + p]);
+  for (int j = lane; j < W2; j += 32) row[j] *= inv;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -519,6 +595,8 @@ size_t generic_readout_workspace(const SwemDims& d) {
   bytes += align_up(U * d.HW * 2 * Lt * 4, 256);              // scores / P
   bytes += align_up(G * d.Ck * d.L * 4, 256) * d.n_banks;     // khat per bank
   bytes += align_up((size_t)d.B * d.HW * 4, 256);             // inv ||q||
+  bytes += align_up(U * 2 * Lt * kMkmMax * 4, 256);           // kernelised memory: best-matching pixels per basis
+  bytes += align_up(U * d.HW * 4, 256);                       //                    row sums of the exp-affinities
   return bytes + 256;
 }
 
@@ -531,6 +609,9 @@ int generic_readout_forward(const SwemReadArgs& a, cudaStream_t st) {
   float* khat[2] = {nullptr, nullptr};
   for (int k = 0; k < d.n_banks; ++k) khat[k] = ws.take<float>((size_t)G * d.Ck * d.L);
   float* inv_nq = ws.take<float>((size_t)d.B * d.HW);
+  int* centers = ws.take<int>((size_t)U * W2 * kMkmMax);
+  float* zsum = ws.take<float>((size_t)U * d.HW);
+  const bool mkm = a.mkm_kernels > 0;
 
   pixel_inv_norm_kernel<<<(d.B * d.HW + 255) / 256, 256, 0, st>>>(a.qk, inv_nq, d.B, d.Ck, d.HW);
   SWEM_LAUNCH_CHECK();
@@ -547,9 +628,21 @@ int generic_readout_forward(const SwemReadArgs& a, cudaStream_t st) {
     g.bC[0] = (long long)d.N * d.HW * W2; g.bC[1] = (long long)d.HW * W2; g.bC[2] = Lt;
     if (int rc = launch_gemm(a.qk, khat[k], P + (size_t)k * d.L, g, st)) return rc;
   }
+  if (mkm) {                                                  // best-matching pixels of every basis, from the raw affinities
+    const long long threads = (long long)U * W2 * 32;
+    mkm_topk_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(P, inv_nq, U, d.N, d.HW, W2, a.mkm_kernels, centers);
+    SWEM_LAUNCH_CHECK();
+  }
   {
     const long long threads = (long long)U * d.HW * 32;
-    readout_rows_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(P, inv_nq, U, d.N, d.HW, W2, 1.f / d.tau);
+    readout_rows_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(P, inv_nq, U, d.N, d.HW, W2, 1.f / d.tau, mkm ? zsum : nullptr);
+    SWEM_LAUNCH_CHECK();
+  }
+  if (mkm) {                                                  // S from the plain affinities (:269), then the kernel weights on the attention
+    if (int rc = launch_perm_inv(P, U, d.HW, Lt, d.topl, a.out, a.out_channels, a.s_channel, a.out_pixel_major, st)) return rc;
+    const long long threads = (long long)U * d.HW * 32;
+    mkm_apply_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(P, zsum, centers, U, d.HW, W2, a.mkm_kernels, a.mkm_width,
+                                                                         1.f / (2.f * a.mkm_sigma * a.mkm_sigma * d.tau));
     SWEM_LAUNCH_CHECK();
   }
   // mem_out[u][dch][p] = sum_{s,k,l} nu_k[u,s][dch][l] P[u][p][s*Lt + k*L + l]
@@ -570,6 +663,7 @@ int generic_readout_forward(const SwemReadArgs& a, cudaStream_t st) {
                                a.out + (a.out_pixel_major ? (size_t)a.mem_channel : (size_t)a.mem_channel * d.HW), g, st))
         return rc;
     }
+  if (mkm) return SWEM_OK;
   return launch_perm_inv(P, U, d.HW, Lt, d.topl, a.out, a.out_channels, a.s_channel, a.out_pixel_major, st);
 }
 

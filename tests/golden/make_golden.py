@@ -5,7 +5,8 @@ Run in the authoring container only (needs /root/reference):
     python tests/golden/make_golden.py
 
 Writes ``core_small.pt``, ``core_prod.pt``, ``steps_small.pt``, ``model_tiny.pt`` next to this
-file (``--wide``: only ``core_wide.pt``, the reference's class default of 256 bases per side).  Each fixture holds the seeded inputs and the reference's outputs; tests replay the inputs
+file (``--wide``: only ``core_wide.pt``, the reference's class default of 256 bases per side; ``--mkm``: only ``mkm_small.pt``,
+the kernelised-memory readout branch).  Each fixture holds the seeded inputs and the reference's outputs; tests replay the inputs
 through ``oracle/swem_oracle.py`` (CPU) and through the CUDA library (GPU).
 """
 from __future__ import annotations
@@ -109,10 +110,36 @@ def model_case(SWEM, name, seed=5):
     print(name, os.path.getsize(os.path.join(HERE, name + '.pt')) // 1024, 'KiB')
 
 
+def mkm_case(ref, name, B=1, N=2, Ck=64, Cv=64, Lt=32, H=12, W=20, tau=0.05, topl=16, n_kernel=7, sigma=7, seed=11):
+    """The reference's kernelised-memory readout (get_affinity with n_kernel > 0, modules.py:232-276 + gen_kernels :210-230; off
+    by default, inference only) on a seeded clustered memory: raw inputs and the reference's (S, mem_out)."""
+    core = ref.SWEMCore(n_bases=Lt // 2, valdim=Cv, n_iters=1, tau=tau, topl=topl)
+    core.eval()
+    g = torch.Generator().manual_seed(seed)
+    q = torch.randn(B, Ck, H, W, generator=g)
+    # memory keys near some of the query pixels, so that the best-matching pixels of a basis are not arbitrary
+    pix = torch.randint(0, H * W, (B, N, 2, Lt), generator=g)
+    qf = q.flatten(start_dim=-2)                                             # B,Ck,HW
+    mk = torch.stack([torch.stack([qf[b][:, pix[b, n].reshape(-1)].reshape(Ck, 2, Lt).permute(1, 0, 2) for n in range(N)]) for b in range(B)])
+    mk = mk + 0.3 * torch.randn(B, N, 2, Ck, Lt, generator=g)
+    mv = torch.randn(B, N, 2, Cv, Lt, generator=g)
+    with torch.no_grad():
+        S, mem_out = core.get_affinity(ref.l2norm(q, dim=1), ref.l2norm(mk, dim=-2), mv, n_kernel=n_kernel, sigma=sigma)
+        S0, mem_out0 = core.get_affinity(ref.l2norm(q, dim=1), ref.l2norm(mk, dim=-2), mv)
+    assert torch.equal(S, S0) and not torch.allclose(mem_out, mem_out0)      # the kernels reweight the attention only
+    fx = dict(cfg=dict(B=B, N=N, Ck=Ck, Cv=Cv, Lt=Lt, H=H, W=W, tau=tau, topl=core.topl, n_kernel=n_kernel, sigma=sigma),
+              q=q, mk=mk, mv=mv, S=S.clone(), mem_out=mem_out.clone())
+    torch.save(fx, os.path.join(HERE, name + '.pt'))
+    print(name, os.path.getsize(os.path.join(HERE, name + '.pt')) // 1024, 'KiB')
+
+
 def main():
     assert ref_shim.available(), 'reference checkout not found'
     torch.set_num_threads(1)                       # fixed reduction order inside ATen
     ref = ref_shim.load_modules()
+    if '--mkm' in sys.argv:                        # added later: only this fixture is (re)generated
+        mkm_case(ref, 'mkm_small')
+        return
     if '--wide' in sys.argv:                       # added later: only this fixture is (re)generated
         core_case(ref, 'core_wide', B=1, n_seq=[1, 1], Ck=64, Cv=512, L=256, H=6, W=10, n_iters=3, tau=0.05,
                   topl=64, seed=31)

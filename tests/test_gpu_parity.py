@@ -1093,3 +1093,47 @@ def test_frame_engine_fusion_kernel_matches_cudnn_path():
             check('context', maxrel(ck, cc), 2e-5)
     finally:
         torch.backends.cudnn.allow_tf32 = old
+
+
+def test_kernelised_memory_readout_vs_reference_golden(golden):
+    """SWEMCore.get_affinity with n_kernel > 0 (the reference's gen_kernels branch, modules.py:210-230,252-256; off by default,
+    inference only) against the outputs of the unmodified reference (tests/golden/mkm_small.pt) and, at a larger shape, against
+    the oracle; n_kernel = 0 through the same entry gives the plain readout; any path but GENERIC refuses loudly."""
+    from swem_b200 import SWEMCore, _lib
+    fx = golden('mkm_small')
+    c = fx['cfg']
+    core = SWEMCore(n_bases=c['Lt'] // 2, valdim=c['Cv'], n_iters=1, tau=c['tau'], topl=c['topl']).to(DEV).eval()
+    core.readout_path = _lib.PATH_GENERIC
+    qn, mkn = O.l2norm(fx['q'], dim=1).to(DEV), O.l2norm(fx['mk'], dim=-2).to(DEV)
+    S, mem_out = core.get_affinity(qn, mkn, fx['mv'].to(DEV), n_kernel=c['n_kernel'], sigma=c['sigma'])
+    check('S', maxrel(S, fx['S']), 2e-4)
+    check('mem_out', maxrel(mem_out, fx['mem_out']), 2e-4)
+    S0, m0 = core.get_affinity(qn, mkn, fx['mv'].to(DEV))
+    wS, wm = O.readout(O.l2norm(fx['q'], dim=1), O.l2norm(fx['mk'], dim=-2), fx['mv'], c['tau'], c['topl'])
+    check('S_plain', maxrel(S0, wS), 2e-4)
+    check('mem_plain', maxrel(m0, wm), 2e-4)
+    assert maxrel(mem_out, m0) > 1e-2                          # the kernels do change the attention
+    # a DAVIS-sized grid, 256 bases per side, other n_kernel / sigma
+    g = torch.Generator().manual_seed(3)
+    B, N, Ck, Cv, Lt, H, W = 1, 2, 64, 512, 256, 30, 54
+    q = torch.randn(B, Ck, H, W, generator=g)
+    pix = torch.randint(0, H * W, (N * 2 * Lt,), generator=g)
+    mk = q.flatten(start_dim=-2)[0][:, pix].reshape(Ck, N, 2, Lt).permute(1, 2, 0, 3)[None] + 0.3 * torch.randn(B, N, 2, Ck, Lt, generator=g)
+    mv = torch.randn(B, N, 2, Cv, Lt, generator=g)
+    big = SWEMCore(n_bases=Lt // 2, valdim=Cv, n_iters=1, tau=0.05, topl=64).to(DEV).eval()
+    S, mem_out = big.get_affinity(O.l2norm(q, dim=1).to(DEV), O.l2norm(mk, dim=-2).to(DEV), mv.to(DEV), n_kernel=5, sigma=4.0)
+    wS, wm = O.readout(O.l2norm(q, dim=1).double(), O.l2norm(mk, dim=-2).double(), mv.double(), 0.05, 64, n_kernel=5, sigma=4.0)
+    check('S_big', maxrel(S, wS), 2e-4)
+    check('mem_big', maxrel(mem_out, wm), 5e-4)
+    # the tcgen05 family does not implement the branch: asking for it there is an error, not a silent plain readout
+    import ctypes as C
+    lib = _lib.load()
+    dims = _lib.SwemDims(B, N, Ck, Cv, H * W, Lt // 2, 0, 2, 64, 0.05)
+    ws = torch.empty(lib.swem_readout_workspace_bytes(C.byref(dims), _lib.PATH_AUTO), dtype=torch.uint8, device=DEV)
+    out = torch.empty(B * N, Cv + 128, H, W, device=DEV)
+    k0 = mk[..., :Lt // 2].contiguous().to(DEV); k1 = mk[..., Lt // 2:].contiguous().to(DEV)
+    n0 = mv[..., :Lt // 2].contiguous().to(DEV); n1 = mv[..., Lt // 2:].contiguous().to(DEV)
+    args = _lib.SwemReadArgs(dims, q.to(DEV).data_ptr(), (C.c_void_p * 2)(k0.data_ptr(), k1.data_ptr()), (C.c_void_p * 2)(n0.data_ptr(), n1.data_ptr()),
+                             out.data_ptr(), Cv + 128, 0, Cv, ws.data_ptr(), ws.numel(), _lib.PATH_AUTO, 0, 0, 7, 7.0, W)
+    assert lib.swem_readout_forward(C.byref(args), torch.cuda.current_stream().cuda_stream) == 2      # SWEM_ERR_UNSUPPORTED
+    assert b'generic family only' in lib.swem_last_error()
