@@ -278,6 +278,7 @@ int swem_readout_forward(const SwemReadArgs* a, void* stream) {
                  a->bank_images_valid, d.n_banks);
   SWEM_CHECK_ARG(a->out_pixel_major == 0 || (a->out_pixel_major == 1 && a->out_channels % 4 == 0 && a->mem_channel % 4 == 0),
                  "out_pixel_major=%d needs out_channels and mem_channel to be multiples of 4", a->out_pixel_major);
+  SWEM_CHECK_ARG(a->out_pixel_major == 0 || (reinterpret_cast<uintptr_t>(a->out) & 15) == 0, "out_pixel_major: `out` must be 16-byte aligned");
   if (a->mkm_kernels != 0) {
     SWEM_CHECK_ARG(a->mkm_kernels > 0 && a->mkm_kernels <= 16 && a->mkm_kernels <= d.HW, "mkm_kernels=%d (1..16, <= HW)", a->mkm_kernels);
     SWEM_CHECK_ARG(a->mkm_sigma > 0.f && a->mkm_width > 0 && d.HW % a->mkm_width == 0, "mkm_sigma=%g mkm_width=%d (HW=%d)",

@@ -54,7 +54,8 @@ constexpr uint32_t kOffQL = kOffQH + 16384;
 constexpr uint32_t kEBytesMax = kOwn * (2 * 256 + 17) * 4;
 constexpr uint32_t kOffMisc = ((kOffE + kEBytesMax + 127) / 128) * 128;
 static_assert(kOffQL + 16384 <= kOffMisc, "query tile inside the aliased region");
-static_assert(16 * 32 * 33 * 4 <= kRing * kStageBytes, "transpose tiles of the store phase fit in the ring");
+constexpr int kTileStride = 68;          // floats per pixel row of a store-phase transpose tile (64 channels + 4: 16-byte aligned, conflict-free)
+static_assert(16 * 32 * kTileStride * 4 <= kOffE + kEBytesMax, "transpose tiles of the store phase fit in the dead ring + E table");
 struct Misc {
   float inv_nq[kTP];
   float ex_max[4][kTP];
@@ -412,31 +413,44 @@ __global__ void __block_size__((32, 16, 1)) __maxnreg__(128) readout_topl_kernel
       }
     }
   }
+  __syncthreads();                                        // (the store tiles below overlay the E table the loop above has just read)
   // ---- normalise and store mem_out: thread <-> (pixel px, 64 channels [64 cb, +64) of this half) ------------------------------
   {
     const float scale = inv_total;             // the 2^10 of E cancels against the row sum of the same operand
     const bool in_range = p0 + px < HW;
     const uint32_t tcol = 128 + (cb >> 1) * 256 + (cb & 1) * 64;
     const int ch0 = p.mem_channel + h * kDH + cb * 64;
-    float* tbuf = reinterpret_cast<float*>(smem + kOffRing) + warp * (32 * 33);   // (pixel-major) 32 x 32 transpose tile of this warp; the ring is idle
+    // (pixel-major) [32 pixels][64 channels + 4] transpose tile of this warp: the ring and the E table are both dead by now
+    float* tbuf = reinterpret_cast<float*>(smem + kOffRing) + warp * (32 * kTileStride);
 #pragma unroll
     for (int qq = 0; qq < 2; ++qq) {
       uint32_t r[32];
       tmem_ld32(tmem_addr(tmem, lane_base, tcol + qq * 32), r);
       tmem_ld_wait();
       if (p.pixel_major) {
-        // [U][HW][C]: through the tile, so that one store instruction writes 32 consecutive channels (128 bytes) of a pixel
+        // [U][HW][C]: the thread's 32 channels of its pixel go into the tile as 8 x 16 bytes (row stride 272 bytes: conflict-free) ...
 #pragma unroll
-        for (int j = 0; j < 32; ++j) tbuf[lane * 33 + j] = __uint_as_float(r[j]) * scale;
-        __syncwarp();
-        const int npx = min(32, HW - (p0 + q * 32));
-        float* o = p.out + ((size_t)u * HW + p0 + q * 32) * p.out_channels + ch0 + qq * 32 + lane;
-        for (int rr = 0; rr < npx; ++rr) o[(size_t)rr * p.out_channels] = tbuf[rr * 33 + lane];
-        __syncwarp();
+        for (int j4 = 0; j4 < 8; ++j4)
+          *reinterpret_cast<float4*>(tbuf + lane * kTileStride + qq * 32 + j4 * 4) =
+              make_float4(__uint_as_float(r[4 * j4]) * scale, __uint_as_float(r[4 * j4 + 1]) * scale, __uint_as_float(r[4 * j4 + 2]) * scale,
+                          __uint_as_float(r[4 * j4 + 3]) * scale);
       } else if (in_range) {
         float* o = p.out + ((size_t)u * p.out_channels + ch0 + qq * 32) * HW + p0 + px;
 #pragma unroll
         for (int j = 0; j < 32; ++j) o[(size_t)j * HW] = __uint_as_float(r[j]) * scale;
+      }
+    }
+    if (p.pixel_major) {
+      // ... and leave as 16-byte stores: half a warp writes the 256 contiguous bytes of one pixel, 16 instructions for the 32 pixels
+      // (the first version wrote 4 bytes per lane: 64 store + 64 shared-load instructions per warp, store phase 4.4 us)
+      __syncwarp();
+      const int npx = min(32, HW - (p0 + q * 32));
+      float* o = p.out + ((size_t)u * HW + p0 + q * 32) * p.out_channels + ch0 + (lane & 15) * 4;
+#pragma unroll 4
+      for (int it = 0; it < 16; ++it) {
+        const int pl = it * 2 + (lane >> 4);
+        const float4 v = *reinterpret_cast<const float4*>(tbuf + pl * kTileStride + (lane & 15) * 4);
+        if (pl < npx) *reinterpret_cast<float4*>(o + (size_t)pl * p.out_channels) = v;
       }
     }
   }
