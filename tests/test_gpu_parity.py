@@ -933,13 +933,14 @@ def test_em_single_launch_is_stable_over_many_calls():
         check(k + '_repeat', e, 1e-3)
 
 
-def test_readout_reuses_bank_images_only_while_they_are_valid():
+@pytest.mark.parametrize('L', [128, 64])
+def test_readout_reuses_bank_images_only_while_they_are_valid(L):
     """SwemReadArgs.bank_images_valid / SwemEmArgs.image_workspace (host side: SWEMCore.memorize / _readout_launch): the operand images
     of the unchanged 'first' bank are reused from the second readout on, those of the 'update' bank are written by the EM kernel
     that produces it -- same features bit for bit as a full conversion, no conversion launch -- and never after a bank changed: an
     in-place update (version counter) or a new tensor object must be seen by the next readout."""
     from swem_b200.synthetic import clustered_em_inputs, em_inputs
-    B, N, Ck, Cv, H, W, L = 1, 3, 64, 512, 30, 54, 128
+    B, N, Ck, Cv, H, W = 1, 3, 64, 512, 30, 54
     core = _core(dict(L=L, Cv=Cv, n_iters=2, tau=0.05, topl=64), 'fused')
     seen = []
     import swem_b200.core as core_mod
