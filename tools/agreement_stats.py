@@ -27,13 +27,19 @@ O.random_init = real
 fr, im = frames.to(DEV), init.to(DEV)
 torch.backends.cudnn.benchmark = True
 print('== split-TF32 convs (main + cross-term TF32 convs over hi/lo splits, FrameEngine(split_tf32=True)) + cudnn.benchmark', flush=True)
-eng = FrameEngine(model, split_tf32=True)
-for rep in range(3):
-    with torch.no_grad():
-        got, _ = evaluate_davis_seq(eng, fr, [im] + [None] * (T - 1), (h, w))
-    got = torch.stack(got).cpu()
-    dis = 1 - (got == want).flatten(1).float().mean(dim=1)
-    print(f'engine+fused     rep {rep}: per-frame disagreement ' + ' '.join(f'{d:.1e}' for d in dis.tolist()) + f' | pooled {dis.mean():.1e} max {dis.max():.1e}', flush=True)
+for label, kw in (('bf16 cross terms, fusion layer on swem_fusion_conv_glu (bench.py)', dict(cross_bf16=True, fusion_kernel=True)),
+                  ('bf16 cross terms, fusion layer on cuDNN', dict(cross_bf16=True, fusion_kernel=False)),
+                  ('TF32 cross terms, fusion layer on swem_fusion_conv_glu', dict(cross_bf16=False, fusion_kernel=True))):
+    eng = FrameEngine(model, split_tf32=True, **kw)
+    print(f'-- {label}', flush=True)
+    for rep in range(3):
+        with torch.no_grad():
+            got, _ = evaluate_davis_seq(eng, fr, [im] + [None] * (T - 1), (h, w))
+        got = torch.stack(got).cpu()
+        dis = 1 - (got == want).flatten(1).float().mean(dim=1)
+        print(f'engine+fused     rep {rep}: per-frame disagreement ' + ' '.join(f'{d:.1e}' for d in dis.tolist()) + f' | pooled {dis.mean():.1e} max {dis.max():.1e}', flush=True)
+if '--split-only' in sys.argv:
+    sys.exit(0)
 torch.backends.cudnn.benchmark = False
 modes = (('fp32 convs', False, False), ('fp32 convs + cudnn.benchmark', False, True),
          ('tf32 convs (torch default)', True, False), ('tf32 convs + cudnn.benchmark', True, True))
