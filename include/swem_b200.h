@@ -151,6 +151,10 @@ typedef struct SwemReadArgs {
   int32_t mkm_kernels;       /* 0 (off) .. 16                                                      */
   float   mkm_sigma;
   int32_t mkm_width;
+  /* Memory dropout (the reference's training-only branch modules.py:258-263; p_drop is hard-wired to 0 there): drop_mask
+   * [B, N, Lt] of 0 / 1 (Lt = n_banks L; one mask for both sides) multiplies the exp-affinities of the attention, normalised with
+   * + 1e-6; S is unchanged.  NULL = off.  SWEM_PATH_GENERIC only; pass the same mask to swem_readout_backward.                    */
+  const float* drop_mask;
 } SwemReadArgs;
 
 size_t swem_readout_workspace_bytes(const SwemDims* dims, int32_t path);
@@ -171,6 +175,7 @@ typedef struct SwemReadBwdArgs {
   float* grad_nu[2];         /* out per bank [B, N, 2, Cv, L] (NULL = skip)                                  */
   void*  workspace;          /* >= swem_readout_backward_workspace_bytes(&dims)                              */
   size_t workspace_bytes;
+  const float* drop_mask;    /* the forward's SwemReadArgs.drop_mask (NULL = none)                           */
 } SwemReadBwdArgs;
 
 size_t swem_readout_backward_workspace_bytes(const SwemDims* dims);

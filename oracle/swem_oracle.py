@@ -203,11 +203,13 @@ def kernel_weights(aff: torch.Tensor, H: int, W: int, n_kernel: int, sigma: floa
 
 
 def readout(qk_unit: torch.Tensor, mk_unit: torch.Tensor, mv: torch.Tensor, tau: float, topl: int,
-            trace: Optional[dict] = None, n_kernel: int = 0, sigma: float = 7) -> Tuple[torch.Tensor, torch.Tensor]:
+            trace: Optional[dict] = None, n_kernel: int = 0, sigma: float = 7,
+            drop_mask: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
     """qk_unit (B,Ck,H,W) and mk_unit (B,N,2,Ck,Lt) already l2-normalised; mv (B,N,2,Cv,Lt).
 
-    Returns S (BN, 2*topl, H, W) and mem_out (B,N,Cv,H,W) (:232-276; p_drop=0; n_kernel > 0: the kernelised branch :252-256,
-    in which the attention -- not S -- is weighted by `kernel_weights` and normalised with + 1e-8).
+    Returns S (BN, 2*topl, H, W) and mem_out (B,N,Cv,H,W) (:232-276; n_kernel > 0: the kernelised branch :252-256, in which the
+    attention -- not S -- is weighted by `kernel_weights` and normalised with + 1e-8; drop_mask (B,N,1,Lt,1) of 0 / 1: the memory
+    dropout of the training branch :258-263 -- the reference draws it as torch.rand(B,N,1,Lt,1) > p_drop -- normalised with + 1e-6).
     """
     B, Ck, H, W = qk_unit.shape
     N, Lt = mk_unit.shape[1], mk_unit.shape[-1]
@@ -218,6 +220,9 @@ def readout(qk_unit: torch.Tensor, mk_unit: torch.Tensor, mv: torch.Tensor, tau:
     if n_kernel > 0:
         eg = (e * kernel_weights(aff, H, W, n_kernel, sigma, tau)).flatten(start_dim=2, end_dim=3)
         p = eg / (eg.sum(dim=2, keepdim=True) + 1e-8)
+    elif drop_mask is not None:
+        ed = e * drop_mask
+        p = (ed / (ed.sum(dim=[2, 3], keepdim=True) + 1e-6)).flatten(start_dim=2, end_dim=3)
     else:
         p = (e / e.sum(dim=[2, 3], keepdim=True)).flatten(start_dim=2, end_dim=3)   # B,N,2Lt,HW
     S = perm_inv_feat(e.view(B * N, 2, Lt, H, W), topl)

@@ -56,7 +56,7 @@ class SwemReadArgs(C.Structure):
                 ('out_channels', C.c_int32), ('mem_channel', C.c_int32), ('s_channel', C.c_int32),
                 ('workspace', C.c_void_p), ('workspace_bytes', C.c_size_t),
                 ('path', C.c_int32), ('out_pixel_major', C.c_int32), ('bank_images_valid', C.c_int32),
-                ('mkm_kernels', C.c_int32), ('mkm_sigma', C.c_float), ('mkm_width', C.c_int32)]
+                ('mkm_kernels', C.c_int32), ('mkm_sigma', C.c_float), ('mkm_width', C.c_int32), ('drop_mask', C.c_void_p)]
 
 
 class SwemReadBwdArgs(C.Structure):
@@ -64,7 +64,7 @@ class SwemReadBwdArgs(C.Structure):
                 ('qk', C.c_void_p), ('kappa', C.c_void_p * 2), ('nu', C.c_void_p * 2), ('grad_out', C.c_void_p),
                 ('out_channels', C.c_int32), ('mem_channel', C.c_int32), ('s_channel', C.c_int32),
                 ('grad_qk', C.c_void_p), ('grad_nu', C.c_void_p * 2),
-                ('workspace', C.c_void_p), ('workspace_bytes', C.c_size_t)]
+                ('workspace', C.c_void_p), ('workspace_bytes', C.c_size_t), ('drop_mask', C.c_void_p)]
 
 
 _lib = None

@@ -75,7 +75,7 @@ def _unit(t: torch.Tensor, dim: int) -> torch.Tensor:
     return t / (torch.linalg.vector_norm(t, dim=dim, keepdim=True) + 1e-6)
 
 
-def readout_torch(qk: torch.Tensor, kappas: List[torch.Tensor], nus: List[torch.Tensor], tau: float, topl: int):
+def readout_torch(qk: torch.Tensor, kappas: List[torch.Tensor], nus: List[torch.Tensor], tau: float, topl: int, drop_mask=None):
     """Differentiable torch evaluation of the readout: -> [mem_out | S] (B*N, Cv + 2*topl, H, W).
 
     qk (B,Ck,H,W) raw; kappas / nus: per bank (B,N,2,Ck,L) / (B,N,2,Cv,L).  Used for the backward only."""
@@ -86,7 +86,11 @@ def readout_torch(qk: torch.Tensor, kappas: List[torch.Tensor], nus: List[torch.
     N, Lt, Cv = mk.shape[1], mk.shape[-1], mv.shape[3]
     aff = mk.transpose(-2, -1) @ q                                               # B,N,2,Lt,HW
     e = torch.exp((aff - aff.amax(dim=(2, 3), keepdim=True)) / tau)
-    p = e / e.sum(dim=(2, 3), keepdim=True)
+    if drop_mask is not None:                                                    # memory dropout (modules.py:258-263): (B,N,Lt) of 0 / 1
+        ed = e * drop_mask[:, :, None, :, None]
+        p = ed / (ed.sum(dim=(2, 3), keepdim=True) + 1e-6)
+    else:
+        p = e / e.sum(dim=(2, 3), keepdim=True)
     mem_out = (mv.transpose(2, 3).flatten(-2) @ p.flatten(2, 3)).reshape(B * N, Cv, H, W)
     run = torch.topk(e, k=topl, dim=3)[0].cumsum(dim=3)                          # sorted descending -> running sums over rank
     f = (run[:, :, 0] / (run[:, :, 0] + run[:, :, 1])).reshape(B * N, topl, H, W)
@@ -97,14 +101,15 @@ class ReadoutFunction(torch.autograd.Function):
     """[mem_out | S] = readout(qk | banks); differentiable in qk and in the nu of every bank."""
 
     @staticmethod
-    def forward(ctx, core, qk, n_banks, *bank_tensors):
+    def forward(ctx, core, qk, n_banks, drop_mask, *bank_tensors):
         kappas, nus = list(bank_tensors[:n_banks]), list(bank_tensors[n_banks:])
         B, _, H, W = qk.shape
         N, Cv = nus[0].shape[1], nus[0].shape[3]
         out = torch.empty(B * N, Cv + 2 * core.topl, H, W, device=qk.device, dtype=torch.float32)
-        core._readout_launch(qk, kappas, nus, out, 0, Cv)
+        core._readout_launch(qk, kappas, nus, out, 0, Cv, drop_mask=drop_mask)
         ctx.tau, ctx.topl, ctx.n_banks = core.tau, core.topl, n_banks
         ctx.core = core
+        ctx.drop_mask = drop_mask
         ctx.save_for_backward(qk, *kappas, *nus)
         return out
 
@@ -119,21 +124,21 @@ class ReadoutFunction(torch.autograd.Function):
         nb = ctx.n_banks
         kappas, nus = rest[:nb], rest[nb:]
         need_q = ctx.needs_input_grad[1]
-        need_nu = [ctx.needs_input_grad[3 + nb + k] for k in range(nb)]
+        need_nu = [ctx.needs_input_grad[4 + nb + k] for k in range(nb)]
         if not (need_q or any(need_nu)):
-            return (None,) * (3 + 2 * nb)
+            return (None,) * (4 + 2 * nb)
         if ReadoutFunction.native_backward:
             gq, gn = _readout_backward_native(ctx, qk, kappas, nus, gout.float().contiguous(), need_q, need_nu)
         else:
             with torch.enable_grad():
                 q_ = qk.detach().requires_grad_(need_q)
                 nus_ = [n.detach().requires_grad_(need_nu[k]) for k, n in enumerate(nus)]
-                out = readout_torch(q_, [k.detach() for k in kappas], nus_, ctx.tau, ctx.topl)
+                out = readout_torch(q_, [k.detach() for k in kappas], nus_, ctx.tau, ctx.topl, ctx.drop_mask)
                 wrt = ([q_] if need_q else []) + [n for k, n in enumerate(nus_) if need_nu[k]]
                 grads = list(torch.autograd.grad(out, wrt, gout))
             gq = grads.pop(0) if need_q else None
             gn = [grads.pop(0) if need_nu[k] else None for k in range(nb)]
-        return (None, gq, None) + (None,) * nb + tuple(gn)
+        return (None, gq, None, None) + (None,) * nb + tuple(gn)
 
 
 def _readout_backward_native(ctx, qk, kappas, nus, gout, need_q, need_nu):
@@ -153,7 +158,7 @@ def _readout_backward_native(ctx, qk, kappas, nus, gout, need_q, need_nu):
     args = _lib.SwemReadBwdArgs(dims, qk.data_ptr(),
                                 (C.c_void_p * 2)(*[ptr(k) for k in kappas] + pad), (C.c_void_p * 2)(*[ptr(n) for n in nus] + pad),
                                 gout.data_ptr(), chans, 0, Cv, ptr(gq), (C.c_void_p * 2)(*[ptr(g) for g in gn] + pad),
-                                ws.data_ptr(), ws.numel())
+                                ws.data_ptr(), ws.numel(), ptr(ctx.drop_mask))
     with torch.cuda.device(dev):
         stream = torch.cuda.current_stream(dev).cuda_stream
         rc = _invoke('readout_backward', lambda: lib.swem_readout_backward(C.byref(args), stream))

@@ -286,10 +286,16 @@ class SWEMCore(nn.Module):
         N, Cv = self._readout_objects()
         banks = self._banks()
         B, _, H, W = qk.shape
+        # memory dropout (modules.py:258-263; training only, p_drop is 0.0 in the reference): one 0 / 1 mask per (b, n, basis of the
+        # concatenated memory), drawn like the reference does -- torch.rand on the CPU's global generator -- and handed to the kernels
+        drop = None
+        if self.training and self.p_drop > 0:
+            Lt = sum(b['nu'].shape[-1] for b in banks)
+            drop = (torch.rand(B, N, 1, Lt, 1) > self.p_drop).to(device=qk.device, dtype=torch.float32).reshape(B, N, Lt).contiguous()
         if _wants_grad(qk, qv, *[b['nu'] for b in banks]):       # training: kernels forward, autograd-visible concat
             from .autograd import ReadoutFunction
             qk = _f32c(qk, 'qk')
-            ms = ReadoutFunction.apply(self, qk, len(banks), *[_f32c(b['kappa'].detach(), 'kappa') for b in banks],
+            ms = ReadoutFunction.apply(self, qk, len(banks), drop, *[_f32c(b['kappa'].detach(), 'kappa') for b in banks],
                                        *[_f32c(b['nu'], 'nu') for b in banks])
             qv = qv.unsqueeze(1).expand(-1, N, -1, -1, -1).flatten(end_dim=1)
             return torch.cat([ms[:, :Cv], qv, ms[:, Cv:]], dim=1), N
@@ -297,7 +303,7 @@ class SWEMCore(nn.Module):
         chans = 2 * Cv + 2 * self.topl
         feats = torch.empty(B * N, chans, H, W, device=qk.device, dtype=torch.float32)
         feats.view(B, N, chans, H, W)[:, :, Cv:2 * Cv] = qv.unsqueeze(1)
-        return self.readout_into(qk, feats, 0, 2 * Cv), N
+        return self.readout_into(qk, feats, 0, 2 * Cv, drop_mask=drop), N
 
     def _banks(self):
         return [m.bases for m in self.memories.values() if m.bases is not None]
@@ -308,7 +314,7 @@ class SWEMCore(nn.Module):
             raise RuntimeError('matching() before any memorize(): memory is empty')
         return banks[0]['nu'].shape[1], banks[0]['nu'].shape[3]
 
-    def readout_into(self, qk, feats, mem_channel: int, s_channel: int) -> torch.Tensor:
+    def readout_into(self, qk, feats, mem_channel: int, s_channel: int, drop_mask=None) -> torch.Tensor:
         """Readout kernels only (no autograd): write ``mem_out`` into channels [mem_channel, +Cv) and ``S`` into
         channels [s_channel, +2*topl) of the caller's fp32 buffer ``feats`` (B*N, C, H, W), which is either contiguous
         (NCHW, the reference layout) or channels-last (NHWC; the kernels then write pixel-major).  The reference
@@ -319,14 +325,13 @@ class SWEMCore(nn.Module):
         return self._readout_launch(_f32c(qk.detach(), 'qk'), [_f32c(b['kappa'].detach(), 'kappa') for b in banks],
                                     [_f32c(b['nu'].detach(), 'nu') for b in banks], feats, mem_channel, s_channel,
                                     first_bank=(banks[0]['kappa'], banks[0]['nu']),
-                                    update_bank=(banks[1]['kappa'], banks[1]['nu']) if len(banks) == 2 else None)
+                                    update_bank=(banks[1]['kappa'], banks[1]['nu']) if len(banks) == 2 else None, drop_mask=drop_mask)
 
-    def _readout_launch(self, qk, kap, nus, feats, mem_channel: int, s_channel: int, first_bank=None, update_bank=None) -> torch.Tensor:
+    def _readout_launch(self, qk, kap, nus, feats, mem_channel: int, s_channel: int, first_bank=None, update_bank=None,
+                        drop_mask=None) -> torch.Tensor:
         """One ``swem_readout_forward`` call on contiguous fp32 CUDA tensors (kap / nus: one entry per bank).  ``first_bank``:
         the (kappa, nu) tensor OBJECTS of the 'first' bank as the bank holds them, or None when the caller cannot vouch for
         them (training): lets the call reuse that bank's operand images, see below."""
-        if self.training and self.p_drop > 0:
-            raise NotImplementedError('swem_b200: memory dropout (p_drop > 0) is not implemented')
         B, Ck, H, W = qk.shape
         _, N, _, Cv, L = nus[0].shape
         dev = qk.device
@@ -341,14 +346,15 @@ class SWEMCore(nn.Module):
 
         lib = _lib.load()
         dims = _lib.SwemDims(B, N, Ck, Cv, H * W, L, 0, len(nus), self.topl, self.tau)
-        need = lib.swem_readout_workspace_bytes(C.byref(dims), self.readout_path)
+        path = self.readout_path if drop_mask is None else _lib.PATH_GENERIC     # (memory dropout: generic family only)
+        need = lib.swem_readout_workspace_bytes(C.byref(dims), path)
         ws = self._workspace.get(dev, need, 'readout')            # not shared with the EM: the bank images in it survive a memorize
         # SwemReadArgs.bank_images_valid: the 'first' bank does not change while a sequence runs (modules.py:44-60); its
         # operand images stay in this workspace, so from the second readout on only the 'update' bank is converted.  The
         # images are keyed by everything they depend on: the workspace, the shapes, and the bank's tensor objects (held here,
         # so their storage cannot be recycled for other data) with their version counters.
         key = None
-        if first_bank is not None and len(nus) == 2 and self.readout_path != _lib.PATH_GENERIC:
+        if first_bank is not None and len(nus) == 2 and path != _lib.PATH_GENERIC:
             key = (ws.data_ptr(), ws.numel(), B, N, Ck, Cv, L, first_bank[0]._version, first_bank[1]._version)
         prev = self._image_key
         valid = 1 if (key is not None and prev is not None and prev[0] == key and prev[1] is first_bank[0]
@@ -363,7 +369,8 @@ class SWEMCore(nn.Module):
                                  (C.c_void_p * 2)(*[k.data_ptr() for k in kap] + [None] * (2 - len(kap))),
                                  (C.c_void_p * 2)(*[n.data_ptr() for n in nus] + [None] * (2 - len(nus))),
                                  feats.data_ptr(), chans, mem_channel, s_channel,
-                                 ws.data_ptr(), ws.numel(), self.readout_path, pixel_major, valid)
+                                 ws.data_ptr(), ws.numel(), path, pixel_major, valid, 0, 0.0, 0,
+                                 None if drop_mask is None else drop_mask.data_ptr())
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev).cuda_stream
             rc = _invoke('readout', lambda: lib.swem_readout_forward(C.byref(args), stream))

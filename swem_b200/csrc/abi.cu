@@ -288,6 +288,13 @@ int swem_readout_forward(const SwemReadArgs* a, void* stream) {
       return SWEM_ERR_UNSUPPORTED;
     }
   }
+  if (a->drop_mask != nullptr) {
+    SWEM_CHECK_ARG(a->mkm_kernels == 0, "drop_mask and mkm_kernels exclude each other (training / inference branches of the reference)");
+    if (a->path != SWEM_PATH_GENERIC) {
+      set_error("memory dropout (drop_mask) is implemented by the generic family only: ask for SWEM_PATH_GENERIC");
+      return SWEM_ERR_UNSUPPORTED;
+    }
+  }
   if (a->path != SWEM_PATH_GENERIC && !fused_readout_supported(d)) {
     set_error("the tcgen05 readout kernels do not cover Ck=%d Cv=%d L=%d banks=%d topl=%d (Ck in {64,128}, L in {64,128,256,512}, Cv=512, "
               "topl<=64); the generic fp32 family runs only on request (SWEM_PATH_GENERIC)", d.Ck, d.Cv, d.L, d.n_banks, d.topl);

@@ -301,30 +301,41 @@ __global__ void __launch_bounds__(256) mkm_topk_kernel(const float* __restrict__
 
 // One warp per (u, p): P[j] <- P[j] G[j] / (sum_j P[j] G[j] + 1e-8 / Z), G[j] = exp(-min_k d^2(p, center_jk) / (2 sigma^2 tau)), Z the row
 // sum of the exp-affinities -- i.e. E G / (sum E G + 1e-8) of the reference (:254-256) written on the normalised P = E / Z.
-__global__ void __launch_bounds__(256) mkm_apply_kernel(float* __restrict__ P, const float* __restrict__ zsum, const int* __restrict__ centers,
-                                                        int U, int HW, int W2, int K, int width, float inv_2s2tau) {
+// The same kernel applies the memory dropout of the training branch (:258-263): centers = NULL, colmask [U][Lt] of 0 / 1 (one mask
+// for both sides), eps = 1e-6; `out` may be P itself (in place) or a second buffer (the backward keeps the plain P); `srow`
+// (optional) receives the denominator sum_j P[j] w[j] + eps / Z of every row.
+__global__ void __launch_bounds__(256) mkm_apply_kernel(const float* __restrict__ P, const float* __restrict__ zsum, const int* __restrict__ centers,
+                                                        const float* __restrict__ colmask, int U, int HW, int W2, int K, int width,
+                                                        float inv_2s2tau, float eps, float* __restrict__ out, float* __restrict__ srow) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= U * HW) return;
-  const int u = warp / HW, p = warp % HW;
+  const int u = warp / HW, p = warp % HW, Lt = W2 / 2;
   const float px = (float)(p % width), py = (float)(p / width);
-  float* row = P + ((long long)u * HW + p) * W2;
+  const float* row = P + ((long long)u * HW + p) * W2;
+  float* orow = out + ((long long)u * HW + p) * W2;
   float sum = 0.f;
   for (int j = lane; j < W2; j += 32) {
-    const int* c = centers + ((long long)u * W2 + j) * kMkmMax;
-    float d2 = FLT_MAX;
-    for (int k = 0; k < K; ++k) {
-      const int q = c[k];
-      const float dx = px - (float)(q % width), dy = py - (float)(q / width);
-      d2 = fminf(d2, dx * dx + dy * dy);
+    float w = row[j];
+    if (centers != nullptr) {
+      const int* c = centers + ((long long)u * W2 + j) * kMkmMax;
+      float d2 = FLT_MAX;
+      for (int k = 0; k < K; ++k) {
+        const int q = c[k];
+        const float dx = px - (float)(q % width), dy = py - (float)(q / width);
+        d2 = fminf(d2, dx * dx + dy * dy);
+      }
+      w *= expf(-d2 * inv_2s2tau);
     }
-    const float w = row[j] * expf(-d2 * inv_2s2tau);
-    row[j] = w;
+    if (colmask != nullptr) w *= colmask[(long long)u * Lt + j % Lt];
+    orow[j] = w;
     sum += w;
   }
   sum = warp_sum(sum);
-  const float inv = 1.f / (sum + 1e-8f / zsum[(long long)u * HW + p]);
-  for (int j = lane; j < W2; j += 32) row[j] *= inv;
+  const float den = sum + eps / zsum[(long long)u * HW + p];
+  const float inv = 1.f / den;
+  for (int j = lane; j < W2; j += 32) orow[j] *= inv;
+  if (srow != nullptr && lane == 0) srow[(long long)u * HW + p] = den;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -611,7 +622,7 @@ int generic_readout_forward(const SwemReadArgs& a, cudaStream_t st) {
   float* inv_nq = ws.take<float>((size_t)d.B * d.HW);
   int* centers = ws.take<int>((size_t)U * W2 * kMkmMax);
   float* zsum = ws.take<float>((size_t)U * d.HW);
-  const bool mkm = a.mkm_kernels > 0;
+  const bool mkm = a.mkm_kernels > 0, drop = a.drop_mask != nullptr, weighted = mkm || drop;
 
   pixel_inv_norm_kernel<<<(d.B * d.HW + 255) / 256, 256, 0, st>>>(a.qk, inv_nq, d.B, d.Ck, d.HW);
   SWEM_LAUNCH_CHECK();
@@ -635,14 +646,15 @@ int generic_readout_forward(const SwemReadArgs& a, cudaStream_t st) {
   }
   {
     const long long threads = (long long)U * d.HW * 32;
-    readout_rows_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(P, inv_nq, U, d.N, d.HW, W2, 1.f / d.tau, mkm ? zsum : nullptr);
+    readout_rows_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(P, inv_nq, U, d.N, d.HW, W2, 1.f / d.tau, weighted ? zsum : nullptr);
     SWEM_LAUNCH_CHECK();
   }
-  if (mkm) {                                                  // S from the plain affinities (:269), then the kernel weights on the attention
+  if (weighted) {                                             // S from the plain affinities (:269), then the weights on the attention
     if (int rc = launch_perm_inv(P, U, d.HW, Lt, d.topl, a.out, a.out_channels, a.s_channel, a.out_pixel_major, st)) return rc;
     const long long threads = (long long)U * d.HW * 32;
-    mkm_apply_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(P, zsum, centers, U, d.HW, W2, a.mkm_kernels, a.mkm_width,
-                                                                         1.f / (2.f * a.mkm_sigma * a.mkm_sigma * d.tau));
+    mkm_apply_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(
+        P, zsum, mkm ? centers : nullptr, a.drop_mask, U, d.HW, W2, a.mkm_kernels, mkm ? a.mkm_width : 1,
+        mkm ? 1.f / (2.f * a.mkm_sigma * a.mkm_sigma * d.tau) : 0.f, mkm ? 1e-8f : 1e-6f, P, nullptr);
     SWEM_LAUNCH_CHECK();
   }
   // mem_out[u][dch][p] = sum_{s,k,l} nu_k[u,s][dch][l] P[u][p][s*Lt + k*L + l]
@@ -663,7 +675,7 @@ int generic_readout_forward(const SwemReadArgs& a, cudaStream_t st) {
                                a.out + (a.out_pixel_major ? (size_t)a.mem_channel : (size_t)a.mem_channel * d.HW), g, st))
         return rc;
     }
-  if (mkm) return SWEM_OK;
+  if (weighted) return SWEM_OK;
   return launch_perm_inv(P, U, d.HW, Lt, d.topl, a.out, a.out_channels, a.s_channel, a.out_pixel_major, st);
 }
 
@@ -794,6 +806,39 @@ __global__ void softmax_backward_rows_kernel(const float* __restrict__ P, float*
   for (int j = lane; j < W2; j += 32) grow[j] = prow[j] * (grow[j] - dot) * inv_tau;
 }
 
+// Memory dropout (forward: Q = E m / (sum E m + eps), E = exp((a - max a) / tau)): one warp per (u, p),
+//   g_a[k] = Q[k] (gQ[k] - sum_j Q[j] gQ[j]) / tau  -  [k = argmax a] (eps / D) (sum_j Q[j] gQ[j]) / tau,   D = sum E m + eps = Z srow
+// (the second term is what the reference's autograd sends through its max subtraction, which no longer cancels once eps is in
+// the denominator), in place on gQ.
+__global__ void drop_softmax_backward_rows_kernel(const float* __restrict__ Q, const float* __restrict__ P, float* __restrict__ gQ,
+                                                  const float* __restrict__ zsum, const float* __restrict__ srow, int U, int HW, int W2,
+                                                  float inv_tau, float eps) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= U * HW) return;
+  const float* qrow = Q + (long long)warp * W2;
+  const float* prow = P + (long long)warp * W2;
+  float* grow = gQ + (long long)warp * W2;
+  float dot = 0.f, best = -1.f;
+  int bj = 0x7fffffff;
+  for (int j = lane; j < W2; j += 32) {
+    dot = fmaf(qrow[j], grow[j], dot);
+    if (prow[j] > best) { best = prow[j]; bj = j; }
+  }
+  dot = warp_sum(dot);
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oj = __shfl_xor_sync(0xffffffffu, bj, o);
+    if (ov > best || (ov == best && oj < bj)) { best = ov; bj = oj; }
+  }
+  const float corr = eps / (zsum[warp] * srow[warp]) * dot;
+  for (int j = lane; j < W2; j += 32) grow[j] = (qrow[j] * (grow[j] - dot) - (j == bj ? corr : 0.f)) * inv_tau;
+}
+__global__ void add_inplace_kernel(float* __restrict__ dst, const float* __restrict__ src, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] += src[i];
+}
+
 // g_q[b][c][p] = g_qhat / d - q (q . g_qhat) / (n d^2)   (l2norm of modules.py:7-9 along the channel axis)
 __global__ void l2norm_backward_kernel(const float* __restrict__ q, const float* __restrict__ gqh, float* __restrict__ gq,
                                        int B, int C, int HW) {
@@ -822,6 +867,8 @@ size_t generic_readout_backward_workspace(const SwemDims& d) {
   bytes += align_up(G * d.Ck * d.L * 4, 256) * d.n_banks;     // khat per bank
   bytes += align_up((size_t)d.B * d.HW * 4, 256);             // inv ||q||
   bytes += align_up((size_t)d.B * d.Ck * d.HW * 4, 256);      // g_qhat
+  bytes += align_up(U * d.HW * 2 * Lt * 4, 256);              // memory dropout: the dropped attention Q / gradient of S
+  bytes += 2 * align_up(U * d.HW * 4, 256);                   //                 row sums Z, denominators
   return bytes + 256;
 }
 
@@ -836,6 +883,10 @@ int generic_readout_backward(const SwemReadBwdArgs& a, cudaStream_t st) {
   for (int k = 0; k < d.n_banks; ++k) khat[k] = ws.take<float>((size_t)G * d.Ck * d.L);
   float* inv_nq = ws.take<float>((size_t)d.B * d.HW);
   float* gqh = ws.take<float>((size_t)d.B * d.Ck * d.HW);
+  float* Qb = ws.take<float>((size_t)U * d.HW * W2);
+  float* zsum = ws.take<float>((size_t)U * d.HW);
+  float* srow = ws.take<float>((size_t)U * d.HW);
+  const bool drop = a.drop_mask != nullptr;
   const float* g_mem = a.grad_out + (size_t)a.mem_channel * d.HW;
   const long long so = (long long)a.out_channels * d.HW;       // per-unit stride of grad_out
 
@@ -856,9 +907,14 @@ int generic_readout_backward(const SwemReadBwdArgs& a, cudaStream_t st) {
   }
   {
     const long long threads = (long long)U * d.HW * 32;
-    readout_rows_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(P, inv_nq, U, d.N, d.HW, W2, 1.f / d.tau);
+    readout_rows_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(P, inv_nq, U, d.N, d.HW, W2, 1.f / d.tau, drop ? zsum : nullptr);
     SWEM_LAUNCH_CHECK();
+    if (drop) {                                                // the attention the forward used: Q = P m / (sum P m + 1e-6 / Z)
+      mkm_apply_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(P, zsum, nullptr, a.drop_mask, U, d.HW, W2, 0, 1, 0.f, 1e-6f, Qb, srow);
+      SWEM_LAUNCH_CHECK();
+    }
   }
+  const float* Pm = drop ? Qb : P;                             // what multiplied nu in the forward
   // ---- gP = nu^T g_mem ;  g_nu = g_mem P^T ----
   for (int s = 0; s < 2; ++s)
     for (int k = 0; k < d.n_banks; ++k) {
@@ -882,7 +938,7 @@ int generic_readout_backward(const SwemReadBwdArgs& a, cudaStream_t st) {
         g.bA[0] = (long long)d.N * so; g.bA[1] = so; g.bA[2] = 0;
         g.bB[0] = (long long)d.N * d.HW * W2; g.bB[1] = (long long)d.HW * W2; g.bB[2] = 0;
         g.bC[0] = (long long)d.N * 2 * d.Cv * d.L; g.bC[1] = 2LL * d.Cv * d.L; g.bC[2] = 0;
-        if (int rc = launch_gemm(g_mem, P + (size_t)s * Lt + (size_t)k * d.L, a.grad_nu[k] + (size_t)s * d.Cv * d.L, g, st)) return rc;
+        if (int rc = launch_gemm(g_mem, Pm + (size_t)s * Lt + (size_t)k * d.L, a.grad_nu[k] + (size_t)s * d.Cv * d.L, g, st)) return rc;
       }
     }
   if (a.grad_qk == nullptr) return SWEM_OK;
@@ -891,7 +947,15 @@ int generic_readout_backward(const SwemReadBwdArgs& a, cudaStream_t st) {
     const long long warps = (long long)U * d.HW;
     const int npl = (Lt + 31) / 32;
     const unsigned grid = (unsigned)((warps + 7) / 8);
-#define SWEM_PIB(NPL_) perm_inv_backward_kernel<NPL_><<<grid, 256, 0, st>>>(P, U, d.HW, Lt, d.topl, a.grad_out, a.out_channels, a.s_channel, gP)
+    float* gS = gP;                                            // where the gradient of S (with respect to the plain P) is added
+    if (drop) {
+      // the mem_out path goes through Q: finish it first (in place on gP), then the S path on its own buffer (Q is no longer needed)
+      drop_softmax_backward_rows_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(Qb, P, gP, zsum, srow, U, d.HW, W2, 1.f / d.tau, 1e-6f);
+      SWEM_LAUNCH_CHECK();
+      SWEM_CUDA(cudaMemsetAsync(Qb, 0, (size_t)U * d.HW * W2 * sizeof(float), st));
+      gS = Qb;
+    }
+#define SWEM_PIB(NPL_) perm_inv_backward_kernel<NPL_><<<grid, 256, 0, st>>>(P, U, d.HW, Lt, d.topl, a.grad_out, a.out_channels, a.s_channel, gS)
     if (npl <= 1) SWEM_PIB(1);
     else if (npl <= 2) SWEM_PIB(2);
     else if (npl <= 4) SWEM_PIB(4);
@@ -900,8 +964,13 @@ int generic_readout_backward(const SwemReadBwdArgs& a, cudaStream_t st) {
     else SWEM_PIB(32);
 #undef SWEM_PIB
     SWEM_LAUNCH_CHECK();
-    softmax_backward_rows_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(P, gP, U, d.HW, W2, 1.f / d.tau);
+    softmax_backward_rows_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(P, gS, U, d.HW, W2, 1.f / d.tau);
     SWEM_LAUNCH_CHECK();
+    if (drop) {
+      const long long n = (long long)U * d.HW * W2;
+      add_inplace_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(gP, gS, n);
+      SWEM_LAUNCH_CHECK();
+    }
   }
   // ---- g_qhat[b][c][p] = sum_{n,s,k,l} khat_k[b,n,s][c][l] g_a[b,n][p][s*Lt + k*L + l] (objects accumulate serially) ----
   bool first = true;

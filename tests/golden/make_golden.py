@@ -6,7 +6,7 @@ Run in the authoring container only (needs /root/reference):
 
 Writes ``core_small.pt``, ``core_prod.pt``, ``steps_small.pt``, ``model_tiny.pt`` next to this
 file (``--wide``: only ``core_wide.pt``, the reference's class default of 256 bases per side; ``--mkm``: only ``mkm_small.pt``,
-the kernelised-memory readout branch).  Each fixture holds the seeded inputs and the reference's outputs; tests replay the inputs
+the kernelised-memory readout branch; ``--drop``: only ``drop_small.pt``, the memory-dropout branch with the reference's gradients).  Each fixture holds the seeded inputs and the reference's outputs; tests replay the inputs
 through ``oracle/swem_oracle.py`` (CPU) and through the CUDA library (GPU).
 """
 from __future__ import annotations
@@ -133,12 +133,43 @@ def mkm_case(ref, name, B=1, N=2, Ck=64, Cv=64, Lt=32, H=12, W=20, tau=0.05, top
     print(name, os.path.getsize(os.path.join(HERE, name + '.pt')) // 1024, 'KiB')
 
 
+def drop_case(ref, name, B=2, N=2, Ck=64, Cv=64, Lt=32, H=10, W=12, tau=0.05, topl=16, p_drop=0.3, seed=21):
+    """The reference's memory dropout (get_affinity in training mode with p_drop > 0, modules.py:258-263; p_drop is hard-wired to
+    0.0 by the reference's constructor): raw inputs, the seed of the mask, the reference's (S, mem_out) and its autograd's gradients
+    of a fixed linear functional with respect to the raw query key and the memory values."""
+    core = ref.SWEMCore(n_bases=Lt // 2, valdim=Cv, n_iters=1, tau=tau, topl=topl)
+    core.train()
+    core.p_drop = p_drop
+    g = torch.Generator().manual_seed(seed)
+    q = torch.randn(B, Ck, H, W, generator=g, requires_grad=True)
+    mk = torch.randn(B, N, 2, Ck, Lt, generator=g)
+    mv = torch.randn(B, N, 2, Cv, Lt, generator=g, requires_grad=True)
+    w_mem = torch.randn(B, N, Cv, H, W, generator=g)
+    w_s = torch.randn(B * N, 2 * core.topl, H, W, generator=g)
+    mask_seed = 777
+    torch.manual_seed(mask_seed)
+    S, mem_out = core.get_affinity(ref.l2norm(q, dim=1), ref.l2norm(mk, dim=-2), mv)
+    loss = (mem_out * w_mem).sum() + (S * w_s).sum()
+    gq, gmv = torch.autograd.grad(loss, [q, mv])
+    torch.manual_seed(mask_seed)
+    mask = (torch.rand(B, N, 1, Lt, 1) > p_drop).float()
+    assert 0 < mask.mean() < 1
+    fx = dict(cfg=dict(B=B, N=N, Ck=Ck, Cv=Cv, Lt=Lt, H=H, W=W, tau=tau, topl=core.topl, p_drop=p_drop, mask_seed=mask_seed),
+              q=q.detach(), mk=mk, mv=mv.detach(), w_mem=w_mem, w_s=w_s, mask=mask, S=S.detach().clone(), mem_out=mem_out.detach().clone(),
+              grad_q=gq.clone(), grad_mv=gmv.clone())
+    torch.save(fx, os.path.join(HERE, name + '.pt'))
+    print(name, os.path.getsize(os.path.join(HERE, name + '.pt')) // 1024, 'KiB')
+
+
 def main():
     assert ref_shim.available(), 'reference checkout not found'
     torch.set_num_threads(1)                       # fixed reduction order inside ATen
     ref = ref_shim.load_modules()
     if '--mkm' in sys.argv:                        # added later: only this fixture is (re)generated
         mkm_case(ref, 'mkm_small')
+        return
+    if '--drop' in sys.argv:
+        drop_case(ref, 'drop_small')
         return
     if '--wide' in sys.argv:                       # added later: only this fixture is (re)generated
         core_case(ref, 'core_wide', B=1, n_seq=[1, 1], Ck=64, Cv=512, L=256, H=6, W=10, n_iters=3, tau=0.05,

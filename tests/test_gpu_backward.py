@@ -256,3 +256,44 @@ def test_training_step_loss_and_grads_match_the_reference_autograd():
     for name in names:
         assert name in grads_k and name in grads_o, (name, sorted(grads_k)[:8])
         check('grad ' + name, maxrel(grads_k[name], grads_o[name]), 2e-3)
+
+
+def test_memory_dropout_forward_and_backward_vs_reference_golden(golden):
+    """SWEMCore.matching_features in training mode with p_drop > 0 (the reference's memory dropout, modules.py:258-263; hard-wired
+    to 0.0 by the reference's constructor, kept for the API: SURVEY 8b) against the unmodified reference's outputs AND its
+    autograd's gradients (tests/golden/drop_small.pt): the mask is drawn like the reference draws it (CPU global generator), the
+    attention is renormalised with + 1e-6, S ignores the mask; gradients to the raw query key and to the memory values of both
+    banks through swem_readout_backward.  In eval mode the same core ignores p_drop."""
+    from swem_b200 import SWEMCore, _lib
+    fx = golden('drop_small')
+    c = fx['cfg']
+    B, N, Cv, Lt, H, W = c['B'], c['N'], c['Cv'], c['Lt'], c['H'], c['W']
+    L = Lt // 2
+    core = SWEMCore(n_bases=L, valdim=Cv, n_iters=1, tau=c['tau'], topl=c['topl']).to(DEV).train()
+    core.em_path = core.readout_path = _lib.PATH_GENERIC
+    core.p_drop = c['p_drop']
+    nus = []
+    for name, sl in (('first', slice(0, L)), ('update', slice(L, Lt))):
+        nu = fx['mv'][..., sl].contiguous().to(DEV).requires_grad_()
+        nus.append(nu)
+        core.memories[name].bases = dict(kappa=fx['mk'][..., sl].contiguous().to(DEV), nu=nu, zita=torch.ones(B, N, 2, 1, L, device=DEV))
+        core.memories[name].n_objs = N
+    q = fx['q'].to(DEV).requires_grad_()
+    qv = torch.zeros(B, Cv, H, W, device=DEV)
+    torch.manual_seed(c['mask_seed'])
+    feats, n = core.matching_features(q, qv)
+    mem_out, S = feats[:, :Cv].reshape(B, N, Cv, H, W), feats[:, 2 * Cv:]
+    check('mem_out', maxrel(mem_out, fx['mem_out']), 2e-4)
+    check('S', maxrel(S, fx['S']), 2e-4)
+    loss = (mem_out * fx['w_mem'].to(DEV)).sum() + (S * fx['w_s'].to(DEV)).sum()
+    loss.backward()
+    check('grad_q', maxrel(q.grad, fx['grad_q']), 2e-3)
+    check('grad_nu', maxrel(torch.cat([nu.grad for nu in nus], dim=-1), fx['grad_mv']), 2e-3)
+    # the dropped bases receive no gradient through the attention
+    dropped = (fx['mask'].reshape(B, N, 1, 1, Lt) == 0).expand(B, N, 2, Cv, Lt)
+    assert torch.cat([nu.grad for nu in nus], dim=-1).cpu()[dropped].abs().max() == 0
+    core.eval()
+    with torch.no_grad():
+        f_eval, _ = core.matching_features(q.detach(), qv)
+    want_S, want_m = O.readout(O.l2norm(fx['q'], dim=1), O.l2norm(fx['mk'], dim=-2), fx['mv'], c['tau'], c['topl'])
+    check('eval_mem', maxrel(f_eval[:, :Cv].reshape(B, N, Cv, H, W), want_m), 2e-4)
