@@ -946,7 +946,7 @@ def test_readout_reuses_bank_images_only_while_they_are_valid(L):
     import swem_b200.core as core_mod
     real_args = core_mod._lib.SwemReadArgs
     def spy(*a):
-        seen.append(a[-1])
+        seen.append(a[12])                                  # SwemReadArgs.bank_images_valid (positional, as _readout_launch passes it)
         return real_args(*a)
     with torch.no_grad():
         for call in range(2):
