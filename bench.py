@@ -42,7 +42,7 @@ H, W = 480, 864
 # dram__bytes_read.sum + dram__bytes_write.sum of one EM kernel launch at this workload, from the committed
 # `ncu --set full` capture under profiles/ (see PROFILE_SOURCE); algorithmic bytes: 23.0 MB
 NCU_TRAFFIC = {'fused-tcgen05': None}
-PROFILE_SOURCE = 'profiles/r2_em_kernel_ncu_full.txt'
+PROFILE_SOURCE = 'profiles/r2z_em_res_kernel_ncu_full.txt'
 _traffic_file = os.path.join(ROOT, 'profiles', 'r2_em_traffic.json')
 if os.path.isfile(_traffic_file):
     NCU_TRAFFIC['fused-tcgen05'] = json.load(open(_traffic_file)).get('dram_bytes_per_launch')
