@@ -88,3 +88,24 @@ def test_tf32_split_conv_identity():
     got = conv(xh.double(), wh.double(), padding=1) + conv(torch.cat([xh, xl], 1).double(), torch.cat([wl, wh], 1).double(), padding=1)
     assert _rel(got, want) < 2.0 ** -20
     assert _rel(conv(xh.double(), wh.double(), padding=1), want) > 2.0 ** -14      # a single TF32 conv is 1e-4 .. 1e-3 off
+
+
+def test_fusion_kernel_is_cuda_only_and_opt_in_by_accuracy_mode():
+    """FrameEngine uses swem_fusion_conv_glu by default exactly when fp32-accurate convolutions are asked for (split_tf32) and never
+    builds its weight images for a CPU model (no CUDA: the layer runs through torch as everywhere else on CPU)."""
+    torch.manual_seed(0)
+    model = SWEM(make_config(keydim=64, n_bases=16, n_iters=1, topl=8, backbone='resnet18')).eval()
+    assert FrameEngine(model).fusion_kernel is False
+    assert FrameEngine(model, split_tf32=True).fusion_kernel is True
+    assert FrameEngine(model, split_tf32=True, fusion_kernel=False).fusion_kernel is False
+    eng = FrameEngine(model, split_tf32=True)
+    eng.refresh()
+    assert eng.g_fused is None
+
+
+def test_get_affinity_refuses_cpu_tensors():
+    """SWEMCore.get_affinity (the reference's signature, incl. the kernelised-memory branch) has no CPU fallback."""
+    from swem_b200 import SWEMCore
+    core = SWEMCore(n_bases=8, valdim=16, n_iters=1, tau=0.05, topl=4).eval()
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        core.get_affinity(torch.randn(1, 16, 4, 5), torch.randn(1, 2, 2, 16, 16), torch.randn(1, 2, 2, 16, 16), n_kernel=3)
