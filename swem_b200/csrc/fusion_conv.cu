@@ -468,7 +468,11 @@ int swem_fusion_conv_glu(const float* feats, const void* wblob, float scale, con
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  SWEM_CUDA(cudaLaunchKernelEx(&cfg, fusion_conv_glu_kernel<true>, p));
+  if (cudaLaunchKernelEx(&cfg, fusion_conv_glu_kernel<true>, p) != cudaSuccess) {
+    // a device (partition) that cannot place 2-CTA clusters of this size: the one-CTA form computes the same sums in the same order
+    cudaGetLastError();
+    fusion_conv_glu_kernel<false><<<(unsigned)(BN * (g.Pimg / fc::kTM) * g.NT), fc::kThreads, fc::kSmemBytes, st>>>(p);
+  }
   SWEM_LAUNCH_CHECK();
   return SWEM_OK;
 }
