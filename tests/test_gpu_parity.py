@@ -1138,3 +1138,31 @@ def test_kernelised_memory_readout_vs_reference_golden(golden):
                              out.data_ptr(), Cv + 128, 0, Cv, ws.data_ptr(), ws.numel(), _lib.PATH_AUTO, 0, 0, 7, 7.0, W)
     assert lib.swem_readout_forward(C.byref(args), torch.cuda.current_stream().cuda_stream) == 2      # SWEM_ERR_UNSUPPORTED
     assert b'generic family only' in lib.swem_last_error()
+
+
+def test_fusion_conv_glu_is_bit_reproducible_over_many_calls():
+    """No atomics and a fixed accumulation order: 200 back-to-back calls (both launch forms: 2-CTA clusters and, with
+    SWEM_FUSION_PAIR=0, one CTA per tile) give bit-identical results, also with another kernel running on a second stream
+    (the cluster form needs its pairs co-scheduled; a protocol slip between the two CTAs would show up as a changed sum or a trap)."""
+    g = torch.Generator().manual_seed(11)
+    BN, H, W, Cin, Cout = 5, 30, 54, 640, 512
+    feats = torch.randn(BN, H, W, Cin, generator=g).to(DEV)
+    w = (torch.randn(2 * Cout, Cin, 3, 3, generator=g) * 0.01).to(DEV)
+    shared = torch.randn(1, H, W, 2 * Cout, generator=g).to(DEV)
+    bias = torch.zeros(2 * Cout, device=DEV)
+    first = _fusion_call(feats, w, shared, bias, BN)
+    side = torch.cuda.Stream()
+    junk = torch.randn(4096, 4096, device=DEV)
+    for i in range(200):
+        if i % 4 == 0:
+            with torch.cuda.stream(side):
+                junk = junk @ junk.t() * 1e-4
+        out = _fusion_call(feats, w, shared, bias, BN)
+        assert torch.equal(out, first), i
+    os.environ['SWEM_FUSION_PAIR'] = '0'
+    try:
+        single = _fusion_call(feats, w, shared, bias, BN)
+    finally:
+        del os.environ['SWEM_FUSION_PAIR']
+    assert torch.equal(single, first)
+    torch.cuda.synchronize()
