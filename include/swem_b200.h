@@ -274,6 +274,10 @@ int swem_tf32_split(const float* x, int64_t pixels, int32_t C, float* hi, float*
  * 2^-11 of the result, so 8 mantissa bits on their operands (and on their bf16 sum) still leave it at 2^-20, and their
  * convolution runs at twice the TF32 rate on half the bytes.                                                              */
 int swem_tf32_split_bf16(const float* x, int64_t pixels, int32_t C, float* hi, void* xl_bf16, void* stream);
+/* out[i] = float(x_bf16[i]) (+ add[i]) (+ add2[i]): widens the bf16 cross-term convolution's output (and folds the block's residual
+ * in) for the fp32 addend of the main-term convolution's fused epilogue, or accumulates it onto the main-term output in place
+ * (out == add); n a multiple of 8, flat (any memory format, equal strides), add / add2 may be NULL.                            */
+int swem_bf16_widen_add(const void* x_bf16, const float* add, const float* add2, int64_t n, float* out, void* stream);
 
 /* ---- misc ------------------------------------------------------------------------------------ */
 int         swem_abi_version(void);          /* == SWEM_B200_ABI_VERSION                          */

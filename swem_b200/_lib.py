@@ -18,7 +18,7 @@ EXPORTS = (
     'swem_em_workspace_bytes', 'swem_em_forward', 'swem_em_fused_supported',
     'swem_readout_workspace_bytes', 'swem_readout_forward', 'swem_readout_fused_supported',
     'swem_em_masks', 'swem_decode_tail', 'swem_set_profile_buffer',
-    'swem_em_backward_workspace_bytes', 'swem_em_backward', 'swem_readout_backward_workspace_bytes', 'swem_readout_backward', 'swem_upsample_add', 'swem_bias_add_act', 'swem_glu_gate', 'swem_maxpool3x3s2', 'swem_tf32_split', 'swem_tf32_split_bf16', 'swem_stem_input', 'swem_resblock_tail_pred',
+    'swem_em_backward_workspace_bytes', 'swem_em_backward', 'swem_readout_backward_workspace_bytes', 'swem_readout_backward', 'swem_upsample_add', 'swem_bias_add_act', 'swem_glu_gate', 'swem_maxpool3x3s2', 'swem_tf32_split', 'swem_tf32_split_bf16', 'swem_bf16_widen_add', 'swem_stem_input', 'swem_resblock_tail_pred',
     'swem_cbam_channel_gate', 'swem_cbam_spatial_pool', 'swem_cbam_apply',
     'swem_fusion_weight_bytes', 'swem_fusion_prepare_weights', 'swem_fusion_workspace_bytes', 'swem_fusion_conv_glu',
 )
@@ -108,6 +108,7 @@ def load() -> C.CDLL:
     lib.swem_maxpool3x3s2.argtypes = [C.c_void_p] + [C.c_int32] * 4 + [C.c_void_p] * 2
     lib.swem_tf32_split.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.swem_tf32_split_bf16.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.swem_bf16_widen_add.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
     lib.swem_stem_input.argtypes = [C.c_void_p] * 4 + [C.c_int32] * 6 + [C.c_void_p] * 2
     lib.swem_resblock_tail_pred.argtypes = [C.c_void_p] * 4 + [C.c_float] + [C.c_int32] * 4 + [C.c_void_p] * 2
     lib.swem_cbam_channel_gate.argtypes = [C.c_void_p] * 5 + [C.c_int32, C.c_int64, C.c_int32, C.c_int32] + [C.c_void_p] * 3

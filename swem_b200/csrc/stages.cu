@@ -161,6 +161,35 @@ __global__ void __launch_bounds__(256) tf32_split_bf16_kernel(const float4* __re
   o[C4] = pack(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w);
 }
 
+// out = float(x_bf16) (+ add) (+ add2): the bf16 cross-term convolution's output widened for the fused epilogue of the TF32 main-term
+// convolution (which takes an fp32 addend) with the residual of the block folded in, or accumulated in place onto the main-term
+// convolution's output (convolutions without a ReLU have no fused cuDNN epilogue) -- one vectorised pass (8 elements per thread)
+// instead of ATen's converting copy followed by one or two in-place adds.
+__global__ void __launch_bounds__(256) bf16_widen_add_kernel(const uint4* __restrict__ x, const float4* add, const float4* __restrict__ add2,
+                                                             long long total8, float4* out) {   // (`out` may be `add`: in place)
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total8) return;
+  const uint4 v = __ldg(x + idx);
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+  float f[8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {                      // bf16 -> fp32: the 16 bits are the upper half of the float
+    f[2 * i] = __uint_as_float(w[i] << 16);
+    f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+  }
+  float4 a = make_float4(f[0], f[1], f[2], f[3]), b = make_float4(f[4], f[5], f[6], f[7]);
+  if (add != nullptr) {
+    a = f4add(a, add[2 * idx]);
+    b = f4add(b, add[2 * idx + 1]);
+  }
+  if (add2 != nullptr) {
+    a = f4add(a, __ldg(add2 + 2 * idx));
+    b = f4add(b, __ldg(add2 + 2 * idx + 1));
+  }
+  out[2 * idx] = a;
+  out[2 * idx + 1] = b;
+}
+
 __global__ void __launch_bounds__(256) bias_add_act_kernel(const float4* __restrict__ a, const float4* __restrict__ b,
                                                            const float4* __restrict__ c, const float4* __restrict__ bias,
                                                            long long total4, long long per_image4, int n_share, int C4, int relu,
@@ -629,6 +658,22 @@ int swem_tf32_split_bf16(const float* x, int64_t pixels, int32_t C, float* hi, v
   const long long total4 = pixels * (C / 4);
   tf32_split_bf16_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const float4*>(x), total4, C / 4, reinterpret_cast<float4*>(hi), reinterpret_cast<uint2*>(xl_bf16));
+  SWEM_LAUNCH_CHECK();
+  return SWEM_OK;
+}
+
+int swem_bf16_widen_add(const void* x_bf16, const float* add, const float* add2, int64_t n, float* out, void* stream) {
+  reset_launch_count();
+  SWEM_CHECK_ARG(x_bf16 && out, "NULL pointer");
+  SWEM_CHECK_ARG(n > 0 && n % 8 == 0, "n=%lld must be a positive multiple of 8", (long long)n);
+  SWEM_CHECK_ARG((reinterpret_cast<uintptr_t>(x_bf16) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
+                     (reinterpret_cast<uintptr_t>(add) & 15) == 0 && (reinterpret_cast<uintptr_t>(add2) & 15) == 0,
+                 "pointers must be 16-byte aligned");
+  SWEM_CHECK_ARG(add2 == nullptr || add2 != out, "only `add` may alias `out`");
+  const long long total8 = n / 8;
+  bf16_widen_add_kernel<<<(unsigned)((total8 + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const uint4*>(x_bf16), reinterpret_cast<const float4*>(add), reinterpret_cast<const float4*>(add2), total8,
+      reinterpret_cast<float4*>(out));
   SWEM_LAUNCH_CHECK();
   return SWEM_OK;
 }

@@ -303,11 +303,33 @@ class FrameEngine:
         torch.backends.cudnn.allow_tf32 = True
         try:
             cross = F.conv2d(hl, wc, None, stride=s, padding=pad)
+            fused_relu = relu and self.fused_conv and x.is_cuda
+            glue = (self.cross_bf16 and self._glue_ok(add) and cross.is_cuda and cross.numel() % 8 == 0
+                    and (add is None or (add.shape == cross.shape and add.stride() == cross.stride()))
+                    and (cross.is_contiguous() or cross.is_contiguous(memory_format=torch.channels_last)))
+            if glue:
+                # swem_bf16_widen_add: one vectorised pass instead of a converting copy and one or two in-place adds
+                lib, st = _lib.load(), torch.cuda.current_stream(cross.device).cuda_stream
+                ptr = lambda t: None if t is None else t.data_ptr()
+                if fused_relu:           # widened (+ residual) addend for the fused epilogue of the main-term convolution
+                    wide = torch.empty_like(cross, dtype=torch.float32)
+                    with torch.cuda.device(cross.device):
+                        _lib.check(lib.swem_bf16_widen_add(cross.data_ptr(), ptr(add), None, cross.numel(), wide.data_ptr(), st), 'swem_bf16_widen_add')
+                    return torch.cudnn_convolution_add_relu(hi, wh, wide, 1.0, zero if b is None else b, (s, s), (pad, pad), (1, 1), 1)
+                y = F.conv2d(hi, wh, b, stride=s, padding=pad)
+                if y.stride() == cross.stride():     # no fused epilogue without a ReLU: accumulate onto the main term in place
+                    with torch.cuda.device(cross.device):
+                        _lib.check(lib.swem_bf16_widen_add(cross.data_ptr(), y.data_ptr(), ptr(add), cross.numel(), y.data_ptr(), st), 'swem_bf16_widen_add')
+                    return F.relu_(y) if relu else y
+                y.add_(cross.float())
+                if add is not None:
+                    y.add_(add)
+                return F.relu_(y) if relu else y
             if self.cross_bf16:
                 cross = cross.float()
             if add is not None:
                 cross.add_(add)
-            if relu and self.fused_conv and x.is_cuda:
+            if fused_relu:
                 return torch.cudnn_convolution_add_relu(hi, wh, cross, 1.0, zero if b is None else b, (s, s), (pad, pad), (1, 1), 1)
             y = F.conv2d(hi, wh, b, stride=s, padding=pad).add_(cross)
             return F.relu_(y) if relu else y
